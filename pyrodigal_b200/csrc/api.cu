@@ -1,0 +1,1046 @@
+// api.cu -- context, host orchestration and the C ABI of libpyrodigal_b200.so (see include/pyrodigal_b200.h).
+//
+// Host-side control flow of one batch mirrors GeneFinder._find_genes_meta / _find_genes_single
+// (src/pyrodigal/lib.pyx:5281-5396) but evaluates every (contig, model) chain of the batch in the same
+// kernel launches instead of looping over bins per contig:
+//   H2D -> encode -> [sync: gc] -> plan chains -> mark -> scan -> [sync: node counts] -> fill -> prep ->
+//   coding score -> start score -> overlapping starts -> DP -> winner/traceback/genes -> final re-score
+//   (meta) -> pack -> [sync: gene counts] -> D2H.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace pgpu;
+
+// ------------------------------------------------------------------------------------------------
+// raw training struct (vendor/Prodigal/training.h:29-51) -- layout only, values come from the caller
+// ------------------------------------------------------------------------------------------------
+struct RawTraining {
+    double gc;
+    int32_t trans_table, pad0;
+    double st_wt;
+    double bias[3];
+    double type_wt[3];
+    int32_t uses_sd, pad1;
+    double rbs_wt[28];
+    double ups_comp[32][4];
+    double mot_wt[4][4][4096];
+    double no_mot;
+    double gene_dc[4096];
+};
+static_assert(sizeof(RawTraining) == PGPU_TRAINING_SIZE, "training struct layout");
+
+struct pgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int n_models = 0;
+    std::vector<RawTraining> h_raw;
+    std::vector<DevModel> h_models;
+    RawTraining *d_raw = nullptr;
+    DevModel *d_models = nullptr;
+    size_t ws_limit = 0;
+    cudaEvent_t ev[16];
+    int64_t launches = 0;
+};
+
+static thread_local std::string g_create_err;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e);                         \
+            return PGPU_ECUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+
+static int fail(pgpu_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stream-ordered device buffers
+// ------------------------------------------------------------------------------------------------
+struct DevPool {
+    pgpu_ctx *ctx;
+    std::vector<void *> ptrs;
+    size_t bytes = 0;
+    bool failed = false;
+    explicit DevPool(pgpu_ctx *c) : ctx(c) {}
+    template <typename T>
+    T *alloc(size_t n, bool zero = false) {
+        size_t sz = std::max<size_t>(n, 1) * sizeof(T);
+        sz = (sz + 255) & ~size_t(255);
+        void *p = nullptr;
+        cudaError_t e = cudaMallocAsync(&p, sz, ctx->stream);
+        if (e != cudaSuccess) {
+            failed = true;
+            ctx->err = std::string("cudaMallocAsync(") + std::to_string(sz) + "): " + cudaGetErrorString(e);
+            return nullptr;
+        }
+        ptrs.push_back(p);
+        bytes += sz;
+        if (zero) cudaMemsetAsync(p, 0, sz, ctx->stream);
+        return (T *)p;
+    }
+    template <typename T>
+    T *upload(const std::vector<T> &v) {
+        T *p = alloc<T>(v.size());
+        if (p && !v.empty()) cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+        return p;
+    }
+    void release() {
+        for (void *p : ptrs) cudaFreeAsync(p, ctx->stream);
+        ptrs.clear();
+    }
+    ~DevPool() { release(); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// model preparation (host): everything that needs libm or is model-only
+// ------------------------------------------------------------------------------------------------
+
+// stop / start codon sets per translation table as bit masks over the 6-bit codon code
+// (code = b0 | b1<<2 | b2<<4, A0 G1 C2 T3).  Rules: src/pyrodigal/_sequence.h:45-73, 117-157.
+static void codon_masks(int tt, uint64_t *stopmask, uint64_t *startmask) {
+    auto in = [&](std::initializer_list<int> l) { for (int v : l) if (v == tt) return true; return false; };
+    const bool taa = in({1, 2, 3, 4, 5, 9, 10, 11, 12, 13, 15, 16, 21, 22, 23, 24, 25, 26, 32});
+    const bool tag = in({1, 2, 3, 4, 5, 9, 10, 11, 12, 13, 14, 21, 23, 24, 25, 26, 33});
+    const bool tga = in({1, 6, 11, 12, 15, 16, 22, 23, 26, 29, 30, 32});
+    uint64_t sm = 0, am = 0;
+    enum { A = 0, G = 1, C = 2, T = 3 };
+    for (int c = 0; c < 64; c++) {
+        const int x0 = c & 3, x1 = (c >> 2) & 3, x2 = (c >> 4) & 3;
+        bool stop = false;
+        if (x0 == T && x1 == A && x2 == G) stop = tag;
+        else if (x0 == T && x1 == G && x2 == A) stop = tga;
+        else if (x0 == T && x1 == A && x2 == A) stop = taa;
+        else if (tt == 2) stop = x0 == A && x1 == G && (x2 == A || x2 == G);
+        else if (tt == 22) stop = x0 == T && x1 == C && x2 == A;
+        else if (tt == 23) stop = x0 == T && x1 == T && x2 == A;
+        bool start = false;
+        if (x1 == T && x2 == G) {
+            if (x0 == A) start = true;
+            else if (in({6, 10, 14, 15, 16, 2})) start = false;
+            else if (x0 == G) start = !in({1, 3, 12, 2});
+            else if (x0 == T) start = !(tt < 4 || tt == 9 || (tt >= 21 && tt < 25));
+        }
+        if (stop) sm |= 1ull << c;
+        if (start) am |= 1ull << c;
+    }
+    *stopmask = sm;
+    *startmask = am;
+}
+
+// Model-independent part of the Shine-Dalgarno search: the set of motif bins the reference's two
+// enumerations (lib.pyx:827-888 exact, 928-977 one mismatch) can report for a window at offset `off`
+// (pos = start-20+off) whose in-range A/G matches are the bits of `gp`.
+static uint32_t g_sd_masks[2][15][64];
+static bool g_sd_ready = false;
+static void build_sd_masks() {
+    if (g_sd_ready) return;
+    static const int8_t tab[15][4] = {{0}, {0}, {0}, {0}, {0}, {0}, {13, 6, 1, 2}, {0}, {15, 12, 11, 3},
+                                      {16, 12, 11, 3}, {0}, {22, 21, 20, 10}, {24, 23, 20, 10}, {0}, {27, 26, 25, 10}};
+    for (int off = 0; off < 15; off++) {
+        const int d = 20 - off;  // start - pos
+        const int limit = std::min(6, d - 4);
+        for (int gp = 0; gp < 64; gp++) {
+            int match[6];
+            // exact
+            for (int i = 0; i < 6; i++) match[i] = (i < limit && ((gp >> i) & 1)) ? (i % 3 == 0 ? 2 : 3) : -10;
+            uint32_t mask = 1;
+            for (int len = limit; len > 2; len--)
+                for (int j = 0; j <= limit - len; j++) {
+                    int ctr = -2;
+                    for (int k = j; k < j + len; k++) ctr += match[k];
+                    if (ctr < 6) continue;
+                    const int rdis = d - j - len;
+                    int flag;
+                    if (rdis < 5) flag = len < 5 ? 2 : 1;
+                    else if (rdis < 11) flag = 0;
+                    else if (rdis < 13) flag = len < 5 ? 1 : 2;
+                    else if (rdis < 16) flag = 3;
+                    else continue;
+                    const bool known = ctr == 6 || ctr == 8 || ctr == 9 || ctr == 11 || ctr == 12 || ctr == 14;
+                    mask |= 1u << (known ? tab[ctr][flag] : 0);
+                }
+            g_sd_masks[0][off][gp] = mask;
+            // one mismatch
+            for (int i = 0; i < 6; i++) {
+                if (i < limit) match[i] = ((gp >> i) & 1) ? (i % 3 == 0 ? 2 : 3) : (i % 3 == 0 ? -3 : -2);
+                else match[i] = -10;
+            }
+            mask = 1;
+            int cur_val = 0;  // sticky across iterations, as in the reference
+            for (int len = limit; len > 4; len--)
+                for (int j = 0; j <= limit - len; j++) {
+                    int ctr = -2, mism = 0;
+                    for (int k = j; k < j + len; k++) {
+                        ctr += match[k];
+                        if (match[k] < 0) { mism++; if (k <= j + 1 || k >= j + len - 2) ctr -= 10; }
+                    }
+                    if (mism != 1 || ctr < 6) continue;
+                    const int rdis = d - j - len;
+                    int flag;
+                    if (rdis < 5) flag = 1;
+                    else if (rdis < 11) flag = 0;
+                    else if (rdis < 13) flag = 2;
+                    else if (rdis < 16) flag = 3;
+                    else continue;
+                    static const int8_t v6[4] = {9, 5, 4, 2}, v7[4] = {14, 8, 7, 2}, v9[4] = {19, 18, 17, 3};
+                    if (ctr == 6) cur_val = v6[flag];
+                    else if (ctr == 7) cur_val = v7[flag];
+                    else if (ctr == 9) cur_val = v9[flag];
+                    mask |= 1u << cur_val;
+                }
+            g_sd_masks[1][off][gp] = mask;
+        }
+    }
+    g_sd_ready = true;
+}
+
+static void prepare_model(const RawTraining &r, DevModel &m, const RawTraining *d_raw_k) {
+    memset(&m, 0, sizeof(m));
+    m.st_wt = r.st_wt; m.gc = r.gc; m.no_mot = r.no_mot;
+    for (int i = 0; i < 3; i++) { m.bias[i] = r.bias[i]; m.type_wt[i] = r.type_wt[i]; }
+    for (int i = 0; i < 28; i++) m.rbs_wt[i] = r.rbs_wt[i];
+    for (int k = 0; k < 32; k++)
+        for (int b = 0; b < 4; b++) m.uc[k][b] = 0.4 * r.st_wt * r.ups_comp[k][b];
+    // length factor table (lib.pyx:2137-2147, 2209-2210): host libm, same as the reference process
+    double no_stop;
+    const double a = 1 - r.gc;
+    if (r.trans_table != 11) { no_stop = (a * a * r.gc) / 8.0; no_stop += (a * a * a) / 8.0; }
+    else { no_stop = (a * a * r.gc) / 4.0; no_stop += (a * a * a) / 8.0; }
+    no_stop = 1 - no_stop;
+    const double lfac_max = log((1 - pow(no_stop, 1000.0)) / pow(no_stop, 1000.0));
+    const double lfac_min = log((1 - pow(no_stop, 80)) / pow(no_stop, 80));
+    for (int g = 0; g <= 1000; g++) {
+        const double tmp = pow(no_stop, (double)g);
+        m.lfac[g] = log((1 - tmp) / tmp) - lfac_min;
+    }
+    m.lfac_span = lfac_max - lfac_min;
+    for (int d = 0; d <= 60; d++) m.igt[d] = (2.0 - ((double)d / kOperDist)) * 0.15 * r.st_wt;
+    m.ig_neg = -0.15 * r.st_wt;
+    m.trans_table = r.trans_table;
+    m.uses_sd = r.uses_sd;
+    codon_masks(r.trans_table, &m.stopmask, &m.startmask);
+    build_sd_masks();
+    for (int x = 0; x < 2; x++)
+        for (int off = 0; off < 15; off++)
+            for (int gp = 0; gp < 64; gp++) {
+                // the reference keeps the candidate with the largest (rbs_wt, bin): lib.pyx:884-888
+                int best = 0;
+                const uint32_t mask = g_sd_masks[x][off][gp];
+                for (int v = 1; v < 28; v++) {
+                    if (!((mask >> v) & 1)) continue;
+                    if (r.rbs_wt[v] < r.rbs_wt[best]) continue;
+                    if (r.rbs_wt[v] == r.rbs_wt[best] && v < best) continue;
+                    best = v;
+                }
+                m.sd_best[x][off][gp] = (uint8_t)best;
+            }
+    m.gene_dc = d_raw_k->gene_dc;
+    m.mot_wt = &d_raw_k->mot_wt[0][0][0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------------
+struct pgpu_result {
+    int n_contigs = 0;
+    std::vector<pgpu_contig_summary> summary;
+    std::vector<int64_t> gene_off;   // [n+1]
+    std::vector<pgpu_gene> genes;
+    std::vector<pgpu_node> gene_nodes;  // 2 per gene
+    bool have_nodes = false;
+    std::vector<int64_t> node_off;   // [n+1]
+    std::vector<pgpu_node> nodes;
+    pgpu_stats stats;
+};
+
+struct pgpu_batch {
+    pgpu_ctx *ctx = nullptr;
+    int n_contigs = 0;
+    std::vector<int64_t> offsets;  // [n+1]
+    uint8_t *d_ascii = nullptr;    // device copy of the whole concatenated input
+    int64_t total = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// one pipeline run over contigs [lo, hi)
+// ------------------------------------------------------------------------------------------------
+struct RunPlan {
+    // what to run
+    int stage = 3;            // 1: extraction only, 2: + scoring/overlap, 3: everything
+    int forced_tt = -1;       // stage 1/2 operator entry points
+    int forced_model = -1;
+    int forced_first_pass = 1;
+    int forced_is_meta = 0;
+};
+
+struct OperatorOut {  // operator-level outputs (single contig)
+    std::vector<int32_t> ndx, stop_val;
+    std::vector<uint8_t> cls;
+    std::vector<pgpu_node> nodes;
+};
+
+static double window_low(double gc) { return fmin(0.65, 0.88495 * gc - 0.0102337); }
+static double window_high(double gc) { return fmax(0.35, 0.86596 * gc + 0.1131991); }
+
+static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, const int64_t *offsets, int lo, int hi,
+                     const pgpu_opts &opts, const RunPlan &plan, pgpu_result *res, OperatorOut *op) {
+    cudaStream_t st = ctx->stream;
+    const int n = hi - lo;
+    if (n <= 0) return PGPU_OK;
+    const bool meta = opts.meta != 0 && plan.forced_model < 0 && plan.forced_tt < 0;
+    if (plan.stage >= 2 && plan.forced_model < 0 && ctx->n_models == 0) return fail(ctx, PGPU_ESTATE, "no models loaded");
+    DevPool pool(ctx);
+    DevBatch B;
+    memset(&B, 0, sizeof(B));
+    RunOpts ro = {opts.closed, opts.min_gene, opts.min_edge_gene, opts.max_overlap};
+    pgpu_stats &S = res->stats;
+    int evi = 0;
+    auto mark = [&]() { cudaEventRecord(ctx->ev[evi], st); return evi++; };
+
+    // ---- stage A: sequences ----------------------------------------------------------------------
+    std::vector<ContigInfo> contigs(n);
+    std::vector<int2> tiles;
+    int64_t dtot = 0;
+    const int64_t abase = offsets[lo];
+    for (int c = 0; c < n; c++) {
+        const int64_t len = offsets[lo + c + 1] - offsets[lo + c];
+        if (len < 0 || len > 0x7ffffff0) return fail(ctx, PGPU_EINVAL, "contig length out of range");
+        contigs[c].doff = dtot;
+        contigs[c].aoff = offsets[lo + c] - abase;
+        contigs[c].slen = (int)len;
+        contigs[c].mask_off = 0; contigs[c].n_masks = 0; contigs[c].pad = 0;
+        dtot += ((len + 16 + 127) / 128) * 128;
+        for (int64_t s = 0; s < len; s += 4096) tiles.push_back(make_int2(c, (int)s));
+    }
+    const int64_t atot = offsets[hi] - abase;
+    int e_start = mark();
+    uint8_t *d_ascii_local = nullptr;
+    if (d_seq) {
+        B.ascii = d_seq + abase;
+    } else {
+        d_ascii_local = pool.alloc<uint8_t>(atot + 16);
+        if (pool.failed) return PGPU_ENOMEM;
+        if (atot) CK(cudaMemcpyAsync(d_ascii_local, h_seq + abase, atot, cudaMemcpyHostToDevice, st));
+        B.ascii = d_ascii_local;
+        S.h2d_bytes += atot;
+    }
+    int e_h2d = mark();
+    B.digits = pool.alloc<uint8_t>(dtot + 256, true);
+    B.cod = pool.alloc<uint8_t>(dtot + 256, true);
+    B.contigs = pool.upload(contigs);
+    B.gc_count = pool.alloc<int32_t>(n, true);
+    B.unknown = pool.alloc<int32_t>(n, true);
+    int2 *d_tiles = pool.upload(tiles);
+    if (pool.failed) return PGPU_ENOMEM;
+    launch_encode(B, d_tiles, (int)tiles.size(), st);
+    ctx->launches++;
+    std::vector<int4> h_masks;
+    if (opts.mask) {
+        const int cap = (int)std::min<int64_t>(std::max<int64_t>(1024, atot / std::max(1, opts.min_mask) + n + 16), 1 << 28);
+        int4 *d_mk = pool.alloc<int4>(cap);
+        int *d_cnt = pool.alloc<int>(1, true);
+        if (pool.failed) return PGPU_ENOMEM;
+        launch_find_masks(B, d_tiles, (int)tiles.size(), opts.min_mask, d_mk, cap, d_cnt, st);
+        ctx->launches++;
+        int cnt = 0;
+        CK(cudaMemcpyAsync(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        cnt = std::min(cnt, cap);
+        h_masks.resize(cnt);
+        if (cnt) CK(cudaMemcpyAsync(h_masks.data(), d_mk, cnt * sizeof(int4), cudaMemcpyDeviceToHost, st));
+    }
+    std::vector<int32_t> h_gc(n), h_unk(n);
+    CK(cudaMemcpyAsync(h_gc.data(), B.gc_count, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_unk.data(), B.unknown, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    int e_enc = mark();
+    CK(cudaStreamSynchronize(st));
+    S.d2h_bytes += 8 * (int64_t)n;
+
+    // masks: sort by (contig, begin) and build the per-contig table
+    std::vector<int32_t> mask_tab;
+    if (!h_masks.empty()) {
+        std::sort(h_masks.begin(), h_masks.end(), [](const int4 &a, const int4 &b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+        for (size_t k = 0; k < h_masks.size(); k++) {
+            ContigInfo &ci = contigs[h_masks[k].x];
+            if (ci.n_masks == 0) ci.mask_off = (int)k;
+            ci.n_masks++;
+            mask_tab.push_back(h_masks[k].y);
+            mask_tab.push_back(h_masks[k].z);
+        }
+    }
+    B.masks = pool.upload(mask_tab);
+
+    // ---- stage B: plan extractions and chains ------------------------------------------------------
+    std::vector<ExtractInfo> exts;
+    std::vector<ChainInfo> chains;
+    std::vector<int32_t> contig_chain_begin(n + 1, 0);
+    std::vector<int32_t> contig_ext_begin(n + 1, 0);
+    int64_t nwords = 0;
+    for (int c = 0; c < n; c++) {
+        contig_chain_begin[c] = (int)chains.size();
+        contig_ext_begin[c] = (int)exts.size();
+        const ContigInfo &ci = contigs[c];
+        auto get_ext = [&](int tt) {
+            for (int e = contig_ext_begin[c]; e < (int)exts.size(); e++)
+                if (exts[e].tt == tt) return e;
+            ExtractInfo X;
+            memset(&X, 0, sizeof(X));
+            X.contig = c; X.tt = tt; X.doff = ci.doff; X.slen = ci.slen;
+            X.slot = (int)exts.size() - contig_ext_begin[c];
+            X.woff = nwords; X.nwords = ci.slen / 32 + 1;
+            X.mask_off = ci.mask_off; X.n_masks = ci.n_masks;
+            codon_masks(tt, &X.stopmask, &X.startmask);
+            nwords += X.nwords;
+            exts.push_back(X);
+            return (int)exts.size() - 1;
+        };
+        auto add_chain = [&](int model, int tt, int first_pass, int is_meta) {
+            ChainInfo K;
+            memset(&K, 0, sizeof(K));
+            K.ext = get_ext(tt); K.model = model; K.contig = c; K.first_pass = first_pass;
+            K.doff = ci.doff; K.slen = ci.slen; K.is_meta = is_meta;
+            chains.push_back(K);
+        };
+        if (plan.forced_tt >= 0) {
+            get_ext(plan.forced_tt);
+        } else if (plan.forced_model >= 0) {
+            add_chain(plan.forced_model, ctx->h_models[plan.forced_model].trans_table, plan.forced_first_pass, plan.forced_is_meta);
+        } else if (!meta) {
+            add_chain(opts.single_model, ctx->h_models[opts.single_model].trans_table, 1, 0);
+        } else {
+            // lib.pyx:5335-5357: bins inside the GC window, in order; re-extraction whenever the table changes
+            const double gc = ci.slen > 0 ? (double)h_gc[c] / (double)ci.slen : 0.0;
+            const double low = window_low(gc), high = window_high(gc);
+            int tt = -1;
+            for (int m = 0; m < ctx->n_models; m++) {
+                const DevModel &M = ctx->h_models[m];
+                if (M.gc < low || M.gc > high) continue;
+                const int first = M.trans_table != tt;
+                tt = M.trans_table;
+                add_chain(m, tt, first, 1);
+            }
+        }
+    }
+    contig_chain_begin[n] = (int)chains.size();
+    contig_ext_begin[n] = (int)exts.size();
+    const int n_ext = (int)exts.size(), n_chains = (int)chains.size();
+
+    // ---- extraction pass 1: mark + scan ------------------------------------------------------------
+    B.bits_fwd = pool.alloc<uint32_t>(nwords + 8, true);
+    B.bits_rev = pool.alloc<uint32_t>(nwords + 8, true);
+    B.wordbase = pool.alloc<int32_t>(nwords + 8);
+    B.exts = pool.upload(exts);
+    int *d_block_sums = pool.alloc<int>(scan_num_blocks(nwords) + 1);
+    int *d_total = pool.alloc<int>(1, true);
+    if (pool.failed) return PGPU_ENOMEM;
+    launch_extract_mark(B, n_ext, ro, st);
+    launch_word_scan(B, nwords, d_block_sums, d_total, st);
+    ctx->launches += 4;
+    // node offsets of every extraction = wordbase[woff]
+    std::vector<int32_t> h_base(n_ext + 1, 0);
+    {
+        // gather with strided copies would be n_ext memcpys; copy the few words we need via a 2D copy is not
+        // possible (irregular), so read wordbase[woff_e] with one small kernel-free trick: cudaMemcpy2D is
+        // regular only.  Use a pinned gather list instead: n_ext is small compared to the data.
+        std::vector<int64_t> idx(n_ext + 1);
+        for (int e = 0; e < n_ext; e++) idx[e] = exts[e].woff;
+        idx[n_ext] = nwords;
+        // device-side gather
+        int64_t *d_idx = pool.upload(idx);
+        int32_t *d_out = pool.alloc<int32_t>(n_ext + 1);
+        if (pool.failed) return PGPU_ENOMEM;
+        extern void launch_gather_i32(const int32_t *src, const int64_t *idx, int n, int32_t *dst, cudaStream_t st);
+        launch_gather_i32(B.wordbase, d_idx, n_ext + 1, d_out, st);
+        ctx->launches++;
+        CK(cudaMemcpyAsync(h_base.data(), d_out, (n_ext + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    int e_mark = mark();
+    CK(cudaStreamSynchronize(st));
+    S.d2h_bytes += 4 * (int64_t)(n_ext + 1);
+    const int total_nodes = h_base[n_ext];
+    if (total_nodes < 0) return fail(ctx, PGPU_EINVAL, "too many nodes in one sub-batch");
+    for (int e = 0; e < n_ext; e++) { exts[e].node_off = h_base[e]; exts[e].nn = h_base[e + 1] - h_base[e]; }
+    int64_t total_cn = 0;
+    for (auto &K : chains) { K.node_off = exts[K.ext].node_off; K.nn = exts[K.ext].nn; K.coff = total_cn; total_cn += K.nn; }
+    CK(cudaMemcpyAsync(B.exts, exts.data(), n_ext * sizeof(ExtractInfo), cudaMemcpyHostToDevice, st));
+
+    // ---- extraction pass 2: fill, then per-extraction preparation ----------------------------------
+    B.ndx = pool.alloc<int32_t>(total_nodes);
+    B.stop_val = pool.alloc<int32_t>(total_nodes);
+    B.cls = pool.alloc<uint8_t>(total_nodes + 16);
+    B.gc_cont = pool.alloc<float>(total_nodes, true);
+    B.sdbits = pool.alloc<uint32_t>(total_nodes);
+    B.win_min = pool.alloc<int32_t>(total_nodes);
+    B.crank = pool.alloc<int32_t>(4 * (size_t)total_nodes + 4);
+    B.clist = pool.alloc<int32_t>(total_nodes);
+    B.cbase = pool.alloc<int32_t>(4 * (size_t)n_ext + 4);
+    unsigned long long *d_ext_pairs = pool.alloc<unsigned long long>(n_ext, true);
+    if (pool.failed) return PGPU_ENOMEM;
+    launch_extract_fill(B, n_ext, ro, st);
+    launch_node_prep(B, n_ext, total_nodes, 1, st);
+    launch_pairs(B, n_ext, total_nodes, d_ext_pairs, st);
+    ctx->launches += 4;
+    int e_ext = mark();
+
+    S.n_contigs += n; S.total_bp += atot; S.total_nodes += total_nodes; S.total_chain_nodes += total_cn;
+    S.n_chains += n_chains; S.dp_steps += total_cn;
+
+    if (plan.stage == 1) {
+        if (op) {
+            op->ndx.resize(total_nodes); op->stop_val.resize(total_nodes); op->cls.resize(total_nodes);
+            if (total_nodes) {
+                CK(cudaMemcpyAsync(op->ndx.data(), B.ndx, total_nodes * 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(op->stop_val.data(), B.stop_val, total_nodes * 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(op->cls.data(), B.cls, total_nodes, cudaMemcpyDeviceToHost, st));
+            }
+        }
+        CK(cudaStreamSynchronize(st));
+        return PGPU_OK;
+    }
+
+    // ---- per-chain scoring ---------------------------------------------------------------------------
+    B.chains = pool.upload(chains);
+    B.cscore = pool.alloc<double>(total_cn); B.sscore = pool.alloc<double>(total_cn);
+    B.rscore = pool.alloc<double>(total_cn); B.uscore = pool.alloc<double>(total_cn);
+    B.tscore = pool.alloc<double>(total_cn);
+    B.opv = pool.alloc<double>(3 * (size_t)total_cn);
+    B.star_ptr = pool.alloc<int32_t>(3 * (size_t)total_cn);
+    B.rbs = pool.alloc<uint8_t>(2 * (size_t)total_cn + 16);
+    B.score = pool.alloc<double>(total_cn);
+    B.traceb = pool.alloc<int32_t>(total_cn);
+    B.ov_mark = pool.alloc<int8_t>(total_cn + 16);
+    B.chain_ipath = pool.alloc<int32_t>(n_chains);
+    B.chain_score = pool.alloc<double>(n_chains);
+    int32_t *d_tracef = pool.alloc<int32_t>(total_cn);
+    uint8_t *d_elim = pool.alloc<uint8_t>(total_cn + 16, true);
+    MotifOut *d_mot_main = (!meta) ? pool.alloc<MotifOut>(total_cn) : nullptr;
+    if (pool.failed) return PGPU_ENOMEM;
+    if (total_cn) CK(cudaMemsetAsync(d_tracef, 0xff, total_cn * sizeof(int32_t), st));
+    launch_score_chains(B, ctx->d_models, n_chains, total_cn, ro, d_mot_main, st);
+    ctx->launches += 2;
+    int e_score = mark();
+    launch_overlap(B, ctx->d_models, n_chains, total_cn, ro, 1, st);
+    ctx->launches++;
+    int e_ovl = mark();
+
+    if (plan.stage == 2) {
+        if (op) {
+            pgpu_node *d_nodes = pool.alloc<pgpu_node>(total_cn);
+            if (pool.failed) return PGPU_ENOMEM;
+            launch_pack_nodes(B, n_chains, total_cn, d_mot_main, d_tracef, d_elim, 2, d_nodes, st);
+            op->nodes.resize(total_cn);
+            if (total_cn) CK(cudaMemcpyAsync(op->nodes.data(), d_nodes, total_cn * sizeof(pgpu_node), cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
+        return PGPU_OK;
+    }
+
+    // ---- DP: largest chains first ---------------------------------------------------------------------
+    std::vector<int32_t> order(n_chains);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return chains[a].nn > chains[b].nn; });
+    int32_t *d_order = pool.upload(order);
+    int32_t *d_ccb = pool.upload(contig_chain_begin);
+    // gene buffers: a gene ends at a distinct STOP node, so nn/2+1 bounds the genes of any chain
+    std::vector<int64_t> gene_off(n + 1, 0), fin_coff(n + 1, 0);
+    for (int c = 0; c < n; c++) {
+        int mx = 0;
+        for (int e = contig_ext_begin[c]; e < contig_ext_begin[c + 1]; e++) mx = std::max(mx, exts[e].nn);
+        gene_off[c + 1] = gene_off[c] + mx / 2 + 1;
+        fin_coff[c + 1] = fin_coff[c] + mx;
+    }
+    pgpu_gene *d_genes = pool.alloc<pgpu_gene>(gene_off[n]);
+    int64_t *d_gene_off = pool.upload(gene_off);
+    std::vector<pgpu_contig_summary> summ(n);
+    for (int c = 0; c < n; c++) { memset(&summ[c], 0, sizeof(summ[c])); summ[c].unknown = h_unk[c]; summ[c].gc_count = h_gc[c]; }
+    pgpu_contig_summary *d_summ = pool.upload(summ);
+    int32_t *d_winner_chain = pool.alloc<int32_t>(n);
+    if (pool.failed) return PGPU_ENOMEM;
+    launch_dp(B, ctx->d_models, d_order, n_chains, 1, st);
+    ctx->launches++;
+    int e_dp = mark();
+    launch_trace(B, ctx->d_models, n, d_ccb, d_tracef, d_elim, d_genes, d_gene_off, d_summ, d_winner_chain, meta ? 1 : 0,
+                 opts.max_overlap, st);
+    ctx->launches++;
+    int e_trace = mark();
+
+    // ---- final node records ------------------------------------------------------------------------------
+    pgpu_node *d_nodes = nullptr;
+    int64_t *d_node_out_off = nullptr;
+    std::vector<int64_t> node_out_off(n + 1, 0);
+    if (meta) {
+        // re-score the winner's nodes as a fresh first pass (lib.pyx:5380-5394)
+        DevBatch F = B;
+        ChainInfo *d_fin = pool.alloc<ChainInfo>(n);
+        int64_t *d_fin_coff = pool.upload(fin_coff);
+        const int64_t ftot = fin_coff[n];
+        F.chains = d_fin;
+        F.cscore = pool.alloc<double>(ftot); F.sscore = pool.alloc<double>(ftot); F.rscore = pool.alloc<double>(ftot);
+        F.uscore = pool.alloc<double>(ftot); F.tscore = pool.alloc<double>(ftot);
+        F.rbs = pool.alloc<uint8_t>(2 * (size_t)ftot + 16);
+        MotifOut *d_mot = pool.alloc<MotifOut>(ftot);
+        d_nodes = pool.alloc<pgpu_node>(ftot);
+        if (pool.failed) return PGPU_ENOMEM;
+        launch_build_final_chains(B, n, d_winner_chain, d_fin_coff, d_fin, st);
+        // chains with nn == 0 keep coff monotone, so the chain search inside the kernels stays valid; the
+        // unused tail of every contig's slot is never touched because kernels index by chain, but the flat
+        // index space must be dense: use per-contig capacity as the chain length for the search only.
+        launch_score_chains(F, ctx->d_models, n, ftot, ro, d_mot, st);
+        launch_pack_nodes(F, n, ftot, d_mot, nullptr, nullptr, 0, d_nodes, st);
+        ctx->launches += 4;
+        node_out_off = fin_coff;
+        d_node_out_off = d_fin_coff;
+    } else {
+        d_nodes = pool.alloc<pgpu_node>(total_cn);
+        if (pool.failed) return PGPU_ENOMEM;
+        launch_pack_nodes(B, n_chains, total_cn, d_mot_main, d_tracef, d_elim, 1, d_nodes, st);
+        ctx->launches++;
+        for (int c = 0; c < n; c++) node_out_off[c] = chains[contig_chain_begin[c]].coff;
+        node_out_off[n] = total_cn;
+        d_node_out_off = pool.upload(node_out_off);
+    }
+    int e_final = mark();
+    std::vector<unsigned long long> h_ext_pairs(n_ext);
+    if (n_ext) CK(cudaMemcpyAsync(h_ext_pairs.data(), d_ext_pairs, n_ext * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(summ.data(), d_summ, n * sizeof(pgpu_contig_summary), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    S.d2h_bytes += n * sizeof(pgpu_contig_summary);
+    for (const auto &K : chains) S.pairs += (int64_t)h_ext_pairs[K.ext];
+
+    // ---- compact genes + their start/stop node records, copy back ---------------------------------------
+    std::vector<int64_t> gene_out_off(n + 1, 0);
+    for (int c = 0; c < n; c++) gene_out_off[c + 1] = gene_out_off[c] + summ[c].n_genes;
+    const int64_t ng = gene_out_off[n];
+    int64_t *d_gene_out_off = pool.upload(gene_out_off);
+    pgpu_gene *d_genes_out = pool.alloc<pgpu_gene>(ng);
+    pgpu_node *d_gene_nodes = pool.alloc<pgpu_node>(2 * ng);
+    if (pool.failed) return PGPU_ENOMEM;
+    launch_pack_gene_nodes(n, d_summ, d_genes, d_gene_off, d_gene_out_off, d_node_out_off, d_nodes, d_gene_nodes, d_genes_out, st);
+    ctx->launches++;
+    const size_t g0 = res->genes.size();
+    res->genes.resize(g0 + ng);
+    res->gene_nodes.resize(2 * (g0 + ng));
+    if (ng) {
+        CK(cudaMemcpyAsync(res->genes.data() + g0, d_genes_out, ng * sizeof(pgpu_gene), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(res->gene_nodes.data() + 2 * g0, d_gene_nodes, 2 * ng * sizeof(pgpu_node), cudaMemcpyDeviceToHost, st));
+        S.d2h_bytes += ng * (sizeof(pgpu_gene) + 2 * sizeof(pgpu_node));
+    }
+    if (opts.want_nodes) {
+        const size_t n0 = res->nodes.size();
+        int64_t tot = 0;
+        for (int c = 0; c < n; c++) tot += summ[c].n_nodes;
+        res->nodes.resize(n0 + tot);
+        int64_t w = n0;
+        for (int c = 0; c < n; c++) {
+            res->node_off[lo + c] = w;
+            if (summ[c].n_nodes)
+                CK(cudaMemcpyAsync(res->nodes.data() + w, d_nodes + node_out_off[c], summ[c].n_nodes * sizeof(pgpu_node),
+                                   cudaMemcpyDeviceToHost, st));
+            w += summ[c].n_nodes;
+        }
+        res->node_off[hi] = w;
+        S.d2h_bytes += tot * sizeof(pgpu_node);
+        res->have_nodes = true;
+    }
+    int e_d2h = mark();
+    CK(cudaStreamSynchronize(st));
+    for (int c = 0; c < n; c++) {
+        res->summary[lo + c] = summ[c];
+        res->gene_off[lo + c + 1] = (int64_t)g0 + gene_out_off[c + 1];
+    }
+    S.total_genes += ng;
+    auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]); return (double)t; };
+    S.ms_h2d += ms(e_start, e_h2d);
+    S.ms_encode += ms(e_h2d, e_enc);
+    S.ms_extract += ms(e_enc, e_mark) + ms(e_mark, e_ext);
+    S.ms_score += ms(e_ext, e_score);
+    S.ms_overlap += ms(e_score, e_ovl);
+    S.ms_dp += ms(e_ovl, e_dp);
+    S.ms_trace += ms(e_dp, e_trace);
+    S.ms_final += ms(e_trace, e_final);
+    S.ms_d2h += ms(e_final, e_d2h);
+    S.ms_total_device += ms(e_h2d, e_final);
+    return PGPU_OK;
+}
+
+// small gather kernel used by run_range (kept here: it is plumbing, not part of the hot path)
+__global__ void k_gather_i32(const int32_t *__restrict__ src, const int64_t *__restrict__ idx, int n, int32_t *__restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+void launch_gather_i32(const int32_t *src, const int64_t *idx, int n, int32_t *dst, cudaStream_t st) {
+    if (n > 0) k_gather_i32<<<(n + 255) / 256, 256, 0, st>>>(src, idx, n, dst);
+}
+
+// ------------------------------------------------------------------------------------------------
+// batching: split the contigs into sub-batches that fit the workspace
+// ------------------------------------------------------------------------------------------------
+static int check_opts(pgpu_ctx *ctx, const pgpu_opts *o) {
+    if (!o) return fail(ctx, PGPU_EINVAL, "opts is NULL");
+    if (o->min_gene <= 0) return fail(ctx, PGPU_EINVAL, "`min_gene` must be strictly positive");
+    if (o->min_edge_gene <= 0) return fail(ctx, PGPU_EINVAL, "`min_edge_gene` must be strictly positive");
+    if (o->min_mask < 0) return fail(ctx, PGPU_EINVAL, "`min_mask` must be positive");
+    if (o->max_overlap < 0) return fail(ctx, PGPU_EINVAL, "`max_overlap` must be positive");
+    if (o->max_overlap > o->min_gene) return fail(ctx, PGPU_EINVAL, "`max_overlap` must be lower than `min_gene`");
+    if (!o->meta && (o->single_model < 0 || o->single_model >= ctx->n_models))
+        return fail(ctx, PGPU_ESTATE, "cannot find genes without having trained in single mode");
+    return PGPU_OK;
+}
+
+static int run_all(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, const int64_t *offsets, int n,
+                   const pgpu_opts *opts, pgpu_result **out) {
+    if (!ctx) return PGPU_EINVAL;
+    if (!out || !offsets || n < 0 || (!h_seq && !d_seq && n > 0 && offsets[n] > offsets[0]))
+        return fail(ctx, PGPU_EINVAL, "bad arguments");
+    int rc = check_opts(ctx, opts);
+    if (rc) return rc;
+    if (ctx->n_models == 0) return fail(ctx, PGPU_ESTATE, "no models loaded");
+    cudaSetDevice(ctx->device);
+    pgpu_result *res = new pgpu_result();
+    res->n_contigs = n;
+    res->summary.resize(n);
+    res->gene_off.assign(n + 1, 0);
+    res->node_off.assign(n + 1, 0);
+    memset(&res->stats, 0, sizeof(res->stats));
+    const int64_t launches0 = ctx->launches;
+    // sub-batch size: bytes per base pair is dominated by per-chain node arrays (~100 B per chain-node,
+    // ~0.06 nodes/bp, up to ~26 chains): budget 160 B/bp against the workspace limit
+    size_t freeb = 0, totalb = 0;
+    cudaMemGetInfo(&freeb, &totalb);
+    size_t limit = ctx->ws_limit ? ctx->ws_limit : (size_t)(0.6 * (double)freeb);
+    const int64_t bp_budget = std::max<int64_t>((int64_t)(limit / 160), 1 << 20);
+    RunPlan plan;
+    int lo = 0;
+    while (lo < n) {
+        int hi = lo;
+        int64_t bp = 0;
+        while (hi < n && (hi == lo || bp + (offsets[hi + 1] - offsets[hi]) <= bp_budget) && hi - lo < (1 << 22)) {
+            bp += offsets[hi + 1] - offsets[hi];
+            hi++;
+        }
+        rc = run_range(ctx, h_seq, d_seq, offsets, lo, hi, *opts, plan, res, nullptr);
+        if (rc) { delete res; return rc; }
+        lo = hi;
+    }
+    res->stats.kernel_launches = ctx->launches - launches0;
+    *out = res;
+    return PGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int pgpu_create(int device, pgpu_ctx **out) {
+    if (!out) return PGPU_EINVAL;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return PGPU_ENODEV;
+    }
+    if (device < 0 || device >= count) { g_create_err = "device index out of range"; return PGPU_ENODEV; }
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_err = "cudaSetDevice failed"; return PGPU_ENODEV; }
+    pgpu_ctx *ctx = new pgpu_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_create_err = "cudaStreamCreate failed";
+        delete ctx;
+        return PGPU_ECUDA;
+    }
+    for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    // keep freed blocks cached in the stream-ordered pool: sub-batches reuse them without going to the driver
+    cudaMemPool_t mp;
+    if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = ctx;
+    return PGPU_OK;
+}
+
+void pgpu_destroy(pgpu_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_raw) cudaFree(ctx->d_raw);
+    if (ctx->d_models) cudaFree(ctx->d_models);
+    for (auto &ev : ctx->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *pgpu_last_error(const pgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int pgpu_set_models(pgpu_ctx *ctx, const void *blobs, int n, size_t stride) {
+    if (!ctx) return PGPU_EINVAL;
+    if (!blobs || n <= 0 || stride < sizeof(RawTraining)) return fail(ctx, PGPU_EINVAL, "bad model blobs");
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_raw) { cudaFree(ctx->d_raw); ctx->d_raw = nullptr; }
+    if (ctx->d_models) { cudaFree(ctx->d_models); ctx->d_models = nullptr; }
+    ctx->h_raw.resize(n);
+    for (int k = 0; k < n; k++) memcpy(&ctx->h_raw[k], (const char *)blobs + k * stride, sizeof(RawTraining));
+    CK(cudaMalloc(&ctx->d_raw, n * sizeof(RawTraining)));
+    CK(cudaMalloc(&ctx->d_models, n * sizeof(DevModel)));
+    ctx->h_models.resize(n);
+    for (int k = 0; k < n; k++) prepare_model(ctx->h_raw[k], ctx->h_models[k], ctx->d_raw + k);
+    CK(cudaMemcpy(ctx->d_raw, ctx->h_raw.data(), n * sizeof(RawTraining), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_models, ctx->h_models.data(), n * sizeof(DevModel), cudaMemcpyHostToDevice));
+    ctx->n_models = n;
+    return PGPU_OK;
+}
+
+int pgpu_num_models(const pgpu_ctx *ctx) { return ctx ? ctx->n_models : 0; }
+
+int pgpu_set_workspace_limit(pgpu_ctx *ctx, size_t bytes) {
+    if (!ctx) return PGPU_EINVAL;
+    ctx->ws_limit = bytes;
+    return PGPU_OK;
+}
+
+int pgpu_find_genes_batch(pgpu_ctx *ctx, const uint8_t *seq, const int64_t *offsets, int n_contigs,
+                          const pgpu_opts *opts, pgpu_result **out) {
+    return run_all(ctx, seq, nullptr, offsets, n_contigs, opts, out);
+}
+
+int pgpu_batch_upload(pgpu_ctx *ctx, const uint8_t *seq, const int64_t *offsets, int n_contigs, pgpu_batch **out) {
+    if (!ctx) return PGPU_EINVAL;
+    if (!out || !offsets || n_contigs < 0) return fail(ctx, PGPU_EINVAL, "bad arguments");
+    cudaSetDevice(ctx->device);
+    pgpu_batch *b = new pgpu_batch();
+    b->ctx = ctx;
+    b->n_contigs = n_contigs;
+    b->offsets.assign(offsets, offsets + n_contigs + 1);
+    const int64_t base = offsets[0];
+    for (auto &o : b->offsets) o -= base;
+    b->total = b->offsets[n_contigs];
+    cudaError_t e = cudaMalloc(&b->d_ascii, std::max<int64_t>(b->total, 1) + 16);
+    if (e != cudaSuccess) { delete b; return fail(ctx, PGPU_ENOMEM, cudaGetErrorString(e)); }
+    if (b->total) {
+        e = cudaMemcpyAsync(b->d_ascii, seq + base, b->total, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { cudaFree(b->d_ascii); delete b; return fail(ctx, PGPU_ECUDA, cudaGetErrorString(e)); }
+    }
+    *out = b;
+    return PGPU_OK;
+}
+
+int pgpu_batch_run(pgpu_ctx *ctx, pgpu_batch *batch, const pgpu_opts *opts, pgpu_result **out) {
+    if (!ctx || !batch) return PGPU_EINVAL;
+    return run_all(ctx, nullptr, batch->d_ascii, batch->offsets.data(), batch->n_contigs, opts, out);
+}
+
+void pgpu_batch_free(pgpu_batch *b) {
+    if (!b) return;
+    if (b->d_ascii) { cudaSetDevice(b->ctx->device); cudaFree(b->d_ascii); }
+    delete b;
+}
+
+int pgpu_result_num_contigs(const pgpu_result *res) { return res ? res->n_contigs : PGPU_EINVAL; }
+
+int pgpu_result_summaries(const pgpu_result *res, pgpu_contig_summary *dst) {
+    if (!res || !dst) return PGPU_EINVAL;
+    if (res->n_contigs) memcpy(dst, res->summary.data(), res->n_contigs * sizeof(pgpu_contig_summary));
+    return PGPU_OK;
+}
+
+int pgpu_result_genes(const pgpu_result *res, int contig, pgpu_gene *dst) {
+    if (!res || contig < 0 || contig >= res->n_contigs) return PGPU_EINVAL;
+    const int64_t a = res->gene_off[contig], b = res->gene_off[contig + 1];
+    if (b > a) { if (!dst) return PGPU_EINVAL; memcpy(dst, res->genes.data() + a, (b - a) * sizeof(pgpu_gene)); }
+    return PGPU_OK;
+}
+
+int pgpu_result_all_genes(const pgpu_result *res, pgpu_gene *dst) {
+    if (!res) return PGPU_EINVAL;
+    if (!res->genes.empty()) { if (!dst) return PGPU_EINVAL; memcpy(dst, res->genes.data(), res->genes.size() * sizeof(pgpu_gene)); }
+    return PGPU_OK;
+}
+
+int pgpu_result_gene_nodes(const pgpu_result *res, pgpu_node *dst) {
+    if (!res) return PGPU_EINVAL;
+    if (!res->gene_nodes.empty()) { if (!dst) return PGPU_EINVAL; memcpy(dst, res->gene_nodes.data(), res->gene_nodes.size() * sizeof(pgpu_node)); }
+    return PGPU_OK;
+}
+
+int pgpu_result_nodes(const pgpu_result *res, int contig, pgpu_node *dst) {
+    if (!res || contig < 0 || contig >= res->n_contigs) return PGPU_EINVAL;
+    if (!res->have_nodes) return PGPU_ESTATE;
+    const int64_t a = res->node_off[contig], b = res->node_off[contig + 1];
+    if (b > a) { if (!dst) return PGPU_EINVAL; memcpy(dst, res->nodes.data() + a, (b - a) * sizeof(pgpu_node)); }
+    return PGPU_OK;
+}
+
+int pgpu_result_stats(const pgpu_result *res, pgpu_stats *dst) {
+    if (!res || !dst) return PGPU_EINVAL;
+    *dst = res->stats;
+    return PGPU_OK;
+}
+
+void pgpu_result_free(pgpu_result *res) { delete res; }
+
+// ---- operator-level twins ---------------------------------------------------------------------------
+
+int pgpu_extract_nodes(pgpu_ctx *ctx, const uint8_t *seq, int slen, int translation_table, const pgpu_opts *opts,
+                       int cap, int32_t *ndx, int32_t *stop_val, int8_t *strand, uint8_t *type, uint8_t *edge) {
+    if (!ctx) return PGPU_EINVAL;
+    if (!opts || slen < 0 || (!seq && slen > 0) || translation_table < 1 || translation_table > 33)
+        return fail(ctx, PGPU_EINVAL, "bad arguments");
+    cudaSetDevice(ctx->device);
+    pgpu_result tmp;
+    memset(&tmp.stats, 0, sizeof(tmp.stats));
+    tmp.summary.resize(1); tmp.gene_off.assign(2, 0); tmp.node_off.assign(2, 0);
+    OperatorOut op;
+    RunPlan plan;
+    plan.stage = 1;
+    plan.forced_tt = translation_table;
+    const int64_t offs[2] = {0, slen};
+    int rc = run_range(ctx, seq, nullptr, offs, 0, 1, *opts, plan, &tmp, &op);
+    if (rc) return rc;
+    const int nn = (int)op.ndx.size();
+    if (ndx || stop_val || strand || type || edge) {
+        if (nn > cap) return fail(ctx, PGPU_EINVAL, "node capacity too small");
+        for (int i = 0; i < nn; i++) {
+            if (ndx) ndx[i] = op.ndx[i];
+            if (stop_val) stop_val[i] = op.stop_val[i];
+            if (strand) strand[i] = (op.cls[i] & CLS_REV) ? -1 : 1;
+            if (type) type[i] = op.cls[i] & CLS_TYPE;
+            if (edge) edge[i] = (op.cls[i] & CLS_EDGE) ? 1 : 0;
+        }
+    }
+    return nn;
+}
+
+int pgpu_score_nodes(pgpu_ctx *ctx, const uint8_t *seq, int slen, int model, const pgpu_opts *opts, int is_meta,
+                     int first_pass, int cap, pgpu_node *dst) {
+    if (!ctx) return PGPU_EINVAL;
+    if (!opts || slen < 0 || (!seq && slen > 0)) return fail(ctx, PGPU_EINVAL, "bad arguments");
+    if (model < 0 || model >= ctx->n_models) return fail(ctx, PGPU_ESTATE, "model index out of range");
+    cudaSetDevice(ctx->device);
+    pgpu_result tmp;
+    memset(&tmp.stats, 0, sizeof(tmp.stats));
+    tmp.summary.resize(1); tmp.gene_off.assign(2, 0); tmp.node_off.assign(2, 0);
+    OperatorOut op;
+    RunPlan plan;
+    plan.stage = 2;
+    plan.forced_model = model;
+    plan.forced_first_pass = first_pass;
+    plan.forced_is_meta = is_meta;
+    const int64_t offs[2] = {0, slen};
+    int rc = run_range(ctx, seq, nullptr, offs, 0, 1, *opts, plan, &tmp, &op);
+    if (rc) return rc;
+    const int nn = (int)op.nodes.size();
+    if (dst) {
+        if (nn > cap) return fail(ctx, PGPU_EINVAL, "node capacity too small");
+        if (nn) memcpy(dst, op.nodes.data(), nn * sizeof(pgpu_node));
+    }
+    return nn;
+}
+
+int pgpu_score_connections(pgpu_ctx *ctx, int n, const int32_t *ndx, const int32_t *stop_val, const int8_t *strand,
+                           const uint8_t *type, const double *cscore, const double *sscore, const double *rscore,
+                           const double *uscore, const double *gc_score, const int32_t *star_ptr, int model, int final,
+                           double *out_score, int32_t *out_traceb, int8_t *out_ov_mark, int64_t *out_pairs,
+                           double *out_ms) {
+    if (!ctx) return PGPU_EINVAL;
+    if (n < 0 || (n > 0 && (!ndx || !stop_val || !strand || !type || !cscore || !sscore || !rscore || !uscore ||
+                            !star_ptr || !out_score || !out_traceb || !out_ov_mark)))
+        return fail(ctx, PGPU_EINVAL, "bad arguments");
+    if (!final && n > 0 && !gc_score) return fail(ctx, PGPU_EINVAL, "gc_score required when final == 0");
+    if (model < 0 || model >= ctx->n_models) return fail(ctx, PGPU_ESTATE, "model index out of range");
+    if (out_pairs) *out_pairs = 0;
+    if (out_ms) *out_ms = 0.0;
+    if (n == 0) return PGPU_OK;
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    DevPool pool(ctx);
+    DevBatch B;
+    memset(&B, 0, sizeof(B));
+    std::vector<uint8_t> cls(n);
+    for (int i = 0; i < n; i++)
+        cls[i] = (uint8_t)((type[i] & 3) | (strand[i] != 1 ? CLS_REV : 0) | ((((ndx[i] % 3) + 3) % 3) << CLS_FRAME_SHIFT));
+    std::vector<ExtractInfo> exts(1);
+    memset(&exts[0], 0, sizeof(ExtractInfo));
+    exts[0].nn = n;
+    std::vector<ChainInfo> chains(1);
+    memset(&chains[0], 0, sizeof(ChainInfo));
+    chains[0].model = model; chains[0].nn = n; chains[0].first_pass = 1;
+    const DevModel &M = ctx->h_models[model];
+    std::vector<double> gcb(n, 0.0);
+    if (!final)
+        for (int i = 0; i < n; i++)
+            gcb[i] = M.bias[0] * gc_score[3 * i] + M.bias[1] * gc_score[3 * i + 1] + M.bias[2] * gc_score[3 * i + 2];
+    B.exts = pool.upload(exts);
+    B.chains = pool.upload(chains);
+    B.ndx = pool.alloc<int32_t>(n); B.stop_val = pool.alloc<int32_t>(n); B.cls = pool.upload(cls);
+    B.win_min = pool.alloc<int32_t>(n); B.crank = pool.alloc<int32_t>(4 * (size_t)n + 4); B.clist = pool.alloc<int32_t>(n);
+    B.cbase = pool.alloc<int32_t>(8);
+    B.cscore = pool.alloc<double>(n); B.sscore = pool.alloc<double>(n); B.rscore = pool.alloc<double>(n);
+    B.uscore = pool.alloc<double>(n); B.opv = pool.alloc<double>(3 * (size_t)n); B.gcb = pool.upload(gcb);
+    B.star_ptr = pool.alloc<int32_t>(3 * (size_t)n);
+    B.score = pool.alloc<double>(n); B.traceb = pool.alloc<int32_t>(n); B.ov_mark = pool.alloc<int8_t>(n + 16);
+    B.chain_ipath = pool.alloc<int32_t>(1); B.chain_score = pool.alloc<double>(1);
+    unsigned long long *d_pairs = pool.alloc<unsigned long long>(1, true);
+    if (pool.failed) return PGPU_ENOMEM;
+    CK(cudaMemcpyAsync(B.ndx, ndx, n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B.stop_val, stop_val, n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B.cscore, cscore, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B.sscore, sscore, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B.rscore, rscore, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B.uscore, uscore, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B.star_ptr, star_ptr, 3 * (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    launch_node_prep(B, 1, n, 0, st);
+    launch_pairs(B, 1, n, d_pairs, st);
+    launch_opv(B, ctx->d_models, 1, n, st);
+    cudaEventRecord(ctx->ev[0], st);
+    launch_dp(B, ctx->d_models, nullptr, 1, final ? 1 : 0, st);
+    cudaEventRecord(ctx->ev[1], st);
+    ctx->launches += 5;
+    unsigned long long pairs = 0;
+    CK(cudaMemcpyAsync(out_score, B.score, n * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_traceb, B.traceb, n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_ov_mark, B.ov_mark, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&pairs, d_pairs, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (out_pairs) *out_pairs = (int64_t)pairs;
+    if (out_ms) { float t = 0; cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]); *out_ms = t; }
+    return PGPU_OK;
+}
+
+int pgpu_compute_skippable(pgpu_ctx *ctx, int n, const int8_t *strand, const uint8_t *type, const int32_t *ndx, int mn,
+                           int i, uint8_t *skip) {
+    if (!ctx) return PGPU_EINVAL;
+    if (n <= 0 || !strand || !type || !ndx || !skip || mn < 0 || i >= n || mn > i) return fail(ctx, PGPU_EINVAL, "bad arguments");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    DevPool pool(ctx);
+    int8_t *d_s = pool.alloc<int8_t>(n);
+    uint8_t *d_t = pool.alloc<uint8_t>(n), *d_k = pool.alloc<uint8_t>(n, true);
+    int32_t *d_n = pool.alloc<int32_t>(n);
+    if (pool.failed) return PGPU_ENOMEM;
+    CK(cudaMemcpyAsync(d_s, strand, n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_t, type, n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_n, ndx, n * 4, cudaMemcpyHostToDevice, st));
+    launch_skippable(n, d_s, d_t, d_n, mn, i, d_k, st);
+    ctx->launches++;
+    CK(cudaMemcpyAsync(skip + mn, d_k + mn, i - mn, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,152 @@
+// common.cuh -- shared definitions of the pyrodigal_b200 CUDA library (sm_100a only).
+//
+// Data model (all device arrays are SoA; see DESIGN.md "Data layout in HBM"):
+//   contig      one input sequence.  digits[doff .. doff+slen) (1 B/nt, A0 G1 C2 T3 N6, padded with
+//               zeros, doff multiple of 128) and cod[] (1 B/nt: 6-bit code of the codon starting at
+//               that base + bit 6 "contains N").
+//   extraction  (contig, translation table): the sorted node list  ndx[], stop_val[], cls[], gc_cont[],
+//               plus DP index tables (window start, per-class ranks, class lists).
+//   chain       (extraction, model): one DP chain.  Per-chain node scores and DP state live at
+//               chain-node offset `coff`.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pyrodigal_b200.h"
+
+namespace pgpu {
+
+constexpr int kMaxNodeDist = 500;  // vendor/Prodigal/dprog.h:29
+constexpr int kMaxOppOvlp = 200;   // vendor/Prodigal/dprog.h:30
+constexpr int kOperDist = 60;      // src/Prodigal/node.h:33
+#define PGPU_EDGE_BONUS 0.74       // node.h:34
+#define PGPU_EDGE_UPS (-1.00)      // node.h:35
+#define PGPU_META_PEN 7.5          // node.h:36
+
+// node kinds: 2*(reverse strand) + (type == STOP)
+enum : int { K_FS = 0, K_FE = 1, K_RS = 2, K_RE = 3 };
+
+// cls byte of a node
+constexpr int CLS_TYPE = 0x03;   // 0 ATG 1 GTG 2 TTG 3 STOP
+constexpr int CLS_REV = 0x04;    // reverse strand
+constexpr int CLS_EDGE = 0x08;   // edge flag as produced by extraction
+constexpr int CLS_CONV = 0x10;   // start that Nodes._score converts to an edge node (lib.pyx:2424-2434)
+constexpr int CLS_FRAME_SHIFT = 5;  // bits 5-6: ndx % 3
+
+__host__ __device__ inline int cls_kind(int c) { return ((c >> 2) & 1) * 2 + ((c & CLS_TYPE) == 3); }
+__host__ __device__ inline int cls_frame(int c) { return (c >> CLS_FRAME_SHIFT) & 3; }
+__host__ __device__ inline bool cls_is_stop(int c) { return (c & CLS_TYPE) == 3; }
+__host__ __device__ inline bool cls_is_rev(int c) { return (c & CLS_REV) != 0; }
+
+// ---- per-model tables derived on the host from the raw `struct _training` blob ----------------
+struct DevModel {
+    double st_wt, gc, no_mot;
+    double bias[3], type_wt[3];
+    double rbs_wt[28];
+    double uc[32][4];      // 0.4 * st_wt * ups_comp[k][b]            (lib.pyx:1642,1648)
+    double lfac[1001];     // log((1-p^g)/p^g) - lfac_min, g = 0..1000 (lib.pyx:2209-2210, host libm)
+    double lfac_span;      // lfac_max - lfac_min                      (lib.pyx:2207)
+    double igt[61];        // (2.0 - d/60) * 0.15 * st_wt, d = 0..60   (_connection.h:74)
+    double ig_neg;         // -0.15 * st_wt                            (_connection.h:48,72)
+    int32_t trans_table, uses_sd;
+    uint64_t stopmask, startmask;  // bit c: codon code c is a stop / start in trans_table
+    uint8_t sd_best[2][15][64];    // best SD bin for (exact|mismatch, offset, 6-bit match pattern)
+    const double *gene_dc;         // device pointers into the raw blob
+    const double *mot_wt;
+};
+
+struct ContigInfo {
+    int64_t doff;   // offset of the contig in digits[] / cod[] (multiple of 128)
+    int64_t aoff;   // offset of the contig in the ASCII input
+    int32_t slen;
+    int32_t mask_off, n_masks;  // masks of this contig in the mask table (pairs)
+    int32_t pad;
+};
+
+struct ExtractInfo {
+    int32_t contig;
+    int32_t tt;
+    int64_t doff;
+    int32_t slen;
+    int32_t slot;        // bitmap slot of this extraction within its contig
+    int64_t woff;        // first 32-bit word of this extraction's node bitmaps
+    int32_t nwords;
+    int32_t node_off;    // first node in the extraction-node arrays
+    int32_t nn;
+    int32_t mask_off, n_masks;
+    int32_t pad;
+    uint64_t stopmask, startmask;
+};
+
+struct ChainInfo {
+    int32_t ext;
+    int32_t model;
+    int32_t contig;
+    int32_t first_pass;  // 1: first model scored after this extraction
+    int32_t node_off;    // extraction-node offset
+    int32_t nn;
+    int64_t coff;        // chain-node offset
+    int64_t doff;
+    int32_t slen;
+    int32_t is_meta;
+};
+
+struct RunOpts {
+    int32_t closed, min_gene, min_edge_gene, max_overlap;
+};
+
+// ---- device arrays of one (sub-)batch ----------------------------------------------------------
+struct DevBatch {
+    // sequences
+    const uint8_t *ascii;
+    uint8_t *digits;
+    uint8_t *cod;
+    ContigInfo *contigs;
+    int32_t *gc_count;   // per contig
+    int32_t *unknown;    // per contig
+    int32_t *masks;      // pairs [begin,end)
+    // extraction
+    ExtractInfo *exts;
+    uint32_t *bits_fwd, *bits_rev;  // node bitmaps (per extraction, word offset woff)
+    int32_t *wordbase;              // exclusive prefix of node counts per bitmap word
+    // extraction nodes
+    int32_t *ndx, *stop_val;
+    uint8_t *cls;
+    float *gc_cont;
+    uint32_t *sdbits;     // upstream A/G pattern for the SD motif search
+    int32_t *win_min;     // DP window start (lib.pyx:1224-1233)
+    int32_t *crank;       // [4 * node]: number of class-c nodes before node
+    int32_t *clist;       // class-sorted node indices (local), segments per class
+    int32_t *cbase;       // [4 * ext]: start of each class segment in clist (relative to node_off)
+    // chains
+    ChainInfo *chains;
+    double *cscore, *sscore, *rscore, *uscore, *tscore;  // per chain-node
+    double *opv;          // [3 * chain-node] operon values (cs[n3] + igm) for STOP nodes
+    double *gcb;          // training DP: bias . gc_score per chain-node (only final == 0)
+    int32_t *star_ptr;    // [3 * chain-node]
+    uint8_t *rbs;         // [2 * chain-node]
+    double *score;
+    int32_t *traceb;
+    int8_t *ov_mark;
+    // per chain results
+    int32_t *chain_ipath;
+    double *chain_score;
+};
+
+// best upstream motif of a start node (struct _motif, src/Prodigal/node.h:39-46)
+struct MotifOut {
+    double score;
+    uint16_t ndx;
+    uint8_t len, spacer, spacendx, pad[3];
+};
+
+// ---- device helpers ------------------------------------------------------------------------------
+
+// codon code of the reverse-strand codon whose 5' base is at forward position p, from the code of the
+// forward codon starting at p-2: complement every base and reverse the base order.
+__host__ __device__ inline int rev_code(int c) {
+    int r = ((c >> 4) & 3) | (c & 0xC) | ((c & 3) << 4);
+    return r ^ 63;
+}
+
+}  // namespace pgpu

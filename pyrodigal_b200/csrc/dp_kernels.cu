@@ -1,0 +1,671 @@
+// dp_kernels.cu -- the connection-scoring dynamic program and everything downstream of it.
+//
+// Reference semantics: BaseConnectionScorer._score_connections / _find_max_index / _disentangle_overlaps /
+// _max_forward_pointers / _dynamic_programming (src/pyrodigal/lib.pyx:1205-1311), the four specialised
+// score_connection functions (src/pyrodigal/_connection.h:94-367), the skip filter
+// (src/pyrodigal/impl/generic.h:29-36), eliminate_bad_genes (vendor/Prodigal/dprog.c:306-335),
+// Genes._extract / _tweak_final_starts (lib.pyx:3231-3401), the meta-mode winner rule (lib.pyx:5364).
+//
+// B200 design:
+//  * one CTA walks one chain (contig x model); chains are independent, so a batch exposes 10^3..10^6 CTAs.
+//  * the SIMD skip filter is not a pass: nodes are pre-bucketed by class (+start,+STOP,-start,-STOP) and a
+//    target only visits the classes the six filter clauses admit (about one third of the window), in index
+//    order, so tie-breaking ("largest j wins") is unchanged.
+//  * the DP-dependent state of the last 1024 nodes (score, ndx of the traceback node) lives in a shared
+//    memory ring; model-independent node data comes from L1/L2; the per-target constants of the next 32
+//    steps are staged cooperatively (coalesced) into shared memory.
+//  * per step: lanes stride over admissible predecessors, warp-shuffle arg-max, one __syncthreads.
+//  * doubles everywhere, no FMA contraction (-fmad=false): results are bit-identical to the reference.
+#include <cfloat>
+
+#include "kernels.cuh"
+
+namespace pgpu {
+
+constexpr int kDpThreads = 128;
+constexpr int kDpWarps = kDpThreads / 32;
+constexpr int kRing = 1024;
+constexpr int kStage = 32;
+constexpr int kTbNone = INT32_MIN;  // "traceb == -1"
+
+struct StepConst {
+    int32_t ndx, sv, m, cls;
+    int32_t cr_i[4];
+    int32_t cr_m[4];
+    int32_t sp[3];
+    int32_t n3ndx[3];
+    int32_t n3sv[3];
+    int32_t pad;
+    double opv[3];
+    double gcb3[3];
+    double cs;   // cscore + sscore of the target (K_RS)
+    double gcb;  // training: bias . gc_score of the target
+};
+
+struct Cand {
+    double v;
+    int32_t j, tn, fr;
+};
+
+__device__ __forceinline__ void cand_take(Cand &a, double v, int j, int tn, int fr) {
+    // candidates of one thread arrive with increasing j: ">=" keeps the largest j among equal values
+    if (v >= a.v) { a.v = v; a.j = j; a.tn = tn; a.fr = fr; }
+}
+__device__ __forceinline__ void cand_merge(Cand &a, double v, int j, int tn, int fr) {
+    if (v > a.v || (v == a.v && j > a.j)) { a.v = v; a.j = j; a.tn = tn; a.fr = fr; }
+}
+
+template <int FINAL>
+__global__ void __launch_bounds__(kDpThreads) k_dp(DevBatch B, const DevModel *__restrict__ models,
+                                                    const int32_t *__restrict__ order, int n_chains) {
+    __shared__ double s_score[kRing];
+    __shared__ int32_t s_tbn[kRing];
+    __shared__ StepConst s_c[kStage];
+    __shared__ Cand s_red[2][kDpWarps];
+
+    const int chain = order ? order[blockIdx.x] : blockIdx.x;
+    const ChainInfo C = B.chains[chain];
+    const int nn = C.nn, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (nn == 0) {
+        if (tid == 0) { B.chain_ipath[chain] = -1; B.chain_score[chain] = 0.0; }
+        return;
+    }
+    const DevModel &M = models[C.model];
+    const int32_t *__restrict__ ndx = B.ndx + C.node_off;
+    const int32_t *__restrict__ sv = B.stop_val + C.node_off;
+    const uint8_t *__restrict__ cls = B.cls + C.node_off;
+    const int32_t *__restrict__ win_min = B.win_min + C.node_off;
+    const int32_t *__restrict__ crank = B.crank + 4 * (int64_t)C.node_off;
+    const int32_t *__restrict__ clist = B.clist + C.node_off;
+    const int32_t *__restrict__ cbase = B.cbase + 4 * C.ext;
+    const double *__restrict__ cscore = B.cscore + C.coff;
+    const double *__restrict__ sscore = B.sscore + C.coff;
+    const double *__restrict__ opv = B.opv + 3 * C.coff;
+    const double *__restrict__ gcb = FINAL ? nullptr : B.gcb + C.coff;
+    const int32_t *__restrict__ star_ptr = B.star_ptr + 3 * C.coff;
+    double *score = B.score + C.coff;
+    int32_t *traceb = B.traceb + C.coff;
+    int8_t *ov_mark = B.ov_mark + C.coff;
+    const int cb0 = cbase[0], cb1 = cbase[1], cb2 = cbase[2], cb3 = cbase[3];
+    const double ig_neg = M.ig_neg;
+
+    double prev_score = 0.0;
+    int prev_tbn = kTbNone;
+    double best_sc = -1.0;
+    int best_i = -1, best_tb = -1;
+
+    for (int i0 = 0; i0 < nn; i0 += kStage) {
+        // ---- stage the constants of the next kStage targets (one lane per target) ----
+        __syncthreads();
+        if (tid < kStage && i0 + tid < nn) {
+            const int i = i0 + tid;
+            StepConst sc;
+            sc.ndx = ndx[i]; sc.sv = sv[i]; sc.cls = cls[i]; sc.m = win_min[i];
+            const int4 a = *reinterpret_cast<const int4 *>(crank + 4 * (int64_t)i);
+            const int4 b = *reinterpret_cast<const int4 *>(crank + 4 * (int64_t)sc.m);
+            sc.cr_i[0] = a.x; sc.cr_i[1] = a.y; sc.cr_i[2] = a.z; sc.cr_i[3] = a.w;
+            sc.cr_m[0] = b.x; sc.cr_m[1] = b.y; sc.cr_m[2] = b.z; sc.cr_m[3] = b.w;
+            const int kind = cls_kind(sc.cls);
+            sc.cs = 0.0; sc.gcb = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) { sc.sp[k] = -1; sc.n3ndx[k] = 0; sc.n3sv[k] = 0; sc.opv[k] = 0.0; sc.gcb3[k] = 0.0; }
+            if (kind == K_RE) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const int s = star_ptr[3 * (int64_t)i + k];
+                    sc.sp[k] = s;
+                    if (s != -1) {
+                        sc.n3ndx[k] = ndx[s]; sc.n3sv[k] = sv[s];
+                        sc.opv[k] = opv[3 * (int64_t)i + k];
+                        if (!FINAL) sc.gcb3[k] = gcb[s];
+                    }
+                }
+            } else if (kind == K_RS) {
+                sc.cs = cscore[i] + sscore[i];
+                if (!FINAL) sc.gcb = gcb[i];
+            }
+            s_c[tid] = sc;
+        }
+        __syncthreads();
+
+        const int iend = min(i0 + kStage, nn);
+        for (int i = i0; i < iend; i++) {
+            const StepConst &K = s_c[i - i0];
+            const int ndx_i = K.ndx, sv_i = K.sv, kind2 = cls_kind(K.cls), f2 = cls_frame(K.cls);
+            Cand best = {-DBL_MAX, -1, kTbNone, -1};
+
+            // DP state of predecessor j: registers (j == i-1), shared ring, or global (giant-ORF windows)
+            auto state = [&](int j, double &sj, int &tj) {
+                if (j == i - 1) { sj = prev_score; tj = prev_tbn; }
+                else if (i - j < kRing) { sj = s_score[j & (kRing - 1)]; tj = s_tbn[j & (kRing - 1)]; }
+                else { sj = score[j]; const int tb = traceb[j]; tj = tb == -1 ? kTbNone : ndx[tb]; }
+            };
+
+            if (kind2 == K_FS) {
+                // <- +STOP (intergenic, same strand)
+                for (int p = cb1 + K.cr_m[1] + tid, pe = cb1 + K.cr_i[1]; p < pe; p += kDpThreads) {
+                    const int j = clist[p], nj = ndx[j];
+                    double sj; int tj; state(j, sj, tj);
+                    if (tj == kTbNone || nj + 2 >= ndx_i) continue;
+                    double term = 0.0;
+                    if (FINAL) { const int dist = ndx_i - nj; term = dist > 3 * kOperDist ? ig_neg : (dist <= kOperDist ? M.igt[dist] : 0.0); }
+                    cand_take(best, sj + term, j, nj, -1);
+                }
+                Cand b2 = {-DBL_MAX, -1, kTbNone, -1};
+                // <- -start (intergenic, strand switch)
+                for (int p = cb2 + K.cr_m[2] + tid, pe = cb2 + K.cr_i[2]; p < pe; p += kDpThreads) {
+                    const int j = clist[p], nj = ndx[j];
+                    double sj; int tj; state(j, sj, tj);
+                    if (tj == kTbNone || nj >= ndx_i) continue;
+                    cand_take(b2, sj + (FINAL ? ig_neg : 0.0), j, nj, -1);
+                }
+                cand_merge(best, b2.v, b2.j, b2.tn, b2.fr);
+            } else if (kind2 == K_FE) {
+                // <- +start of the same frame (gene)
+                for (int p = cb0 + K.cr_m[0] + tid, pe = cb0 + K.cr_i[0]; p < pe; p += kDpThreads) {
+                    const int j = clist[p];
+                    if (cls_frame(cls[j]) != f2) continue;
+                    const int nj = ndx[j];
+                    if (sv_i >= nj) continue;
+                    double sj; int tj; state(j, sj, tj);
+                    double term;
+                    if (FINAL) term = cscore[j] + sscore[j];
+                    else term = ((double)(ndx_i + 2 - nj + 1)) * gcb[j];
+                    cand_take(best, sj + term, j, nj, -1);
+                }
+                Cand b2 = {-DBL_MAX, -1, kTbNone, -1};
+                // <- +STOP (operon: overlapping forward genes)
+                for (int p = cb1 + K.cr_m[1] + tid, pe = cb1 + K.cr_i[1]; p < pe; p += kDpThreads) {
+                    const int j = clist[p], nj = ndx[j];
+                    if (sv_i >= nj) continue;
+                    double sj; int tj; state(j, sj, tj);
+                    if (tj == kTbNone) continue;
+                    const int s = star_ptr[3 * (int64_t)j + f2];
+                    if (s == -1) continue;
+                    double term;
+                    if (FINAL) term = opv[3 * (int64_t)j + f2];
+                    else term = ((double)(ndx_i + 2 - ndx[s] + 1)) * gcb[s];
+                    cand_take(b2, sj + term, j, nj, -1);
+                }
+                cand_merge(best, b2.v, b2.j, b2.tn, b2.fr);
+            } else if (kind2 == K_RS) {
+                // <- -STOP of the same frame (reverse gene)
+                for (int p = cb3 + K.cr_m[3] + tid, pe = cb3 + K.cr_i[3]; p < pe; p += kDpThreads) {
+                    const int j = clist[p];
+                    if (cls_frame(cls[j]) != f2) continue;
+                    if (sv[j] <= ndx_i) continue;
+                    const int nj = ndx[j];
+                    double sj; int tj; state(j, sj, tj);
+                    double term;
+                    if (FINAL) term = K.cs;
+                    else term = ((double)(ndx_i - (nj - 2) + 1)) * K.gcb;
+                    cand_take(best, sj + term, j, nj, -1);
+                }
+                Cand b2 = {-DBL_MAX, -1, kTbNone, -1};
+                // <- +STOP (overlapping opposite-strand 3' ends)
+                const double cs_diff = K.cs + ig_neg;
+                for (int p = cb1 + K.cr_m[1] + tid, pe = cb1 + K.cr_i[1]; p < pe; p += kDpThreads) {
+                    const int j = clist[p], nj = ndx[j];
+                    if (sv_i - 2 >= nj + 2) continue;
+                    const int ovlp = (nj + 2) - (sv_i - 2) + 1;
+                    if (ovlp >= kMaxOppOvlp) continue;
+                    if ((nj - sv_i) >= (ndx_i - nj + 3)) continue;
+                    double sj; int tj; state(j, sj, tj);
+                    if (tj == kTbNone) continue;
+                    if ((nj - sv_i) >= (sv_i - 3 - tj)) continue;
+                    double term;
+                    if (FINAL) term = cs_diff;
+                    else term = ((double)(ndx_i - (sv_i - 2) + 1 - ovlp * 2)) * K.gcb;
+                    cand_take(b2, sj + term, j, nj, -1);
+                }
+                cand_merge(best, b2.v, b2.j, b2.tn, b2.fr);
+            } else {  // K_RE
+                // <- +STOP (intergenic with the triple-overlap search)
+                for (int p = cb1 + K.cr_m[1] + tid, pe = cb1 + K.cr_i[1]; p < pe; p += kDpThreads) {
+                    const int j = clist[p], nj = ndx[j];
+                    const int left = nj + 2, right = ndx_i - 2;
+                    if (left >= right) continue;
+                    double sj; int tj; state(j, sj, tj);
+                    if (tj == kTbNone) continue;
+                    int maxfr = -1, ovlp = 0;
+                    double maxval = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        if (K.sp[k] == -1) continue;
+                        ovlp = left - K.n3sv[k] + 3;
+                        if (ovlp <= 0 || ovlp >= kMaxOppOvlp) continue;
+                        if (ovlp >= K.n3ndx[k] - left) continue;
+                        if (ovlp >= K.n3sv[k] - tj - 2) continue;
+                        const double cur = K.opv[k];
+                        if (FINAL ? (cur > maxval) : (K.gcb3[k] > maxval)) { maxfr = k; maxval = cur; }
+                    }
+                    double term;
+                    if (FINAL) term = maxfr != -1 ? K.opv[maxfr] : ig_neg;
+                    else term = ((double)(right - left + 1 - ovlp * 2)) * (maxfr != -1 ? K.gcb3[maxfr] : 0.0);
+                    cand_take(best, sj + term, j, nj, maxfr);
+                }
+                Cand b2 = {-DBL_MAX, -1, kTbNone, -1};
+                // <- -start (intergenic, same strand)
+                for (int p = cb2 + K.cr_m[2] + tid, pe = cb2 + K.cr_i[2]; p < pe; p += kDpThreads) {
+                    const int j = clist[p], nj = ndx[j];
+                    if (nj >= ndx_i - 2) continue;
+                    double sj; int tj; state(j, sj, tj);
+                    if (tj == kTbNone) continue;
+                    double term = 0.0;
+                    if (FINAL) { const int dist = ndx_i - nj; term = dist > 3 * kOperDist ? ig_neg : (dist <= kOperDist ? M.igt[dist] : 0.0); }
+                    cand_take(b2, sj + term, j, nj, -1);
+                }
+                cand_merge(best, b2.v, b2.j, b2.tn, b2.fr);
+                Cand b3 = {-DBL_MAX, -1, kTbNone, -1};
+                // <- -STOP (operon: overlapping reverse genes)
+                for (int p = cb3 + K.cr_m[3] + tid, pe = cb3 + K.cr_i[3]; p < pe; p += kDpThreads) {
+                    const int j = clist[p];
+                    if (sv[j] <= ndx_i) continue;
+                    const int fj = cls_frame(cls[j]);
+                    if (K.sp[fj] == -1) continue;
+                    const int nj = ndx[j];
+                    double sj; int tj; state(j, sj, tj);
+                    double term;
+                    if (FINAL) term = K.opv[fj];
+                    else term = ((double)(K.n3ndx[fj] - (nj - 2) + 1)) * K.gcb3[fj];
+                    cand_take(b3, sj + term, j, nj, -1);
+                }
+                cand_merge(best, b3.v, b3.j, b3.tn, b3.fr);
+            }
+
+            // ---- arg-max over the CTA: equal values -> larger j ----
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double v = __shfl_xor_sync(0xffffffffu, best.v, off);
+                const int j = __shfl_xor_sync(0xffffffffu, best.j, off);
+                const int tn = __shfl_xor_sync(0xffffffffu, best.tn, off);
+                const int fr = __shfl_xor_sync(0xffffffffu, best.fr, off);
+                cand_merge(best, v, j, tn, fr);
+            }
+            const int par = i & 1;
+            if (lane == 0) s_red[par][wid] = best;
+            __syncthreads();
+            Cand fin = s_red[par][0];
+#pragma unroll
+            for (int w = 1; w < kDpWarps; w++) { const Cand c = s_red[par][w]; cand_merge(fin, c.v, c.j, c.tn, c.fr); }
+
+            // "if (n1->score + score >= n2->score)" starting from score 0, traceb -1
+            double sc_i = 0.0;
+            int tb_i = -1, tbn_i = kTbNone, fr_i = -1;
+            if (fin.j >= 0 && fin.v >= 0.0) { sc_i = fin.v; tb_i = fin.j; tbn_i = fin.tn; fr_i = fin.fr; }
+            if (tid == 0) { score[i] = sc_i; traceb[i] = tb_i; ov_mark[i] = (int8_t)fr_i; }
+            if (tid == 32) { s_score[i & (kRing - 1)] = sc_i; s_tbn[i & (kRing - 1)] = tbn_i; }
+            prev_score = sc_i;
+            prev_tbn = tbn_i;
+            if ((kind2 == K_FE || kind2 == K_RS) && sc_i >= best_sc) { best_sc = sc_i; best_i = i; best_tb = tb_i; }
+        }
+    }
+    if (tid == 0) {
+        // lib.pyx:1239-1251 + 1311: largest index among equal maxima; -1 when nothing leads into it
+        const bool ok = best_i >= 0 && best_tb != -1;
+        B.chain_ipath[chain] = ok ? best_i : -1;
+        B.chain_score[chain] = ok ? best_sc : 0.0;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// winner selection + traceback + gene extraction: one thread per contig
+// --------------------------------------------------------------------------------------------------
+struct NodeRef {
+    const int32_t *ndx, *sv;
+    const uint8_t *cls;
+    double *cscore, *sscore, *rscore, *uscore, *tscore;
+    int32_t *traceb, *tracef, *star_ptr;
+    int8_t *ov_mark;
+    uint8_t *elim;
+};
+
+__device__ __forceinline__ double igm_nodes(const NodeRef &N, int a, int b, const DevModel &M) {
+    // _intergenic_mod (_connection.h:81-91)
+    const int ca = N.cls[a], cb = N.cls[b];
+    if (((ca ^ cb) & CLS_REV) != 0) return M.ig_neg;
+    const int sa = (ca & CLS_REV) ? -1 : 1;
+    const int na = N.ndx[a], nb = N.ndx[b];
+    const int dist = abs(na - nb);
+    const bool overlap = na + 2 * sa >= nb;
+    double r = 0.0;
+    if (na + 2 == nb || na == nb + 1) {
+        const int s = sa == 1 ? b : a;
+        if (N.rscore[s] < 0) r -= N.rscore[s];
+        if (N.uscore[s] < 0) r -= N.uscore[s];
+    }
+    if (dist > 3 * kOperDist) r -= 0.15 * M.st_wt;
+    else if ((dist <= kOperDist && !overlap) || dist * 4 < kOperDist) r += (2.0 - ((double)dist / kOperDist)) * 0.15 * M.st_wt;
+    return r;
+}
+
+struct TraceArgs {
+    const int32_t *contig_chain_begin;  // [n_contigs + 1] chains of contig c
+    int32_t *tracef;                    // per chain-node
+    uint8_t *elim;                      // per chain-node
+    pgpu_gene *genes;                   // gene buffers
+    const int64_t *gene_off;            // [n_contigs] offset of each contig's gene buffer
+    pgpu_contig_summary *summary;       // [n_contigs]
+    int32_t *winner_chain;              // [n_contigs] chain index of the winner or -1
+    int meta;
+    int max_overlap;
+};
+
+__global__ void __launch_bounds__(64) k_trace(DevBatch B, const DevModel *__restrict__ models, int n_contigs,
+                                               TraceArgs A) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_contigs) return;
+    // ---- winner: strict ">" from -100 in bin order, so the lowest bin wins ties (lib.pyx:5331,5364) ----
+    int win = -1;
+    double max_score = -100.0;
+    for (int k = A.contig_chain_begin[c]; k < A.contig_chain_begin[c + 1]; k++) {
+        const int ip = B.chain_ipath[k];
+        if (A.meta) {
+            if (B.chains[k].nn > 0 && ip >= 0 && B.chain_score[k] > max_score) { max_score = B.chain_score[k]; win = k; }
+        } else {
+            win = k;  // single mode: exactly one chain, kept even when no path exists
+        }
+    }
+    pgpu_contig_summary S = A.summary[c];
+    S.n_genes = 0; S.n_nodes = 0; S.winner = -1; S.ipath = -1; S.score = 0.0;
+    A.winner_chain[c] = win;
+    if (win < 0) { A.summary[c] = S; return; }
+    const ChainInfo C = B.chains[win];
+    const DevModel &M = models[C.model];
+    const int nn = C.nn;
+    const int ipath = B.chain_ipath[win];
+    S.winner = C.model; S.n_nodes = nn; S.ipath = ipath; S.score = ipath >= 0 ? B.chain_score[win] : 0.0;
+    NodeRef N;
+    N.ndx = B.ndx + C.node_off; N.sv = B.stop_val + C.node_off; N.cls = B.cls + C.node_off;
+    N.cscore = B.cscore + C.coff; N.sscore = B.sscore + C.coff; N.rscore = B.rscore + C.coff;
+    N.uscore = B.uscore + C.coff; N.tscore = B.tscore + C.coff;
+    N.traceb = B.traceb + C.coff; N.tracef = A.tracef + C.coff; N.star_ptr = B.star_ptr + 3 * C.coff;
+    N.ov_mark = B.ov_mark + C.coff; N.elim = A.elim + C.coff;
+    if (nn == 0) { A.summary[c] = S; return; }
+
+    // the reference untangles overlaps from the arg-max node even when that node has no traceback
+    // (then both loops fall through); we only have work when a path exists
+    if (ipath >= 0) {
+        // pass 1: triple overlaps (lib.pyx:1258-1271)
+        for (int path = ipath; N.traceb[path] != -1; path = N.traceb[path]) {
+            const int nxt = N.traceb[path];
+            if (cls_kind(N.cls[path]) == K_RE && cls_kind(N.cls[nxt]) == K_FE && N.ov_mark[path] != -1 &&
+                N.ndx[path] > N.ndx[nxt]) {
+                const int tmp = N.star_ptr[3 * path + N.ov_mark[path]];
+                int i = tmp;
+                while (N.ndx[i] != N.sv[tmp]) i--;
+                N.traceb[path] = tmp;
+                N.traceb[tmp] = i;
+                N.ov_mark[i] = -1;
+                N.traceb[i] = nxt;
+            }
+        }
+        // pass 2: simple overlaps (lib.pyx:1273-1289)
+        for (int path = ipath; N.traceb[path] != -1; path = N.traceb[path]) {
+            const int nxt = N.traceb[path];
+            const int kp = cls_kind(N.cls[path]), kn = cls_kind(N.cls[nxt]);
+            if (kp == K_RS && kn == K_FE) {
+                int i = path;
+                while (N.ndx[i] != N.sv[path]) i--;
+                N.traceb[path] = i;
+                N.traceb[i] = nxt;
+            }
+            if (kp == K_FE && kn == K_FE) {
+                N.traceb[path] = N.star_ptr[3 * nxt + N.ndx[path] % 3];
+                N.traceb[N.traceb[path]] = nxt;
+            }
+            if (kp == K_RE && kn == K_RE) {
+                N.traceb[path] = N.star_ptr[3 * path + N.ndx[nxt] % 3];
+                N.traceb[N.traceb[path]] = nxt;
+            }
+        }
+        // forward pointers (lib.pyx:1291-1295)
+        for (int path = ipath; N.traceb[path] != -1; path = N.traceb[path]) N.tracef[N.traceb[path]] = path;
+
+        // eliminate_bad_genes (dprog.c:306-335)
+        int head = ipath;
+        while (N.traceb[head] != -1) head = N.traceb[head];
+        for (int p = head; N.tracef[p] != -1; p = N.tracef[p]) {
+            const int nx = N.tracef[p], k = cls_kind(N.cls[p]);
+            if (k == K_FE) N.sscore[nx] += igm_nodes(N, p, nx, M);
+            if (k == K_RS) N.sscore[p] += igm_nodes(N, p, nx, M);
+        }
+        for (int p = head; N.tracef[p] != -1; p = N.tracef[p]) {
+            const int nx = N.tracef[p], k = cls_kind(N.cls[p]);
+            if (k == K_FS && N.cscore[p] + N.sscore[p] < 0) { N.elim[p] = 1; N.elim[nx] = 1; }
+            if (k == K_RE && N.cscore[nx] + N.sscore[nx] < 0) { N.elim[p] = 1; N.elim[nx] = 1; }
+        }
+
+        // Genes._extract (lib.pyx:3231-3270)
+        pgpu_gene *genes = A.genes + A.gene_off[c];
+        int ng = 0, begin = 0, end = 0, start_ndx = 0, stop_ndx = 0;
+        for (int p = head; p != -1; p = N.tracef[p]) {
+            if (N.elim[p] == 1) continue;
+            const int cp = N.cls[p];
+            bool emit = false;
+            if (!(cp & CLS_REV)) {
+                if (!cls_is_stop(cp)) { begin = N.ndx[p] + 1; start_ndx = p; }
+                else { end = N.ndx[p] + 3; stop_ndx = p; emit = true; }
+            } else {
+                if (!cls_is_stop(cp)) { end = N.ndx[p] + 1; start_ndx = p; emit = true; }
+                else { begin = N.ndx[p] - 1; stop_ndx = p; }
+            }
+            if (emit) { genes[ng].begin = begin; genes[ng].end = end; genes[ng].start_ndx = start_ndx; genes[ng].stop_ndx = stop_ndx; ng++; }
+        }
+        S.n_genes = ng;
+
+        // Genes._tweak_final_starts (lib.pyx:3272-3401); edge flags are the post-scoring ones
+        auto is_edge = [&](int x) { return (N.cls[x] & (CLS_EDGE | CLS_CONV)) != 0; };
+        auto strand_of = [&](int x) { return (N.cls[x] & CLS_REV) ? -1 : 1; };
+        for (int gi = 0; gi < ng; gi++) {
+            const int cur = genes[gi].start_ndx;
+            const double sc = N.sscore[cur] + N.cscore[cur];
+            double igm0 = 0.0;
+            const int pstart = gi > 0 ? genes[gi - 1].start_ndx : -1, pstop = gi > 0 ? genes[gi - 1].stop_ndx : -1;
+            const int nstart = gi < ng - 1 ? genes[gi + 1].start_ndx : -1, nstop = gi < ng - 1 ? genes[gi + 1].stop_ndx : -1;
+            const int scur = strand_of(cur);
+            if (pstart >= 0 && scur == 1 && strand_of(pstart) == 1) igm0 = igm_nodes(N, pstop, cur, M);
+            if (pstart >= 0 && scur == 1 && strand_of(pstart) == -1) igm0 = M.ig_neg;
+            if (nstart >= 0 && scur == -1 && strand_of(nstart) == 1) igm0 = M.ig_neg;
+            if (nstart >= 0 && scur == -1 && strand_of(nstart) == -1) igm0 = igm_nodes(N, cur, nstop, M);
+
+            int maxndx[2] = {-1, -1};
+            double maxsc[2] = {0, 0}, maxigm[2] = {0, 0};
+            for (int j = cur - 100; j < cur + 100; j++) {
+                if (j < 0 || j >= nn || j == cur) continue;
+                if (cls_is_stop(N.cls[j]) || N.sv[j] != N.sv[cur]) continue;
+                const int sj = strand_of(j);
+                double tigm = 0.0;
+                if (pstart >= 0 && sj == 1 && strand_of(pstart) == 1) {
+                    if (N.ndx[pstop] - N.ndx[j] > A.max_overlap) continue;
+                    tigm = igm_nodes(N, pstop, j, M);
+                }
+                if (pstart >= 0 && sj == 1 && strand_of(pstart) == -1) {
+                    if (N.ndx[pstart] - N.ndx[j] >= 0) continue;
+                    tigm = M.ig_neg;
+                }
+                if (nstart >= 0 && sj == -1 && strand_of(nstart) == 1) {
+                    if (N.ndx[j] - N.ndx[nstart] >= 0) continue;
+                    tigm = M.ig_neg;
+                }
+                if (nstart >= 0 && sj == -1 && strand_of(nstart) == -1) {
+                    if (N.ndx[j] - N.ndx[nstop] > A.max_overlap) continue;
+                    tigm = igm_nodes(N, j, nstop, M);
+                }
+                const double csc = N.cscore[j] + N.sscore[j];
+                if (maxndx[0] == -1) {
+                    maxndx[0] = j; maxsc[0] = csc; maxigm[0] = tigm;
+                } else if (csc + tigm > maxsc[0]) {
+                    maxndx[1] = maxndx[0]; maxsc[1] = maxsc[0]; maxigm[1] = maxigm[0];
+                    maxndx[0] = j; maxsc[0] = csc; maxigm[0] = tigm;
+                } else if (maxndx[1] == -1 || csc + tigm > maxsc[1]) {
+                    maxndx[1] = j; maxsc[1] = csc; maxigm[1] = tigm;
+                }
+            }
+            for (int q = 0; q < 2; q++) {
+                const int m = maxndx[q];
+                if (m == -1) continue;
+                if (N.tscore[m] < N.tscore[cur] && maxsc[q] - N.tscore[m] >= sc - N.tscore[cur] + M.st_wt &&
+                    N.rscore[m] > N.rscore[cur] && N.uscore[m] > N.uscore[cur] && N.cscore[m] > N.cscore[cur] &&
+                    abs(N.ndx[m] - N.ndx[cur]) > 15) {
+                    maxsc[q] += N.tscore[cur] - N.tscore[m];
+                } else if (abs(N.ndx[m] - N.ndx[cur]) <= 15 &&
+                           N.rscore[m] + N.tscore[m] > N.rscore[cur] + N.tscore[cur] && !is_edge(cur) && !is_edge(m)) {
+                    if (N.cscore[cur] > N.cscore[m]) maxsc[q] += N.cscore[cur] - N.cscore[m];
+                    if (N.uscore[cur] > N.uscore[m]) maxsc[q] += N.uscore[cur] - N.uscore[m];
+                    if (igm0 > maxigm[q]) maxsc[q] += igm0 - maxigm[q];
+                } else {
+                    maxsc[q] = -1000.0;
+                }
+            }
+            int pick = -1;
+            for (int q = 0; q < 2; q++) {
+                if (maxndx[q] == -1) continue;
+                if (pick == -1 && maxsc[q] + maxigm[q] > sc + igm0) pick = q;
+                else if (pick >= 0 && maxsc[q] + maxigm[q] > maxsc[pick] + maxigm[pick]) pick = q;
+            }
+            if (pick != -1) {
+                const int m = maxndx[pick];
+                genes[gi].start_ndx = m;
+                if (strand_of(m) == 1) genes[gi].begin = N.ndx[m] + 1;
+                else genes[gi].end = N.ndx[m] + 1;
+            }
+        }
+    }
+    A.summary[c] = S;
+}
+
+// --------------------------------------------------------------------------------------------------
+// output packing
+// --------------------------------------------------------------------------------------------------
+
+// nodes of a chain list -> pgpu_node records.  `dp_state`: 1 = single mode (keep the DP state of the
+// winning chain), 0 = meta mode (nodes were re-extracted and re-scored: score 0, traceb/tracef -1,
+// star_ptr 0)
+__global__ void __launch_bounds__(128) k_pack_nodes(DevBatch B, int n_chains, int64_t total,
+                                                     const MotifOut *__restrict__ mot, const int32_t *__restrict__ tracef,
+                                                     const uint8_t *__restrict__ elim, int dp_state,
+                                                     pgpu_node *__restrict__ out) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    int lo = 0, hi = n_chains - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (B.chains[mid].coff <= g) lo = mid; else hi = mid - 1;
+    }
+    const ChainInfo C = B.chains[lo];
+    const int i = (int)(g - C.coff);
+    if (i >= C.nn) return;
+    const int c = B.cls[C.node_off + i];
+    pgpu_node n;
+    n.ndx = B.ndx[C.node_off + i];
+    n.stop_val = B.stop_val[C.node_off + i];
+    n.strand = (c & CLS_REV) ? -1 : 1;
+    n.type = c & CLS_TYPE;
+    n.edge = (c & (CLS_EDGE | CLS_CONV)) ? 1 : 0;  // flags after Nodes._score (lib.pyx:2431)
+    n.gc_cont = cls_is_stop(c) ? 0.0f : B.gc_cont[C.node_off + i];
+    n.rbs[0] = B.rbs[2 * g]; n.rbs[1] = B.rbs[2 * g + 1];
+    const MotifOut m = mot ? mot[g] : MotifOut{};
+    n.mot_score = m.score; n.mot_ndx = m.ndx; n.mot_len = m.len; n.mot_spacer = m.spacer; n.mot_spacendx = m.spacendx;
+    n.cscore = B.cscore[g]; n.uscore = B.uscore[g]; n.tscore = B.tscore[g]; n.rscore = B.rscore[g]; n.sscore = B.sscore[g];
+    if (dp_state == 1) {
+        n.score = B.score[g]; n.traceb = B.traceb[g]; n.tracef = tracef[g]; n.ov_mark = B.ov_mark[g];
+        n.elim = elim[g];
+        n.star_ptr[0] = B.star_ptr[3 * g]; n.star_ptr[1] = B.star_ptr[3 * g + 1]; n.star_ptr[2] = B.star_ptr[3 * g + 2];
+    } else {
+        n.score = 0.0; n.traceb = -1; n.tracef = -1; n.ov_mark = -1; n.elim = 0;
+        n.star_ptr[0] = n.star_ptr[1] = n.star_ptr[2] = 0;
+        if (dp_state == 2) {  // scored + record_overlapping_starts, no DP (pgpu_score_nodes)
+            n.star_ptr[0] = B.star_ptr[3 * g]; n.star_ptr[1] = B.star_ptr[3 * g + 1]; n.star_ptr[2] = B.star_ptr[3 * g + 2];
+        }
+    }
+    out[g] = n;
+}
+
+// meta mode: the winner's nodes are re-extracted and re-scored from scratch (lib.pyx:5380-5394); this
+// builds the chain list of that final scoring pass (first_pass = 1: fresh extraction)
+__global__ void k_build_final_chains(DevBatch B, int n_contigs, const int32_t *__restrict__ winner_chain,
+                                     const int64_t *__restrict__ fin_coff, ChainInfo *__restrict__ fin) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_contigs) return;
+    const int w = winner_chain[c];
+    ChainInfo F;
+    if (w >= 0) { F = B.chains[w]; F.first_pass = 1; }
+    else { F = ChainInfo{}; F.contig = c; F.nn = 0; }
+    F.coff = fin_coff[c];
+    fin[c] = F;
+}
+
+// start/stop node records of every gene (what Gene accessors read), 2 per gene
+__global__ void __launch_bounds__(128) k_pack_gene_nodes(int n_contigs, const pgpu_contig_summary *__restrict__ summary,
+                                                          const pgpu_gene *__restrict__ genes,
+                                                          const int64_t *__restrict__ gene_off,
+                                                          const int64_t *__restrict__ gene_out_off,
+                                                          const int64_t *__restrict__ node_out_off,
+                                                          const pgpu_node *__restrict__ nodes, pgpu_node *__restrict__ out,
+                                                          pgpu_gene *__restrict__ genes_out) {
+    const int c = blockIdx.x;
+    const int ng = summary[c].n_genes;
+    for (int g = threadIdx.x; g < ng; g += blockDim.x) {
+        const pgpu_gene G = genes[gene_off[c] + g];
+        genes_out[gene_out_off[c] + g] = G;
+        out[2 * (gene_out_off[c] + g)] = nodes[node_out_off[c] + G.start_ndx];
+        out[2 * (gene_out_off[c] + g) + 1] = nodes[node_out_off[c] + G.stop_ndx];
+    }
+}
+
+// the skip filter as a stand-alone operator (impl/generic.h:29-36), via the class table
+__global__ void k_skippable(int n, const int8_t *__restrict__ strand, const uint8_t *__restrict__ type,
+                            const int32_t *__restrict__ ndx, int mn, int i, uint8_t *__restrict__ skip) {
+    const int j = mn + blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= i) return;
+    const int k1 = 2 * (strand[j] != 1) + (type[j] == 3), k2 = 2 * (strand[i] != 1) + (type[i] == 3);
+    const bool same_frame = ndx[j] % 3 == ndx[i] % 3;
+    bool ok;
+    switch (k2) {
+    case K_FS: ok = (k1 == K_FE || k1 == K_RS); break;
+    case K_FE: ok = ((k1 == K_FS && same_frame) || k1 == K_FE); break;
+    case K_RS: ok = ((k1 == K_RE && same_frame) || k1 == K_FE); break;
+    default: ok = (k1 == K_FE || k1 == K_RS || k1 == K_RE); break;
+    }
+    skip[j] = ok ? 0 : 1;
+}
+
+// --------------------------------------------------------------------------------------------------
+// launch wrappers
+// --------------------------------------------------------------------------------------------------
+void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, int n_chains, int final, cudaStream_t st) {
+    if (n_chains == 0) return;
+    if (final) k_dp<1><<<n_chains, kDpThreads, 0, st>>>(B, models, order, n_chains);
+    else k_dp<0><<<n_chains, kDpThreads, 0, st>>>(B, models, order, n_chains);
+}
+void launch_trace(const DevBatch &B, const DevModel *models, int n_contigs, const int32_t *contig_chain_begin,
+                  int32_t *tracef, uint8_t *elim, pgpu_gene *genes, const int64_t *gene_off,
+                  pgpu_contig_summary *summary, int32_t *winner_chain, int meta, int max_overlap, cudaStream_t st) {
+    if (n_contigs == 0) return;
+    TraceArgs A = {contig_chain_begin, tracef, elim, genes, gene_off, summary, winner_chain, meta, max_overlap};
+    k_trace<<<(n_contigs + 63) / 64, 64, 0, st>>>(B, models, n_contigs, A);
+}
+void launch_pack_nodes(const DevBatch &B, int n_chains, int64_t total, const void *mot, const int32_t *tracef,
+                       const uint8_t *elim, int dp_state, pgpu_node *out, cudaStream_t st) {
+    if (n_chains == 0 || total == 0) return;
+    k_pack_nodes<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, n_chains, total, (const MotifOut *)mot, tracef, elim,
+                                                                   dp_state, out);
+}
+void launch_pack_gene_nodes(int n_contigs, const pgpu_contig_summary *summary, const pgpu_gene *genes,
+                            const int64_t *gene_off, const int64_t *gene_out_off, const int64_t *node_out_off,
+                            const pgpu_node *nodes, pgpu_node *out, pgpu_gene *genes_out, cudaStream_t st) {
+    if (n_contigs == 0) return;
+    k_pack_gene_nodes<<<n_contigs, 64, 0, st>>>(n_contigs, summary, genes, gene_off, gene_out_off, node_out_off, nodes, out,
+                                                genes_out);
+}
+void launch_build_final_chains(const DevBatch &B, int n_contigs, const int32_t *winner_chain, const int64_t *fin_coff,
+                               ChainInfo *fin_chains, cudaStream_t st) {
+    if (n_contigs > 0) k_build_final_chains<<<(n_contigs + 127) / 128, 128, 0, st>>>(B, n_contigs, winner_chain, fin_coff, fin_chains);
+}
+void launch_skippable(int n, const int8_t *strand, const uint8_t *type, const int32_t *ndx, int mn, int i, uint8_t *skip,
+                      cudaStream_t st) {
+    if (i > mn) k_skippable<<<(i - mn + 127) / 128, 128, 0, st>>>(n, strand, type, ndx, mn, i, skip);
+}
+
+}  // namespace pgpu

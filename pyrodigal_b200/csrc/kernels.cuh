@@ -1,0 +1,41 @@
+// kernels.cuh -- launch wrappers shared between the translation units of libpyrodigal_b200.so
+#pragma once
+#include "common.cuh"
+
+namespace pgpu {
+
+// seq_kernels.cu
+void launch_encode(const DevBatch &B, const int2 *tiles, int n_tiles, cudaStream_t st);
+void launch_find_masks(const DevBatch &B, const int2 *tiles, int n_tiles, int min_mask, int4 *out, int cap,
+                       int *count, cudaStream_t st);
+void launch_extract_mark(const DevBatch &B, int n_ext, RunOpts o, cudaStream_t st);
+void launch_extract_fill(const DevBatch &B, int n_ext, RunOpts o, cudaStream_t st);
+int scan_num_blocks(int64_t nwords);
+void launch_word_scan(const DevBatch &B, int64_t nwords, int *block_sums, int *total_out, cudaStream_t st);
+
+// score_kernels.cu
+void launch_node_prep(const DevBatch &B, int n_ext, int total_nodes, int seq_parts, cudaStream_t st);
+void launch_score_chains(const DevBatch &B, const DevModel *models, int n_chains, int64_t total_chain_nodes,
+                         RunOpts o, void *mot_out, cudaStream_t st);
+void launch_overlap(const DevBatch &B, const DevModel *models, int n_chains, int64_t total_chain_nodes, RunOpts o,
+                    int flag, cudaStream_t st);
+void launch_opv(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, cudaStream_t st);
+void launch_pairs(const DevBatch &B, int n_ext, int total_nodes, unsigned long long *ext_pairs, cudaStream_t st);
+
+// dp_kernels.cu
+void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, int n_chains, int final,
+               cudaStream_t st);
+void launch_trace(const DevBatch &B, const DevModel *models, int n_contigs, const int32_t *contig_chain_begin,
+                  int32_t *tracef, uint8_t *elim, pgpu_gene *genes, const int64_t *gene_off,
+                  pgpu_contig_summary *summary, int32_t *winner_chain, int meta, int max_overlap, cudaStream_t st);
+void launch_pack_nodes(const DevBatch &B, int n_chains, int64_t total, const void *mot, const int32_t *tracef,
+                       const uint8_t *elim, int dp_state, pgpu_node *out, cudaStream_t st);
+void launch_pack_gene_nodes(int n_contigs, const pgpu_contig_summary *summary, const pgpu_gene *genes,
+                            const int64_t *gene_off, const int64_t *gene_out_off, const int64_t *node_out_off,
+                            const pgpu_node *nodes, pgpu_node *out, pgpu_gene *genes_out, cudaStream_t st);
+void launch_skippable(int n, const int8_t *strand, const uint8_t *type, const int32_t *ndx, int mn, int i,
+                      uint8_t *skip, cudaStream_t st);
+void launch_build_final_chains(const DevBatch &B, int n_contigs, const int32_t *winner_chain, const int64_t *fin_coff,
+                               ChainInfo *fin_chains, cudaStream_t st);
+
+}  // namespace pgpu

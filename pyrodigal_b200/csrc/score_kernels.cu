@@ -1,0 +1,609 @@
+// score_kernels.cu -- per-node scoring (score_nodes family) and overlapping-start bookkeeping.
+//
+// Reference semantics: Nodes._calc_orf_gc (lib.pyx:1846-1896), _raw_coding_score (2119-2239),
+// _rbs_score + Sequence._shine_dalgarno_exact/_mm (2241-2277, 791-979), Node._find_best_upstream_motif
+// (1557-1616), _score_upstream_composition (1619-1650), Nodes._score (2331-2487),
+// Nodes._record_overlapping_starts (2279-2329), BaseConnectionScorer._index / window logic (1126-1162,
+// 1224-1233).
+//
+// B200 design notes
+//  * every ORF (stop-to-stop segment of one strand/frame) is an independent unit: the reference's three
+//    sequential sweeps over all nodes reset their state at every STOP node, so one thread per STOP node
+//    reproduces the exact summation order (bit-identical doubles) while exposing 10^4..10^6-way
+//    parallelism per batch.
+//  * dicodon indices slide over the 1-byte codon-code array (one load per codon).
+//  * the Shine-Dalgarno search is table driven: the motif found for a 6-base window depends only on the
+//    window's A/G match pattern and its distance to the start, so a per-model 15x64 byte table (built on
+//    the host) replaces the nested loops; the per-node 32-bit A/G pattern is model independent.
+//  * log/pow of the length factor come from a host table (host libm == the reference's libm).
+#include "kernels.cuh"
+
+namespace pgpu {
+
+__device__ __forceinline__ int find_chain(const ChainInfo *__restrict__ ch, int n, int64_t g) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (ch[mid].coff <= g) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+__device__ __forceinline__ int find_ext(const ExtractInfo *__restrict__ ex, int n, int g) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (ex[mid].node_off <= g) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// GC count of the three bases starting at p, from the codon code (N counts as GC: _sequence.h:35-43;
+// padding beyond the sequence end is 'A').
+__device__ __forceinline__ int gc3(int code) {
+    int b0 = code & 3, b1 = (code >> 2) & 3, b2 = (code >> 4) & 3;
+    return ((b0 ^ (b0 >> 1)) & 1) + ((b1 ^ (b1 >> 1)) & 1) + ((b2 ^ (b2 >> 1)) & 1);
+}
+
+// strand-oriented 2-bit base for k-mer indices (_sequence.h:207-220): N -> C on both strands
+__device__ __forceinline__ int mer_base(const uint8_t *__restrict__ d, int slen, int x, bool rev) {
+    if (!rev) return d[x] & 3;
+    int b = d[slen - 1 - x];
+    return b == 6 ? 2 : (b ^ 3);
+}
+
+// code of the reverse-strand codon whose 5' base is at forward position p (bases p, p-1, p-2)
+__device__ __forceinline__ int rcode_at(const uint8_t *__restrict__ d, const uint8_t *__restrict__ cod, int p) {
+    int c = cod[p - 2];
+    if (!(c & 64)) return rev_code(c & 63);
+    int r = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        int b = d[p - k];
+        r |= (b == 6 ? 2 : (b ^ 3)) << (2 * k);
+    }
+    return r;
+}
+
+// --------------------------------------------------------------------------------------------------
+// per-extraction preparation: gc_cont, SD match bits, DP window start
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_node_prep(DevBatch B, int n_ext, int total_nodes, int seq_parts) {
+    __shared__ int s_first;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x == 0) s_first = find_ext(B.exts, n_ext, min(blockIdx.x * blockDim.x, total_nodes - 1));
+    __syncthreads();
+    if (g >= total_nodes) return;
+    int e = s_first;
+    while (e + 1 < n_ext && B.exts[e + 1].node_off <= g) e++;
+    const ExtractInfo X = B.exts[e];
+    const int z = g - X.node_off, nn = X.nn, slen = X.slen;
+    const int32_t *__restrict__ ndx = B.ndx + X.node_off;
+    const int32_t *__restrict__ sv = B.stop_val + X.node_off;
+    const uint8_t *__restrict__ cls = B.cls + X.node_off;
+    const uint8_t *__restrict__ d = B.digits + X.doff;
+    const uint8_t *__restrict__ cod = B.cod + X.doff;
+    const int c = cls[z], kind = cls_kind(c), f = cls_frame(c), my = ndx[z];
+
+    // ---- DP window start (lib.pyx:1224-1233) ----
+    {
+        int m = z < kMaxNodeDist ? 0 : z - kMaxNodeDist;
+        if ((kind == K_RS || kind == K_FE) && ndx[m] > sv[z]) {
+            // highest index whose ndx == stop_val, or 0 (binary search instead of the reference's walk)
+            const int target = sv[z];
+            int lo = 0, hi = m;  // first index with ndx > target in [0, m]
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (ndx[mid] > target) hi = mid; else lo = mid + 1;
+            }
+            m = (lo > 0 && ndx[lo - 1] == target) ? lo - 1 : 0;
+        }
+        B.win_min[X.node_off + z] = m < kMaxNodeDist ? 0 : m - kMaxNodeDist;
+    }
+    if (!seq_parts) return;  // operator-level DP: nodes supplied by the caller, no sequence
+
+    if (kind == K_FS || kind == K_RS) {
+        // ---- upstream A/G pattern for the SD search: bit k = A at start-20+k, bit 16+k = G ----
+        const bool rev = kind == K_RS;
+        const int start = rev ? slen - 1 - my : my;
+        uint32_t bits = 0;
+#pragma unroll 4
+        for (int k = 0; k < 16; k++) {
+            int x = start - 20 + k;
+            if (x < 0 || x >= slen) continue;
+            int b = rev ? d[slen - 1 - x] : d[x];
+            if (b == (rev ? 3 : 0)) bits |= 1u << k;
+            if (b == (rev ? 2 : 1)) bits |= 1u << (16 + k);
+        }
+        B.sdbits[X.node_off + z] = bits;
+        return;
+    }
+
+    // ---- gc_cont of every start of this ORF (lib.pyx:1846-1896) ----
+    if (kind == K_FE) {
+        int gc = gc3(cod[my] & 63), last = my;
+        for (int i = z - 1; i >= 0; i--) {
+            int ci = cls[i];
+            if ((ci & CLS_REV) || cls_frame(ci) != f) continue;
+            if (cls_is_stop(ci)) break;
+            const int ni = ndx[i];
+            for (int j = last - 3; j >= ni; j -= 3) gc += gc3(cod[j] & 63);
+            B.gc_cont[X.node_off + i] = (float)((double)gc / (abs(sv[i] - ni) + 3.0));
+            last = ni;
+        }
+    } else {
+        int gc = my >= 2 ? gc3(cod[my - 2] & 63) : 0, last = my;
+        if (my < 2) for (int k = my; k > my - 3; k--) if (k >= 0) { int b = d[k]; gc += (b != 0 && b != 3); }
+        for (int i = z + 1; i < nn; i++) {
+            int ci = cls[i];
+            if (!(ci & CLS_REV) || cls_frame(ci) != f) continue;
+            if (cls_is_stop(ci)) break;
+            const int ni = ndx[i];
+            // window starts at j (two bases right of the codon), bounds-guarded: lib.pyx:1887-1890
+            for (int j = last + 3; j <= ni; j += 3) gc += gc3(cod[j] & 63);
+            B.gc_cont[X.node_off + i] = (float)((double)gc / (abs(sv[i] - ni) + 3.0));
+            last = ni;
+        }
+    }
+}
+
+// per-class ranks and class-sorted index lists (SoA replacement of ConnectionScorer._index,
+// lib.pyx:1126-1162): one warp per extraction
+__global__ void __launch_bounds__(128) k_class_index(DevBatch B, int n_ext) {
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (e >= n_ext) return;
+    const ExtractInfo X = B.exts[e];
+    const uint8_t *__restrict__ cls = B.cls + X.node_off;
+    int32_t *crank = B.crank + 4 * (int64_t)X.node_off;
+    int32_t *clist = B.clist + X.node_off;
+    const uint32_t lt = (1u << lane) - 1u;
+    int tot[4] = {0, 0, 0, 0};
+    for (int base = 0; base < X.nn; base += 32) {
+        int i = base + lane;
+        int k = i < X.nn ? cls_kind(cls[i]) : -1;
+#pragma unroll
+        for (int c = 0; c < 4; c++) tot[c] += __popc(__ballot_sync(0xffffffffu, k == c));
+    }
+    int cb[4] = {0, tot[0], tot[0] + tot[1], tot[0] + tot[1] + tot[2]};
+    if (lane < 4) B.cbase[4 * e + lane] = cb[lane];
+    int run[4] = {0, 0, 0, 0};
+    for (int base = 0; base < X.nn; base += 32) {
+        int i = base + lane;
+        int k = i < X.nn ? cls_kind(cls[i]) : -1;
+        int r[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint32_t m = __ballot_sync(0xffffffffu, k == c);
+            r[c] = run[c] + __popc(m & lt);
+            run[c] += __popc(m);
+        }
+        if (i < X.nn) {
+            *reinterpret_cast<int4 *>(crank + 4 * (int64_t)i) = make_int4(r[0], r[1], r[2], r[3]);
+            clist[cb[k] + r[k]] = i;
+        }
+    }
+    // sentinel rank row (index nn) is not needed: the DP reads crank[i] for i < nn only
+}
+
+// --------------------------------------------------------------------------------------------------
+// raw coding score: one thread per STOP node (= per ORF)
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_coding(DevBatch B, const DevModel *__restrict__ models, int n_chains,
+                                                 int64_t total) {
+    __shared__ int s_first;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x == 0) s_first = find_chain(B.chains, n_chains, min((int64_t)blockIdx.x * blockDim.x, total - 1));
+    __syncthreads();
+    if (g >= total) return;
+    int k = s_first;
+    while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
+    const ChainInfo C = B.chains[k];
+    const int z = (int)(g - C.coff);
+    if (z >= C.nn) return;  // unused tail of a fixed-capacity slot (final re-scoring pass)
+    const uint8_t *__restrict__ cls = B.cls + C.node_off;
+    const int c = cls[z];
+    if (!cls_is_stop(c)) return;
+    const DevModel &M = models[C.model];
+    const double *__restrict__ dc = M.gene_dc;
+    const int32_t *__restrict__ ndx = B.ndx + C.node_off;
+    const int32_t *__restrict__ sv = B.stop_val + C.node_off;
+    const uint8_t *__restrict__ d = B.digits + C.doff;
+    const uint8_t *__restrict__ cod = B.cod + C.doff;
+    double *__restrict__ cscore = B.cscore + C.coff;
+    const int f = cls_frame(c), my = ndx[z], nn = C.nn;
+    const bool rev = c & CLS_REV;
+
+    // sweep A: dicodon log-odds accumulated from the stop towards each start (lib.pyx:2149-2173)
+    int far = -1, last = my;
+    double acc = 0.0;
+    if (!rev) {
+        int low = cod[my] & 63;
+        for (int i = z - 1; i >= 0; i--) {
+            int ci = cls[i];
+            if ((ci & CLS_REV) || cls_frame(ci) != f) continue;
+            if (cls_is_stop(ci)) break;
+            const int ni = ndx[i];
+            for (int j = last - 3; j >= ni; j -= 3) {
+                int cj = cod[j] & 63;
+                acc += __ldg(&dc[cj | (low << 6)]);
+                low = cj;
+            }
+            cscore[i] = acc;
+            last = ni;
+            far = i;
+        }
+    } else {
+        int low = rcode_at(d, cod, my);
+        for (int i = z + 1; i < nn; i++) {
+            int ci = cls[i];
+            if (!(ci & CLS_REV) || cls_frame(ci) != f) continue;
+            if (cls_is_stop(ci)) break;
+            const int ni = ndx[i];
+            for (int j = last + 3; j <= ni; j += 3) {
+                int cj = rcode_at(d, cod, j);
+                acc += __ldg(&dc[cj | (low << 6)]);
+                low = cj;
+            }
+            cscore[i] = acc;
+            last = ni;
+            far = i;
+        }
+    }
+    if (far < 0) return;
+
+    // sweep B: the two penalty passes fused, walking back towards the stop (lib.pyx:2175-2236)
+    double s2 = -10000.0, s3 = -10000.0;
+    const int step = rev ? -1 : 1;
+    for (int i = far; i != z; i += step) {
+        int ci = cls[i];
+        if (((ci & CLS_REV) != 0) != rev || cls_frame(ci) != f) continue;
+        double cs = cscore[i];
+        if (cs > s2) s2 = cs; else cs -= (s2 - cs);
+        const double gsize = rev ? (((double)ndx[i] - sv[i]) + 3.0) / 3.0 : (((double)sv[i] - ndx[i]) + 3.0) / 3.0;
+        double lfac;
+        if (gsize > 1000.0) lfac = M.lfac_span * (gsize - 80) / 920.0;
+        else lfac = M.lfac[(int)gsize];
+        if (lfac > s3) s3 = lfac; else lfac -= fmax(fmin(s3 - lfac, lfac), 0.0);
+        if (lfac > 3.0 && cs < 0.5 * lfac) cs = 0.5 * lfac;
+        cs += lfac;
+        cscore[i] = cs;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// start scoring: RBS / upstream motif / type / upstream composition / penalties (lib.pyx:2331-2487)
+// --------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel *__restrict__ models, int n_chains,
+                                                      int64_t total, RunOpts o, MotifOut *__restrict__ mot_out) {
+    __shared__ int s_first;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x == 0) s_first = find_chain(B.chains, n_chains, min((int64_t)blockIdx.x * blockDim.x, total - 1));
+    __syncthreads();
+    if (g >= total) return;
+    int k = s_first;
+    while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
+    const ChainInfo C = B.chains[k];
+    const int i = (int)(g - C.coff);
+    if (i >= C.nn) return;
+    const uint8_t *__restrict__ cls = B.cls + C.node_off;
+    const int c = cls[i];
+    if (cls_is_stop(c)) {
+        // STOP nodes keep the reset state (node.c:176-197)
+        B.cscore[g] = 0.0; B.sscore[g] = 0.0; B.rscore[g] = 0.0; B.uscore[g] = 0.0; B.tscore[g] = 0.0;
+        B.rbs[2 * g] = 0; B.rbs[2 * g + 1] = 0;
+        if (mot_out) { MotifOut m = {}; mot_out[g] = m; }
+        return;
+    }
+    const DevModel &M = models[C.model];
+    const int32_t *__restrict__ ndxa = B.ndx + C.node_off;
+    const int32_t *__restrict__ sva = B.stop_val + C.node_off;
+    const uint8_t *__restrict__ d = B.digits + C.doff;
+    const uint8_t *__restrict__ cod = B.cod + C.doff;
+    const int slen = C.slen, nn = C.nn, ndx = ndxa[i], stop_val = sva[i];
+    const bool rev = c & CLS_REV;
+    const int type = c & CLS_TYPE;
+    const int edge_mask_now = C.first_pass ? CLS_EDGE : (CLS_EDGE | CLS_CONV);
+    bool edge = (c & edge_mask_now) != 0;
+    const int start = rev ? slen - 1 - ndx : ndx;
+    const double st_wt = M.st_wt;
+
+    int rbs0 = 0, rbs1 = 0;
+    MotifOut mot = {};
+    if (!edge) {
+        if (M.uses_sd) {
+            // table-driven Shine-Dalgarno search (lib.pyx:2241-2277 + 791-979)
+            const uint32_t bits = B.sdbits[C.node_off + i];
+            const uint32_t A = bits & 0xffffu, G = bits >> 16;
+            const int omin = rev ? 0 : max(0, 20 - start);  // forward skips negative offsets only
+            for (int off = omin; off < 15; off++) {
+                const uint32_t gp = ((A >> off) & 0x09u) | ((G >> off) & 0x36u);
+                int e = M.sd_best[0][off][gp], m = M.sd_best[1][off][gp];
+                rbs0 = max(rbs0, e);
+                rbs1 = max(rbs1, m);
+            }
+        } else {
+            // best upstream motif, stage 2 (lib.pyx:1557-1616)
+            uint64_t U = 0;
+            for (int q = 0; q < 18; q++) {
+                int x = start - 21 + q;
+                if (x >= 0 && x < slen) U |= (uint64_t)mer_base(d, slen, x, rev) << (2 * q);
+            }
+            int max_spacer = 0, max_spacendx = 0, max_len = 0, max_ndx = 0;
+            double max_sc = -100.0;
+            for (int l = 3; l >= 0; l--) {
+                for (int j = start - 18 - l; j <= start - 6 - l; j++) {
+                    if (j < 0) continue;
+                    int spacendx;
+                    if (j <= start - 16 - l) spacendx = 3;
+                    else if (j <= start - 14 - l) spacendx = 2;
+                    else if (j >= start - 7 - l) spacendx = 1;
+                    else spacendx = 0;
+                    const int index = (int)((U >> (2 * (j - (start - 21)))) & ((1u << (2 * (l + 3))) - 1u));
+                    const double sc = __ldg(&M.mot_wt[(l * 4 + spacendx) * 4096 + index]);
+                    if (sc > max_sc) {
+                        max_sc = sc; max_spacendx = spacendx; max_spacer = start - j - l - 3;
+                        max_ndx = index; max_len = l + 3;
+                    }
+                }
+            }
+            if (max_sc == -4.0 || max_sc < M.no_mot + 0.69) {
+                mot.score = M.no_mot;
+            } else {
+                mot.ndx = (uint16_t)max_ndx; mot.len = (uint8_t)max_len; mot.spacendx = (uint8_t)max_spacendx;
+                mot.spacer = (uint8_t)max_spacer; mot.score = max_sc;
+            }
+        }
+    }
+
+    const int orf_length = abs(ndx - stop_val);
+    int edge_gene = edge ? 1 : 0;
+    {
+        // does the ORF run off the edge?  (is the "stop" a real stop codon)
+        int code;
+        bool has_n;
+        if (!rev) { int cc = cod[stop_val]; has_n = cc & 64; code = cc & 63; }
+        else { int cc = cod[stop_val - 2]; has_n = cc & 64; code = rev_code(cc & 63); }
+        if (has_n || !((M.stopmask >> code) & 1)) edge_gene++;
+    }
+    double cscore = B.cscore[g], tscore, uscore, rscore;
+    if (edge) {
+        tscore = PGPU_EDGE_BONUS * st_wt / edge_gene;
+        uscore = 0.0;
+        rscore = 0.0;
+    } else {
+        tscore = M.type_wt[type] * st_wt;
+        const double rbs1w = M.rbs_wt[rbs0], rbs2w = M.rbs_wt[rbs1];
+        const double sd_score = fmax(rbs1w, rbs2w) * st_wt;
+        if (M.uses_sd) {
+            rscore = sd_score;
+        } else {
+            rscore = st_wt * mot.score;
+            if (rscore < sd_score && M.no_mot > -0.5) rscore = sd_score;
+        }
+        // upstream composition (lib.pyx:1619-1650)
+        uscore = 0.0;
+        int count = 0;
+        for (int q = 1; q < 3 && q <= start; q++, count++) uscore += M.uc[count][mer_base(d, slen, start - q, rev)];
+        for (int q = 15; q < 45 && q <= start; q++, count++) uscore += M.uc[count][mer_base(d, slen, start - q, rev)];
+        // starts that would stop the gene from running off the edge (lib.pyx:2407-2422)
+        if (!o.closed && ndx <= 2 && !rev) {
+            uscore += PGPU_EDGE_UPS * st_wt;
+        } else if (!o.closed && ndx >= slen - 3 && rev) {
+            uscore += PGPU_EDGE_UPS * st_wt;
+        } else if (i < 500 && !rev) {
+            // nodes before i already carry their converted edge flag in this sweep
+            for (int j = i - 1; j >= 0; j--)
+                if ((cls[j] & (CLS_EDGE | CLS_CONV)) && stop_val == sva[j]) { uscore += PGPU_EDGE_UPS * st_wt; break; }
+        } else if (i + 500 >= nn && rev) {
+            // nodes after i still carry the flag of the previous sweep
+            for (int j = i + 1; j < nn; j++)
+                if ((cls[j] & edge_mask_now) && stop_val == sva[j]) { uscore += PGPU_EDGE_UPS * st_wt; break; }
+        }
+    }
+    // convert starts at the first/last bases into edge nodes (lib.pyx:2424-2434)
+    if (!o.closed && !edge && ((ndx <= 2 && !rev) || (ndx >= slen - 3 && rev))) {
+        edge_gene++;
+        edge = true;
+        tscore = 0.0;
+        uscore = PGPU_EDGE_BONUS * st_wt / edge_gene;
+        rscore = 0.0;
+    }
+    if (!edge && edge_gene == 1) uscore -= 0.5 * PGPU_EDGE_BONUS * st_wt;
+    if (edge_gene == 0 && orf_length < 250) {
+        const double negf = 250.0 / (float)orf_length, posf = (float)orf_length / 250.0;
+        rscore *= rscore < 0 ? negf : posf;
+        uscore *= uscore < 0 ? negf : posf;
+        tscore *= tscore < 0 ? negf : posf;
+    }
+    if (C.is_meta && slen < 3000 && edge_gene == 0 && (cscore < 5.0 || orf_length < 120))
+        cscore -= PGPU_META_PEN * fmax(0.0, (3000.0 - slen) / 2700.0);
+    double sscore = tscore + rscore + uscore;
+    if (cscore < 0.0) {
+        if (edge_gene > 0 && !edge) {
+            if (!C.is_meta || slen > 1500) sscore -= st_wt;
+            else sscore -= 10.31 - 0.004 * slen;
+        } else if (C.is_meta && slen < 3000 && edge) {
+            const double min_meta_len = sqrt((double)slen) * 5.0;
+            if (orf_length >= min_meta_len) {
+                if (cscore >= 0) cscore = -1.0;
+                sscore = 0.0;
+                uscore = 0.0;
+            }
+        } else {
+            sscore -= 0.5;
+        }
+    } else if (C.is_meta && cscore < 5.0 && orf_length < 120 && sscore < 0.0) {
+        sscore -= st_wt;
+    }
+    B.cscore[g] = cscore; B.sscore[g] = sscore; B.rscore[g] = rscore; B.uscore[g] = uscore; B.tscore[g] = tscore;
+    B.rbs[2 * g] = (uint8_t)rbs0; B.rbs[2 * g + 1] = (uint8_t)rbs1;
+    if (mot_out) mot_out[g] = mot;
+}
+
+// --------------------------------------------------------------------------------------------------
+// overlapping starts (lib.pyx:2279-2329) + operon values for the DP
+// --------------------------------------------------------------------------------------------------
+struct NodeView {
+    int ndx, strand;
+    double rscore, uscore;
+};
+
+// _connection.h:52-78
+__device__ __forceinline__ double igm_same(const NodeView &n1, const NodeView &n2, const DevModel &M) {
+    const int dist = abs(n1.ndx - n2.ndx);
+    const bool overlap = n1.ndx + 2 * n1.strand >= n2.ndx;
+    double r = 0.0;
+    if (n1.ndx + 2 == n2.ndx || n1.ndx == n2.ndx + 1) {
+        const NodeView &s = n1.strand == 1 ? n2 : n1;
+        if (s.rscore < 0) r -= s.rscore;
+        if (s.uscore < 0) r -= s.uscore;
+    }
+    if (dist > 3 * kOperDist) r -= 0.15 * M.st_wt;
+    else if ((dist <= kOperDist && !overlap) || dist * 4 < kOperDist) r += (2.0 - ((double)dist / kOperDist)) * 0.15 * M.st_wt;
+    return r;
+}
+
+// cs[n3] + intergenic_mod for the start n3 recorded in star_ptr of STOP node z:
+// forward STOP: _connection.h:189 (n1 = z, n3);  reverse STOP: _connection.h:320,329,354 (n3, n2 = z)
+__device__ __forceinline__ double operon_value(int cz, int z, int s, const uint8_t *__restrict__ cls,
+                                               const int32_t *__restrict__ ndx, const double *__restrict__ cscore,
+                                               const double *__restrict__ sscore, const double *__restrict__ rscore,
+                                               const double *__restrict__ uscore, const DevModel &M) {
+    const int cs_ = cls[s];
+    const double base = cscore[s] + sscore[s];
+    if (((cz ^ cs_) & CLS_REV) != 0) return base + M.ig_neg;
+    NodeView a = {ndx[z], (cz & CLS_REV) ? -1 : 1, rscore[z], uscore[z]};
+    NodeView b = {ndx[s], (cs_ & CLS_REV) ? -1 : 1, rscore[s], uscore[s]};
+    return (cz & CLS_REV) ? base + igm_same(b, a, M) : base + igm_same(a, b, M);
+}
+
+__global__ void __launch_bounds__(128) k_overlap(DevBatch B, const DevModel *__restrict__ models, int n_chains,
+                                                  int64_t total, RunOpts o, int flag) {
+    __shared__ int s_first;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x == 0) s_first = find_chain(B.chains, n_chains, min((int64_t)blockIdx.x * blockDim.x, total - 1));
+    __syncthreads();
+    if (g >= total) return;
+    int k = s_first;
+    while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
+    const ChainInfo C = B.chains[k];
+    const int i = (int)(g - C.coff), nn = C.nn;
+    if (i >= nn) return;
+    const uint8_t *__restrict__ cls = B.cls + C.node_off;
+    const int32_t *__restrict__ ndx = B.ndx + C.node_off;
+    const int32_t *__restrict__ sv = B.stop_val + C.node_off;
+    const double *__restrict__ cscore = B.cscore + C.coff;
+    const double *__restrict__ sscore = B.sscore + C.coff;
+    const double *__restrict__ rscore = B.rscore + C.coff;
+    const double *__restrict__ uscore = B.uscore + C.coff;
+    const DevModel &M = models[C.model];
+    int sp[3] = {-1, -1, -1};
+    const int c = cls[i];
+    if (cls_is_stop(c) && !(c & CLS_EDGE)) {
+        const int my = ndx[i];
+        double max_sc = -100.0;
+        if (!(c & CLS_REV)) {
+            NodeView me = {my, 1, 0.0, 0.0};
+            for (int j = i + 3; j >= 0; j--) {
+                if (j >= nn || ndx[j] > my + 2) continue;
+                if (ndx[j] + o.max_overlap < my) break;
+                const int cj = cls[j];
+                if ((cj & CLS_REV) || cls_is_stop(cj)) continue;
+                if (sv[j] <= my) continue;
+                const int f = ndx[j] % 3;
+                if (flag == 0) {
+                    if (sp[f] == -1) sp[f] = j;
+                } else {
+                    NodeView st = {ndx[j], 1, rscore[j], uscore[j]};
+                    const double sc = cscore[j] + sscore[j] + igm_same(me, st, M);
+                    if (sc > max_sc) { sp[f] = j; max_sc = sc; }
+                }
+            }
+        } else {
+            NodeView me = {my, -1, 0.0, 0.0};
+            for (int j = i - 3; j < nn; j++) {
+                if (j < 0 || ndx[j] < my - 2) continue;
+                if (ndx[j] - o.max_overlap > my) break;
+                const int cj = cls[j];
+                if (!(cj & CLS_REV) || cls_is_stop(cj)) continue;
+                if (sv[j] >= my) continue;
+                const int f = ndx[j] % 3;
+                if (flag == 0) {
+                    if (sp[f] == -1) sp[f] = j;
+                } else {
+                    NodeView st = {ndx[j], -1, rscore[j], uscore[j]};
+                    const double sc = cscore[j] + sscore[j] + igm_same(st, me, M);
+                    if (sc > max_sc) { sp[f] = j; max_sc = sc; }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+        B.star_ptr[3 * g + f] = sp[f];
+        B.opv[3 * g + f] = sp[f] == -1 ? 0.0 : operon_value(c, i, sp[f], cls, ndx, cscore, sscore, rscore, uscore, M);
+    }
+}
+
+// operon values for caller-supplied star_ptr (operator-level pgpu_score_connections)
+__global__ void __launch_bounds__(128) k_opv(DevBatch B, const DevModel *__restrict__ models, int n_chains, int64_t total) {
+    __shared__ int s_first;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x == 0) s_first = find_chain(B.chains, n_chains, min((int64_t)blockIdx.x * blockDim.x, total - 1));
+    __syncthreads();
+    if (g >= total) return;
+    int k = s_first;
+    while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
+    const ChainInfo C = B.chains[k];
+    const int i = (int)(g - C.coff);
+    if (i >= C.nn) return;
+    const uint8_t *__restrict__ cls = B.cls + C.node_off;
+    const int c = cls[i];
+#pragma unroll
+    for (int f = 0; f < 3; f++) {
+        const int s = B.star_ptr[3 * g + f];
+        B.opv[3 * g + f] = (s < 0 || s >= C.nn || !cls_is_stop(c)) ? 0.0
+            : operon_value(c, i, s, cls, B.ndx + C.node_off, B.cscore + C.coff, B.sscore + C.coff, B.rscore + C.coff,
+                           B.uscore + C.coff, models[C.model]);
+    }
+}
+
+// node pairs of an extraction: sum_i (i - min_i)  (implementation independent)
+__global__ void __launch_bounds__(256) k_pairs(DevBatch B, int n_ext, int total_nodes, unsigned long long *ext_pairs) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_nodes) return;
+    const int e = find_ext(B.exts, n_ext, g);
+    const int z = g - B.exts[e].node_off;
+    atomicAdd(&ext_pairs[e], (unsigned long long)(z - B.win_min[g]));
+}
+
+// --------------------------------------------------------------------------------------------------
+// launch wrappers
+// --------------------------------------------------------------------------------------------------
+void launch_node_prep(const DevBatch &B, int n_ext, int total_nodes, int seq_parts, cudaStream_t st) {
+    if (n_ext == 0) return;
+    if (total_nodes > 0) k_node_prep<<<(total_nodes + 127) / 128, 128, 0, st>>>(B, n_ext, total_nodes, seq_parts);
+    k_class_index<<<(n_ext * 32 + 127) / 128, 128, 0, st>>>(B, n_ext);
+}
+void launch_score_chains(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o,
+                         void *mot_out, cudaStream_t st) {
+    if (n_chains == 0 || total == 0) return;
+    const unsigned nb = (unsigned)((total + 127) / 128);
+    k_coding<<<nb, 128, 0, st>>>(B, models, n_chains, total);
+    k_start_score<<<nb, 128, 0, st>>>(B, models, n_chains, total, o, (MotifOut *)mot_out);
+}
+void launch_opv(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, cudaStream_t st) {
+    if (n_chains == 0 || total == 0) return;
+    k_opv<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total);
+}
+void launch_pairs(const DevBatch &B, int n_ext, int total_nodes, unsigned long long *ext_pairs, cudaStream_t st) {
+    if (n_ext == 0 || total_nodes == 0) return;
+    k_pairs<<<(total_nodes + 255) / 256, 256, 0, st>>>(B, n_ext, total_nodes, ext_pairs);
+}
+void launch_overlap(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o, int flag,
+                    cudaStream_t st) {
+    if (n_chains == 0 || total == 0) return;
+    k_overlap<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total, o, flag);
+}
+
+}  // namespace pgpu

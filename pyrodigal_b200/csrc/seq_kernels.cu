@@ -1,0 +1,280 @@
+// seq_kernels.cu -- sequence encoding and node extraction (add_nodes) on the device.
+//
+// Reference semantics: Sequence._build / _mask (src/pyrodigal/lib.pyx:664-713), Nodes._extract
+// (lib.pyx:1905-2117) + Nodes._sort (lib.pyx:2489, node.c:1578-1587).
+//
+// B200 design: the sequence is streamed once (encode: 1 B in, 2 B out per base, 16-byte stores); node
+// extraction is a backward scan per (contig, strand, frame) over the 1-byte codon-code array that first
+// marks node positions in two bitmaps, a prefix sum over bitmap words then gives every node its final
+// rank in (ndx, strand) order, and a second scan writes the nodes straight into their sorted slots --
+// no sort pass and no per-node atomics.
+#include "kernels.cuh"
+
+namespace pgpu {
+
+// --------------------------------------------------------------------------------------------------
+// encode: ASCII -> digits (A0 G1 C2 T3 N6) + codon codes; per-contig G/C and unknown counts
+// --------------------------------------------------------------------------------------------------
+constexpr int kTile = 4096;
+
+__device__ __forceinline__ uint8_t encode_base(uint8_t a) {
+    switch (a) {
+    case 'A': case 'a': return 0;
+    case 'G': case 'g': return 1;
+    case 'C': case 'c': return 2;
+    case 'T': case 't': return 3;
+    default: return 6;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_encode(DevBatch B, const int2 *__restrict__ tiles) {
+    __shared__ __align__(16) uint8_t s[kTile + 16];
+    const int2 tile = tiles[blockIdx.x];
+    const ContigInfo ci = B.contigs[tile.x];
+    const int start = tile.y;
+    const int n = min(kTile, ci.slen - start);
+    const uint8_t *src = B.ascii + ci.aoff + start;
+    for (int k = threadIdx.x; k < kTile + 16; k += 256)
+        s[k] = (k < n + 2 && start + k < ci.slen) ? encode_base(src[k]) : 0;
+    __syncthreads();
+    const int k0 = threadIdx.x * 16;
+    int gc = 0, unk = 0;
+    if (k0 < n) {
+        uint32_t d[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            int p = k0 + k;
+            if (p < n) {
+                uint32_t b0 = s[p], b1 = s[p + 1], b2 = s[p + 2];
+                gc += (b0 == 1) | (b0 == 2);
+                unk += (b0 == 6);
+                uint32_t code = (b0 & 3) | ((b1 & 3) << 2) | ((b2 & 3) << 4) | (((b0 | b1 | b2) & 4) << 4);
+                d[k >> 2] |= b0 << ((k & 3) * 8);
+                c[k >> 2] |= code << ((k & 3) * 8);
+            }
+        }
+        const int64_t o = ci.doff + start + k0;
+        *reinterpret_cast<uint4 *>(B.digits + o) = make_uint4(d[0], d[1], d[2], d[3]);
+        *reinterpret_cast<uint4 *>(B.cod + o) = make_uint4(c[0], c[1], c[2], c[3]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        gc += __shfl_down_sync(0xffffffffu, gc, off);
+        unk += __shfl_down_sync(0xffffffffu, unk, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (gc) atomicAdd(&B.gc_count[tile.x], gc);
+        if (unk) atomicAdd(&B.unknown[tile.x], unk);
+    }
+}
+
+// runs of N: one thread per run start walks to the end of its run (lib.pyx:699-713)
+__global__ void k_find_masks(DevBatch B, const int2 *__restrict__ tiles, int min_mask, int4 *out, int cap,
+                             int *count) {
+    const int2 tile = tiles[blockIdx.x];
+    const ContigInfo ci = B.contigs[tile.x];
+    const uint8_t *d = B.digits + ci.doff;
+    for (int k = threadIdx.x; k < kTile; k += blockDim.x) {
+        int p = tile.y + k;
+        if (p >= ci.slen) break;
+        if (d[p] != 6 || (p > 0 && d[p - 1] == 6)) continue;
+        int e = p + 1;
+        while (e < ci.slen && d[e] == 6) e++;
+        if (e - p >= min_mask || e == ci.slen) {
+            int slot = atomicAdd(count, 1);
+            if (slot < cap) out[slot] = make_int4(tile.x, p, e, 0);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// node extraction
+// --------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ bool masked_any(const int32_t *__restrict__ m, int n, int begin, int end) {
+    // masks are disjoint and sorted: first mask whose end is > begin, then test its begin (lib.pyx:337-340)
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (m[2 * mid + 1] > begin) hi = mid; else lo = mid + 1;
+    }
+    return lo < n && m[2 * lo] < end;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_extract(DevBatch B, int n_ext, RunOpts o) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_ext * 6) return;
+    const int e = t / 6, sf = t % 6, rev = sf / 3, f = sf % 3;
+    const ExtractInfo X = B.exts[e];
+    const int slen = X.slen;
+    if (slen < 3) return;
+    const uint8_t *__restrict__ cod = B.cod + X.doff;
+    uint32_t *bits = (rev ? B.bits_rev : B.bits_fwd) + X.woff;
+    const uint32_t *__restrict__ bf = B.bits_fwd + X.woff;
+    const uint32_t *__restrict__ br = B.bits_rev + X.woff;
+    const int32_t *__restrict__ wb = B.wordbase + X.woff;
+    const int32_t *__restrict__ masks = B.masks + 2 * (int64_t)X.mask_off;
+
+    auto emit = [&](int pos, int type, int sv, int edge) {
+        const int p = rev ? slen - 1 - pos : pos;
+        if (!FILL) {
+            atomicOr(&bits[p >> 5], 1u << (p & 31));
+        } else {
+            const int w = p >> 5, b = p & 31;
+            const uint32_t lt = (1u << b) - 1u;
+            int slot = wb[w] + __popc(bf[w] & lt) + __popc(br[w] & lt) + (rev ? (int)((bf[w] >> b) & 1u) : 0);
+            int conv = (!o.closed && type != 3 && !edge && (rev ? p >= slen - 3 : p <= 2)) ? CLS_CONV : 0;
+            B.ndx[slot] = p;
+            B.stop_val[slot] = rev ? slen - 1 - sv : sv;
+            B.cls[slot] = (uint8_t)(type | (rev ? CLS_REV : 0) | (edge ? CLS_EDGE : 0) | conv | ((p % 3) << CLS_FRAME_SHIFT));
+        }
+    };
+
+    // initial "last" of this frame: lib.pyx:1933-1939
+    int last = slen + ((f - slen % 3 + 3) % 3);
+    if (!o.closed)
+        while (last + 3 > slen) last -= 3;
+    bool last_real = false, saw = false;
+    int min_dist = o.min_edge_gene;
+    int i = slen - 3;
+    i -= ((i % 3) - f + 3) % 3;  // largest i <= slen-3 in this frame
+    for (; i >= 0; i -= 3) {
+        int c = rev ? cod[slen - 3 - i] : cod[i];
+        const bool has_n = c & 64;
+        c &= 63;
+        if (rev) c = rev_code(c);
+        if (!has_n && ((X.stopmask >> c) & 1)) {
+            if (saw) emit(last, 3, i, !last_real);
+            min_dist = o.min_gene;
+            last = i;
+            last_real = true;
+            saw = false;
+            continue;
+        }
+        if (last >= slen) continue;
+        if (X.n_masks) {
+            bool hit = rev ? masked_any(masks, X.n_masks, slen - last - 1, slen - i - 1)
+                           : masked_any(masks, X.n_masks, i, last);
+            if (hit) continue;
+        }
+        if (last - i + 3 >= min_dist && !has_n && ((X.startmask >> c) & 1)) {
+            const int b0 = c & 3;
+            emit(i, b0 == 0 ? 0 : (b0 == 1 ? 1 : 2), last, 0);
+            saw = true;
+        } else if (i <= 2 && !o.closed && last - i > o.min_edge_gene) {
+            emit(i, 0, last, 1);
+            saw = true;
+        }
+    }
+    if (saw) emit(last, 3, f - 6, !last_real);
+}
+
+// --------------------------------------------------------------------------------------------------
+// exclusive prefix sum of per-word node counts (three-phase: block sums, top scan, apply)
+// --------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanBlock = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
+    __shared__ int warp_sums[kScanThreads / 32];
+    __shared__ int block_total;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += y;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, wi, off);
+            if (lane >= off) wi += y;
+        }
+        if (lane < kScanThreads / 32) warp_sums[lane] = wi - w;
+        if (lane == kScanThreads / 32 - 1) block_total = wi;
+    }
+    __syncthreads();
+    int res = incl - v + warp_sums[wid];
+    *total = block_total;
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_count_words(const uint32_t *__restrict__ bf,
+                                                              const uint32_t *__restrict__ br, int64_t nwords,
+                                                              int *__restrict__ block_sums) {
+    const int64_t base = (int64_t)blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++)
+        if (base + k < nwords) s += __popc(bf[base + k]) + __popc(br[base + k]);
+    int total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_top(int *__restrict__ block_sums, int nblocks, int *total_out) {
+    int carry = 0;
+    for (int base = 0; base < nblocks; base += kScanThreads) {
+        int idx = base + threadIdx.x;
+        int v = idx < nblocks ? block_sums[idx] : 0;
+        int total;
+        int ex = block_exclusive_scan(v, &total);
+        if (idx < nblocks) block_sums[idx] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const uint32_t *__restrict__ bf,
+                                                             const uint32_t *__restrict__ br, int64_t nwords,
+                                                             const int *__restrict__ block_sums,
+                                                             int32_t *__restrict__ wordbase) {
+    const int64_t base = (int64_t)blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
+    int c[kScanItems], s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        c[k] = (base + k < nwords) ? __popc(bf[base + k]) + __popc(br[base + k]) : 0;
+        s += c[k];
+    }
+    int total;
+    int ex = block_exclusive_scan(s, &total) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        if (base + k <= nwords) wordbase[base + k] = ex;  // index nwords = sentinel (grand total)
+        ex += c[k];
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// launch wrappers
+// --------------------------------------------------------------------------------------------------
+void launch_encode(const DevBatch &B, const int2 *tiles, int n_tiles, cudaStream_t st) {
+    if (n_tiles > 0) k_encode<<<n_tiles, 256, 0, st>>>(B, tiles);
+}
+void launch_find_masks(const DevBatch &B, const int2 *tiles, int n_tiles, int min_mask, int4 *out, int cap,
+                       int *count, cudaStream_t st) {
+    if (n_tiles > 0) k_find_masks<<<n_tiles, 256, 0, st>>>(B, tiles, min_mask, out, cap, count);
+}
+void launch_extract_mark(const DevBatch &B, int n_ext, RunOpts o, cudaStream_t st) {
+    if (n_ext > 0) k_extract<false><<<(n_ext * 6 + 127) / 128, 128, 0, st>>>(B, n_ext, o);
+}
+void launch_extract_fill(const DevBatch &B, int n_ext, RunOpts o, cudaStream_t st) {
+    if (n_ext > 0) k_extract<true><<<(n_ext * 6 + 127) / 128, 128, 0, st>>>(B, n_ext, o);
+}
+int scan_num_blocks(int64_t nwords) { return (int)((nwords + 1 + kScanBlock - 1) / kScanBlock); }
+void launch_word_scan(const DevBatch &B, int64_t nwords, int *block_sums, int *total_out, cudaStream_t st) {
+    const int nb = scan_num_blocks(nwords);
+    k_count_words<<<nb, kScanThreads, 0, st>>>(B.bits_fwd, B.bits_rev, nwords, block_sums);
+    k_scan_top<<<1, kScanThreads, 0, st>>>(block_sums, nb, total_out);
+    k_scan_apply<<<nb, kScanThreads, 0, st>>>(B.bits_fwd, B.bits_rev, nwords, block_sums, B.wordbase);
+}
+
+}  // namespace pgpu

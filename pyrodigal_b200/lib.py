@@ -1,0 +1,622 @@
+"""Host-side mirror of the reference's public surface for the find_genes path.
+
+Same class names, constructor keywords, attributes and error behaviour as `pyrodigal.lib`
+(src/pyrodigal/lib.pyx; stubs src/pyrodigal/lib.pyi) for: GeneFinder.find_genes (+ the added batched
+find_genes_many), Genes, Gene, Nodes, Node, Sequence, Mask(s), TrainingInfo, MetagenomicBin(s) and
+lib.ConnectionScorer.  All computation happens in libpyrodigal_b200.so on the GPU through the C ABI
+(include/pyrodigal_b200.h); this module only marshals buffers and formats results.
+"""
+import json
+import lzma
+import math
+import os
+import threading
+import typing
+
+import numpy as np
+
+from . import _capi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+TRAINING_SIZE = _capi.TRAINING_SIZE
+MIN_SINGLE_GENOME = 20000
+IDEAL_SINGLE_GENOME = 100000
+TRANSLATION_TABLES = frozenset((1, 2, 3, 4, 5, 6, 9, 10, 11, 12, 13, 14, 15, 16, 21, 22, 23, 24, 25, 26, 29, 30, 32, 33))
+
+# lib.pyx:209-228
+_RBS_MOTIF = [None, "GGA/GAG/AGG", "3Base/5BMM", "4Base/6BMM", "AGxAG", "AGxAG", "GGA/GAG/AGG", "GGxGG", "GGxGG",
+              "AGxAG", "AGGAG(G)/GGAGG", "AGGA/GGAG/GAGG", "AGGA/GGAG/GAGG", "GGA/GAG/AGG", "GGxGG", "AGGA",
+              "GGAG/GAGG", "AGxAGG/AGGxGG", "AGxAGG/AGGxGG", "AGxAGG/AGGxGG", "AGGAG/GGAGG", "AGGAG", "AGGAG",
+              "GGAGG", "GGAGG", "AGGAGG", "AGGAGG", "AGGAGG"]
+_RBS_SPACER = [None, "3-4bp", "13-15bp", "13-15bp", "11-12bp", "3-4bp", "11-12bp", "11-12bp", "3-4bp", "5-10bp",
+               "13-15bp", "3-4bp", "11-12bp", "5-10bp", "5-10bp", "5-10bp", "5-10bp", "11-12bp", "3-4bp", "5-10bp",
+               "11-12bp", "3-4bp", "5-10bp", "3-4bp", "5-10bp", "11-12bp", "3-4bp", "5-10bp"]
+_NODE_TYPE = ["ATG", "GTG", "TTG", "Edge"]
+_LETTERS = "AGCTNNN"
+
+# field offsets inside `struct _training` (vendor/Prodigal/training.h:29-51)
+_T_DTYPE = np.dtype(
+    [("gc", "<f8"), ("trans_table", "<i4"), ("_p0", "<i4"), ("st_wt", "<f8"), ("bias", "<f8", (3,)),
+     ("type_wt", "<f8", (3,)), ("uses_sd", "<i4"), ("_p1", "<i4"), ("rbs_wt", "<f8", (28,)),
+     ("ups_comp", "<f8", (32, 4)), ("mot_wt", "<f8", (4, 4, 4096)), ("no_mot", "<f8"), ("gene_dc", "<f8", (4096,))]
+)
+assert _T_DTYPE.itemsize == TRAINING_SIZE
+
+
+# --- Training info ----------------------------------------------------------------------------------
+class TrainingInfo:
+    """Parameters of one model, stored in the reference's raw struct layout (lib.pyx:3898-4283)."""
+
+    def __init__(self, gc, *, translation_table=11, start_weight=4.35, bias=None, type_weights=None, uses_sd=True,
+                 rbs_weights=None, upstream_compositions=None, motif_weights=None, missing_motif_weight=0.0,
+                 coding_statistics=None):
+        if translation_table not in TRANSLATION_TABLES:
+            raise ValueError(f"{translation_table} is not a valid translation table index")
+        self._raw = np.zeros(1, dtype=_T_DTYPE)
+        r = self._raw[0]
+        r["gc"], r["trans_table"], r["st_wt"], r["uses_sd"], r["no_mot"] = gc, translation_table, start_weight, int(uses_sd), missing_motif_weight
+        for name, val in (("bias", bias), ("type_wt", type_weights), ("rbs_wt", rbs_weights),
+                          ("ups_comp", upstream_compositions), ("mot_wt", motif_weights), ("gene_dc", coding_statistics)):
+            if val is not None:
+                r[name] = np.asarray(val, dtype=np.float64).reshape(r[name].shape)
+
+    @classmethod
+    def _from_bytes(cls, raw):
+        if len(raw) != TRAINING_SIZE:
+            raise EOFError(f"Expected {TRAINING_SIZE} bytes, only read {len(raw)}")
+        self = cls.__new__(cls)
+        self._raw = np.frombuffer(bytes(raw), dtype=_T_DTYPE).copy()
+        return self
+
+    @classmethod
+    def load(cls, fp):
+        """Load a raw `struct _training` file as written by Prodigal / TrainingInfo.dump (lib.pyx:3911-3953)."""
+        return cls._from_bytes(fp.read(TRAINING_SIZE))
+
+    def dump(self, fp):
+        fp.write(self._raw.tobytes())
+
+    def __bytes__(self):
+        return self._raw.tobytes()
+
+    def __repr__(self):
+        return f"<pyrodigal_b200.TrainingInfo gc={self.gc!r} translation_table={self.translation_table!r}>"
+
+    def __getstate__(self):
+        return {"raw": self._raw.tobytes()}
+
+    def __setstate__(self, state):
+        self._raw = np.frombuffer(state["raw"], dtype=_T_DTYPE).copy()
+
+    def __eq__(self, other):
+        return isinstance(other, TrainingInfo) and self._raw.tobytes() == other._raw.tobytes()
+
+    def __hash__(self):
+        return hash(self._raw.tobytes()[:2048])
+
+    translation_table = property(lambda s: int(s._raw[0]["trans_table"]))
+    gc = property(lambda s: float(s._raw[0]["gc"]))
+    start_weight = property(lambda s: float(s._raw[0]["st_wt"]))
+    uses_sd = property(lambda s: bool(s._raw[0]["uses_sd"]))
+    missing_motif_weight = property(lambda s: float(s._raw[0]["no_mot"]))
+    bias = property(lambda s: s._raw[0]["bias"])
+    type_weights = property(lambda s: s._raw[0]["type_wt"])
+    rbs_weights = property(lambda s: s._raw[0]["rbs_wt"])
+    upstream_compositions = property(lambda s: s._raw[0]["ups_comp"])
+    motif_weights = property(lambda s: s._raw[0]["mot_wt"])
+    coding_statistics = property(lambda s: s._raw[0]["gene_dc"])
+
+
+class MetagenomicBin:
+    def __init__(self, training_info, description):
+        self.training_info = training_info
+        self.description = description
+
+    def __repr__(self):
+        return f"<pyrodigal_b200.MetagenomicBin description={self.description!r}>"
+
+    def __reduce__(self):
+        return type(self), (self.training_info, self.description)
+
+
+class MetagenomicBins(typing.Sequence):
+    def __init__(self, iterable):
+        self._bins = list(iterable)
+        self._blob = None
+
+    def __len__(self):
+        return len(self._bins)
+
+    def __getitem__(self, index):
+        if isinstance(index, slice):
+            return MetagenomicBins(self._bins[index])
+        return self._bins[index]
+
+    def __reduce__(self):
+        return type(self), (self._bins,)
+
+    def _blob_bytes(self):
+        if self._blob is None:
+            self._blob = b"".join(bytes(b.training_info) for b in self._bins)
+        return self._blob
+
+
+def _load_builtin_bins():
+    """The 50 pre-trained Prodigal models (data dumped by tools/dump_metagenomic_bins.py)."""
+    with open(os.path.join(_HERE, "data", "metagenomic_bins.json")) as f:
+        meta = json.load(f)
+    with lzma.open(os.path.join(_HERE, "data", "metagenomic_bins.bin.xz")) as f:
+        blob = f.read()
+    n, stride = meta["count"], meta["stride"]
+    assert len(blob) == n * stride and stride == TRAINING_SIZE
+    bins = MetagenomicBins(
+        MetagenomicBin(TrainingInfo._from_bytes(blob[i * stride:(i + 1) * stride]), meta["descriptions"][i])
+        for i in range(n))
+    bins._blob = blob
+    return bins
+
+
+class _LazyBins:
+    _bins = None
+
+    @classmethod
+    def get(cls):
+        if cls._bins is None:
+            cls._bins = _load_builtin_bins()
+        return cls._bins
+
+
+def __getattr__(name):
+    if name == "METAGENOMIC_BINS":
+        return _LazyBins.get()
+    raise AttributeError(name)
+
+
+# --- contexts (one per device and model set) -----------------------------------------------------------
+_ctx_lock = threading.Lock()
+_ctx_cache = {}
+
+
+def _context_for(model_blob, n_models, device=0):
+    key = (device, n_models, hash(model_blob))
+    with _ctx_lock:
+        ctx = _ctx_cache.get(key)
+        if ctx is None:
+            if len(_ctx_cache) >= 4:  # keep the device footprint bounded
+                _ctx_cache.pop(next(iter(_ctx_cache))).close()
+            ctx = _capi.Context(device)
+            ctx.set_models(model_blob, n_models, key)
+            ctx.lock = threading.Lock()
+            _ctx_cache[key] = ctx
+        return ctx
+
+
+def _as_ascii(sequence):
+    if isinstance(sequence, Sequence):
+        return sequence._ascii
+    if isinstance(sequence, str):
+        return np.frombuffer(sequence.encode("ascii", "replace"), dtype=np.uint8)
+    return np.frombuffer(memoryview(sequence).cast("B"), dtype=np.uint8)
+
+
+# --- Sequence / masks -------------------------------------------------------------------------------
+class Mask:
+    def __init__(self, begin, end):
+        self.begin, self.end = begin, end
+
+    def __repr__(self):
+        return f"<pyrodigal_b200.Mask begin={self.begin!r} end={self.end!r}>"
+
+    def __eq__(self, other):
+        return isinstance(other, Mask) and (self.begin, self.end) == (other.begin, other.end)
+
+    def intersects(self, begin, end):
+        return self.begin < end and begin < self.end
+
+
+class Masks(list):
+    pass
+
+
+_ENC = np.full(256, 6, dtype=np.uint8)
+for _c, _v in ((b"Aa", 0), (b"Gg", 1), (b"Cc", 2), (b"Tt", 3)):
+    for _b in _c:
+        _ENC[_b] = _v
+
+
+class Sequence(typing.Sized):
+    """Input sequence.  The digitised form (`bytes(memoryview(seq))` in the reference, lib.pyx:642-658) is
+    produced lazily on the host for accessors only; the compute path encodes on the GPU."""
+
+    def __init__(self, sequence, mask=False, mask_size=50):
+        if isinstance(sequence, Sequence):
+            self._ascii = sequence._ascii
+        else:
+            self._ascii = _as_ascii(sequence)
+        self._digits = None
+        self._mask, self._mask_size = mask, mask_size
+        self._masks = None
+        self._gc_count = self._unknown = None
+
+    def __len__(self):
+        return len(self._ascii)
+
+    @property
+    def digits(self):
+        if self._digits is None:
+            self._digits = _ENC[self._ascii]
+        return self._digits
+
+    def __bytes__(self):
+        return self.digits.tobytes()
+
+    def __str__(self):
+        return "".join(_LETTERS[d] for d in self.digits)
+
+    def _counts(self):
+        if self._gc_count is None:
+            d = self.digits
+            self._gc_count = int(np.count_nonzero((d == 1) | (d == 2)))
+            self._unknown = int(np.count_nonzero(d == 6))
+        return self._gc_count, self._unknown
+
+    @property
+    def gc(self):
+        n = len(self)
+        return self._counts()[0] / n if n else 0.0
+
+    @property
+    def unknown(self):
+        return self._counts()[1]
+
+    @property
+    def gc_known(self):
+        gc, unk = self._counts()
+        return gc / (len(self) - unk) if len(self) > unk else 0.0
+
+    @property
+    def masks(self):
+        if self._masks is None:
+            m = Masks()
+            if self._mask:
+                d = self.digits == 6
+                if d.any():
+                    edges = np.flatnonzero(np.diff(np.concatenate(([0], d.view(np.int8), [0]))))
+                    for b, e in zip(edges[::2], edges[1::2]):
+                        if e - b >= self._mask_size or e == len(d):
+                            m.append(Mask(int(b), int(e)))
+            self._masks = m
+        return self._masks
+
+
+# --- Nodes --------------------------------------------------------------------------------------------
+class Node:
+    """View on one node record (lib.pyx:1440-1552)."""
+
+    __slots__ = ("owner", "_r")
+
+    def __init__(self, owner, record):
+        self.owner, self._r = owner, record
+
+    index = property(lambda s: int(s._r["ndx"]))
+    strand = property(lambda s: int(s._r["strand"]))
+    type = property(lambda s: ["ATG", "GTG", "TTG", "Stop"][int(s._r["type"])])
+    edge = property(lambda s: bool(s._r["edge"]))
+    gc_bias = property(lambda s: 0)
+    cscore = property(lambda s: float(s._r["cscore"]))
+    gc_cont = property(lambda s: float(s._r["gc_cont"]))
+    score = property(lambda s: float(s._r["score"]))
+    rscore = property(lambda s: float(s._r["rscore"]))
+    sscore = property(lambda s: float(s._r["sscore"]))
+    tscore = property(lambda s: float(s._r["tscore"]))
+    uscore = property(lambda s: float(s._r["uscore"]))
+
+    def __repr__(self):
+        return f"<pyrodigal_b200.Node index={self.index!r} strand={self.strand:+} type={self.type!r} edge={self.edge!r}>"
+
+
+class Nodes(typing.Sequence):
+    """Sorted node array of one contig as a numpy structured array (`_capi.NODE_DTYPE`)."""
+
+    def __init__(self, array=None):
+        self.array = np.zeros(0, dtype=_capi.NODE_DTYPE) if array is None else array
+
+    def __len__(self):
+        return len(self.array)
+
+    def __getitem__(self, index):
+        if isinstance(index, slice):
+            return Nodes(self.array[index])
+        return Node(self, self.array[index])
+
+    def copy(self):
+        return Nodes(self.array.copy())
+
+    def __getstate__(self):
+        return {"array": self.array}
+
+    def __setstate__(self, state):
+        self.array = state["array"]
+
+
+# --- Genes ----------------------------------------------------------------------------------------------
+def calculate_confidence(score, start_weight):
+    """vendor/Prodigal/gene.c:522-532"""
+    if score / start_weight < 41:
+        conf = math.exp(score / start_weight)
+        conf = (conf / (conf + 1)) * 100.0
+    else:
+        conf = 99.99
+    return 50.0 if conf <= 50.0 else conf
+
+
+class Gene:
+    """One predicted gene (lib.pyx:2610-3047); reads the start/stop node records copied back with it."""
+
+    __slots__ = ("owner", "_g", "_start", "_stop", "_i")
+
+    def __init__(self, owner, i):
+        self.owner, self._i = owner, i
+        self._g = owner._genes[i]
+        self._start, self._stop = owner._gene_nodes[i, 0], owner._gene_nodes[i, 1]
+
+    begin = property(lambda s: int(s._g["begin"]))
+    end = property(lambda s: int(s._g["end"]))
+    strand = property(lambda s: int(s._start["strand"]))
+    gc_cont = property(lambda s: float(s._start["gc_cont"]))
+    cscore = property(lambda s: float(s._start["cscore"]))
+    rscore = property(lambda s: float(s._start["rscore"]))
+    sscore = property(lambda s: float(s._start["sscore"]))
+    tscore = property(lambda s: float(s._start["tscore"]))
+    uscore = property(lambda s: float(s._start["uscore"]))
+    score = property(lambda s: float(s._start["cscore"]) + float(s._start["sscore"]))
+    translation_table = property(lambda s: s.owner.training_info.translation_table)
+    start_node = property(lambda s: Node(None, s._start))
+    stop_node = property(lambda s: Node(None, s._stop))
+
+    @property
+    def partial_begin(self):
+        return bool((self._start if self.strand == 1 else self._stop)["edge"])
+
+    @property
+    def partial_end(self):
+        return bool((self._stop if self.strand == 1 else self._start)["edge"])
+
+    @property
+    def start_type(self):
+        return _NODE_TYPE[3 if self._start["edge"] else int(self._start["type"])]
+
+    def _rbs_pick(self, table):
+        # lib.pyx:2694-2720 / 2723-2751
+        t, n = self.owner.training_info, self._start
+        rbs1 = float(t.rbs_weights[int(n["rbs"][0])]) * t.start_weight
+        rbs2 = float(t.rbs_weights[int(n["rbs"][1])]) * t.start_weight
+        if t.uses_sd:
+            return table[int(n["rbs"][0 if rbs1 > rbs2 else 1])], False
+        mot = float(n["mot_score"]) * t.start_weight
+        if t.missing_motif_weight > -0.5 and rbs1 > rbs2 and rbs1 > mot:
+            return table[int(n["rbs"][0])], False
+        if t.missing_motif_weight > -0.5 and rbs2 >= rbs1 and rbs2 > mot:
+            return table[int(n["rbs"][1])], False
+        if int(n["mot_len"]) == 0:
+            return None, False
+        return None, True
+
+    @property
+    def rbs_motif(self):
+        val, use_motif = self._rbs_pick(_RBS_MOTIF)
+        if not use_motif:
+            return val
+        ndx, ln = int(self._start["mot_ndx"]), int(self._start["mot_len"])
+        return "".join("AGCT"[(ndx >> (2 * i)) & 3] for i in range(ln))  # sequence.c:624-636
+
+    @property
+    def rbs_spacer(self):
+        val, use_motif = self._rbs_pick(_RBS_SPACER)
+        return f"{int(self._start['mot_spacer'])}bp" if use_motif else val
+
+    def confidence(self):
+        return calculate_confidence(self.score, self.owner.training_info.start_weight)
+
+    def _gene_data(self, sequence_id):
+        return "ID={}_{};partial={}{};start_type={};rbs_motif={};rbs_spacer={};gc_cont={:.3f}".format(
+            sequence_id, self._i + 1, int(self.partial_begin), int(self.partial_end), self.start_type, self.rbs_motif,
+            self.rbs_spacer, self.gc_cont)
+
+    def _score_data(self):
+        return "conf={:.2f};score={:.2f};cscore={:.2f};sscore={:.2f};rscore={:.2f};uscore={:.2f};tscore={:.2f};".format(
+            self.confidence(), self.score, self.cscore, self.sscore, self.rscore, self.uscore, self.tscore)
+
+    def sequence(self):
+        d = self.owner.sequence.digits
+        if self.strand == 1:
+            return "".join(_LETTERS[x] for x in d[self.begin - 1:self.end])
+        seg = d[self.begin - 1:self.end][::-1]
+        return "".join(_LETTERS[x ^ 3 if x < 4 else x] for x in seg)
+
+    def __repr__(self):
+        return f"<pyrodigal_b200.Gene begin={self.begin} end={self.end} strand={self.strand:+}>"
+
+
+class Genes(typing.Sequence):
+    """Predicted genes of one contig (lib.pyx:3049-3184)."""
+
+    def __init__(self, genes, gene_nodes, *, sequence, training_info, metagenomic_bin, meta, nodes, ipath, num_seq=1):
+        self._genes, self._gene_nodes = genes, gene_nodes
+        self.sequence, self.training_info, self.metagenomic_bin = sequence, training_info, metagenomic_bin
+        self.meta, self._nodes, self.ipath, self._num_seq = meta, nodes, ipath, num_seq
+
+    def __len__(self):
+        return len(self._genes)
+
+    def __bool__(self):
+        return len(self._genes) > 0
+
+    def __getitem__(self, index):
+        if isinstance(index, slice):
+            return [Gene(self, i) for i in range(*index.indices(len(self)))]
+        if index < 0:
+            index += len(self)
+        if index < 0 or index >= len(self):
+            raise IndexError("genes index out of range")
+        return Gene(self, index)
+
+    @property
+    def nodes(self):
+        if self._nodes is None:
+            raise RuntimeError("node arrays were not requested: use GeneFinder.find_genes or want_nodes=True")
+        return self._nodes
+
+    @property
+    def score(self):
+        """lib.pyx:3170-3184: nodes[ipath].score (0.0 after the meta-mode re-scoring)"""
+        if self.ipath < 0 or self._nodes is None:
+            return 0.0
+        return float(self._nodes.array["score"][self.ipath])
+
+    def __getstate__(self):
+        return self.__dict__.copy()
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+
+
+# --- ConnectionScorer (operator-level surface, lib.pyx:1086-1432) -------------------------------------------
+class ConnectionScorer:
+    """GPU replacement of the SIMD-filter + score_connection plug-in host.
+
+    `backend` is accepted for signature compatibility; there is exactly one backend (CUDA, sm_100a)."""
+
+    def __init__(self, backend="detect", device=0):
+        if backend not in ("detect", "cuda", "generic", "sse", "avx", "avx512", "neon", "swar64", None):
+            raise ValueError(f"Unsupported backend: {backend}")
+        self.backend = "cuda"
+        self.device = device
+        self._idx = None
+
+    def index(self, nodes):
+        a = nodes.array
+        self._idx = (a["strand"].copy(), a["type"].copy(), a["ndx"].copy())
+        self.skip_connection = np.zeros(len(a), dtype=np.uint8)
+
+    def compute_skippable(self, min, i):
+        assert self._idx is not None and min <= i
+        blob = _LazyBins.get()._blob_bytes()
+        ctx = _context_for(blob, 50, self.device)
+        with ctx.lock:
+            skip = ctx.compute_skippable(*self._idx, min, i)
+        self.skip_connection[min:i] = skip[min:i]
+
+    def score_connections(self, nodes, tinf, final=False, gc_score=None):
+        blob = bytes(tinf)
+        ctx = _context_for(blob, 1, self.device)
+        a = nodes.array
+        if gc_score is None:
+            gc_score = np.zeros((len(a), 3))
+        with ctx.lock:
+            score, traceb, ov, pairs, ms = ctx.score_connections(
+                a["ndx"], a["stop_val"], a["strand"], a["type"], a["cscore"], a["sscore"], a["rscore"], a["uscore"],
+                gc_score, a["star_ptr"], 0, final)
+        a["score"], a["traceb"], a["ov_mark"] = score, traceb, ov
+        a["tracef"] = -1
+        self.last_pairs, self.last_ms = pairs, ms
+
+
+# --- GeneFinder ------------------------------------------------------------------------------------------
+class GeneFinder:
+    """Drop-in for pyrodigal.GeneFinder on the find_genes path (lib.pyx:5073-5575)."""
+
+    def __init__(self, training_info=None, *, meta=False, metagenomic_bins=None, closed=False, mask=False, min_mask=50,
+                 min_gene=90, min_edge_gene=60, max_overlap=60, backend="detect", device=0):
+        if meta and training_info is not None:
+            raise ValueError("cannot use a training info in meta mode.")
+        if min_gene <= 0:
+            raise ValueError("`min_gene` must be strictly positive")
+        if min_edge_gene <= 0:
+            raise ValueError("`min_edge_gene` must be strictly positive")
+        if min_mask < 0:
+            raise ValueError("`min_mask` must be positive")
+        if max_overlap < 0:
+            raise ValueError("`max_overlap` must be positive")
+        elif max_overlap > min_gene:
+            raise ValueError("`max_overlap` must be lower than `min_gene`")
+        self.meta, self.closed, self.mask = meta, closed, mask
+        self.training_info = training_info
+        self.min_mask, self.min_gene, self.min_edge_gene, self.max_overlap = min_mask, min_gene, min_edge_gene, max_overlap
+        self.backend = backend
+        self.device = device
+        self.metagenomic_bins = _LazyBins.get() if metagenomic_bins is None else metagenomic_bins
+        self.lock = threading.Lock()
+        self._num_seq = 1
+
+    def __repr__(self):
+        return f"pyrodigal_b200.GeneFinder(meta={self.meta!r}, closed={self.closed!r}, mask={self.mask!r})"
+
+    def __reduce__(self):
+        import functools
+        fn = functools.partial(type(self), meta=self.meta, metagenomic_bins=self.metagenomic_bins, closed=self.closed,
+                               mask=self.mask, min_mask=self.min_mask, min_gene=self.min_gene,
+                               min_edge_gene=self.min_edge_gene, max_overlap=self.max_overlap, backend=self.backend)
+        return fn, (self.training_info,)
+
+    # ---- internals ----
+    def _context(self):
+        if self.meta:
+            bins = self.metagenomic_bins
+            return _context_for(bins._blob_bytes(), len(bins), self.device)
+        return _context_for(bytes(self.training_info), 1, self.device)
+
+    def _opts(self, want_nodes):
+        return _capi.make_opts(meta=self.meta, single_model=0, closed=self.closed, mask=self.mask,
+                               min_mask=self.min_mask, min_gene=self.min_gene, min_edge_gene=self.min_edge_gene,
+                               max_overlap=self.max_overlap, want_nodes=want_nodes)
+
+    def _wrap(self, res, k, seq, want_nodes, num_seq):
+        s = res.summary[k]
+        a, b = int(res.gene_off[k]), int(res.gene_off[k + 1])
+        if self.meta:
+            w = int(s["winner"])
+            mbin = self.metagenomic_bins[w] if w >= 0 else None
+            tinf = mbin.training_info if mbin is not None else None
+        else:
+            mbin, tinf = None, self.training_info
+        if not isinstance(seq, Sequence):
+            seq = Sequence(seq, mask=self.mask, mask_size=self.min_mask)
+        seq._gc_count, seq._unknown = int(s["gc_count"]), int(s["unknown"])
+        nodes = Nodes(res.nodes(k)) if want_nodes else None
+        return Genes(res.genes[a:b], res.gene_nodes[a:b], sequence=seq, training_info=tinf, metagenomic_bin=mbin,
+                     meta=self.meta, nodes=nodes, ipath=int(s["ipath"]), num_seq=num_seq)
+
+    # ---- public ----
+    def find_genes(self, sequence):
+        """Find all the genes in one input sequence (lib.pyx:5400-5469)."""
+        return self.find_genes_many([sequence], want_nodes=True)[0]
+
+    def find_genes_many(self, sequences, want_nodes=False):
+        """Batched find_genes: one GPU pass over all the given contigs (the reference maps find_genes over
+        records with a thread pool, cli.py:286-300; one contig cannot fill a B200)."""
+        if not self.meta and self.training_info is None:
+            raise RuntimeError("cannot find genes without having trained in single mode")
+        arrays = [_as_ascii(s) for s in sequences]
+        n = len(arrays)
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        if n:
+            np.cumsum([len(a) for a in arrays], out=offsets[1:])
+        flat = np.concatenate(arrays) if n > 1 else (arrays[0] if n else np.zeros(0, np.uint8))
+        flat = np.ascontiguousarray(flat)
+        with self.lock:
+            first = self._num_seq
+            self._num_seq += n
+        ctx = self._context()
+        with ctx.lock:
+            res = ctx.find_genes_batch(flat, offsets, self._opts(want_nodes))
+        self.last_stats = res.stats
+        out = [self._wrap(res, k, sequences[k], want_nodes, first + k) for k in range(n)]
+        return out
+
+    def train(self, sequence, *sequences, force_nonsd=False, start_weight=4.35, translation_table=11):
+        """Training (lib.pyx:5471-5575) is outside the accelerated path: supply a
+        TrainingInfo (e.g. TrainingInfo.load of a Prodigal training file) to GeneFinder instead."""
+        if self.meta:
+            raise RuntimeError("cannot use training sequence in metagenomic mode")
+        raise NotImplementedError("GeneFinder.train is not part of the B200 hot path; pass a TrainingInfo")

@@ -1,0 +1,275 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+(a) the golden fixtures generated from the unmodified reference and (b) the CPU oracle on seeded inputs.
+Integers / indices bit-exact; doubles compared with tolerance 0 first and 1e-5 (the north star's bound)
+as the hard limit -- see TOL below."""
+import os
+
+import numpy as np
+import pytest
+
+import refutil as R
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5      # BASELINE.json north star: cscore/sscore within 1e-5
+EXACT = 0.0     # what we actually expect: identical doubles (no FMA, same summation order)
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+META = np.load(os.path.join(G, "meta_cases.npz"), allow_pickle=True)
+SINGLE = np.load(os.path.join(G, "single_cases.npz"), allow_pickle=True)
+DP = np.load(os.path.join(G, "dp_cases.npz"), allow_pickle=True)
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from pyrodigal_b200 import _capi
+    return _capi
+
+
+@pytest.fixture(scope="module")
+def ctx(capi):
+    c = capi.Context(0)
+    c.set_models(R.bins_blob(), 50)
+    yield c
+    c.close()
+
+
+def cmp_float(a, b, what, tol=EXACT):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if a.size == 0:
+        return
+    d = np.abs(a - b)
+    if d.max() > tol:
+        k = int(np.argmax(d))
+        raise AssertionError(f"{what}: max |diff| {d.max():.3e} at {k}: gpu {a.flat[k]!r} ref {b.flat[k]!r} "
+                             f"({int((d > tol).sum())} of {a.size} differ)")
+
+
+def cmp_int(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if not np.array_equal(a, b):
+        bad = np.argwhere(a != b)[:8]
+        raise AssertionError(f"{what}: {len(np.argwhere(a != b))} mismatches, first at {bad.ravel().tolist()}: "
+                             f"gpu {a[tuple(bad[0])]} ref {b[tuple(bad[0])]}")
+
+
+def cmp_nodes(gpu, ref, what, dp=False, star=False):
+    assert len(gpu) == len(ref), (what, len(gpu), len(ref))
+    for f in ("ndx", "stop_val", "strand", "type", "edge", "rbs"):
+        cmp_int(gpu[f], ref[f], f"{what}.{f}")
+    for f, g in (("mot_ndx", "mot_ndx"), ("mot_len", "mot_len"), ("mot_spacer", "mot_spacer"), ("mot_spacendx", "mot_spacendx")):
+        cmp_int(gpu[f], ref[g], f"{what}.{f}")
+    for f in ("cscore", "uscore", "tscore", "rscore", "sscore", "gc_cont"):
+        cmp_float(gpu[f], ref[f], f"{what}.{f}")
+    if star or dp:
+        cmp_int(gpu["star_ptr"], ref["star_ptr"], f"{what}.star_ptr")
+    if dp:
+        for f in ("traceb", "tracef", "ov_mark", "elim"):
+            cmp_int(gpu[f], ref[f], f"{what}.{f}")
+        cmp_float(gpu["score"], ref["score"], f"{what}.score")
+
+
+# ---------------------------------------------------------------------------------------------------
+# operators
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("length,gc,seed,nfrac", [(10000, .5, 1, 0), (50000, .35, 2, 0), (3001, .62, 3, 0),
+                                                   (20000, .45, 4, .002), (100, .5, 5, 0), (5, .5, 6, 0), (3, .5, 7, 0)])
+@pytest.mark.parametrize("tt", [11, 4, 1, 2, 22, 23, 25, 33])
+@pytest.mark.parametrize("closed", [False, True])
+def test_extract_nodes(ctx, capi, length, gc, seed, nfrac, tt, closed):
+    seq = R.synth(length, gc, seed, n_frac=nfrac)
+    d, _, _ = orc.encode(seq)
+    want = orc.extract(d, tt, orc.make_opts(closed=closed))
+    got = ctx.extract_nodes(np.frombuffer(seq, np.uint8), tt, capi.make_opts(closed=closed))
+    for f in ("ndx", "stop_val", "strand", "type", "edge"):
+        cmp_int(got[f], want[f], f"extract.{f}")
+
+
+@pytest.mark.parametrize("mask_size", [50, 10])
+def test_extract_nodes_masked(ctx, capi, mask_size):
+    seq = R.synth(40000, .5, 11, n_frac=0.003)
+    d, _, _ = orc.encode(seq)
+    masks = orc.find_masks(d, mask_size)
+    assert len(masks) > 0
+    want = orc.extract(d, 11, orc.make_opts(masks=masks))
+    got = ctx.extract_nodes(np.frombuffer(seq, np.uint8), 11, capi.make_opts(mask=True, min_mask=mask_size))
+    for f in ("ndx", "stop_val", "strand", "type", "edge"):
+        cmp_int(got[f], want[f], f"extract_masked.{f}")
+
+
+@pytest.mark.parametrize("length,gc,seed", [(10000, .5, 21), (2500, .4, 22), (60000, .6, 23), (900, .55, 24)])
+@pytest.mark.parametrize("model", [0, 2, 11, 24, 33, 49])
+@pytest.mark.parametrize("is_meta", [True, False])
+def test_score_nodes(ctx, capi, length, gc, seed, model, is_meta):
+    seq = R.synth(length, gc, seed)
+    d, _, _ = orc.encode(seq)
+    blob = R.bin_blob(model)
+    tt = int(np.frombuffer(blob, np.int32, count=1, offset=8)[0])
+    ref = orc.extract(d, tt)
+    for first_pass in (True, False):
+        # first_pass=False == a second model scored on the same node array (edge flags carried)
+        orc.reset_scores(ref)
+        orc.score(d, ref, blob, closed=False, is_meta=is_meta)
+        orc.record_overlapping_starts(ref, blob, flag=1, max_overlap=60)
+        got = ctx.score_nodes(np.frombuffer(seq, np.uint8), model, capi.make_opts(), is_meta=is_meta, first_pass=first_pass)
+        cmp_nodes(got, ref, f"score_nodes[m{model} L{length} fp{first_pass}]", star=True)
+
+
+@pytest.mark.parametrize("name", list(DP["names"]))
+@pytest.mark.parametrize("final", [True, False])
+def test_score_connections_golden(ctx, name, final):
+    """the reference's tests/test_connection_scorer.py protocol: same node arrays in, score/traceb/ov_mark out"""
+    a = DP[name + "/in"]
+    b = int(DP[name + "/bin"])
+    score, traceb, ov, pairs, ms = ctx.score_connections(
+        a["ndx"], a["stop_val"], a["strand"], a["type"], a["cscore"], a["sscore"], a["rscore"], a["uscore"],
+        a["gc_score"], a["star_ptr"], b, final)
+    tag = "final" if final else "train"
+    cmp_int(traceb, DP[f"{name}/{tag}/traceb"], f"{name}.traceb")
+    cmp_int(ov, DP[f"{name}/{tag}/ov_mark"], f"{name}.ov_mark")
+    cmp_float(score, DP[f"{name}/{tag}/score"], f"{name}.score")
+    ref = a.copy()
+    assert pairs == orc.score_connections(ref, R.bin_blob(b), final=final)
+
+
+def test_compute_skippable(ctx):
+    a = DP["kk_bin38/in"]
+    i = len(a) - 1
+    mn = max(0, i - 1000)
+    skip = ctx.compute_skippable(a["strand"], a["type"], a["ndx"], mn, i)
+    want = np.array([orc.skippable(a, j, i) for j in range(mn, i)], dtype=np.uint8)
+    cmp_int(skip[mn:i], want, "skippable")
+
+
+# ---------------------------------------------------------------------------------------------------
+# find_genes
+# ---------------------------------------------------------------------------------------------------
+def run_meta(ctx, capi, seqs, closed=False, mask=False, want_nodes=True):
+    arrs = [np.frombuffer(s, np.uint8) for s in seqs]
+    off = np.zeros(len(arrs) + 1, np.int64)
+    np.cumsum([len(a) for a in arrs], out=off[1:])
+    flat = np.ascontiguousarray(np.concatenate(arrs)) if arrs else np.zeros(0, np.uint8)
+    return ctx.find_genes_batch(flat, off, capi.make_opts(meta=True, closed=closed, mask=mask, want_nodes=want_nodes))
+
+
+@pytest.mark.parametrize("name", list(META["names"]))
+def test_find_genes_meta_golden(ctx, capi, name):
+    seq = META[name + "/seq"].tobytes()
+    closed, mask = (int(v) for v in META[name + "/opts"])
+    res = run_meta(ctx, capi, [seq], closed=closed, mask=mask)
+    s = res.summary[0]
+    assert int(s["winner"]) == int(META[name + "/winner"]), name
+    cmp_int(res.genes, META[name + "/genes"], f"{name}.genes")
+    cmp_nodes(res.nodes(0), META[name + "/nodes"], name)
+    # start/stop node records copied with the genes == the node array entries
+    nodes = res.nodes(0)
+    for k, g in enumerate(res.genes):
+        assert res.gene_nodes[k, 0].tobytes() == nodes[g["start_ndx"]].tobytes()
+        assert res.gene_nodes[k, 1].tobytes() == nodes[g["stop_ndx"]].tobytes()
+
+
+@pytest.mark.parametrize("name", list(SINGLE["names"]))
+def test_find_genes_single_golden(capi, name):
+    seq = SINGLE[name + "/seq"]
+    closed, mask = (int(v) for v in SINGLE[name + "/opts"])
+    c = capi.Context(0)
+    c.set_models(SINGLE[name + "/tinf"].tobytes(), 1)
+    res = c.find_genes_batch(np.ascontiguousarray(seq), np.array([0, len(seq)], np.int64),
+                             capi.make_opts(meta=False, single_model=0, closed=closed, want_nodes=True))
+    cmp_int(res.genes, SINGLE[name + "/genes"], f"{name}.genes")
+    cmp_nodes(res.nodes(0), SINGLE[name + "/nodes"], name, dp=True)
+    c.close()
+
+
+def test_find_genes_batch_vs_oracle(ctx, capi):
+    """one batched call over ragged contigs (empty, tiny, short-meta, long) == oracle contig by contig"""
+    rng = np.random.default_rng(99)
+    seqs = [b"", b"ACG", R.synth(89, .5, 1), R.synth(120000, .52, 2)]
+    for k in range(60):
+        seqs.append(R.synth(int(rng.integers(100, 30000)), float(rng.uniform(.28, .72)), 1000 + k,
+                            n_frac=0.001 if k % 7 == 0 else 0.0))
+    res = run_meta(ctx, capi, seqs)
+    total_pairs = 0
+    for k, s in enumerate(seqs):
+        d, gc, unk = orc.encode(s)
+        genes, nodes, winner, pairs = orc.find_genes_meta(d, gc / len(d) if len(d) else 0.0, R.bins_blob())
+        total_pairs += pairs
+        assert int(res.summary["winner"][k]) == winner, k
+        assert int(res.summary["gc_count"][k]) == gc and int(res.summary["unknown"][k]) == unk
+        a, b = res.gene_off[k], res.gene_off[k + 1]
+        cmp_int(res.genes[a:b], genes, f"contig{k}.genes")
+        if winner >= 0:
+            cmp_nodes(res.nodes(k), nodes, f"contig{k}")
+    assert res.stats["pairs"] == total_pairs
+    assert res.stats["kernel_launches"] > 0
+
+
+@pytest.mark.parametrize("closed,mask", [(True, False), (False, True)])
+def test_find_genes_options_vs_oracle(ctx, capi, closed, mask):
+    seqs = [R.synth(int(L), gc, 500 + i, n_frac=0.002 if mask else 0.0)
+            for i, (L, gc) in enumerate([(8000, .4), (2500, .55), (40000, .65), (1400, .5)])]
+    res = run_meta(ctx, capi, seqs, closed=closed, mask=mask)
+    for k, s in enumerate(seqs):
+        d, gc, unk = orc.encode(s)
+        masks = orc.find_masks(d, 50) if mask else None
+        genes, nodes, winner, _ = orc.find_genes_meta(d, gc / len(d), R.bins_blob(), orc.make_opts(closed=closed, masks=masks))
+        assert int(res.summary["winner"][k]) == winner
+        a, b = res.gene_off[k], res.gene_off[k + 1]
+        cmp_int(res.genes[a:b], genes, f"contig{k}.genes")
+        if winner >= 0:
+            cmp_nodes(res.nodes(k), nodes, f"contig{k}")
+
+
+def test_resident_batch_matches_host_batch(ctx, capi):
+    seqs = [R.synth(5000 + 700 * k, .4 + 0.02 * k, 700 + k) for k in range(12)]
+    arrs = [np.frombuffer(s, np.uint8) for s in seqs]
+    off = np.zeros(len(arrs) + 1, np.int64)
+    np.cumsum([len(a) for a in arrs], out=off[1:])
+    flat = np.ascontiguousarray(np.concatenate(arrs))
+    o = capi.make_opts(meta=True)
+    r1 = ctx.find_genes_batch(flat, off, o)
+    b = ctx.upload(flat, off)
+    r2 = b.run(o)
+    r3 = b.run(o)
+    for r in (r2, r3):
+        cmp_int(r.genes, r1.genes, "resident.genes")
+        assert r.gene_nodes.tobytes() == r1.gene_nodes.tobytes()
+    b.free()
+
+
+def test_python_api_drop_in():
+    """GeneFinder / Genes / Gene surface vs the attribute table recorded from the reference"""
+    import pyrodigal_b200
+    for name in ("cfg1_10k", "KK037166", "s20k_N_mask"):
+        seq = META[name + "/seq"].tobytes()
+        closed, mask = (bool(v) for v in META[name + "/opts"])
+        gf = pyrodigal_b200.GeneFinder(meta=True, closed=closed, mask=mask)
+        genes = gf.find_genes(seq)
+        table = META[name + "/gene_table"]
+        assert len(genes) == len(table)
+        for g, row in zip(genes, table):
+            assert (g.begin, g.end, g.strand, int(g.partial_begin), int(g.partial_end), g.start_type) == tuple(row[:6])
+            assert str(g.rbs_motif) == row[6] and str(g.rbs_spacer) == row[7]
+            for got, want in zip((g.gc_cont, g.cscore, g.rscore, g.sscore, g.tscore, g.uscore, g.score, g.confidence()), row[8:]):
+                assert abs(got - float(want)) <= TOL
+        w = int(META[name + "/winner"])
+        assert (genes.metagenomic_bin is pyrodigal_b200.METAGENOMIC_BINS[w]) if w >= 0 else genes.metagenomic_bin is None
+        assert len(genes.nodes) == len(META[name + "/nodes"])
+        hdr = list(META[name + "/prodigal"])
+        if hdr and not (closed or mask):
+            for g, h in zip(genes, hdr):
+                f = [x.strip() for x in h.split("#")]
+                assert (int(f[1]), int(f[2]), int(f[3])) == (g.begin, g.end, g.strand)
+                assert g._gene_data(f[4].split(";")[0].split("=")[1].rsplit("_", 1)[0]) == f[4]
+    # single mode through the Python surface
+    name = "srr_trained"
+    ti = pyrodigal_b200.TrainingInfo._from_bytes(SINGLE[name + "/tinf"].tobytes())
+    genes = pyrodigal_b200.GeneFinder(ti).find_genes(SINGLE[name + "/seq"].tobytes())
+    table = SINGLE[name + "/gene_table"]
+    assert [(g.begin, g.end, g.strand) for g in genes] == [tuple(r[:3]) for r in table]
+    with pytest.raises(RuntimeError):
+        pyrodigal_b200.GeneFinder().find_genes(b"ACGT")
+    with pytest.raises(ValueError):
+        pyrodigal_b200.GeneFinder(ti, meta=True)
