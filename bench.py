@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py -- Mbp/s of find_genes (meta mode) on synthetic contig batches, 1..8 B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path
+
+Workload (BASELINE.json configs[3]): the 100 000-contig synthetic metagenome
+(contig lengths uniform 1-100 kbp, GC uniform 0.30-0.70, iid bases, seeds 1 000 000 + k), sharded
+over the GPUs of one box: every rank owns 12 500 contigs (~630 Mbp), so per-GPU work is fixed as N
+grows ("weak" scaling) and N = 8 is exactly the 100k-contig / ~5 Gbp batch.  A "step" is one pass of
+the whole hot path (encode -> add_nodes -> score_nodes -> overlapping starts -> connection DP for every
+(contig, model) chain -> winner / traceback / genes -> final re-score) over the rank's shard.
+
+Printed JSON line (rank 0): see the task contract; additionally `roofline` (dominant kernel = the
+connection-scoring DP), `cpu_baseline`, `e2e`, `clocks`, `gpu_launches`, `phases`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CONTIGS_PER_GPU = 12500
+DP_BYTES_PER_STEP = 72  # algorithmic HBM bytes of one DP step (final=1)
+
+
+def make_contigs(first, count, seed=4):
+    """cfg4 contigs [first, first+count): (flat uint8 ASCII array, int64 offsets)"""
+    rng = np.random.default_rng(seed)
+    # lengths / gc of the whole 100k-contig config are drawn once so that shards are disjoint slices of it
+    lengths = rng.integers(1_000, 100_001, size=100_000)
+    gcs = rng.uniform(0.30, 0.70, size=100_000)
+    idx = np.arange(first, first + count) % 100_000
+    lens = lengths[idx]
+    offsets = np.zeros(count + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    flat = np.empty(int(offsets[-1]), dtype=np.uint8)
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for k, i in enumerate(idx):
+        g = np.random.default_rng(1_000_000 + int(i))
+        gc = gcs[i]
+        # P(A)=P(T)=(1-gc)/2, P(C)=P(G)=gc/2 through a single uniform draw per base
+        u = g.random(int(lens[k]), dtype=np.float32)
+        a = (1 - gc) / 2
+        code = (u >= a).astype(np.uint8) + (u >= a + gc / 2) + (u >= a + gc)
+        flat[offsets[k]:offsets[k + 1]] = lut[code]
+    return flat, offsets
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_reference_runner():
+    """returns (fn(list_of_bytes) -> total genes, kind, description, cores)"""
+    cores = os.cpu_count() or 1
+    from multiprocessing.pool import ThreadPool
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    try:
+        if not os.path.exists(os.path.join(ref_dir, "pyrodigal")):
+            raise ImportError("oracle/_ref not present")
+        sys.path.insert(0, ref_dir)
+        import pyrodigal  # the unmodified reference
+        gf = pyrodigal.GeneFinder(meta=True)  # backend="detect" (SSE2/AVX2 SIMD skip filter)
+        pool = ThreadPool(cores)
+
+        def run(seqs):
+            # the reference's documented parallel recipe: docs/guide/parallel.rst:24-41, cli.py:286-300
+            return sum(len(g) for g in pool.map(gf.find_genes, seqs))
+        return run, "reference", f"pyrodigal {pyrodigal.__version__} GeneFinder(meta=True) ThreadPool({cores})", cores
+    except Exception as e:
+        from oracle import oracle as orc
+        import refutil as R
+        blob = R.bins_blob()
+        pool = ThreadPool(cores)
+
+        def one(s):
+            d, gc, unk = orc.encode(s)
+            return len(orc.find_genes_meta(d, gc / len(d) if len(d) else 0.0, blob)[0])
+
+        def run(seqs):
+            return sum(pool.map(one, seqs))
+        return run, "port", f"C oracle port ThreadPool({cores}) [{type(e).__name__}: {e}]", cores
+
+
+def time_cpu(flat, offsets, steps, warmup, max_contigs):
+    run, kind, desc, cores = cpu_reference_runner()
+    n = min(len(offsets) - 1, max_contigs)
+    seqs = [flat[offsets[k]:offsets[k + 1]].tobytes() for k in range(n)]
+    bp = int(offsets[n] - offsets[0])
+    for _ in range(warmup):
+        run(seqs[: max(1, n // 8)])
+    t0 = time.perf_counter()
+    genes = 0
+    for _ in range(steps):
+        genes = run(seqs)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": bp / dt / 1e6, "unit": "Mbp/s", "cores": cores, "kind": kind,
+            "sample": f"first {n} contigs of the rank-0 shard ({bp / 1e6:.1f} Mbp), {desc}", "s_per_step": dt,
+            "genes": genes}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--contigs", type=int, default=CONTIGS_PER_GPU, help="contigs per GPU (default = cfg4 shard)")
+    ap.add_argument("--cpu-contigs", type=int, default=0, help="contigs in the CPU sample (0 = 16 per core)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_gpus = max(args.gpus, world)
+    config = {"workload": "cfg4: 100k-contig synthetic metagenome (1-100 kbp, GC 0.30-0.70), meta mode, "
+                          f"{args.contigs} contigs per GPU, contig-sharded", "contigs_per_gpu": args.contigs,
+              "parallelism": f"contig-shard x{n_gpus}", "l2_policy": "inputs larger than L2 (shard >> 126 MB)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU) --------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        flat, offsets = make_contigs(0, args.contigs if args.contigs < CONTIGS_PER_GPU else 2048)
+        cores = os.cpu_count() or 1
+        cb = time_cpu(flat, offsets, args.steps, min(args.warmup, 1), args.cpu_contigs or 16 * cores)
+        line = {"impl": "reference", "metric": "Mbp/s find_genes (meta mode)", "value": cb["value"], "unit": "Mbp/s",
+                "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["s_per_step"] * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config, "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "Mbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm --------------------
+    import torch
+    import torch.distributed as dist
+    from pyrodigal_b200 import _capi
+    import refutil as R
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    flat, offsets = make_contigs(rank * args.contigs, args.contigs)
+    bp = int(offsets[-1])
+    # pinned host staging of the step's input (the e2e leg copies from here every step)
+    pinned = torch.empty(bp, dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = flat
+    host = pinned.numpy()
+
+    ctx = _capi.Context(local_rank)
+    ctx.set_models(R.bins_blob(), 50)
+    opts = _capi.make_opts(meta=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize; CUDA events on the library's stream; max over ranks"""
+        barrier()
+        ctx.timer_start()
+        t0 = time.perf_counter()
+        last = None
+        for _ in range(steps):
+            last = fn()
+        ms = ctx.timer_stop()
+        wall = (time.perf_counter() - t0) * 1e3
+        torch.cuda.synchronize()
+        t = torch.tensor([ms, wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(t[0]), float(t[1]), last
+
+    # ---- device-resident leg ("value") ----
+    batch = ctx.upload(host, offsets)
+    for _ in range(args.warmup):
+        r = batch.run(opts)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, wall_ms, res = timed(lambda: batch.run(opts), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    stats = res.stats
+    genes_rank = int(res.summary["n_genes"].sum())
+
+    # ---- end-to-end leg: C ABI call with host buffers, H2D + D2H inside ----
+    for _ in range(1):
+        r = ctx.find_genes_batch(host, offsets, opts)
+    ms_e2e, wall_e2e, res2 = timed(lambda: ctx.find_genes_batch(host, offsets, opts), args.steps)
+    st2 = res2.stats
+    batch.free()
+
+    tot = torch.tensor([bp, stats["pairs"], stats["dp_steps"], genes_rank, stats["kernel_launches"]],
+                       dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    tot_bp, tot_pairs, tot_steps, tot_genes, tot_launch = (float(x) for x in tot)
+
+    if rank == 0:
+        per_step = ms / args.steps
+        peak, peak_src = measured_peak()
+        dp_ms = stats["ms_dp"]
+        achieved = DP_BYTES_PER_STEP * stats["dp_steps"] / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else 0.0
+        line = {
+            "metric": "Mbp/s find_genes (meta mode)", "value": tot_bp / (per_step * 1e-3) / 1e6, "unit": "Mbp/s",
+            "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config,
+            "e2e": {"value": tot_bp / (ms_e2e / args.steps * 1e-3) / 1e6, "unit": "Mbp/s",
+                    "h2d_bytes_per_step": int(st2["h2d_bytes"]), "d2h_bytes_per_step": int(st2["d2h_bytes"]),
+                    "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e / args.steps,
+                    "api": "pgpu_find_genes_batch (C ABI, pinned host input)"},
+            "gpu_launches": int(tot_launch * args.steps),
+            "roofline": {"bound": "hbm", "kernel": "k_dp<1> (connection-scoring DP)", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_dp_step": DP_BYTES_PER_STEP, "dp_steps_per_launch": int(stats["dp_steps"]),
+                         "kernel_ms": dp_ms, "node_pairs_per_s": stats["pairs"] / (dp_ms * 1e-3) if dp_ms > 0 else None},
+            "node_pairs_per_s_job": tot_pairs / (per_step * 1e-3),
+            "phases_ms_rank0": {k: stats[k] for k in ("ms_encode", "ms_extract", "ms_score", "ms_overlap", "ms_dp",
+                                                      "ms_trace", "ms_final", "ms_d2h", "ms_total_device")},
+            "wall_ms_per_step": wall_ms / args.steps,
+            "totals": {"bp": int(tot_bp), "genes": int(tot_genes), "dp_steps": int(tot_steps), "pairs": int(tot_pairs),
+                       "chains_rank0": int(stats["n_chains"]), "nodes_rank0": int(stats["total_nodes"])},
+            "clocks": clocks,
+        }
+        if not args.no_cpu and world == 1:
+            cores = os.cpu_count() or 1
+            line["cpu_baseline"] = {k: v for k, v in time_cpu(flat, offsets, 1, 1, args.cpu_contigs or 16 * cores).items()
+                                    if k in ("value", "unit", "cores", "kind", "sample")}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

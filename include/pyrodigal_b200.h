@@ -114,6 +114,12 @@ const char *pgpu_last_error(const pgpu_ctx *ctx);
 int pgpu_set_models(pgpu_ctx *ctx, const void *blobs, int n, size_t stride);
 int pgpu_num_models(const pgpu_ctx *ctx);
 
+/* CUDA-event stopwatch on the library's own stream (the stream every kernel of this context is launched
+ * on): start records an event, stop records a second one, waits for it and returns the elapsed device
+ * time.  Used by bench.py so that the timed region is measured on the launching stream. */
+int pgpu_timer_start(pgpu_ctx *ctx);
+int pgpu_timer_stop(pgpu_ctx *ctx, double *ms);
+
 /* Upper bound for the workspace the library may allocate on the device (bytes; 0 = default). */
 int pgpu_set_workspace_limit(pgpu_ctx *ctx, size_t bytes);
 

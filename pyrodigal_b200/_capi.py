@@ -73,6 +73,8 @@ lib.pgpu_last_error.restype = C.c_char_p
 lib.pgpu_set_models.argtypes = [_vp, _vp, C.c_int, C.c_size_t]
 lib.pgpu_num_models.argtypes = [_vp]
 lib.pgpu_set_workspace_limit.argtypes = [_vp, C.c_size_t]
+lib.pgpu_timer_start.argtypes = [_vp]
+lib.pgpu_timer_stop.argtypes = [_vp, C.POINTER(C.c_double)]
 lib.pgpu_find_genes_batch.argtypes = [_vp, _vp, _vp, C.c_int, C.POINTER(Opts), C.POINTER(_vp)]
 lib.pgpu_batch_upload.argtypes = [_vp, _vp, _vp, C.c_int, C.POINTER(_vp)]
 lib.pgpu_batch_run.argtypes = [_vp, _vp, C.POINTER(Opts), C.POINTER(_vp)]
@@ -147,6 +149,14 @@ class Context:
         assert len(buf) == n * TRAINING_SIZE
         check(lib.pgpu_set_models(self.handle, ptr(buf), n, TRAINING_SIZE), self.handle)
         self.model_key = key
+
+    def timer_start(self):
+        check(lib.pgpu_timer_start(self.handle), self.handle)
+
+    def timer_stop(self):
+        ms = C.c_double(0)
+        check(lib.pgpu_timer_stop(self.handle, C.byref(ms)), self.handle)
+        return ms.value
 
     # ---- hot path -------------------------------------------------------------------------------
     def find_genes_batch(self, seq, offsets, opts):

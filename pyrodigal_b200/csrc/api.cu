@@ -813,6 +813,24 @@ int pgpu_set_workspace_limit(pgpu_ctx *ctx, size_t bytes) {
     return PGPU_OK;
 }
 
+int pgpu_timer_start(pgpu_ctx *ctx) {
+    if (!ctx) return PGPU_EINVAL;
+    cudaSetDevice(ctx->device);
+    CK(cudaEventRecord(ctx->ev[14], ctx->stream));
+    return PGPU_OK;
+}
+
+int pgpu_timer_stop(pgpu_ctx *ctx, double *ms) {
+    if (!ctx || !ms) return PGPU_EINVAL;
+    cudaSetDevice(ctx->device);
+    CK(cudaEventRecord(ctx->ev[15], ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev[15]));
+    float t = 0;
+    CK(cudaEventElapsedTime(&t, ctx->ev[14], ctx->ev[15]));
+    *ms = t;
+    return PGPU_OK;
+}
+
 int pgpu_find_genes_batch(pgpu_ctx *ctx, const uint8_t *seq, const int64_t *offsets, int n_contigs,
                           const pgpu_opts *opts, pgpu_result **out) {
     return run_all(ctx, seq, nullptr, offsets, n_contigs, opts, out);

@@ -17,6 +17,7 @@
 //  * per step: lanes stride over admissible predecessors, warp-shuffle arg-max, one __syncthreads.
 //  * doubles everywhere, no FMA contraction (-fmad=false): results are bit-identical to the reference.
 #include <cfloat>
+#include <cstring>
 
 #include "kernels.cuh"
 
@@ -558,6 +559,7 @@ __global__ void __launch_bounds__(128) k_pack_nodes(DevBatch B, int n_chains, in
     if (i >= C.nn) return;
     const int c = B.cls[C.node_off + i];
     pgpu_node n;
+    memset(&n, 0, sizeof(n));  // deterministic padding bytes: records are compared / hashed as raw bytes
     n.ndx = B.ndx[C.node_off + i];
     n.stop_val = B.stop_val[C.node_off + i];
     n.strand = (c & CLS_REV) ? -1 : 1;
