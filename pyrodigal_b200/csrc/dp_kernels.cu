@@ -581,7 +581,10 @@ __global__ void __launch_bounds__(128) k_pack_nodes(DevBatch B, int n_chains, in
             n.star_ptr[0] = B.star_ptr[3 * g]; n.star_ptr[1] = B.star_ptr[3 * g + 1]; n.star_ptr[2] = B.star_ptr[3 * g + 2];
         }
     }
-    out[g] = n;
+    const uint64_t *src = reinterpret_cast<const uint64_t *>(&n);
+    uint64_t *dst = reinterpret_cast<uint64_t *>(out + g);
+#pragma unroll
+    for (int q = 0; q < (int)(sizeof(pgpu_node) / 8); q++) dst[q] = src[q];
 }
 
 // meta mode: the winner's nodes are re-extracted and re-scored from scratch (lib.pyx:5380-5394); this
@@ -611,8 +614,13 @@ __global__ void __launch_bounds__(128) k_pack_gene_nodes(int n_contigs, const pg
     for (int g = threadIdx.x; g < ng; g += blockDim.x) {
         const pgpu_gene G = genes[gene_off[c] + g];
         genes_out[gene_out_off[c] + g] = G;
-        out[2 * (gene_out_off[c] + g)] = nodes[node_out_off[c] + G.start_ndx];
-        out[2 * (gene_out_off[c] + g) + 1] = nodes[node_out_off[c] + G.stop_ndx];
+        // raw 8-byte copies: a struct assignment may skip padding bytes, records must be byte-identical
+        static_assert(sizeof(pgpu_node) % 8 == 0, "pgpu_node size");
+        const uint64_t *s0 = reinterpret_cast<const uint64_t *>(nodes + node_out_off[c] + G.start_ndx);
+        const uint64_t *s1 = reinterpret_cast<const uint64_t *>(nodes + node_out_off[c] + G.stop_ndx);
+        uint64_t *d0 = reinterpret_cast<uint64_t *>(out + 2 * (gene_out_off[c] + g));
+#pragma unroll
+        for (int q = 0; q < (int)(sizeof(pgpu_node) / 8); q++) { d0[q] = s0[q]; d0[sizeof(pgpu_node) / 8 + q] = s1[q]; }
     }
 }
 
