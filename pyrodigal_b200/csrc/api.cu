@@ -48,6 +48,20 @@ struct pgpu_ctx {
     size_t ws_limit = 0;
     cudaEvent_t ev[16];
     int64_t launches = 0;
+    int dp_algo = 1;           // 1: k_dp_fast (default), 0: all-pairs k_dp (PGPU_DP_ALGO=0)
+    void *h_stage = nullptr;   // pinned staging for result D2H (grow-only)
+    size_t h_stage_size = 0;
+    void *stage(size_t bytes) {
+        if (bytes > h_stage_size) {
+            if (h_stage) cudaFreeHost(h_stage);
+            h_stage = nullptr;
+            h_stage_size = 0;
+            size_t want = bytes + bytes / 4 + (1 << 20);
+            if (cudaHostAlloc(&h_stage, want, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+            h_stage_size = want;
+        }
+        return h_stage;
+    }
 };
 
 static thread_local std::string g_create_err;
@@ -487,12 +501,15 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     B.crank = pool.alloc<int32_t>(4 * (size_t)total_nodes + 4);
     B.clist = pool.alloc<int32_t>(total_nodes);
     B.cbase = pool.alloc<int32_t>(4 * (size_t)n_ext + 4);
+    B.cndx = pool.alloc<int32_t>(total_nodes);
+    B.dpx = pool.alloc<int4>(total_nodes);
     unsigned long long *d_ext_pairs = pool.alloc<unsigned long long>(n_ext, true);
     if (pool.failed) return PGPU_ENOMEM;
     launch_extract_fill(B, n_ext, ro, st);
     launch_node_prep(B, n_ext, total_nodes, 1, st);
+    launch_dp_index(B, n_ext, total_nodes, st);
     launch_pairs(B, n_ext, total_nodes, d_ext_pairs, st);
-    ctx->launches += 4;
+    ctx->launches += 5;
     int e_ext = mark();
 
     S.n_contigs += n; S.total_bp += atot; S.total_nodes += total_nodes; S.total_chain_nodes += total_cn;
@@ -524,6 +541,12 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     B.ov_mark = pool.alloc<int8_t>(total_cn + 16);
     B.chain_ipath = pool.alloc<int32_t>(n_chains);
     B.chain_score = pool.alloc<double>(n_chains);
+    if (ctx->dp_algo == 1) {
+        B.dp_sv = pool.alloc<double>(total_cn);
+        B.dp_tbn = pool.alloc<int32_t>(total_cn);
+        B.dp_bx = pool.alloc<double>(total_cn / 16 + 2 * (size_t)n_chains + 8);
+        B.dp_bj = pool.alloc<int32_t>(total_cn / 16 + 2 * (size_t)n_chains + 8);
+    }
     int32_t *d_tracef = pool.alloc<int32_t>(total_cn);
     uint8_t *d_elim = pool.alloc<uint8_t>(total_cn + 16, true);
     MotifOut *d_mot_main = (!meta) ? pool.alloc<MotifOut>(total_cn) : nullptr;
@@ -569,7 +592,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     pgpu_contig_summary *d_summ = pool.upload(summ);
     int32_t *d_winner_chain = pool.alloc<int32_t>(n);
     if (pool.failed) return PGPU_ENOMEM;
-    launch_dp(B, ctx->d_models, d_order, n_chains, 1, st);
+    launch_dp(B, ctx->d_models, d_order, n_chains, 1, ctx->dp_algo, st);
     ctx->launches++;
     int e_dp = mark();
     launch_trace(B, ctx->d_models, n, d_ccb, d_tracef, d_elim, d_genes, d_gene_off, d_summ, d_winner_chain, meta ? 1 : 0,
@@ -633,10 +656,15 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     const size_t g0 = res->genes.size();
     res->genes.resize(g0 + ng);
     res->gene_nodes.resize(2 * (g0 + ng));
+    char *stage = nullptr;
+    const size_t gbytes = ng * sizeof(pgpu_gene), nbytes = 2 * ng * sizeof(pgpu_node);
     if (ng) {
-        CK(cudaMemcpyAsync(res->genes.data() + g0, d_genes_out, ng * sizeof(pgpu_gene), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(res->gene_nodes.data() + 2 * g0, d_gene_nodes, 2 * ng * sizeof(pgpu_node), cudaMemcpyDeviceToHost, st));
-        S.d2h_bytes += ng * (sizeof(pgpu_gene) + 2 * sizeof(pgpu_node));
+        // D2H through the context's pinned staging buffer (pageable destinations would serialise the copy)
+        stage = (char *)ctx->stage(gbytes + nbytes);
+        if (!stage) return fail(ctx, PGPU_ENOMEM, "pinned staging allocation failed");
+        CK(cudaMemcpyAsync(stage, d_genes_out, gbytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(stage + gbytes, d_gene_nodes, nbytes, cudaMemcpyDeviceToHost, st));
+        S.d2h_bytes += gbytes + nbytes;
     }
     if (opts.want_nodes) {
         const size_t n0 = res->nodes.size();
@@ -657,6 +685,10 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     }
     int e_d2h = mark();
     CK(cudaStreamSynchronize(st));
+    if (ng) {
+        memcpy(res->genes.data() + g0, stage, gbytes);
+        memcpy(res->gene_nodes.data() + 2 * g0, stage + gbytes, nbytes);
+    }
     for (int c = 0; c < n; c++) {
         res->summary[lo + c] = summ[c];
         res->gene_off[lo + c + 1] = (int64_t)g0 + gene_out_off[c + 1];
@@ -763,6 +795,7 @@ int pgpu_create(int device, pgpu_ctx **out) {
         return PGPU_ECUDA;
     }
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    if (const char *a = getenv("PGPU_DP_ALGO")) ctx->dp_algo = atoi(a);
     // keep freed blocks cached in the stream-ordered pool: sub-batches reuse them without going to the driver
     cudaMemPool_t mp;
     if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
@@ -780,6 +813,7 @@ void pgpu_destroy(pgpu_ctx *ctx) {
     if (ctx->d_raw) cudaFree(ctx->d_raw);
     if (ctx->d_models) cudaFree(ctx->d_models);
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1013,6 +1047,12 @@ int pgpu_score_connections(pgpu_ctx *ctx, int n, const int32_t *ndx, const int32
     B.star_ptr = pool.alloc<int32_t>(3 * (size_t)n);
     B.score = pool.alloc<double>(n); B.traceb = pool.alloc<int32_t>(n); B.ov_mark = pool.alloc<int8_t>(n + 16);
     B.chain_ipath = pool.alloc<int32_t>(1); B.chain_score = pool.alloc<double>(1);
+    B.cndx = pool.alloc<int32_t>(n);
+    B.dpx = pool.alloc<int4>(n);
+    if (final && ctx->dp_algo == 1) {
+        B.dp_sv = pool.alloc<double>(n); B.dp_tbn = pool.alloc<int32_t>(n);
+        B.dp_bx = pool.alloc<double>(n / 16 + 16); B.dp_bj = pool.alloc<int32_t>(n / 16 + 16);
+    }
     unsigned long long *d_pairs = pool.alloc<unsigned long long>(1, true);
     if (pool.failed) return PGPU_ENOMEM;
     CK(cudaMemcpyAsync(B.ndx, ndx, n * 4, cudaMemcpyHostToDevice, st));
@@ -1023,10 +1063,11 @@ int pgpu_score_connections(pgpu_ctx *ctx, int n, const int32_t *ndx, const int32
     CK(cudaMemcpyAsync(B.uscore, uscore, n * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(B.star_ptr, star_ptr, 3 * (size_t)n * 4, cudaMemcpyHostToDevice, st));
     launch_node_prep(B, 1, n, 0, st);
+    launch_dp_index(B, 1, n, st);
     launch_pairs(B, 1, n, d_pairs, st);
     launch_opv(B, ctx->d_models, 1, n, st);
     cudaEventRecord(ctx->ev[0], st);
-    launch_dp(B, ctx->d_models, nullptr, 1, final ? 1 : 0, st);
+    launch_dp(B, ctx->d_models, nullptr, 1, final ? 1 : 0, ctx->dp_algo, st);
     cudaEventRecord(ctx->ev[1], st);
     ctx->launches += 5;
     unsigned long long pairs = 0;

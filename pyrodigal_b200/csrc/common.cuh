@@ -118,6 +118,8 @@ struct DevBatch {
     int32_t *crank;       // [4 * node]: number of class-c nodes before node
     int32_t *clist;       // class-sorted node indices (local), segments per class
     int32_t *cbase;       // [4 * ext]: start of each class segment in clist (relative to node_off)
+    int32_t *cndx;        // ndx in class order: cndx[p] = ndx[clist[p]]
+    int4 *dpx;            // per node: pre-resolved DP candidates / ranges (see k_dp_index)
     // chains
     ChainInfo *chains;
     double *cscore, *sscore, *rscore, *uscore, *tscore;  // per chain-node
@@ -128,6 +130,11 @@ struct DevBatch {
     double *score;
     int32_t *traceb;
     int8_t *ov_mark;
+    // class-ordered DP state (fast DP): per chain, indexed like clist
+    double *dp_sv;        // score of a finalized +STOP / -start node, or -DBL_MAX when nothing leads into it
+    int32_t *dp_tbn;      // ndx of the traceback node of a +STOP node
+    double *dp_bx;        // per 16-entry block: max of (sv + ig_neg), ties -> later entry
+    int32_t *dp_bj;       // node index of that maximum
     // per chain results
     int32_t *chain_ipath;
     double *chain_score;

@@ -310,6 +310,293 @@ __global__ void __launch_bounds__(kDpThreads) k_dp(DevBatch B, const DevModel *_
 }
 
 // --------------------------------------------------------------------------------------------------
+// k_dp_fast: the final-scoring DP (final == 1) restructured around what the connection rules actually
+// depend on.  One WARP per chain.  For every predecessor class the value "score[j] + term" is either
+//   * a constant-term connection (intergenic, more than 180 bp away: term = -0.15*st_wt), answered by a
+//     range maximum over per-16-entry block summaries of fl(score + term) -- exact, ties -> later j;
+//   * one of a handful of geometrically pinned candidates (own stop of a reverse gene, the +STOPs around a
+//     3' overlap, the <=3 reverse STOPs whose ORF spans the target, the +STOPs inside the target's ORF);
+//   * or a running per-frame maximum (best start of the current forward ORF).
+// Every candidate value is computed with exactly the reference's operations, so score / traceb / ov_mark
+// are bit-identical to _connection.h:94-367; only pairs that cannot win are never materialised.
+// --------------------------------------------------------------------------------------------------
+constexpr int kFastWarps = 4;  // chains per CTA (independent warps)
+constexpr double kNeg = -DBL_MAX;
+
+struct WCand {
+    double v;
+    int32_t j, fr;
+};
+__device__ __forceinline__ void wc_merge(WCand &a, double v, int j, int fr) {
+    if (v > a.v || (v == a.v && j > a.j)) { a.v = v; a.j = j; a.fr = fr; }
+}
+
+__global__ void __launch_bounds__(32 * kFastWarps) k_dp_fast(DevBatch B, const DevModel *__restrict__ models,
+                                                              const int32_t *__restrict__ order, int n_chains) {
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * kFastWarps + (threadIdx.x >> 5);
+    if (slot >= n_chains) return;
+    const int chain = order ? order[slot] : slot;
+    const ChainInfo C = B.chains[chain];
+    const int nn = C.nn;
+    if (nn == 0) {
+        if (lane == 0) { B.chain_ipath[chain] = -1; B.chain_score[chain] = 0.0; }
+        return;
+    }
+    const DevModel &M = models[C.model];
+    const int32_t *__restrict__ ndx = B.ndx + C.node_off;
+    const int32_t *__restrict__ sv = B.stop_val + C.node_off;
+    const uint8_t *__restrict__ cls = B.cls + C.node_off;
+    const int32_t *__restrict__ win_min = B.win_min + C.node_off;
+    const int32_t *__restrict__ crank = B.crank + 4 * (int64_t)C.node_off;
+    const int32_t *__restrict__ clist = B.clist + C.node_off;
+    const int32_t *__restrict__ cndx = B.cndx + C.node_off;
+    const int4 *__restrict__ dpx = B.dpx + C.node_off;
+    const int32_t *__restrict__ cbase = B.cbase + 4 * C.ext;
+    const double *__restrict__ cscore = B.cscore + C.coff;
+    const double *__restrict__ sscore = B.sscore + C.coff;
+    const double *__restrict__ opv = B.opv + 3 * C.coff;
+    const int32_t *__restrict__ star_ptr = B.star_ptr + 3 * C.coff;
+    // written and re-read by this warp: no __restrict__ / read-only path
+    double *score = B.score + C.coff;
+    int32_t *traceb = B.traceb + C.coff;
+    int8_t *ov_mark = B.ov_mark + C.coff;
+    const int cbFE = cbase[1], cbRS = cbase[2], cbRE = cbase[3];
+    const int nFE = cbRS - cbFE;
+    double *svFE = B.dp_sv + C.coff + cbFE, *svRS = B.dp_sv + C.coff + cbRS;
+    int32_t *tbnFE = B.dp_tbn + C.coff + cbFE;
+    const int64_t boff = (C.coff >> 4) + 2 * (int64_t)chain;
+    double *bxFE = B.dp_bx + boff, *bxRS = bxFE + ((nFE + 15) >> 4);
+    int32_t *bjFE = B.dp_bj + boff, *bjRS = bjFE + ((nFE + 15) >> 4);
+    const int32_t *__restrict__ clFE = clist + cbFE, *__restrict__ clRS = clist + cbRS;
+    const int32_t *__restrict__ cnFE = cndx + cbFE, *__restrict__ cnRS = cndx + cbRS;
+    const double ig_neg = M.ig_neg;
+
+    // class cursors (class-relative positions): cur = finalized entries, lo = first entry inside the
+    // regular 1000-node window, far = first entry NOT more than 180 bp behind the target
+    int curFE = 0, curRS = 0, loFE = 0, loRS = 0, farFE = 0, farRS = 0;
+    // best +start of the open forward ORF of each frame (scalars + selects: no local-memory arrays)
+    double rc_v0 = kNeg, rc_v1 = kNeg, rc_v2 = kNeg;
+    int rc_j0 = -1, rc_j1 = -1, rc_j2 = -1;
+    double best_sc = -1.0;
+    int best_i = -1, best_tb = -1;
+
+    // range maximum of fl(sv + ig_neg) over class positions [a, b): lanes stride over head entries, whole
+    // blocks and tail entries
+    auto range_far = [&](WCand &w, const double *svc, const double *bx, const int32_t *bj, const int32_t *cl, int a, int b) {
+        if (a >= b) return;
+        const int fb = (a + 15) >> 4, lb = b >> 4;
+        int nh, nb, nt, t0;
+        if (fb < lb) { nh = fb * 16 - a; nb = lb - fb; nt = b - lb * 16; t0 = lb * 16; }
+        else { nh = b - a; nb = 0; nt = 0; t0 = b; }
+        for (int t = lane; t < nh + nb + nt; t += 32) {
+            if (t < nh || t >= nh + nb) {
+                const int p = t < nh ? a + t : t0 + (t - nh - nb);
+                const double s = svc[p];
+                if (s != kNeg) wc_merge(w, s + ig_neg, cl[p], -1);
+            } else {
+                const int q = fb + (t - nh);
+                wc_merge(w, bx[q], bj[q], -1);
+            }
+        }
+    };
+
+    for (int i = 0; i < nn; i++) {
+        const int ci = cls[i], kind = cls_kind(ci), f2 = cls_frame(ci), ndx_i = ndx[i], sv_i = sv[i];
+        // node i-1001 drops out of the regular window [i-1000, i)
+        if (i > 2 * kMaxNodeDist) {
+            const int kl = cls_kind(cls[i - 2 * kMaxNodeDist - 1]);
+            loFE += kl == K_FE;
+            loRS += kl == K_RS;
+        }
+        WCand w = {kNeg, -1, -1};
+        double cs_i = 0.0;
+
+        if (kind == K_FS || kind == K_RE) {
+            // advance the 180-bp boundaries (32 entries per probe)
+            const int thr = ndx_i - 3 * kOperDist;
+            for (;;) {
+                const int p = farFE + lane;
+                const int c = __popc(__ballot_sync(0xffffffffu, p < curFE && cnFE[p] < thr));
+                farFE += c;
+                if (c < 32) break;
+            }
+            for (;;) {
+                const int p = farRS + lane;
+                const int c = __popc(__ballot_sync(0xffffffffu, p < curRS && cnRS[p] < thr));
+                farRS += c;
+                if (c < 32) break;
+            }
+            const int fFE = max(farFE, loFE), fRS = max(farRS, loRS);
+            // far parts: constant term
+            range_far(w, svFE, bxFE, bjFE, clFE, loFE, fFE);
+            range_far(w, svRS, bxRS, bjRS, clRS, loRS, fRS);
+            if (kind == K_FS) {
+                cs_i = cscore[i] + sscore[i];
+                // near +STOPs: distance-dependent intergenic term (_connection.h:116-123, 52-78)
+                for (int p = fFE + lane; p < curFE; p += 32) {
+                    const double s = svFE[p];
+                    const int nj = cnFE[p];
+                    if (s == kNeg || nj + 2 >= ndx_i) continue;
+                    const int dist = ndx_i - nj;
+                    const double term = dist > 3 * kOperDist ? ig_neg : (dist <= kOperDist ? M.igt[dist] : 0.0);
+                    wc_merge(w, s + term, clFE[p], -1);
+                }
+                // near -starts: strand switch (_connection.h:124-129)
+                for (int p = fRS + lane; p < curRS; p += 32) {
+                    const double s = svRS[p];
+                    if (s == kNeg || cnRS[p] >= ndx_i) continue;
+                    wc_merge(w, s + ig_neg, clRS[p], -1);
+                }
+            } else {
+                const int sp0 = star_ptr[3 * (int64_t)i], sp1 = star_ptr[3 * (int64_t)i + 1], sp2 = star_ptr[3 * (int64_t)i + 2];
+                const int n3n0 = sp0 != -1 ? ndx[sp0] : 0, n3n1 = sp1 != -1 ? ndx[sp1] : 0, n3n2 = sp2 != -1 ? ndx[sp2] : 0;
+                const int n3s0 = sp0 != -1 ? sv[sp0] : 0, n3s1 = sp1 != -1 ? sv[sp1] : 0, n3s2 = sp2 != -1 ? sv[sp2] : 0;
+                const double op0 = sp0 != -1 ? opv[3 * (int64_t)i] : 0.0, op1 = sp1 != -1 ? opv[3 * (int64_t)i + 1] : 0.0,
+                             op2 = sp2 != -1 ? opv[3 * (int64_t)i + 2] : 0.0;
+                // +STOP with the triple-overlap search (_connection.h:297-334), for one class position
+                auto eval_fe = [&](int p) {
+                    const double s = svFE[p];
+                    const int nj = cnFE[p];
+                    const int left = nj + 2, right = ndx_i - 2;
+                    if (s == kNeg || left >= right) return;
+                    const int tj = tbnFE[p];
+                    int maxfr = -1;
+                    double maxval = 0.0;
+                    auto probe = [&](int k, int spk, int n3n, int n3s, double op) {
+                        if (spk == -1) return;
+                        const int ovlp = left - n3s + 3;
+                        if (ovlp <= 0 || ovlp >= kMaxOppOvlp) return;
+                        if (ovlp >= n3n - left) return;
+                        if (ovlp >= n3s - tj - 2) return;
+                        if (op > maxval) { maxfr = k; maxval = op; }
+                    };
+                    probe(0, sp0, n3n0, n3s0, op0);
+                    probe(1, sp1, n3n1, n3s1, op1);
+                    probe(2, sp2, n3n2, n3s2, op2);
+                    // maxval == opv of the selected frame (it is only ever assigned from it)
+                    wc_merge(w, s + (maxfr != -1 ? maxval : ig_neg), clFE[p], maxfr);
+                };
+                for (int p = fFE + lane; p < curFE; p += 32) eval_fe(p);
+                // +STOPs far away whose position can trigger the triple overlap: the 200 bp after the stop of
+                // each recorded start (their plain value is already in the range maximum; the overlap value
+                // can only be larger, so evaluating them again is exact)
+                auto special = [&](int spk, int n3s) {
+                    if (spk == -1) return;
+                    // left = ndx+2 in (n3s-3, n3s+197)  <=>  ndx in [n3s-4, n3s+194]
+                    int lo_ = loFE, hi_ = fFE;
+                    while (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if (cnFE[mid] < n3s - 4) lo_ = mid + 1; else hi_ = mid; }
+                    const int a = lo_;
+                    hi_ = fFE;
+                    while (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if (cnFE[mid] < n3s + 195) lo_ = mid + 1; else hi_ = mid; }
+                    for (int p = a + lane; p < lo_; p += 32) eval_fe(p);
+                };
+                special(sp0, n3s0);
+                special(sp1, n3s1);
+                special(sp2, n3s2);
+                // near -starts (_connection.h:335-341)
+                for (int p = fRS + lane; p < curRS; p += 32) {
+                    const double s = svRS[p];
+                    const int nj = cnRS[p];
+                    if (s == kNeg || nj >= ndx_i - 2) continue;
+                    const int dist = ndx_i - nj;
+                    const double term = dist > 3 * kOperDist ? ig_neg : (dist <= kOperDist ? M.igt[dist] : 0.0);
+                    wc_merge(w, s + term, clRS[p], -1);
+                }
+                // -STOPs whose ORF spans this stop: operon (_connection.h:343-356); at most one per frame
+                if (lane < 3) {
+                    const int4 dx = dpx[i];
+                    const int j = lane == 0 ? dx.x : (lane == 1 ? dx.y : dx.z);
+                    const int spl = lane == 0 ? sp0 : (lane == 1 ? sp1 : sp2);
+                    const double opl = lane == 0 ? op0 : (lane == 1 ? op1 : op2);
+                    if (j >= 0 && j >= i - 2 * kMaxNodeDist && spl != -1) wc_merge(w, score[j] + opl, j, -1);
+                }
+            }
+        } else if (kind == K_FE) {
+            // best +start of this ORF (gene): running maximum of fl(score + cscore + sscore)
+            {
+                const double rv = f2 == 0 ? rc_v0 : (f2 == 1 ? rc_v1 : rc_v2);
+                const int rj = f2 == 0 ? rc_j0 : (f2 == 1 ? rc_j1 : rc_j2);
+                if (lane == 0 && rj >= 0) wc_merge(w, rv, rj, -1);
+            }
+            // +STOPs inside the ORF (operon, _connection.h:178-191)
+            const int wlo = crank[4 * (int64_t)win_min[i] + 1];
+            for (int p = max(dpx[i].x, wlo) + lane; p < curFE; p += 32) {
+                const double s = svFE[p];
+                if (s == kNeg) continue;
+                const int j = clFE[p];
+                if (star_ptr[3 * (int64_t)j + f2] == -1) continue;
+                wc_merge(w, s + opv[3 * (int64_t)j + f2], j, -1);
+            }
+        } else {  // K_RS
+            cs_i = cscore[i] + sscore[i];
+            const int4 dx = dpx[i];
+            const int wmin = win_min[i];
+            // own -STOP (gene, _connection.h:228-237)
+            if (lane == 0 && dx.x >= wmin && dx.x >= 0 && dx.x < i) wc_merge(w, score[dx.x] + cs_i, dx.x, -1);
+            // +STOPs overlapping the 3' end (_connection.h:239-256)
+            const int wlo = crank[4 * (int64_t)wmin + 1];
+            const double cs_diff = cs_i + ig_neg;
+            for (int p = max(dx.y, wlo) + lane; p < min(dx.z, curFE); p += 32) {
+                const double s = svFE[p];
+                if (s == kNeg) continue;
+                const int nj = cnFE[p];
+                if (sv_i - 2 >= nj + 2) continue;
+                const int ovlp = (nj + 2) - (sv_i - 2) + 1;
+                if (ovlp >= kMaxOppOvlp) continue;
+                if ((nj - sv_i) >= (ndx_i - nj + 3)) continue;
+                if ((nj - sv_i) >= (sv_i - 3 - tbnFE[p])) continue;
+                wc_merge(w, s + cs_diff, clFE[p], -1);
+            }
+        }
+
+        // ---- warp arg-max: equal values -> larger j ----
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double v = __shfl_xor_sync(0xffffffffu, w.v, off);
+            const int j = __shfl_xor_sync(0xffffffffu, w.j, off);
+            const int fr = __shfl_xor_sync(0xffffffffu, w.fr, off);
+            wc_merge(w, v, j, fr);
+        }
+        double sc_i = 0.0;
+        int tb_i = -1, fr_i = -1;
+        if (w.j >= 0 && w.v >= 0.0) { sc_i = w.v; tb_i = w.j; fr_i = w.fr; }
+        if (lane == 0) {
+            score[i] = sc_i; traceb[i] = tb_i; ov_mark[i] = (int8_t)fr_i;
+            if (kind == K_FE || kind == K_RS) {
+                const bool fe = kind == K_FE;
+                const int p = fe ? curFE : curRS;
+                const double s = tb_i == -1 ? kNeg : sc_i;  // edge artifact rule: nothing leads into it
+                (fe ? svFE : svRS)[p] = s;
+                if (fe) tbnFE[p] = tb_i == -1 ? 0 : ndx[tb_i];
+                double *bx = fe ? bxFE : bxRS;
+                int32_t *bj = fe ? bjFE : bjRS;
+                const double x = s + ig_neg;
+                if ((p & 15) == 0 || x >= bx[p >> 4]) { bx[p >> 4] = x; bj[p >> 4] = i; }
+            }
+        }
+        if (kind == K_FE) {
+            curFE++;
+            if (f2 == 0) { rc_v0 = kNeg; rc_j0 = -1; } else if (f2 == 1) { rc_v1 = kNeg; rc_j1 = -1; } else { rc_v2 = kNeg; rc_j2 = -1; }
+        } else if (kind == K_RS) {
+            curRS++;
+        } else if (kind == K_FS) {
+            const double g = sc_i + cs_i;
+            if (f2 == 0) { if (g >= rc_v0) { rc_v0 = g; rc_j0 = i; } }
+            else if (f2 == 1) { if (g >= rc_v1) { rc_v1 = g; rc_j1 = i; } }
+            else { if (g >= rc_v2) { rc_v2 = g; rc_j2 = i; } }
+        }
+        if ((kind == K_FE || kind == K_RS) && sc_i >= best_sc) { best_sc = sc_i; best_i = i; best_tb = tb_i; }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        const bool ok = best_i >= 0 && best_tb != -1;
+        B.chain_ipath[chain] = ok ? best_i : -1;
+        B.chain_score[chain] = ok ? best_sc : 0.0;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
 // winner selection + traceback + gene extraction: one thread per contig
 // --------------------------------------------------------------------------------------------------
 struct NodeRef {
@@ -644,9 +931,13 @@ __global__ void k_skippable(int n, const int8_t *__restrict__ strand, const uint
 // --------------------------------------------------------------------------------------------------
 // launch wrappers
 // --------------------------------------------------------------------------------------------------
-void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, int n_chains, int final, cudaStream_t st) {
+void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, int n_chains, int final, int algo,
+               cudaStream_t st) {
     if (n_chains == 0) return;
-    if (final) k_dp<1><<<n_chains, kDpThreads, 0, st>>>(B, models, order, n_chains);
+    // algo 1 (default): k_dp_fast, final scoring only; algo 0: the all-pairs kernel (also the training DP)
+    if (final && algo == 1 && B.dp_sv)
+        k_dp_fast<<<(n_chains + kFastWarps - 1) / kFastWarps, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);
+    else if (final) k_dp<1><<<n_chains, kDpThreads, 0, st>>>(B, models, order, n_chains);
     else k_dp<0><<<n_chains, kDpThreads, 0, st>>>(B, models, order, n_chains);
 }
 void launch_trace(const DevBatch &B, const DevModel *models, int n_contigs, const int32_t *contig_chain_begin,

@@ -20,10 +20,11 @@ void launch_score_chains(const DevBatch &B, const DevModel *models, int n_chains
 void launch_overlap(const DevBatch &B, const DevModel *models, int n_chains, int64_t total_chain_nodes, RunOpts o,
                     int flag, cudaStream_t st);
 void launch_opv(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, cudaStream_t st);
+void launch_dp_index(const DevBatch &B, int n_ext, int total_nodes, cudaStream_t st);
 void launch_pairs(const DevBatch &B, int n_ext, int total_nodes, unsigned long long *ext_pairs, cudaStream_t st);
 
 // dp_kernels.cu
-void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, int n_chains, int final,
+void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, int n_chains, int final, int algo,
                cudaStream_t st);
 void launch_trace(const DevBatch &B, const DevModel *models, int n_contigs, const int32_t *contig_chain_begin,
                   int32_t *tracef, uint8_t *elim, pgpu_gene *genes, const int64_t *gene_off,

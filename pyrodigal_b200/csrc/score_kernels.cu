@@ -197,11 +197,16 @@ __global__ void __launch_bounds__(128) k_coding(DevBatch B, const DevModel *__re
     int k = s_first;
     while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
     const ChainInfo C = B.chains[k];
-    const int z = (int)(g - C.coff);
-    if (z >= C.nn) return;  // unused tail of a fixed-capacity slot (final re-scoring pass)
+    // the first (#STOP nodes) threads of a chain's index range take one STOP node each, through the
+    // class-sorted index list, so that warps are either fully busy or exit at once
+    const int t = (int)(g - C.coff);
+    if (t >= C.nn) return;
+    const int32_t *__restrict__ cbase = B.cbase + 4 * C.ext;
+    const int n_fe = cbase[2] - cbase[1], n_re = C.nn - cbase[3];
+    if (t >= n_fe + n_re) return;
+    const int z = (B.clist + C.node_off)[t < n_fe ? cbase[1] + t : cbase[3] + (t - n_fe)];
     const uint8_t *__restrict__ cls = B.cls + C.node_off;
     const int c = cls[z];
-    if (!cls_is_stop(c)) return;
     const DevModel &M = models[C.model];
     const double *__restrict__ dc = M.gene_dc;
     const int32_t *__restrict__ ndx = B.ndx + C.node_off;
@@ -604,6 +609,89 @@ void launch_overlap(const DevBatch &B, const DevModel *models, int n_chains, int
                     cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
     k_overlap<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total, o, flag);
+}
+
+}  // namespace pgpu
+
+// --------------------------------------------------------------------------------------------------
+// DP index (model independent, once per extraction): class-ordered ndx and, per node, the predecessor
+// candidates / ranges that the connection rules pin down geometrically (see dp_kernels.cu, k_dp_fast)
+//   +STOP  i: x = first +STOP (class position) with ndx > stop_val(i)                    [operon range]
+//   -start i: x = node index of its own -STOP (ndx == stop_val), y/z = class-position range of the
+//             +STOPs with ndx in (stop_val-4, stop_val+195)                              [gene, 3' overlap]
+//   -STOP  i: x,y,z = for frame 0,1,2 the nearest previous -STOP node whose ORF spans ndx(i), or -1  [operon]
+// --------------------------------------------------------------------------------------------------
+namespace pgpu {
+
+__device__ __forceinline__ int lower_bound_ndx(const int32_t *__restrict__ a, int n, int key) {
+    // first position with a[p] >= key
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(128) k_dp_index(DevBatch B, int n_ext, int total_nodes) {
+    __shared__ int s_first;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x == 0) s_first = find_ext(B.exts, n_ext, min(blockIdx.x * blockDim.x, total_nodes - 1));
+    __syncthreads();
+    if (g >= total_nodes) return;
+    int e = s_first;
+    while (e + 1 < n_ext && B.exts[e + 1].node_off <= g) e++;
+    const ExtractInfo X = B.exts[e];
+    const int p = g - X.node_off, nn = X.nn;  // p = class-ordered position
+    const int32_t *__restrict__ ndx = B.ndx + X.node_off;
+    const int32_t *__restrict__ sv = B.stop_val + X.node_off;
+    const uint8_t *__restrict__ cls = B.cls + X.node_off;
+    const int32_t *__restrict__ clist = B.clist + X.node_off;
+    const int32_t *__restrict__ cb = B.cbase + 4 * e;
+    // (1) class-ordered ndx
+    const int i = clist[p];
+    B.cndx[X.node_off + p] = ndx[i];
+    // (2) per-node candidates; computed by the thread that owns class position p == node clist[p]
+    const int c = cls[i], kind = cls_kind(c), my = ndx[i], msv = sv[i];
+    int4 r = make_int4(-1, -1, -1, -1);
+    // class-ordered ndx of +STOPs / -STOPs are not complete yet for other threads' positions, so search
+    // through clist -> ndx (sorted within a class segment)
+    auto lb_class = [&](int cbeg, int cend, int key) {  // first class position with ndx >= key
+        int lo = cbeg, hi = cend;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (ndx[clist[mid]] < key) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    const int fe0 = cb[1], fe1 = cb[2], re0 = cb[3], re1 = nn;
+    if (kind == K_FE) {
+        r.x = lb_class(fe0, fe1, msv + 1) - fe0;
+    } else if (kind == K_RS) {
+        const int q = lb_class(re0, re1, msv);
+        r.x = (q < re1 && ndx[clist[q]] == msv) ? clist[q] : -1;
+        r.y = lb_class(fe0, fe1, msv - 3) - fe0;
+        r.z = lb_class(fe0, fe1, msv + 195) - fe0;
+    } else if (kind == K_RE) {
+        // nearest previous -STOP of every frame, within the 1000-node window
+        int found = 0;
+        int cand[3] = {-1, -1, -1};
+        for (int q = p - 1; q >= re0 && found != 7; q--) {
+            const int j = clist[q];
+            if (j < i - 2 * kMaxNodeDist) break;
+            const int fj = cls_frame(cls[j]);
+            if (found & (1 << fj)) continue;
+            found |= 1 << fj;
+            if (sv[j] > my) cand[fj] = j;
+        }
+        r.x = cand[0]; r.y = cand[1]; r.z = cand[2];
+    }
+    B.dpx[X.node_off + i] = r;
+}
+
+void launch_dp_index(const DevBatch &B, int n_ext, int total_nodes, cudaStream_t st) {
+    if (n_ext == 0 || total_nodes == 0) return;
+    k_dp_index<<<(total_nodes + 127) / 128, 128, 0, st>>>(B, n_ext, total_nodes);
 }
 
 }  // namespace pgpu
