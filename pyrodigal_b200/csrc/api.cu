@@ -541,7 +541,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     B.ov_mark = pool.alloc<int8_t>(total_cn + 16);
     B.chain_ipath = pool.alloc<int32_t>(n_chains);
     B.chain_score = pool.alloc<double>(n_chains);
-    if (ctx->dp_algo == 1) {
+    if (ctx->dp_algo >= 1) {
         B.dp_sv = pool.alloc<double>(total_cn);
         B.dp_tbn = pool.alloc<int32_t>(total_cn);
         B.dp_bx = pool.alloc<double>(total_cn / 16 + 2 * (size_t)n_chains + 8);
@@ -1049,7 +1049,7 @@ int pgpu_score_connections(pgpu_ctx *ctx, int n, const int32_t *ndx, const int32
     B.chain_ipath = pool.alloc<int32_t>(1); B.chain_score = pool.alloc<double>(1);
     B.cndx = pool.alloc<int32_t>(n);
     B.dpx = pool.alloc<int4>(n);
-    if (final && ctx->dp_algo == 1) {
+    if (final && ctx->dp_algo >= 1) {
         B.dp_sv = pool.alloc<double>(n); B.dp_tbn = pool.alloc<int32_t>(n);
         B.dp_bx = pool.alloc<double>(n / 16 + 16); B.dp_bj = pool.alloc<int32_t>(n / 16 + 16);
     }

@@ -327,12 +327,23 @@ struct WCand {
     double v;
     int32_t j, fr;
 };
+struct FastK {  // per-target constants staged in shared memory, 32 targets per warp at a time
+    int32_t ndx, sv, cls, leave;
+    int32_t wlo, wmin;
+    int32_t dx, dy, dz;
+    int32_t sp0, sp1, sp2;
+    int32_t n3n0, n3n1, n3n2, n3s0, n3s1, n3s2;
+    double op0, op1, op2;
+    double cs;
+};
 __device__ __forceinline__ void wc_merge(WCand &a, double v, int j, int fr) {
     if (v > a.v || (v == a.v && j > a.j)) { a.v = v; a.j = j; a.fr = fr; }
 }
 
-__global__ void __launch_bounds__(32 * kFastWarps) k_dp_fast(DevBatch B, const DevModel *__restrict__ models,
+template <int MINB>
+__global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_fast(DevBatch B, const DevModel *__restrict__ models,
                                                               const int32_t *__restrict__ order, int n_chains) {
+    __shared__ FastK s_fast[kFastWarps][32];
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * kFastWarps + (threadIdx.x >> 5);
     if (slot >= n_chains) return;
@@ -401,16 +412,43 @@ __global__ void __launch_bounds__(32 * kFastWarps) k_dp_fast(DevBatch B, const D
         }
     };
 
-    for (int i = 0; i < nn; i++) {
-        const int ci = cls[i], kind = cls_kind(ci), f2 = cls_frame(ci), ndx_i = ndx[i], sv_i = sv[i];
+    FastK *sk = s_fast[threadIdx.x >> 5];
+    for (int i0 = 0; i0 < nn; i0 += 32) {
+      // ---- stage the model/geometry constants of the next 32 targets: one lane per target, so the dependent
+      //      lookups (star_ptr -> ndx/sv, win_min -> crank) of 32 steps overlap instead of serialising ----
+      __syncwarp();
+      if (i0 + lane < nn) {
+          const int i = i0 + lane;
+          FastK k;
+          k.ndx = ndx[i]; k.sv = sv[i]; k.cls = cls[i];
+          k.leave = i > 2 * kMaxNodeDist ? cls_kind(cls[i - 2 * kMaxNodeDist - 1]) : -1;
+          const int kind = cls_kind(k.cls);
+          const int4 dx = dpx[i];
+          k.dx = dx.x; k.dy = dx.y; k.dz = dx.z;
+          k.wmin = win_min[i];
+          k.wlo = (kind == K_FE || kind == K_RS) ? crank[4 * (int64_t)k.wmin + 1] : 0;
+          k.cs = (kind == K_FS || kind == K_RS) ? cscore[i] + sscore[i] : 0.0;
+          k.sp0 = k.sp1 = k.sp2 = -1;
+          k.n3n0 = k.n3n1 = k.n3n2 = k.n3s0 = k.n3s1 = k.n3s2 = 0;
+          k.op0 = k.op1 = k.op2 = 0.0;
+          if (kind == K_RE) {
+              k.sp0 = star_ptr[3 * (int64_t)i]; k.sp1 = star_ptr[3 * (int64_t)i + 1]; k.sp2 = star_ptr[3 * (int64_t)i + 2];
+              if (k.sp0 != -1) { k.n3n0 = ndx[k.sp0]; k.n3s0 = sv[k.sp0]; k.op0 = opv[3 * (int64_t)i]; }
+              if (k.sp1 != -1) { k.n3n1 = ndx[k.sp1]; k.n3s1 = sv[k.sp1]; k.op1 = opv[3 * (int64_t)i + 1]; }
+              if (k.sp2 != -1) { k.n3n2 = ndx[k.sp2]; k.n3s2 = sv[k.sp2]; k.op2 = opv[3 * (int64_t)i + 2]; }
+          }
+          sk[lane] = k;
+      }
+      __syncwarp();
+      const int iend = min(i0 + 32, nn);
+      for (int i = i0; i < iend; i++) {
+        const FastK &K = sk[i - i0];
+        const int ci = K.cls, kind = cls_kind(ci), f2 = cls_frame(ci), ndx_i = K.ndx, sv_i = K.sv;
         // node i-1001 drops out of the regular window [i-1000, i)
-        if (i > 2 * kMaxNodeDist) {
-            const int kl = cls_kind(cls[i - 2 * kMaxNodeDist - 1]);
-            loFE += kl == K_FE;
-            loRS += kl == K_RS;
-        }
+        loFE += K.leave == K_FE;
+        loRS += K.leave == K_RS;
         WCand w = {kNeg, -1, -1};
-        double cs_i = 0.0;
+        const double cs_i = K.cs;
 
         if (kind == K_FS || kind == K_RE) {
             // advance the 180-bp boundaries (32 entries per probe)
@@ -432,7 +470,6 @@ __global__ void __launch_bounds__(32 * kFastWarps) k_dp_fast(DevBatch B, const D
             range_far(w, svFE, bxFE, bjFE, clFE, loFE, fFE);
             range_far(w, svRS, bxRS, bjRS, clRS, loRS, fRS);
             if (kind == K_FS) {
-                cs_i = cscore[i] + sscore[i];
                 // near +STOPs: distance-dependent intergenic term (_connection.h:116-123, 52-78)
                 for (int p = fFE + lane; p < curFE; p += 32) {
                     const double s = svFE[p];
@@ -449,25 +486,23 @@ __global__ void __launch_bounds__(32 * kFastWarps) k_dp_fast(DevBatch B, const D
                     wc_merge(w, s + ig_neg, clRS[p], -1);
                 }
             } else {
-                const int sp0 = star_ptr[3 * (int64_t)i], sp1 = star_ptr[3 * (int64_t)i + 1], sp2 = star_ptr[3 * (int64_t)i + 2];
-                const int n3n0 = sp0 != -1 ? ndx[sp0] : 0, n3n1 = sp1 != -1 ? ndx[sp1] : 0, n3n2 = sp2 != -1 ? ndx[sp2] : 0;
-                const int n3s0 = sp0 != -1 ? sv[sp0] : 0, n3s1 = sp1 != -1 ? sv[sp1] : 0, n3s2 = sp2 != -1 ? sv[sp2] : 0;
-                const double op0 = sp0 != -1 ? opv[3 * (int64_t)i] : 0.0, op1 = sp1 != -1 ? opv[3 * (int64_t)i + 1] : 0.0,
-                             op2 = sp2 != -1 ? opv[3 * (int64_t)i + 2] : 0.0;
+                const int sp0 = K.sp0, sp1 = K.sp1, sp2 = K.sp2;
+                const int n3n0 = K.n3n0, n3n1 = K.n3n1, n3n2 = K.n3n2, n3s0 = K.n3s0, n3s1 = K.n3s1, n3s2 = K.n3s2;
+                const double op0 = K.op0, op1 = K.op1, op2 = K.op2;
                 // +STOP with the triple-overlap search (_connection.h:297-334), for one class position
                 auto eval_fe = [&](int p) {
                     const double s = svFE[p];
                     const int nj = cnFE[p];
                     const int left = nj + 2, right = ndx_i - 2;
                     if (s == kNeg || left >= right) return;
-                    const int tj = tbnFE[p];
-                    int maxfr = -1;
+                    int maxfr = -1, tj = kTbNone;
                     double maxval = 0.0;
                     auto probe = [&](int k, int spk, int n3n, int n3s, double op) {
                         if (spk == -1) return;
                         const int ovlp = left - n3s + 3;
                         if (ovlp <= 0 || ovlp >= kMaxOppOvlp) return;
                         if (ovlp >= n3n - left) return;
+                        if (tj == kTbNone) tj = ndx[tbnFE[p]];  // ndx of the traceback node (resolved on demand)
                         if (ovlp >= n3s - tj - 2) return;
                         if (op > maxval) { maxfr = k; maxval = op; }
                     };
@@ -505,8 +540,7 @@ __global__ void __launch_bounds__(32 * kFastWarps) k_dp_fast(DevBatch B, const D
                 }
                 // -STOPs whose ORF spans this stop: operon (_connection.h:343-356); at most one per frame
                 if (lane < 3) {
-                    const int4 dx = dpx[i];
-                    const int j = lane == 0 ? dx.x : (lane == 1 ? dx.y : dx.z);
+                    const int j = lane == 0 ? K.dx : (lane == 1 ? K.dy : K.dz);
                     const int spl = lane == 0 ? sp0 : (lane == 1 ? sp1 : sp2);
                     const double opl = lane == 0 ? op0 : (lane == 1 ? op1 : op2);
                     if (j >= 0 && j >= i - 2 * kMaxNodeDist && spl != -1) wc_merge(w, score[j] + opl, j, -1);
@@ -520,8 +554,7 @@ __global__ void __launch_bounds__(32 * kFastWarps) k_dp_fast(DevBatch B, const D
                 if (lane == 0 && rj >= 0) wc_merge(w, rv, rj, -1);
             }
             // +STOPs inside the ORF (operon, _connection.h:178-191)
-            const int wlo = crank[4 * (int64_t)win_min[i] + 1];
-            for (int p = max(dpx[i].x, wlo) + lane; p < curFE; p += 32) {
+            for (int p = max(K.dx, K.wlo) + lane; p < curFE; p += 32) {
                 const double s = svFE[p];
                 if (s == kNeg) continue;
                 const int j = clFE[p];
@@ -529,15 +562,11 @@ __global__ void __launch_bounds__(32 * kFastWarps) k_dp_fast(DevBatch B, const D
                 wc_merge(w, s + opv[3 * (int64_t)j + f2], j, -1);
             }
         } else {  // K_RS
-            cs_i = cscore[i] + sscore[i];
-            const int4 dx = dpx[i];
-            const int wmin = win_min[i];
             // own -STOP (gene, _connection.h:228-237)
-            if (lane == 0 && dx.x >= wmin && dx.x >= 0 && dx.x < i) wc_merge(w, score[dx.x] + cs_i, dx.x, -1);
+            if (lane == 0 && K.dx >= K.wmin && K.dx >= 0 && K.dx < i) wc_merge(w, score[K.dx] + cs_i, K.dx, -1);
             // +STOPs overlapping the 3' end (_connection.h:239-256)
-            const int wlo = crank[4 * (int64_t)wmin + 1];
             const double cs_diff = cs_i + ig_neg;
-            for (int p = max(dx.y, wlo) + lane; p < min(dx.z, curFE); p += 32) {
+            for (int p = max(K.dy, K.wlo) + lane; p < min(K.dz, curFE); p += 32) {
                 const double s = svFE[p];
                 if (s == kNeg) continue;
                 const int nj = cnFE[p];
@@ -545,7 +574,7 @@ __global__ void __launch_bounds__(32 * kFastWarps) k_dp_fast(DevBatch B, const D
                 const int ovlp = (nj + 2) - (sv_i - 2) + 1;
                 if (ovlp >= kMaxOppOvlp) continue;
                 if ((nj - sv_i) >= (ndx_i - nj + 3)) continue;
-                if ((nj - sv_i) >= (sv_i - 3 - tbnFE[p])) continue;
+                if ((nj - sv_i) >= (sv_i - 3 - ndx[tbnFE[p]])) continue;
                 wc_merge(w, s + cs_diff, clFE[p], -1);
             }
         }
@@ -568,7 +597,7 @@ __global__ void __launch_bounds__(32 * kFastWarps) k_dp_fast(DevBatch B, const D
                 const int p = fe ? curFE : curRS;
                 const double s = tb_i == -1 ? kNeg : sc_i;  // edge artifact rule: nothing leads into it
                 (fe ? svFE : svRS)[p] = s;
-                if (fe) tbnFE[p] = tb_i == -1 ? 0 : ndx[tb_i];
+                if (fe) tbnFE[p] = tb_i;  // traceback node; its ndx is looked up only where a rule needs it
                 double *bx = fe ? bxFE : bxRS;
                 int32_t *bj = fe ? bjFE : bjRS;
                 const double x = s + ig_neg;
@@ -588,6 +617,7 @@ __global__ void __launch_bounds__(32 * kFastWarps) k_dp_fast(DevBatch B, const D
         }
         if ((kind == K_FE || kind == K_RS) && sc_i >= best_sc) { best_sc = sc_i; best_i = i; best_tb = tb_i; }
         __syncwarp();
+      }
     }
     if (lane == 0) {
         const bool ok = best_i >= 0 && best_tb != -1;
@@ -935,8 +965,11 @@ void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, 
                cudaStream_t st) {
     if (n_chains == 0) return;
     // algo 1 (default): k_dp_fast, final scoring only; algo 0: the all-pairs kernel (also the training DP)
-    if (final && algo == 1 && B.dp_sv)
-        k_dp_fast<<<(n_chains + kFastWarps - 1) / kFastWarps, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);
+    if (final && algo >= 1 && B.dp_sv) {
+        const int nb = (n_chains + kFastWarps - 1) / kFastWarps;
+        if (algo == 2) k_dp_fast<4><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);   // up to 128 regs
+        else k_dp_fast<8><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);             // 64 regs, 32 warps/SM
+    }
     else if (final) k_dp<1><<<n_chains, kDpThreads, 0, st>>>(B, models, order, n_chains);
     else k_dp<0><<<n_chains, kDpThreads, 0, st>>>(B, models, order, n_chains);
 }
