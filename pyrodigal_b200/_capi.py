@@ -164,7 +164,7 @@ class Context:
         res = _vp()
         check(lib.pgpu_find_genes_batch(self.handle, ptr(seq), ptr(offsets), len(offsets) - 1, C.byref(opts),
                                         C.byref(res)), self.handle)
-        return Result(res)
+        return Result(res, self)
 
     def upload(self, seq, offsets):
         b = _vp()
@@ -223,7 +223,7 @@ class Batch:
     def run(self, opts):
         res = _vp()
         check(lib.pgpu_batch_run(self.ctx.handle, self.handle, C.byref(opts), C.byref(res)), self.ctx.handle)
-        return Result(res)
+        return Result(res, self.ctx)
 
     def free(self):
         if self.handle:
@@ -240,8 +240,9 @@ class Batch:
 class Result:
     """Owns a pgpu_result; materialises numpy views on demand."""
 
-    def __init__(self, handle):
+    def __init__(self, handle, ctx=None):
         self.handle = handle
+        self.ctx = ctx  # the result returns its pinned buffers to the context when freed: keep it alive
         self.n = lib.pgpu_result_num_contigs(handle)
         self.summary = np.zeros(self.n, dtype=SUMMARY_DTYPE)
         if self.n:

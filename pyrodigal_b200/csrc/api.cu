@@ -45,22 +45,40 @@ struct pgpu_ctx {
     std::vector<DevModel> h_models;
     RawTraining *d_raw = nullptr;
     DevModel *d_models = nullptr;
+    double *d_dcT = nullptr;   // dicodon weights transposed: [4096][n_models], columns sorted by (tt, gc)
     size_t ws_limit = 0;
     cudaEvent_t ev[16];
     int64_t launches = 0;
     int dp_algo = 1;           // 1: k_dp_fast (default), 0: all-pairs k_dp (PGPU_DP_ALGO=0)
-    void *h_stage = nullptr;   // pinned staging for result D2H (grow-only)
-    size_t h_stage_size = 0;
-    void *stage(size_t bytes) {
-        if (bytes > h_stage_size) {
-            if (h_stage) cudaFreeHost(h_stage);
-            h_stage = nullptr;
-            h_stage_size = 0;
-            size_t want = bytes + bytes / 4 + (1 << 20);
-            if (cudaHostAlloc(&h_stage, want, cudaHostAllocDefault) != cudaSuccess) return nullptr;
-            h_stage_size = want;
+    // pinned host buffers for results: recycled through a small free list so that steady-state calls neither
+    // allocate pinned memory nor zero-fill / re-copy result arrays
+    struct PinnedBuf { void *p = nullptr; size_t cap = 0; };
+    std::vector<PinnedBuf> pinned_free;
+    PinnedBuf acquire_pinned(size_t bytes) {
+        int best = -1;
+        for (int i = 0; i < (int)pinned_free.size(); i++)
+            if (pinned_free[i].cap >= bytes && (best < 0 || pinned_free[i].cap < pinned_free[best].cap)) best = i;
+        if (best >= 0) {
+            PinnedBuf b = pinned_free[best];
+            pinned_free.erase(pinned_free.begin() + best);
+            return b;
         }
-        return h_stage;
+        PinnedBuf b;
+        const size_t want = bytes + bytes / 4 + (1 << 16);
+        if (cudaHostAlloc(&b.p, want, cudaHostAllocDefault) != cudaSuccess) { b.p = nullptr; return b; }
+        b.cap = want;
+        return b;
+    }
+    void release_pinned(PinnedBuf b) {
+        if (!b.p) return;
+        if (pinned_free.size() >= 6) {  // bound the pinned footprint: drop the smallest
+            int s = 0;
+            for (int i = 1; i < (int)pinned_free.size(); i++) if (pinned_free[i].cap < pinned_free[s].cap) s = i;
+            if (pinned_free[s].cap < b.cap) { cudaFreeHost(pinned_free[s].p); pinned_free[s] = b; }
+            else cudaFreeHost(b.p);
+            return;
+        }
+        pinned_free.push_back(b);
     }
 };
 
@@ -268,16 +286,28 @@ static void prepare_model(const RawTraining &r, DevModel &m, const RawTraining *
 // ------------------------------------------------------------------------------------------------
 // results
 // ------------------------------------------------------------------------------------------------
+struct ResSeg {  // genes of one sub-batch, in a pinned buffer filled directly by the D2H copy
+    int lo = 0, hi = 0;
+    int64_t g0 = 0, ng = 0;
+    pgpu_ctx::PinnedBuf buf;
+    pgpu_gene *genes = nullptr;
+    pgpu_node *gnodes = nullptr;
+};
+
 struct pgpu_result {
+    pgpu_ctx *ctx = nullptr;
     int n_contigs = 0;
     std::vector<pgpu_contig_summary> summary;
     std::vector<int64_t> gene_off;   // [n+1]
-    std::vector<pgpu_gene> genes;
-    std::vector<pgpu_node> gene_nodes;  // 2 per gene
+    std::vector<ResSeg> segs;
+    int64_t total_genes = 0;
     bool have_nodes = false;
     std::vector<int64_t> node_off;   // [n+1]
     std::vector<pgpu_node> nodes;
     pgpu_stats stats;
+    ~pgpu_result() {
+        if (ctx) for (auto &s : segs) ctx->release_pinned(s.buf);
+    }
 };
 
 struct pgpu_batch {
@@ -530,6 +560,17 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
 
     // ---- per-chain scoring ---------------------------------------------------------------------------
     B.chains = pool.upload(chains);
+    {
+        std::vector<int32_t> eoff(n_ext + 1, 0), elist(n_chains);
+        for (const auto &K : chains) eoff[K.ext + 1]++;
+        for (int e = 0; e < n_ext; e++) eoff[e + 1] += eoff[e];
+        std::vector<int32_t> fillp(eoff.begin(), eoff.end() - 1);
+        for (int k = 0; k < n_chains; k++) elist[fillp[chains[k].ext]++] = k;
+        B.ext_chain_off = pool.upload(eoff);
+        B.ext_chains = pool.upload(elist);
+        B.dcT = ctx->d_dcT;
+        B.n_models = ctx->n_models;
+    }
     B.cscore = pool.alloc<double>(total_cn); B.sscore = pool.alloc<double>(total_cn);
     B.rscore = pool.alloc<double>(total_cn); B.uscore = pool.alloc<double>(total_cn);
     B.tscore = pool.alloc<double>(total_cn);
@@ -552,7 +593,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     MotifOut *d_mot_main = (!meta) ? pool.alloc<MotifOut>(total_cn) : nullptr;
     if (pool.failed) return PGPU_ENOMEM;
     if (total_cn) CK(cudaMemsetAsync(d_tracef, 0xff, total_cn * sizeof(int32_t), st));
-    launch_score_chains(B, ctx->d_models, n_chains, total_cn, ro, d_mot_main, st);
+    launch_score_chains(B, ctx->d_models, n_chains, total_cn, ro, d_mot_main, n_ext, total_nodes, st);
     ctx->launches += 2;
     int e_score = mark();
     launch_overlap(B, ctx->d_models, n_chains, total_cn, ro, 1, st);
@@ -621,7 +662,8 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         // chains with nn == 0 keep coff monotone, so the chain search inside the kernels stays valid; the
         // unused tail of every contig's slot is never touched because kernels index by chain, but the flat
         // index space must be dense: use per-contig capacity as the chain length for the search only.
-        launch_score_chains(F, ctx->d_models, n, ftot, ro, d_mot, st);
+        F.ext_chains = nullptr;  // final pass: one chain per contig, use the per-chain kernel
+        launch_score_chains(F, ctx->d_models, n, ftot, ro, d_mot, n_ext, total_nodes, st);
         launch_pack_nodes(F, n, ftot, d_mot, nullptr, nullptr, 0, d_nodes, st);
         ctx->launches += 4;
         node_out_off = fin_coff;
@@ -653,19 +695,21 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     if (pool.failed) return PGPU_ENOMEM;
     launch_pack_gene_nodes(n, d_summ, d_genes, d_gene_off, d_gene_out_off, d_node_out_off, d_nodes, d_gene_nodes, d_genes_out, st);
     ctx->launches++;
-    const size_t g0 = res->genes.size();
-    res->genes.resize(g0 + ng);
-    res->gene_nodes.resize(2 * (g0 + ng));
-    char *stage = nullptr;
+    ResSeg seg;
+    seg.lo = lo; seg.hi = hi; seg.g0 = res->total_genes; seg.ng = ng;
     const size_t gbytes = ng * sizeof(pgpu_gene), nbytes = 2 * ng * sizeof(pgpu_node);
     if (ng) {
-        // D2H through the context's pinned staging buffer (pageable destinations would serialise the copy)
-        stage = (char *)ctx->stage(gbytes + nbytes);
-        if (!stage) return fail(ctx, PGPU_ENOMEM, "pinned staging allocation failed");
-        CK(cudaMemcpyAsync(stage, d_genes_out, gbytes, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(stage + gbytes, d_gene_nodes, nbytes, cudaMemcpyDeviceToHost, st));
+        seg.buf = ctx->acquire_pinned(gbytes + nbytes);
+        if (!seg.buf.p) return fail(ctx, PGPU_ENOMEM, "pinned result allocation failed");
+        seg.genes = (pgpu_gene *)seg.buf.p;
+        seg.gnodes = (pgpu_node *)((char *)seg.buf.p + gbytes);
+        CK(cudaMemcpyAsync(seg.genes, d_genes_out, gbytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(seg.gnodes, d_gene_nodes, nbytes, cudaMemcpyDeviceToHost, st));
         S.d2h_bytes += gbytes + nbytes;
     }
+    const int64_t g0 = res->total_genes;
+    res->segs.push_back(seg);
+    res->total_genes += ng;
     if (opts.want_nodes) {
         const size_t n0 = res->nodes.size();
         int64_t tot = 0;
@@ -685,13 +729,9 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     }
     int e_d2h = mark();
     CK(cudaStreamSynchronize(st));
-    if (ng) {
-        memcpy(res->genes.data() + g0, stage, gbytes);
-        memcpy(res->gene_nodes.data() + 2 * g0, stage + gbytes, nbytes);
-    }
     for (int c = 0; c < n; c++) {
         res->summary[lo + c] = summ[c];
-        res->gene_off[lo + c + 1] = (int64_t)g0 + gene_out_off[c + 1];
+        res->gene_off[lo + c + 1] = g0 + gene_out_off[c + 1];
     }
     S.total_genes += ng;
     auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]); return (double)t; };
@@ -742,6 +782,7 @@ static int run_all(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, co
     if (ctx->n_models == 0) return fail(ctx, PGPU_ESTATE, "no models loaded");
     cudaSetDevice(ctx->device);
     pgpu_result *res = new pgpu_result();
+    res->ctx = ctx;
     res->n_contigs = n;
     res->summary.resize(n);
     res->gene_off.assign(n + 1, 0);
@@ -812,8 +853,9 @@ void pgpu_destroy(pgpu_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->d_raw) cudaFree(ctx->d_raw);
     if (ctx->d_models) cudaFree(ctx->d_models);
+    if (ctx->d_dcT) cudaFree(ctx->d_dcT);
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
-    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (auto &b : ctx->pinned_free) cudaFreeHost(b.p);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -833,6 +875,24 @@ int pgpu_set_models(pgpu_ctx *ctx, const void *blobs, int n, size_t stride) {
     CK(cudaMalloc(&ctx->d_models, n * sizeof(DevModel)));
     ctx->h_models.resize(n);
     for (int k = 0; k < n; k++) prepare_model(ctx->h_raw[k], ctx->h_models[k], ctx->d_raw + k);
+    {
+        // transposed dicodon table: models that are evaluated together (same table, neighbouring GC) get
+        // neighbouring columns, so the lanes of k_coding_orf read one or two cache lines per codon
+        std::vector<int> ord(n);
+        std::iota(ord.begin(), ord.end(), 0);
+        std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
+            const RawTraining &x = ctx->h_raw[a], &y = ctx->h_raw[b];
+            return x.trans_table != y.trans_table ? x.trans_table < y.trans_table : x.gc < y.gc;
+        });
+        std::vector<double> t((size_t)4096 * n);
+        for (int c = 0; c < n; c++) {
+            ctx->h_models[ord[c]].col = c;
+            for (int i = 0; i < 4096; i++) t[(size_t)i * n + c] = ctx->h_raw[ord[c]].gene_dc[i];
+        }
+        if (ctx->d_dcT) { cudaFree(ctx->d_dcT); ctx->d_dcT = nullptr; }
+        CK(cudaMalloc(&ctx->d_dcT, t.size() * sizeof(double)));
+        CK(cudaMemcpy(ctx->d_dcT, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     CK(cudaMemcpy(ctx->d_raw, ctx->h_raw.data(), n * sizeof(RawTraining), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_models, ctx->h_models.data(), n * sizeof(DevModel), cudaMemcpyHostToDevice));
     ctx->n_models = n;
@@ -914,19 +974,27 @@ int pgpu_result_summaries(const pgpu_result *res, pgpu_contig_summary *dst) {
 int pgpu_result_genes(const pgpu_result *res, int contig, pgpu_gene *dst) {
     if (!res || contig < 0 || contig >= res->n_contigs) return PGPU_EINVAL;
     const int64_t a = res->gene_off[contig], b = res->gene_off[contig + 1];
-    if (b > a) { if (!dst) return PGPU_EINVAL; memcpy(dst, res->genes.data() + a, (b - a) * sizeof(pgpu_gene)); }
+    if (b > a) {
+        if (!dst) return PGPU_EINVAL;
+        for (const auto &s : res->segs)
+            if (contig >= s.lo && contig < s.hi) { memcpy(dst, s.genes + (a - s.g0), (b - a) * sizeof(pgpu_gene)); break; }
+    }
     return PGPU_OK;
 }
 
 int pgpu_result_all_genes(const pgpu_result *res, pgpu_gene *dst) {
     if (!res) return PGPU_EINVAL;
-    if (!res->genes.empty()) { if (!dst) return PGPU_EINVAL; memcpy(dst, res->genes.data(), res->genes.size() * sizeof(pgpu_gene)); }
+    if (res->total_genes && !dst) return PGPU_EINVAL;
+    for (const auto &s : res->segs)
+        if (s.ng) memcpy(dst + s.g0, s.genes, s.ng * sizeof(pgpu_gene));
     return PGPU_OK;
 }
 
 int pgpu_result_gene_nodes(const pgpu_result *res, pgpu_node *dst) {
     if (!res) return PGPU_EINVAL;
-    if (!res->gene_nodes.empty()) { if (!dst) return PGPU_EINVAL; memcpy(dst, res->gene_nodes.data(), res->gene_nodes.size() * sizeof(pgpu_node)); }
+    if (res->total_genes && !dst) return PGPU_EINVAL;
+    for (const auto &s : res->segs)
+        if (s.ng) memcpy(dst + 2 * s.g0, s.gnodes, 2 * s.ng * sizeof(pgpu_node));
     return PGPU_OK;
 }
 

@@ -53,6 +53,8 @@ struct DevModel {
     uint8_t sd_best[2][15][64];    // best SD bin for (exact|mismatch, offset, 6-bit match pattern)
     const double *gene_dc;         // device pointers into the raw blob
     const double *mot_wt;
+    int32_t col;                   // column of this model in the transposed dicodon table (sorted by tt, gc)
+    int32_t pad;
 };
 
 struct ContigInfo {
@@ -120,6 +122,10 @@ struct DevBatch {
     int32_t *cbase;       // [4 * ext]: start of each class segment in clist (relative to node_off)
     int32_t *cndx;        // ndx in class order: cndx[p] = ndx[clist[p]]
     int4 *dpx;            // per node: pre-resolved DP candidates / ranges (see k_dp_index)
+    int32_t *ext_chain_off;   // [n_ext + 1] chains that use an extraction ...
+    int32_t *ext_chains;      // ... chain indices, grouped by extraction
+    const double *dcT;        // dicodon table transposed: dcT[index * n_models + DevModel.col]
+    int32_t n_models;
     // chains
     ChainInfo *chains;
     double *cscore, *sscore, *rscore, *uscore, *tscore;  // per chain-node

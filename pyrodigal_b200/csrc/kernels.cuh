@@ -16,7 +16,7 @@ void launch_word_scan(const DevBatch &B, int64_t nwords, int *block_sums, int *t
 // score_kernels.cu
 void launch_node_prep(const DevBatch &B, int n_ext, int total_nodes, int seq_parts, cudaStream_t st);
 void launch_score_chains(const DevBatch &B, const DevModel *models, int n_chains, int64_t total_chain_nodes,
-                         RunOpts o, void *mot_out, cudaStream_t st);
+                         RunOpts o, void *mot_out, int n_ext, int total_nodes, cudaStream_t st);
 void launch_overlap(const DevBatch &B, const DevModel *models, int n_chains, int64_t total_chain_nodes, RunOpts o,
                     int flag, cudaStream_t st);
 void launch_opv(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, cudaStream_t st);

@@ -275,6 +275,107 @@ __global__ void __launch_bounds__(128) k_coding(DevBatch B, const DevModel *__re
 }
 
 // --------------------------------------------------------------------------------------------------
+// raw coding score, warp per ORF: all models that share an extraction walk the same codons, so the lanes
+// of a warp take one model each -- identical control flow (no divergence), codon loads are warp-uniform
+// broadcasts and the per-model dicodon weights of one index sit next to each other in the transposed
+// table.  Summation order per (ORF, model) is unchanged, so results stay bit-identical.
+// --------------------------------------------------------------------------------------------------
+constexpr int kOrfWarps = 8;
+
+__global__ void __launch_bounds__(32 * kOrfWarps) k_coding_orf(DevBatch B, const DevModel *__restrict__ models, int n_ext,
+                                                                int total_nodes) {
+    __shared__ int s_first;
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kOrfWarps + (threadIdx.x >> 5);  // flat extraction-node index
+    if (threadIdx.x == 0) s_first = find_ext(B.exts, n_ext, min(blockIdx.x * kOrfWarps, total_nodes - 1));
+    __syncthreads();
+    if (t >= total_nodes) return;
+    int e = s_first;
+    while (e + 1 < n_ext && B.exts[e + 1].node_off <= t) e++;
+    const ExtractInfo X = B.exts[e];
+    const int32_t *__restrict__ cbase = B.cbase + 4 * e;
+    const int tl = t - X.node_off, nn = X.nn;
+    const int n_fe = cbase[2] - cbase[1], n_re = nn - cbase[3];
+    if (tl >= n_fe + n_re) return;  // only the first (#STOP nodes) warps of an extraction have work
+    const int z = (B.clist + X.node_off)[tl < n_fe ? cbase[1] + tl : cbase[3] + (tl - n_fe)];
+    const uint8_t *__restrict__ cls = B.cls + X.node_off;
+    const int32_t *__restrict__ ndx = B.ndx + X.node_off;
+    const int32_t *__restrict__ sv = B.stop_val + X.node_off;
+    const uint8_t *__restrict__ d = B.digits + X.doff;
+    const uint8_t *__restrict__ cod = B.cod + X.doff;
+    const double *__restrict__ dcT = B.dcT;
+    const int nm = B.n_models;
+    const int c = cls[z], f = cls_frame(c), my = ndx[z];
+    const bool rev = c & CLS_REV;
+    const int ch0 = B.ext_chain_off[e], nch = B.ext_chain_off[e + 1] - ch0;
+
+    for (int c0 = 0; c0 < nch; c0 += 32) {
+        const bool active = c0 + lane < nch;
+        const int chain = active ? B.ext_chains[ch0 + c0 + lane] : 0;
+        const ChainInfo C = B.chains[active ? chain : B.ext_chains[ch0]];
+        const DevModel &M = models[C.model];
+        const int col = M.col;
+        double *__restrict__ cscore = B.cscore + C.coff;
+
+        // sweep A: dicodon log-odds accumulated from the stop towards each start (lib.pyx:2149-2173)
+        int far = -1, last = my;
+        double acc = 0.0;
+        if (!rev) {
+            int low = cod[my] & 63;
+            for (int i = z - 1; i >= 0; i--) {
+                const int ci = cls[i];
+                if ((ci & CLS_REV) || cls_frame(ci) != f) continue;
+                if (cls_is_stop(ci)) break;
+                const int ni = ndx[i];
+                for (int j = last - 3; j >= ni; j -= 3) {
+                    const int cj = cod[j] & 63;
+                    acc += dcT[(size_t)(cj | (low << 6)) * nm + col];
+                    low = cj;
+                }
+                if (active) cscore[i] = acc;
+                last = ni;
+                far = i;
+            }
+        } else {
+            int low = rcode_at(d, cod, my);
+            for (int i = z + 1; i < nn; i++) {
+                const int ci = cls[i];
+                if (!(ci & CLS_REV) || cls_frame(ci) != f) continue;
+                if (cls_is_stop(ci)) break;
+                const int ni = ndx[i];
+                for (int j = last + 3; j <= ni; j += 3) {
+                    const int cj = rcode_at(d, cod, j);
+                    acc += dcT[(size_t)(cj | (low << 6)) * nm + col];
+                    low = cj;
+                }
+                if (active) cscore[i] = acc;
+                last = ni;
+                far = i;
+            }
+        }
+        if (far < 0) continue;
+
+        // sweep B: the two penalty passes fused, walking back towards the stop (lib.pyx:2175-2236)
+        double s2 = -10000.0, s3 = -10000.0;
+        const int step = rev ? -1 : 1;
+        for (int i = far; i != z; i += step) {
+            const int ci = cls[i];
+            if (((ci & CLS_REV) != 0) != rev || cls_frame(ci) != f) continue;
+            double cs = active ? cscore[i] : 0.0;
+            if (cs > s2) s2 = cs; else cs -= (s2 - cs);
+            const double gsize = rev ? (((double)ndx[i] - sv[i]) + 3.0) / 3.0 : (((double)sv[i] - ndx[i]) + 3.0) / 3.0;
+            double lfac;
+            if (gsize > 1000.0) lfac = M.lfac_span * (gsize - 80) / 920.0;
+            else lfac = M.lfac[(int)gsize];
+            if (lfac > s3) s3 = lfac; else lfac -= fmax(fmin(s3 - lfac, lfac), 0.0);
+            if (lfac > 3.0 && cs < 0.5 * lfac) cs = 0.5 * lfac;
+            cs += lfac;
+            if (active) cscore[i] = cs;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
 // start scoring: RBS / upstream motif / type / upstream composition / penalties (lib.pyx:2331-2487)
 // --------------------------------------------------------------------------------------------------
 
@@ -591,10 +692,13 @@ void launch_node_prep(const DevBatch &B, int n_ext, int total_nodes, int seq_par
     k_class_index<<<(n_ext * 32 + 127) / 128, 128, 0, st>>>(B, n_ext);
 }
 void launch_score_chains(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o,
-                         void *mot_out, cudaStream_t st) {
+                         void *mot_out, int n_ext, int total_nodes, cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
     const unsigned nb = (unsigned)((total + 127) / 128);
-    k_coding<<<nb, 128, 0, st>>>(B, models, n_chains, total);
+    if (B.ext_chains && B.dcT && n_ext > 0 && total_nodes > 0)
+        k_coding_orf<<<(total_nodes + kOrfWarps - 1) / kOrfWarps, 32 * kOrfWarps, 0, st>>>(B, models, n_ext, total_nodes);
+    else
+        k_coding<<<nb, 128, 0, st>>>(B, models, n_chains, total);
     k_start_score<<<nb, 128, 0, st>>>(B, models, n_chains, total, o, (MotifOut *)mot_out);
 }
 void launch_opv(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, cudaStream_t st) {
