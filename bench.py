@@ -55,6 +55,44 @@ def make_contigs(first, count, seed=4):
     return flat, offsets
 
 
+def shard_range(rank, contigs_per_gpu):
+    """contigs owned by `rank`: a disjoint slice of the 100k-contig configuration (weak scaling)"""
+    return rank * contigs_per_gpu, contigs_per_gpu
+
+
+class Dist:
+    """torch.distributed plumbing of the bench (barrier, max over ranks, sums); nccl on GPUs, gloo in CPU tests"""
+
+    def __init__(self, backend=None, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.device = device if device is not None else "cpu"
+        if self.world > 1 and not dist.is_initialized():
+            kw = {}
+            if backend == "nccl":
+                kw["device_id"] = torch.device(self.device)
+            dist.init_process_group(backend, **kw)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        if str(self.device).startswith("cuda"):
+            self.torch.cuda.synchronize()
+
+    def reduce(self, values, op="sum"):
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+    def close(self):
+        if self.world > 1 and self.dist.is_initialized():
+            self.dist.destroy_process_group()
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
 
@@ -189,14 +227,13 @@ def main():
 
     # ------------------------------------------------------------------ our arm --------------------
     import torch
-    import torch.distributed as dist
     from pyrodigal_b200 import _capi
     import refutil as R
 
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    flat, offsets = make_contigs(rank * args.contigs, args.contigs)
+    D = Dist("nccl", f"cuda:{local_rank}")
+    first, count = shard_range(rank, args.contigs)
+    flat, offsets = make_contigs(first, count)
     bp = int(offsets[-1])
     # pinned host staging of the step's input (the e2e leg copies from here every step)
     pinned = torch.empty(bp, dtype=torch.uint8).pin_memory()
@@ -207,14 +244,9 @@ def main():
     ctx.set_models(R.bins_blob(), 50)
     opts = _capi.make_opts(meta=True)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     def timed(fn, steps):
         """K steps bracketed by barrier + synchronize; CUDA events on the library's stream; max over ranks"""
-        barrier()
+        D.barrier()
         ctx.timer_start()
         t0 = time.perf_counter()
         last = None
@@ -223,11 +255,9 @@ def main():
         ms = ctx.timer_stop()
         wall = (time.perf_counter() - t0) * 1e3
         torch.cuda.synchronize()
-        t = torch.tensor([ms, wall], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        barrier()
-        return float(t[0]), float(t[1]), last
+        ms, wall = D.reduce([ms, wall], "max")
+        D.barrier()
+        return ms, wall, last
 
     # ---- device-resident leg ("value") ----
     batch = ctx.upload(host, offsets)
@@ -248,11 +278,8 @@ def main():
     st2 = res2.stats
     batch.free()
 
-    tot = torch.tensor([bp, stats["pairs"], stats["dp_steps"], genes_rank, stats["kernel_launches"]],
-                       dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    tot_bp, tot_pairs, tot_steps, tot_genes, tot_launch = (float(x) for x in tot)
+    tot_bp, tot_pairs, tot_steps, tot_genes, tot_launch = D.reduce(
+        [bp, stats["pairs"], stats["dp_steps"], genes_rank, stats["kernel_launches"]], "sum")
 
     if rank == 0:
         per_step = ms / args.steps
@@ -288,8 +315,7 @@ def main():
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
 
 
 if __name__ == "__main__":
