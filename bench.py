@@ -301,8 +301,9 @@ def main():
                          "algorithmic_bytes_per_dp_step": DP_BYTES_PER_STEP, "dp_steps_per_launch": int(stats["dp_steps"]),
                          "kernel_ms": dp_ms, "node_pairs_per_s": stats["pairs"] / (dp_ms * 1e-3) if dp_ms > 0 else None},
             "node_pairs_per_s_job": tot_pairs / (per_step * 1e-3),
-            "phases_ms_rank0": {k: stats[k] for k in ("ms_encode", "ms_extract", "ms_score", "ms_overlap", "ms_dp",
-                                                      "ms_trace", "ms_final", "ms_d2h", "ms_total_device")},
+            "phases_ms_rank0": dict({k: stats[k] for k in ("ms_encode", "ms_extract", "ms_score", "ms_overlap", "ms_dp",
+                                                           "ms_trace", "ms_final", "ms_d2h", "ms_total_device")},
+                                    host_issue_ms=stats["host_ms"]),
             "wall_ms_per_step": wall_ms / args.steps,
             "totals": {"bp": int(tot_bp), "genes": int(tot_genes), "dp_steps": int(tot_steps), "pairs": int(tot_pairs),
                        "chains_rank0": int(stats["n_chains"]), "nodes_rank0": int(stats["total_nodes"])},

@@ -41,7 +41,9 @@ class Stats(C.Structure):
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d["host_ms"] = [self.reserved[i] for i in range(4)]  # host time issuing work before each of the 4 syncs
+        return d
 
 
 GENE_DTYPE = np.dtype([("begin", "<i4"), ("end", "<i4"), ("start_ndx", "<i4"), ("stop_ndx", "<i4")])

@@ -7,6 +7,7 @@
 //   coding score -> start score -> overlapping starts -> DP -> winner/traceback/genes -> final re-score
 //   (meta) -> pack -> [sync: gene counts] -> D2H.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -49,7 +50,7 @@ struct pgpu_ctx {
     size_t ws_limit = 0;
     cudaEvent_t ev[16];
     int64_t launches = 0;
-    int dp_algo = 1;           // 1: k_dp_fast (default), 0: all-pairs k_dp (PGPU_DP_ALGO=0)
+    int dp_algo = 3;           // 3: k_dp_dq (default), 1/2: k_dp_fast, 0: all-pairs k_dp (PGPU_DP_ALGO=n)
     // pinned host buffers for results: recycled through a small free list so that steady-state calls neither
     // allocate pinned memory nor zero-fill / re-copy result arrays
     struct PinnedBuf { void *p = nullptr; size_t cap = 0; };
@@ -353,6 +354,14 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     pgpu_stats &S = res->stats;
     int evi = 0;
     auto mark = [&]() { cudaEventRecord(ctx->ev[evi], st); return evi++; };
+    auto now = []() { return std::chrono::steady_clock::now(); };
+    auto since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    auto t_host = now();
+    const bool trace = getenv("PGPU_TRACE") != nullptr;
+    const auto t_begin = now();
+    auto tr = [&](const char *what) { if (trace) fprintf(stderr, "[pgpu %8.2f ms] %s\n", since(t_begin), what); };
 
     // ---- stage A: sequences ----------------------------------------------------------------------
     std::vector<ContigInfo> contigs(n);
@@ -410,7 +419,9 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     CK(cudaMemcpyAsync(h_gc.data(), B.gc_count, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h_unk.data(), B.unknown, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     int e_enc = mark();
+    S.reserved[0] += since(t_host);  // host: stage A issue
     CK(cudaStreamSynchronize(st));
+    t_host = now();
     S.d2h_bytes += 8 * (int64_t)n;
 
     // masks: sort by (contig, begin) and build the per-contig table
@@ -427,6 +438,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     }
     B.masks = pool.upload(mask_tab);
 
+    tr("sync1 done (gc counts)");
     // ---- stage B: plan extractions and chains ------------------------------------------------------
     std::vector<ExtractInfo> exts;
     std::vector<ChainInfo> chains;
@@ -482,6 +494,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     contig_ext_begin[n] = (int)exts.size();
     const int n_ext = (int)exts.size(), n_chains = (int)chains.size();
 
+    tr("planned chains");
     // ---- extraction pass 1: mark + scan ------------------------------------------------------------
     B.bits_fwd = pool.alloc<uint32_t>(nwords + 8, true);
     B.bits_rev = pool.alloc<uint32_t>(nwords + 8, true);
@@ -512,8 +525,11 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         CK(cudaMemcpyAsync(h_base.data(), d_out, (n_ext + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     }
     int e_mark = mark();
+    S.reserved[1] += since(t_host);  // host: chain planning + mark/scan issue
     CK(cudaStreamSynchronize(st));
+    t_host = now();
     S.d2h_bytes += 4 * (int64_t)(n_ext + 1);
+    tr("sync2 done (node counts)");
     const int total_nodes = h_base[n_ext];
     if (total_nodes < 0) return fail(ctx, PGPU_EINVAL, "too many nodes in one sub-batch");
     for (int e = 0; e < n_ext; e++) { exts[e].node_off = h_base[e]; exts[e].nn = h_base[e + 1] - h_base[e]; }
@@ -533,6 +549,9 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     B.cbase = pool.alloc<int32_t>(4 * (size_t)n_ext + 4);
     B.cndx = pool.alloc<int32_t>(total_nodes);
     B.dpx = pool.alloc<int4>(total_nodes);
+    B.ig_node = pool.alloc<int32_t>(total_nodes + 1);
+    B.ig_ndx = pool.alloc<int32_t>(total_nodes + 1);
+    B.dqx = pool.alloc<int4>(total_nodes);
     unsigned long long *d_ext_pairs = pool.alloc<unsigned long long>(n_ext, true);
     if (pool.failed) return PGPU_ENOMEM;
     launch_extract_fill(B, n_ext, ro, st);
@@ -558,6 +577,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         return PGPU_OK;
     }
 
+    tr("issued fill/prep");
     // ---- per-chain scoring ---------------------------------------------------------------------------
     B.chains = pool.upload(chains);
     {
@@ -582,7 +602,10 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     B.ov_mark = pool.alloc<int8_t>(total_cn + 16);
     B.chain_ipath = pool.alloc<int32_t>(n_chains);
     B.chain_score = pool.alloc<double>(n_chains);
-    if (ctx->dp_algo >= 1) {
+    if (ctx->dp_algo >= 3) {
+        B.dp_svig = pool.alloc<double>(total_cn);
+        B.dp_tbig = pool.alloc<int32_t>(total_cn);
+    } else if (ctx->dp_algo >= 1) {
         B.dp_sv = pool.alloc<double>(total_cn);
         B.dp_tbn = pool.alloc<int32_t>(total_cn);
         B.dp_bx = pool.alloc<double>(total_cn / 16 + 2 * (size_t)n_chains + 8);
@@ -612,6 +635,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         return PGPU_OK;
     }
 
+    tr("issued scoring/overlap");
     // ---- DP: largest chains first ---------------------------------------------------------------------
     std::vector<int32_t> order(n_chains);
     std::iota(order.begin(), order.end(), 0);
@@ -633,6 +657,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     pgpu_contig_summary *d_summ = pool.upload(summ);
     int32_t *d_winner_chain = pool.alloc<int32_t>(n);
     if (pool.failed) return PGPU_ENOMEM;
+    tr("uploaded dp tables");
     launch_dp(B, ctx->d_models, d_order, n_chains, 1, ctx->dp_algo, st);
     ctx->launches++;
     int e_dp = mark();
@@ -641,6 +666,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     ctx->launches++;
     int e_trace = mark();
 
+    tr("issued dp/trace");
     // ---- final node records ------------------------------------------------------------------------------
     pgpu_node *d_nodes = nullptr;
     int64_t *d_node_out_off = nullptr;
@@ -681,10 +707,13 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     std::vector<unsigned long long> h_ext_pairs(n_ext);
     if (n_ext) CK(cudaMemcpyAsync(h_ext_pairs.data(), d_ext_pairs, n_ext * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(summ.data(), d_summ, n * sizeof(pgpu_contig_summary), cudaMemcpyDeviceToHost, st));
+    S.reserved[2] += since(t_host);  // host: everything issued between the node-count sync and the summary sync
     CK(cudaStreamSynchronize(st));
+    t_host = now();
     S.d2h_bytes += n * sizeof(pgpu_contig_summary);
     for (const auto &K : chains) S.pairs += (int64_t)h_ext_pairs[K.ext];
 
+    tr("sync3 done (summaries)");
     // ---- compact genes + their start/stop node records, copy back ---------------------------------------
     std::vector<int64_t> gene_out_off(n + 1, 0);
     for (int c = 0; c < n; c++) gene_out_off[c + 1] = gene_out_off[c] + summ[c].n_genes;
@@ -727,12 +756,15 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         S.d2h_bytes += tot * sizeof(pgpu_node);
         res->have_nodes = true;
     }
+    tr("issued pack + d2h");
     int e_d2h = mark();
+    S.reserved[3] += since(t_host);  // host: result compaction issue
     CK(cudaStreamSynchronize(st));
     for (int c = 0; c < n; c++) {
         res->summary[lo + c] = summ[c];
         res->gene_off[lo + c + 1] = g0 + gene_out_off[c + 1];
     }
+    tr("sync4 done");
     S.total_genes += ng;
     auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]); return (double)t; };
     S.ms_h2d += ms(e_start, e_h2d);
@@ -793,6 +825,14 @@ static int run_all(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, co
     // ~0.06 nodes/bp, up to ~26 chains): budget 160 B/bp against the workspace limit
     size_t freeb = 0, totalb = 0;
     cudaMemGetInfo(&freeb, &totalb);
+    {   // blocks cached by the stream-ordered pool are reusable: count them as free
+        cudaMemPool_t mp;
+        uint64_t reserved = 0, used = 0;
+        if (cudaDeviceGetDefaultMemPool(&mp, ctx->device) == cudaSuccess &&
+            cudaMemPoolGetAttribute(mp, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+            cudaMemPoolGetAttribute(mp, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+            freeb += reserved - used;
+    }
     size_t limit = ctx->ws_limit ? ctx->ws_limit : (size_t)(0.6 * (double)freeb);
     const int64_t bp_budget = std::max<int64_t>((int64_t)(limit / 160), 1 << 20);
     RunPlan plan;
@@ -1117,7 +1157,10 @@ int pgpu_score_connections(pgpu_ctx *ctx, int n, const int32_t *ndx, const int32
     B.chain_ipath = pool.alloc<int32_t>(1); B.chain_score = pool.alloc<double>(1);
     B.cndx = pool.alloc<int32_t>(n);
     B.dpx = pool.alloc<int4>(n);
-    if (final && ctx->dp_algo >= 1) {
+    B.ig_node = pool.alloc<int32_t>(n + 1); B.ig_ndx = pool.alloc<int32_t>(n + 1); B.dqx = pool.alloc<int4>(n);
+    if (final && ctx->dp_algo >= 3) {
+        B.dp_svig = pool.alloc<double>(n); B.dp_tbig = pool.alloc<int32_t>(n);
+    } else if (final && ctx->dp_algo >= 1) {
         B.dp_sv = pool.alloc<double>(n); B.dp_tbn = pool.alloc<int32_t>(n);
         B.dp_bx = pool.alloc<double>(n / 16 + 16); B.dp_bj = pool.alloc<int32_t>(n / 16 + 16);
     }

@@ -122,6 +122,9 @@ struct DevBatch {
     int32_t *cbase;       // [4 * ext]: start of each class segment in clist (relative to node_off)
     int32_t *cndx;        // ndx in class order: cndx[p] = ndx[clist[p]]
     int4 *dpx;            // per node: pre-resolved DP candidates / ranges (see k_dp_index)
+    int32_t *ig_node;     // merged stream of +STOP and -start nodes ("intergenic sources") in node order:
+    int32_t *ig_ndx;      //   node index (bit 31 set for +STOP) and position
+    int4 *dqx;            // per node: candidates / ranges in merged-stream positions (k_dp_index)
     int32_t *ext_chain_off;   // [n_ext + 1] chains that use an extraction ...
     int32_t *ext_chains;      // ... chain indices, grouped by extraction
     const double *dcT;        // dicodon table transposed: dcT[index * n_models + DevModel.col]
@@ -141,6 +144,8 @@ struct DevBatch {
     int32_t *dp_tbn;      // ndx of the traceback node of a +STOP node
     double *dp_bx;        // per 16-entry block: max of (sv + ig_neg), ties -> later entry
     int32_t *dp_bj;       // node index of that maximum
+    double *dp_svig;      // merged-stream order: score of a finalized +STOP / -start, -DBL_MAX if no traceback
+    int32_t *dp_tbig;     // merged-stream order: traceback node of a +STOP
     // per chain results
     int32_t *chain_ipath;
     double *chain_score;

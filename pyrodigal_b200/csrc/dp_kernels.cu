@@ -627,6 +627,308 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_fast(DevBatch B, c
 }
 
 // --------------------------------------------------------------------------------------------------
+// k_dp_dq: like k_dp_fast, but the constant-term (far intergenic) maximum is a sliding-window maximum kept
+// in a monotone deque (shared memory, per warp), so a DP step costs O(1) instead of a range query:
+//   * +STOP and -start nodes form one merged stream ("intergenic sources"); both add the same constant
+//     (-0.15*st_wt) once they are more than 180 bp behind the target, for both target kinds that use them
+//     (+start and -STOP), and those targets always have the regular window [i-1000, i);
+//   * entries enter the deque when they cross the 180-bp boundary (values fl(score + const); an entry pops
+//     every older entry with a value <= its own, so the front is the maximum with ties -> latest j) and leave
+//     it when they drop out of the window;
+//   * everything within 180 bp, and every geometrically pinned candidate, is evaluated individually.
+// The warp arg-max uses redux.sync on an order-preserving integer image of the doubles.
+// --------------------------------------------------------------------------------------------------
+constexpr int kDqCap = 64;
+
+struct DqK {  // per-target constants, staged 32 targets at a time
+    int32_t ndx, sv, cls, leave;
+    int32_t x, y, z, w;  // dqx
+    int32_t sp0, sp1, sp2;
+    int32_t n3n0, n3n1, n3n2, n3s0, n3s1, n3s2;
+    int32_t pad;
+    double op0, op1, op2;
+    double cs;
+};
+
+// arg-max over the warp of (v, j): larger v wins, equal v -> larger j; returns the winner in every lane
+__device__ __forceinline__ void warp_argmax(double &v, int &j, int &fr) {
+    if (v == 0.0) v = 0.0;  // -0.0 and +0.0 compare equal as doubles: give them one integer image
+    long long b = __double_as_longlong(v);
+    b = b >= 0 ? b : (b ^ 0x7fffffffffffffffLL);  // order-preserving map double -> int64
+    const int hi = (int)(b >> 32);
+    const unsigned lo = (unsigned)b;
+    const int mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    const bool top = hi == mhi && lo == mlo;
+    const int mj = __reduce_max_sync(0xffffffffu, top ? j : -1);
+    const int mfr = __reduce_max_sync(0xffffffffu, (top && j == mj) ? fr + 1 : 0) - 1;
+    long long r = ((long long)mhi << 32) | (long long)mlo;
+    r = r >= 0 ? r : (r ^ 0x7fffffffffffffffLL);
+    v = __longlong_as_double(r);
+    j = mj;
+    fr = mfr;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, const DevModel *__restrict__ models,
+                                                                   const int32_t *__restrict__ order, int n_chains) {
+    __shared__ DqK s_k[kFastWarps][32];
+    __shared__ double s_dqv[kFastWarps][kDqCap];
+    __shared__ int32_t s_dqj[kFastWarps][kDqCap];
+    const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
+    const int slot = blockIdx.x * kFastWarps + wslot;
+    if (slot >= n_chains) return;
+    const int chain = order ? order[slot] : slot;
+    const ChainInfo C = B.chains[chain];
+    const int nn = C.nn;
+    if (nn == 0) {
+        if (lane == 0) { B.chain_ipath[chain] = -1; B.chain_score[chain] = 0.0; }
+        return;
+    }
+    const DevModel &M = models[C.model];
+    const int32_t *__restrict__ ndx = B.ndx + C.node_off;
+    const int32_t *__restrict__ sv = B.stop_val + C.node_off;
+    const uint8_t *__restrict__ cls = B.cls + C.node_off;
+    const int32_t *__restrict__ ig_node = B.ig_node + C.node_off;
+    const int32_t *__restrict__ ig_ndx = B.ig_ndx + C.node_off;
+    const int4 *__restrict__ dqx = B.dqx + C.node_off;
+    const double *__restrict__ cscore = B.cscore + C.coff;
+    const double *__restrict__ sscore = B.sscore + C.coff;
+    const double *__restrict__ opv = B.opv + 3 * C.coff;
+    const int32_t *__restrict__ star_ptr = B.star_ptr + 3 * C.coff;
+    double *score = B.score + C.coff;       // written and re-read by this warp: no read-only path
+    int32_t *traceb = B.traceb + C.coff;
+    int8_t *ov_mark = B.ov_mark + C.coff;
+    double *svig = B.dp_svig + C.coff;
+    int32_t *tbig = B.dp_tbig + C.coff;
+    DqK *sk = s_k[wslot];
+    double *dqv = s_dqv[wslot];
+    int32_t *dqj = s_dqj[wslot];
+    const double ig_neg = M.ig_neg;
+
+    // merged-stream cursors: cur = finalized entries, lo = first entry inside [i-1000, i), far = first entry
+    // that is NOT more than 180 bp behind the target
+    int cur = 0, lo = 0, far = 0;
+    int dq_head = 0, dq_cnt = 0;
+    bool dq_ok = true;
+    double rc_v0 = kNeg, rc_v1 = kNeg, rc_v2 = kNeg;
+    int rc_j0 = -1, rc_j1 = -1, rc_j2 = -1;
+    double best_sc = -1.0;
+    int best_i = -1, best_tb = -1;
+
+    for (int i0 = 0; i0 < nn; i0 += 32) {
+      __syncwarp();
+      if (i0 + lane < nn) {
+          const int i = i0 + lane;
+          DqK k;
+          k.ndx = ndx[i]; k.sv = sv[i]; k.cls = cls[i];
+          k.leave = i > 2 * kMaxNodeDist ? cls_kind(cls[i - 2 * kMaxNodeDist - 1]) : -1;
+          const int kind = cls_kind(k.cls);
+          const int4 dx = dqx[i];
+          k.x = dx.x; k.y = dx.y; k.z = dx.z; k.w = dx.w;
+          k.cs = (kind == K_FS || kind == K_RS) ? cscore[i] + sscore[i] : 0.0;
+          k.sp0 = k.sp1 = k.sp2 = -1;
+          k.n3n0 = k.n3n1 = k.n3n2 = k.n3s0 = k.n3s1 = k.n3s2 = 0;
+          k.op0 = k.op1 = k.op2 = 0.0;
+          k.pad = kind == K_RS ? B.win_min[C.node_off + i] : 0;  // node index of the window start
+          if (kind == K_RE) {
+              k.sp0 = star_ptr[3 * (int64_t)i]; k.sp1 = star_ptr[3 * (int64_t)i + 1]; k.sp2 = star_ptr[3 * (int64_t)i + 2];
+              if (k.sp0 != -1) { k.n3n0 = ndx[k.sp0]; k.n3s0 = sv[k.sp0]; k.op0 = opv[3 * (int64_t)i]; }
+              if (k.sp1 != -1) { k.n3n1 = ndx[k.sp1]; k.n3s1 = sv[k.sp1]; k.op1 = opv[3 * (int64_t)i + 1]; }
+              if (k.sp2 != -1) { k.n3n2 = ndx[k.sp2]; k.n3s2 = sv[k.sp2]; k.op2 = opv[3 * (int64_t)i + 2]; }
+          }
+          sk[lane] = k;
+      }
+      __syncwarp();
+      const int iend = min(i0 + 32, nn);
+      for (int i = i0; i < iend; i++) {
+        const DqK &K = sk[i - i0];
+        const int ci = K.cls, kind = cls_kind(ci), f2 = cls_frame(ci), ndx_i = K.ndx, sv_i = K.sv;
+        lo += (K.leave == K_FE) | (K.leave == K_RS);
+        double wv = kNeg;
+        int wj = -1, wfr = -1;
+        auto cand = [&](double v, int j, int fr) { if (v > wv || (v == wv && j > wj)) { wv = v; wj = j; wfr = fr; } };
+        const double cs_i = K.cs;
+
+        if (kind == K_FS || kind == K_RE) {
+            // ---- entries that fall more than 180 bp behind move into the deque ----
+            const int thr = ndx_i - 3 * kOperDist;
+            for (;;) {
+                const int q = far + lane;
+                const bool in = q < cur;
+                const int nq = in ? ig_ndx[q] : 0x7fffffff;
+                const double sq = in ? svig[q] : kNeg;
+                const int jq = in ? (ig_node[q] & 0x7fffffff) : 0;
+                const int c = __popc(__ballot_sync(0xffffffffu, nq < thr));  // ndx sorted: a prefix of the lanes
+                for (int t = 0; t < c; t++) {
+                    const double s = __shfl_sync(0xffffffffu, sq, t);
+                    const int j = __shfl_sync(0xffffffffu, jq, t);
+                    if (s == kNeg || !dq_ok) continue;
+                    const double x = s + ig_neg;
+                    while (dq_cnt > 0 && dqv[(dq_head + dq_cnt - 1) & (kDqCap - 1)] <= x) dq_cnt--;
+                    if (dq_cnt == kDqCap) { dq_ok = false; continue; }
+                    if (lane == 0) { dqv[(dq_head + dq_cnt) & (kDqCap - 1)] = x; dqj[(dq_head + dq_cnt) & (kDqCap - 1)] = j; }
+                    dq_cnt++;
+                    __syncwarp();
+                }
+                far += c;
+                if (c < 32) break;
+            }
+            const int flo = max(far, lo);
+            if (dq_ok) {
+                while (dq_cnt > 0 && dqj[dq_head] < i - 2 * kMaxNodeDist) { dq_head = (dq_head + 1) & (kDqCap - 1); dq_cnt--; }
+                if (dq_cnt > 0 && lane == 0) cand(dqv[dq_head], dqj[dq_head], -1);
+            } else {
+                // deque overflowed once (scores fell monotonically over > 64 entries): scan the far range
+                for (int q = lo + lane; q < flo; q += 32) {
+                    const double s = svig[q];
+                    if (s != kNeg) cand(s + ig_neg, ig_node[q] & 0x7fffffff, -1);
+                }
+            }
+            if (kind == K_FS) {
+                // near sources (_connection.h:116-129): +STOP distance-dependent term, -start strand switch
+                for (int q = flo + lane; q < cur; q += 32) {
+                    const double s = svig[q];
+                    if (s == kNeg) continue;
+                    const int nd = ig_node[q], nj = ig_ndx[q];
+                    if (nd < 0) {
+                        if (nj + 2 >= ndx_i) continue;
+                        const int dist = ndx_i - nj;
+                        cand(s + (dist > 3 * kOperDist ? ig_neg : (dist <= kOperDist ? M.igt[dist] : 0.0)), nd & 0x7fffffff, -1);
+                    } else {
+                        if (nj >= ndx_i) continue;
+                        cand(s + ig_neg, nd, -1);
+                    }
+                }
+            } else {
+                // +STOP with the triple-overlap search (_connection.h:297-334), for one merged-stream position
+                auto eval_fe = [&](int q, double s, int nj, int nd) {
+                    const int left = nj + 2, right = ndx_i - 2;
+                    if (left >= right) return;
+                    int maxfr = -1, tj = kTbNone;
+                    double maxval = 0.0;
+                    auto probe = [&](int k, int spk, int n3n, int n3s, double op) {
+                        if (spk == -1) return;
+                        const int ovlp = left - n3s + 3;
+                        if (ovlp <= 0 || ovlp >= kMaxOppOvlp) return;
+                        if (ovlp >= n3n - left) return;
+                        if (tj == kTbNone) tj = ndx[tbig[q]];
+                        if (ovlp >= n3s - tj - 2) return;
+                        if (op > maxval) { maxfr = k; maxval = op; }
+                    };
+                    probe(0, K.sp0, K.n3n0, K.n3s0, K.op0);
+                    probe(1, K.sp1, K.n3n1, K.n3s1, K.op1);
+                    probe(2, K.sp2, K.n3n2, K.n3s2, K.op2);
+                    cand(s + (maxfr != -1 ? maxval : ig_neg), nd & 0x7fffffff, maxfr);
+                };
+                for (int q = flo + lane; q < cur; q += 32) {
+                    const double s = svig[q];
+                    if (s == kNeg) continue;
+                    const int nd = ig_node[q], nj = ig_ndx[q];
+                    if (nd < 0) {
+                        eval_fe(q, s, nj, nd);
+                    } else {  // -start (_connection.h:335-341)
+                        if (nj >= ndx_i - 2) continue;
+                        const int dist = ndx_i - nj;
+                        cand(s + (dist > 3 * kOperDist ? ig_neg : (dist <= kOperDist ? M.igt[dist] : 0.0)), nd, -1);
+                    }
+                }
+                // far +STOPs whose position can trigger the triple overlap (200 bp after the stop of a recorded
+                // start): their plain value is covered by the far maximum, the overlap value can only be larger
+                auto special = [&](int spk, int n3s) {
+                    if (spk == -1) return;
+                    int a_ = lo, b_ = flo;  // ndx in [n3s-4, n3s+194]
+                    while (a_ < b_) { const int mid = (a_ + b_) >> 1; if (ig_ndx[mid] < n3s - 4) a_ = mid + 1; else b_ = mid; }
+                    const int a = a_;
+                    b_ = flo;
+                    while (a_ < b_) { const int mid = (a_ + b_) >> 1; if (ig_ndx[mid] < n3s + 195) a_ = mid + 1; else b_ = mid; }
+                    for (int q = a + lane; q < a_; q += 32) {
+                        const int nd = ig_node[q];
+                        const double s = svig[q];
+                        if (nd < 0 && s != kNeg) eval_fe(q, s, ig_ndx[q], nd);
+                    }
+                };
+                special(K.sp0, K.n3s0);
+                special(K.sp1, K.n3s1);
+                special(K.sp2, K.n3s2);
+                // -STOPs whose ORF spans this stop: operon (_connection.h:343-356); at most one per frame
+                if (lane < 3) {
+                    const int j = lane == 0 ? K.x : (lane == 1 ? K.y : K.z);
+                    const int spl = lane == 0 ? K.sp0 : (lane == 1 ? K.sp1 : K.sp2);
+                    const double opl = lane == 0 ? K.op0 : (lane == 1 ? K.op1 : K.op2);
+                    if (j >= 0 && j >= i - 2 * kMaxNodeDist && spl != -1) cand(score[j] + opl, j, -1);
+                }
+            }
+        } else if (kind == K_FE) {
+            {   // best +start of this ORF (gene): running maximum of fl(score + cscore + sscore)
+                const double rv = f2 == 0 ? rc_v0 : (f2 == 1 ? rc_v1 : rc_v2);
+                const int rj = f2 == 0 ? rc_j0 : (f2 == 1 ? rc_j1 : rc_j2);
+                if (lane == 0 && rj >= 0) cand(rv, rj, -1);
+            }
+            // +STOPs inside the ORF (operon, _connection.h:178-191)
+            for (int q = max(K.x, K.w) + lane; q < cur; q += 32) {
+                const int nd = ig_node[q];
+                if (nd >= 0) continue;
+                const double s = svig[q];
+                if (s == kNeg) continue;
+                const int j = nd & 0x7fffffff;
+                if (star_ptr[3 * (int64_t)j + f2] == -1) continue;
+                cand(s + opv[3 * (int64_t)j + f2], j, -1);
+            }
+        } else {  // K_RS
+            // own -STOP (gene, _connection.h:228-237); K.w = merged-stream rank of the window start
+            if (lane == 0 && K.x >= K.pad && K.x >= 0 && K.x < i) cand(score[K.x] + cs_i, K.x, -1);
+            // +STOPs overlapping the 3' end (_connection.h:239-256)
+            const double cs_diff = cs_i + ig_neg;
+            for (int q = max(K.y, K.w) + lane; q < min(K.z, cur); q += 32) {
+                const int nd = ig_node[q];
+                if (nd >= 0) continue;
+                const double s = svig[q];
+                if (s == kNeg) continue;
+                const int nj = ig_ndx[q];
+                if (sv_i - 2 >= nj + 2) continue;
+                const int ovlp = (nj + 2) - (sv_i - 2) + 1;
+                if (ovlp >= kMaxOppOvlp) continue;
+                if ((nj - sv_i) >= (ndx_i - nj + 3)) continue;
+                if ((nj - sv_i) >= (sv_i - 3 - ndx[tbig[q]])) continue;
+                cand(s + cs_diff, nd & 0x7fffffff, -1);
+            }
+        }
+
+        warp_argmax(wv, wj, wfr);
+        double sc_i = 0.0;
+        int tb_i = -1, fr_i = -1;
+        if (wj >= 0 && wv >= 0.0) { sc_i = wv; tb_i = wj; fr_i = wfr; }
+        if (lane == 0) {
+            score[i] = sc_i; traceb[i] = tb_i; ov_mark[i] = (int8_t)fr_i;
+            if (kind == K_FE || kind == K_RS) {
+                svig[cur] = tb_i == -1 ? kNeg : sc_i;  // edge-artifact rule: nothing leads into it
+                if (kind == K_FE) tbig[cur] = tb_i;
+            }
+        }
+        if (kind == K_FE) {
+            cur++;
+            if (f2 == 0) { rc_v0 = kNeg; rc_j0 = -1; } else if (f2 == 1) { rc_v1 = kNeg; rc_j1 = -1; } else { rc_v2 = kNeg; rc_j2 = -1; }
+        } else if (kind == K_RS) {
+            cur++;
+        } else if (kind == K_FS) {
+            const double g = sc_i + cs_i;
+            if (f2 == 0) { if (g >= rc_v0) { rc_v0 = g; rc_j0 = i; } }
+            else if (f2 == 1) { if (g >= rc_v1) { rc_v1 = g; rc_j1 = i; } }
+            else { if (g >= rc_v2) { rc_v2 = g; rc_j2 = i; } }
+        }
+        if ((kind == K_FE || kind == K_RS) && sc_i >= best_sc) { best_sc = sc_i; best_i = i; best_tb = tb_i; }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) {
+        const bool ok = best_i >= 0 && best_tb != -1;
+        B.chain_ipath[chain] = ok ? best_i : -1;
+        B.chain_score[chain] = ok ? best_sc : 0.0;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
 // winner selection + traceback + gene extraction: one thread per contig
 // --------------------------------------------------------------------------------------------------
 struct NodeRef {
@@ -965,7 +1267,11 @@ void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, 
                cudaStream_t st) {
     if (n_chains == 0) return;
     // algo 1 (default): k_dp_fast, final scoring only; algo 0: the all-pairs kernel (also the training DP)
-    if (final && algo >= 1 && B.dp_sv) {
+    if (final && algo >= 3 && B.dp_svig) {
+        const int nb = (n_chains + kFastWarps - 1) / kFastWarps;
+        if (algo == 4) k_dp_dq<4><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);
+        else k_dp_dq<8><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);
+    } else if (final && algo >= 1 && B.dp_sv) {
         const int nb = (n_chains + kFastWarps - 1) / kFastWarps;
         if (algo == 2) k_dp_fast<4><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);   // up to 128 regs
         else k_dp_fast<8><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);             // 64 regs, 32 warps/SM

@@ -791,6 +791,37 @@ __global__ void __launch_bounds__(128) k_dp_index(DevBatch B, int n_ext, int tot
         r.x = cand[0]; r.y = cand[1]; r.z = cand[2];
     }
     B.dpx[X.node_off + i] = r;
+
+    // ---- merged stream of +STOP / -start nodes (k_dp_dq): rank = (#FE + #RS nodes before the node) ----
+    const int32_t *__restrict__ crank = B.crank + 4 * (int64_t)X.node_off;
+    auto igrank = [&](int node) { return crank[4 * (int64_t)node + 1] + crank[4 * (int64_t)node + 2]; };
+    if (kind == K_FE || kind == K_RS) {
+        const int q = igrank(i);
+        B.ig_node[X.node_off + q] = i | (kind == K_FE ? (int)0x80000000 : 0);
+        B.ig_ndx[X.node_off + q] = my;
+    }
+    // first merged-stream position whose ndx >= key: binary search over node indices (ndx sorted), then rank
+    auto ig_lb = [&](int key) {
+        int lo = 0, hi = nn;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (ndx[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        return lo < nn ? igrank(lo) : igrank(nn - 1) + ((cls_kind(cls[nn - 1]) == K_FE || cls_kind(cls[nn - 1]) == K_RS) ? 1 : 0);
+    };
+    int4 q4 = make_int4(-1, -1, -1, -1);
+    if (kind == K_FE) {
+        q4.x = ig_lb(msv + 1);               // operon range: +STOPs with ndx > stop_val
+        q4.w = igrank(B.win_min[X.node_off + i]);
+    } else if (kind == K_RS) {
+        q4.x = r.x;                          // own -STOP (node index)
+        q4.y = ig_lb(msv - 3);               // 3' overlap range: +STOPs with ndx in [stop_val-3, stop_val+195)
+        q4.z = ig_lb(msv + 195);
+        q4.w = igrank(B.win_min[X.node_off + i]);
+    } else if (kind == K_RE) {
+        q4.x = r.x; q4.y = r.y; q4.z = r.z;
+    }
+    B.dqx[X.node_off + i] = q4;
 }
 
 void launch_dp_index(const DevBatch &B, int n_ext, int total_nodes, cudaStream_t st) {
