@@ -543,6 +543,8 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     B.cls = pool.alloc<uint8_t>(total_nodes + 16);
     B.gc_cont = pool.alloc<float>(total_nodes, true);
     B.sdbits = pool.alloc<uint32_t>(total_nodes);
+    B.upc = pool.alloc<uint64_t>(total_nodes);
+    B.umot = pool.alloc<uint64_t>(total_nodes);
     B.win_min = pool.alloc<int32_t>(total_nodes);
     B.crank = pool.alloc<int32_t>(4 * (size_t)total_nodes + 4);
     B.clist = pool.alloc<int32_t>(total_nodes);

@@ -116,6 +116,8 @@ struct DevBatch {
     uint8_t *cls;
     float *gc_cont;
     uint32_t *sdbits;     // upstream A/G pattern for the SD motif search
+    uint64_t *upc;        // 2-bit strand-oriented bases at start-1, start-2, start-15 .. start-44 (composition)
+    uint64_t *umot;       // 2-bit strand-oriented bases at start-21 .. start-4 (upstream motif search)
     int32_t *win_min;     // DP window start (lib.pyx:1224-1233)
     int32_t *crank;       // [4 * node]: number of class-c nodes before node
     int32_t *clist;       // class-sorted node indices (local), segments per class

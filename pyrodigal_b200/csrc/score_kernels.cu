@@ -115,6 +115,19 @@ __global__ void __launch_bounds__(128) k_node_prep(DevBatch B, int n_ext, int to
             if (b == (rev ? 2 : 1)) bits |= 1u << (16 + k);
         }
         B.sdbits[X.node_off + z] = bits;
+        // packed upstream bases (model independent): composition positions in the reference's loop order
+        // (lib.pyx:1638-1649: q = 1, 2 then 15..44, stopping at the first q > start), and the motif window
+        uint64_t pc = 0;
+        int cnt = 0;
+        for (int q = 1; q < 3 && q <= start; q++, cnt++) pc |= (uint64_t)mer_base(d, slen, start - q, rev) << (2 * cnt);
+        for (int q = 15; q < 45 && q <= start; q++, cnt++) pc |= (uint64_t)mer_base(d, slen, start - q, rev) << (2 * cnt);
+        B.upc[X.node_off + z] = pc;
+        uint64_t U = 0;
+        for (int q = 0; q < 18; q++) {
+            const int x = start - 21 + q;
+            if (x >= 0 && x < slen) U |= (uint64_t)mer_base(d, slen, x, rev) << (2 * q);
+        }
+        B.umot[X.node_off + z] = U;
         return;
     }
 
@@ -428,24 +441,22 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
                 rbs1 = max(rbs1, m);
             }
         } else {
-            // best upstream motif, stage 2 (lib.pyx:1557-1616)
-            uint64_t U = 0;
-            for (int q = 0; q < 18; q++) {
-                int x = start - 21 + q;
-                if (x >= 0 && x < slen) U |= (uint64_t)mer_base(d, slen, x, rev) << (2 * q);
-            }
+            // best upstream motif, stage 2 (lib.pyx:1557-1616); spacer class of the p-th window of a length is
+            // fixed: j <= start-16-l (p <= 2) -> 3, p <= 4 -> 2, j >= start-7-l (p >= 11) -> 1, else 0
+            const uint64_t U = B.umot[C.node_off + i];
             int max_spacer = 0, max_spacendx = 0, max_len = 0, max_ndx = 0;
             double max_sc = -100.0;
+            const double *__restrict__ mw = M.mot_wt;
+#pragma unroll
             for (int l = 3; l >= 0; l--) {
-                for (int j = start - 18 - l; j <= start - 6 - l; j++) {
+                const uint32_t lmask = (1u << (2 * (l + 3))) - 1u;
+#pragma unroll
+                for (int p = 0; p < 13; p++) {
+                    const int j = start - 18 - l + p;
                     if (j < 0) continue;
-                    int spacendx;
-                    if (j <= start - 16 - l) spacendx = 3;
-                    else if (j <= start - 14 - l) spacendx = 2;
-                    else if (j >= start - 7 - l) spacendx = 1;
-                    else spacendx = 0;
-                    const int index = (int)((U >> (2 * (j - (start - 21)))) & ((1u << (2 * (l + 3))) - 1u));
-                    const double sc = __ldg(&M.mot_wt[(l * 4 + spacendx) * 4096 + index]);
+                    const int spacendx = p <= 2 ? 3 : (p <= 4 ? 2 : (p >= 11 ? 1 : 0));
+                    const int index = (int)((U >> (2 * (3 - l + p))) & lmask);
+                    const double sc = __ldg(&mw[(l * 4 + spacendx) * 4096 + index]);
                     if (sc > max_sc) {
                         max_sc = sc; max_spacendx = spacendx; max_spacer = start - j - l - 3;
                         max_ndx = index; max_len = l + 3;
@@ -488,9 +499,11 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
         }
         // upstream composition (lib.pyx:1619-1650)
         uscore = 0.0;
-        int count = 0;
-        for (int q = 1; q < 3 && q <= start; q++, count++) uscore += M.uc[count][mer_base(d, slen, start - q, rev)];
-        for (int q = 15; q < 45 && q <= start; q++, count++) uscore += M.uc[count][mer_base(d, slen, start - q, rev)];
+        {
+            const int ncomp = min(2, start) + max(0, min(30, start - 14));
+            uint64_t pc = B.upc[C.node_off + i];
+            for (int k = 0; k < ncomp; k++, pc >>= 2) uscore += M.uc[k][pc & 3];
+        }
         // starts that would stop the gene from running off the edge (lib.pyx:2407-2422)
         if (!o.closed && ndx <= 2 && !rev) {
             uscore += PGPU_EDGE_UPS * st_wt;
@@ -593,8 +606,13 @@ __global__ void __launch_bounds__(128) k_overlap(DevBatch B, const DevModel *__r
     int k = s_first;
     while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
     const ChainInfo C = B.chains[k];
-    const int i = (int)(g - C.coff), nn = C.nn;
-    if (i >= nn) return;
+    const int t = (int)(g - C.coff), nn = C.nn;
+    if (t >= nn) return;
+    // star_ptr was preset to -1 for every node; only STOP nodes (first #STOP threads of the chain) have work
+    const int32_t *__restrict__ cbase = B.cbase + 4 * C.ext;
+    const int n_fe = cbase[2] - cbase[1], n_re = nn - cbase[3];
+    if (t >= n_fe + n_re) return;
+    const int i = (B.clist + C.node_off)[t < n_fe ? cbase[1] + t : cbase[3] + (t - n_fe)];
     const uint8_t *__restrict__ cls = B.cls + C.node_off;
     const int32_t *__restrict__ ndx = B.ndx + C.node_off;
     const int32_t *__restrict__ sv = B.stop_val + C.node_off;
@@ -644,10 +662,11 @@ __global__ void __launch_bounds__(128) k_overlap(DevBatch B, const DevModel *__r
             }
         }
     }
+    const int64_t gi = C.coff + i;
 #pragma unroll
     for (int f = 0; f < 3; f++) {
-        B.star_ptr[3 * g + f] = sp[f];
-        B.opv[3 * g + f] = sp[f] == -1 ? 0.0 : operon_value(c, i, sp[f], cls, ndx, cscore, sscore, rscore, uscore, M);
+        B.star_ptr[3 * gi + f] = sp[f];
+        B.opv[3 * gi + f] = sp[f] == -1 ? 0.0 : operon_value(c, i, sp[f], cls, ndx, cscore, sscore, rscore, uscore, M);
     }
 }
 
@@ -712,6 +731,7 @@ void launch_pairs(const DevBatch &B, int n_ext, int total_nodes, unsigned long l
 void launch_overlap(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o, int flag,
                     cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
+    cudaMemsetAsync(B.star_ptr, 0xff, 3 * (size_t)total * sizeof(int32_t), st);  // -1 everywhere
     k_overlap<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total, o, flag);
 }
 

@@ -273,3 +273,27 @@ def test_python_api_drop_in():
         pyrodigal_b200.GeneFinder().find_genes(b"ACGT")
     with pytest.raises(ValueError):
         pyrodigal_b200.GeneFinder(ti, meta=True)
+
+
+def test_long_contig_meta_and_single_vs_oracle(ctx, capi):
+    """one long chain (1.2 Mbp): windows slide over > 1000 nodes, many ORFs, both modes; plus a tt=4 model on a
+    GC-rich contig, which produces the giant-ORF windows of SURVEY T2"""
+    seq = R.synth(1_200_000, 0.5, 4242)
+    d, gc, unk = orc.encode(seq)
+    res = run_meta(ctx, capi, [seq])
+    genes, nodes, winner, pairs = orc.find_genes_meta(d, gc / len(d), R.bins_blob())
+    assert int(res.summary["winner"][0]) == winner
+    cmp_int(res.genes, genes, "long.genes")
+    cmp_nodes(res.nodes(0), nodes, "long")
+    assert res.stats["pairs"] == pairs
+    for b in (0, 30):  # bin 0: translation table 4 (no TGA stop) -> ORFs of 10^4..10^5 nodes at GC 0.5
+        c = capi.Context(0)
+        c.set_models(R.bin_blob(b), 1)
+        sub = np.frombuffer(seq, np.uint8)[:600_000]
+        r = c.find_genes_batch(np.ascontiguousarray(sub), np.array([0, len(sub)], np.int64),
+                               capi.make_opts(meta=False, single_model=0, want_nodes=True))
+        g2, n2, ipath = orc.find_genes_single(d[:600_000], R.bin_blob(b))
+        cmp_int(r.genes, g2, f"single{b}.genes")
+        cmp_nodes(r.nodes(0), n2, f"single{b}", dp=True)
+        assert int(r.summary["ipath"][0]) == ipath
+        c.close()
