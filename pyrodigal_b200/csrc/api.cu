@@ -11,6 +11,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -37,6 +39,46 @@ struct RawTraining {
 };
 static_assert(sizeof(RawTraining) == PGPU_TRAINING_SIZE, "training struct layout");
 
+// pinned host buffers for results: recycled through a small free list so that steady-state calls neither
+// allocate pinned memory nor zero-fill / re-copy result arrays.  Reference counted: results keep the pool alive
+// even when their context is destroyed first.
+struct PinnedBuf { void *p = nullptr; size_t cap = 0; };
+struct PinnedPool {
+    std::mutex mu;
+    std::vector<PinnedBuf> free_list;
+    PinnedBuf acquire(size_t bytes) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            int best = -1;
+            for (int i = 0; i < (int)free_list.size(); i++)
+                if (free_list[i].cap >= bytes && (best < 0 || free_list[i].cap < free_list[best].cap)) best = i;
+            if (best >= 0) {
+                PinnedBuf b = free_list[best];
+                free_list.erase(free_list.begin() + best);
+                return b;
+            }
+        }
+        PinnedBuf b;
+        const size_t want = bytes + bytes / 4 + (1 << 16);
+        if (cudaHostAlloc(&b.p, want, cudaHostAllocDefault) != cudaSuccess) { b.p = nullptr; return b; }
+        b.cap = want;
+        return b;
+    }
+    void release(PinnedBuf b) {
+        if (!b.p) return;
+        std::lock_guard<std::mutex> g(mu);
+        if (free_list.size() >= 6) {  // bound the pinned footprint: keep the larger buffers
+            int s = 0;
+            for (int i = 1; i < (int)free_list.size(); i++) if (free_list[i].cap < free_list[s].cap) s = i;
+            if (free_list[s].cap < b.cap) { cudaFreeHost(free_list[s].p); free_list[s] = b; }
+            else cudaFreeHost(b.p);
+            return;
+        }
+        free_list.push_back(b);
+    }
+    ~PinnedPool() { for (auto &b : free_list) cudaFreeHost(b.p); }
+};
+
 struct pgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -51,36 +93,7 @@ struct pgpu_ctx {
     cudaEvent_t ev[16];
     int64_t launches = 0;
     int dp_algo = 3;           // 3: k_dp_dq (default), 1/2: k_dp_fast, 0: all-pairs k_dp (PGPU_DP_ALGO=n)
-    // pinned host buffers for results: recycled through a small free list so that steady-state calls neither
-    // allocate pinned memory nor zero-fill / re-copy result arrays
-    struct PinnedBuf { void *p = nullptr; size_t cap = 0; };
-    std::vector<PinnedBuf> pinned_free;
-    PinnedBuf acquire_pinned(size_t bytes) {
-        int best = -1;
-        for (int i = 0; i < (int)pinned_free.size(); i++)
-            if (pinned_free[i].cap >= bytes && (best < 0 || pinned_free[i].cap < pinned_free[best].cap)) best = i;
-        if (best >= 0) {
-            PinnedBuf b = pinned_free[best];
-            pinned_free.erase(pinned_free.begin() + best);
-            return b;
-        }
-        PinnedBuf b;
-        const size_t want = bytes + bytes / 4 + (1 << 16);
-        if (cudaHostAlloc(&b.p, want, cudaHostAllocDefault) != cudaSuccess) { b.p = nullptr; return b; }
-        b.cap = want;
-        return b;
-    }
-    void release_pinned(PinnedBuf b) {
-        if (!b.p) return;
-        if (pinned_free.size() >= 6) {  // bound the pinned footprint: drop the smallest
-            int s = 0;
-            for (int i = 1; i < (int)pinned_free.size(); i++) if (pinned_free[i].cap < pinned_free[s].cap) s = i;
-            if (pinned_free[s].cap < b.cap) { cudaFreeHost(pinned_free[s].p); pinned_free[s] = b; }
-            else cudaFreeHost(b.p);
-            return;
-        }
-        pinned_free.push_back(b);
-    }
+    std::shared_ptr<struct PinnedPool> pinned;  // shared with the results it backs (they may outlive the context)
 };
 
 static thread_local std::string g_create_err;
@@ -290,13 +303,13 @@ static void prepare_model(const RawTraining &r, DevModel &m, const RawTraining *
 struct ResSeg {  // genes of one sub-batch, in a pinned buffer filled directly by the D2H copy
     int lo = 0, hi = 0;
     int64_t g0 = 0, ng = 0;
-    pgpu_ctx::PinnedBuf buf;
+    PinnedBuf buf;
     pgpu_gene *genes = nullptr;
     pgpu_node *gnodes = nullptr;
 };
 
 struct pgpu_result {
-    pgpu_ctx *ctx = nullptr;
+    std::shared_ptr<PinnedPool> pinned;
     int n_contigs = 0;
     std::vector<pgpu_contig_summary> summary;
     std::vector<int64_t> gene_off;   // [n+1]
@@ -307,7 +320,7 @@ struct pgpu_result {
     std::vector<pgpu_node> nodes;
     pgpu_stats stats;
     ~pgpu_result() {
-        if (ctx) for (auto &s : segs) ctx->release_pinned(s.buf);
+        if (pinned) for (auto &s : segs) pinned->release(s.buf);
     }
 };
 
@@ -730,7 +743,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     seg.lo = lo; seg.hi = hi; seg.g0 = res->total_genes; seg.ng = ng;
     const size_t gbytes = ng * sizeof(pgpu_gene), nbytes = 2 * ng * sizeof(pgpu_node);
     if (ng) {
-        seg.buf = ctx->acquire_pinned(gbytes + nbytes);
+        seg.buf = res->pinned->acquire(gbytes + nbytes);
         if (!seg.buf.p) return fail(ctx, PGPU_ENOMEM, "pinned result allocation failed");
         seg.genes = (pgpu_gene *)seg.buf.p;
         seg.gnodes = (pgpu_node *)((char *)seg.buf.p + gbytes);
@@ -816,7 +829,7 @@ static int run_all(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, co
     if (ctx->n_models == 0) return fail(ctx, PGPU_ESTATE, "no models loaded");
     cudaSetDevice(ctx->device);
     pgpu_result *res = new pgpu_result();
-    res->ctx = ctx;
+    res->pinned = ctx->pinned;
     res->n_contigs = n;
     res->summary.resize(n);
     res->gene_off.assign(n + 1, 0);
@@ -872,6 +885,7 @@ int pgpu_create(int device, pgpu_ctx **out) {
     if (cudaSetDevice(device) != cudaSuccess) { g_create_err = "cudaSetDevice failed"; return PGPU_ENODEV; }
     pgpu_ctx *ctx = new pgpu_ctx();
     ctx->device = device;
+    ctx->pinned = std::make_shared<PinnedPool>();
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         g_create_err = "cudaStreamCreate failed";
         delete ctx;
@@ -897,7 +911,6 @@ void pgpu_destroy(pgpu_ctx *ctx) {
     if (ctx->d_models) cudaFree(ctx->d_models);
     if (ctx->d_dcT) cudaFree(ctx->d_dcT);
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
-    for (auto &b : ctx->pinned_free) cudaFreeHost(b.p);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1065,6 +1078,7 @@ int pgpu_extract_nodes(pgpu_ctx *ctx, const uint8_t *seq, int slen, int translat
         return fail(ctx, PGPU_EINVAL, "bad arguments");
     cudaSetDevice(ctx->device);
     pgpu_result tmp;
+    tmp.pinned = ctx->pinned;
     memset(&tmp.stats, 0, sizeof(tmp.stats));
     tmp.summary.resize(1); tmp.gene_off.assign(2, 0); tmp.node_off.assign(2, 0);
     OperatorOut op;
@@ -1095,6 +1109,7 @@ int pgpu_score_nodes(pgpu_ctx *ctx, const uint8_t *seq, int slen, int model, con
     if (model < 0 || model >= ctx->n_models) return fail(ctx, PGPU_ESTATE, "model index out of range");
     cudaSetDevice(ctx->device);
     pgpu_result tmp;
+    tmp.pinned = ctx->pinned;
     memset(&tmp.stats, 0, sizeof(tmp.stats));
     tmp.summary.resize(1); tmp.gene_off.assign(2, 0); tmp.node_off.assign(2, 0);
     OperatorOut op;

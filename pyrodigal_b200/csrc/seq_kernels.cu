@@ -170,6 +170,106 @@ __global__ void __launch_bounds__(128) k_extract(DevBatch B, int n_ext, RunOpts 
     if (saw) emit(last, 3, f - 6, !last_real);
 }
 
+// Warp-cooperative version of the same scan: one warp per (extraction, strand, frame) looks at 32 codons of
+// its frame per iteration.  The sequential state of the reference's loop (lib.pyx:1940-2010) depends only on
+// the nearest stop codon seen earlier in scan order and on "has a start been emitted since that stop", both
+// of which are bit operations on the ballot masks of the block (stops S, qualifying starts Q):
+//   lane k: earlier stops Sb = S & lt(k);  nearest = highest bit of Sb  -> last / min_dist / last_real
+//   stop lane k: saw = any Q bit strictly between the nearest earlier stop and k (or carried in)
+// so 32 codons cost a few dozen instructions instead of 32 dependent iterations.
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_extract_w(DevBatch B, int n_ext, RunOpts o) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_ext * 6) return;
+    const int e = w / 6, sf = w % 6, rev = sf / 3, f = sf % 3;
+    const ExtractInfo X = B.exts[e];
+    const int slen = X.slen;
+    if (slen < 3) return;
+    const uint8_t *__restrict__ cod = B.cod + X.doff;
+    uint32_t *bits = (rev ? B.bits_rev : B.bits_fwd) + X.woff;
+    const uint32_t *__restrict__ bf = B.bits_fwd + X.woff;
+    const uint32_t *__restrict__ br = B.bits_rev + X.woff;
+    const int32_t *__restrict__ wb = B.wordbase + X.woff;
+    const int32_t *__restrict__ masks = B.masks + 2 * (int64_t)X.mask_off;
+
+    auto emit = [&](int pos, int type, int sv, int edge) {
+        const int p = rev ? slen - 1 - pos : pos;
+        if (!FILL) {
+            atomicOr(&bits[p >> 5], 1u << (p & 31));
+        } else {
+            const int ww = p >> 5, b = p & 31;
+            const uint32_t lt = (1u << b) - 1u;
+            int slot = wb[ww] + __popc(bf[ww] & lt) + __popc(br[ww] & lt) + (rev ? (int)((bf[ww] >> b) & 1u) : 0);
+            int conv = (!o.closed && type != 3 && !edge && (rev ? p >= slen - 3 : p <= 2)) ? CLS_CONV : 0;
+            B.ndx[slot] = p;
+            B.stop_val[slot] = rev ? slen - 1 - sv : sv;
+            B.cls[slot] = (uint8_t)(type | (rev ? CLS_REV : 0) | (edge ? CLS_EDGE : 0) | conv | ((p % 3) << CLS_FRAME_SHIFT));
+        }
+    };
+
+    // incoming state (warp uniform)
+    int last = slen + ((f - slen % 3 + 3) % 3);
+    if (!o.closed)
+        while (last + 3 > slen) last -= 3;
+    bool last_real = false, saw = false;
+    int min_dist = o.min_edge_gene;
+    int i_top = slen - 3;
+    i_top -= ((i_top % 3) - f + 3) % 3;
+    const uint32_t lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
+
+    for (; i_top >= 0; i_top -= 96) {
+        const int i = i_top - 3 * lane;
+        const bool valid = i >= 0;
+        int c = 0;
+        bool has_n = true;
+        if (valid) {
+            c = rev ? cod[slen - 3 - i] : cod[i];
+            has_n = c & 64;
+            c &= 63;
+            if (rev) c = rev_code(c);
+        }
+        const bool is_stop = valid && !has_n && ((X.stopmask >> c) & 1);
+        const bool is_startc = valid && !has_n && ((X.startmask >> c) & 1);
+        const uint32_t S = __ballot_sync(0xffffffffu, is_stop);
+        const uint32_t Sb = S & lt_mask;
+        int my_last = last, my_min = min_dist;
+        bool my_real = last_real;
+        int h = -1;
+        if (Sb) { h = 31 - __clz(Sb); my_last = i_top - 3 * h; my_min = o.min_gene; my_real = true; }
+        bool qual = false, q_start = false;
+        if (valid && !is_stop && my_last < slen) {
+            bool hit = false;
+            if (X.n_masks)
+                hit = rev ? masked_any(masks, X.n_masks, slen - my_last - 1, slen - i - 1) : masked_any(masks, X.n_masks, i, my_last);
+            if (!hit) {
+                q_start = is_startc && (my_last - i + 3 >= my_min);
+                qual = q_start || (i <= 2 && !o.closed && my_last - i > o.min_edge_gene);
+            }
+        }
+        const uint32_t Q = __ballot_sync(0xffffffffu, qual);
+        if (is_stop) {
+            const uint32_t seg = lt_mask & ~(h >= 0 ? ((2u << h) - 1u) : 0u);
+            const bool saw_here = (Q & seg) != 0 || (h < 0 && saw);
+            if (saw_here) emit(my_last, 3, i, !my_real);
+        } else if (qual) {
+            if (q_start) { const int b0 = c & 3; emit(i, b0 == 0 ? 0 : (b0 == 1 ? 1 : 2), my_last, 0); }
+            else emit(i, 0, my_last, 1);
+        }
+        // carry the state out of the block
+        if (S) {
+            const int hl = 31 - __clz(S);
+            last = i_top - 3 * hl;
+            last_real = true;
+            min_dist = o.min_gene;
+            saw = (Q & ~((hl == 31) ? 0xffffffffu : ((2u << hl) - 1u))) != 0;
+        } else {
+            saw = saw || Q != 0;
+        }
+    }
+    if (saw && lane == 0) emit(last, 3, f - 6, !last_real);
+    (void)le_mask;
+}
+
 // --------------------------------------------------------------------------------------------------
 // exclusive prefix sum of per-word node counts (three-phase: block sums, top scan, apply)
 // --------------------------------------------------------------------------------------------------
@@ -264,10 +364,10 @@ void launch_find_masks(const DevBatch &B, const int2 *tiles, int n_tiles, int mi
     if (n_tiles > 0) k_find_masks<<<n_tiles, 256, 0, st>>>(B, tiles, min_mask, out, cap, count);
 }
 void launch_extract_mark(const DevBatch &B, int n_ext, RunOpts o, cudaStream_t st) {
-    if (n_ext > 0) k_extract<false><<<(n_ext * 6 + 127) / 128, 128, 0, st>>>(B, n_ext, o);
+    if (n_ext > 0) k_extract_w<false><<<(n_ext * 6 * 32 + 127) / 128, 128, 0, st>>>(B, n_ext, o);
 }
 void launch_extract_fill(const DevBatch &B, int n_ext, RunOpts o, cudaStream_t st) {
-    if (n_ext > 0) k_extract<true><<<(n_ext * 6 + 127) / 128, 128, 0, st>>>(B, n_ext, o);
+    if (n_ext > 0) k_extract_w<true><<<(n_ext * 6 * 32 + 127) / 128, 128, 0, st>>>(B, n_ext, o);
 }
 int scan_num_blocks(int64_t nwords) { return (int)((nwords + 1 + kScanBlock - 1) / kScanBlock); }
 void launch_word_scan(const DevBatch &B, int64_t nwords, int *block_sums, int *total_out, cudaStream_t st) {
