@@ -375,6 +375,15 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     const bool trace = getenv("PGPU_TRACE") != nullptr;
     const auto t_begin = now();
     auto tr = [&](const char *what) { if (trace) fprintf(stderr, "[pgpu %8.2f ms] %s\n", since(t_begin), what); };
+    std::vector<std::pair<const char *, cudaEvent_t>> tevs;
+    auto tev = [&](const char *name) {   // device-time trace point (PGPU_TRACE only)
+        if (!trace) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, st);
+        tevs.push_back({name, ev});
+    };
+    tev("begin");
 
     // ---- stage A: sequences ----------------------------------------------------------------------
     std::vector<ContigInfo> contigs(n);
@@ -404,14 +413,17 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         S.h2d_bytes += atot;
     }
     int e_h2d = mark();
-    B.digits = pool.alloc<uint8_t>(dtot + 256, true);
-    B.cod = pool.alloc<uint8_t>(dtot + 256, true);
+    // no memset: k_encode writes every byte that is ever read (whole 16-byte groups, zero padded past the end)
+    B.digits = pool.alloc<uint8_t>(dtot + 256);
+    B.cod = pool.alloc<uint8_t>(dtot + 256);
     B.contigs = pool.upload(contigs);
     B.gc_count = pool.alloc<int32_t>(n, true);
     B.unknown = pool.alloc<int32_t>(n, true);
     int2 *d_tiles = pool.upload(tiles);
     if (pool.failed) return PGPU_ENOMEM;
+    tev("setup/alloc/memset");
     launch_encode(B, d_tiles, (int)tiles.size(), st);
+    tev("k_encode");
     ctx->launches++;
     std::vector<int4> h_masks;
     if (opts.mask) {
@@ -516,8 +528,11 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     int *d_block_sums = pool.alloc<int>(scan_num_blocks(nwords) + 1);
     int *d_total = pool.alloc<int>(1, true);
     if (pool.failed) return PGPU_ENOMEM;
+    tev("plan+alloc");
     launch_extract_mark(B, n_ext, ro, st);
+    tev("k_extract mark");
     launch_word_scan(B, nwords, d_block_sums, d_total, st);
+    tev("word scan");
     ctx->launches += 4;
     // node offsets of every extraction = wordbase[woff]
     std::vector<int32_t> h_base(n_ext + 1, 0);
@@ -569,10 +584,15 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     B.dqx = pool.alloc<int4>(total_nodes);
     unsigned long long *d_ext_pairs = pool.alloc<unsigned long long>(n_ext, true);
     if (pool.failed) return PGPU_ENOMEM;
+    tev("sync2+alloc");
     launch_extract_fill(B, n_ext, ro, st);
+    tev("k_extract fill");
     launch_node_prep(B, n_ext, total_nodes, 1, st);
+    tev("k_node_prep+class_index");
     launch_dp_index(B, n_ext, total_nodes, st);
+    tev("k_dp_index");
     launch_pairs(B, n_ext, total_nodes, d_ext_pairs, st);
+    tev("k_pairs");
     ctx->launches += 5;
     int e_ext = mark();
 
@@ -631,10 +651,15 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     MotifOut *d_mot_main = (!meta) ? pool.alloc<MotifOut>(total_cn) : nullptr;
     if (pool.failed) return PGPU_ENOMEM;
     if (total_cn) CK(cudaMemsetAsync(d_tracef, 0xff, total_cn * sizeof(int32_t), st));
-    launch_score_chains(B, ctx->d_models, n_chains, total_cn, ro, d_mot_main, n_ext, total_nodes, st);
+    tev("chain alloc/upload");
+    launch_coding(B, ctx->d_models, n_chains, total_cn, n_ext, total_nodes, st);
+    tev("k_coding_orf");
+    launch_start_score(B, ctx->d_models, n_chains, total_cn, ro, d_mot_main, st);
+    tev("k_start_score");
     ctx->launches += 2;
     int e_score = mark();
     launch_overlap(B, ctx->d_models, n_chains, total_cn, ro, 1, st);
+    tev("k_overlap");
     ctx->launches++;
     int e_ovl = mark();
 
@@ -673,12 +698,15 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     int32_t *d_winner_chain = pool.alloc<int32_t>(n);
     if (pool.failed) return PGPU_ENOMEM;
     tr("uploaded dp tables");
+    tev("dp uploads");
     launch_dp(B, ctx->d_models, d_order, n_chains, 1, ctx->dp_algo, st);
+    tev("k_dp");
     ctx->launches++;
     int e_dp = mark();
     launch_trace(B, ctx->d_models, n, d_ccb, d_tracef, d_elim, d_genes, d_gene_off, d_summ, d_winner_chain, meta ? 1 : 0,
                  opts.max_overlap, st);
     ctx->launches++;
+    tev("k_trace");
     int e_trace = mark();
 
     tr("issued dp/trace");
@@ -718,6 +746,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         node_out_off[n] = total_cn;
         d_node_out_off = pool.upload(node_out_off);
     }
+    tev("final rescoring + pack");
     int e_final = mark();
     std::vector<unsigned long long> h_ext_pairs(n_ext);
     if (n_ext) CK(cudaMemcpyAsync(h_ext_pairs.data(), d_ext_pairs, n_ext * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -772,6 +801,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         res->have_nodes = true;
     }
     tr("issued pack + d2h");
+    tev("compaction + d2h issue");
     int e_d2h = mark();
     S.reserved[3] += since(t_host);  // host: result compaction issue
     CK(cudaStreamSynchronize(st));
@@ -780,6 +810,14 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         res->gene_off[lo + c + 1] = g0 + gene_out_off[c + 1];
     }
     tr("sync4 done");
+    if (trace) {
+        for (size_t k = 1; k < tevs.size(); k++) {
+            float t = 0;
+            cudaEventElapsedTime(&t, tevs[k - 1].second, tevs[k].second);
+            fprintf(stderr, "[pgpu dev] %-32s %8.3f ms\n", tevs[k].first, t);
+        }
+        for (auto &p : tevs) cudaEventDestroy(p.second);
+    }
     S.total_genes += ng;
     auto ms = [&](int a, int b) { float t = 0; cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]); return (double)t; };
     S.ms_h2d += ms(e_start, e_h2d);

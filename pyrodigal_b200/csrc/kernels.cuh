@@ -17,6 +17,10 @@ void launch_word_scan(const DevBatch &B, int64_t nwords, int *block_sums, int *t
 void launch_node_prep(const DevBatch &B, int n_ext, int total_nodes, int seq_parts, cudaStream_t st);
 void launch_score_chains(const DevBatch &B, const DevModel *models, int n_chains, int64_t total_chain_nodes,
                          RunOpts o, void *mot_out, int n_ext, int total_nodes, cudaStream_t st);
+void launch_coding(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, int n_ext, int total_nodes,
+                   cudaStream_t st);
+void launch_start_score(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o, void *mot_out,
+                        cudaStream_t st);
 void launch_overlap(const DevBatch &B, const DevModel *models, int n_chains, int64_t total_chain_nodes, RunOpts o,
                     int flag, cudaStream_t st);
 void launch_opv(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, cudaStream_t st);

@@ -340,10 +340,24 @@ __global__ void __launch_bounds__(32 * kOrfWarps) k_coding_orf(DevBatch B, const
                 if ((ci & CLS_REV) || cls_frame(ci) != f) continue;
                 if (cls_is_stop(ci)) break;
                 const int ni = ndx[i];
-                for (int j = last - 3; j >= ni; j -= 3) {
-                    const int cj = cod[j] & 63;
-                    acc += dcT[(size_t)(cj | (low << 6)) * nm + col];
-                    low = cj;
+                // 8 codons per round: all codon loads, then all weight loads, then the adds in the original order, so
+                // that two memory round trips cover 8 codons instead of 16 (the chain is latency bound)
+                for (int j = last - 3; j >= ni;) {
+                    const int n = min(8, (j - ni) / 3 + 1);
+                    int cj[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) cj[k] = k < n ? (cod[j - 3 * k] & 63) : 0;
+                    double w[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const int prev = k == 0 ? low : cj[k - 1];
+                        w[k] = k < n ? dcT[(size_t)(cj[k] | (prev << 6)) * nm + col] : 0.0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; k++) if (k < n) acc += w[k];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) if (k == n - 1) low = cj[k];
+                    j -= 3 * n;
                 }
                 if (active) cscore[i] = acc;
                 last = ni;
@@ -356,10 +370,22 @@ __global__ void __launch_bounds__(32 * kOrfWarps) k_coding_orf(DevBatch B, const
                 if (!(ci & CLS_REV) || cls_frame(ci) != f) continue;
                 if (cls_is_stop(ci)) break;
                 const int ni = ndx[i];
-                for (int j = last + 3; j <= ni; j += 3) {
-                    const int cj = rcode_at(d, cod, j);
-                    acc += dcT[(size_t)(cj | (low << 6)) * nm + col];
-                    low = cj;
+                for (int j = last + 3; j <= ni;) {
+                    const int n = min(8, (ni - j) / 3 + 1);
+                    int cj[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) cj[k] = k < n ? rcode_at(d, cod, j + 3 * k) : 0;
+                    double w[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const int prev = k == 0 ? low : cj[k - 1];
+                        w[k] = k < n ? dcT[(size_t)(cj[k] | (prev << 6)) * nm + col] : 0.0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; k++) if (k < n) acc += w[k];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) if (k == n - 1) low = cj[k];
+                    j += 3 * n;
                 }
                 if (active) cscore[i] = acc;
                 last = ni;
@@ -434,11 +460,11 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
             const uint32_t bits = B.sdbits[C.node_off + i];
             const uint32_t A = bits & 0xffffu, G = bits >> 16;
             const int omin = rev ? 0 : max(0, 20 - start);  // forward skips negative offsets only
-            for (int off = omin; off < 15; off++) {
+#pragma unroll
+            for (int off = 0; off < 15; off++) {  // fully unrolled: the 30 table loads are independent
                 const uint32_t gp = ((A >> off) & 0x09u) | ((G >> off) & 0x36u);
-                int e = M.sd_best[0][off][gp], m = M.sd_best[1][off][gp];
-                rbs0 = max(rbs0, e);
-                rbs1 = max(rbs1, m);
+                const int e = M.sd_best[0][off][gp], m = M.sd_best[1][off][gp];
+                if (off >= omin) { rbs0 = max(rbs0, e); rbs1 = max(rbs1, m); }
             }
         } else {
             // best upstream motif, stage 2 (lib.pyx:1557-1616); spacer class of the p-th window of a length is
@@ -502,7 +528,13 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
         {
             const int ncomp = min(2, start) + max(0, min(30, start - 14));
             uint64_t pc = B.upc[C.node_off + i];
-            for (int k = 0; k < ncomp; k++, pc >>= 2) uscore += M.uc[k][pc & 3];
+            for (int k0 = 0; k0 < ncomp; k0 += 8, pc >>= 16) {  // 8 independent loads, then the adds in order
+                double w[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) w[k] = k0 + k < ncomp ? M.uc[k0 + k][(pc >> (2 * k)) & 3] : 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) if (k0 + k < ncomp) uscore += w[k];
+            }
         }
         // starts that would stop the gene from running off the edge (lib.pyx:2407-2422)
         if (!o.closed && ndx <= 2 && !rev) {
@@ -695,11 +727,26 @@ __global__ void __launch_bounds__(128) k_opv(DevBatch B, const DevModel *__restr
 
 // node pairs of an extraction: sum_i (i - min_i)  (implementation independent)
 __global__ void __launch_bounds__(256) k_pairs(DevBatch B, int n_ext, int total_nodes, unsigned long long *ext_pairs) {
+    __shared__ int s_first;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total_nodes) return;
-    const int e = find_ext(B.exts, n_ext, g);
-    const int z = g - B.exts[e].node_off;
-    atomicAdd(&ext_pairs[e], (unsigned long long)(z - B.win_min[g]));
+    if (threadIdx.x == 0) s_first = find_ext(B.exts, n_ext, min(blockIdx.x * blockDim.x, total_nodes - 1));
+    __syncthreads();
+    int e = -1;
+    unsigned long long v = 0;
+    if (g < total_nodes) {
+        e = s_first;
+        while (e + 1 < n_ext && B.exts[e + 1].node_off <= g) e++;
+        v = (unsigned long long)((g - B.exts[e].node_off) - B.win_min[g]);
+    }
+    // warp-level pre-reduction when the whole warp belongs to one extraction
+    const int e0 = __shfl_sync(0xffffffffu, e, 0);
+    if (__all_sync(0xffffffffu, e == e0)) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0 && e0 >= 0 && v) atomicAdd(&ext_pairs[e0], v);
+    } else if (e >= 0 && v) {
+        atomicAdd(&ext_pairs[e], v);
+    }
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -710,15 +757,23 @@ void launch_node_prep(const DevBatch &B, int n_ext, int total_nodes, int seq_par
     if (total_nodes > 0) k_node_prep<<<(total_nodes + 127) / 128, 128, 0, st>>>(B, n_ext, total_nodes, seq_parts);
     k_class_index<<<(n_ext * 32 + 127) / 128, 128, 0, st>>>(B, n_ext);
 }
-void launch_score_chains(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o,
-                         void *mot_out, int n_ext, int total_nodes, cudaStream_t st) {
+void launch_coding(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, int n_ext, int total_nodes,
+                   cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
-    const unsigned nb = (unsigned)((total + 127) / 128);
     if (B.ext_chains && B.dcT && n_ext > 0 && total_nodes > 0)
         k_coding_orf<<<(total_nodes + kOrfWarps - 1) / kOrfWarps, 32 * kOrfWarps, 0, st>>>(B, models, n_ext, total_nodes);
     else
-        k_coding<<<nb, 128, 0, st>>>(B, models, n_chains, total);
-    k_start_score<<<nb, 128, 0, st>>>(B, models, n_chains, total, o, (MotifOut *)mot_out);
+        k_coding<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total);
+}
+void launch_start_score(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o, void *mot_out,
+                        cudaStream_t st) {
+    if (n_chains == 0 || total == 0) return;
+    k_start_score<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total, o, (MotifOut *)mot_out);
+}
+void launch_score_chains(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o,
+                         void *mot_out, int n_ext, int total_nodes, cudaStream_t st) {
+    launch_coding(B, models, n_chains, total, n_ext, total_nodes, st);
+    launch_start_score(B, models, n_chains, total, o, mot_out, st);
 }
 void launch_opv(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
