@@ -76,6 +76,8 @@ struct ExtractInfo {
     int32_t node_off;    // first node in the extraction-node arrays
     int32_t nn;
     int32_t mask_off, n_masks;
+    int32_t n_lo;        // number of nodes with ndx <= 4          (only these and the n_hi last ones can carry an
+    int32_t n_hi;        // number of nodes with ndx >= slen - 5    edge flag; written by k_class_index)
     int32_t pad;
     uint64_t stopmask, startmask;
 };

@@ -52,16 +52,19 @@ __device__ __forceinline__ int mer_base(const uint8_t *__restrict__ d, int slen,
 }
 
 // code of the reverse-strand codon whose 5' base is at forward position p (bases p, p-1, p-2)
-__device__ __forceinline__ int rcode_at(const uint8_t *__restrict__ d, const uint8_t *__restrict__ cod, int p) {
-    int c = cod[p - 2];
-    if (!(c & 64)) return rev_code(c & 63);
+__device__ __noinline__ int rcode_slow(const uint8_t *__restrict__ d, int p) {
+    // a codon with unknown bases: _mer_ndx complements N to N and then keeps its low 2 bits (= C)
     int r = 0;
-#pragma unroll
     for (int k = 0; k < 3; k++) {
         int b = d[p - k];
         r |= (b == 6 ? 2 : (b ^ 3)) << (2 * k);
     }
     return r;
+}
+__device__ __forceinline__ int rcode_at(const uint8_t *__restrict__ d, const uint8_t *__restrict__ cod, int p) {
+    const int c = cod[p - 2];
+    if (__builtin_expect((c & 64) != 0, 0)) return rcode_slow(d, p);  // rare: keep it out of the hot loop
+    return rev_code(c & 63);
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -178,6 +181,16 @@ __global__ void __launch_bounds__(128) k_class_index(DevBatch B, int n_ext) {
     }
     int cb[4] = {0, tot[0], tot[0] + tot[1], tot[0] + tot[1] + tot[2]};
     if (lane < 4) B.cbase[4 * e + lane] = cb[lane];
+    if (lane == 0) {
+        // edge-flagged nodes sit within 5 bp of either sequence end: count the nodes there (ndx is sorted)
+        const int32_t *__restrict__ ndx = B.ndx + X.node_off;
+        int lo = 0, hi = X.nn;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (ndx[mid] <= 4) lo = mid + 1; else hi = mid; }
+        B.exts[e].n_lo = lo;
+        lo = 0; hi = X.nn;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (ndx[mid] < X.slen - 5) lo = mid + 1; else hi = mid; }
+        B.exts[e].n_hi = X.nn - lo;
+    }
     int run[4] = {0, 0, 0, 0};
     for (int base = 0; base < X.nn; base += 32) {
         int i = base + lane;
@@ -340,24 +353,10 @@ __global__ void __launch_bounds__(32 * kOrfWarps) k_coding_orf(DevBatch B, const
                 if ((ci & CLS_REV) || cls_frame(ci) != f) continue;
                 if (cls_is_stop(ci)) break;
                 const int ni = ndx[i];
-                // 8 codons per round: all codon loads, then all weight loads, then the adds in the original order, so
-                // that two memory round trips cover 8 codons instead of 16 (the chain is latency bound)
-                for (int j = last - 3; j >= ni;) {
-                    const int n = min(8, (j - ni) / 3 + 1);
-                    int cj[8];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) cj[k] = k < n ? (cod[j - 3 * k] & 63) : 0;
-                    double w[8];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const int prev = k == 0 ? low : cj[k - 1];
-                        w[k] = k < n ? dcT[(size_t)(cj[k] | (prev << 6)) * nm + col] : 0.0;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 8; k++) if (k < n) acc += w[k];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) if (k == n - 1) low = cj[k];
-                    j -= 3 * n;
+                for (int j = last - 3; j >= ni; j -= 3) {
+                    const int cj = cod[j] & 63;
+                    acc += dcT[(size_t)(cj | (low << 6)) * nm + col];
+                    low = cj;
                 }
                 if (active) cscore[i] = acc;
                 last = ni;
@@ -370,22 +369,10 @@ __global__ void __launch_bounds__(32 * kOrfWarps) k_coding_orf(DevBatch B, const
                 if (!(ci & CLS_REV) || cls_frame(ci) != f) continue;
                 if (cls_is_stop(ci)) break;
                 const int ni = ndx[i];
-                for (int j = last + 3; j <= ni;) {
-                    const int n = min(8, (ni - j) / 3 + 1);
-                    int cj[8];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) cj[k] = k < n ? rcode_at(d, cod, j + 3 * k) : 0;
-                    double w[8];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const int prev = k == 0 ? low : cj[k - 1];
-                        w[k] = k < n ? dcT[(size_t)(cj[k] | (prev << 6)) * nm + col] : 0.0;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 8; k++) if (k < n) acc += w[k];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) if (k == n - 1) low = cj[k];
-                    j += 3 * n;
+                for (int j = last + 3; j <= ni; j += 3) {
+                    const int cj = rcode_at(d, cod, j);
+                    acc += dcT[(size_t)(cj | (low << 6)) * nm + col];
+                    low = cj;
                 }
                 if (active) cscore[i] = acc;
                 last = ni;
@@ -460,11 +447,11 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
             const uint32_t bits = B.sdbits[C.node_off + i];
             const uint32_t A = bits & 0xffffu, G = bits >> 16;
             const int omin = rev ? 0 : max(0, 20 - start);  // forward skips negative offsets only
-#pragma unroll
-            for (int off = 0; off < 15; off++) {  // fully unrolled: the 30 table loads are independent
+            for (int off = omin; off < 15; off++) {
                 const uint32_t gp = ((A >> off) & 0x09u) | ((G >> off) & 0x36u);
-                const int e = M.sd_best[0][off][gp], m = M.sd_best[1][off][gp];
-                if (off >= omin) { rbs0 = max(rbs0, e); rbs1 = max(rbs1, m); }
+                int e = M.sd_best[0][off][gp], m = M.sd_best[1][off][gp];
+                rbs0 = max(rbs0, e);
+                rbs1 = max(rbs1, m);
             }
         } else {
             // best upstream motif, stage 2 (lib.pyx:1557-1616); spacer class of the p-th window of a length is
@@ -528,13 +515,7 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
         {
             const int ncomp = min(2, start) + max(0, min(30, start - 14));
             uint64_t pc = B.upc[C.node_off + i];
-            for (int k0 = 0; k0 < ncomp; k0 += 8, pc >>= 16) {  // 8 independent loads, then the adds in order
-                double w[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) w[k] = k0 + k < ncomp ? M.uc[k0 + k][(pc >> (2 * k)) & 3] : 0.0;
-#pragma unroll
-                for (int k = 0; k < 8; k++) if (k0 + k < ncomp) uscore += w[k];
-            }
+            for (int k = 0; k < ncomp; k++, pc >>= 2) uscore += M.uc[k][pc & 3];
         }
         // starts that would stop the gene from running off the edge (lib.pyx:2407-2422)
         if (!o.closed && ndx <= 2 && !rev) {
@@ -542,13 +523,25 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
         } else if (!o.closed && ndx >= slen - 3 && rev) {
             uscore += PGPU_EDGE_UPS * st_wt;
         } else if (i < 500 && !rev) {
-            // nodes before i already carry their converted edge flag in this sweep
-            for (int j = i - 1; j >= 0; j--)
-                if ((cls[j] & (CLS_EDGE | CLS_CONV)) && stop_val == sva[j]) { uscore += PGPU_EDGE_UPS * st_wt; break; }
+            // lib.pyx:2413-2417: is there an edge node before i with the same stop_val?  Only nodes within 5 bp
+            // of a sequence end can carry an edge flag, i.e. the first n_lo / last n_hi nodes.  Nodes before i
+            // already carry their converted edge flag in this sweep.
+            const int n_lo = B.exts[C.ext].n_lo, n_hi = B.exts[C.ext].n_hi;
+            bool hit = false;
+            for (int j = min(i, n_lo) - 1; j >= 0 && !hit; j--)
+                hit = (cls[j] & (CLS_EDGE | CLS_CONV)) && stop_val == sva[j];
+            for (int j = i - 1; j >= max(nn - n_hi, n_lo) && !hit; j--)
+                hit = (cls[j] & (CLS_EDGE | CLS_CONV)) && stop_val == sva[j];
+            if (hit) uscore += PGPU_EDGE_UPS * st_wt;
         } else if (i + 500 >= nn && rev) {
-            // nodes after i still carry the flag of the previous sweep
-            for (int j = i + 1; j < nn; j++)
-                if ((cls[j] & edge_mask_now) && stop_val == sva[j]) { uscore += PGPU_EDGE_UPS * st_wt; break; }
+            // lib.pyx:2418-2422; nodes after i still carry the flag of the previous sweep
+            const int n_lo = B.exts[C.ext].n_lo, n_hi = B.exts[C.ext].n_hi;
+            bool hit = false;
+            for (int j = max(i + 1, nn - n_hi); j < nn && !hit; j++)
+                hit = (cls[j] & edge_mask_now) && stop_val == sva[j];
+            for (int j = i + 1; j < min(n_lo, nn - n_hi) && !hit; j++)
+                hit = (cls[j] & edge_mask_now) && stop_val == sva[j];
+            if (hit) uscore += PGPU_EDGE_UPS * st_wt;
         }
     }
     // convert starts at the first/last bases into edge nodes (lib.pyx:2424-2434)
