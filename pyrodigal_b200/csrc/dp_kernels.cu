@@ -713,8 +713,41 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
     bool dq_ok = true;
     double rc_v0 = kNeg, rc_v1 = kNeg, rc_v2 = kNeg;
     int rc_j0 = -1, rc_j1 = -1, rc_j2 = -1;
-    double best_sc = -1.0;
-    int best_i = -1, best_tb = -1;
+    // -start nodes depend only on STOP nodes (their own -STOP, +STOPs around a 3' overlap): they are parked and
+    // evaluated lane-parallel just before the next target that reads them (a +start or -STOP) or at the end of
+    // the staged block
+    int pend_cnt = 0, pend_i = 0, pend_q = 0;
+    auto flush = [&](int i0) {
+        if (lane < pend_cnt) {
+            const DqK &P = sk[pend_i - i0];
+            double bv = kNeg;
+            int bj = -1;
+            if (P.x >= P.pad && P.x >= 0 && P.x < pend_i) { bv = score[P.x] + P.cs; bj = P.x; }  // own -STOP (gene)
+            const double cs_diff = P.cs + ig_neg;
+            for (int q = max(P.y, P.w); q < min(P.z, pend_q); q++) {  // +STOPs overlapping the 3' end
+                const int nd = ig_node[q];
+                if (nd >= 0) continue;
+                const double s = svig[q];
+                if (s == kNeg) continue;
+                const int nj = ig_ndx[q];
+                if (P.sv - 2 >= nj + 2) continue;
+                const int ovlp = (nj + 2) - (P.sv - 2) + 1;
+                if (ovlp >= kMaxOppOvlp) continue;
+                if ((nj - P.sv) >= (P.ndx - nj + 3)) continue;
+                if ((nj - P.sv) >= (P.sv - 3 - ndx[tbig[q]])) continue;
+                const double v = s + cs_diff;
+                const int j = nd & 0x7fffffff;
+                if (v > bv || (v == bv && j > bj)) { bv = v; bj = j; }
+            }
+            double sc = 0.0;
+            int tb = -1;
+            if (bj >= 0 && bv >= 0.0) { sc = bv; tb = bj; }
+            score[pend_i] = sc; traceb[pend_i] = tb; ov_mark[pend_i] = -1;
+            svig[pend_q] = tb == -1 ? kNeg : sc;
+        }
+        pend_cnt = 0;
+        __syncwarp();
+    };
 
     for (int i0 = 0; i0 < nn; i0 += 32) {
       __syncwarp();
@@ -745,6 +778,13 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
         const DqK &K = sk[i - i0];
         const int ci = K.cls, kind = cls_kind(ci), f2 = cls_frame(ci), ndx_i = K.ndx, sv_i = K.sv;
         lo += (K.leave == K_FE) | (K.leave == K_RS);
+        if (kind == K_RS) {  // park it (merged-stream slot reserved now)
+            if (lane == pend_cnt) { pend_i = i; pend_q = cur; }
+            pend_cnt++;
+            cur++;
+            continue;
+        }
+        if (kind != K_FE && pend_cnt) flush(i0);
         double wv = kNeg;
         int wj = -1, wfr = -1;
         auto cand = [&](double v, int j, int fr) { if (v > wv || (v == wv && j > wj)) { wv = v; wj = j; wfr = fr; } };
@@ -875,56 +915,68 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
                 if (star_ptr[3 * (int64_t)j + f2] == -1) continue;
                 cand(s + opv[3 * (int64_t)j + f2], j, -1);
             }
-        } else {  // K_RS
-            // own -STOP (gene, _connection.h:228-237); K.w = merged-stream rank of the window start
-            if (lane == 0 && K.x >= K.pad && K.x >= 0 && K.x < i) cand(score[K.x] + cs_i, K.x, -1);
-            // +STOPs overlapping the 3' end (_connection.h:239-256)
-            const double cs_diff = cs_i + ig_neg;
-            for (int q = max(K.y, K.w) + lane; q < min(K.z, cur); q += 32) {
-                const int nd = ig_node[q];
-                if (nd >= 0) continue;
-                const double s = svig[q];
-                if (s == kNeg) continue;
-                const int nj = ig_ndx[q];
-                if (sv_i - 2 >= nj + 2) continue;
-                const int ovlp = (nj + 2) - (sv_i - 2) + 1;
-                if (ovlp >= kMaxOppOvlp) continue;
-                if ((nj - sv_i) >= (ndx_i - nj + 3)) continue;
-                if ((nj - sv_i) >= (sv_i - 3 - ndx[tbig[q]])) continue;
-                cand(s + cs_diff, nd & 0x7fffffff, -1);
-            }
         }
 
-        warp_argmax(wv, wj, wfr);
+        {
+            const unsigned have = __ballot_sync(0xffffffffu, wj >= 0);
+            if ((have & (have - 1)) == 0) {  // at most one lane holds a candidate: broadcast it
+                const int src = have ? __ffs(have) - 1 : 0;
+                wv = __shfl_sync(0xffffffffu, wv, src);
+                wj = __shfl_sync(0xffffffffu, wj, src);
+                wfr = __shfl_sync(0xffffffffu, wfr, src);
+            } else {
+                warp_argmax(wv, wj, wfr);
+            }
+        }
         double sc_i = 0.0;
         int tb_i = -1, fr_i = -1;
         if (wj >= 0 && wv >= 0.0) { sc_i = wv; tb_i = wj; fr_i = wfr; }
         if (lane == 0) {
             score[i] = sc_i; traceb[i] = tb_i; ov_mark[i] = (int8_t)fr_i;
-            if (kind == K_FE || kind == K_RS) {
+            if (kind == K_FE) {
                 svig[cur] = tb_i == -1 ? kNeg : sc_i;  // edge-artifact rule: nothing leads into it
-                if (kind == K_FE) tbig[cur] = tb_i;
+                tbig[cur] = tb_i;
             }
         }
         if (kind == K_FE) {
             cur++;
             if (f2 == 0) { rc_v0 = kNeg; rc_j0 = -1; } else if (f2 == 1) { rc_v1 = kNeg; rc_j1 = -1; } else { rc_v2 = kNeg; rc_j2 = -1; }
-        } else if (kind == K_RS) {
-            cur++;
         } else if (kind == K_FS) {
             const double g = sc_i + cs_i;
             if (f2 == 0) { if (g >= rc_v0) { rc_v0 = g; rc_j0 = i; } }
             else if (f2 == 1) { if (g >= rc_v1) { rc_v1 = g; rc_j1 = i; } }
             else { if (g >= rc_v2) { rc_v2 = g; rc_j2 = i; } }
         }
-        if ((kind == K_FE || kind == K_RS) && sc_i >= best_sc) { best_sc = sc_i; best_i = i; best_tb = tb_i; }
         __syncwarp();
       }
+      if (pend_cnt) flush(i0);  // the staged constants are about to be replaced
     }
+    // the best terminal node (lib.pyx:1239-1251) is found by k_chain_best
+}
+
+// arg-max of the DP score over the terminal node kinds (+STOP, -start), largest index among equal maxima
+// (lib.pyx:1239-1251 scans from the end with a strict ">"); -1 when nothing leads into it (lib.pyx:1311)
+__global__ void __launch_bounds__(128) k_chain_best(DevBatch B, int n_chains) {
+    const int chain = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (chain >= n_chains) return;
+    const ChainInfo C = B.chains[chain];
+    const uint8_t *__restrict__ cls = B.cls + C.node_off;
+    const double *__restrict__ score = B.score + C.coff;
+    double bv = -1.0;
+    int bi = -1;
+    for (int i = lane; i < C.nn; i += 32) {
+        const int k = cls_kind(cls[i]);
+        if (k != K_FE && k != K_RS) continue;
+        const double v = score[i];
+        if (v >= bv) { bv = v; bi = i; }   // i increases within a lane
+    }
+    int fr = 0;
+    if (bi < 0) bv = -DBL_MAX;
+    warp_argmax(bv, bi, fr);
     if (lane == 0) {
-        const bool ok = best_i >= 0 && best_tb != -1;
-        B.chain_ipath[chain] = ok ? best_i : -1;
-        B.chain_score[chain] = ok ? best_sc : 0.0;
+        const bool ok = bi >= 0 && (B.traceb + C.coff)[bi] != -1;
+        B.chain_ipath[chain] = ok ? bi : -1;
+        B.chain_score[chain] = ok ? bv : 0.0;
     }
 }
 
@@ -1271,6 +1323,7 @@ void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, 
         const int nb = (n_chains + kFastWarps - 1) / kFastWarps;
         if (algo == 4) k_dp_dq<4><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);
         else k_dp_dq<8><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);
+        k_chain_best<<<(n_chains * 32 + 127) / 128, 128, 0, st>>>(B, n_chains);
     } else if (final && algo >= 1 && B.dp_sv) {
         const int nb = (n_chains + kFastWarps - 1) / kFastWarps;
         if (algo == 2) k_dp_fast<4><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);   // up to 128 regs
