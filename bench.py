@@ -251,6 +251,7 @@ def main():
         t0 = time.perf_counter()
         last = None
         for _ in range(steps):
+            last = None  # release the previous result first: its pinned buffer is reused by the next step
             last = fn()
         ms = ctx.timer_stop()
         wall = (time.perf_counter() - t0) * 1e3
