@@ -92,7 +92,7 @@ struct pgpu_ctx {
     size_t ws_limit = 0;
     cudaEvent_t ev[16];
     int64_t launches = 0;
-    int dp_algo = 5;           // 5: k_dp_dq2 (default), 3: k_dp_dq, 1/2: k_dp_fast, 0: all-pairs k_dp (PGPU_DP_ALGO=n)
+    int dp_algo = 3;           // 3: k_dp_dq (default), 1/2: k_dp_fast, 0: all-pairs k_dp (PGPU_DP_ALGO=n)
     std::shared_ptr<struct PinnedPool> pinned;  // shared with the results it backs (they may outlive the context)
 };
 
