@@ -417,13 +417,20 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     B.digits = pool.alloc<uint8_t>(dtot + 256);
     B.cod = pool.alloc<uint8_t>(dtot + 256);
     B.contigs = pool.upload(contigs);
+    const int64_t gcwords = dtot / 32 + 8;
+    B.gcbits = pool.alloc<uint32_t>(gcwords);
+    B.gcpre = pool.alloc<int32_t>(gcwords + 1);
+    int *d_gc_bs = pool.alloc<int>(scan_num_blocks(gcwords) + 1);
+    int *d_gc_tot = pool.alloc<int>(1);
     B.gc_count = pool.alloc<int32_t>(n, true);
     B.unknown = pool.alloc<int32_t>(n, true);
     int2 *d_tiles = pool.upload(tiles);
     if (pool.failed) return PGPU_ENOMEM;
     tev("setup/alloc/memset");
     launch_encode(B, d_tiles, (int)tiles.size(), st);
-    tev("k_encode");
+    launch_gc_scan(B, dtot / 32, d_gc_bs, d_gc_tot, st);
+    ctx->launches += 3;
+    tev("k_encode+gc scan");
     ctx->launches++;
     std::vector<int4> h_masks;
     if (opts.mask) {
@@ -691,6 +698,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         fin_coff[c + 1] = fin_coff[c] + mx;
     }
     pgpu_gene *d_genes = pool.alloc<pgpu_gene>(gene_off[n]);
+    pgpu_gene *d_genes_raw = pool.alloc<pgpu_gene>(gene_off[n]);
     int64_t *d_gene_off = pool.upload(gene_off);
     std::vector<pgpu_contig_summary> summ(n);
     for (int c = 0; c < n; c++) { memset(&summ[c], 0, sizeof(summ[c])); summ[c].unknown = h_unk[c]; summ[c].gc_count = h_gc[c]; }
@@ -703,9 +711,9 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     tev("k_dp");
     ctx->launches++;
     int e_dp = mark();
-    launch_trace(B, ctx->d_models, n, d_ccb, d_tracef, d_elim, d_genes, d_gene_off, d_summ, d_winner_chain, meta ? 1 : 0,
-                 opts.max_overlap, st);
-    ctx->launches++;
+    launch_trace(B, ctx->d_models, n, d_ccb, d_tracef, d_elim, d_genes, d_genes_raw, d_gene_off, gene_off[n], d_summ,
+                 d_winner_chain, meta ? 1 : 0, opts.max_overlap, st);
+    ctx->launches += 3;
     tev("k_trace");
     int e_trace = mark();
 

@@ -105,6 +105,8 @@ struct DevBatch {
     const uint8_t *ascii;
     uint8_t *digits;
     uint8_t *cod;
+    uint32_t *gcbits;     // 1 bit per base: not A / not T (unknown bases count as GC, _sequence.h:35-43)
+    int32_t *gcpre;       // exclusive prefix of popcount(gcbits) per 32-base word
     ContigInfo *contigs;
     int32_t *gc_count;   // per contig
     int32_t *unknown;    // per contig

@@ -1015,7 +1015,8 @@ struct TraceArgs {
     const int32_t *contig_chain_begin;  // [n_contigs + 1] chains of contig c
     int32_t *tracef;                    // per chain-node
     uint8_t *elim;                      // per chain-node
-    pgpu_gene *genes;                   // gene buffers
+    pgpu_gene *genes;                   // gene buffers (final, after k_tweak)
+    pgpu_gene *genes_raw;               // gene buffers as extracted (before k_tweak)
     const int64_t *gene_off;            // [n_contigs] offset of each contig's gene buffer
     pgpu_contig_summary *summary;       // [n_contigs]
     int32_t *winner_chain;              // [n_contigs] chain index of the winner or -1
@@ -1109,7 +1110,7 @@ __global__ void __launch_bounds__(64) k_trace(DevBatch B, const DevModel *__rest
         }
 
         // Genes._extract (lib.pyx:3231-3270)
-        pgpu_gene *genes = A.genes + A.gene_off[c];
+        pgpu_gene *genes = A.genes_raw + A.gene_off[c];
         int ng = 0, begin = 0, end = 0, start_ndx = 0, stop_ndx = 0;
         for (int p = head; p != -1; p = N.tracef[p]) {
             if (N.elim[p] == 1) continue;
@@ -1126,85 +1127,127 @@ __global__ void __launch_bounds__(64) k_trace(DevBatch B, const DevModel *__rest
         }
         S.n_genes = ng;
 
-        // Genes._tweak_final_starts (lib.pyx:3272-3401); edge flags are the post-scoring ones
-        auto is_edge = [&](int x) { return (N.cls[x] & (CLS_EDGE | CLS_CONV)) != 0; };
-        auto strand_of = [&](int x) { return (N.cls[x] & CLS_REV) ? -1 : 1; };
-        for (int gi = 0; gi < ng; gi++) {
-            const int cur = genes[gi].start_ndx;
-            const double sc = N.sscore[cur] + N.cscore[cur];
-            double igm0 = 0.0;
-            const int pstart = gi > 0 ? genes[gi - 1].start_ndx : -1, pstop = gi > 0 ? genes[gi - 1].stop_ndx : -1;
-            const int nstart = gi < ng - 1 ? genes[gi + 1].start_ndx : -1, nstop = gi < ng - 1 ? genes[gi + 1].stop_ndx : -1;
-            const int scur = strand_of(cur);
-            if (pstart >= 0 && scur == 1 && strand_of(pstart) == 1) igm0 = igm_nodes(N, pstop, cur, M);
-            if (pstart >= 0 && scur == 1 && strand_of(pstart) == -1) igm0 = M.ig_neg;
-            if (nstart >= 0 && scur == -1 && strand_of(nstart) == 1) igm0 = M.ig_neg;
-            if (nstart >= 0 && scur == -1 && strand_of(nstart) == -1) igm0 = igm_nodes(N, cur, nstop, M);
-
-            int maxndx[2] = {-1, -1};
-            double maxsc[2] = {0, 0}, maxigm[2] = {0, 0};
-            for (int j = cur - 100; j < cur + 100; j++) {
-                if (j < 0 || j >= nn || j == cur) continue;
-                if (cls_is_stop(N.cls[j]) || N.sv[j] != N.sv[cur]) continue;
-                const int sj = strand_of(j);
-                double tigm = 0.0;
-                if (pstart >= 0 && sj == 1 && strand_of(pstart) == 1) {
-                    if (N.ndx[pstop] - N.ndx[j] > A.max_overlap) continue;
-                    tigm = igm_nodes(N, pstop, j, M);
-                }
-                if (pstart >= 0 && sj == 1 && strand_of(pstart) == -1) {
-                    if (N.ndx[pstart] - N.ndx[j] >= 0) continue;
-                    tigm = M.ig_neg;
-                }
-                if (nstart >= 0 && sj == -1 && strand_of(nstart) == 1) {
-                    if (N.ndx[j] - N.ndx[nstart] >= 0) continue;
-                    tigm = M.ig_neg;
-                }
-                if (nstart >= 0 && sj == -1 && strand_of(nstart) == -1) {
-                    if (N.ndx[j] - N.ndx[nstop] > A.max_overlap) continue;
-                    tigm = igm_nodes(N, j, nstop, M);
-                }
-                const double csc = N.cscore[j] + N.sscore[j];
-                if (maxndx[0] == -1) {
-                    maxndx[0] = j; maxsc[0] = csc; maxigm[0] = tigm;
-                } else if (csc + tigm > maxsc[0]) {
-                    maxndx[1] = maxndx[0]; maxsc[1] = maxsc[0]; maxigm[1] = maxigm[0];
-                    maxndx[0] = j; maxsc[0] = csc; maxigm[0] = tigm;
-                } else if (maxndx[1] == -1 || csc + tigm > maxsc[1]) {
-                    maxndx[1] = j; maxsc[1] = csc; maxigm[1] = tigm;
-                }
-            }
-            for (int q = 0; q < 2; q++) {
-                const int m = maxndx[q];
-                if (m == -1) continue;
-                if (N.tscore[m] < N.tscore[cur] && maxsc[q] - N.tscore[m] >= sc - N.tscore[cur] + M.st_wt &&
-                    N.rscore[m] > N.rscore[cur] && N.uscore[m] > N.uscore[cur] && N.cscore[m] > N.cscore[cur] &&
-                    abs(N.ndx[m] - N.ndx[cur]) > 15) {
-                    maxsc[q] += N.tscore[cur] - N.tscore[m];
-                } else if (abs(N.ndx[m] - N.ndx[cur]) <= 15 &&
-                           N.rscore[m] + N.tscore[m] > N.rscore[cur] + N.tscore[cur] && !is_edge(cur) && !is_edge(m)) {
-                    if (N.cscore[cur] > N.cscore[m]) maxsc[q] += N.cscore[cur] - N.cscore[m];
-                    if (N.uscore[cur] > N.uscore[m]) maxsc[q] += N.uscore[cur] - N.uscore[m];
-                    if (igm0 > maxigm[q]) maxsc[q] += igm0 - maxigm[q];
-                } else {
-                    maxsc[q] = -1000.0;
-                }
-            }
-            int pick = -1;
-            for (int q = 0; q < 2; q++) {
-                if (maxndx[q] == -1) continue;
-                if (pick == -1 && maxsc[q] + maxigm[q] > sc + igm0) pick = q;
-                else if (pick >= 0 && maxsc[q] + maxigm[q] > maxsc[pick] + maxigm[pick]) pick = q;
-            }
-            if (pick != -1) {
-                const int m = maxndx[pick];
-                genes[gi].start_ndx = m;
-                if (strand_of(m) == 1) genes[gi].begin = N.ndx[m] + 1;
-                else genes[gi].end = N.ndx[m] + 1;
-            }
-        }
+        // Genes._tweak_final_starts runs gene-parallel in k_tweak
     }
     A.summary[c] = S;
+}
+
+// --------------------------------------------------------------------------------------------------
+// Genes._tweak_final_starts (lib.pyx:3272-3401), one thread per gene.  In the reference the genes are tweaked in
+// order and in place; gene i only ever reads (a) its predecessor's stop node and strand (never changed by a
+// tweak), (b) its predecessor's *start* node position when the predecessor is on the reverse strand and gene i on
+// the forward strand, (c) its successor's untouched start/stop.  So two passes reproduce the sequential result:
+// pass 0 tweaks the reverse-strand genes (reading the original array), pass 1 the forward-strand genes (reading
+// reverse predecessors from the pass-0 output).
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_tweak(DevBatch B, const DevModel *__restrict__ models, int n_contigs, TraceArgs A,
+                                                const pgpu_gene *__restrict__ orig, int64_t total_slots, int pass) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_slots) return;
+    // contig of this gene slot
+    int lo = 0, hi = n_contigs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (A.gene_off[mid] <= t) lo = mid; else hi = mid - 1;
+    }
+    const int c = lo;
+    const int gi = (int)(t - A.gene_off[c]);
+    const int ng = A.summary[c].n_genes;
+    if (gi >= ng) return;
+    const int win = A.winner_chain[c];
+    const ChainInfo C = B.chains[win];
+    const DevModel &M = models[C.model];
+    const int nn = C.nn;
+    NodeRef N;
+    N.ndx = B.ndx + C.node_off; N.sv = B.stop_val + C.node_off; N.cls = B.cls + C.node_off;
+    N.cscore = B.cscore + C.coff; N.sscore = B.sscore + C.coff; N.rscore = B.rscore + C.coff;
+    N.uscore = B.uscore + C.coff; N.tscore = B.tscore + C.coff;
+    N.traceb = nullptr; N.tracef = nullptr; N.star_ptr = nullptr; N.ov_mark = nullptr; N.elim = nullptr;
+    const pgpu_gene *og = orig + A.gene_off[c];   // untouched genes (Genes._extract)
+    pgpu_gene *genes = A.genes + A.gene_off[c];    // output (pass 0: reverse genes, pass 1: forward genes)
+    auto is_edge = [&](int x) { return (N.cls[x] & (CLS_EDGE | CLS_CONV)) != 0; };
+    auto strand_of = [&](int x) { return (N.cls[x] & CLS_REV) ? -1 : 1; };
+    const int cur = og[gi].start_ndx;
+    const int scur = strand_of(cur);
+    if ((pass == 0) != (scur == -1)) return;
+    // neighbours as the sequential loop sees them
+    int pstart = gi > 0 ? og[gi - 1].start_ndx : -1;
+    // a reverse-strand predecessor was tweaked in pass 0 (a tweak keeps stop and strand, only the start moves)
+    if (pass == 1 && pstart >= 0 && strand_of(pstart) == -1) pstart = genes[gi - 1].start_ndx;
+    const int pstop = gi > 0 ? og[gi - 1].stop_ndx : -1;
+    const int nstart = gi < ng - 1 ? og[gi + 1].start_ndx : -1, nstop = gi < ng - 1 ? og[gi + 1].stop_ndx : -1;
+    pgpu_gene G = og[gi];
+    {
+        const double sc = N.sscore[cur] + N.cscore[cur];
+        double igm0 = 0.0;
+        if (pstart >= 0 && scur == 1 && strand_of(pstart) == 1) igm0 = igm_nodes(N, pstop, cur, M);
+        if (pstart >= 0 && scur == 1 && strand_of(pstart) == -1) igm0 = M.ig_neg;
+        if (nstart >= 0 && scur == -1 && strand_of(nstart) == 1) igm0 = M.ig_neg;
+        if (nstart >= 0 && scur == -1 && strand_of(nstart) == -1) igm0 = igm_nodes(N, cur, nstop, M);
+
+        int maxndx[2] = {-1, -1};
+        double maxsc[2] = {0, 0}, maxigm[2] = {0, 0};
+        for (int j = cur - 100; j < cur + 100; j++) {
+            if (j < 0 || j >= nn || j == cur) continue;
+            if (cls_is_stop(N.cls[j]) || N.sv[j] != N.sv[cur]) continue;
+            const int sj = strand_of(j);
+            double tigm = 0.0;
+            if (pstart >= 0 && sj == 1 && strand_of(pstart) == 1) {
+                if (N.ndx[pstop] - N.ndx[j] > A.max_overlap) continue;
+                tigm = igm_nodes(N, pstop, j, M);
+            }
+            if (pstart >= 0 && sj == 1 && strand_of(pstart) == -1) {
+                if (N.ndx[pstart] - N.ndx[j] >= 0) continue;
+                tigm = M.ig_neg;
+            }
+            if (nstart >= 0 && sj == -1 && strand_of(nstart) == 1) {
+                if (N.ndx[j] - N.ndx[nstart] >= 0) continue;
+                tigm = M.ig_neg;
+            }
+            if (nstart >= 0 && sj == -1 && strand_of(nstart) == -1) {
+                if (N.ndx[j] - N.ndx[nstop] > A.max_overlap) continue;
+                tigm = igm_nodes(N, j, nstop, M);
+            }
+            const double csc = N.cscore[j] + N.sscore[j];
+            if (maxndx[0] == -1) {
+                maxndx[0] = j; maxsc[0] = csc; maxigm[0] = tigm;
+            } else if (csc + tigm > maxsc[0]) {
+                maxndx[1] = maxndx[0]; maxsc[1] = maxsc[0]; maxigm[1] = maxigm[0];
+                maxndx[0] = j; maxsc[0] = csc; maxigm[0] = tigm;
+            } else if (maxndx[1] == -1 || csc + tigm > maxsc[1]) {
+                maxndx[1] = j; maxsc[1] = csc; maxigm[1] = tigm;
+            }
+        }
+        for (int q = 0; q < 2; q++) {
+            const int m = maxndx[q];
+            if (m == -1) continue;
+            if (N.tscore[m] < N.tscore[cur] && maxsc[q] - N.tscore[m] >= sc - N.tscore[cur] + M.st_wt &&
+                N.rscore[m] > N.rscore[cur] && N.uscore[m] > N.uscore[cur] && N.cscore[m] > N.cscore[cur] &&
+                abs(N.ndx[m] - N.ndx[cur]) > 15) {
+                maxsc[q] += N.tscore[cur] - N.tscore[m];
+            } else if (abs(N.ndx[m] - N.ndx[cur]) <= 15 &&
+                       N.rscore[m] + N.tscore[m] > N.rscore[cur] + N.tscore[cur] && !is_edge(cur) && !is_edge(m)) {
+                if (N.cscore[cur] > N.cscore[m]) maxsc[q] += N.cscore[cur] - N.cscore[m];
+                if (N.uscore[cur] > N.uscore[m]) maxsc[q] += N.uscore[cur] - N.uscore[m];
+                if (igm0 > maxigm[q]) maxsc[q] += igm0 - maxigm[q];
+            } else {
+                maxsc[q] = -1000.0;
+            }
+        }
+        int pick = -1;
+        for (int q = 0; q < 2; q++) {
+            if (maxndx[q] == -1) continue;
+            if (pick == -1 && maxsc[q] + maxigm[q] > sc + igm0) pick = q;
+            else if (pick >= 0 && maxsc[q] + maxigm[q] > maxsc[pick] + maxigm[pick]) pick = q;
+        }
+        if (pick != -1) {
+            const int m = maxndx[pick];
+            G.start_ndx = m;
+            if (strand_of(m) == 1) G.begin = N.ndx[m] + 1;
+            else G.end = N.ndx[m] + 1;
+        }
+    }
+    genes[gi] = G;
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -1333,11 +1376,17 @@ void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, 
     else k_dp<0><<<n_chains, kDpThreads, 0, st>>>(B, models, order, n_chains);
 }
 void launch_trace(const DevBatch &B, const DevModel *models, int n_contigs, const int32_t *contig_chain_begin,
-                  int32_t *tracef, uint8_t *elim, pgpu_gene *genes, const int64_t *gene_off,
-                  pgpu_contig_summary *summary, int32_t *winner_chain, int meta, int max_overlap, cudaStream_t st) {
+                  int32_t *tracef, uint8_t *elim, pgpu_gene *genes, pgpu_gene *genes_raw, const int64_t *gene_off,
+                  int64_t total_gene_slots, pgpu_contig_summary *summary, int32_t *winner_chain, int meta, int max_overlap,
+                  cudaStream_t st) {
     if (n_contigs == 0) return;
-    TraceArgs A = {contig_chain_begin, tracef, elim, genes, gene_off, summary, winner_chain, meta, max_overlap};
+    TraceArgs A = {contig_chain_begin, tracef, elim, genes, genes_raw, gene_off, summary, winner_chain, meta, max_overlap};
     k_trace<<<(n_contigs + 63) / 64, 64, 0, st>>>(B, models, n_contigs, A);
+    if (total_gene_slots > 0) {
+        const unsigned nb = (unsigned)((total_gene_slots + 127) / 128);
+        k_tweak<<<nb, 128, 0, st>>>(B, models, n_contigs, A, genes_raw, total_gene_slots, 0);
+        k_tweak<<<nb, 128, 0, st>>>(B, models, n_contigs, A, genes_raw, total_gene_slots, 1);
+    }
 }
 void launch_pack_nodes(const DevBatch &B, int n_chains, int64_t total, const void *mot, const int32_t *tracef,
                        const uint8_t *elim, int dp_state, pgpu_node *out, cudaStream_t st) {

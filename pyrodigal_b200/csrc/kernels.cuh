@@ -11,6 +11,7 @@ void launch_find_masks(const DevBatch &B, const int2 *tiles, int n_tiles, int mi
 void launch_extract_mark(const DevBatch &B, int n_ext, RunOpts o, cudaStream_t st);
 void launch_extract_fill(const DevBatch &B, int n_ext, RunOpts o, cudaStream_t st);
 int scan_num_blocks(int64_t nwords);
+void launch_gc_scan(const DevBatch &B, int64_t nwords, int *block_sums, int *total_out, cudaStream_t st);
 void launch_word_scan(const DevBatch &B, int64_t nwords, int *block_sums, int *total_out, cudaStream_t st);
 
 // score_kernels.cu
@@ -31,8 +32,9 @@ void launch_pairs(const DevBatch &B, int n_ext, int total_nodes, unsigned long l
 void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, int n_chains, int final, int algo,
                cudaStream_t st);
 void launch_trace(const DevBatch &B, const DevModel *models, int n_contigs, const int32_t *contig_chain_begin,
-                  int32_t *tracef, uint8_t *elim, pgpu_gene *genes, const int64_t *gene_off,
-                  pgpu_contig_summary *summary, int32_t *winner_chain, int meta, int max_overlap, cudaStream_t st);
+                  int32_t *tracef, uint8_t *elim, pgpu_gene *genes, pgpu_gene *genes_raw, const int64_t *gene_off,
+                  int64_t total_gene_slots, pgpu_contig_summary *summary, int32_t *winner_chain, int meta, int max_overlap,
+                  cudaStream_t st);
 void launch_pack_nodes(const DevBatch &B, int n_chains, int64_t total, const void *mot, const int32_t *tracef,
                        const uint8_t *elim, int dp_state, pgpu_node *out, cudaStream_t st);
 void launch_pack_gene_nodes(int n_contigs, const pgpu_contig_summary *summary, const pgpu_gene *genes,

@@ -131,35 +131,23 @@ __global__ void __launch_bounds__(128) k_node_prep(DevBatch B, int n_ext, int to
             if (x >= 0 && x < slen) U |= (uint64_t)mer_base(d, slen, x, rev) << (2 * q);
         }
         B.umot[X.node_off + z] = U;
+        // gc_cont (lib.pyx:1846-1896): the reference accumulates GC counts of codon triplets from the stop to
+        // the start; that is the GC count of a contiguous range, taken here from the GC bitmap + word prefix:
+        //   forward: [ndx, stop+3);  reverse: the stop's bases [stop-2, stop] plus [stop+3, ndx+3) (T14: the
+        //   reverse window is shifted by two bases), positions beyond the sequence end count 0
+        const uint32_t *__restrict__ gb = B.gcbits + (X.doff >> 5);
+        const int32_t *__restrict__ gp = B.gcpre + (X.doff >> 5);
+        auto P = [&](int x) {  // number of GC bits in [0, x)
+            x = max(0, min(x, slen));
+            return gp[x >> 5] + __popc(gb[x >> 5] & ((1u << (x & 31)) - 1u));
+        };
+        const int stop = sv[z];
+        const int gc = rev ? (P(stop + 1) - P(stop - 2)) + (P(my + 3) - P(stop + 3)) : P(stop + 3) - P(my);
+        B.gc_cont[X.node_off + z] = (float)((double)gc / (abs(stop - my) + 3.0));
         return;
     }
 
-    // ---- gc_cont of every start of this ORF (lib.pyx:1846-1896) ----
-    if (kind == K_FE) {
-        int gc = gc3(cod[my] & 63), last = my;
-        for (int i = z - 1; i >= 0; i--) {
-            int ci = cls[i];
-            if ((ci & CLS_REV) || cls_frame(ci) != f) continue;
-            if (cls_is_stop(ci)) break;
-            const int ni = ndx[i];
-            for (int j = last - 3; j >= ni; j -= 3) gc += gc3(cod[j] & 63);
-            B.gc_cont[X.node_off + i] = (float)((double)gc / (abs(sv[i] - ni) + 3.0));
-            last = ni;
-        }
-    } else {
-        int gc = my >= 2 ? gc3(cod[my - 2] & 63) : 0, last = my;
-        if (my < 2) for (int k = my; k > my - 3; k--) if (k >= 0) { int b = d[k]; gc += (b != 0 && b != 3); }
-        for (int i = z + 1; i < nn; i++) {
-            int ci = cls[i];
-            if (!(ci & CLS_REV) || cls_frame(ci) != f) continue;
-            if (cls_is_stop(ci)) break;
-            const int ni = ndx[i];
-            // window starts at j (two bases right of the codon), bounds-guarded: lib.pyx:1887-1890
-            for (int j = last + 3; j <= ni; j += 3) gc += gc3(cod[j] & 63);
-            B.gc_cont[X.node_off + i] = (float)((double)gc / (abs(sv[i] - ni) + 3.0));
-            last = ni;
-        }
-    }
+    // STOP nodes: nothing else to prepare
 }
 
 // per-class ranks and class-sorted index lists (SoA replacement of ConnectionScorer._index,

@@ -57,6 +57,20 @@ __global__ void __launch_bounds__(256) k_encode(DevBatch B, const int2 *__restri
         *reinterpret_cast<uint4 *>(B.digits + o) = make_uint4(d[0], d[1], d[2], d[3]);
         *reinterpret_cast<uint4 *>(B.cod + o) = make_uint4(c[0], c[1], c[2], c[3]);
     }
+    {
+        // GC bitmap: 16 bits per thread, two neighbouring threads share a 32-bit word
+        uint32_t bits = 0;
+        if (k0 < n) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int p = k0 + k;
+                if (p < n) { const uint32_t b0 = s[p]; bits |= (uint32_t)(b0 != 0 && b0 != 3) << k; }
+            }
+        }
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, bits, 1);
+        if ((threadIdx.x & 1) == 0 && k0 < ((n + 31) & ~31))
+            B.gcbits[(ci.doff + start + k0) >> 5] = bits | (other << 16);
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         gc += __shfl_down_sync(0xffffffffu, gc, off);
@@ -353,9 +367,46 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(const uint32_t *__r
     }
 }
 
+// same three phases for a single bit array (GC bitmap)
+__global__ void __launch_bounds__(kScanThreads) k_count_words1(const uint32_t *__restrict__ a, int64_t nwords,
+                                                               int *__restrict__ block_sums) {
+    const int64_t base = (int64_t)blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++)
+        if (base + k < nwords) s += __popc(a[base + k]);
+    int total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply1(const uint32_t *__restrict__ a, int64_t nwords,
+                                                              const int *__restrict__ block_sums,
+                                                              int32_t *__restrict__ pre) {
+    const int64_t base = (int64_t)blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
+    int c[kScanItems], s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        c[k] = (base + k < nwords) ? __popc(a[base + k]) : 0;
+        s += c[k];
+    }
+    int total;
+    int ex = block_exclusive_scan(s, &total) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        if (base + k <= nwords) pre[base + k] = ex;
+        ex += c[k];
+    }
+}
+
 // --------------------------------------------------------------------------------------------------
 // launch wrappers
 // --------------------------------------------------------------------------------------------------
+void launch_gc_scan(const DevBatch &B, int64_t nwords, int *block_sums, int *total_out, cudaStream_t st) {
+    const int nb = scan_num_blocks(nwords);
+    k_count_words1<<<nb, kScanThreads, 0, st>>>(B.gcbits, nwords, block_sums);
+    k_scan_top<<<1, kScanThreads, 0, st>>>(block_sums, nb, total_out);
+    k_scan_apply1<<<nb, kScanThreads, 0, st>>>(B.gcbits, nwords, block_sums, B.gcpre);
+}
 void launch_encode(const DevBatch &B, const int2 *tiles, int n_tiles, cudaStream_t st) {
     if (n_tiles > 0) k_encode<<<n_tiles, 256, 0, st>>>(B, tiles);
 }

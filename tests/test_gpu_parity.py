@@ -297,3 +297,33 @@ def test_long_contig_meta_and_single_vs_oracle(ctx, capi):
         cmp_nodes(r.nodes(0), n2, f"single{b}", dp=True)
         assert int(r.summary["ipath"][0]) == ipath
         c.close()
+
+
+def test_sub_batching_matches_single_batch(capi):
+    """a tiny workspace limit forces run_all to split the contigs into several sub-batches; genes, their node
+    records and the per-contig node arrays must be identical to the single-batch run"""
+    seqs = [R.synth(60_000 + 1000 * (k % 7), 0.35 + 0.005 * k, 9000 + k) for k in range(64)]
+    arrs = [np.frombuffer(s, np.uint8) for s in seqs]
+    off = np.zeros(len(arrs) + 1, np.int64)
+    np.cumsum([len(a) for a in arrs], out=off[1:])
+    flat = np.ascontiguousarray(np.concatenate(arrs))
+    o = capi.make_opts(meta=True, want_nodes=True)
+    c1 = capi.Context(0)
+    c1.set_models(R.bins_blob(), 50)
+    r1 = c1.find_genes_batch(flat, off, o)
+    c2 = capi.Context(0)
+    c2.set_models(R.bins_blob(), 50)
+    capi.check(capi.lib.pgpu_set_workspace_limit(c2.handle, 1), c2.handle)  # -> 1 Mbp per sub-batch
+    r2 = c2.find_genes_batch(flat, off, o)
+    assert r2.stats["kernel_launches"] > 2 * r1.stats["kernel_launches"]
+    assert r1.summary.tobytes() == r2.summary.tobytes()
+    cmp_int(r2.genes, r1.genes, "subbatch.genes")
+    assert r2.gene_nodes.tobytes() == r1.gene_nodes.tobytes()
+    for k in (0, 17, 63):
+        assert r1.nodes(k).tobytes() == r2.nodes(k).tobytes()
+    for k in range(len(seqs)):
+        a, b = r2.gene_off[k], r2.gene_off[k + 1]
+        g = np.zeros(b - a, dtype=capi.GENE_DTYPE)
+        capi.check(capi.lib.pgpu_result_genes(r2.handle, k, capi.ptr(g)))
+        cmp_int(g, r1.genes[a:b], f"subbatch.contig{k}")
+    r1.free(); r2.free(); c1.close(); c2.close()
