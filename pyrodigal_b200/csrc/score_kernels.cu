@@ -341,7 +341,17 @@ __global__ void __launch_bounds__(32 * kOrfWarps) k_coding_orf(DevBatch B, const
                 if ((ci & CLS_REV) || cls_frame(ci) != f) continue;
                 if (cls_is_stop(ci)) break;
                 const int ni = ndx[i];
-                for (int j = last - 3; j >= ni; j -= 3) {
+                // the chain (codon load -> weight load -> add) is latency bound: take 4 codons per round while at
+                // least 4 remain (their loads are independent and in flight together; adds keep the original order)
+                int j = last - 3;
+                for (; j - 9 >= ni; j -= 12) {
+                    const int c0 = cod[j] & 63, c1 = cod[j - 3] & 63, c2 = cod[j - 6] & 63, c3 = cod[j - 9] & 63;
+                    const double w0 = dcT[(size_t)(c0 | (low << 6)) * nm + col], w1 = dcT[(size_t)(c1 | (c0 << 6)) * nm + col];
+                    const double w2 = dcT[(size_t)(c2 | (c1 << 6)) * nm + col], w3 = dcT[(size_t)(c3 | (c2 << 6)) * nm + col];
+                    acc += w0; acc += w1; acc += w2; acc += w3;
+                    low = c3;
+                }
+                for (; j >= ni; j -= 3) {
                     const int cj = cod[j] & 63;
                     acc += dcT[(size_t)(cj | (low << 6)) * nm + col];
                     low = cj;
@@ -357,7 +367,16 @@ __global__ void __launch_bounds__(32 * kOrfWarps) k_coding_orf(DevBatch B, const
                 if (!(ci & CLS_REV) || cls_frame(ci) != f) continue;
                 if (cls_is_stop(ci)) break;
                 const int ni = ndx[i];
-                for (int j = last + 3; j <= ni; j += 3) {
+                int j = last + 3;
+                for (; j + 9 <= ni; j += 12) {
+                    const int c0 = rcode_at(d, cod, j), c1 = rcode_at(d, cod, j + 3), c2 = rcode_at(d, cod, j + 6),
+                              c3 = rcode_at(d, cod, j + 9);
+                    const double w0 = dcT[(size_t)(c0 | (low << 6)) * nm + col], w1 = dcT[(size_t)(c1 | (c0 << 6)) * nm + col];
+                    const double w2 = dcT[(size_t)(c2 | (c1 << 6)) * nm + col], w3 = dcT[(size_t)(c3 | (c2 << 6)) * nm + col];
+                    acc += w0; acc += w1; acc += w2; acc += w3;
+                    low = c3;
+                }
+                for (; j <= ni; j += 3) {
                     const int cj = rcode_at(d, cod, j);
                     acc += dcT[(size_t)(cj | (low << 6)) * nm + col];
                     low = cj;
@@ -503,7 +522,13 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
         {
             const int ncomp = min(2, start) + max(0, min(30, start - 14));
             uint64_t pc = B.upc[C.node_off + i];
-            for (int k = 0; k < ncomp; k++, pc >>= 2) uscore += M.uc[k][pc & 3];
+            int k = 0;
+            for (; k + 4 <= ncomp; k += 4, pc >>= 8) {  // 4 independent loads, adds in the reference's order
+                const double w0 = M.uc[k][pc & 3], w1 = M.uc[k + 1][(pc >> 2) & 3], w2 = M.uc[k + 2][(pc >> 4) & 3],
+                             w3 = M.uc[k + 3][(pc >> 6) & 3];
+                uscore += w0; uscore += w1; uscore += w2; uscore += w3;
+            }
+            for (; k < ncomp; k++, pc >>= 2) uscore += M.uc[k][pc & 3];
         }
         // starts that would stop the gene from running off the edge (lib.pyx:2407-2422)
         if (!o.closed && ndx <= 2 && !rev) {
