@@ -86,6 +86,8 @@ struct pgpu_ctx {
     int n_models = 0;
     std::vector<RawTraining> h_raw;
     std::vector<DevModel> h_models;
+    std::vector<double> model_gc;     // compact copies for the per-contig planning loop
+    std::vector<int> model_tt;
     RawTraining *d_raw = nullptr;
     DevModel *d_models = nullptr;
     double *d_dcT = nullptr;   // dicodon weights transposed: [4096][n_models], columns sorted by (tt, gc)
@@ -477,6 +479,8 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     std::vector<int32_t> contig_chain_begin(n + 1, 0);
     std::vector<int32_t> contig_ext_begin(n + 1, 0);
     int64_t nwords = 0;
+    exts.reserve((size_t)n * 2);
+    chains.reserve((size_t)n * (meta ? 16 : 1));
     for (int c = 0; c < n; c++) {
         contig_chain_begin[c] = (int)chains.size();
         contig_ext_begin[c] = (int)exts.size();
@@ -490,7 +494,16 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
             X.slot = (int)exts.size() - contig_ext_begin[c];
             X.woff = nwords; X.nwords = ci.slen / 32 + 1;
             X.mask_off = ci.mask_off; X.n_masks = ci.n_masks;
-            codon_masks(tt, &X.stopmask, &X.startmask);
+            {   // codon masks per translation table, computed once
+                static thread_local uint64_t cache[34][2];
+                static thread_local bool have[34] = {false};
+                if (tt >= 0 && tt < 34) {
+                    if (!have[tt]) { codon_masks(tt, &cache[tt][0], &cache[tt][1]); have[tt] = true; }
+                    X.stopmask = cache[tt][0]; X.startmask = cache[tt][1];
+                } else {
+                    codon_masks(tt, &X.stopmask, &X.startmask);
+                }
+            }
             nwords += X.nwords;
             exts.push_back(X);
             return (int)exts.size() - 1;
@@ -513,11 +526,12 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
             const double gc = ci.slen > 0 ? (double)h_gc[c] / (double)ci.slen : 0.0;
             const double low = window_low(gc), high = window_high(gc);
             int tt = -1;
+            const double *mgc = ctx->model_gc.data();
+            const int *mtt = ctx->model_tt.data();
             for (int m = 0; m < ctx->n_models; m++) {
-                const DevModel &M = ctx->h_models[m];
-                if (M.gc < low || M.gc > high) continue;
-                const int first = M.trans_table != tt;
-                tt = M.trans_table;
+                if (mgc[m] < low || mgc[m] > high) continue;
+                const int first = mtt[m] != tt;
+                tt = mtt[m];
                 add_chain(m, tt, first, 1);
             }
         }
@@ -997,6 +1011,9 @@ int pgpu_set_models(pgpu_ctx *ctx, const void *blobs, int n, size_t stride) {
     CK(cudaMemcpy(ctx->d_raw, ctx->h_raw.data(), n * sizeof(RawTraining), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_models, ctx->h_models.data(), n * sizeof(DevModel), cudaMemcpyHostToDevice));
     ctx->n_models = n;
+    ctx->model_gc.resize(n);
+    ctx->model_tt.resize(n);
+    for (int k = 0; k < n; k++) { ctx->model_gc[k] = ctx->h_raw[k].gc; ctx->model_tt[k] = ctx->h_raw[k].trans_table; }
     return PGPU_OK;
 }
 

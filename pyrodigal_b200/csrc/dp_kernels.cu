@@ -793,6 +793,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
         if (kind == K_FS || kind == K_RE) {
             // ---- entries that fall more than 180 bp behind move into the deque ----
             const int thr = ndx_i - 3 * kOperDist;
+            if (far < cur && ig_ndx[far] < thr)  // usually nothing crosses the boundary at this step
             for (;;) {
                 const int q = far + lane;
                 const bool in = q < cur;
