@@ -327,3 +327,21 @@ def test_sub_batching_matches_single_batch(capi):
         capi.check(capi.lib.pgpu_result_genes(r2.handle, k, capi.ptr(g)))
         cmp_int(g, r1.genes[a:b], f"subbatch.contig{k}")
     r1.free(); r2.free(); c1.close(); c2.close()
+
+
+def test_single_chain_16mbp_vs_oracle(capi):
+    """cfg5-style stress (one long chromosome, single mode, one DP chain of ~0.9 M nodes): gene boundaries and the
+    whole DP state must match the oracle; also exercises int32/int64 offsets well beyond the batch tests"""
+    seq = R.synth(16_000_000, 0.5, 55)
+    d, gc, unk = orc.encode(seq)
+    blob = R.bin_blob(20)
+    g2, n2, ipath = orc.find_genes_single(d, blob)
+    c = capi.Context(0)
+    c.set_models(blob, 1)
+    a = np.frombuffer(seq, np.uint8)
+    r = c.find_genes_batch(np.ascontiguousarray(a), np.array([0, len(a)], np.int64),
+                           capi.make_opts(meta=False, single_model=0, want_nodes=True))
+    cmp_int(r.genes, g2, "chr.genes")
+    cmp_nodes(r.nodes(0), n2, "chr", dp=True)
+    assert int(r.summary["ipath"][0]) == ipath and len(n2) > 500_000
+    r.free(); c.close()
