@@ -140,53 +140,88 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_reference_runner():
-    """returns (fn(list_of_bytes) -> total genes, kind, description, cores)"""
+_REF_GF = None
+
+
+def _ref_init(ref_dir):
+    """process-pool worker initialiser: import the unmodified reference and build one GeneFinder"""
+    global _REF_GF
+    sys.path.insert(0, ref_dir)
+    import pyrodigal
+    _REF_GF = pyrodigal.GeneFinder(meta=True)
+
+
+def _ref_work(seq):
+    return len(_REF_GF.find_genes(seq))
+
+
+def cpu_reference_runners():
+    """[(label, kind, fn(list_of_bytes) -> total genes, close)] -- the reference's own CPU implementation with every
+    host core: its documented thread-pool recipe (docs/guide/parallel.rst:24-41, cli.py:286-300) and the process
+    pool its CLI also offers (cli.py:292-293).  Falls back to the C oracle port when oracle/_ref is absent."""
     cores = os.cpu_count() or 1
     from multiprocessing.pool import ThreadPool
+    import multiprocessing as mp
     ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    out = []
     try:
         if not os.path.exists(os.path.join(ref_dir, "pyrodigal")):
             raise ImportError("oracle/_ref not present")
         sys.path.insert(0, ref_dir)
         import pyrodigal  # the unmodified reference
         gf = pyrodigal.GeneFinder(meta=True)  # backend="detect" (SSE2/AVX2 SIMD skip filter)
-        pool = ThreadPool(cores)
-
-        def run(seqs):
-            # the reference's documented parallel recipe: docs/guide/parallel.rst:24-41, cli.py:286-300
-            return sum(len(g) for g in pool.map(gf.find_genes, seqs))
-        return run, "reference", f"pyrodigal {pyrodigal.__version__} GeneFinder(meta=True) ThreadPool({cores})", cores
+        tp = ThreadPool(cores)
+        out.append((f"pyrodigal {pyrodigal.__version__} GeneFinder(meta=True) ThreadPool({cores})", "reference",
+                    lambda seqs: sum(len(g) for g in tp.map(gf.find_genes, seqs)), tp.close))
+        try:
+            pp = mp.get_context("spawn").Pool(cores, initializer=_ref_init, initargs=(ref_dir,))
+            out.append((f"pyrodigal {pyrodigal.__version__} GeneFinder(meta=True) multiprocessing.Pool({cores})", "reference",
+                        lambda seqs: sum(pp.map(_ref_work, seqs, chunksize=1)), pp.terminate))
+        except Exception:
+            pass
     except Exception as e:
         from oracle import oracle as orc
         import refutil as R
         blob = R.bins_blob()
-        pool = ThreadPool(cores)
+        tp = ThreadPool(cores)
 
         def one(s):
             d, gc, unk = orc.encode(s)
             return len(orc.find_genes_meta(d, gc / len(d) if len(d) else 0.0, blob)[0])
-
-        def run(seqs):
-            return sum(pool.map(one, seqs))
-        return run, "port", f"C oracle port ThreadPool({cores}) [{type(e).__name__}: {e}]", cores
+        out.append((f"C oracle port ThreadPool({cores}) [{type(e).__name__}: {e}]", "port",
+                    lambda seqs: sum(tp.map(one, seqs)), tp.close))
+    return out, cores
 
 
 def time_cpu(flat, offsets, steps, warmup, max_contigs):
-    run, kind, desc, cores = cpu_reference_runner()
+    """times every available CPU configuration on the same bounded sample and reports the fastest"""
+    runners, cores = cpu_reference_runners()
     n = min(len(offsets) - 1, max_contigs)
-    seqs = [flat[offsets[k]:offsets[k + 1]].tobytes() for k in range(n)]
+    # longest contigs first: the pools then finish without a long tail
+    seqs = sorted((flat[offsets[k]:offsets[k + 1]].tobytes() for k in range(n)), key=len, reverse=True)
     bp = int(offsets[n] - offsets[0])
-    for _ in range(warmup):
-        run(seqs[: max(1, n // 8)])
-    t0 = time.perf_counter()
-    genes = 0
-    for _ in range(steps):
-        genes = run(seqs)
-    dt = (time.perf_counter() - t0) / steps
-    return {"value": bp / dt / 1e6, "unit": "Mbp/s", "cores": cores, "kind": kind,
-            "sample": f"first {n} contigs of the rank-0 shard ({bp / 1e6:.1f} Mbp), {desc}", "s_per_step": dt,
-            "genes": genes}
+    best = None
+    tried = []
+    for label, kind, run, close in runners:
+        try:
+            for _ in range(max(1, warmup)):
+                run(seqs[: max(cores, n // 8)])
+            t0 = time.perf_counter()
+            genes = 0
+            for _ in range(steps):
+                genes = run(seqs)
+            dt = (time.perf_counter() - t0) / steps
+            tried.append(f"{label}: {bp / dt / 1e6:.1f} Mbp/s")
+            if best is None or dt < best["s_per_step"]:
+                best = {"value": bp / dt / 1e6, "unit": "Mbp/s", "cores": cores, "kind": kind, "s_per_step": dt,
+                        "genes": genes, "label": label}
+        finally:
+            try:
+                close()
+            except Exception:
+                pass
+    best["sample"] = (f"first {n} contigs of the rank-0 shard ({bp / 1e6:.1f} Mbp); fastest of: " + "; ".join(tried))
+    return best
 
 
 def main():
