@@ -955,367 +955,6 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
     // the best terminal node (lib.pyx:1239-1251) is found by k_chain_best
 }
 
-// --------------------------------------------------------------------------------------------------
-// k_dp_dq3: k_dp_dq with BOTH start kinds parked.  A start node's DP value is read only (a) through the merged
-// stream (-starts) and (b) as "best start of the open ORF" (+starts), i.e. by STOP nodes, so every run of starts
-// between two STOP nodes is evaluated in one flush:
-//   phase 1  -starts, lane-parallel (they depend on STOP nodes only);
-//   phase 2  a warp-uniform pass in node order over the parked +starts that advances the 180-bp boundary and the
-//            deque and hands each +start its far maximum (no warp reduction at all);
-//   phase 3  +starts, 8 lanes per start (4 starts per round): the sources within 180 bp are spread over the lanes
-//            of the group and reduced with three shuffle rounds; the group leader merges the far maximum;
-//   phase 4  fold into the per-frame running maximum in node order (ties -> later start).
-// Only STOP nodes (23 % of the nodes) take a warp-cooperative step.
-// --------------------------------------------------------------------------------------------------
-template <int MINB>
-__global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq3(DevBatch B, const DevModel *__restrict__ models,
-                                                                    const int32_t *__restrict__ order, int n_chains) {
-    __shared__ DqK s_k[kFastWarps][32];
-    __shared__ double s_dqv[kFastWarps][kDqCap];
-    __shared__ int32_t s_dqj[kFastWarps][kDqCap];
-    const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
-    const int slot = blockIdx.x * kFastWarps + wslot;
-    if (slot >= n_chains) return;
-    const int chain = order ? order[slot] : slot;
-    const ChainInfo C = B.chains[chain];
-    const int nn = C.nn;
-    if (nn == 0) return;  // k_chain_best reports "no path"
-    const DevModel &M = models[C.model];
-    const int32_t *__restrict__ ndx = B.ndx + C.node_off;
-    const int32_t *__restrict__ sv = B.stop_val + C.node_off;
-    const uint8_t *__restrict__ cls = B.cls + C.node_off;
-    const int32_t *__restrict__ ig_node = B.ig_node + C.node_off;
-    const int32_t *__restrict__ ig_ndx = B.ig_ndx + C.node_off;
-    const int4 *__restrict__ dqx = B.dqx + C.node_off;
-    const double *__restrict__ cscore = B.cscore + C.coff;
-    const double *__restrict__ sscore = B.sscore + C.coff;
-    const double *__restrict__ opv = B.opv + 3 * C.coff;
-    const int32_t *__restrict__ star_ptr = B.star_ptr + 3 * C.coff;
-    double *score = B.score + C.coff;       // written and re-read by this warp: no read-only path
-    int32_t *traceb = B.traceb + C.coff;
-    int8_t *ov_mark = B.ov_mark + C.coff;
-    double *svig = B.dp_svig + C.coff;
-    int32_t *tbig = B.dp_tbig + C.coff;
-    DqK *sk = s_k[wslot];
-    double *dqv = s_dqv[wslot];
-    int32_t *dqj = s_dqj[wslot];
-    const double ig_neg = M.ig_neg;
-
-    int cur = 0, lo = 0, far = 0;
-    int dq_head = 0, dq_cnt = 0;
-    bool dq_ok = true;
-    double rc_v0 = kNeg, rc_v1 = kNeg, rc_v2 = kNeg;
-    int rc_j0 = -1, rc_j1 = -1, rc_j2 = -1;
-
-    // moves every merged-stream entry with ndx < thr into the deque, then drops entries that left [i-1000, i)
-    auto advance_far = [&](int thr, int i) {
-        for (;;) {
-            const int q = far + lane;
-            const bool in = q < cur;
-            const int nq = in ? ig_ndx[q] : 0x7fffffff;
-            const double sq = in ? svig[q] : kNeg;
-            const int jq = in ? (ig_node[q] & 0x7fffffff) : 0;
-            const int c = __popc(__ballot_sync(0xffffffffu, nq < thr));  // ndx sorted: a prefix of the lanes
-            for (int t = 0; t < c; t++) {
-                const double s = __shfl_sync(0xffffffffu, sq, t);
-                const int j = __shfl_sync(0xffffffffu, jq, t);
-                if (s == kNeg || !dq_ok) continue;
-                const double x = s + ig_neg;
-                while (dq_cnt > 0 && dqv[(dq_head + dq_cnt - 1) & (kDqCap - 1)] <= x) dq_cnt--;
-                if (dq_cnt == kDqCap) { dq_ok = false; continue; }
-                if (lane == 0) { dqv[(dq_head + dq_cnt) & (kDqCap - 1)] = x; dqj[(dq_head + dq_cnt) & (kDqCap - 1)] = j; }
-                dq_cnt++;
-                __syncwarp();
-            }
-            far += c;
-            if (c < 32) break;
-        }
-        if (dq_ok)
-            while (dq_cnt > 0 && dqj[dq_head] < i - 2 * kMaxNodeDist) { dq_head = (dq_head + 1) & (kDqCap - 1); dq_cnt--; }
-    };
-
-    // parked starts: lane t holds the t-th one
-    int pend_cnt = 0, pend_i = 0, pend_q = 0, pend_lo = 0, pend_cur = 0;
-    bool pend_rs = false;
-    auto flush = [&](int i0) {
-        // ---- phase 1: -starts (own -STOP, +STOPs around a 3' overlap) ----
-        if (lane < pend_cnt && pend_rs) {
-            const DqK &P = sk[pend_i - i0];
-            double bv = kNeg;
-            int bj = -1;
-            if (P.x >= P.pad && P.x >= 0 && P.x < pend_i) { bv = score[P.x] + P.cs; bj = P.x; }
-            const double cs_diff = P.cs + ig_neg;
-            for (int q = max(P.y, P.w); q < min(P.z, pend_q); q++) {
-                const int nd = ig_node[q];
-                if (nd >= 0) continue;
-                const double s = svig[q];
-                if (s == kNeg) continue;
-                const int nj = ig_ndx[q];
-                if (P.sv - 2 >= nj + 2) continue;
-                const int ovlp = (nj + 2) - (P.sv - 2) + 1;
-                if (ovlp >= kMaxOppOvlp) continue;
-                if ((nj - P.sv) >= (P.ndx - nj + 3)) continue;
-                if ((nj - P.sv) >= (P.sv - 3 - ndx[tbig[q]])) continue;
-                const double v = s + cs_diff;
-                const int j = nd & 0x7fffffff;
-                if (v > bv || (v == bv && j > bj)) { bv = v; bj = j; }
-            }
-            double sc = 0.0;
-            int tb = -1;
-            if (bj >= 0 && bv >= 0.0) { sc = bv; tb = bj; }
-            score[pend_i] = sc; traceb[pend_i] = tb; ov_mark[pend_i] = -1;
-            svig[pend_q] = tb == -1 ? kNeg : sc;
-        }
-        __syncwarp();
-        // ---- phase 2: far maximum of every parked +start, in node order (warp uniform) ----
-        const unsigned fs_mask = __ballot_sync(0xffffffffu, lane < pend_cnt && !pend_rs);
-        double far_v = kNeg;
-        int far_j = -1, my_flo = 0;
-        for (unsigned m = fs_mask; m; m &= m - 1) {
-            const int t = __ffs(m) - 1;
-            const int it = __shfl_sync(0xffffffffu, pend_i, t);
-            const int lot = __shfl_sync(0xffffffffu, pend_lo, t);
-            const int ndx_t = sk[it - i0].ndx;
-            advance_far(ndx_t - 3 * kOperDist, it);
-            const int flo = max(far, lot);
-            if (lane == t) {
-                my_flo = flo;
-                if (dq_ok) { if (dq_cnt > 0) { far_v = dqv[dq_head]; far_j = dqj[dq_head]; } }
-                else {  // deque overflowed once: scan the far range of this target
-                    for (int q = lot; q < flo; q++) {
-                        const double s = svig[q];
-                        if (s == kNeg) continue;
-                        const double v = s + ig_neg;
-                        const int j = ig_node[q] & 0x7fffffff;
-                        if (v > far_v || (v == far_v && j > far_j)) { far_v = v; far_j = j; }
-                    }
-                }
-            }
-        }
-        // ---- phase 3: +starts, 8 lanes per start: sources within 180 bp, then merge with the far maximum ----
-        double g = 0.0;
-        int my_f = 3;
-        {
-            const int nfs = __popc(fs_mask);
-            for (int r0 = 0; r0 < nfs; r0 += 4) {
-                const int grp = lane >> 3, sub = lane & 7;
-                const int which = r0 + grp;                      // ordinal of the +start this group serves
-                // lane holding that start: the (which+1)-th set bit of fs_mask
-                unsigned mm = fs_mask;
-                for (int z = 0; z < which && mm; z++) mm &= mm - 1;
-                const bool live = which < nfs && mm != 0;
-                const int src = live ? __ffs(mm) - 1 : 0;
-                const int it = __shfl_sync(0xffffffffu, pend_i, src);
-                const int flo_t = __shfl_sync(0xffffffffu, my_flo, src);
-                const int cur_t = __shfl_sync(0xffffffffu, pend_cur, src);
-                const double fv = __shfl_sync(0xffffffffu, far_v, src);
-                const int fj = __shfl_sync(0xffffffffu, far_j, src);
-                double bv = kNeg;
-                int bj = -1;
-                int ndx_t = 0;
-                if (live) {
-                    ndx_t = sk[it - i0].ndx;
-                    for (int q = flo_t + sub; q < cur_t; q += 8) {
-                        const double s = svig[q];
-                        if (s == kNeg) continue;
-                        const int nd = ig_node[q], nj = ig_ndx[q];
-                        double v;
-                        int j;
-                        if (nd < 0) {  // +STOP (_connection.h:116-123)
-                            if (nj + 2 >= ndx_t) continue;
-                            const int dist = ndx_t - nj;
-                            v = s + (dist > 3 * kOperDist ? ig_neg : (dist <= kOperDist ? M.igt[dist] : 0.0));
-                            j = nd & 0x7fffffff;
-                        } else {       // -start (_connection.h:124-129)
-                            if (nj >= ndx_t) continue;
-                            v = s + ig_neg;
-                            j = nd;
-                        }
-                        if (v > bv || (v == bv && j > bj)) { bv = v; bj = j; }
-                    }
-                }
-#pragma unroll
-                for (int off = 1; off < 8; off <<= 1) {  // arg-max inside the 8-lane group
-                    const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-                    const int oj = __shfl_xor_sync(0xffffffffu, bj, off);
-                    if (ov > bv || (ov == bv && oj > bj)) { bv = ov; bj = oj; }
-                }
-                if (live && sub == 0) {
-                    if (fv > bv || (fv == bv && fj > bj)) { bv = fv; bj = fj; }
-                    double sc = 0.0;
-                    int tb = -1;
-                    if (bj >= 0 && bv >= 0.0) { sc = bv; tb = bj; }
-                    score[it] = sc; traceb[it] = tb; ov_mark[it] = -1;
-                    g = sc + sk[it - i0].cs;            // held by the group leader (lane 8*grp)
-                    my_f = cls_frame(sk[it - i0].cls) | (it << 2);
-                }
-                // hand (g, frame, node) of the 4 groups to phase 4 in node order
-                for (int gq = 0; gq < 4 && r0 + gq < nfs; gq++) {
-                    const double gt = __shfl_sync(0xffffffffu, g, 8 * gq);
-                    const int fi = __shfl_sync(0xffffffffu, my_f, 8 * gq);
-                    const int ft = fi & 3, itq = fi >> 2;
-                    if (ft == 0) { if (gt >= rc_v0) { rc_v0 = gt; rc_j0 = itq; } }
-                    else if (ft == 1) { if (gt >= rc_v1) { rc_v1 = gt; rc_j1 = itq; } }
-                    else { if (gt >= rc_v2) { rc_v2 = gt; rc_j2 = itq; } }
-                }
-            }
-        }
-        pend_cnt = 0;
-        __syncwarp();
-    };
-
-    for (int i0 = 0; i0 < nn; i0 += 32) {
-      __syncwarp();
-      if (i0 + lane < nn) {
-          const int i = i0 + lane;
-          DqK k;
-          k.ndx = ndx[i]; k.sv = sv[i]; k.cls = cls[i];
-          k.leave = i > 2 * kMaxNodeDist ? cls_kind(cls[i - 2 * kMaxNodeDist - 1]) : -1;
-          const int kind = cls_kind(k.cls);
-          const int4 dx = dqx[i];
-          k.x = dx.x; k.y = dx.y; k.z = dx.z; k.w = dx.w;
-          k.cs = (kind == K_FS || kind == K_RS) ? cscore[i] + sscore[i] : 0.0;
-          k.sp0 = k.sp1 = k.sp2 = -1;
-          k.n3n0 = k.n3n1 = k.n3n2 = k.n3s0 = k.n3s1 = k.n3s2 = 0;
-          k.op0 = k.op1 = k.op2 = 0.0;
-          k.pad = kind == K_RS ? B.win_min[C.node_off + i] : 0;
-          if (kind == K_RE) {
-              k.sp0 = star_ptr[3 * (int64_t)i]; k.sp1 = star_ptr[3 * (int64_t)i + 1]; k.sp2 = star_ptr[3 * (int64_t)i + 2];
-              if (k.sp0 != -1) { k.n3n0 = ndx[k.sp0]; k.n3s0 = sv[k.sp0]; k.op0 = opv[3 * (int64_t)i]; }
-              if (k.sp1 != -1) { k.n3n1 = ndx[k.sp1]; k.n3s1 = sv[k.sp1]; k.op1 = opv[3 * (int64_t)i + 1]; }
-              if (k.sp2 != -1) { k.n3n2 = ndx[k.sp2]; k.n3s2 = sv[k.sp2]; k.op2 = opv[3 * (int64_t)i + 2]; }
-          }
-          sk[lane] = k;
-      }
-      __syncwarp();
-      const int iend = min(i0 + 32, nn);
-      for (int i = i0; i < iend; i++) {
-        const DqK &K = sk[i - i0];
-        const int ci = K.cls, kind = cls_kind(ci), f2 = cls_frame(ci), ndx_i = K.ndx;
-        lo += (K.leave == K_FE) | (K.leave == K_RS);
-        if (kind == K_FS || kind == K_RS) {  // park (a -start reserves its merged-stream slot now)
-            if (lane == pend_cnt) { pend_i = i; pend_q = cur; pend_lo = lo; pend_cur = cur; pend_rs = kind == K_RS; }
-            pend_cnt++;
-            cur += kind == K_RS;
-            continue;
-        }
-        if (pend_cnt) flush(i0);
-        double wv = kNeg;
-        int wj = -1, wfr = -1;
-        auto cand = [&](double v, int j, int fr) { if (v > wv || (v == wv && j > wj)) { wv = v; wj = j; wfr = fr; } };
-
-        if (kind == K_RE) {
-            advance_far(ndx_i - 3 * kOperDist, i);
-            const int flo = max(far, lo);
-            if (dq_ok) {
-                if (dq_cnt > 0 && lane == 0) cand(dqv[dq_head], dqj[dq_head], -1);
-            } else {
-                for (int q = lo + lane; q < flo; q += 32) {
-                    const double s = svig[q];
-                    if (s != kNeg) cand(s + ig_neg, ig_node[q] & 0x7fffffff, -1);
-                }
-            }
-            // +STOP with the triple-overlap search (_connection.h:297-334), for one merged-stream position
-            auto eval_fe = [&](int q, double s, int nj, int nd) {
-                const int left = nj + 2, right = ndx_i - 2;
-                if (left >= right) return;
-                int maxfr = -1, tj = kTbNone;
-                double maxval = 0.0;
-                auto probe = [&](int k, int spk, int n3n, int n3s, double op) {
-                    if (spk == -1) return;
-                    const int ovlp = left - n3s + 3;
-                    if (ovlp <= 0 || ovlp >= kMaxOppOvlp) return;
-                    if (ovlp >= n3n - left) return;
-                    if (tj == kTbNone) tj = ndx[tbig[q]];
-                    if (ovlp >= n3s - tj - 2) return;
-                    if (op > maxval) { maxfr = k; maxval = op; }
-                };
-                probe(0, K.sp0, K.n3n0, K.n3s0, K.op0);
-                probe(1, K.sp1, K.n3n1, K.n3s1, K.op1);
-                probe(2, K.sp2, K.n3n2, K.n3s2, K.op2);
-                cand(s + (maxfr != -1 ? maxval : ig_neg), nd & 0x7fffffff, maxfr);
-            };
-            for (int q = flo + lane; q < cur; q += 32) {
-                const double s = svig[q];
-                if (s == kNeg) continue;
-                const int nd = ig_node[q], nj = ig_ndx[q];
-                if (nd < 0) {
-                    eval_fe(q, s, nj, nd);
-                } else {  // -start (_connection.h:335-341)
-                    if (nj >= ndx_i - 2) continue;
-                    const int dist = ndx_i - nj;
-                    cand(s + (dist > 3 * kOperDist ? ig_neg : (dist <= kOperDist ? M.igt[dist] : 0.0)), nd, -1);
-                }
-            }
-            auto special = [&](int spk, int n3s) {
-                if (spk == -1) return;
-                int a_ = lo, b_ = flo;  // ndx in [n3s-4, n3s+194]
-                while (a_ < b_) { const int mid = (a_ + b_) >> 1; if (ig_ndx[mid] < n3s - 4) a_ = mid + 1; else b_ = mid; }
-                const int a = a_;
-                b_ = flo;
-                while (a_ < b_) { const int mid = (a_ + b_) >> 1; if (ig_ndx[mid] < n3s + 195) a_ = mid + 1; else b_ = mid; }
-                for (int q = a + lane; q < a_; q += 32) {
-                    const int nd = ig_node[q];
-                    const double s = svig[q];
-                    if (nd < 0 && s != kNeg) eval_fe(q, s, ig_ndx[q], nd);
-                }
-            };
-            special(K.sp0, K.n3s0);
-            special(K.sp1, K.n3s1);
-            special(K.sp2, K.n3s2);
-            if (lane < 3) {  // -STOPs whose ORF spans this stop: operon (_connection.h:343-356)
-                const int j = lane == 0 ? K.x : (lane == 1 ? K.y : K.z);
-                const int spl = lane == 0 ? K.sp0 : (lane == 1 ? K.sp1 : K.sp2);
-                const double opl = lane == 0 ? K.op0 : (lane == 1 ? K.op1 : K.op2);
-                if (j >= 0 && j >= i - 2 * kMaxNodeDist && spl != -1) cand(score[j] + opl, j, -1);
-            }
-        } else {  // K_FE
-            {   // best +start of this ORF (gene)
-                const double rv = f2 == 0 ? rc_v0 : (f2 == 1 ? rc_v1 : rc_v2);
-                const int rj = f2 == 0 ? rc_j0 : (f2 == 1 ? rc_j1 : rc_j2);
-                if (lane == 0 && rj >= 0) cand(rv, rj, -1);
-            }
-            for (int q = max(K.x, K.w) + lane; q < cur; q += 32) {  // +STOPs inside the ORF (operon)
-                const int nd = ig_node[q];
-                if (nd >= 0) continue;
-                const double s = svig[q];
-                if (s == kNeg) continue;
-                const int j = nd & 0x7fffffff;
-                if (star_ptr[3 * (int64_t)j + f2] == -1) continue;
-                cand(s + opv[3 * (int64_t)j + f2], j, -1);
-            }
-        }
-        {
-            const unsigned have = __ballot_sync(0xffffffffu, wj >= 0);
-            if ((have & (have - 1)) == 0) {
-                const int src = have ? __ffs(have) - 1 : 0;
-                wv = __shfl_sync(0xffffffffu, wv, src);
-                wj = __shfl_sync(0xffffffffu, wj, src);
-                wfr = __shfl_sync(0xffffffffu, wfr, src);
-            } else {
-                warp_argmax(wv, wj, wfr);
-            }
-        }
-        double sc_i = 0.0;
-        int tb_i = -1, fr_i = -1;
-        if (wj >= 0 && wv >= 0.0) { sc_i = wv; tb_i = wj; fr_i = wfr; }
-        if (lane == 0) {
-            score[i] = sc_i; traceb[i] = tb_i; ov_mark[i] = (int8_t)fr_i;
-            if (kind == K_FE) {
-                svig[cur] = tb_i == -1 ? kNeg : sc_i;
-                tbig[cur] = tb_i;
-            }
-        }
-        if (kind == K_FE) {
-            cur++;
-            if (f2 == 0) { rc_v0 = kNeg; rc_j0 = -1; } else if (f2 == 1) { rc_v1 = kNeg; rc_j1 = -1; } else { rc_v2 = kNeg; rc_j2 = -1; }
-        }
-        __syncwarp();
-      }
-      if (pend_cnt) flush(i0);
-    }
-}
-
 // arg-max of the DP score over the terminal node kinds (+STOP, -start), largest index among equal maxima
 // (lib.pyx:1239-1251 scans from the end with a strict ">"); -1 when nothing leads into it (lib.pyx:1311)
 __global__ void __launch_bounds__(128) k_chain_best(DevBatch B, int n_chains) {
@@ -1724,11 +1363,7 @@ void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, 
                cudaStream_t st) {
     if (n_chains == 0) return;
     // algo 1 (default): k_dp_fast, final scoring only; algo 0: the all-pairs kernel (also the training DP)
-    if (final && algo >= 5 && B.dp_svig) {
-        const int nb = (n_chains + kFastWarps - 1) / kFastWarps;
-        k_dp_dq3<8><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);
-        k_chain_best<<<(n_chains * 32 + 127) / 128, 128, 0, st>>>(B, n_chains);
-    } else if (final && algo >= 3 && B.dp_svig) {
+    if (final && algo >= 3 && B.dp_svig) {
         const int nb = (n_chains + kFastWarps - 1) / kFastWarps;
         if (algo == 4) k_dp_dq<4><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);
         else k_dp_dq<8><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);
