@@ -140,6 +140,28 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def effective_cores():
+    """host cores this process may actually use: min(os.cpu_count, affinity mask, cgroup CPU quota)"""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(round(int(quota) / int(period)))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, int(round(q / p))))
+        except Exception:
+            pass
+    return n
+
+
 _REF_GF = None
 
 
@@ -159,7 +181,7 @@ def cpu_reference_runners():
     """[(label, kind, fn(list_of_bytes) -> total genes, close)] -- the reference's own CPU implementation with every
     host core: its documented thread-pool recipe (docs/guide/parallel.rst:24-41, cli.py:286-300) and the process
     pool its CLI also offers (cli.py:292-293).  Falls back to the C oracle port when oracle/_ref is absent."""
-    cores = os.cpu_count() or 1
+    cores = effective_cores()  # cgroup quota aware (os.cpu_count() reports the whole host)
     from multiprocessing.pool import ThreadPool
     import multiprocessing as mp
     ref_dir = os.path.join(ROOT, "oracle", "_ref")
@@ -249,8 +271,8 @@ def main():
         if rank != 0:
             return
         flat, offsets = make_contigs(0, args.contigs if args.contigs < CONTIGS_PER_GPU else 2048)
-        cores = os.cpu_count() or 1
-        cb = time_cpu(flat, offsets, args.steps, min(args.warmup, 1), args.cpu_contigs or 16 * cores)
+        cores = effective_cores()
+        cb = time_cpu(flat, offsets, args.steps, min(args.warmup, 1), args.cpu_contigs or 32 * cores)
         line = {"impl": "reference", "metric": "Mbp/s find_genes (meta mode)", "value": cb["value"], "unit": "Mbp/s",
                 "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["s_per_step"] * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -362,8 +384,8 @@ def main():
             "clocks": clocks,
         }
         if not args.no_cpu and world == 1:
-            cores = os.cpu_count() or 1
-            line["cpu_baseline"] = {k: v for k, v in time_cpu(flat, offsets, 1, 1, args.cpu_contigs or 16 * cores).items()
+            cores = effective_cores()
+            line["cpu_baseline"] = {k: v for k, v in time_cpu(flat, offsets, 1, 1, args.cpu_contigs or 32 * cores).items()
                                     if k in ("value", "unit", "cores", "kind", "sample")}
         else:
             line["cpu_baseline"] = None

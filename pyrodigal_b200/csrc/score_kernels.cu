@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(128) k_coding(DevBatch B, const DevModel *__re
 // --------------------------------------------------------------------------------------------------
 constexpr int kOrfWarps = 8;
 
-__global__ void __launch_bounds__(32 * kOrfWarps) k_coding_orf(DevBatch B, const DevModel *__restrict__ models, int n_ext,
+__global__ void __launch_bounds__(32 * kOrfWarps, 8) k_coding_orf(DevBatch B, const DevModel *__restrict__ models, int n_ext,
                                                                 int total_nodes) {
     __shared__ int s_first;
     const int lane = threadIdx.x & 31;
@@ -445,13 +445,19 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
     bool edge = (c & edge_mask_now) != 0;
     const int start = rev ? slen - 1 - ndx : ndx;
     const double st_wt = M.st_wt;
+    // issue every independent load up front: the kernel is latency bound
+    const uint32_t pre_bits = B.sdbits[C.node_off + i];
+    const uint64_t pre_U = B.umot[C.node_off + i];
+    const uint64_t pre_pc = B.upc[C.node_off + i];
+    const double pre_cscore = B.cscore[g];
+    const int pre_cc = rev ? cod[stop_val - 2] : cod[stop_val];
 
     int rbs0 = 0, rbs1 = 0;
     MotifOut mot = {};
     if (!edge) {
         if (M.uses_sd) {
             // table-driven Shine-Dalgarno search (lib.pyx:2241-2277 + 791-979)
-            const uint32_t bits = B.sdbits[C.node_off + i];
+            const uint32_t bits = pre_bits;
             const uint32_t A = bits & 0xffffu, G = bits >> 16;
             const int omin = rev ? 0 : max(0, 20 - start);  // forward skips negative offsets only
             for (int off = omin; off < 15; off++) {
@@ -463,7 +469,7 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
         } else {
             // best upstream motif, stage 2 (lib.pyx:1557-1616); spacer class of the p-th window of a length is
             // fixed: j <= start-16-l (p <= 2) -> 3, p <= 4 -> 2, j >= start-7-l (p >= 11) -> 1, else 0
-            const uint64_t U = B.umot[C.node_off + i];
+            const uint64_t U = pre_U;
             int max_spacer = 0, max_spacendx = 0, max_len = 0, max_ndx = 0;
             double max_sc = -100.0;
             const double *__restrict__ mw = M.mot_wt;
@@ -498,11 +504,11 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
         // does the ORF run off the edge?  (is the "stop" a real stop codon)
         int code;
         bool has_n;
-        if (!rev) { int cc = cod[stop_val]; has_n = cc & 64; code = cc & 63; }
-        else { int cc = cod[stop_val - 2]; has_n = cc & 64; code = rev_code(cc & 63); }
+        has_n = pre_cc & 64;
+        code = rev ? rev_code(pre_cc & 63) : (pre_cc & 63);
         if (has_n || !((M.stopmask >> code) & 1)) edge_gene++;
     }
-    double cscore = B.cscore[g], tscore, uscore, rscore;
+    double cscore = pre_cscore, tscore, uscore, rscore;
     if (edge) {
         tscore = PGPU_EDGE_BONUS * st_wt / edge_gene;
         uscore = 0.0;
@@ -521,7 +527,7 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
         uscore = 0.0;
         {
             const int ncomp = min(2, start) + max(0, min(30, start - 14));
-            uint64_t pc = B.upc[C.node_off + i];
+            uint64_t pc = pre_pc;
             int k = 0;
             for (; k + 4 <= ncomp; k += 4, pc >>= 8) {  // 4 independent loads, adds in the reference's order
                 const double w0 = M.uc[k][pc & 3], w1 = M.uc[k + 1][(pc >> 2) & 3], w2 = M.uc[k + 2][(pc >> 4) & 3],
@@ -634,7 +640,7 @@ __device__ __forceinline__ double operon_value(int cz, int z, int s, const uint8
     return (cz & CLS_REV) ? base + igm_same(b, a, M) : base + igm_same(a, b, M);
 }
 
-__global__ void __launch_bounds__(128) k_overlap(DevBatch B, const DevModel *__restrict__ models, int n_chains,
+__global__ void __launch_bounds__(128, 12) k_overlap(DevBatch B, const DevModel *__restrict__ models, int n_chains,
                                                   int64_t total, RunOpts o, int flag) {
     __shared__ int s_first;
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
