@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(128) k_extract(DevBatch B, int n_ext, RunOpts 
 //   stop lane k: saw = any Q bit strictly between the nearest earlier stop and k (or carried in)
 // so 32 codons cost a few dozen instructions instead of 32 dependent iterations.
 template <bool FILL>
-__global__ void __launch_bounds__(128, 16) k_extract_w(DevBatch B, int n_ext, RunOpts o) {
+__global__ void __launch_bounds__(128) k_extract_w(DevBatch B, int n_ext, RunOpts o) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= n_ext * 6) return;
     const int e = w / 6, sf = w % 6, rev = sf / 3, f = sf % 3;
