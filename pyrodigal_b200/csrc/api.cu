@@ -94,7 +94,9 @@ struct pgpu_ctx {
     size_t ws_limit = 0;
     cudaEvent_t ev[16];
     int64_t launches = 0;
-    int dp_algo = 3;           // 3: k_dp_dq (default), 1/2: k_dp_fast, 0: all-pairs k_dp (PGPU_DP_ALGO=n)
+    bool dp_verify = false;    // PGPU_DP_VERIFY=1: run k_dp_dq after k_dp_ml and fail on any difference (self-check)
+    int dp_algo = 5;           // 5: k_dp_ml for multi-model batches, k_dp_dq otherwise (default); 6: k_dp_ml always;
+                               // 3/4: k_dp_dq, 1/2: k_dp_fast, 0: all-pairs k_dp (PGPU_DP_ALGO=n)
     std::shared_ptr<struct PinnedPool> pinned;  // shared with the results it backs (they may outlive the context)
 };
 
@@ -636,8 +638,11 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     tr("issued fill/prep");
     // ---- per-chain scoring ---------------------------------------------------------------------------
     B.chains = pool.upload(chains);
+    std::vector<int32_t> h_eoff;  // chains of an extraction: [h_eoff[e], h_eoff[e+1]) in B.ext_chains
     {
-        std::vector<int32_t> eoff(n_ext + 1, 0), elist(n_chains);
+        std::vector<int32_t> &eoff = h_eoff;
+        eoff.assign(n_ext + 1, 0);
+        std::vector<int32_t> elist(n_chains);
         for (const auto &K : chains) eoff[K.ext + 1]++;
         for (int e = 0; e < n_ext; e++) eoff[e + 1] += eoff[e];
         std::vector<int32_t> fillp(eoff.begin(), eoff.end() - 1);
@@ -658,9 +663,14 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     B.ov_mark = pool.alloc<int8_t>(total_cn + 16);
     B.chain_ipath = pool.alloc<int32_t>(n_chains);
     B.chain_score = pool.alloc<double>(n_chains);
+    const bool dp_ml = ctx->dp_algo >= 6 || (ctx->dp_algo == 5 && n_chains > n_ext);
     if (ctx->dp_algo >= 3) {
         B.dp_svig = pool.alloc<double>(total_cn);
         B.dp_tbig = pool.alloc<int32_t>(total_cn);
+        if (dp_ml) {
+            B.dp_fmv = pool.alloc<double>(total_cn);
+            B.dp_fmj = pool.alloc<int32_t>(total_cn);
+        }
     } else if (ctx->dp_algo >= 1) {
         B.dp_sv = pool.alloc<double>(total_cn);
         B.dp_tbn = pool.alloc<int32_t>(total_cn);
@@ -721,7 +731,41 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     if (pool.failed) return PGPU_ENOMEM;
     tr("uploaded dp tables");
     tev("dp uploads");
-    launch_dp(B, ctx->d_models, d_order, n_chains, 1, ctx->dp_algo, st);
+    if (dp_ml) {
+        // one warp per extraction (contig x translation table) and <= 32 of its chains, longest first
+        std::vector<int4> groups;
+        for (int e = 0; e < n_ext; e++)
+            for (int c = h_eoff[e]; c < h_eoff[e + 1]; c += 32) groups.push_back(make_int4(c, std::min(32, h_eoff[e + 1] - c), e, exts[e].nn));
+        std::stable_sort(groups.begin(), groups.end(), [](const int4 &a, const int4 &b) { return a.w > b.w; });
+        std::vector<int64_t> goff(groups.size() + 1, 0);
+        for (size_t g = 0; g < groups.size(); g++) goff[g + 1] = goff[g] + (int64_t)groups[g].w * groups[g].y;
+        int4 *d_groups = pool.upload(groups);
+        int64_t *d_goff = pool.upload(goff);
+        if (pool.failed) return PGPU_ENOMEM;
+        launch_dp_ml(B, ctx->d_models, d_groups, d_goff, (int)groups.size(), n_chains, st);
+        ctx->launches++;
+        if (ctx->dp_verify && total_cn > 0) {
+            // self-check: the per-chain kernel must reproduce every score / traceback / overlap frame
+            DevBatch V = B;
+            V.score = pool.alloc<double>(total_cn);
+            V.traceb = pool.alloc<int32_t>(total_cn);
+            V.ov_mark = pool.alloc<int8_t>(total_cn + 16);
+            unsigned long long *d_bad = pool.alloc<unsigned long long>(1, true);
+            if (pool.failed) return PGPU_ENOMEM;
+            launch_dp(V, ctx->d_models, d_order, n_chains, 1, 3, st);
+            launch_dp_compare(B.score, V.score, B.traceb, V.traceb, B.ov_mark, V.ov_mark, total_cn, d_bad, st);
+            unsigned long long bad = 0;
+            CK(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (bad) {
+                char msg[96];
+                snprintf(msg, sizeof(msg), "PGPU_DP_VERIFY: %llu of %lld chain-nodes differ", bad, (long long)total_cn);
+                return fail(ctx, PGPU_ESTATE, msg);
+            }
+        }
+    } else {
+        launch_dp(B, ctx->d_models, d_order, n_chains, 1, ctx->dp_algo >= 5 ? 3 : ctx->dp_algo, st);
+    }
     tev("k_dp");
     ctx->launches++;
     int e_dp = mark();
@@ -953,6 +997,7 @@ int pgpu_create(int device, pgpu_ctx **out) {
     }
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     if (const char *a = getenv("PGPU_DP_ALGO")) ctx->dp_algo = atoi(a);
+    if (const char *a = getenv("PGPU_DP_VERIFY")) ctx->dp_verify = atoi(a) != 0;
     // keep freed blocks cached in the stream-ordered pool: sub-batches reuse them without going to the driver
     cudaMemPool_t mp;
     if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {

@@ -152,6 +152,8 @@ struct DevBatch {
     int32_t *dp_bj;       // node index of that maximum
     double *dp_svig;      // merged-stream order: score of a finalized +STOP / -start, -DBL_MAX if no traceback
     int32_t *dp_tbig;     // merged-stream order: traceback node of a +STOP
+    double *dp_fmv;       // k_dp_ml: suffix maxima of the far window (value), interleaved [entry][lane]
+    int32_t *dp_fmj;      // k_dp_ml: ... and their nodes
     // per chain results
     int32_t *chain_ipath;
     double *chain_score;

@@ -222,6 +222,47 @@ def test_find_genes_options_vs_oracle(ctx, capi, closed, mask):
             cmp_nodes(res.nodes(k), nodes, f"contig{k}")
 
 
+@pytest.mark.parametrize("algo", [3, 6])
+def test_dp_kernel_variants_single_golden(capi, algo, monkeypatch):
+    """every DP field of the single-mode goldens, through the per-chain deque kernel (3) and through the
+    model-lane kernel forced onto a one-chain group (6)"""
+    monkeypatch.setenv("PGPU_DP_ALGO", str(algo))
+    for name in list(SINGLE["names"]):
+        seq = SINGLE[name + "/seq"]
+        closed, mask = (int(v) for v in SINGLE[name + "/opts"])
+        c = capi.Context(0)
+        c.set_models(SINGLE[name + "/tinf"].tobytes(), 1)
+        res = c.find_genes_batch(np.ascontiguousarray(seq), np.array([0, len(seq)], np.int64),
+                                 capi.make_opts(meta=False, single_model=0, closed=closed, want_nodes=True))
+        cmp_int(res.genes, SINGLE[name + "/genes"], f"{name}.genes")
+        cmp_nodes(res.nodes(0), SINGLE[name + "/nodes"], name, dp=True)
+        c.close()
+
+
+def test_dp_model_lane_kernel_equals_per_chain_kernel(capi, monkeypatch):
+    """PGPU_DP_VERIFY: in one meta batch, every score / traceback / overlap frame of every chain from the
+    model-lane kernel (one warp per contig x table, one lane per model) equals the per-chain kernel's"""
+    monkeypatch.setenv("PGPU_DP_VERIFY", "1")
+    c = capi.Context(0)
+    c.set_models(R.bins_blob(), 50)
+    rng = np.random.default_rng(7)
+    seqs = [b"", R.synth(89, .5, 1), R.synth(150000, .55, 3), R.synth(90000, .33, 4)]
+    for k in range(80):
+        seqs.append(R.synth(int(rng.integers(100, 40000)), float(rng.uniform(.26, .74)), 3000 + k,
+                            n_frac=0.001 if k % 9 == 0 else 0.0))
+    res = run_meta(c, capi, seqs)
+    assert res.stats["n_chains"] > 5 * len(seqs)
+    # same genes as the default context's path
+    monkeypatch.delenv("PGPU_DP_VERIFY")
+    monkeypatch.setenv("PGPU_DP_ALGO", "3")
+    c3 = capi.Context(0)
+    c3.set_models(R.bins_blob(), 50)
+    res3 = run_meta(c3, capi, seqs)
+    cmp_int(res.genes, res3.genes, "ml-vs-dq.genes")
+    assert res.gene_nodes.tobytes() == res3.gene_nodes.tobytes()
+    c.close(); c3.close()
+
+
 def test_resident_batch_matches_host_batch(ctx, capi):
     seqs = [R.synth(5000 + 700 * k, .4 + 0.02 * k, 700 + k) for k in range(12)]
     arrs = [np.frombuffer(s, np.uint8) for s in seqs]
