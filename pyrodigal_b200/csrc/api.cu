@@ -94,6 +94,7 @@ struct pgpu_ctx {
     size_t ws_limit = 0;
     cudaEvent_t ev[16];
     int64_t launches = 0;
+    int dp_ml_minb = 6;        // k_dp_ml register budget: min CTAs/SM 5, 6 or 8 (PGPU_DP_ML_MINB)
     bool dp_verify = false;    // PGPU_DP_VERIFY=1: run k_dp_dq after k_dp_ml and fail on any difference (self-check)
     int dp_algo = 5;           // 5: k_dp_ml for multi-model batches, k_dp_dq otherwise (default); 6: k_dp_ml always;
                                // 3/4: k_dp_dq, 1/2: k_dp_fast, 0: all-pairs k_dp (PGPU_DP_ALGO=n)
@@ -605,6 +606,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     B.ig_node = pool.alloc<int32_t>(total_nodes + 1);
     B.ig_ndx = pool.alloc<int32_t>(total_nodes + 1);
     B.dqx = pool.alloc<int4>(total_nodes);
+    B.feq = pool.alloc<int32_t>(total_nodes);
     unsigned long long *d_ext_pairs = pool.alloc<unsigned long long>(n_ext, true);
     if (pool.failed) return PGPU_ENOMEM;
     tev("sync2+alloc");
@@ -742,7 +744,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         int4 *d_groups = pool.upload(groups);
         int64_t *d_goff = pool.upload(goff);
         if (pool.failed) return PGPU_ENOMEM;
-        launch_dp_ml(B, ctx->d_models, d_groups, d_goff, (int)groups.size(), n_chains, st);
+        launch_dp_ml(B, ctx->d_models, d_groups, d_goff, (int)groups.size(), n_chains, ctx->dp_ml_minb, st);
         ctx->launches++;
         if (ctx->dp_verify && total_cn > 0) {
             // self-check: the per-chain kernel must reproduce every score / traceback / overlap frame
@@ -750,16 +752,33 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
             V.score = pool.alloc<double>(total_cn);
             V.traceb = pool.alloc<int32_t>(total_cn);
             V.ov_mark = pool.alloc<int8_t>(total_cn + 16);
-            unsigned long long *d_bad = pool.alloc<unsigned long long>(1, true);
+            unsigned long long *d_bad = pool.alloc<unsigned long long>(2);
             if (pool.failed) return PGPU_ENOMEM;
+            const unsigned long long init[2] = {0ULL, ~0ULL};
+            CK(cudaMemcpyAsync(d_bad, init, sizeof(init), cudaMemcpyHostToDevice, st));
             launch_dp(V, ctx->d_models, d_order, n_chains, 1, 3, st);
             launch_dp_compare(B.score, V.score, B.traceb, V.traceb, B.ov_mark, V.ov_mark, total_cn, d_bad, st);
-            unsigned long long bad = 0;
-            CK(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, st));
+            unsigned long long bad[2] = {0, 0};
+            CK(cudaMemcpyAsync(bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            if (bad) {
-                char msg[96];
-                snprintf(msg, sizeof(msg), "PGPU_DP_VERIFY: %llu of %lld chain-nodes differ", bad, (long long)total_cn);
+            if (bad[0]) {
+                // describe the first differing chain-node
+                const int64_t g = (int64_t)bad[1];
+                int k = 0;
+                while (k + 1 < n_chains && chains[k + 1].coff <= g) k++;
+                const int node = (int)(g - chains[k].coff);
+                double sc[2]; int32_t tb[2]; int8_t ov[2]; int32_t nx = 0, svv = 0; uint8_t cl = 0;
+                cudaMemcpy(&sc[0], B.score + g, 8, cudaMemcpyDeviceToHost); cudaMemcpy(&sc[1], V.score + g, 8, cudaMemcpyDeviceToHost);
+                cudaMemcpy(&tb[0], B.traceb + g, 4, cudaMemcpyDeviceToHost); cudaMemcpy(&tb[1], V.traceb + g, 4, cudaMemcpyDeviceToHost);
+                cudaMemcpy(&ov[0], B.ov_mark + g, 1, cudaMemcpyDeviceToHost); cudaMemcpy(&ov[1], V.ov_mark + g, 1, cudaMemcpyDeviceToHost);
+                cudaMemcpy(&nx, B.ndx + chains[k].node_off + node, 4, cudaMemcpyDeviceToHost);
+                cudaMemcpy(&svv, B.stop_val + chains[k].node_off + node, 4, cudaMemcpyDeviceToHost);
+                cudaMemcpy(&cl, B.cls + chains[k].node_off + node, 1, cudaMemcpyDeviceToHost);
+                char msg[320];
+                snprintf(msg, sizeof(msg), "PGPU_DP_VERIFY: %llu of %lld chain-nodes differ; first: chain %d (contig %d model %d nn %d) "
+                         "node %d kind %d ndx %d sv %d: score %.17g/%.17g traceb %d/%d ov %d/%d", bad[0], (long long)total_cn, k,
+                         chains[k].contig, chains[k].model, chains[k].nn, node, cls_kind(cl), nx, svv, sc[0], sc[1], tb[0], tb[1],
+                         (int)ov[0], (int)ov[1]);
                 return fail(ctx, PGPU_ESTATE, msg);
             }
         }
@@ -998,6 +1017,7 @@ int pgpu_create(int device, pgpu_ctx **out) {
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     if (const char *a = getenv("PGPU_DP_ALGO")) ctx->dp_algo = atoi(a);
     if (const char *a = getenv("PGPU_DP_VERIFY")) ctx->dp_verify = atoi(a) != 0;
+    if (const char *a = getenv("PGPU_DP_ML_MINB")) ctx->dp_ml_minb = atoi(a);
     // keep freed blocks cached in the stream-ordered pool: sub-batches reuse them without going to the driver
     cudaMemPool_t mp;
     if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {

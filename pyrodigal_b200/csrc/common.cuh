@@ -127,6 +127,7 @@ struct DevBatch {
     int32_t *clist;       // class-sorted node indices (local), segments per class
     int32_t *cbase;       // [4 * ext]: start of each class segment in clist (relative to node_off)
     int32_t *cndx;        // ndx in class order: cndx[p] = ndx[clist[p]]
+    int32_t *feq;         // class order, +STOP segment only: position in the merged +STOP / -start stream
     int4 *dpx;            // per node: pre-resolved DP candidates / ranges (see k_dp_index)
     int32_t *ig_node;     // merged stream of +STOP and -start nodes ("intergenic sources") in node order:
     int32_t *ig_ndx;      //   node index (bit 31 set for +STOP) and position

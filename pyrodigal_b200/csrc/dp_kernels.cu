@@ -967,27 +967,34 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
 //     positions are geometric, hence uniform: the rebuild loop does not diverge.
 //   * DP-private arrays (source values, traceback nodes, suffix maxima) are interleaved [entry][lane], so a
 //     warp access touches L consecutive elements; the public score / traceb / ov_mark arrays stay chain-major.
-//   * the cscore + sscore sums of the next 32 targets are staged through shared memory (coalesced per chain).
+//   * rules that only admit +STOPs (operon, 3' overlap, triple overlap) walk the +STOP class list (node, ndx,
+//     merged position) instead of the merged stream; their ranges are geometric and come from k_dp_index.
 // Candidate order does not matter: the arg-max is "larger value, then larger node index", as everywhere else.
 // --------------------------------------------------------------------------------------------------
 constexpr int kMlWarps = 4;
-constexpr int kMlPitch = 33;  // doubles per staged target: conflict-free for lane==target and lane==model
+constexpr int kMlBatch = 2;  // near-source loads issued together (hides the L2 round trip of the source values)
 
 struct MlK {  // geometric constants of a target, staged 32 targets at a time (model independent)
     int32_t ndx, sv, cls, leave;
-    int32_t x, y, z, w;  // dqx
-    int32_t wmin, pad;
+    // +STOP : a = first +STOP (class position) inside the ORF and the window            [operon]
+    // -start: a = node of its own -STOP (or -1), [b, c) = +STOP class positions of the 3' overlap range
+    // -STOP : a, b, c = per frame the previous -STOP whose ORF spans this stop (or -1)   [operon]
+    int32_t a, b, c, pad;
 };
 
-__global__ void __launch_bounds__(32 * kMlWarps, 4) k_dp_ml(DevBatch B, const DevModel *__restrict__ models,
-                                                            const int4 *__restrict__ groups,
-                                                            const int64_t *__restrict__ group_off, int n_groups) {
+__device__ double g_ml_no_source = -DBL_MAX;  // what idle lanes read instead of a source value
+
+template <int MINB>
+__global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const DevModel *__restrict__ models,
+                                                               const int4 *__restrict__ groups,
+                                                               const int64_t *__restrict__ group_off, int n_groups) {
     __shared__ MlK s_k[kMlWarps][32];
-    __shared__ double s_cs[kMlWarps][32 * kMlPitch];
+    __shared__ double s_rcv[3][32 * kMlWarps];  // per frame: best +start of the open forward ORF (value, node)
+    __shared__ int32_t s_rcj[3][32 * kMlWarps];
     const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
     const int slot = blockIdx.x * kMlWarps + wslot;
     if (slot >= n_groups) return;
-    const int4 G = groups[slot];  // x: first entry in ext_chains, y: number of chains (<= 32)
+    const int4 G = groups[slot];  // x: first entry in ext_chains, y: number of chains (<= 32), z: extraction
     const int L = G.y;
     const bool act = lane < L;
     const int ll = act ? lane : 0;  // idle lanes shadow lane 0 (loads stay in bounds, stores are suppressed)
@@ -1001,7 +1008,13 @@ __global__ void __launch_bounds__(32 * kMlWarps, 4) k_dp_ml(DevBatch B, const De
     const uint8_t *__restrict__ cls = B.cls + C.node_off;
     const int32_t *__restrict__ ig_node = B.ig_node + C.node_off;
     const int32_t *__restrict__ ig_ndx = B.ig_ndx + C.node_off;
-    const int4 *__restrict__ dqx = B.dqx + C.node_off;
+    const int4 *__restrict__ dpx = B.dpx + C.node_off;
+    const int fe0 = B.cbase[4 * G.z + 1];
+    const int32_t *__restrict__ fe_node = B.clist + C.node_off + fe0;  // +STOPs in class order: node,
+    const int32_t *__restrict__ fe_ndx = B.cndx + C.node_off + fe0;    // ndx,
+    const int32_t *__restrict__ fe_q = B.feq + C.node_off + fe0;       // merged-stream position
+    const double *__restrict__ cscore = B.cscore + C.coff;
+    const double *__restrict__ sscore = B.sscore + C.coff;
     const double *__restrict__ opv = B.opv + 3 * C.coff;
     const int32_t *__restrict__ star_ptr = B.star_ptr + 3 * C.coff;
     double *score = B.score + C.coff;
@@ -1014,41 +1027,49 @@ __global__ void __launch_bounds__(32 * kMlWarps, 4) k_dp_ml(DevBatch B, const De
     double *fmv = B.dp_fmv + goff;
     int32_t *fmj = B.dp_fmj + goff;
     MlK *sk = s_k[wslot];
-    double *scs = s_cs[wslot];
     const double ig_neg = M.ig_neg;
     const double *__restrict__ igt = M.igt;
-    // source value of a merged-stream entry for this lane; idle lanes never see a source
-    auto SV = [&](int q) -> double { return act ? svig[(int64_t)q * L] : kNeg; };
-    const unsigned coff_lo = (unsigned)C.coff, coff_hi = (unsigned)((unsigned long long)C.coff >> 32);
+    // source value of a merged-stream entry for this lane; idle lanes read "no source" (stride 0)
+    const double *svr = act ? svig : &g_ml_no_source;
+    const int svs = act ? L : 0;
+    auto SV = [&](int q) -> double { return svr[q * svs]; };
 
     // merged-stream cursors (uniform): cur = finalized entries, lo = first entry inside [i-1000, i), far = first
-    // entry that is NOT more than 180 bp behind the target, split = boundary between front and back stack
-    int cur = 0, lo = 0, far = 0, split = 0;
+    // entry that is NOT more than 180 bp behind the target, split = boundary between front and back stack;
+    // *_fe: the same positions counted in +STOPs only
+    int cur = 0, lo = 0, far = 0, split = 0, cur_fe = 0, lo_fe = 0, far_fe = 0;
     double bk_v = kNeg;  // back stack: running maximum over the entries [split, far)
     int bk_j = -1;
-    double rc_v0 = kNeg, rc_v1 = kNeg, rc_v2 = kNeg;
-    int rc_j0 = -1, rc_j1 = -1, rc_j2 = -1;
+#pragma unroll
+    for (int f = 0; f < 3; f++) { s_rcv[f][threadIdx.x] = kNeg; s_rcj[f][threadIdx.x] = -1; }
 
     for (int i0 = 0; i0 < nn; i0 += 32) {
       __syncwarp();
-      {
+      if (i0 + lane < nn) {
           const int i = i0 + lane;
-          const bool in = i < nn;
-          if (in) {
-              MlK k;
-              k.ndx = ndx[i]; k.sv = sv[i]; k.cls = cls[i];
-              k.leave = i > 2 * kMaxNodeDist ? cls_kind(cls[i - 2 * kMaxNodeDist - 1]) : -1;
-              const int4 dx = dqx[i];
-              k.x = dx.x; k.y = dx.y; k.z = dx.z; k.w = dx.w;
-              k.wmin = B.win_min[C.node_off + i];
-              k.pad = 0;
-              sk[lane] = k;
+          MlK k;
+          k.ndx = ndx[i]; k.sv = sv[i]; k.cls = cls[i];
+          k.leave = i > 2 * kMaxNodeDist ? cls_kind(cls[i - 2 * kMaxNodeDist - 1]) : -1;
+          const int kind = cls_kind(k.cls);
+          const int4 dx = dpx[i];
+          k.a = k.b = k.c = -1; k.pad = 0;
+          if (kind == K_FE || kind == K_RS) {
+              const int wmin = B.win_min[C.node_off + i];                       // first node of the window
+              const int wlo = B.crank[4 * (int64_t)(C.node_off + wmin) + 1];    // +STOPs before it
+              if (kind == K_FE) { k.a = max(dx.x, wlo); }
+              else { k.a = (dx.x >= wmin && dx.x >= 0 && dx.x < i) ? dx.x : -1; k.b = max(dx.y, wlo); k.c = dx.z; }
+          } else if (kind == K_RE) {
+              const int w0 = i - 2 * kMaxNodeDist;
+              k.a = dx.x >= max(w0, 0) ? dx.x : -1; k.b = dx.y >= max(w0, 0) ? dx.y : -1; k.c = dx.z >= max(w0, 0) ? dx.z : -1;
           }
-          // cscore + sscore of the 32 targets, for every chain of the group (lane == target here)
-          for (int c = 0; c < L; c++) {
-              const unsigned lo32 = __shfl_sync(0xffffffffu, coff_lo, c), hi32 = __shfl_sync(0xffffffffu, coff_hi, c);
-              const int64_t co = (int64_t)(((unsigned long long)hi32 << 32) | lo32) + i;
-              scs[lane * kMlPitch + c] = in ? B.cscore[co] + B.sscore[co] : 0.0;
+          sk[lane] = k;
+      }
+      if (act && i0 + 32 < nn) {  // the chain-major score lines of the next block
+          const double *pc = cscore + i0 + 32, *ps = sscore + i0 + 32;
+#pragma unroll
+          for (int t = 0; t < 3; t++) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + min(16 * t, 31)));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + min(16 * t, 31)));
           }
       }
       __syncwarp();
@@ -1057,106 +1078,126 @@ __global__ void __launch_bounds__(32 * kMlWarps, 4) k_dp_ml(DevBatch B, const De
         const MlK &K = sk[i - i0];
         const int ci = K.cls, kind = cls_kind(ci), f2 = cls_frame(ci), ndx_i = K.ndx, sv_i = K.sv;
         lo += (K.leave == K_FE) | (K.leave == K_RS);
-        const double cs_i = scs[(i - i0) * kMlPitch + ll];
+        lo_fe += K.leave == K_FE;
+        // cscore + sscore of a start target (chain-major, sequential per lane: L1 lines are reused 16 times)
+        double cs_i = 0.0;
+        if (kind == K_FS || kind == K_RS) cs_i = cscore[i] + sscore[i];
         double wv = kNeg;
-        int wj = -1, wfr = -1;
+        int wkey = -1;  // (node << 2) | (overlap frame + 1)
         // larger value, then larger node; the same node seen twice (far maximum + overlap re-evaluation) keeps the
         // overlap frame, as the reference evaluates it only once with it
         auto cand = [&](double v, int j, int fr) {
-            if (v > wv || (v == wv && (j > wj || (j == wj && fr > wfr)))) { wv = v; wj = j; wfr = fr; }
+            const int key = (j << 2) | (fr + 1);
+            if (v > wv || (v == wv && key > wkey)) { wv = v; wkey = key; }
         };
 
         if (kind == K_RS) {
             // own -STOP (gene, _connection.h:228-237)
-            if (K.x >= K.wmin && K.x >= 0 && K.x < i) cand(score[K.x] + cs_i, K.x, -1);
+            if (K.a >= 0) cand(score[K.a] + cs_i, K.a, -1);
             // +STOPs overlapping the 3' end (_connection.h:239-256)
             const double cs_diff = cs_i + ig_neg;
-            for (int q = max(K.y, K.w); q < min(K.z, cur); q++) {
-                const int nd = ig_node[q];
-                if (nd >= 0) continue;
-                const int nj = ig_ndx[q];
+            const int re = min(K.c, cur_fe);
+#pragma unroll 1
+            for (int r = K.b; r < re; r++) {
+                const int nj = fe_ndx[r], q = fe_q[r], j = fe_node[r];
+                const double s = SV(q);
                 if (sv_i - 2 >= nj + 2) continue;
                 const int ovlp = (nj + 2) - (sv_i - 2) + 1;
                 if (ovlp >= kMaxOppOvlp) continue;
                 if ((nj - sv_i) >= (ndx_i - nj + 3)) continue;
-                const double s = SV(q);
                 if (s == kNeg) continue;
-                if ((nj - sv_i) >= (sv_i - 3 - ndx[tbig[(int64_t)q * L]])) continue;
-                cand(s + cs_diff, nd & 0x7fffffff, -1);
+                if ((nj - sv_i) >= (sv_i - 3 - ndx[tbig[q * L]])) continue;
+                cand(s + cs_diff, j, -1);
             }
         } else if (kind == K_FE) {
             {   // best +start of this ORF (gene): running maximum of fl(score + cscore + sscore)
-                const double rv = f2 == 0 ? rc_v0 : (f2 == 1 ? rc_v1 : rc_v2);
-                const int rj = f2 == 0 ? rc_j0 : (f2 == 1 ? rc_j1 : rc_j2);
-                if (rj >= 0) cand(rv, rj, -1);
+                const int rj = s_rcj[f2][threadIdx.x];
+                if (rj >= 0) cand(s_rcv[f2][threadIdx.x], rj, -1);
             }
             // +STOPs inside the ORF (operon, _connection.h:178-191)
-            for (int q = max(K.x, K.w); q < cur; q++) {
-                const int nd = ig_node[q];
-                if (nd >= 0) continue;
-                const int j = nd & 0x7fffffff;
+#pragma unroll 1
+            for (int r = K.a; r < cur_fe; r++) {
+                const int q = fe_q[r], j = fe_node[r];
                 const double s = SV(q);
-                if (s == kNeg) continue;
-                if (star_ptr[3 * (int64_t)j + f2] == -1) continue;
-                cand(s + opv[3 * (int64_t)j + f2], j, -1);
+                const int spj = star_ptr[3 * (int64_t)j + f2];
+                const double opj = opv[3 * (int64_t)j + f2];
+                if (s != kNeg && spj != -1) cand(s + opj, j, -1);
             }
         } else {  // K_FS, K_RE: intergenic sources
-            // -STOP only: the recorded overlapping starts of this model (lane)
+            // -STOP only: the recorded overlapping -starts of this model (lane): node, its -STOP, and the class
+            // range of the +STOPs that can trigger the triple overlap with it
             int sp0 = -1, sp1 = -1, sp2 = -1, n3n0 = 0, n3n1 = 0, n3n2 = 0, n3s0 = 0, n3s1 = 0, n3s2 = 0;
+            int sa0 = 0, sa1 = 0, sa2 = 0, sb0 = 0, sb1 = 0, sb2 = 0;
             double op0 = 0.0, op1 = 0.0, op2 = 0.0;
             if (kind == K_RE) {
                 sp0 = star_ptr[3 * (int64_t)i]; sp1 = star_ptr[3 * (int64_t)i + 1]; sp2 = star_ptr[3 * (int64_t)i + 2];
-                if (sp0 != -1) { n3n0 = ndx[sp0]; n3s0 = sv[sp0]; op0 = opv[3 * (int64_t)i]; }
-                if (sp1 != -1) { n3n1 = ndx[sp1]; n3s1 = sv[sp1]; op1 = opv[3 * (int64_t)i + 1]; }
-                if (sp2 != -1) { n3n2 = ndx[sp2]; n3s2 = sv[sp2]; op2 = opv[3 * (int64_t)i + 2]; }
+                if (sp0 != -1) { n3n0 = ndx[sp0]; n3s0 = sv[sp0]; op0 = opv[3 * (int64_t)i]; const int4 d = dpx[sp0]; sa0 = d.y; sb0 = d.z; }
+                if (sp1 != -1) { n3n1 = ndx[sp1]; n3s1 = sv[sp1]; op1 = opv[3 * (int64_t)i + 1]; const int4 d = dpx[sp1]; sa1 = d.y; sb1 = d.z; }
+                if (sp2 != -1) { n3n2 = ndx[sp2]; n3s2 = sv[sp2]; op2 = opv[3 * (int64_t)i + 2]; const int4 d = dpx[sp2]; sa2 = d.y; sb2 = d.z; }
             }
             // ---- entries that fall more than 180 bp behind move onto the back stack ----
             const int thr = ndx_i - 3 * kOperDist;
+#pragma unroll 1
             while (far < cur && ig_ndx[far] < thr) {
+                const int nd = ig_node[far];
                 if (far >= lo) {
                     const double s = SV(far);
                     if (s != kNeg) {
                         const double x = s + ig_neg;
-                        if (x >= bk_v) { bk_v = x; bk_j = ig_node[far] & 0x7fffffff; }  // later entry wins a tie
+                        if (x >= bk_v) { bk_v = x; bk_j = nd & 0x7fffffff; }  // later entry wins a tie
                     }
                 }
+                far_fe += nd < 0;
                 far++;
             }
             // ---- the window start passed the split: flip the back stack into suffix maxima ----
             if (lo > split) {
                 double fv = kNeg;
                 int fj = -1;
+#pragma unroll 2
                 for (int q = far - 1; q >= lo; q--) {
                     const double s = SV(q);
                     if (s != kNeg) {
                         const double x = s + ig_neg;
                         if (x > fv) { fv = x; fj = ig_node[q] & 0x7fffffff; }  // earlier entry loses a tie
                     }
-                    if (act) { fmv[(int64_t)q * L] = fv; fmj[(int64_t)q * L] = fj; }
+                    if (act) { fmv[q * L] = fv; fmj[q * L] = fj; }
                 }
                 split = far;
                 bk_v = kNeg; bk_j = -1;
             }
             if (lo < split && act) {
-                const int fj = fmj[(int64_t)lo * L];
-                if (fj >= 0) cand(fmv[(int64_t)lo * L], fj, -1);
+                const int fj = fmj[lo * L];
+                const double fv = fmv[lo * L];
+                if (fj >= 0) cand(fv, fj, -1);
             }
             if (bk_j >= 0) cand(bk_v, bk_j, -1);
             const int flo = max(far, lo);
             if (kind == K_FS) {
                 // near sources (_connection.h:116-129): +STOP distance-dependent term, -start strand switch
-                for (int q = flo; q < cur; q++) {
-                    const int nd = ig_node[q], nj = ig_ndx[q];
-                    if (nd < 0 ? (nj + 2 >= ndx_i) : (nj >= ndx_i)) continue;
-                    const double s = SV(q);
-                    if (s == kNeg) continue;
-                    const int dist = ndx_i - nj;
-                    const double term = (nd >= 0 || dist > 3 * kOperDist) ? ig_neg : (dist <= kOperDist ? igt[dist] : 0.0);
-                    cand(s + term, nd & 0x7fffffff, -1);
+#pragma unroll 1
+                for (int q0 = flo; q0 < cur; q0 += kMlBatch) {
+                    double s[kMlBatch];
+                    int nd[kMlBatch], nj[kMlBatch];
+#pragma unroll
+                    for (int u = 0; u < kMlBatch; u++) {
+                        const int q = min(q0 + u, cur - 1);  // a clamped slot repeats the last entry: harmless
+                        nd[u] = ig_node[q];
+                        nj[u] = ig_ndx[q];
+                        s[u] = SV(q);
+                    }
+#pragma unroll
+                    for (int u = 0; u < kMlBatch; u++) {
+                        if (s[u] == kNeg) continue;
+                        if (nd[u] < 0 ? (nj[u] + 2 >= ndx_i) : (nj[u] >= ndx_i)) continue;
+                        const int dist = ndx_i - nj[u];
+                        const double term = (nd[u] >= 0 || dist > 3 * kOperDist) ? ig_neg : (dist <= kOperDist ? igt[dist] : 0.0);
+                        cand(s[u] + term, nd[u] & 0x7fffffff, -1);
+                    }
                 }
             } else {
                 // +STOP with the triple-overlap search (_connection.h:297-334), for one merged-stream position
-                auto eval_fe = [&](int q, double s, int nj, int nd) {
+                auto eval_fe = [&](int q, double s, int nj, int j) {
                     const int left = nj + 2, right = ndx_i - 2;
                     if (left >= right) return;
                     int maxfr = -1, tj = kTbNone;
@@ -1166,83 +1207,83 @@ __global__ void __launch_bounds__(32 * kMlWarps, 4) k_dp_ml(DevBatch B, const De
                         const int ovlp = left - n3s + 3;
                         if (ovlp <= 0 || ovlp >= kMaxOppOvlp) return;
                         if (ovlp >= n3n - left) return;
-                        if (tj == kTbNone) tj = ndx[tbig[(int64_t)q * L]];
+                        if (tj == kTbNone) tj = ndx[tbig[q * L]];
                         if (ovlp >= n3s - tj - 2) return;
                         if (op > maxval) { maxfr = k; maxval = op; }
                     };
                     probe(0, sp0, n3n0, n3s0, op0);
                     probe(1, sp1, n3n1, n3s1, op1);
                     probe(2, sp2, n3n2, n3s2, op2);
-                    cand(s + (maxfr != -1 ? maxval : ig_neg), nd & 0x7fffffff, maxfr);
+                    cand(s + (maxfr != -1 ? maxval : ig_neg), j, maxfr);
                 };
+#pragma unroll 1
                 for (int q = flo; q < cur; q++) {
                     const int nd = ig_node[q], nj = ig_ndx[q];
                     const double s = SV(q);
                     if (s == kNeg) continue;
                     if (nd < 0) {
-                        eval_fe(q, s, nj, nd);
+                        eval_fe(q, s, nj, nd & 0x7fffffff);
                     } else {  // -start (_connection.h:335-341)
                         if (nj >= ndx_i - 2) continue;
                         const int dist = ndx_i - nj;
                         cand(s + (dist > 3 * kOperDist ? ig_neg : (dist <= kOperDist ? igt[dist] : 0.0)), nd, -1);
                     }
                 }
-                // far +STOPs whose position can trigger the triple overlap (200 bp after the stop of a recorded
-                // start): their plain value is covered by the far maximum, the overlap value can only be larger.
-                // The recorded start differs per model, so the position range is per lane; the loop runs over the
-                // union of the lanes' ranges.
-                auto special = [&](int spk, int n3s) {
-                    int a_ = lo, b_ = lo;
-                    if (spk != -1) {  // ndx in [n3s-4, n3s+194]
-                        b_ = flo;
-                        while (a_ < b_) { const int mid = (a_ + b_) >> 1; if (ig_ndx[mid] < n3s - 4) a_ = mid + 1; else b_ = mid; }
-                        const int a = a_;
-                        b_ = flo;
-                        while (a_ < b_) { const int mid = (a_ + b_) >> 1; if (ig_ndx[mid] < n3s + 195) a_ = mid + 1; else b_ = mid; }
-                        b_ = a_; a_ = a;
+                // far +STOPs whose position can trigger the triple overlap (ndx in [n3s-4, n3s+194], n3s = the -STOP
+                // of a recorded start): their plain value is covered by the far maximum, the overlap value can only
+                // be larger.  The recorded start differs per model, so the class range is per lane (the 3' overlap
+                // range of that -start, k_dp_index, widened by the entries with ndx == n3s-4 and clamped to the far
+                // zone); the loop runs over the union of the lanes' ranges.
+                const int ffe = max(far_fe, lo_fe);  // +STOPs below the far / near boundary
+                if (lo_fe < ffe) {
+#pragma unroll 1
+                    for (int k = 0; k < 3; k++) {
+                        const int spk = k == 0 ? sp0 : (k == 1 ? sp1 : sp2), n3s = k == 0 ? n3s0 : (k == 1 ? n3s1 : n3s2);
+                        int sa = k == 0 ? sa0 : (k == 1 ? sa1 : sa2);
+                        const int sb = k == 0 ? sb0 : (k == 1 ? sb1 : sb2);
+                        int a_ = 0, b_ = 0;
+                        if (spk != -1) {
+                            while (sa > lo_fe && fe_ndx[sa - 1] >= n3s - 4) sa--;
+                            a_ = max(sa, lo_fe); b_ = min(sb, ffe);
+                        }
+                        const bool any = a_ < b_;
+                        if (!__any_sync(0xffffffffu, any)) continue;
+                        const int ua = __reduce_min_sync(0xffffffffu, any ? a_ : 0x7fffffff);
+                        const int ub = __reduce_max_sync(0xffffffffu, any ? b_ : -1);
+#pragma unroll 1
+                        for (int r = ua; r < ub; r++) {
+                            if (r < a_ || r >= b_) continue;
+                            const int q = fe_q[r];
+                            const double s = SV(q);
+                            if (s != kNeg) eval_fe(q, s, fe_ndx[r], fe_node[r]);
+                        }
                     }
-                    const bool any = a_ < b_;
-                    const int ua = __reduce_min_sync(0xffffffffu, any ? a_ : 0x7fffffff);
-                    const int ub = __reduce_max_sync(0xffffffffu, any ? b_ : -1);
-                    for (int q = ua; q < ub; q++) {
-                        const int nd = ig_node[q];
-                        if (nd >= 0 || q < a_ || q >= b_) continue;
-                        const double s = SV(q);
-                        if (s != kNeg) eval_fe(q, s, ig_ndx[q], nd);
-                    }
-                };
-                if (lo < flo) {
-                    special(sp0, n3s0);
-                    special(sp1, n3s1);
-                    special(sp2, n3s2);
                 }
                 // -STOPs whose ORF spans this stop: operon (_connection.h:343-356); at most one per frame
-                if (K.x >= 0 && K.x >= i - 2 * kMaxNodeDist && sp0 != -1) cand(score[K.x] + op0, K.x, -1);
-                if (K.y >= 0 && K.y >= i - 2 * kMaxNodeDist && sp1 != -1) cand(score[K.y] + op1, K.y, -1);
-                if (K.z >= 0 && K.z >= i - 2 * kMaxNodeDist && sp2 != -1) cand(score[K.z] + op2, K.z, -1);
+                if (K.a >= 0 && sp0 != -1) cand(score[K.a] + op0, K.a, -1);
+                if (K.b >= 0 && sp1 != -1) cand(score[K.b] + op1, K.b, -1);
+                if (K.c >= 0 && sp2 != -1) cand(score[K.c] + op2, K.c, -1);
             }
         }
 
         double sc_i = 0.0;
         int tb_i = -1, fr_i = -1;
-        if (wj >= 0 && wv >= 0.0) { sc_i = wv; tb_i = wj; fr_i = wfr; }
+        if (wkey >= 0 && wv >= 0.0) { sc_i = wv; tb_i = wkey >> 2; fr_i = (wkey & 3) - 1; }
         if (act) {
             score[i] = sc_i; traceb[i] = tb_i; ov_mark[i] = (int8_t)fr_i;
             if (kind == K_FE || kind == K_RS) {
-                svig[(int64_t)cur * L] = tb_i == -1 ? kNeg : sc_i;  // edge-artifact rule: nothing leads into it
-                tbig[(int64_t)cur * L] = tb_i;
+                svig[cur * L] = tb_i == -1 ? kNeg : sc_i;  // edge-artifact rule: nothing leads into it
+                tbig[cur * L] = tb_i;
             }
         }
         if (kind == K_FE) {
-            cur++;
-            if (f2 == 0) { rc_v0 = kNeg; rc_j0 = -1; } else if (f2 == 1) { rc_v1 = kNeg; rc_j1 = -1; } else { rc_v2 = kNeg; rc_j2 = -1; }
+            cur++; cur_fe++;
+            s_rcv[f2][threadIdx.x] = kNeg; s_rcj[f2][threadIdx.x] = -1;
         } else if (kind == K_RS) {
             cur++;
         } else if (kind == K_FS) {
             const double g = sc_i + cs_i;
-            if (f2 == 0) { if (g >= rc_v0) { rc_v0 = g; rc_j0 = i; } }
-            else if (f2 == 1) { if (g >= rc_v1) { rc_v1 = g; rc_j1 = i; } }
-            else { if (g >= rc_v2) { rc_v2 = g; rc_j2 = i; } }
+            if (g >= s_rcv[f2][threadIdx.x]) { s_rcv[f2][threadIdx.x] = g; s_rcj[f2][threadIdx.x] = i; }
         }
         __syncwarp();  // every lane reads only its own column; the barrier just keeps the warp converged
       }
@@ -1671,9 +1712,12 @@ void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, 
     else k_dp<0><<<n_chains, kDpThreads, 0, st>>>(B, models, order, n_chains);
 }
 void launch_dp_ml(const DevBatch &B, const DevModel *models, const int4 *groups, const int64_t *group_off, int n_groups,
-                  int n_chains, cudaStream_t st) {
+                  int n_chains, int minb, cudaStream_t st) {
     if (n_groups == 0 || n_chains == 0) return;
-    k_dp_ml<<<(n_groups + kMlWarps - 1) / kMlWarps, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, n_groups);
+    const int nb = (n_groups + kMlWarps - 1) / kMlWarps;
+    if (minb == 8) k_dp_ml<8><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, n_groups);
+    else if (minb == 6) k_dp_ml<6><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, n_groups);
+    else k_dp_ml<5><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, n_groups);
     k_chain_best<<<(n_chains * 32 + 127) / 128, 128, 0, st>>>(B, n_chains);
 }
 // PGPU_DP_VERIFY: element-wise comparison of two DP results (score, traceback, overlap frame)
@@ -1682,7 +1726,7 @@ __global__ void k_dp_compare(const double *__restrict__ sa, const double *__rest
                              int64_t n, unsigned long long *bad) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
-    if (!(sa[g] == sb[g]) || ta[g] != tb[g] || oa[g] != ob[g]) atomicAdd(bad, 1ULL);
+    if (!(sa[g] == sb[g]) || ta[g] != tb[g] || oa[g] != ob[g]) { atomicAdd(bad, 1ULL); atomicMin(bad + 1, (unsigned long long)g); }
 }
 void launch_dp_compare(const double *sa, const double *sb, const int32_t *ta, const int32_t *tb, const int8_t *oa,
                        const int8_t *ob, int64_t n, unsigned long long *bad, cudaStream_t st) {

@@ -886,6 +886,7 @@ __global__ void __launch_bounds__(128) k_dp_index(DevBatch B, int n_ext, int tot
         const int q = igrank(i);
         B.ig_node[X.node_off + q] = i | (kind == K_FE ? (int)0x80000000 : 0);
         B.ig_ndx[X.node_off + q] = my;
+        if (kind == K_FE && B.feq) B.feq[X.node_off + p] = q;  // class order -> merged position (k_dp_ml)
     }
     // first merged-stream position whose ndx >= key: binary search over node indices (ndx sorted), then rank
     auto ig_lb = [&](int key) {
