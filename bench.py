@@ -368,10 +368,11 @@ def main():
                     "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e / args.steps,
                     "api": "pgpu_find_genes_batch (C ABI, pinned host input)"},
             "gpu_launches": int(tot_launch * args.steps),
-            "roofline": {"bound": "hbm", "kernel": "k_dp_dq<8> (connection-scoring DP)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "note": "the DP is issue bound (ncu: 78 % issue-active, 250 warp-instructions per DP step), not "
-                                 "HBM bound; DRAM traffic ~ algorithmic bytes (no re-reads)",
+            "roofline": {"bound": "hbm", "kernel": "k_dp_ml (connection-scoring DP, one lane per model)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "note": "the DP is latency / issue bound (ncu: 34 % issue-active, ~400 warp-instructions per warp "
+                                 "step covering ~11 chains), not HBM bound; DRAM traffic 1.5x the algorithmic bytes "
+                                 "(suffix-maximum arrays of the window maximum)",
                          "algorithmic_bytes_per_dp_step": DP_BYTES_PER_STEP, "dp_steps_per_launch": int(stats["dp_steps"]),
                          "kernel_ms": dp_ms, "node_pairs_per_s": stats["pairs"] / (dp_ms * 1e-3) if dp_ms > 0 else None},
             "node_pairs_per_s_job": tot_pairs / (per_step * 1e-3),

@@ -149,6 +149,12 @@ int pgpu_result_genes(const pgpu_result *res, int contig, pgpu_gene *dst);
 int pgpu_result_all_genes(const pgpu_result *res, pgpu_gene *dst);
 /* start/stop node records of every gene, contig-major: dst[2 * sum n_genes] (start, stop) */
 int pgpu_result_gene_nodes(const pgpu_result *res, pgpu_node *dst);
+/* zero-copy access: the result is stored as one segment per sub-batch (normally one), each holding the
+ * genes of a contiguous contig range and their (start, stop) node records in page-locked host memory owned
+ * by the result.  pgpu_result_segment returns the number of genes of segment k (or <0) and the pointers. */
+int pgpu_result_num_segments(const pgpu_result *res);
+long long pgpu_result_segment(const pgpu_result *res, int k, long long *first_gene, const pgpu_gene **genes,
+                              const pgpu_node **gene_nodes);
 /* final node array of one contig (requires opts.want_nodes) -> dst[n_nodes] */
 int pgpu_result_nodes(const pgpu_result *res, int contig, pgpu_node *dst);
 int pgpu_result_stats(const pgpu_result *res, pgpu_stats *dst);

@@ -87,6 +87,9 @@ lib.pgpu_result_summaries.argtypes = [_vp, _vp]
 lib.pgpu_result_genes.argtypes = [_vp, C.c_int, _vp]
 lib.pgpu_result_all_genes.argtypes = [_vp, _vp]
 lib.pgpu_result_gene_nodes.argtypes = [_vp, _vp]
+lib.pgpu_result_num_segments.argtypes = [_vp]
+lib.pgpu_result_segment.argtypes = [_vp, C.c_int, C.POINTER(C.c_longlong), C.POINTER(_vp), C.POINTER(_vp)]
+lib.pgpu_result_segment.restype = C.c_longlong
 lib.pgpu_result_nodes.argtypes = [_vp, C.c_int, _vp]
 lib.pgpu_result_stats.argtypes = [_vp, C.POINTER(Stats)]
 lib.pgpu_result_free.argtypes = [_vp]
@@ -240,7 +243,9 @@ class Batch:
 
 
 class Result:
-    """Owns a pgpu_result; materialises numpy views on demand."""
+    """Owns a pgpu_result.  `summary`, `gene_off` and `stats` are read eagerly (small); `genes` and
+    `gene_nodes` are materialised on first use: zero-copy numpy views of the result's page-locked buffers when
+    the batch ran as one sub-batch (the views keep the Result alive), a concatenated copy otherwise."""
 
     def __init__(self, handle, ctx=None):
         self.handle = handle
@@ -251,15 +256,44 @@ class Result:
             lib.pgpu_result_summaries(handle, ptr(self.summary))
         self.gene_off = np.zeros(self.n + 1, dtype=np.int64)
         np.cumsum(self.summary["n_genes"], out=self.gene_off[1:])
-        ng = int(self.gene_off[-1])
-        self.genes = np.zeros(ng, dtype=GENE_DTYPE)
-        self.gene_nodes = np.zeros((ng, 2), dtype=NODE_DTYPE)
-        if ng:
-            lib.pgpu_result_all_genes(handle, ptr(self.genes))
-            lib.pgpu_result_gene_nodes(handle, ptr(self.gene_nodes))
+        self._genes = self._gene_nodes = None
         st = Stats()
         lib.pgpu_result_stats(handle, C.byref(st))
         self.stats = st.as_dict()
+
+    def _materialise(self):
+        if self.handle is None:
+            raise RuntimeError("result already freed")
+        ng = int(self.gene_off[-1])
+        nseg = lib.pgpu_result_num_segments(self.handle)
+        if ng and nseg == 1:
+            g0, pg, pn = C.c_longlong(0), _vp(), _vp()
+            cnt = lib.pgpu_result_segment(self.handle, 0, C.byref(g0), C.byref(pg), C.byref(pn))
+            assert cnt == ng and g0.value == 0
+            gbuf = (C.c_char * (ng * GENE_DTYPE.itemsize)).from_address(pg.value)
+            nbuf = (C.c_char * (2 * ng * NODE_DTYPE.itemsize)).from_address(pn.value)
+            gbuf._owner = nbuf._owner = self  # the buffers live as long as this Result
+            self._genes = np.frombuffer(gbuf, dtype=GENE_DTYPE)
+            self._gene_nodes = np.frombuffer(nbuf, dtype=NODE_DTYPE).reshape(ng, 2)
+            self._genes.flags.writeable = self._gene_nodes.flags.writeable = False
+        else:
+            self._genes = np.zeros(ng, dtype=GENE_DTYPE)
+            self._gene_nodes = np.zeros((ng, 2), dtype=NODE_DTYPE)
+            if ng:
+                lib.pgpu_result_all_genes(self.handle, ptr(self._genes))
+                lib.pgpu_result_gene_nodes(self.handle, ptr(self._gene_nodes))
+
+    @property
+    def genes(self):
+        if self._genes is None:
+            self._materialise()
+        return self._genes
+
+    @property
+    def gene_nodes(self):
+        if self._gene_nodes is None:
+            self._materialise()
+        return self._gene_nodes
 
     def nodes(self, contig):
         n = int(self.summary["n_nodes"][contig])

@@ -951,6 +951,13 @@ static int run_all(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, co
     if (rc) return rc;
     if (ctx->n_models == 0) return fail(ctx, PGPU_ESTATE, "no models loaded");
     cudaSetDevice(ctx->device);
+    const bool trace = getenv("PGPU_TRACE") != nullptr;
+    const auto t_entry = std::chrono::steady_clock::now();
+    auto tr = [&](const char *what) {
+        if (trace) fprintf(stderr, "[pgpu api %8.2f ms] %s\n",
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count(), what);
+    };
+    tr("entry");
     pgpu_result *res = new pgpu_result();
     res->pinned = ctx->pinned;
     res->n_contigs = n;
@@ -982,12 +989,15 @@ static int run_all(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, co
             bp += offsets[hi + 1] - offsets[hi];
             hi++;
         }
+        tr("sub-batch begin");
         rc = run_range(ctx, h_seq, d_seq, offsets, lo, hi, *opts, plan, res, nullptr);
+        tr("sub-batch end (buffers released)");
         if (rc) { delete res; return rc; }
         lo = hi;
     }
     res->stats.kernel_launches = ctx->launches - launches0;
     *out = res;
+    tr("exit");
     return PGPU_OK;
 }
 
@@ -1181,6 +1191,18 @@ int pgpu_result_gene_nodes(const pgpu_result *res, pgpu_node *dst) {
     return PGPU_OK;
 }
 
+int pgpu_result_num_segments(const pgpu_result *res) { return res ? (int)res->segs.size() : PGPU_EINVAL; }
+
+long long pgpu_result_segment(const pgpu_result *res, int k, long long *first_gene, const pgpu_gene **genes,
+                              const pgpu_node **gene_nodes) {
+    if (!res || k < 0 || k >= (int)res->segs.size()) return PGPU_EINVAL;
+    const auto &s = res->segs[k];
+    if (first_gene) *first_gene = s.g0;
+    if (genes) *genes = s.ng ? s.genes : nullptr;
+    if (gene_nodes) *gene_nodes = s.ng ? s.gnodes : nullptr;
+    return s.ng;
+}
+
 int pgpu_result_nodes(const pgpu_result *res, int contig, pgpu_node *dst) {
     if (!res || contig < 0 || contig >= res->n_contigs) return PGPU_EINVAL;
     if (!res->have_nodes) return PGPU_ESTATE;
@@ -1195,7 +1217,13 @@ int pgpu_result_stats(const pgpu_result *res, pgpu_stats *dst) {
     return PGPU_OK;
 }
 
-void pgpu_result_free(pgpu_result *res) { delete res; }
+void pgpu_result_free(pgpu_result *res) {
+    const bool trace = res && getenv("PGPU_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    delete res;
+    if (trace) fprintf(stderr, "[pgpu api] result_free %.2f ms\n",
+                       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+}
 
 // ---- operator-level twins ---------------------------------------------------------------------------
 

@@ -584,7 +584,7 @@ class GeneFinder:
             seq = Sequence(seq, mask=self.mask, mask_size=self.min_mask)
         seq._gc_count, seq._unknown = int(s["gc_count"]), int(s["unknown"])
         nodes = Nodes(res.nodes(k)) if want_nodes else None
-        return Genes(res.genes[a:b], res.gene_nodes[a:b], sequence=seq, training_info=tinf, metagenomic_bin=mbin,
+        return Genes(res.genes[a:b].copy(), res.gene_nodes[a:b].copy(), sequence=seq, training_info=tinf, metagenomic_bin=mbin,
                      meta=self.meta, nodes=nodes, ipath=int(s["ipath"]), num_seq=num_seq)
 
     # ---- public ----
