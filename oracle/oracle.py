@@ -182,3 +182,36 @@ def find_genes_meta(digits, gc, bins_blob, opts=None, n_bins=None):
            _p(genes), gcap, C.byref(winner), C.byref(pairs))
     assert ng >= 0
     return genes[:ng].copy(), nodes[: nn.value].copy(), winner.value, pairs.value
+
+
+# ---- training (GeneFinder.train) ------------------------------------------------------------------
+TRAINING_DTYPE = np.dtype(
+    [
+        ("gc", "f8"), ("trans_table", "i4"), ("_pad0", "i4"), ("st_wt", "f8"), ("bias", "f8", (3,)),
+        ("type_wt", "f8", (3,)), ("uses_sd", "i4"), ("_pad1", "i4"), ("rbs_wt", "f8", (28,)),
+        ("ups_comp", "f8", (32, 4)), ("mot_wt", "f8", (4, 4, 4096)), ("no_mot", "f8"), ("gene_dc", "f8", (4096,)),
+    ]
+)
+assert TRAINING_DTYPE.itemsize == TRAINING_SIZE
+
+
+def gc_frame_plot(digits):
+    gp = np.empty(len(digits), dtype=np.int8)
+    lib().orc_gc_frame_plot(_p(digits), len(digits), _p(gp))
+    return gp
+
+
+def train(digits, gc, translation_table=11, start_weight=4.35, force_nonsd=False, opts=None, return_nodes=False):
+    """GeneFinder.train on an encoded sequence -> raw training struct (bytes)"""
+    opts = opts or make_opts()
+    cap = node_capacity(len(digits))
+    nodes = np.zeros(cap, dtype=NODE_DTYPE)
+    out = np.zeros(1, dtype=TRAINING_DTYPE)
+    f = lib().orc_train
+    f.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                  C.c_void_p]
+    nn = f(_p(digits), len(digits), float(gc), translation_table, float(start_weight), int(force_nonsd),
+           C.byref(opts), _p(nodes), cap, _p(out))
+    assert nn >= 0
+    blob = out.tobytes()
+    return (blob, nodes[:nn].copy()) if return_nodes else blob

@@ -426,8 +426,8 @@ void orc_rbs_score(const uint8_t *d, int slen, orc_node *nodes, int nn, const or
     }
 }
 
-/* lib.pyx:1557-1616, stage 2 */
-static void best_upstream_motif(const uint8_t *d, int slen, orc_node *x, const orc_training *t) {
+/* lib.pyx:1557-1616; only stage 2 (scoring, last training rounds) may report "no motif" */
+static void best_upstream_motif(const uint8_t *d, int slen, orc_node *x, const orc_training *t, int stage) {
     if (x->type == ORC_STOP || x->edge) return;
     int start = x->strand == 1 ? x->ndx : slen - 1 - x->ndx;
     int max_spacer = 0, max_spacendx = 0, max_len = 0, max_ndx = 0;
@@ -448,7 +448,7 @@ static void best_upstream_motif(const uint8_t *d, int slen, orc_node *x, const o
             }
         }
     }
-    if (max_sc == -4.0 || max_sc < t->no_mot + 0.69) {
+    if (stage == 2 && (max_sc == -4.0 || max_sc < t->no_mot + 0.69)) {
         x->mot_ndx = 0; x->mot_len = 0; x->mot_spacendx = 0; x->mot_spacer = 0; x->mot_score = t->no_mot;
     } else {
         x->mot_ndx = max_ndx; x->mot_len = max_len; x->mot_spacendx = max_spacendx;
@@ -473,7 +473,7 @@ void orc_score(const uint8_t *d, int slen, orc_node *nodes, int nn, const orc_tr
     orc_calc_orf_gc(d, slen, nodes, nn);
     orc_raw_coding_score(d, slen, nodes, nn, t);
     if (t->uses_sd) orc_rbs_score(d, slen, nodes, nn, t);
-    else for (int i = 0; i < nn; i++) best_upstream_motif(d, slen, &nodes[i], t);
+    else for (int i = 0; i < nn; i++) best_upstream_motif(d, slen, &nodes[i], t, 2);
 
     for (int i = 0; i < nn; i++) {
         orc_node *x = &nodes[i];
@@ -1019,6 +1019,458 @@ int orc_find_genes_meta(const uint8_t *digits, int slen, double gc, const orc_tr
     if (winner) *winner = max_phase;
     if (pairs) *pairs = tot_pairs;
     return ng;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* training (GeneFinder.train, lib.pyx:5236-5279)                                        */
+/* ------------------------------------------------------------------------------------ */
+
+/* vendor/Prodigal/sequence.c:559-564: index of the strictly largest value, later index on ties */
+static int frame_of_max(int a, int b, int c) {
+    if (a > b) return a > c ? 0 : 2;
+    return b > c ? 1 : 2;
+}
+
+/* lib.pyx:724-768.  tot[i] = number of GC bases among i-57, i-54, .., i+57 that lie inside the
+ * sequence (the reference builds it from two running sums 60 positions apart); every codon
+ * triplet then gets the frame with the largest count, the tail that has no full triplet stays -1. */
+void orc_gc_frame_plot(const uint8_t *d, int slen, int8_t *gp) {
+    for (int i = 0; i < slen; i++) gp[i] = -1;
+    for (int i = 0; i + 2 < slen; i += 3) {
+        int tot[3];
+        for (int f = 0; f < 3; f++) {
+            int c = 0;
+            for (int k = -19; k <= 19; k++) {
+                int x = i + f + 3 * k;
+                if (x >= 0 && x < slen) c += is_gc_fwd(d, x);
+            }
+            tot[f] = c;
+        }
+        int w = frame_of_max(tot[0], tot[1], tot[2]);
+        gp[i] = gp[i + 1] = gp[i + 2] = (int8_t)w;
+    }
+}
+
+/* vendor/Prodigal/node.c:263-317.  Each ORF is walked from its stop towards its starts, counting in
+ * which codon position the GC-richest frame of every codon falls; bias[] is an order-dependent
+ * floating point sum over the start nodes in index order. */
+void orc_record_gc_bias(const int8_t *gp, orc_node *nodes, int nn, orc_training *t) {
+    if (nn == 0) return;
+    int ctr[3][3] = {{0}}, last[3] = {0, 0, 0};
+    for (int i = nn - 1; i >= 0; i--) {
+        orc_node *x = &nodes[i];
+        if (x->strand != 1) continue;
+        int fr = x->ndx % 3, shift = 3 - fr;
+        if (x->type == ORC_STOP) {
+            ctr[fr][0] = ctr[fr][1] = ctr[fr][2] = 0;
+            last[fr] = x->ndx;
+            ctr[fr][(gp[x->ndx] + shift) % 3] = 1;
+        } else {
+            for (int j = last[fr] - 3; j >= x->ndx; j -= 3) ctr[fr][(gp[j] + shift) % 3]++;
+            x->gc_bias = frame_of_max(ctr[fr][0], ctr[fr][1], ctr[fr][2]);
+            for (int j = 0; j < 3; j++) {
+                x->gc_score[j] = 3.0 * ctr[fr][j];
+                x->gc_score[j] /= 1.0 * (x->stop_val - x->ndx + 3);
+            }
+            last[fr] = x->ndx;
+        }
+    }
+    for (int i = 0; i < nn; i++) {
+        orc_node *x = &nodes[i];
+        if (x->strand != -1) continue;
+        int fr = x->ndx % 3, shift = fr;
+        if (x->type == ORC_STOP) {
+            ctr[fr][0] = ctr[fr][1] = ctr[fr][2] = 0;
+            last[fr] = x->ndx;
+            ctr[fr][((3 - gp[x->ndx]) + shift) % 3] = 1;
+        } else {
+            for (int j = last[fr] + 3; j <= x->ndx; j += 3) ctr[fr][((3 - gp[j]) + shift) % 3]++;
+            x->gc_bias = frame_of_max(ctr[fr][0], ctr[fr][1], ctr[fr][2]);
+            for (int j = 0; j < 3; j++) {
+                x->gc_score[j] = 3.0 * ctr[fr][j];
+                x->gc_score[j] /= 1.0 * (x->ndx - x->stop_val + 3);
+            }
+            last[fr] = x->ndx;
+        }
+    }
+    t->bias[0] = t->bias[1] = t->bias[2] = 0.0;
+    for (int i = 0; i < nn; i++) {
+        const orc_node *x = &nodes[i];
+        if (x->type == ORC_STOP) continue;
+        int len = abs(x->stop_val - x->ndx) + 1;
+        t->bias[x->gc_bias] += (x->gc_score[x->gc_bias] * len) / 1000.0;
+    }
+    double tot = t->bias[0] + t->bias[1] + t->bias[2];
+    for (int i = 0; i < 3; i++) t->bias[i] *= (3.0 / tot);
+}
+
+/* lib.pyx:4284-4358: log-odds of every 6-mer inside the genes of the training path against the
+ * whole sequence (both strands), clamped to [-5, 5] */
+void orc_calc_dicodon_gene(const uint8_t *d, int slen, const orc_node *nodes, int ipath, orc_training *t) {
+    int counts[4096];
+    double bg[4096];
+    int glob = 0;
+    memset(counts, 0, sizeof(counts));
+    for (int i = 0; i < slen - 5; i++) {
+        counts[mer_ndx(d, slen, i, 6, 1)]++;
+        counts[mer_ndx(d, slen, i, 6, -1)]++;
+        glob += 2;
+    }
+    for (int i = 0; i < 4096; i++) bg[i] = (double)counts[i] / (double)glob;
+
+    glob = 0;
+    memset(counts, 0, sizeof(counts));
+    int in_gene = 0, left = -1, right = -1;
+    for (int p = ipath; p != -1; p = nodes[p].traceb) {
+        const orc_node *x = &nodes[p];
+        if (x->strand == 1) {
+            if (x->type == ORC_STOP) {
+                in_gene = 1;
+                right = x->ndx + 2;
+            } else if (in_gene == 1) {
+                left = x->ndx;
+                for (int i = left; i < right - 5; i += 3) { counts[mer_ndx(d, slen, i, 6, 1)]++; glob++; }
+                in_gene = 0;
+            }
+        } else {
+            if (x->type != ORC_STOP) {
+                in_gene = -1;
+                left = slen - x->ndx - 1;
+            } else if (in_gene == -1) {
+                right = slen - x->ndx + 1;
+                for (int i = left; i < right - 5; i += 3) { counts[mer_ndx(d, slen, i, 6, -1)]++; glob++; }
+                in_gene = 0;
+            }
+        }
+    }
+    for (int i = 0; i < 4096; i++) {
+        double prob = (double)counts[i] / (double)glob, v;
+        if (prob == 0 && bg[i] != 0) v = -5.0;
+        else if (bg[i] == 0) v = 0.0;
+        else v = log(prob / bg[i]);
+        if (v > 5.0) v = 5.0;
+        else if (v < -5.0) v = -5.0;
+        t->gene_dc[i] = v;
+    }
+}
+
+/* lib.pyx:4360-4389: tally the bases at start-1, start-2, start-15 .. start-44 (strand oriented) */
+static void count_upstream(const uint8_t *d, int slen, int pos, int strand, orc_training *t) {
+    static const int off[2][2] = {{1, 3}, {15, 45}};
+    int slot = 0;
+    for (int g = 0; g < 2; g++)
+        for (int j = off[g][0]; j < off[g][1]; j++, slot++) {
+            if (strand == 1) {
+                if (pos >= j) t->ups_comp[slot][d[pos - j] & 3] += 1.0;
+            } else {
+                static const uint8_t comp[7] = {dT, dC, dG, dA, dN, dN, dN};
+                if (pos + j < slen) t->ups_comp[slot][comp[d[pos + j]] & 3] += 1.0;
+            }
+        }
+}
+
+/* shared tail of both start-training loops: counts -> clamped log-odds against the GC content
+ * (lib.pyx:4561-4599 == 4793-4826) */
+static void upstream_to_log(orc_training *t) {
+    for (int i = 0; i < 32; i++) {
+        double sum = 0.0;
+        for (int j = 0; j < 4; j++) sum += t->ups_comp[i][j];
+        if (sum == 0.0) {
+            for (int j = 0; j < 4; j++) t->ups_comp[i][j] = 0.0;
+            continue;
+        }
+        for (int j = 0; j < 4; j++) {
+            int at = j == 0 || j == 3;
+            double den;
+            if (t->gc <= 0.1) den = at ? 0.90 : 0.10;
+            else if (t->gc >= 0.9) den = at ? 0.10 : 0.90;
+            else den = at ? 1.0 - t->gc : t->gc;
+            double v = t->ups_comp[i][j] / sum;
+            v = log(v * 2.0 / den);
+            if (v > 4.0) v = 4.0;
+            if (v < -4.0) v = -4.0;
+            t->ups_comp[i][j] = v;
+        }
+    }
+}
+
+/* counts -> clamped log-odds of the start codon types (lib.pyx:4540-4557 == 4771-4788);
+ * returns the number of genes that contributed */
+static double type_weights_from_counts(double treal[3], const double tbg[3], orc_training *t) {
+    double sum = treal[0] + treal[1] + treal[2];
+    for (int j = 0; j < 3; j++) {
+        if (sum == 0.0) { t->type_wt[j] = 0.0; continue; }
+        treal[j] /= sum;
+        double v = tbg[j] != 0 ? log(treal[j] / tbg[j]) : -4.0;
+        if (v > 4.0) v = 4.0;
+        else if (v < -4.0) v = -4.0;
+        t->type_wt[j] = v;
+    }
+    return sum;
+}
+
+/* which of the two SD motif bins (exact / one mismatch) a start is credited with
+ * (lib.pyx:4442-4449 and three more copies) */
+static int preferred_rbs(const orc_node *x, const double *rbs_wt) {
+    int a = x->rbs[0], b = x->rbs[1];
+    if (rbs_wt[a] > rbs_wt[b] + 1.0 || b == 0) return a;
+    if (rbs_wt[a] < rbs_wt[b] - 1.0 || a == 0) return b;
+    return a > b ? a : b;
+}
+
+static void type_background(const orc_node *nodes, int nn, double tbg[3]) {
+    tbg[0] = tbg[1] = tbg[2] = 0.0;
+    for (int i = 0; i < nn; i++)
+        if (nodes[i].type != ORC_STOP) tbg[nodes[i].type] += 1.0;
+    double sum = tbg[0] + tbg[1] + tbg[2];
+    for (int i = 0; i < 3; i++) tbg[i] /= sum;
+}
+
+/* lib.pyx:4391-4599 */
+void orc_train_starts_sd(const uint8_t *d, int slen, orc_node *nodes, int nn, orc_training *t) {
+    double tbg[3], sthresh = 35.0;
+    const double wt = t->st_wt;
+    memset(t->type_wt, 0, sizeof(t->type_wt));
+    memset(t->rbs_wt, 0, sizeof(t->rbs_wt));
+    memset(t->ups_comp, 0, sizeof(t->ups_comp));
+    type_background(nodes, nn, tbg);
+
+    for (int it = 0; it < 10; it++) {
+        double rbg[28] = {0}, rreal[28] = {0}, treal[3] = {0};
+        for (int j = 0; j < nn; j++)
+            if (nodes[j].type != ORC_STOP && !nodes[j].edge) rbg[preferred_rbs(&nodes[j], t->rbs_wt)] += 1.0;
+        double sum = 0.0;
+        for (int j = 0; j < 28; j++) sum += rbg[j];
+        for (int j = 0; j < 28; j++) rbg[j] /= sum;
+
+        /* one sweep per strand: forward in index order, reverse against it; per frame the best
+         * scoring start since the last STOP is credited when that STOP is reached */
+        for (int strand = 1; strand >= -1; strand -= 2) {
+            double best[3] = {0, 0, 0};
+            int bndx[3] = {-1, -1, -1}, brbs[3] = {0, 0, 0}, btype[3] = {0, 0, 0};
+            for (int q = 0; q < nn; q++) {
+                int j = strand == 1 ? q : nn - 1 - q;
+                const orc_node *x = &nodes[j];
+                if ((x->type != ORC_STOP && x->edge) || x->strand != strand) continue;
+                int ph = x->ndx % 3;
+                if (x->type == ORC_STOP) {
+                    if (best[ph] >= sthresh && nodes[bndx[ph]].ndx % 3 == ph) {
+                        rreal[brbs[ph]] += 1.0;
+                        treal[btype[ph]] += 1.0;
+                        if (it == 9) count_upstream(d, slen, nodes[bndx[ph]].ndx, strand, t);
+                    }
+                    best[ph] = 0.0; bndx[ph] = -1; brbs[ph] = 0; btype[ph] = 0;
+                } else {
+                    int rb = preferred_rbs(x, t->rbs_wt);
+                    double v = x->cscore + wt * t->rbs_wt[rb] + wt * t->type_wt[x->type];
+                    if (v >= best[ph]) { best[ph] = v; bndx[ph] = j; btype[ph] = x->type; brbs[ph] = rb; }
+                }
+            }
+        }
+
+        sum = 0.0;
+        for (int j = 0; j < 28; j++) sum += rreal[j];
+        for (int j = 0; j < 28; j++) {
+            if (sum == 0.0) { t->rbs_wt[j] = 0.0; continue; }
+            rreal[j] /= sum;
+            double v = rbg[j] != 0 ? log(rreal[j] / rbg[j]) : -4.0;
+            if (v > 4.0) v = 4.0;
+            else if (v < -4.0) v = -4.0;
+            t->rbs_wt[j] = v;
+        }
+        sum = type_weights_from_counts(treal, tbg, t);
+        if (sum * 2000.0 <= nn) sthresh /= 2.0;
+    }
+    upstream_to_log(t);
+}
+
+/* vendor/Prodigal/node.c:686-693 */
+void orc_determine_sd_usage(orc_training *t) {
+    const double *w = t->rbs_wt;
+    t->uses_sd = 1;
+    if (w[0] >= 0.0) t->uses_sd = 0;
+    if (w[16] < 1.0 && w[13] < 1.0 && w[15] < 1.0 && (w[0] >= -0.5 || (w[22] < 2.0 && w[24] < 2.0 && w[27] < 2.0)))
+        t->uses_sd = 0;
+}
+
+/* lib.pyx:4226-4282 */
+static void update_motif_counts(double (*cnt)[4][4096], double *zero, const uint8_t *d, int slen, const orc_node *x,
+                                int stage) {
+    if (x->type == ORC_STOP || x->edge == 1) return;
+    if (x->mot_len == 0) { *zero += 1.0; return; }
+    int start = x->strand == 1 ? x->ndx : slen - 1 - x->ndx;
+    if (stage == 0) {
+        /* every window of every length, credited to all four spacer classes */
+        for (int l = 3; l >= 0; l--)
+            for (int j = start - 18 - l; j <= start - 6 - l; j++) {
+                if (j < 0) continue;
+                int mer = mer_ndx(d, slen, j, l + 3, x->strand);
+                for (int k = 0; k < 4; k++) cnt[l][k][mer] += 1.0;
+            }
+    } else if (stage == 1) {
+        /* the best motif and every shorter word inside it */
+        cnt[x->mot_len - 3][x->mot_spacendx][x->mot_ndx] += 1.0;
+        for (int l = 0; l < x->mot_len - 3; l++)
+            for (int j = start - x->mot_spacer - x->mot_len; j <= start - x->mot_spacer - l - 3; j++) {
+                if (j < 0) continue;
+                int sp;
+                if (j <= start - 16 - l) sp = 3;
+                else if (j <= start - 14 - l) sp = 2;
+                else if (j >= start - 7 - l) sp = 1;
+                else sp = 0;
+                cnt[l][sp][mer_ndx(d, slen, j, l + 3, x->strand)] += 1.0;
+            }
+    } else {
+        cnt[x->mot_len - 3][x->mot_spacendx][x->mot_ndx] += 1.0;
+    }
+}
+
+/* vendor/Prodigal/node.c:1307-1357: which motifs are frequent enough (or made of frequent words) */
+static void coverage_map(double (*real)[4][4096], int (*good)[4][4096], double ng, int stage) {
+    (void)stage;
+    memset(good, 0, sizeof(int) * 4 * 4 * 4096);
+    for (int s = 0; s < 4; s++)
+        for (int m = 0; m < 64; m++)
+            if (real[0][s][m] / ng >= 0.2)
+                for (int k = 0; k < 4; k++) good[0][k][m] = 1;
+    for (int s = 0; s < 4; s++)
+        for (int m = 0; m < 256; m++)
+            if (good[0][s][(m & 252) >> 2] && good[0][s][m & 63]) good[1][s][m] = 1;
+    for (int s = 0; s < 4; s++)
+        for (int m = 0; m < 1024; m++) {
+            if (!good[0][s][(m & 1008) >> 4] || !good[0][s][(m & 252) >> 2] || !good[0][s][m & 63]) continue;
+            good[2][s][m] = 1;
+            /* the three variants with the middle base changed are allowed as "mismatch" motifs */
+            int v = m;
+            for (int a = 0; a <= 16; a += 16) {
+                v ^= a;
+                for (int b = 0; b <= 32; b += 32) {
+                    v ^= b;
+                    if (good[2][s][v] == 0) good[2][s][v] = 2;
+                }
+            }
+        }
+    for (int s = 0; s < 4; s++)
+        for (int m = 0; m < 4096; m++) {
+            int a = good[2][s][(m & 4092) >> 2], b = good[2][s][m & 1023];
+            if (a == 0 || b == 0) continue;
+            good[3][s][m] = (a == 1 && b == 1) ? 1 : 2;
+        }
+}
+
+/* lib.pyx:4601-4826 */
+void orc_train_starts_nonsd(const uint8_t *d, int slen, orc_node *nodes, int nn, orc_training *t) {
+    double(*mbg)[4][4096] = malloc(sizeof(double) * 4 * 4 * 4096);
+    double(*mreal)[4][4096] = malloc(sizeof(double) * 4 * 4 * 4096);
+    int(*mgood)[4][4096] = malloc(sizeof(int) * 4 * 4 * 4096);
+    double tbg[3], sthresh = 35.0;
+    const double wt = t->st_wt;
+    memset(t->ups_comp, 0, sizeof(t->ups_comp));
+    memset(t->type_wt, 0, sizeof(t->type_wt));
+    type_background(nodes, nn, tbg);
+    /* the reference never initialises mgood before stage 2 is reached without stages 0/1 having
+     * run; iterations 0..11 always fill it, so start from zero */
+    memset(mgood, 0, sizeof(int) * 4 * 4 * 4096);
+
+    for (int it = 0; it < 20; it++) {
+        int stage = it < 4 ? 0 : (it < 12 ? 1 : 2);
+        double zbg = 0.0, zreal = 0.0, treal[3] = {0}, ngenes = 0.0;
+        memset(mbg, 0, sizeof(double) * 4 * 4 * 4096);
+        memset(mreal, 0, sizeof(double) * 4 * 4 * 4096);
+        for (int j = 0; j < nn; j++) {
+            if (nodes[j].type == ORC_STOP || nodes[j].edge) continue;
+            best_upstream_motif(d, slen, &nodes[j], t, stage);
+            update_motif_counts(mbg, &zbg, d, slen, &nodes[j], stage);
+        }
+        double sum = 0.0;
+        for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) for (int c = 0; c < 4096; c++) sum += mbg[a][b][c];
+        sum += zbg;
+        for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) for (int c = 0; c < 4096; c++) mbg[a][b][c] /= sum;
+        zbg /= sum;
+
+        for (int strand = 1; strand >= -1; strand -= 2) {
+            double best[3] = {0, 0, 0};
+            int bndx[3] = {-1, -1, -1};
+            for (int q = 0; q < nn; q++) {
+                int j = strand == 1 ? q : nn - 1 - q;
+                const orc_node *x = &nodes[j];
+                if ((x->type != ORC_STOP && x->edge) || x->strand != strand) continue;
+                int fr = x->ndx % 3;
+                if (x->type == ORC_STOP) {
+                    if (best[fr] >= sthresh) {
+                        ngenes += 1.0;
+                        treal[nodes[bndx[fr]].type] += 1.0;
+                        update_motif_counts(mreal, &zreal, d, slen, &nodes[bndx[fr]], stage);
+                        if (it == 19) count_upstream(d, slen, nodes[bndx[fr]].ndx, strand, t);
+                    }
+                    best[fr] = 0.0; bndx[fr] = -1;
+                } else {
+                    double v = x->cscore + wt * x->mot_score + wt * t->type_wt[x->type];
+                    if (v >= best[fr]) { best[fr] = v; bndx[fr] = j; }
+                }
+            }
+        }
+
+        if (stage < 2) coverage_map(mreal, mgood, ngenes, stage);
+        sum = 0.0;
+        for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) for (int c = 0; c < 4096; c++) sum += mreal[a][b][c];
+        sum += zreal;
+        if (sum == 0.0) {
+            memset(t->mot_wt, 0, sizeof(t->mot_wt));
+            t->no_mot = 0.0;
+        } else {
+            for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) for (int c = 0; c < 4096; c++) {
+                if (mgood[a][b][c] == 0) {
+                    zreal += mreal[a][b][c];
+                    zbg += mreal[a][b][c];
+                    mreal[a][b][c] = 0.0;
+                    mbg[a][b][c] = 0.0;
+                }
+                mreal[a][b][c] /= sum;
+                double v = mbg[a][b][c] != 0 ? log(mreal[a][b][c] / mbg[a][b][c]) : -4.0;
+                if (v > 4.0) v = 4.0;
+                else if (v < -4.0) v = -4.0;
+                t->mot_wt[a][b][c] = v;
+            }
+        }
+        /* no_mot is recomputed even when sum == 0 (0/0 = NaN compares false everywhere) */
+        zreal /= sum;
+        {
+            double v = zbg != 0 ? log(zreal / zbg) : -4.0;
+            if (v > 4.0) v = 4.0;
+            else if (v < -4.0) v = -4.0;
+            t->no_mot = v;
+        }
+        sum = type_weights_from_counts(treal, tbg, t);
+        if (sum * 2000.0 <= nn) sthresh /= 2.0;
+    }
+    upstream_to_log(t);
+    free(mbg); free(mreal); free(mgood);
+}
+
+/* lib.pyx:5236-5279 (+ the TrainingInfo constructor, 3960-4003).  `nodes` is scratch of node_cap
+ * entries; returns the node count or -1 when node_cap is too small. */
+int orc_train(const uint8_t *digits, int slen, double gc, int tt, double st_wt, int force_nonsd, const orc_opts *o,
+              orc_node *nodes, int node_cap, orc_training *t) {
+    memset(t, 0, sizeof(*t));
+    t->gc = gc; t->trans_table = tt; t->st_wt = st_wt; t->uses_sd = 1;
+    int nn = orc_extract(digits, slen, tt, o, nodes, node_cap);
+    if (nn < 0) return -1;
+    orc_sort(nodes, nn);
+    int8_t *gp = malloc(slen > 0 ? slen : 1);
+    orc_gc_frame_plot(digits, slen, gp);
+    orc_record_gc_bias(gp, nodes, nn, t);
+    free(gp);
+    orc_record_overlapping_starts(nodes, nn, t, 0, o->max_overlap);
+    int ipath = orc_dynamic_programming(nodes, nn, t, 0);
+    orc_calc_dicodon_gene(digits, slen, nodes, ipath, t);
+    orc_raw_coding_score(digits, slen, nodes, nn, t);
+    orc_rbs_score(digits, slen, nodes, nn, t);
+    orc_train_starts_sd(digits, slen, nodes, nn, t);
+    if (force_nonsd) t->uses_sd = 0;
+    else orc_determine_sd_usage(t);
+    if (!t->uses_sd) orc_train_starts_nonsd(digits, slen, nodes, nn, t);
+    return nn;
 }
 
 /* layout probes for the ctypes/numpy binding in oracle/oracle.py */

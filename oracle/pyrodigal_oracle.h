@@ -120,6 +120,23 @@ int orc_find_genes_meta(const uint8_t *digits, int slen, double gc, const orc_tr
                         const orc_opts *o, orc_node *nodes, int node_cap, int *nn_out, orc_gene *genes,
                         int gene_cap, int *winner, int64_t *pairs);
 
+/* ---- training (GeneFinder.train, lib.pyx:5236-5279) ---- */
+/* lib.pyx:724-768: gp[i] = GC-richest frame (0..2) of the codon triplet holding i, -1 in the tail */
+void orc_gc_frame_plot(const uint8_t *digits, int slen, int8_t *gp);
+/* vendor/Prodigal/node.c:263-317: fills gc_bias / gc_score of every start and t->bias */
+void orc_record_gc_bias(const int8_t *gp, orc_node *nodes, int nn, orc_training *t);
+/* lib.pyx:4284-4358 */
+void orc_calc_dicodon_gene(const uint8_t *digits, int slen, const orc_node *nodes, int ipath, orc_training *t);
+/* lib.pyx:4391-4599 */
+void orc_train_starts_sd(const uint8_t *digits, int slen, orc_node *nodes, int nn, orc_training *t);
+/* vendor/Prodigal/node.c:686-693 */
+void orc_determine_sd_usage(orc_training *t);
+/* lib.pyx:4601-4826 */
+void orc_train_starts_nonsd(const uint8_t *digits, int slen, orc_node *nodes, int nn, orc_training *t);
+/* lib.pyx:5236-5279 on a zero-initialised TrainingInfo(gc, tt, st_wt).  returns nn or -1 (cap) */
+int orc_train(const uint8_t *digits, int slen, double gc, int tt, double st_wt, int force_nonsd, const orc_opts *o,
+              orc_node *nodes, int node_cap, orc_training *t);
+
 int orc_sizeof_node(void);
 int orc_sizeof_training(void);
 

@@ -11,6 +11,10 @@ Fixtures (all small):
   dp_cases.npz      operator level: node arrays in, ConnectionScorer.score_connections out,
                     final=True and final=False (the reference's tests/test_connection_scorer.py
                     protocol, with real scores / star_ptr / gc_score injected via __setstate__).
+  train_cases.npz   GeneFinder.train(): sequence + options in, raw TrainingInfo struct out, incl. the
+                    reference's own golden (tests/test_training_info.py:60-66, the 100 kb slice trained with
+                    closed=True must equal GCF_..._100kb.tinf_closed.bin.gz) and the contig of
+                    tests/test_gene_finder.py:329-345; plus Sequence.max_gc_frame_plot() of every case.
   misc.npz          node counts per translation table (tests/test_nodes.py:28-39), Shine-Dalgarno
                     known answers (tests/test_sequence.py:52-75).
 """
@@ -234,8 +238,55 @@ def misc():
     print("misc ok")
 
 
+def train_cases():
+    import warnings
+    out = {}
+    names = []
+    _, srr = R.read_fasta_gz(os.path.join(R.REF_DATA, "SRR492066.fna.gz"))[0]
+    recs = R.read_fasta_gz(os.path.join(R.REF_DATA, "GCF_001457455.1_NCTC11397_genomic_100kb.fna.gz"))
+    g100 = "TTAATTAATTAA".join([s for _, s in recs] + [""]) if len(recs) > 1 else recs[0][1]
+    with gzip.open(os.path.join(R.REF_DATA, "GCF_001457455.1_NCTC11397_genomic_100kb.tinf_closed.bin.gz"), "rb") as f:
+        expected_100k = bytes(memoryview(pyrodigal.TrainingInfo.load(f)))
+    # name, sequence, GeneFinder kwargs, train kwargs
+    specs = [
+        ("ref100k_closed", g100.encode(), dict(closed=True), {}),
+        ("ref100k_open", g100.encode(), {}, {}),
+        ("srr_contig", srr.encode(), {}, {}),
+        ("s60k_nonsd", R.synth(60000, 0.45, seed=501), {}, {}),
+        ("s30k_tt4_forced", R.synth(30000, 0.38, seed=502), {}, dict(force_nonsd=True, translation_table=4)),
+        ("s40k_N_mask", R.synth(40000, 0.55, seed=503, n_frac=0.002), dict(mask=True), dict(start_weight=3.9)),
+        ("s25k_closed_hi", R.synth(25000, 0.68, seed=504), dict(closed=True), {}),
+        ("s20000_min", R.synth(20000, 0.5, seed=505), {}, {}),
+    ]
+    for name, seq, gk, tk in specs:
+        gf = pyrodigal.GeneFinder(**gk)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ti = gf.train(seq, **tk)
+        blob = bytes(memoryview(ti))
+        if name == "ref100k_closed":
+            assert blob == expected_100k, "reference build does not reproduce its own training golden"
+        names.append(name)
+        out[name + "/seq"] = np.frombuffer(seq, dtype=np.uint8)
+        out[name + "/opts"] = np.array([int(gk.get("closed", False)), int(gk.get("mask", False)),
+                                        int(tk.get("force_nonsd", False)), int(tk.get("translation_table", 11))])
+        out[name + "/start_weight"] = np.array(float(tk.get("start_weight", 4.35)))
+        out[name + "/tinf"] = np.frombuffer(blob, dtype=np.uint8)
+        out[name + "/gc_frame"] = np.array(pyrodigal.Sequence(seq).max_gc_frame_plot(), dtype=np.int8)
+    # the published scalars of tests/test_gene_finder.py:329-345
+    out["srr_expected"] = np.array([0.3010045159434068, 2.6770525781861187, 0.17260535063729165, 0.1503420711765898,
+                                    0.71796361273324, -1.3722361344058844, -2.136731395763296])
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "train_cases.npz"), **out)
+    print("train_cases", len(names))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        train_cases()
+        sys.exit(0)
     meta_cases()
     single_cases()
     dp_cases()
     misc()
+    train_cases()
