@@ -161,6 +161,28 @@ int pgpu_result_stats(const pgpu_result *res, pgpu_stats *dst);
 void pgpu_result_free(pgpu_result *res);
 
 /* -------------------------------------------------------------------------------------------- */
+/* training (the caller side of the hot path in single mode)                */
+/* -------------------------------------------------------------------------------------------- */
+
+/* Keyword arguments of GeneFinder.train (lib.pyx:5471-5478). */
+typedef struct {
+    int32_t translation_table; /* default 11; must be one of lib.pyx:172                        */
+    int32_t force_nonsd;       /* 1 = skip the Shine-Dalgarno usage heuristic (node.c:686-693)  */
+    double start_weight;       /* default 4.35                                                  */
+    int32_t reserved[4];
+} pgpu_train_opts;
+
+/* GeneFinder.train (lib.pyx:5471-5575, _train 5236-5279): extract the nodes of `seq` (several training
+ * sequences are joined by the caller with TTAATTAATTAA linkers, lib.pyx:5534-5541), GC frame bias, training DP,
+ * dicodon statistics, SD / non-SD start training.  Writes the resulting `struct _training`
+ * (PGPU_TRAINING_SIZE bytes, the reference's raw layout) to out_training.  opts supplies closed / mask /
+ * min_mask / min_gene / min_edge_gene / max_overlap; opts->meta must be 0 (RuntimeError in the reference).
+ * Sequences shorter than 20000 bases are rejected with PGPU_EINVAL (ValueError, lib.pyx:5547-5550).
+ * Does not touch the loaded model set.  stats may be NULL. */
+int pgpu_train(pgpu_ctx *ctx, const uint8_t *seq, int64_t slen, const pgpu_opts *opts, const pgpu_train_opts *topts,
+               void *out_training, pgpu_stats *stats);
+
+/* -------------------------------------------------------------------------------------------- */
 /* operator-level twins (what the reference's own backend tests drive)                          */
 /* -------------------------------------------------------------------------------------------- */
 

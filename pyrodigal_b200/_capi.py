@@ -46,6 +46,11 @@ class Stats(C.Structure):
         return d
 
 
+class TrainOpts(C.Structure):
+    _fields_ = [("translation_table", C.c_int32), ("force_nonsd", C.c_int32), ("start_weight", C.c_double),
+                ("reserved", C.c_int32 * 4)]
+
+
 GENE_DTYPE = np.dtype([("begin", "<i4"), ("end", "<i4"), ("start_ndx", "<i4"), ("stop_ndx", "<i4")])
 
 NODE_DTYPE = np.dtype(
@@ -94,6 +99,7 @@ lib.pgpu_result_nodes.argtypes = [_vp, C.c_int, _vp]
 lib.pgpu_result_stats.argtypes = [_vp, C.POINTER(Stats)]
 lib.pgpu_result_free.argtypes = [_vp]
 lib.pgpu_result_free.restype = None
+lib.pgpu_train.argtypes = [_vp, _vp, C.c_int64, C.POINTER(Opts), C.POINTER(TrainOpts), _vp, C.POINTER(Stats)]
 lib.pgpu_extract_nodes.argtypes = [_vp, _vp, C.c_int, C.c_int, C.POINTER(Opts), C.c_int, _vp, _vp, _vp, _vp, _vp]
 lib.pgpu_score_nodes.argtypes = [_vp, _vp, C.c_int, C.c_int, C.POINTER(Opts), C.c_int, C.c_int, C.c_int, _vp]
 lib.pgpu_score_connections.argtypes = [_vp, C.c_int] + [_vp] * 10 + [C.c_int, C.c_int] + [_vp] * 5
@@ -175,6 +181,16 @@ class Context:
         b = _vp()
         check(lib.pgpu_batch_upload(self.handle, ptr(seq), ptr(offsets), len(offsets) - 1, C.byref(b)), self.handle)
         return Batch(self, b)
+
+    def train(self, seq, opts, translation_table=11, start_weight=4.35, force_nonsd=False):
+        """GeneFinder.train on one (already joined) ASCII sequence -> (raw training struct bytes, stats dict)"""
+        t = TrainOpts()
+        t.translation_table, t.force_nonsd, t.start_weight = int(translation_table), int(bool(force_nonsd)), float(start_weight)
+        out = np.zeros(TRAINING_SIZE, dtype=np.uint8)
+        st = Stats()
+        check(lib.pgpu_train(self.handle, ptr(seq), len(seq), C.byref(opts), C.byref(t), ptr(out), C.byref(st)),
+              self.handle)
+        return out.tobytes(), st.as_dict()
 
     # ---- operators ------------------------------------------------------------------------------
     def extract_nodes(self, seq, translation_table, opts):

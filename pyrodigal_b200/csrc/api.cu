@@ -18,26 +18,9 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "train_host.hpp"  // RawTraining + host half of the training path
 
 using namespace pgpu;
-
-// ------------------------------------------------------------------------------------------------
-// raw training struct (vendor/Prodigal/training.h:29-51) -- layout only, values come from the caller
-// ------------------------------------------------------------------------------------------------
-struct RawTraining {
-    double gc;
-    int32_t trans_table, pad0;
-    double st_wt;
-    double bias[3];
-    double type_wt[3];
-    int32_t uses_sd, pad1;
-    double rbs_wt[28];
-    double ups_comp[32][4];
-    double mot_wt[4][4][4096];
-    double no_mot;
-    double gene_dc[4096];
-};
-static_assert(sizeof(RawTraining) == PGPU_TRAINING_SIZE, "training struct layout");
 
 // pinned host buffers for results: recycled through a small free list so that steady-state calls neither
 // allocate pinned memory nor zero-fill / re-copy result arrays.  Reference counted: results keep the pool alive
@@ -340,6 +323,12 @@ struct pgpu_batch {
 // ------------------------------------------------------------------------------------------------
 // one pipeline run over contigs [lo, hi)
 // ------------------------------------------------------------------------------------------------
+struct TrainRequest {
+    int tt = 11, force_nonsd = 0;
+    double st_wt = 4.35;
+    RawTraining *out = nullptr;
+};
+
 struct RunPlan {
     // what to run
     int stage = 3;            // 1: extraction only, 2: + scoring/overlap, 3: everything
@@ -347,7 +336,11 @@ struct RunPlan {
     int forced_model = -1;
     int forced_first_pass = 1;
     int forced_is_meta = 0;
+    TrainRequest *train = nullptr;  // pgpu_train: run the training pass on the (single) extraction
 };
+
+static int train_stage(pgpu_ctx *ctx, DevPool &pool, DevBatch &B, const ExtractInfo &X, RunOpts ro, int gc_count,
+                       const TrainRequest &R, pgpu_stats &S);
 
 struct OperatorOut {  // operator-level outputs (single contig)
     std::vector<int32_t> ndx, stop_val;
@@ -623,6 +616,8 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
 
     S.n_contigs += n; S.total_bp += atot; S.total_nodes += total_nodes; S.total_chain_nodes += total_cn;
     S.n_chains += n_chains; S.dp_steps += total_cn;
+
+    if (plan.train) return train_stage(ctx, pool, B, exts[0], ro, h_gc[0], *plan.train, S);
 
     if (plan.stage == 1) {
         if (op) {
@@ -915,6 +910,155 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     S.ms_final += ms(e_trace, e_final);
     S.ms_d2h += ms(e_final, e_d2h);
     S.ms_total_device += ms(e_h2d, e_final);
+    return PGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// training (GeneFinder._train, lib.pyx:5236-5279) on the extraction run_range has just prepared
+// ------------------------------------------------------------------------------------------------
+static int train_stage(pgpu_ctx *ctx, DevPool &pool, DevBatch &B, const ExtractInfo &X, RunOpts ro, int gc_count,
+                       const TrainRequest &R, pgpu_stats &S) {
+    namespace th = pgpu::train_host;
+    using namespace pgpu::train;
+    cudaStream_t st = ctx->stream;
+    const int nn = X.nn, slen = X.slen;
+    RawTraining &T = *R.out;
+    memset(&T, 0, sizeof(T));   // TrainingInfo.__init__ (lib.pyx:3960-4003)
+    T.gc = slen > 0 ? (double)gc_count / (double)slen : 0.0;
+    T.trans_table = R.tt; T.st_wt = R.st_wt; T.uses_sd = 1;
+    cudaEventRecord(ctx->ev[8], st);
+
+    // one model slot and one chain (chain-node offset 0) on the device
+    RawTraining *d_raw = pool.alloc<RawTraining>(1);
+    DevModel *d_model = pool.alloc<DevModel>(1);
+    std::vector<ChainInfo> chain(1);
+    memset(&chain[0], 0, sizeof(ChainInfo));
+    chain[0].first_pass = 1; chain[0].node_off = X.node_off; chain[0].nn = nn; chain[0].doff = X.doff; chain[0].slen = slen;
+    B.chains = pool.upload(chain);
+    B.ext_chains = nullptr; B.dcT = nullptr; B.n_models = 1;
+    const size_t n1 = std::max(nn, 1);
+    B.cscore = pool.alloc<double>(n1, true); B.sscore = pool.alloc<double>(n1, true);
+    B.rscore = pool.alloc<double>(n1, true); B.uscore = pool.alloc<double>(n1, true); B.tscore = pool.alloc<double>(n1, true);
+    B.opv = pool.alloc<double>(3 * n1, true); B.gcb = pool.alloc<double>(n1, true);
+    B.star_ptr = pool.alloc<int32_t>(3 * n1); B.rbs = pool.alloc<uint8_t>(2 * n1 + 16, true);
+    B.score = pool.alloc<double>(n1, true); B.traceb = pool.alloc<int32_t>(n1); B.ov_mark = pool.alloc<int8_t>(n1 + 16, true);
+    B.chain_ipath = pool.alloc<int32_t>(1); B.chain_score = pool.alloc<double>(1);
+    TrainView V;
+    memset(&V, 0, sizeof(V));
+    V.N.ndx = B.ndx + X.node_off; V.N.sv = B.stop_val + X.node_off; V.N.cls = B.cls + X.node_off; V.N.nn = nn; V.N.slen = slen;
+    V.node_off = X.node_off; V.cb = B.cbase;   // extraction 0
+    V.gp = pool.alloc<int8_t>((size_t)slen + 16);
+    V.gc_score = pool.alloc<double>(3 * n1, true); V.gc_bias = pool.alloc<int8_t>(n1 + 16, true);
+    V.term = pool.alloc<double>(n1, true);
+    V.cscore = B.cscore; V.rbs = B.rbs; V.upc = B.upc + X.node_off; V.umot = B.umot + X.node_off;
+    V.mot = pool.alloc<MotifOut>(n1, true);
+    const int icap = nn / 2 + 2;
+    int4 *d_iv = pool.alloc<int4>(icap);
+    int *d_niv = pool.alloc<int>(1, true);
+    double *d_bias = pool.alloc<double>(4, true);
+    uint32_t *d_dc = pool.alloc<uint32_t>(2 * 4096, true);             // background | genes
+    unsigned long long *d_gene_total = pool.alloc<unsigned long long>(1, true);
+    uint32_t *d_cnt = pool.alloc<uint32_t>(C_TOTAL, true);
+    uint32_t *d_cells = pool.alloc<uint32_t>(2 * (size_t)kMotCells);    // background | accepted
+    if (pool.failed) return PGPU_ENOMEM;
+
+    // the counting passes as a backend of train_host::run_training (which owns the schedule and the host math)
+    struct Gpu {
+        pgpu_ctx *ctx; cudaStream_t st; DevBatch &B; TrainView &V; const ExtractInfo &X; RunOpts ro;
+        RawTraining *d_raw; DevModel *d_model; DevModel hm;
+        int4 *d_iv; int *d_niv; int icap; double *d_bias; uint32_t *d_dc; unsigned long long *d_gene_total;
+        uint32_t *d_cnt, *d_cells;
+        // PGPU_TRAIN_DUMP=<prefix>: write intermediate device arrays to <prefix>.<name>.bin (diagnostics for the
+        // GPU parity tests: tells which stage diverges from the oracle first)
+        void dump(const char *name, const void *dptr, size_t bytes) {
+            const char *prefix = getenv("PGPU_TRAIN_DUMP");
+            if (!prefix || !bytes) return;
+            std::vector<char> h(bytes);
+            cudaMemcpyAsync(h.data(), dptr, bytes, cudaMemcpyDeviceToHost, st);
+            cudaStreamSynchronize(st);
+            FILE *f = fopen((std::string(prefix) + "." + name + ".bin").c_str(), "wb");
+            if (f) { fwrite(h.data(), 1, bytes, f); fclose(f); }
+        }
+        int err(cudaError_t e, const char *what) {
+            if (e == cudaSuccess) return 0;
+            ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+            return PGPU_ECUDA;
+        }
+        void upload_model(const RawTraining &T) {
+            prepare_model(T, hm, d_raw);
+            cudaMemcpyAsync(d_raw, &T, sizeof(T), cudaMemcpyHostToDevice, st);
+            cudaMemcpyAsync(d_model, &hm, sizeof(hm), cudaMemcpyHostToDevice, st);
+        }
+        int first_gene_set(const RawTraining &T, double *bias, uint32_t *dicodon, long long *gene_codons) {
+            const int nn = X.nn, slen = X.slen;
+            launch_gc_frame(B.gcbits + (X.doff >> 5), slen, V.gp, st);
+            launch_gc_bias(B, V, d_bias, B.gcb, st);
+            upload_model(T);
+            launch_overlap(B, d_model, 1, nn, ro, 0, st);        // first start of each frame, no scores yet
+            launch_dp(B, d_model, nullptr, 1, 0, 0, st);          // final == 0: GC frame bias is the only score
+            launch_training_path(B, V, d_iv, icap, d_niv, st);
+            launch_dicodon(B.digits + X.doff, slen, d_iv, d_niv, icap, d_dc, d_dc + 4096, d_gene_total, st);
+            ctx->launches += 10;
+            unsigned long long total = 0;
+            cudaMemcpyAsync(dicodon, d_dc, 2 * 4096 * 4, cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(&total, d_gene_total, 8, cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(bias, d_bias, 3 * 8, cudaMemcpyDeviceToHost, st);
+            cudaEventRecord(ctx->ev[9], st);
+            const int rc = err(cudaStreamSynchronize(st), "training: first gene set");
+            *gene_codons = (long long)total;
+            if (!rc && getenv("PGPU_TRAIN_DUMP")) {
+                dump("gp", V.gp, (size_t)slen); dump("gc_score", V.gc_score, 24 * (size_t)nn);
+                dump("gc_bias", V.gc_bias, (size_t)nn); dump("gcb", B.gcb, 8 * (size_t)nn);
+                dump("star_ptr", B.star_ptr, 12 * (size_t)nn); dump("score", B.score, 8 * (size_t)nn);
+                dump("traceb", B.traceb, 4 * (size_t)nn); dump("ipath", B.chain_ipath, 4);
+                dump("n_intervals", d_niv, 4); dump("dicodon", d_dc, 2 * 4096 * 4);
+                dump("ndx", V.N.ndx, 4 * (size_t)nn); dump("cls", V.N.cls, (size_t)nn);
+            }
+            return rc;
+        }
+        int score_starts(const RawTraining &T, uint32_t *cnt) {
+            upload_model(T);
+            launch_coding(B, d_model, 1, X.nn, 1, X.nn, st);
+            launch_start_score(B, d_model, 1, X.nn, ro, nullptr, st);   // rbs[2] of every non-edge start
+            cudaMemsetAsync(d_cnt, 0, C_TOTAL * 4, st);
+            launch_type_background(V, d_cnt, st);
+            ctx->launches += 3;
+            cudaMemcpyAsync(cnt, d_cnt, C_TOTAL * 4, cudaMemcpyDeviceToHost, st);
+            const int rc = err(cudaStreamSynchronize(st), "training: start scores");
+            if (!rc && getenv("PGPU_TRAIN_DUMP")) { dump("cscore", B.cscore, 8 * (size_t)X.nn); dump("rbs", B.rbs, 2 * (size_t)X.nn); }
+            return rc;
+        }
+        int sd_iteration(const SdParams &P, uint32_t *cnt) {
+            cudaMemsetAsync(d_cnt, 0, C_TOTAL * 4, st);
+            launch_sd_iteration(B, V, P, d_cnt, st);
+            ctx->launches++;
+            cudaMemcpyAsync(cnt, d_cnt, C_TOTAL * 4, cudaMemcpyDeviceToHost, st);
+            return err(cudaStreamSynchronize(st), "training: SD iteration");
+        }
+        int motif_iteration(const MotParams &P, const RawTraining &T, uint32_t *cells, uint32_t *cnt) {
+            double *d_mot_wt = &d_raw->mot_wt[0][0][0];
+            cudaMemcpyAsync(d_mot_wt, &T.mot_wt[0][0][0], sizeof(T.mot_wt), cudaMemcpyHostToDevice, st);
+            cudaMemsetAsync(d_cnt, 0, C_TOTAL * 4, st);
+            cudaMemsetAsync(d_cells, 0, 2 * (size_t)kMotCells * 4, st);
+            launch_motif_iteration(B, V, d_mot_wt, P, d_cells, d_cells + kMotCells, d_cnt, st);
+            ctx->launches += 2;
+            cudaMemcpyAsync(cells, d_cells, 2 * (size_t)kMotCells * 4, cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(cnt, d_cnt, C_TOTAL * 4, cudaMemcpyDeviceToHost, st);
+            return err(cudaStreamSynchronize(st), "training: motif iteration");
+        }
+    } gpu{ctx, st, B, V, X, ro, d_raw, d_model, DevModel(), d_iv, d_niv, icap, d_bias, d_dc, d_gene_total, d_cnt, d_cells};
+    cudaEventRecord(ctx->ev[9], st);  // re-recorded after the first gene set
+    const int rc = th::run_training(gpu, T, nn, slen, R.force_nonsd);
+    if (rc) return rc;
+    cudaEventRecord(ctx->ev[10], st);
+    CK(cudaStreamSynchronize(st));
+    float t1 = 0, t2 = 0;
+    cudaEventElapsedTime(&t1, ctx->ev[8], ctx->ev[9]);
+    cudaEventElapsedTime(&t2, ctx->ev[9], ctx->ev[10]);
+    S.ms_dp += t1;       // frame plot + bias + training DP + dicodon counts
+    S.ms_score += t2;    // coding / SD scores + the start-training rounds
+    S.ms_total_device += t1 + t2;
+    S.n_chains = 1; S.total_chain_nodes = nn; S.dp_steps = nn;
     return PGPU_OK;
 }
 
@@ -1362,6 +1506,46 @@ int pgpu_score_connections(pgpu_ctx *ctx, int n, const int32_t *ndx, const int32
     CK(cudaStreamSynchronize(st));
     if (out_pairs) *out_pairs = (int64_t)pairs;
     if (out_ms) { float t = 0; cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]); *out_ms = t; }
+    return PGPU_OK;
+}
+
+/* GeneFinder.train (lib.pyx:5471-5575 / _train 5236-5279) */
+int pgpu_train(pgpu_ctx *ctx, const uint8_t *seq, int64_t slen, const pgpu_opts *opts, const pgpu_train_opts *topts,
+               void *out_training, pgpu_stats *stats) {
+    if (!ctx) return PGPU_EINVAL;
+    if (!opts || !topts || !out_training || (!seq && slen > 0)) return fail(ctx, PGPU_EINVAL, "bad arguments");
+    if (opts->meta) return fail(ctx, PGPU_ESTATE, "cannot use training sequence in metagenomic mode");
+    {   // _TRANSLATION_TABLES, lib.pyx:172
+        static const int valid[] = {1, 2, 3, 4, 5, 6, 9, 10, 11, 12, 13, 14, 15, 16, 21, 22, 23, 24, 25, 26, 29, 30, 32, 33};
+        bool ok = false;
+        for (int v : valid) ok |= v == topts->translation_table;
+        if (!ok) return fail(ctx, PGPU_EINVAL, std::to_string(topts->translation_table) + " is not a valid translation table index");
+    }
+    if (opts->min_gene <= 0) return fail(ctx, PGPU_EINVAL, "`min_gene` must be strictly positive");
+    if (opts->min_edge_gene <= 0) return fail(ctx, PGPU_EINVAL, "`min_edge_gene` must be strictly positive");
+    if (opts->max_overlap < 0) return fail(ctx, PGPU_EINVAL, "`max_overlap` must be positive");
+    if (slen < 20000)   // _MIN_SINGLE_GENOME, lib.pyx:170, 5547-5550
+        return fail(ctx, PGPU_EINVAL, "sequence must be at least 20000 characters (" + std::to_string(slen) + " found)");
+    if (slen > 0x7ffffff0) return fail(ctx, PGPU_EINVAL, "contig length out of range");
+    cudaSetDevice(ctx->device);
+    pgpu_result tmp;
+    tmp.pinned = ctx->pinned;
+    memset(&tmp.stats, 0, sizeof(tmp.stats));
+    tmp.summary.resize(1); tmp.gene_off.assign(2, 0); tmp.node_off.assign(2, 0);
+    std::vector<RawTraining> T(1);
+    TrainRequest req;
+    req.tt = topts->translation_table; req.force_nonsd = topts->force_nonsd; req.st_wt = topts->start_weight;
+    req.out = &T[0];
+    RunPlan plan;
+    plan.stage = 1;
+    plan.forced_tt = topts->translation_table;
+    plan.train = &req;
+    const int64_t offs[2] = {0, slen};
+    const int64_t launches0 = ctx->launches;
+    int rc = run_range(ctx, seq, nullptr, offs, 0, 1, *opts, plan, &tmp, nullptr);
+    if (rc) return rc;
+    memcpy(out_training, &T[0], sizeof(RawTraining));
+    if (stats) { *stats = tmp.stats; stats->kernel_launches = ctx->launches - launches0; }
     return PGPU_OK;
 }
 

@@ -1,6 +1,7 @@
 // kernels.cuh -- launch wrappers shared between the translation units of libpyrodigal_b200.so
 #pragma once
 #include "common.cuh"
+#include "train_device.cuh"
 
 namespace pgpu {
 
@@ -48,5 +49,30 @@ void launch_skippable(int n, const int8_t *strand, const uint8_t *type, const in
                       uint8_t *skip, cudaStream_t st);
 void launch_build_final_chains(const DevBatch &B, int n_contigs, const int32_t *winner_chain, const int64_t *fin_coff,
                                ChainInfo *fin_chains, cudaStream_t st);
+
+// train_kernels.cu -- the training pass works on ONE extraction (the training sequence) and ONE chain at
+// chain-node offset 0
+struct TrainView {
+    train::NodeArrays N;
+    int node_off;            // offset of the extraction's nodes (clist is indexed relative to it)
+    const int32_t *cb;       // its four class-segment offsets (DevBatch::cbase)
+    int8_t *gp;              // GC frame plot, one byte per base (-1 in the tail)
+    double *gc_score;        // [3 * nn]
+    int8_t *gc_bias;         // [nn]
+    double *term;            // [nn] addends of the bias sum
+    const double *cscore;    // [nn]
+    const uint8_t *rbs;      // [2 * nn]
+    const uint64_t *upc, *umot;
+    MotifOut *mot;           // [nn] best upstream motif under the current weights (non-SD training)
+};
+void launch_gc_frame(const uint32_t *gcbits, int slen, int8_t *gp, cudaStream_t st);
+void launch_gc_bias(const DevBatch &B, const TrainView &V, double *bias_out, double *gcb, cudaStream_t st);
+void launch_training_path(const DevBatch &B, const TrainView &V, int4 *intervals, int cap, int *n_out, cudaStream_t st);
+void launch_dicodon(const uint8_t *digits, int slen, const int4 *intervals, const int *n_intervals, int cap,
+                    uint32_t *bg_counts, uint32_t *gene_counts, unsigned long long *gene_total, cudaStream_t st);
+void launch_type_background(const TrainView &V, uint32_t *cnt, cudaStream_t st);
+void launch_sd_iteration(const DevBatch &B, const TrainView &V, const train::SdParams &P, uint32_t *cnt, cudaStream_t st);
+void launch_motif_iteration(const DevBatch &B, const TrainView &V, const double *mot_wt, const train::MotParams &P,
+                            uint32_t *bg_cells, uint32_t *real_cells, uint32_t *cnt, cudaStream_t st);
 
 }  // namespace pgpu

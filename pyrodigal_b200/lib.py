@@ -6,12 +6,14 @@ find_genes_many), Genes, Gene, Nodes, Node, Sequence, Mask(s), TrainingInfo, Met
 lib.ConnectionScorer.  All computation happens in libpyrodigal_b200.so on the GPU through the C ABI
 (include/pyrodigal_b200.h); this module only marshals buffers and formats results.
 """
+import itertools
 import json
 import lzma
 import math
 import os
 import threading
 import typing
+import warnings
 
 import numpy as np
 
@@ -186,6 +188,18 @@ def _context_for(model_blob, n_models, device=0):
                 _ctx_cache.pop(next(iter(_ctx_cache))).close()
             ctx = _capi.Context(device)
             ctx.set_models(model_blob, n_models, key)
+            ctx.lock = threading.Lock()
+            _ctx_cache[key] = ctx
+        return ctx
+
+
+def _training_context(device=0):
+    """training needs a device and a stream but no model set: one model-less context per device"""
+    key = (device, "train")
+    with _ctx_lock:
+        ctx = _ctx_cache.get(key)
+        if ctx is None:
+            ctx = _capi.Context(device)
             ctx.lock = threading.Lock()
             _ctx_cache[key] = ctx
         return ctx
@@ -615,8 +629,39 @@ class GeneFinder:
         return out
 
     def train(self, sequence, *sequences, force_nonsd=False, start_weight=4.35, translation_table=11):
-        """Training (lib.pyx:5471-5575) is outside the accelerated path: supply a
-        TrainingInfo (e.g. TrainingInfo.load of a Prodigal training file) to GeneFinder instead."""
+        """Search parameters for the ORF finder using a training sequence (lib.pyx:5471-5575).
+
+        Several sequences are treated as contigs of one genome and joined by ``TTAATTAATTAA`` linkers, like the
+        reference does.  The whole training pass (node extraction, GC frame bias, training DP, dicodon statistics,
+        SD / non-SD start training) runs on the GPU through ``pgpu_train``; the returned `TrainingInfo` is
+        byte-identical to the reference's and becomes ``self.training_info``."""
         if self.meta:
             raise RuntimeError("cannot use training sequence in metagenomic mode")
-        raise NotImplementedError("GeneFinder.train is not part of the B200 hot path; pass a TrainingInfo")
+        if translation_table not in TRANSLATION_TABLES:
+            raise ValueError(f"{translation_table} is not a valid translation table index")
+        if isinstance(sequence, Sequence):
+            if sequences:
+                raise NotImplementedError("cannot use more than one `Sequence` object in `GeneFinder.train`")
+            ascii_ = sequence._ascii
+        elif isinstance(sequence, str):
+            if sequences:
+                sequence = "TTAATTAATTAA".join(itertools.chain([sequence], sequences, [""]))
+            ascii_ = _as_ascii(sequence)
+        else:
+            if sequences:
+                sequence = b"TTAATTAATTAA".join(bytes(memoryview(x)) for x in itertools.chain([sequence], sequences, [b""]))
+            ascii_ = _as_ascii(sequence)
+        slen = len(ascii_)
+        if slen < MIN_SINGLE_GENOME:
+            raise ValueError(f"sequence must be at least {MIN_SINGLE_GENOME} characters ({slen} found)")
+        elif slen < IDEAL_SINGLE_GENOME:
+            warnings.warn(f"sequence should be at least {IDEAL_SINGLE_GENOME} characters ({slen} found)")
+        ctx = _training_context(self.device)
+        with ctx.lock:
+            blob, self.last_train_stats = ctx.train(np.ascontiguousarray(ascii_), self._opts(False),
+                                                    translation_table=translation_table, start_weight=start_weight,
+                                                    force_nonsd=force_nonsd)
+        tinf = TrainingInfo._from_bytes(blob)
+        with self.lock:
+            self.training_info = tinf
+        return tinf

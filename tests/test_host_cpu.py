@@ -102,3 +102,25 @@ def test_two_rank_gloo_sharding_and_reduction(tmp_path):
         d, gc, unk = orc.encode(s)
         genes += len(orc.find_genes_meta(d, gc / len(d), R.bins_blob())[0])
     assert int(line[1]) == int(off[-1]) and int(line[2]) == genes and float(line[3]) == 2.0 and int(line[4]) == 2
+
+
+def test_train_argument_errors_mirror_the_reference():
+    """lib.pyx:5522-5555: checked on the host, before any device work"""
+    import warnings
+    import pyrodigal_b200 as p
+    with pytest.raises(RuntimeError, match="metagenomic"):
+        p.GeneFinder(meta=True).train("A" * 30000)
+    with pytest.raises(ValueError, match="not a valid translation table"):
+        p.GeneFinder().train("A" * 30000, translation_table=7)
+    with pytest.raises(ValueError, match="at least 20000"):
+        p.GeneFinder().train("ACGT" * 100)
+    with pytest.raises(ValueError, match="at least 20000"):
+        p.GeneFinder().train(b"ACGT" * 100, b"ACGT" * 100)
+    with pytest.raises(NotImplementedError):
+        p.GeneFinder().train(p.Sequence("ACGT" * 6000), "ACGT")
+    import torch
+    if not torch.cuda.is_available():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            with pytest.raises(RuntimeError, match="no CPU fallback"):   # enough sequence: reaches pgpu_create
+                p.GeneFinder().train("ACGT" * 6000)
