@@ -475,6 +475,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     std::vector<int32_t> contig_chain_begin(n + 1, 0);
     std::vector<int32_t> contig_ext_begin(n + 1, 0);
     int64_t nwords = 0;
+    int total_chunks = 0;
     exts.reserve((size_t)n * 2);
     chains.reserve((size_t)n * (meta ? 16 : 1));
     for (int c = 0; c < n; c++) {
@@ -489,6 +490,9 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
             X.contig = c; X.tt = tt; X.doff = ci.doff; X.slen = ci.slen;
             X.slot = (int)exts.size() - contig_ext_begin[c];
             X.woff = nwords; X.nwords = ci.slen / 32 + 1;
+            X.chunk_off = total_chunks;
+            X.n_chunks = std::max(1, (ci.slen / 3 + kExtractChunkCodons - 1) / kExtractChunkCodons);
+            total_chunks += X.n_chunks;
             X.mask_off = ci.mask_off; X.n_masks = ci.n_masks;
             {   // codon masks per translation table, computed once
                 static thread_local uint64_t cache[34][2];
@@ -546,7 +550,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     int *d_total = pool.alloc<int>(1, true);
     if (pool.failed) return PGPU_ENOMEM;
     tev("plan+alloc");
-    launch_extract_mark(B, n_ext, ro, st);
+    launch_extract_mark(B, n_ext, total_chunks, ro, st);
     tev("k_extract mark");
     launch_word_scan(B, nwords, d_block_sums, d_total, st);
     tev("word scan");
@@ -603,7 +607,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     unsigned long long *d_ext_pairs = pool.alloc<unsigned long long>(n_ext, true);
     if (pool.failed) return PGPU_ENOMEM;
     tev("sync2+alloc");
-    launch_extract_fill(B, n_ext, ro, st);
+    launch_extract_fill(B, n_ext, total_chunks, ro, st);
     tev("k_extract fill");
     launch_node_prep(B, n_ext, total_nodes, 1, st);
     tev("k_node_prep+class_index");

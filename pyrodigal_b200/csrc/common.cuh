@@ -19,6 +19,7 @@ namespace pgpu {
 constexpr int kMaxNodeDist = 500;  // vendor/Prodigal/dprog.h:29
 constexpr int kMaxOppOvlp = 200;   // vendor/Prodigal/dprog.h:30
 constexpr int kOperDist = 60;      // src/Prodigal/node.h:33
+constexpr int kExtractChunkCodons = 2048;  // codons of one frame scanned by one warp of k_extract_w (64 ballots)
 #define PGPU_EDGE_BONUS 0.74       // node.h:34
 #define PGPU_EDGE_UPS (-1.00)      // node.h:35
 #define PGPU_META_PEN 7.5          // node.h:36
@@ -78,6 +79,8 @@ struct ExtractInfo {
     int32_t mask_off, n_masks;
     int32_t n_lo;        // number of nodes with ndx <= 4          (only these and the n_hi last ones can carry an
     int32_t n_hi;        // number of nodes with ndx >= slen - 5    edge flag; written by k_class_index)
+    int32_t chunk_off;   // first extraction chunk of this extraction (k_extract_w: one warp per chunk x strand x frame)
+    int32_t n_chunks;    // ceil(codons of the longest frame / kExtractChunkCodons), >= 1
     int32_t pad;
     uint64_t stopmask, startmask;
 };

@@ -184,19 +184,34 @@ __global__ void __launch_bounds__(128) k_extract(DevBatch B, int n_ext, RunOpts 
     if (saw) emit(last, 3, f - 6, !last_real);
 }
 
-// Warp-cooperative version of the same scan: one warp per (extraction, strand, frame) looks at 32 codons of
-// its frame per iteration.  The sequential state of the reference's loop (lib.pyx:1940-2010) depends only on
-// the nearest stop codon seen earlier in scan order and on "has a start been emitted since that stop", both
-// of which are bit operations on the ballot masks of the block (stops S, qualifying starts Q):
+// Warp-cooperative, chunked version of the same scan: one warp per (extraction, chunk, strand, frame) looks at
+// 32 codons of its frame per iteration.  The sequential state of the reference's loop (lib.pyx:1940-2010)
+// depends only on the nearest stop codon seen earlier in scan order and on "has a start been emitted since that
+// stop", both of which are bit operations on the ballot masks of the block (stops S, qualifying starts Q):
 //   lane k: earlier stops Sb = S & lt(k);  nearest = highest bit of Sb  -> last / min_dist / last_real
 //   stop lane k: saw = any Q bit strictly between the nearest earlier stop and k (or carried in)
 // so 32 codons cost a few dozen instructions instead of 32 dependent iterations.
+// Chunks: a frame is cut into runs of kExtractChunkCodons codons (scan order = descending strand coordinate).  The
+// state entering a chunk is fully determined by the stretch between the chunk and the nearest stop codon before
+// it in scan order, so a warp first looks back for that stop ("pre-roll", on average one or two ballots), replays
+// the codons between the stop and its chunk without emitting, and then owns every node whose *triggering* codon
+// lies inside the chunk (a start at its own codon; a STOP node at the next stop codon of the frame; the trailing
+// STOP node belongs to the last chunk).  One long contig therefore spreads over thousands of warps.
 template <bool FILL>
-__global__ void __launch_bounds__(128) k_extract_w(DevBatch B, int n_ext, RunOpts o) {
+__global__ void __launch_bounds__(128) k_extract_w(DevBatch B, int n_ext, int total_chunks, RunOpts o) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= n_ext * 6) return;
-    const int e = w / 6, sf = w % 6, rev = sf / 3, f = sf % 3;
+    if (w >= total_chunks * 6) return;
+    const int cidx = w / 6, sf = w % 6, rev = sf / 3, f = sf % 3;
+    int e = 0;
+    {   // extraction that owns chunk cidx (chunk_off is increasing)
+        int hi = n_ext - 1;
+        while (e < hi) {
+            const int mid = (e + hi + 1) >> 1;
+            if (B.exts[mid].chunk_off <= cidx) e = mid; else hi = mid - 1;
+        }
+    }
     const ExtractInfo X = B.exts[e];
+    const int chunk = cidx - X.chunk_off;
     const int slen = X.slen;
     if (slen < 3) return;
     const uint8_t *__restrict__ cod = B.cod + X.doff;
@@ -220,28 +235,56 @@ __global__ void __launch_bounds__(128) k_extract_w(DevBatch B, int n_ext, RunOpt
             B.cls[slot] = (uint8_t)(type | (rev ? CLS_REV : 0) | (edge ? CLS_EDGE : 0) | conv | ((p % 3) << CLS_FRAME_SHIFT));
         }
     };
+    // codon code at strand coordinate i (>= 0, <= slen - 3) and whether it holds an unknown base
+    auto codon = [&](int i, bool &has_n) {
+        int c = rev ? cod[slen - 3 - i] : cod[i];
+        has_n = c & 64;
+        c &= 63;
+        return rev ? rev_code(c) : c;
+    };
 
-    // incoming state (warp uniform)
+    int i_top0 = slen - 3;
+    i_top0 -= ((i_top0 % 3) - f + 3) % 3;                       // first codon of the frame in scan order
+    const bool bottom = chunk == X.n_chunks - 1;
+    const int hi_i = i_top0 - 3 * kExtractChunkCodons * chunk;    // first codon this chunk owns
+    const int lo_i = bottom ? 0 : hi_i - 3 * (kExtractChunkCodons - 1);
+
+    // state at the top of the frame (warp uniform): lib.pyx:1933-1939
     int last = slen + ((f - slen % 3 + 3) % 3);
     if (!o.closed)
         while (last + 3 > slen) last -= 3;
     bool last_real = false, saw = false;
     int min_dist = o.min_edge_gene;
-    int i_top = slen - 3;
-    i_top -= ((i_top % 3) - f + 3) % 3;
-    const uint32_t lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
+    int i_start = i_top0;
+    if (chunk > 0) {
+        // pre-roll: nearest stop codon before the chunk in scan order
+        for (int base = hi_i + 3; base <= i_top0; base += 96) {
+            const int i = base + 3 * lane;
+            bool st = false;
+            if (i >= 0 && i <= i_top0) {
+                bool has_n;
+                const int c = codon(i, has_n);
+                st = !has_n && ((X.stopmask >> c) & 1);
+            }
+            const uint32_t S = __ballot_sync(0xffffffffu, st);
+            if (S) {
+                last = base + 3 * (__ffs(S) - 1);
+                last_real = true;
+                min_dist = o.min_gene;
+                i_start = last - 3;
+                break;
+            }
+        }
+    }
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
-    for (; i_top >= 0; i_top -= 96) {
+    for (int i_top = i_start; i_top >= lo_i; i_top -= 96) {
         const int i = i_top - 3 * lane;
-        const bool valid = i >= 0;
+        const bool valid = i >= lo_i;
+        const bool own = i <= hi_i;   // nodes triggered above the chunk belong to the previous chunk
         int c = 0;
         bool has_n = true;
-        if (valid) {
-            c = rev ? cod[slen - 3 - i] : cod[i];
-            has_n = c & 64;
-            c &= 63;
-            if (rev) c = rev_code(c);
-        }
+        if (valid) c = codon(i, has_n);
         const bool is_stop = valid && !has_n && ((X.stopmask >> c) & 1);
         const bool is_startc = valid && !has_n && ((X.startmask >> c) & 1);
         const uint32_t S = __ballot_sync(0xffffffffu, is_stop);
@@ -264,8 +307,8 @@ __global__ void __launch_bounds__(128) k_extract_w(DevBatch B, int n_ext, RunOpt
         if (is_stop) {
             const uint32_t seg = lt_mask & ~(h >= 0 ? ((2u << h) - 1u) : 0u);
             const bool saw_here = (Q & seg) != 0 || (h < 0 && saw);
-            if (saw_here) emit(my_last, 3, i, !my_real);
-        } else if (qual) {
+            if (saw_here && own) emit(my_last, 3, i, !my_real);
+        } else if (qual && own) {
             if (q_start) { const int b0 = c & 3; emit(i, b0 == 0 ? 0 : (b0 == 1 ? 1 : 2), my_last, 0); }
             else emit(i, 0, my_last, 1);
         }
@@ -280,8 +323,7 @@ __global__ void __launch_bounds__(128) k_extract_w(DevBatch B, int n_ext, RunOpt
             saw = saw || Q != 0;
         }
     }
-    if (saw && lane == 0) emit(last, 3, f - 6, !last_real);
-    (void)le_mask;
+    if (bottom && saw && lane == 0) emit(last, 3, f - 6, !last_real);
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -414,11 +456,13 @@ void launch_find_masks(const DevBatch &B, const int2 *tiles, int n_tiles, int mi
                        int *count, cudaStream_t st) {
     if (n_tiles > 0) k_find_masks<<<n_tiles, 256, 0, st>>>(B, tiles, min_mask, out, cap, count);
 }
-void launch_extract_mark(const DevBatch &B, int n_ext, RunOpts o, cudaStream_t st) {
-    if (n_ext > 0) k_extract_w<false><<<(n_ext * 6 * 32 + 127) / 128, 128, 0, st>>>(B, n_ext, o);
+void launch_extract_mark(const DevBatch &B, int n_ext, int total_chunks, RunOpts o, cudaStream_t st) {
+    if (n_ext > 0 && total_chunks > 0)
+        k_extract_w<false><<<(unsigned)(((int64_t)total_chunks * 6 * 32 + 127) / 128), 128, 0, st>>>(B, n_ext, total_chunks, o);
 }
-void launch_extract_fill(const DevBatch &B, int n_ext, RunOpts o, cudaStream_t st) {
-    if (n_ext > 0) k_extract_w<true><<<(n_ext * 6 * 32 + 127) / 128, 128, 0, st>>>(B, n_ext, o);
+void launch_extract_fill(const DevBatch &B, int n_ext, int total_chunks, RunOpts o, cudaStream_t st) {
+    if (n_ext > 0 && total_chunks > 0)
+        k_extract_w<true><<<(unsigned)(((int64_t)total_chunks * 6 * 32 + 127) / 128), 128, 0, st>>>(B, n_ext, total_chunks, o);
 }
 int scan_num_blocks(int64_t nwords) { return (int)((nwords + 1 + kScanBlock - 1) / kScanBlock); }
 void launch_word_scan(const DevBatch &B, int64_t nwords, int *block_sums, int *total_out, cudaStream_t st) {

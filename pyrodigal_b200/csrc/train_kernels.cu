@@ -27,30 +27,38 @@ __global__ void __launch_bounds__(128) k_gc_bias(DevBatch B, TrainView V) {
     if (z >= 0) gc_bias_orf(z, V.N, V.gp, V.gc_score, V.gc_bias, V.term);
 }
 
-// bias[] is a floating point sum over the start nodes in index order (node.c:306-311): one warp streams the
-// addends coalesced and every lane performs the same sequential adds, so the result has the reference's rounding
+// bias[] is a floating point sum over the start nodes in index order (node.c:306-311), one accumulator per GC
+// frame: the warp stages 256 addends at a time in shared memory (coalesced), then lanes 0..2 each run through
+// them and add the ones of "their" frame in order -- three independent dependent-add chains with the reference's
+// rounding, reading from shared memory instead of shuffling every addend through the warp.
 __global__ void __launch_bounds__(32) k_bias_sum(TrainView V, double *bias_out) {
+    constexpr int kChunk = 256;
+    __shared__ double s_t[kChunk];
+    __shared__ int8_t s_g[kChunk];
+    __shared__ double s_b[3];
     const int lane = threadIdx.x;
-    double b0 = 0.0, b1 = 0.0, b2 = 0.0;
-    for (int base = 0; base < V.N.nn; base += 32) {
-        const int i = base + lane;
-        double t = 0.0;
-        int g = -1;
-        if (i < V.N.nn && !cls_is_stop(V.N.cls[i])) { t = V.term[i]; g = V.gc_bias[i]; }
-#pragma unroll 4
-        for (int k = 0; k < 32; k++) {
-            const double tk = __shfl_sync(0xffffffffu, t, k);
-            const int gk = __shfl_sync(0xffffffffu, g, k);
-            if (gk == 0) b0 += tk;
-            else if (gk == 1) b1 += tk;
-            else if (gk == 2) b2 += tk;
+    double acc = 0.0;
+    for (int base = 0; base < V.N.nn; base += kChunk) {
+        const int n = min(kChunk, V.N.nn - base);
+        for (int k = lane; k < n; k += 32) {
+            const int i = base + k;
+            const bool start = !cls_is_stop(V.N.cls[i]);
+            s_t[k] = start ? V.term[i] : 0.0;
+            s_g[k] = start ? V.gc_bias[i] : (int8_t)-1;
         }
+        __syncwarp();
+        if (lane < 3)
+            for (int k = 0; k < n; k++)
+                if (s_g[k] == lane) acc += s_t[k];
+        __syncwarp();
     }
+    if (lane < 3) s_b[lane] = acc;
+    __syncwarp();
     if (lane == 0) {
-        const double tot = b0 + b1 + b2;
-        bias_out[0] = b0 * (3.0 / tot);
-        bias_out[1] = b1 * (3.0 / tot);
-        bias_out[2] = b2 * (3.0 / tot);
+        const double tot = s_b[0] + s_b[1] + s_b[2];
+        bias_out[0] = s_b[0] * (3.0 / tot);
+        bias_out[1] = s_b[1] * (3.0 / tot);
+        bias_out[2] = s_b[2] * (3.0 / tot);
     }
 }
 
