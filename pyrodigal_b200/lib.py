@@ -6,11 +6,13 @@ find_genes_many), Genes, Gene, Nodes, Node, Sequence, Mask(s), TrainingInfo, Met
 lib.ConnectionScorer.  All computation happens in libpyrodigal_b200.so on the GPU through the C ABI
 (include/pyrodigal_b200.h); this module only marshals buffers and formats results.
 """
+import datetime
 import itertools
 import json
 import lzma
 import math
 import os
+import textwrap
 import threading
 import typing
 import warnings
@@ -35,6 +37,58 @@ _RBS_SPACER = [None, "3-4bp", "13-15bp", "13-15bp", "11-12bp", "3-4bp", "11-12bp
                "11-12bp", "3-4bp", "5-10bp", "3-4bp", "5-10bp", "11-12bp", "3-4bp", "5-10bp"]
 _NODE_TYPE = ["ATG", "GTG", "TTG", "Edge"]
 _LETTERS = "AGCTNNN"
+# the writers emit the reference's version tag so that their output is byte-identical to pyrodigal's
+# (lib.pyx:3485, 3595, 3605, 3826); `pyrodigal_b200.__version__` is this package's own version
+PYRODIGAL_COMPAT_VERSION = "3.7.1"
+
+# Genetic codes in NCBI order (first base T, C, A, G; then second, then third): the published NCBI tables
+# (https://www.ncbi.nlm.nih.gov/Taxonomy/Utils/wprintgc.cgi), written as differences from the standard code.
+_NCBI_STANDARD = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"
+_NCBI_CHANGES = {
+    1: {}, 11: {}, 2: {"AGA": "*", "AGG": "*", "ATA": "M", "TGA": "W"},
+    3: {"ATA": "M", "CTT": "T", "CTC": "T", "CTA": "T", "CTG": "T", "TGA": "W"},
+    4: {"TGA": "W"}, 5: {"AGA": "S", "AGG": "S", "ATA": "M", "TGA": "W"}, 6: {"TAA": "Q", "TAG": "Q"},
+    9: {"AAA": "N", "AGA": "S", "AGG": "S", "TGA": "W"}, 10: {"TGA": "C"}, 12: {"CTG": "S"},
+    13: {"AGA": "G", "AGG": "G", "ATA": "M", "TGA": "W"}, 14: {"AAA": "N", "AGA": "S", "AGG": "S", "TAA": "Y", "TGA": "W"},
+    15: {"TAG": "Q"}, 16: {"TAG": "L"}, 21: {"TGA": "W", "ATA": "M", "AGA": "S", "AGG": "S", "AAA": "N"},
+    22: {"TCA": "*", "TAG": "L"}, 23: {"TTA": "*"}, 24: {"AGA": "S", "AGG": "K", "TGA": "W"}, 25: {"TGA": "G"},
+    26: {"CTG": "A"}, 27: {"TAG": "Q", "TAA": "Q", "TGA": "W"}, 28: {"TAA": "Q", "TAG": "Q", "TGA": "W"},
+    29: {"TAA": "Y", "TAG": "Y"}, 30: {"TAA": "E", "TAG": "E"}, 31: {"TGA": "W", "TAG": "E", "TAA": "E"},
+    32: {"TAG": "W"}, 33: {"TAA": "Y", "TGA": "W", "AGA": "S", "AGG": "K"},
+}
+_DIGIT_OF = {"A": 0, "G": 1, "C": 2, "T": 3}
+
+
+def _translation_table(tt):
+    """64-entry amino acid table indexed by (x0 << 4) + (x1 << 2) + x2 over the digit alphabet A0 G1 C2 T3
+    (the indexing of _translation.h:37-40)"""
+    tab = _TT_CACHE.get(tt)
+    if tab is None:
+        code = {}
+        for k, aa in enumerate(_NCBI_STANDARD):
+            code["TCAG"[k >> 4] + "TCAG"[(k >> 2) & 3] + "TCAG"[k & 3]] = aa
+        code.update(_NCBI_CHANGES[tt])
+        tab = np.zeros(64, dtype=np.uint8)
+        for codon, aa in code.items():
+            tab[(_DIGIT_OF[codon[0]] << 4) + (_DIGIT_OF[codon[1]] << 2) + _DIGIT_OF[codon[2]]] = ord(aa)
+        _TT_CACHE[tt] = tab
+    return tab
+
+
+_TT_CACHE = {}
+# stop codons per table exactly as the reference lists them (lib.pyx:174-201; the listing is only used to decide
+# whether Gene.translate warns about a table with different stops, so its quirks -- e.g. table 6 -- are kept)
+_STOP_LISTING = {
+    1: ("TAA", "TAG", "TGA"), 2: ("TAA", "TAG", "AGA", "AGG"), 3: ("TAA", "TAG"), 4: ("TAA", "TAG"), 5: ("TAA", "TAG"),
+    6: ("TAA", "TAG", "TGA"), 9: ("TAA", "TAG"), 10: ("TAA", "TAG"), 11: ("TAA", "TAG", "TGA"), 12: ("TAA", "TAG", "TGA"),
+    13: ("TAA", "TAG"), 14: "TAG", 15: ("TAA", "TGA"), 16: ("TAA", "TGA"), 21: ("TAA", "TAG"), 22: ("TCA", "TAA", "TGA"),
+    23: ("TTA", "TAA", "TGA"), 24: ("TAA", "TAG"), 25: ("TAA", "TAG"), 26: ("TAA", "TAG", "TGA"), 27: (), 28: (),
+    29: "TGA", 30: "TGA", 31: (), 32: ("TAA", "TGA"), 33: "TAG",
+}
+
+
+def _stop_codons(tt):
+    return _STOP_LISTING[tt]
 
 # field offsets inside `struct _training` (vendor/Prodigal/training.h:29-51)
 _T_DTYPE = np.dtype(
@@ -353,6 +407,52 @@ class Nodes(typing.Sequence):
         self.array = state["array"]
 
 
+def _codon_masks(tt):
+    """(is_stop[64], is_start[64]) over the 6-bit codon index (x0 << 4) + (x1 << 2) + x2: the scanner rules of
+    _sequence.h:45-73 (starts) and 117-157 (stops)"""
+    m = _MASK_CACHE.get(tt)
+    if m is None:
+        A, G, C, T = 0, 1, 2, 3
+        taa = tt in (1, 2, 3, 4, 5, 9, 10, 11, 12, 13, 15, 16, 21, 22, 23, 24, 25, 26, 32)
+        tag = tt in (1, 2, 3, 4, 5, 9, 10, 11, 12, 13, 14, 21, 23, 24, 25, 26, 33)
+        tga = tt in (1, 6, 11, 12, 15, 16, 22, 23, 26, 29, 30, 32)
+        stop, start = np.zeros(64, dtype=bool), np.zeros(64, dtype=bool)
+        for x0 in range(4):
+            for x1 in range(4):
+                for x2 in range(4):
+                    k = (x0 << 4) + (x1 << 2) + x2
+                    if (x0, x1, x2) == (T, A, G):
+                        st = tag
+                    elif (x0, x1, x2) == (T, G, A):
+                        st = tga
+                    elif (x0, x1, x2) == (T, A, A):
+                        st = taa
+                    elif tt == 2:
+                        st = x0 == A and x1 == G and x2 in (A, G)
+                    elif tt == 22:
+                        st = (x0, x1, x2) == (T, C, A)
+                    elif tt == 23:
+                        st = (x0, x1, x2) == (T, T, A)
+                    else:
+                        st = False
+                    sa = False
+                    if x1 == T and x2 == G:
+                        if x0 == A:
+                            sa = True
+                        elif tt in (6, 10, 14, 15, 16, 2):
+                            sa = False
+                        elif x0 == G:
+                            sa = tt not in (1, 3, 12, 2)
+                        elif x0 == T:
+                            sa = not (tt < 4 or tt == 9 or 21 <= tt < 25)
+                    stop[k], start[k] = bool(st), bool(sa)
+        m = _MASK_CACHE[tt] = (stop, start)
+    return m
+
+
+_MASK_CACHE = {}
+
+
 # --- Genes ----------------------------------------------------------------------------------------------
 def calculate_confidence(score, start_weight):
     """vendor/Prodigal/gene.c:522-532"""
@@ -448,6 +548,54 @@ class Gene:
         seg = d[self.begin - 1:self.end][::-1]
         return "".join(_LETTERS[x ^ 3 if x < 4 else x] for x in seg)
 
+    def translate(self, translation_table=None, unknown_residue="X", include_stop=True, strict=True):
+        """Translate the predicted gene into a protein sequence (lib.pyx:2926-3047, _sequence.h:75-157)."""
+        owner_table = self.owner.training_info.translation_table
+        if translation_table is None:
+            tt = owner_table
+        elif translation_table not in _NCBI_CHANGES:
+            raise ValueError(f"{translation_table} is not a valid translation table index")
+        else:
+            if _stop_codons(translation_table) != _stop_codons(owner_table):
+                warnings.warn(
+                    f"requested translation table ({translation_table!r}) has different STOP codons "
+                    f"than the one these genes were called with ({owner_table!r}), consider calling "
+                    "genes with the proper translation table instead. This may become an error "
+                    "in the future.", stacklevel=2)
+            tt = translation_table
+        d = self.owner.sequence.digits
+        seg = d[self.begin - 1:self.end]
+        if self.strand != 1:
+            seg = seg[::-1] ^ 3          # the reference complements with xor 3 here, unknown bases included
+        start_edge, stop_edge = bool(self._start["edge"]), bool(self._stop["edge"])
+        ncod = len(seg) // 3
+        if not stop_edge and not include_stop:
+            ncod -= 1
+        if ncod <= 0:
+            return ""
+        cod = seg[:3 * ncod].reshape(ncod, 3).astype(np.int64)
+        known = (cod <= 3).all(axis=1)
+        tab = _translation_table(tt)
+        idx = np.where(known, (cod[:, 0] << 4) + (cod[:, 1] << 2) + cod[:, 2], 0)
+        unk = ord(unknown_residue) if isinstance(unknown_residue, str) else int(unknown_residue)
+        aa = np.where(known, tab[idx], unk).astype(np.uint8)
+        # the stop / start scanners of _sequence.h override the table: table-specific stops and the initial M
+        stop_m, start_m = _codon_masks(tt)
+        aa[known & stop_m[idx]] = ord("*")
+        if not start_edge and known[0] and start_m[idx[0]] and not stop_m[idx[0]]:
+            aa[0] = ord("M")
+        if not strict:
+            # third base unknown: translate when all four completions agree (_sequence.h:95-102); an unknown
+            # middle base never resolves in the reference (its loop at 104-111 does not advance), nor does the first
+            for k in np.flatnonzero(~known):
+                x0, x1, x2 = (int(v) for v in cod[k])
+                if x0 <= 3 and x1 <= 3 and x2 > 3:
+                    opts = {int(tab[(x0 << 4) + (x1 << 2) + b]) for b in range(4)}
+                    if len(opts) == 1:
+                        v = opts.pop()
+                        aa[k] = unk if v == ord("X") else v
+        return aa.tobytes().decode("ascii")
+
     def __repr__(self):
         return f"<pyrodigal_b200.Gene begin={self.begin} end={self.end} strand={self.strand:+}>"
 
@@ -493,6 +641,163 @@ class Genes(typing.Sequence):
 
     def __setstate__(self, state):
         self.__dict__.update(state)
+
+    # ---- writers (lib.pyx:3405-3895): host-side formatting of the records the GPU path returned ----
+    def _model(self):
+        """(training info, model description) used in headers; the reference falls back to bin #5 when meta mode
+        found no gene (lib.pyx:3583-3590)"""
+        tinf, mbin = self.training_info, self.metagenomic_bin
+        if self.meta:
+            if mbin is None:
+                mbin = _LazyBins.get()[5]
+            if tinf is None:
+                tinf = mbin.training_info
+            return tinf, mbin.description
+        return tinf, "Ab initio"
+
+    def write_gff(self, file, sequence_id, header=True, include_translation_table=False, full_id=True,
+                  version_separator="_v"):
+        """GFF3 (lib.pyx:3529-3645)"""
+        tinf, desc = self._model()
+        run = "Metagenomic" if self.meta else "Single"
+        n = 0
+        if header:
+            n += file.write("##gff-version  3\n")
+        n += file.write(f'# Sequence Data: seqnum={self._num_seq};seqlen={len(self.sequence)};seqhdr="{sequence_id}"\n')
+        n += file.write(f'# Model Data: version=pyrodigal.v{PYRODIGAL_COMPAT_VERSION};run_type={run};model="{desc}";'
+                        f"gc_cont={tinf.gc * 100:.2f};transl_table={tinf.translation_table};uses_sd={int(tinf.uses_sd)}\n")
+        for gene in self:
+            fields = [sequence_id, f"pyrodigal{version_separator}{PYRODIGAL_COMPAT_VERSION}", "CDS", str(gene.begin),
+                      str(gene.end), "{:.1f}".format(gene.sscore + gene.cscore), "+" if gene.strand > 0 else "-", "0"]
+            attr = gene._gene_data(sequence_id if full_id else self._num_seq) + ";"
+            if include_translation_table:
+                attr += f"transl_table={tinf.translation_table};"
+            n += file.write("\t".join(fields) + "\t" + attr + gene._score_data() + "\n")
+        return n
+
+    def _fasta_header(self, i, gene, sequence_id, full_id):
+        return ">{}_{} # {} # {} # {} # {}\n".format(sequence_id, i + 1, gene.begin, gene.end, gene.strand,
+                                                      gene._gene_data(sequence_id if full_id else self._num_seq))
+
+    def write_genes(self, file, sequence_id, width=70, full_id=False):
+        """nucleotide FASTA of the genes (lib.pyx:3647-3702)"""
+        n = 0
+        for i, gene in enumerate(self):
+            n += file.write(self._fasta_header(i, gene, sequence_id, full_id))
+            for line in textwrap.wrap(gene.sequence(), width=width):
+                n += file.write(line + "\n")
+        return n
+
+    def write_translations(self, file, sequence_id, width=60, translation_table=None, include_stop=True,
+                           strict_translation=True, full_id=False):
+        """protein FASTA (lib.pyx:3704-3781)"""
+        if translation_table is not None and translation_table not in TRANSLATION_TABLES:
+            raise ValueError(f"{translation_table} is not a valid translation table index")
+        n = 0
+        for i, gene in enumerate(self):
+            n += file.write(self._fasta_header(i, gene, sequence_id, full_id))
+            trans = gene.translate(translation_table, include_stop=include_stop, strict=strict_translation)
+            for line in textwrap.wrap(trans, width=width):
+                n += file.write(line + "\n")
+        return n
+
+    def write_genbank(self, file, sequence_id, division="BCT", date=None, translation_table=None, strict_translation=True):
+        """complete GenBank record (lib.pyx:3405-3527)"""
+        if translation_table is None:
+            if self.training_info is not None:
+                translation_table = self.training_info.translation_table
+        elif translation_table not in TRANSLATION_TABLES:
+            raise ValueError(f"{translation_table} is not a valid translation table index")
+        if date is None:
+            date = datetime.date.today()
+        elif not isinstance(date, datetime.date):
+            raise TypeError(f"Expected datetime.date, found {type(date).__name__}")
+        slen = len(self.sequence)
+        n = file.write("LOCUS       {:<23} {} bp    DNA     linear   {} {}\n".format(
+            sequence_id, slen, division, date.strftime("%d-%b-%y").upper()))
+        n += file.write(
+            f"REFERENCE   1  (bases 1 to {slen})\n"
+            "  AUTHORS   Hyatt,D., Chen,G-L., LoCascio,P.F., Land,M.L., Larimer,F.W.\n"
+            "            Hauser,L.J.\n"
+            "  TITLE     Prodigal: prokaryotic gene recognition and translation initiation\n"
+            "            site identification\n"
+            "  JOURNAL   BMC Bioinformatics. 2010;11:119.\n"
+            "   PUBMED   20211023\n"
+            f"REFERENCE   2  (bases 1 to {slen})\n"
+            "  AUTHORS   Larralde,M.\n"
+            "  TITLE     Pyrodigal: Python bindings and interface to Prodigal, an efficient\n"
+            "            method for gene prediction in prokaryotes\n"
+            "  JOURNAL   Journal of Open Source Software, 7(72), 4296.\n"
+            "FEATURES             Location/Qualifiers\n")
+        pad = " " * 21
+        for i, gene in enumerate(self):
+            begin = f"<{gene.begin}" if gene.start_node.edge else f"{gene.begin}"
+            end = f">{gene.end}" if gene.stop_node.edge else f"{gene.end}"
+            loc = f"{begin}..{end}" if gene.strand == 1 else f"complement({begin}..{end})"
+            n += file.write(f"     CDS             {loc}\n{pad}/codon_start=1\n"
+                            f'{pad}/inference="ab initio prediction:pyrodigal:{PYRODIGAL_COMPAT_VERSION}"\n'
+                            f'{pad}/locus_tag="{sequence_id}_{i + 1}"\n{pad}/transl_table={translation_table}\n')
+            translation = '/translation="{}"'.format(
+                gene.translate(translation_table=translation_table, include_stop=False, strict=strict_translation))
+            for block in textwrap.wrap(translation, 59):
+                n += file.write(pad + block + "\n")
+        seq = str(self.sequence).lower()
+        n += file.write("ORIGIN\n")
+        for i in range(0, len(seq), 60):
+            n += file.write("{:>9}".format(i + 1))
+            for j in range(i, min(i + 60, len(seq)), 10):
+                n += file.write(" " + seq[j:j + 10])
+            n += file.write("\n")
+        n += file.write("//\n")
+        return n
+
+    def write_scores(self, file, sequence_id, header=True):
+        """every potential start with its scores, grouped by stop codon (lib.pyx:3783-3895)"""
+        tinf = _LazyBins.get()[5].training_info if (self.meta and self.training_info is None) else self.training_info
+        n = 0
+        if header:
+            n += file.write(f'# Sequence Data: seqnum={self._num_seq};seqlen={len(self.sequence)};seqhdr="{sequence_id}"\n')
+            n += file.write(f"# Run Data: version=pyrodigal.v{PYRODIGAL_COMPAT_VERSION};gc_cont={tinf.gc * 100:.2f};"
+                            f"transl_table={tinf.translation_table};uses_sd={int(tinf.uses_sd)}\n")
+            n += file.write("Beg\tEnd\tStd\tTotal\tCodPot\tStrtSc\tCodon\tRBSMot\tSpacer\tRBSScr\tUpsScr\tTypeScr\tGCCont\n")
+        a = self.nodes.array
+        # stopcmp_nodes (vendor/Prodigal/node.c:1591-1602): stop position, forward strand first, then position
+        order = np.lexsort((a["ndx"], -a["strand"].astype(np.int64), a["stop_val"]))
+        st_wt, rbs_wt = tinf.start_weight, tinf.rbs_weights
+        prev = None
+        for k in order:
+            nd = a[k]
+            if nd["type"] == 3:
+                continue
+            key = (int(nd["stop_val"]), int(nd["strand"]))
+            if key != prev:
+                prev = key
+                n += file.write("\n")
+            if nd["strand"] == 1:
+                n += file.write(f"{int(nd['ndx']) + 1:d}\t{int(nd['stop_val']) + 3:d}\t+\t")
+            else:
+                n += file.write(f"{int(nd['stop_val']) - 1:d}\t{int(nd['ndx']) + 1:d}\t-\t")
+            cs, ss, rs = float(nd["cscore"]), float(nd["sscore"]), float(nd["rscore"])
+            n += file.write(f"{cs + ss:.2f}\t{cs:.2f}\t{ss:.2f}\t{_NODE_TYPE[3 if nd['edge'] else int(nd['type'])]}\t")
+            r0, r1 = int(nd["rbs"][0]), int(nd["rbs"][1])
+            rbs1, rbs2 = float(rbs_wt[r0]) * st_wt, float(rbs_wt[r1]) * st_wt
+            mot = float(nd["mot_score"]) * st_wt
+            if tinf.uses_sd:
+                pick = r0 if rbs1 > rbs2 else r1
+                n += file.write(f"{_RBS_MOTIF[pick]}\t{_RBS_SPACER[pick]}\t{rs:.2f}\t")
+            elif tinf.missing_motif_weight > -0.5 and rbs1 > rbs2 and rbs1 > mot:
+                n += file.write(f"{_RBS_MOTIF[r0]}\t{_RBS_SPACER[r0]}\t{rs:.2f}\t")
+            elif tinf.missing_motif_weight > -0.5 and rbs2 >= rbs1 and rbs2 > mot:
+                n += file.write(f"{_RBS_MOTIF[r1]}\t{_RBS_SPACER[r1]}\t{rs:.2f}\t")
+            elif int(nd["mot_len"]) == 0:
+                n += file.write(f"None\tNone\t{rs:.2f}\t")
+            else:
+                ndx, ln = int(nd["mot_ndx"]), int(nd["mot_len"])
+                word = "".join("AGCT"[(ndx >> (2 * i)) & 3] for i in range(ln))
+                n += file.write(f"{word}\t{int(nd['mot_spacer']):d}bp\t{rs:.2f}\t")
+            n += file.write(f"{float(nd['uscore']):.2f}\t{float(nd['tscore']):.2f}\t{float(nd['gc_cont']):.3f}\n")
+        n += file.write("\n")
+        return n
 
 
 # --- ConnectionScorer (operator-level surface, lib.pyx:1086-1432) -------------------------------------------
@@ -609,15 +914,22 @@ class GeneFinder:
     def find_genes_many(self, sequences, want_nodes=False):
         """Batched find_genes: one GPU pass over all the given contigs (the reference maps find_genes over
         records with a thread pool, cli.py:286-300; one contig cannot fill a B200)."""
-        if not self.meta and self.training_info is None:
-            raise RuntimeError("cannot find genes without having trained in single mode")
         arrays = [_as_ascii(s) for s in sequences]
         n = len(arrays)
         offsets = np.zeros(n + 1, dtype=np.int64)
         if n:
             np.cumsum([len(a) for a in arrays], out=offsets[1:])
         flat = np.concatenate(arrays) if n > 1 else (arrays[0] if n else np.zeros(0, np.uint8))
-        flat = np.ascontiguousarray(flat)
+        return self.find_genes_batch(flat, offsets, want_nodes=want_nodes, sequences=sequences)
+
+    def find_genes_batch(self, flat, offsets, want_nodes=False, sequences=None):
+        """find_genes over contigs that already sit back to back in one uint8 buffer (`fasta.read_batch`):
+        contig k is flat[offsets[k]:offsets[k + 1]].  This is the layout of the C ABI, passed through unchanged."""
+        if not self.meta and self.training_info is None:
+            raise RuntimeError("cannot find genes without having trained in single mode")
+        n = len(offsets) - 1
+        flat = np.ascontiguousarray(flat, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         with self.lock:
             first = self._num_seq
             self._num_seq += n
@@ -625,8 +937,9 @@ class GeneFinder:
         with ctx.lock:
             res = ctx.find_genes_batch(flat, offsets, self._opts(want_nodes))
         self.last_stats = res.stats
-        out = [self._wrap(res, k, sequences[k], want_nodes, first + k) for k in range(n)]
-        return out
+        if sequences is None:
+            sequences = [flat[offsets[k]:offsets[k + 1]] for k in range(n)]
+        return [self._wrap(res, k, sequences[k], want_nodes, first + k) for k in range(n)]
 
     def train(self, sequence, *sequences, force_nonsd=False, start_weight=4.35, translation_table=11):
         """Search parameters for the ORF finder using a training sequence (lib.pyx:5471-5575).

@@ -15,6 +15,9 @@ Fixtures (all small):
                     reference's own golden (tests/test_training_info.py:60-66, the 100 kb slice trained with
                     closed=True must equal GCF_..._100kb.tinf_closed.bin.gz) and the contig of
                     tests/test_gene_finder.py:329-345; plus Sequence.max_gc_frame_plot() of every case.
+  writer_cases.npz  the reference's command line (pyrodigal.cli.main) run on small FASTA inputs: GFF / GenBank, protein
+                    and nucleotide FASTA, score tables, and the training file it writes in single mode -- byte for byte
+                    what the drop-in CLI and writers must produce.
   misc.npz          node counts per translation table (tests/test_nodes.py:28-39), Shine-Dalgarno
                     known answers (tests/test_sequence.py:52-75).
 """
@@ -281,7 +284,60 @@ def train_cases():
     print("train_cases", len(names))
 
 
+def writer_cases():
+    import io
+    import tempfile
+    from pyrodigal import cli
+    out = {}
+    names = []
+    _, srr = R.read_fasta_gz(os.path.join(R.REF_DATA, "SRR492066.fna.gz"))[0]
+
+    def fasta_text(records, width=70):
+        lines = []
+        for name, seq in records:
+            lines.append(">" + name)
+            lines.extend(seq[i:i + width] for i in range(0, len(seq), width))
+        return "\n".join(lines) + "\n"
+
+    specs = [
+        ("srr_meta_gff", fasta_text([("SRR492066 test contig", srr)]), ["-p", "meta"]),
+        ("multi_meta_gbk", fasta_text([(f"ctg{k} synthetic", R.synth(L, gc, seed=600 + k, n_frac=nf).decode())
+                                       for k, (L, gc, nf) in enumerate([(9000, .4, 0), (700, .5, 0), (15000, .62, .002), (90, .5, 0)])]),
+         ["-p", "meta", "-f", "gbk", "-m", "--no-stop-codon"]),
+        ("multi_single_train", fasta_text([(f"chr{k}", R.synth(L, .5, seed=610 + k).decode()) for k, L in enumerate([30000, 12000, 8000])]),
+         ["-p", "single", "-c"]),
+        ("single_nonsd_tt4", fasta_text([("g", R.synth(40000, .38, seed=620).decode())]), ["-p", "single", "-n", "-g", "4"]),
+    ]
+    for name, text, argv in specs:
+        with tempfile.TemporaryDirectory() as tmp:
+            fa = os.path.join(tmp, "in.fna")
+            with open(fa, "w") as f:
+                f.write(text)
+            paths = {k: os.path.join(tmp, k) for k in ("o", "a", "d", "s", "t")}
+            full = ["-i", fa, "-o", paths["o"], "-a", paths["a"], "-d", paths["d"], "-s", paths["s"]] + argv
+            if "single" in argv:
+                full += ["-t", paths["t"]]
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                rc = cli.main(full, stdout=io.StringIO(), stderr=io.StringIO())
+            assert rc == 0
+            names.append(name)
+            out[name + "/fasta"] = np.frombuffer(text.encode(), dtype=np.uint8)
+            out[name + "/argv"] = np.array(argv, dtype=object)
+            for k in ("o", "a", "d", "s"):
+                out[f"{name}/{k}"] = np.frombuffer(open(paths[k], "rb").read(), dtype=np.uint8)
+            if os.path.exists(paths["t"]):
+                out[name + "/t"] = np.frombuffer(open(paths["t"], "rb").read(), dtype=np.uint8)
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "writer_cases.npz"), **out)
+    print("writer_cases", len(names))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "writers":
+        writer_cases()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "train":
         train_cases()
         sys.exit(0)
@@ -290,3 +346,4 @@ if __name__ == "__main__":
     dp_cases()
     misc()
     train_cases()
+    writer_cases()

@@ -116,3 +116,34 @@ def assert_nodes_equal(a, b, ints=INT_FIELDS, floats=FLOAT_FIELDS, tol=0.0, what
         if d.size and d.max() > tol:
             k = int(np.argmax(d))
             raise AssertionError(f"{what}: float field {f} differs at {k}: {x[k]!r} vs {y[k]!r} (tol {tol})")
+
+
+def genes_from_oracle(seq, meta=True, tinf_blob=None, closed=False, mask=False, num_seq=1):
+    """A pyrodigal_b200.Genes built from ORACLE results, for CPU tests of the host-side writers (the product fills
+    the same records from the GPU; this helper exists so that formatting can be tested where there is no GPU)."""
+    import pyrodigal_b200 as P
+    from oracle import oracle as orc
+    from pyrodigal_b200 import _capi, lib as L
+    if isinstance(seq, str):
+        seq = seq.encode()
+    d, gc, unk = orc.encode(seq)
+    masks = orc.find_masks(d, 50) if mask else None
+    opts = orc.make_opts(closed=closed, masks=masks)
+    if meta:
+        genes, nodes, winner, _ = orc.find_genes_meta(d, gc / len(d) if len(d) else 0.0, bins_blob(), opts)
+        mbin = P.METAGENOMIC_BINS[winner] if winner >= 0 else None
+        ti, ipath = (mbin.training_info if mbin else None), -1
+    else:
+        genes, nodes, ipath = orc.find_genes_single(d, tinf_blob, opts)
+        mbin, ti = None, L.TrainingInfo._from_bytes(tinf_blob)
+    a = np.zeros(len(nodes), dtype=_capi.NODE_DTYPE)
+    for f in _capi.NODE_DTYPE.names:
+        a[f] = nodes[f]
+    g = np.zeros(len(genes), dtype=_capi.GENE_DTYPE)
+    for f in ("begin", "end", "start_ndx", "stop_ndx"):
+        g[f] = genes[f]
+    gn = np.zeros((len(genes), 2), dtype=_capi.NODE_DTYPE)
+    if len(genes):
+        gn[:, 0], gn[:, 1] = a[g["start_ndx"]], a[g["stop_ndx"]]
+    return L.Genes(g, gn, sequence=L.Sequence(seq, mask=mask), training_info=ti, metagenomic_bin=mbin, meta=meta,
+                   nodes=L.Nodes(a), ipath=ipath, num_seq=num_seq)
