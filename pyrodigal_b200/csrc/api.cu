@@ -73,6 +73,7 @@ struct pgpu_ctx {
     std::vector<int> model_tt;
     RawTraining *d_raw = nullptr;
     DevModel *d_models = nullptr;
+    uint32_t *d_live = nullptr; // [n_models][2048] motif cells with a weight other than the floor (DevModel::mot_live)
     double *d_dcT = nullptr;   // dicodon weights transposed: [4096][n_models], columns sorted by (tt, gc)
     size_t ws_limit = 0;
     cudaEvent_t ev[16];
@@ -241,7 +242,15 @@ static void build_sd_masks() {
     g_sd_ready = true;
 }
 
-static void prepare_model(const RawTraining &r, DevModel &m, const RawTraining *d_raw_k) {
+// 1 bit per motif cell: weight != -4.0 (host side of DevModel::mot_live)
+static void motif_live_bits(const RawTraining &r, uint32_t *bits) {
+    const double *w = &r.mot_wt[0][0][0];
+    for (int k = 0; k < 2048; k++) bits[k] = 0;
+    for (int c = 0; c < 4 * 4 * 4096; c++)
+        if (!(w[c] == -4.0)) bits[c >> 5] |= 1u << (c & 31);
+}
+
+static void prepare_model(const RawTraining &r, DevModel &m, const RawTraining *d_raw_k, const uint32_t *d_live_k = nullptr) {
     memset(&m, 0, sizeof(m));
     m.st_wt = r.st_wt; m.gc = r.gc; m.no_mot = r.no_mot;
     for (int i = 0; i < 3; i++) { m.bias[i] = r.bias[i]; m.type_wt[i] = r.type_wt[i]; }
@@ -283,6 +292,7 @@ static void prepare_model(const RawTraining &r, DevModel &m, const RawTraining *
             }
     m.gene_dc = d_raw_k->gene_dc;
     m.mot_wt = &d_raw_k->mot_wt[0][0][0];
+    m.mot_live = d_live_k;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -414,6 +424,8 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     // no memset: k_encode writes every byte that is ever read (whole 16-byte groups, zero padded past the end)
     B.digits = pool.alloc<uint8_t>(dtot + 256);
     B.cod = pool.alloc<uint8_t>(dtot + 256);
+    B.dic_f = pool.alloc<uint16_t>(dtot + 256);
+    B.dic_r = pool.alloc<uint16_t>(dtot + 256);
     B.contigs = pool.upload(contigs);
     const int64_t gcwords = dtot / 32 + 8;
     B.gcbits = pool.alloc<uint32_t>(gcwords);
@@ -427,6 +439,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     tev("setup/alloc/memset");
     launch_encode(B, d_tiles, (int)tiles.size(), st);
     launch_gc_scan(B, dtot / 32, d_gc_bs, d_gc_tot, st);
+    if (plan.stage >= 2 || plan.train) { launch_dicodon_index(B, d_tiles, (int)tiles.size(), st); ctx->launches++; }
     ctx->launches += 3;
     tev("k_encode+gc scan");
     ctx->launches++;
@@ -606,6 +619,13 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     B.feq = pool.alloc<int32_t>(total_nodes);
     unsigned long long *d_ext_pairs = pool.alloc<unsigned long long>(n_ext, true);
     if (pool.failed) return PGPU_ENOMEM;
+    {
+        int32_t *tab = pool.alloc<int32_t>((size_t)total_nodes / 128 + 2);
+        if (pool.failed) return PGPU_ENOMEM;
+        launch_block_owner_exts(B.exts, n_ext, tab, st);
+        B.blk_ext = tab;
+        ctx->launches++;
+    }
     tev("sync2+alloc");
     launch_extract_fill(B, n_ext, total_chunks, ro, st);
     tev("k_extract fill");
@@ -683,6 +703,13 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     MotifOut *d_mot_main = (!meta) ? pool.alloc<MotifOut>(total_cn) : nullptr;
     if (pool.failed) return PGPU_ENOMEM;
     if (total_cn) CK(cudaMemsetAsync(d_tracef, 0xff, total_cn * sizeof(int32_t), st));
+    {
+        int32_t *tab = pool.alloc<int32_t>((size_t)total_cn / 128 + 2);
+        if (pool.failed) return PGPU_ENOMEM;
+        launch_block_owner_chains(B.chains, n_chains, tab, st);
+        B.blk_chain = tab;
+        ctx->launches++;
+    }
     tev("chain alloc/upload");
     launch_coding(B, ctx->d_models, n_chains, total_cn, n_ext, total_nodes, st);
     tev("k_coding_orf");
@@ -805,6 +832,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         int64_t *d_fin_coff = pool.upload(fin_coff);
         const int64_t ftot = fin_coff[n];
         F.chains = d_fin;
+        F.blk_chain = nullptr;   // the final pass has its own chain-node index space
         F.cscore = pool.alloc<double>(ftot); F.sscore = pool.alloc<double>(ftot); F.rscore = pool.alloc<double>(ftot);
         F.uscore = pool.alloc<double>(ftot); F.tscore = pool.alloc<double>(ftot);
         F.rbs = pool.alloc<uint8_t>(2 * (size_t)ftot + 16);
@@ -1193,6 +1221,7 @@ void pgpu_destroy(pgpu_ctx *ctx) {
     if (ctx->d_raw) cudaFree(ctx->d_raw);
     if (ctx->d_models) cudaFree(ctx->d_models);
     if (ctx->d_dcT) cudaFree(ctx->d_dcT);
+    if (ctx->d_live) cudaFree(ctx->d_live);
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1211,8 +1240,15 @@ int pgpu_set_models(pgpu_ctx *ctx, const void *blobs, int n, size_t stride) {
     for (int k = 0; k < n; k++) memcpy(&ctx->h_raw[k], (const char *)blobs + k * stride, sizeof(RawTraining));
     CK(cudaMalloc(&ctx->d_raw, n * sizeof(RawTraining)));
     CK(cudaMalloc(&ctx->d_models, n * sizeof(DevModel)));
+    if (ctx->d_live) { cudaFree(ctx->d_live); ctx->d_live = nullptr; }
+    CK(cudaMalloc(&ctx->d_live, (size_t)n * 2048 * sizeof(uint32_t)));
+    {
+        std::vector<uint32_t> live((size_t)n * 2048);
+        for (int k = 0; k < n; k++) motif_live_bits(ctx->h_raw[k], live.data() + (size_t)k * 2048);
+        CK(cudaMemcpy(ctx->d_live, live.data(), live.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
     ctx->h_models.resize(n);
-    for (int k = 0; k < n; k++) prepare_model(ctx->h_raw[k], ctx->h_models[k], ctx->d_raw + k);
+    for (int k = 0; k < n; k++) prepare_model(ctx->h_raw[k], ctx->h_models[k], ctx->d_raw + k, ctx->d_live + (size_t)k * 2048);
     {
         // transposed dicodon table: models that are evaluated together (same table, neighbouring GC) get
         // neighbouring columns, so the lanes of k_coding_orf read one or two cache lines per codon

@@ -54,6 +54,8 @@ struct DevModel {
     uint8_t sd_best[2][15][64];    // best SD bin for (exact|mismatch, offset, 6-bit match pattern)
     const double *gene_dc;         // device pointers into the raw blob
     const double *mot_wt;
+    const uint32_t *mot_live;      // bitmap over the 4*4*4096 motif cells: weight != -4.0 (the clamped floor, which is
+                                   // what all but a few dozen cells of a trained model hold); nullptr = always load
     int32_t col;                   // column of this model in the transposed dicodon table (sorted by tt, gc)
     int32_t pad;
 };
@@ -108,6 +110,8 @@ struct DevBatch {
     const uint8_t *ascii;
     uint8_t *digits;
     uint8_t *cod;
+    uint16_t *dic_f;      // per base: index of the forward 6-mer starting here = cod[p] | cod[p+3] << 6
+    uint16_t *dic_r;      // per base p: reverse-strand 6-mer whose first codon has its 5' base at p (N indexes as C)
     uint32_t *gcbits;     // 1 bit per base: not A / not T (unknown bases count as GC, _sequence.h:35-43)
     int32_t *gcpre;       // exclusive prefix of popcount(gcbits) per 32-base word
     ContigInfo *contigs;
@@ -158,6 +162,10 @@ struct DevBatch {
     int32_t *dp_tbig;     // merged-stream order: traceback node of a +STOP
     double *dp_fmv;       // k_dp_ml: suffix maxima of the far window (value), interleaved [entry][lane]
     int32_t *dp_fmj;      // k_dp_ml: ... and their nodes
+    // block -> owner tables (optional; nullptr = binary search): the chain that contains chain-node index 128*b and
+    // the extraction that contains node index 128*b, so that a thread block does not start with a serial search
+    const int32_t *blk_chain;
+    const int32_t *blk_ext;
     // per chain results
     int32_t *chain_ipath;
     double *chain_score;

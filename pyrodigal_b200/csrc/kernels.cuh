@@ -7,6 +7,7 @@ namespace pgpu {
 
 // seq_kernels.cu
 void launch_encode(const DevBatch &B, const int2 *tiles, int n_tiles, cudaStream_t st);
+void launch_dicodon_index(const DevBatch &B, const int2 *tiles, int n_tiles, cudaStream_t st);
 void launch_find_masks(const DevBatch &B, const int2 *tiles, int n_tiles, int min_mask, int4 *out, int cap,
                        int *count, cudaStream_t st);
 void launch_extract_mark(const DevBatch &B, int n_ext, int total_chunks, RunOpts o, cudaStream_t st);
@@ -16,6 +17,8 @@ void launch_gc_scan(const DevBatch &B, int64_t nwords, int *block_sums, int *tot
 void launch_word_scan(const DevBatch &B, int64_t nwords, int *block_sums, int *total_out, cudaStream_t st);
 
 // score_kernels.cu
+void launch_block_owner_chains(const ChainInfo *chains, int n, int32_t *tab, cudaStream_t st);
+void launch_block_owner_exts(const ExtractInfo *exts, int n, int32_t *tab, cudaStream_t st);
 void launch_node_prep(const DevBatch &B, int n_ext, int total_nodes, int seq_parts, cudaStream_t st);
 void launch_score_chains(const DevBatch &B, const DevModel *models, int n_chains, int64_t total_chain_nodes,
                          RunOpts o, void *mot_out, int n_ext, int total_nodes, cudaStream_t st);

@@ -37,6 +37,21 @@ __device__ __forceinline__ int find_ext(const ExtractInfo *__restrict__ ex, int 
     return lo;
 }
 
+// First candidate owner of flat index g: from the block table when the batch has one (one broadcast load), else by
+// binary search shared through the CTA.  Callers advance linearly from it (`while (next.off <= g) k++`).
+__device__ __forceinline__ int chain_hint(const DevBatch &B, int n_chains, int64_t g, int64_t total, int *s_first) {
+    if (B.blk_chain) return B.blk_chain[g >> 7];
+    if (threadIdx.x == 0) *s_first = find_chain(B.chains, n_chains, min((int64_t)blockIdx.x * blockDim.x, total - 1));
+    __syncthreads();
+    return *s_first;
+}
+__device__ __forceinline__ int ext_hint(const DevBatch &B, int n_ext, int g, int block_first, int total_nodes, int *s_first) {
+    if (B.blk_ext) return B.blk_ext[g >> 7];
+    if (threadIdx.x == 0) *s_first = find_ext(B.exts, n_ext, min(block_first, total_nodes - 1));
+    __syncthreads();
+    return *s_first;
+}
+
 // GC count of the three bases starting at p, from the codon code (N counts as GC: _sequence.h:35-43;
 // padding beyond the sequence end is 'A').
 __device__ __forceinline__ int gc3(int code) {
@@ -73,10 +88,8 @@ __device__ __forceinline__ int rcode_at(const uint8_t *__restrict__ d, const uin
 __global__ void __launch_bounds__(128) k_node_prep(DevBatch B, int n_ext, int total_nodes, int seq_parts) {
     __shared__ int s_first;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (threadIdx.x == 0) s_first = find_ext(B.exts, n_ext, min(blockIdx.x * blockDim.x, total_nodes - 1));
-    __syncthreads();
+    int e = ext_hint(B, n_ext, min(g, total_nodes - 1), blockIdx.x * blockDim.x, total_nodes, &s_first);
     if (g >= total_nodes) return;
-    int e = s_first;
     while (e + 1 < n_ext && B.exts[e + 1].node_off <= g) e++;
     const ExtractInfo X = B.exts[e];
     const int z = g - X.node_off, nn = X.nn, slen = X.slen;
@@ -205,10 +218,8 @@ __global__ void __launch_bounds__(128) k_coding(DevBatch B, const DevModel *__re
                                                  int64_t total) {
     __shared__ int s_first;
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (threadIdx.x == 0) s_first = find_chain(B.chains, n_chains, min((int64_t)blockIdx.x * blockDim.x, total - 1));
-    __syncthreads();
+    int k = chain_hint(B, n_chains, min(g, total - 1), total, &s_first);
     if (g >= total) return;
-    int k = s_first;
     while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
     const ChainInfo C = B.chains[k];
     // the first (#STOP nodes) threads of a chain's index range take one STOP node each, through the
@@ -225,43 +236,46 @@ __global__ void __launch_bounds__(128) k_coding(DevBatch B, const DevModel *__re
     const double *__restrict__ dc = M.gene_dc;
     const int32_t *__restrict__ ndx = B.ndx + C.node_off;
     const int32_t *__restrict__ sv = B.stop_val + C.node_off;
-    const uint8_t *__restrict__ d = B.digits + C.doff;
-    const uint8_t *__restrict__ cod = B.cod + C.doff;
+    const uint16_t *__restrict__ dicf = B.dic_f + C.doff;
+    const uint16_t *__restrict__ dicr = B.dic_r + C.doff;
     double *__restrict__ cscore = B.cscore + C.coff;
     const int f = cls_frame(c), my = ndx[z], nn = C.nn;
     const bool rev = c & CLS_REV;
 
-    // sweep A: dicodon log-odds accumulated from the stop towards each start (lib.pyx:2149-2173)
+    // sweep A: dicodon log-odds accumulated from the stop towards each start (lib.pyx:2149-2173); the 6-mer index of
+    // every position is precomputed (k_dicodon_index), so a codon costs one 2-byte load and one weight load
     int far = -1, last = my;
     double acc = 0.0;
     if (!rev) {
-        int low = cod[my] & 63;
         for (int i = z - 1; i >= 0; i--) {
             int ci = cls[i];
             if ((ci & CLS_REV) || cls_frame(ci) != f) continue;
             if (cls_is_stop(ci)) break;
             const int ni = ndx[i];
-            for (int j = last - 3; j >= ni; j -= 3) {
-                int cj = cod[j] & 63;
-                acc += __ldg(&dc[cj | (low << 6)]);
-                low = cj;
+            int j = last - 3;
+            for (; j - 9 >= ni; j -= 12) {   // four independent loads in flight, adds in the reference's order
+                const double w0 = __ldg(&dc[dicf[j]]), w1 = __ldg(&dc[dicf[j - 3]]), w2 = __ldg(&dc[dicf[j - 6]]),
+                             w3 = __ldg(&dc[dicf[j - 9]]);
+                acc += w0; acc += w1; acc += w2; acc += w3;
             }
+            for (; j >= ni; j -= 3) acc += __ldg(&dc[dicf[j]]);
             cscore[i] = acc;
             last = ni;
             far = i;
         }
     } else {
-        int low = rcode_at(d, cod, my);
         for (int i = z + 1; i < nn; i++) {
             int ci = cls[i];
             if (!(ci & CLS_REV) || cls_frame(ci) != f) continue;
             if (cls_is_stop(ci)) break;
             const int ni = ndx[i];
-            for (int j = last + 3; j <= ni; j += 3) {
-                int cj = rcode_at(d, cod, j);
-                acc += __ldg(&dc[cj | (low << 6)]);
-                low = cj;
+            int j = last + 3;
+            for (; j + 9 <= ni; j += 12) {
+                const double w0 = __ldg(&dc[dicr[j]]), w1 = __ldg(&dc[dicr[j + 3]]), w2 = __ldg(&dc[dicr[j + 6]]),
+                             w3 = __ldg(&dc[dicr[j + 9]]);
+                acc += w0; acc += w1; acc += w2; acc += w3;
             }
+            for (; j <= ni; j += 3) acc += __ldg(&dc[dicr[j]]);
             cscore[i] = acc;
             last = ni;
             far = i;
@@ -296,15 +310,13 @@ __global__ void __launch_bounds__(128) k_coding(DevBatch B, const DevModel *__re
 // --------------------------------------------------------------------------------------------------
 constexpr int kOrfWarps = 8;
 
-__global__ void __launch_bounds__(32 * kOrfWarps, 8) k_coding_orf(DevBatch B, const DevModel *__restrict__ models, int n_ext,
+__global__ void __launch_bounds__(32 * kOrfWarps, 5) k_coding_orf(DevBatch B, const DevModel *__restrict__ models, int n_ext,
                                                                 int total_nodes) {
     __shared__ int s_first;
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * kOrfWarps + (threadIdx.x >> 5);  // flat extraction-node index
-    if (threadIdx.x == 0) s_first = find_ext(B.exts, n_ext, min(blockIdx.x * kOrfWarps, total_nodes - 1));
-    __syncthreads();
+    int e = ext_hint(B, n_ext, min(t, total_nodes - 1), blockIdx.x * kOrfWarps, total_nodes, &s_first);
     if (t >= total_nodes) return;
-    int e = s_first;
     while (e + 1 < n_ext && B.exts[e + 1].node_off <= t) e++;
     const ExtractInfo X = B.exts[e];
     const int32_t *__restrict__ cbase = B.cbase + 4 * e;
@@ -315,8 +327,8 @@ __global__ void __launch_bounds__(32 * kOrfWarps, 8) k_coding_orf(DevBatch B, co
     const uint8_t *__restrict__ cls = B.cls + X.node_off;
     const int32_t *__restrict__ ndx = B.ndx + X.node_off;
     const int32_t *__restrict__ sv = B.stop_val + X.node_off;
-    const uint8_t *__restrict__ d = B.digits + X.doff;
-    const uint8_t *__restrict__ cod = B.cod + X.doff;
+    const uint16_t *__restrict__ dicf = B.dic_f + X.doff;
+    const uint16_t *__restrict__ dicr = B.dic_r + X.doff;
     const double *__restrict__ dcT = B.dcT;
     const int nm = B.n_models;
     const int c = cls[z], f = cls_frame(c), my = ndx[z];
@@ -335,52 +347,45 @@ __global__ void __launch_bounds__(32 * kOrfWarps, 8) k_coding_orf(DevBatch B, co
         int far = -1, last = my;
         double acc = 0.0;
         if (!rev) {
-            int low = cod[my] & 63;
             for (int i = z - 1; i >= 0; i--) {
                 const int ci = cls[i];
                 if ((ci & CLS_REV) || cls_frame(ci) != f) continue;
                 if (cls_is_stop(ci)) break;
                 const int ni = ndx[i];
-                // the chain (codon load -> weight load -> add) is latency bound: take 4 codons per round while at
-                // least 4 remain (their loads are independent and in flight together; adds keep the original order)
+                // the chain (index load -> weight load -> add) is latency bound: eight codons per round while at least
+                // eight remain (their loads are independent and in flight together; adds keep the original order)
                 int j = last - 3;
-                for (; j - 9 >= ni; j -= 12) {
-                    const int c0 = cod[j] & 63, c1 = cod[j - 3] & 63, c2 = cod[j - 6] & 63, c3 = cod[j - 9] & 63;
-                    const double w0 = dcT[(size_t)(c0 | (low << 6)) * nm + col], w1 = dcT[(size_t)(c1 | (c0 << 6)) * nm + col];
-                    const double w2 = dcT[(size_t)(c2 | (c1 << 6)) * nm + col], w3 = dcT[(size_t)(c3 | (c2 << 6)) * nm + col];
-                    acc += w0; acc += w1; acc += w2; acc += w3;
-                    low = c3;
+                for (; j - 21 >= ni; j -= 24) {
+                    const int i0 = dicf[j], i1 = dicf[j - 3], i2 = dicf[j - 6], i3 = dicf[j - 9];
+                    const int i4 = dicf[j - 12], i5 = dicf[j - 15], i6 = dicf[j - 18], i7 = dicf[j - 21];
+                    const double w0 = dcT[(size_t)i0 * nm + col], w1 = dcT[(size_t)i1 * nm + col];
+                    const double w2 = dcT[(size_t)i2 * nm + col], w3 = dcT[(size_t)i3 * nm + col];
+                    const double w4 = dcT[(size_t)i4 * nm + col], w5 = dcT[(size_t)i5 * nm + col];
+                    const double w6 = dcT[(size_t)i6 * nm + col], w7 = dcT[(size_t)i7 * nm + col];
+                    acc += w0; acc += w1; acc += w2; acc += w3; acc += w4; acc += w5; acc += w6; acc += w7;
                 }
-                for (; j >= ni; j -= 3) {
-                    const int cj = cod[j] & 63;
-                    acc += dcT[(size_t)(cj | (low << 6)) * nm + col];
-                    low = cj;
-                }
+                for (; j >= ni; j -= 3) acc += dcT[(size_t)dicf[j] * nm + col];
                 if (active) cscore[i] = acc;
                 last = ni;
                 far = i;
             }
         } else {
-            int low = rcode_at(d, cod, my);
             for (int i = z + 1; i < nn; i++) {
                 const int ci = cls[i];
                 if (!(ci & CLS_REV) || cls_frame(ci) != f) continue;
                 if (cls_is_stop(ci)) break;
                 const int ni = ndx[i];
                 int j = last + 3;
-                for (; j + 9 <= ni; j += 12) {
-                    const int c0 = rcode_at(d, cod, j), c1 = rcode_at(d, cod, j + 3), c2 = rcode_at(d, cod, j + 6),
-                              c3 = rcode_at(d, cod, j + 9);
-                    const double w0 = dcT[(size_t)(c0 | (low << 6)) * nm + col], w1 = dcT[(size_t)(c1 | (c0 << 6)) * nm + col];
-                    const double w2 = dcT[(size_t)(c2 | (c1 << 6)) * nm + col], w3 = dcT[(size_t)(c3 | (c2 << 6)) * nm + col];
-                    acc += w0; acc += w1; acc += w2; acc += w3;
-                    low = c3;
+                for (; j + 21 <= ni; j += 24) {
+                    const int i0 = dicr[j], i1 = dicr[j + 3], i2 = dicr[j + 6], i3 = dicr[j + 9];
+                    const int i4 = dicr[j + 12], i5 = dicr[j + 15], i6 = dicr[j + 18], i7 = dicr[j + 21];
+                    const double w0 = dcT[(size_t)i0 * nm + col], w1 = dcT[(size_t)i1 * nm + col];
+                    const double w2 = dcT[(size_t)i2 * nm + col], w3 = dcT[(size_t)i3 * nm + col];
+                    const double w4 = dcT[(size_t)i4 * nm + col], w5 = dcT[(size_t)i5 * nm + col];
+                    const double w6 = dcT[(size_t)i6 * nm + col], w7 = dcT[(size_t)i7 * nm + col];
+                    acc += w0; acc += w1; acc += w2; acc += w3; acc += w4; acc += w5; acc += w6; acc += w7;
                 }
-                for (; j <= ni; j += 3) {
-                    const int cj = rcode_at(d, cod, j);
-                    acc += dcT[(size_t)(cj | (low << 6)) * nm + col];
-                    low = cj;
-                }
+                for (; j <= ni; j += 3) acc += dcT[(size_t)dicr[j] * nm + col];
                 if (active) cscore[i] = acc;
                 last = ni;
                 far = i;
@@ -416,10 +421,8 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
                                                       int64_t total, RunOpts o, MotifOut *__restrict__ mot_out) {
     __shared__ int s_first;
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (threadIdx.x == 0) s_first = find_chain(B.chains, n_chains, min((int64_t)blockIdx.x * blockDim.x, total - 1));
-    __syncthreads();
+    int k = chain_hint(B, n_chains, min(g, total - 1), total, &s_first);
     if (g >= total) return;
-    int k = s_first;
     while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
     const ChainInfo C = B.chains[k];
     const int i = (int)(g - C.coff);
@@ -473,6 +476,7 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
             int max_spacer = 0, max_spacendx = 0, max_len = 0, max_ndx = 0;
             double max_sc = -100.0;
             const double *__restrict__ mw = M.mot_wt;
+            const uint32_t *__restrict__ live = M.mot_live;  // all but a few dozen cells hold the floor weight -4.0
 #pragma unroll
             for (int l = 3; l >= 0; l--) {
                 const uint32_t lmask = (1u << (2 * (l + 3))) - 1u;
@@ -482,7 +486,9 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
                     if (j < 0) continue;
                     const int spacendx = p <= 2 ? 3 : (p <= 4 ? 2 : (p >= 11 ? 1 : 0));
                     const int index = (int)((U >> (2 * (3 - l + p))) & lmask);
-                    const double sc = __ldg(&mw[(l * 4 + spacendx) * 4096 + index]);
+                    const int cell = (l * 4 + spacendx) * 4096 + index;
+                    double sc = -4.0;
+                    if (!live || ((__ldg(&live[cell >> 5]) >> (cell & 31)) & 1u)) sc = __ldg(&mw[cell]);
                     if (sc > max_sc) {
                         max_sc = sc; max_spacendx = spacendx; max_spacer = start - j - l - 3;
                         max_ndx = index; max_len = l + 3;
@@ -644,10 +650,8 @@ __global__ void __launch_bounds__(128, 12) k_overlap(DevBatch B, const DevModel 
                                                   int64_t total, RunOpts o, int flag) {
     __shared__ int s_first;
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (threadIdx.x == 0) s_first = find_chain(B.chains, n_chains, min((int64_t)blockIdx.x * blockDim.x, total - 1));
-    __syncthreads();
+    int k = chain_hint(B, n_chains, min(g, total - 1), total, &s_first);
     if (g >= total) return;
-    int k = s_first;
     while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
     const ChainInfo C = B.chains[k];
     const int t = (int)(g - C.coff), nn = C.nn;
@@ -718,10 +722,8 @@ __global__ void __launch_bounds__(128, 12) k_overlap(DevBatch B, const DevModel 
 __global__ void __launch_bounds__(128) k_opv(DevBatch B, const DevModel *__restrict__ models, int n_chains, int64_t total) {
     __shared__ int s_first;
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (threadIdx.x == 0) s_first = find_chain(B.chains, n_chains, min((int64_t)blockIdx.x * blockDim.x, total - 1));
-    __syncthreads();
+    int k = chain_hint(B, n_chains, min(g, total - 1), total, &s_first);
     if (g >= total) return;
-    int k = s_first;
     while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
     const ChainInfo C = B.chains[k];
     const int i = (int)(g - C.coff);
@@ -741,12 +743,11 @@ __global__ void __launch_bounds__(128) k_opv(DevBatch B, const DevModel *__restr
 __global__ void __launch_bounds__(256) k_pairs(DevBatch B, int n_ext, int total_nodes, unsigned long long *ext_pairs) {
     __shared__ int s_first;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (threadIdx.x == 0) s_first = find_ext(B.exts, n_ext, min(blockIdx.x * blockDim.x, total_nodes - 1));
-    __syncthreads();
+    const int hint = ext_hint(B, n_ext, min(g, total_nodes - 1), blockIdx.x * blockDim.x, total_nodes, &s_first);
     int e = -1;
     unsigned long long v = 0;
     if (g < total_nodes) {
-        e = s_first;
+        e = hint;
         while (e + 1 < n_ext && B.exts[e + 1].node_off <= g) e++;
         v = (unsigned long long)((g - B.exts[e].node_off) - B.win_min[g]);
     }
@@ -764,6 +765,26 @@ __global__ void __launch_bounds__(256) k_pairs(DevBatch B, int n_ext, int total_
 // --------------------------------------------------------------------------------------------------
 // launch wrappers
 // --------------------------------------------------------------------------------------------------
+// block -> owner tables: owner k covers flat indices [off_k, off_k + nn_k); entry b is the owner of index 128*b
+__global__ void __launch_bounds__(128) k_block_owner_chains(const ChainInfo *__restrict__ chains, int n, int32_t *__restrict__ tab) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t a = chains[k].coff, e = a + chains[k].nn;
+    for (int64_t b = (a + 127) >> 7; (b << 7) < e; b++) tab[b] = k;
+}
+__global__ void __launch_bounds__(128) k_block_owner_exts(const ExtractInfo *__restrict__ exts, int n, int32_t *__restrict__ tab) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t a = exts[k].node_off, e = a + exts[k].nn;
+    for (int64_t b = (a + 127) >> 7; (b << 7) < e; b++) tab[b] = k;
+}
+void launch_block_owner_chains(const ChainInfo *chains, int n, int32_t *tab, cudaStream_t st) {
+    if (n > 0) k_block_owner_chains<<<(n + 127) / 128, 128, 0, st>>>(chains, n, tab);
+}
+void launch_block_owner_exts(const ExtractInfo *exts, int n, int32_t *tab, cudaStream_t st) {
+    if (n > 0) k_block_owner_exts<<<(n + 127) / 128, 128, 0, st>>>(exts, n, tab);
+}
+
 void launch_node_prep(const DevBatch &B, int n_ext, int total_nodes, int seq_parts, cudaStream_t st) {
     if (n_ext == 0) return;
     if (total_nodes > 0) k_node_prep<<<(total_nodes + 127) / 128, 128, 0, st>>>(B, n_ext, total_nodes, seq_parts);
@@ -827,10 +848,8 @@ __device__ __forceinline__ int lower_bound_ndx(const int32_t *__restrict__ a, in
 __global__ void __launch_bounds__(128) k_dp_index(DevBatch B, int n_ext, int total_nodes) {
     __shared__ int s_first;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (threadIdx.x == 0) s_first = find_ext(B.exts, n_ext, min(blockIdx.x * blockDim.x, total_nodes - 1));
-    __syncthreads();
+    int e = ext_hint(B, n_ext, min(g, total_nodes - 1), blockIdx.x * blockDim.x, total_nodes, &s_first);
     if (g >= total_nodes) return;
-    int e = s_first;
     while (e + 1 < n_ext && B.exts[e + 1].node_off <= g) e++;
     const ExtractInfo X = B.exts[e];
     const int p = g - X.node_off, nn = X.nn;  // p = class-ordered position

@@ -82,6 +82,36 @@ __global__ void __launch_bounds__(256) k_encode(DevBatch B, const int2 *__restri
     }
 }
 
+// Dicodon (6-mer) index of every position on both strands, so that the coding-score walk needs one 2-byte load per
+// codon and no dependency on the previous codon (_sequence.h:207-220: first base in the low bits, N indexes as C).
+//   forward  p: codons at p and p+3                       = cod[p] | cod[p+3] << 6
+//   reverse  p: reverse codon with its 5' base at p (bases p, p-1, p-2) and the one before it in reverse reading
+//               order (5' base at p-3)                     = rc(p) | rc(p-3) << 6
+__device__ __forceinline__ int rev_codon_at(const uint8_t *__restrict__ d, const uint8_t *__restrict__ cod, int p) {
+    const int c = cod[p - 2];
+    if (!(c & 64)) return rev_code(c & 63);
+    int r = 0;
+    for (int k = 0; k < 3; k++) {
+        const int b = d[p - k];
+        r |= (b == 6 ? 2 : (b ^ 3)) << (2 * k);
+    }
+    return r;
+}
+__global__ void __launch_bounds__(256) k_dicodon_index(DevBatch B, const int2 *__restrict__ tiles) {
+    const int2 tile = tiles[blockIdx.x];
+    const ContigInfo ci = B.contigs[tile.x];
+    const uint8_t *__restrict__ d = B.digits + ci.doff;
+    const uint8_t *__restrict__ cod = B.cod + ci.doff;
+    uint16_t *__restrict__ df = B.dic_f + ci.doff;
+    uint16_t *__restrict__ dr = B.dic_r + ci.doff;
+    for (int k = threadIdx.x; k < kTile; k += 256) {
+        const int p = tile.y + k;
+        if (p >= ci.slen) break;
+        df[p] = (uint16_t)((cod[p] & 63) | ((cod[p + 3] & 63) << 6));     // cod is zero padded past the end
+        dr[p] = p >= 5 ? (uint16_t)(rev_codon_at(d, cod, p) | (rev_codon_at(d, cod, p - 3) << 6)) : (uint16_t)0;
+    }
+}
+
 // runs of N: one thread per run start walks to the end of its run (lib.pyx:699-713)
 __global__ void k_find_masks(DevBatch B, const int2 *__restrict__ tiles, int min_mask, int4 *out, int cap,
                              int *count) {
@@ -451,6 +481,9 @@ void launch_gc_scan(const DevBatch &B, int64_t nwords, int *block_sums, int *tot
 }
 void launch_encode(const DevBatch &B, const int2 *tiles, int n_tiles, cudaStream_t st) {
     if (n_tiles > 0) k_encode<<<n_tiles, 256, 0, st>>>(B, tiles);
+}
+void launch_dicodon_index(const DevBatch &B, const int2 *tiles, int n_tiles, cudaStream_t st) {
+    if (n_tiles > 0) k_dicodon_index<<<n_tiles, 256, 0, st>>>(B, tiles);
 }
 void launch_find_masks(const DevBatch &B, const int2 *tiles, int n_tiles, int min_mask, int4 *out, int cap,
                        int *count, cudaStream_t st) {
