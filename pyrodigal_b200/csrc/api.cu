@@ -74,7 +74,7 @@ struct pgpu_ctx {
     RawTraining *d_raw = nullptr;
     DevModel *d_models = nullptr;
     uint32_t *d_live = nullptr; // [n_models][2048] motif cells with a weight other than the floor (DevModel::mot_live)
-    double *d_dcT = nullptr;   // dicodon weights transposed: [4096][n_models], columns sorted by (tt, gc)
+    double *d_dcT = nullptr;   // dicodon weights transposed: [4096][kDcCols], columns sorted by (tt, gc); null if n_models > kDcCols
     size_t ws_limit = 0;
     cudaEvent_t ev[16];
     int64_t launches = 0;
@@ -293,6 +293,13 @@ static void prepare_model(const RawTraining &r, DevModel &m, const RawTraining *
     m.gene_dc = d_raw_k->gene_dc;
     m.mot_wt = &d_raw_k->mot_wt[0][0][0];
     m.mot_live = d_live_k;
+    for (int l = 0; l < 4; l++) {
+        uint64_t f = 0;
+        for (int sp = 0; sp < 4; sp++)
+            for (int x = 0; x < 4096; x++)
+                if (!(r.mot_wt[l][sp][x] == -4.0)) f |= 1ull << (x & 63);
+        m.mot_pf[l] = d_live_k ? f : ~0ull;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1258,14 +1265,17 @@ int pgpu_set_models(pgpu_ctx *ctx, const void *blobs, int n, size_t stride) {
             const RawTraining &x = ctx->h_raw[a], &y = ctx->h_raw[b];
             return x.trans_table != y.trans_table ? x.trans_table < y.trans_table : x.gc < y.gc;
         });
-        std::vector<double> t((size_t)4096 * n);
-        for (int c = 0; c < n; c++) {
-            ctx->h_models[ord[c]].col = c;
-            for (int i = 0; i < 4096; i++) t[(size_t)i * n + c] = ctx->h_raw[ord[c]].gene_dc[i];
-        }
+        // rows are kDcCols wide (a compile-time stride: one multiply-add per weight address in the kernel); a model
+        // set with more columns than that runs the per-chain kernel k_coding instead (d_dcT stays null)
         if (ctx->d_dcT) { cudaFree(ctx->d_dcT); ctx->d_dcT = nullptr; }
-        CK(cudaMalloc(&ctx->d_dcT, t.size() * sizeof(double)));
-        CK(cudaMemcpy(ctx->d_dcT, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+        for (int c = 0; c < n; c++) ctx->h_models[ord[c]].col = c;
+        if (n <= kDcCols) {
+            std::vector<double> t((size_t)4096 * kDcCols, 0.0);
+            for (int c = 0; c < n; c++)
+                for (int i = 0; i < 4096; i++) t[(size_t)i * kDcCols + c] = ctx->h_raw[ord[c]].gene_dc[i];
+            CK(cudaMalloc(&ctx->d_dcT, t.size() * sizeof(double)));
+            CK(cudaMemcpy(ctx->d_dcT, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
     }
     CK(cudaMemcpy(ctx->d_raw, ctx->h_raw.data(), n * sizeof(RawTraining), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_models, ctx->h_models.data(), n * sizeof(DevModel), cudaMemcpyHostToDevice));

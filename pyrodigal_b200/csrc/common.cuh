@@ -19,6 +19,7 @@ namespace pgpu {
 constexpr int kMaxNodeDist = 500;  // vendor/Prodigal/dprog.h:29
 constexpr int kMaxOppOvlp = 200;   // vendor/Prodigal/dprog.h:30
 constexpr int kOperDist = 60;      // src/Prodigal/node.h:33
+constexpr int kDcCols = 64;        // row width of the transposed dicodon table (DevBatch::dcT): a power of two >= the 50 built-in models
 constexpr int kExtractChunkCodons = 2048;  // codons of one frame scanned by one warp of k_extract_w (64 ballots)
 #define PGPU_EDGE_BONUS 0.74       // node.h:34
 #define PGPU_EDGE_UPS (-1.00)      // node.h:35
@@ -56,6 +57,8 @@ struct DevModel {
     const double *mot_wt;
     const uint32_t *mot_live;      // bitmap over the 4*4*4096 motif cells: weight != -4.0 (the clamped floor, which is
                                    // what all but a few dozen cells of a trained model hold); nullptr = always load
+    uint64_t mot_pf[4];            // per motif length: bit (index & 63) set when any cell [len][*][index] is live; a
+                                   // register-only pre-filter in front of mot_live (exactness never depends on it)
     int32_t col;                   // column of this model in the transposed dicodon table (sorted by tt, gc)
     int32_t pad;
 };
@@ -141,7 +144,7 @@ struct DevBatch {
     int4 *dqx;            // per node: candidates / ranges in merged-stream positions (k_dp_index)
     int32_t *ext_chain_off;   // [n_ext + 1] chains that use an extraction ...
     int32_t *ext_chains;      // ... chain indices, grouped by extraction
-    const double *dcT;        // dicodon table transposed: dcT[index * n_models + DevModel.col]
+    const double *dcT;        // dicodon table transposed: dcT[index * kDcCols + DevModel.col]
     int32_t n_models;
     // chains
     ChainInfo *chains;

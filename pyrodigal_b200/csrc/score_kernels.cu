@@ -329,8 +329,6 @@ __global__ void __launch_bounds__(32 * kOrfWarps, 5) k_coding_orf(DevBatch B, co
     const int32_t *__restrict__ sv = B.stop_val + X.node_off;
     const uint16_t *__restrict__ dicf = B.dic_f + X.doff;
     const uint16_t *__restrict__ dicr = B.dic_r + X.doff;
-    const double *__restrict__ dcT = B.dcT;
-    const int nm = B.n_models;
     const int c = cls[z], f = cls_frame(c), my = ndx[z];
     const bool rev = c & CLS_REV;
     const int ch0 = B.ext_chain_off[e], nch = B.ext_chain_off[e + 1] - ch0;
@@ -340,10 +338,16 @@ __global__ void __launch_bounds__(32 * kOrfWarps, 5) k_coding_orf(DevBatch B, co
         const int chain = active ? B.ext_chains[ch0 + c0 + lane] : 0;
         const ChainInfo C = B.chains[active ? chain : B.ext_chains[ch0]];
         const DevModel &M = models[C.model];
-        const int col = M.col;
+        // this lane's column of the transposed table; a weight address is one 32x32->64 multiply-add from it
+        const char *__restrict__ wcol = (const char *)(B.dcT + M.col);
+        auto W = [&](uint32_t index) -> double {
+            return *(const double *)(wcol + (uint64_t)index * (uint64_t)(kDcCols * sizeof(double)));
+        };
         double *__restrict__ cscore = B.cscore + C.coff;
 
-        // sweep A: dicodon log-odds accumulated from the stop towards each start (lib.pyx:2149-2173)
+        // sweep A: dicodon log-odds accumulated from the stop towards each start (lib.pyx:2149-2173).  The chain
+        // (index load -> weight load -> add) is latency bound: eight codons per round while at least eight remain
+        // (their loads are independent and in flight together), then 4 / 2 / 1; adds keep the reference's order.
         int far = -1, last = my;
         double acc = 0.0;
         if (!rev) {
@@ -352,19 +356,27 @@ __global__ void __launch_bounds__(32 * kOrfWarps, 5) k_coding_orf(DevBatch B, co
                 if ((ci & CLS_REV) || cls_frame(ci) != f) continue;
                 if (cls_is_stop(ci)) break;
                 const int ni = ndx[i];
-                // the chain (index load -> weight load -> add) is latency bound: eight codons per round while at least
-                // eight remain (their loads are independent and in flight together; adds keep the original order)
-                int j = last - 3;
-                for (; j - 21 >= ni; j -= 24) {
-                    const int i0 = dicf[j], i1 = dicf[j - 3], i2 = dicf[j - 6], i3 = dicf[j - 9];
-                    const int i4 = dicf[j - 12], i5 = dicf[j - 15], i6 = dicf[j - 18], i7 = dicf[j - 21];
-                    const double w0 = dcT[(size_t)i0 * nm + col], w1 = dcT[(size_t)i1 * nm + col];
-                    const double w2 = dcT[(size_t)i2 * nm + col], w3 = dcT[(size_t)i3 * nm + col];
-                    const double w4 = dcT[(size_t)i4 * nm + col], w5 = dcT[(size_t)i5 * nm + col];
-                    const double w6 = dcT[(size_t)i6 * nm + col], w7 = dcT[(size_t)i7 * nm + col];
+                const uint16_t *__restrict__ q = dicf + (last - 3);  // codons q[0], q[-3], ... down to position ni
+                int rem = (last - ni) / 3;
+#pragma unroll 1
+                for (; rem >= 8; rem -= 8, q -= 24) {
+                    const uint32_t i0 = q[0], i1 = q[-3], i2 = q[-6], i3 = q[-9], i4 = q[-12], i5 = q[-15], i6 = q[-18], i7 = q[-21];
+                    const double w0 = W(i0), w1 = W(i1), w2 = W(i2), w3 = W(i3), w4 = W(i4), w5 = W(i5), w6 = W(i6), w7 = W(i7);
                     acc += w0; acc += w1; acc += w2; acc += w3; acc += w4; acc += w5; acc += w6; acc += w7;
                 }
-                for (; j >= ni; j -= 3) acc += dcT[(size_t)dicf[j] * nm + col];
+                if (rem & 4) {
+                    const uint32_t i0 = q[0], i1 = q[-3], i2 = q[-6], i3 = q[-9];
+                    const double w0 = W(i0), w1 = W(i1), w2 = W(i2), w3 = W(i3);
+                    acc += w0; acc += w1; acc += w2; acc += w3;
+                    q -= 12;
+                }
+                if (rem & 2) {
+                    const uint32_t i0 = q[0], i1 = q[-3];
+                    const double w0 = W(i0), w1 = W(i1);
+                    acc += w0; acc += w1;
+                    q -= 6;
+                }
+                if (rem & 1) acc += W(q[0]);
                 if (active) cscore[i] = acc;
                 last = ni;
                 far = i;
@@ -375,17 +387,27 @@ __global__ void __launch_bounds__(32 * kOrfWarps, 5) k_coding_orf(DevBatch B, co
                 if (!(ci & CLS_REV) || cls_frame(ci) != f) continue;
                 if (cls_is_stop(ci)) break;
                 const int ni = ndx[i];
-                int j = last + 3;
-                for (; j + 21 <= ni; j += 24) {
-                    const int i0 = dicr[j], i1 = dicr[j + 3], i2 = dicr[j + 6], i3 = dicr[j + 9];
-                    const int i4 = dicr[j + 12], i5 = dicr[j + 15], i6 = dicr[j + 18], i7 = dicr[j + 21];
-                    const double w0 = dcT[(size_t)i0 * nm + col], w1 = dcT[(size_t)i1 * nm + col];
-                    const double w2 = dcT[(size_t)i2 * nm + col], w3 = dcT[(size_t)i3 * nm + col];
-                    const double w4 = dcT[(size_t)i4 * nm + col], w5 = dcT[(size_t)i5 * nm + col];
-                    const double w6 = dcT[(size_t)i6 * nm + col], w7 = dcT[(size_t)i7 * nm + col];
+                const uint16_t *__restrict__ q = dicr + (last + 3);  // codons q[0], q[3], ... up to position ni
+                int rem = (ni - last) / 3;
+#pragma unroll 1
+                for (; rem >= 8; rem -= 8, q += 24) {
+                    const uint32_t i0 = q[0], i1 = q[3], i2 = q[6], i3 = q[9], i4 = q[12], i5 = q[15], i6 = q[18], i7 = q[21];
+                    const double w0 = W(i0), w1 = W(i1), w2 = W(i2), w3 = W(i3), w4 = W(i4), w5 = W(i5), w6 = W(i6), w7 = W(i7);
                     acc += w0; acc += w1; acc += w2; acc += w3; acc += w4; acc += w5; acc += w6; acc += w7;
                 }
-                for (; j <= ni; j += 3) acc += dcT[(size_t)dicr[j] * nm + col];
+                if (rem & 4) {
+                    const uint32_t i0 = q[0], i1 = q[3], i2 = q[6], i3 = q[9];
+                    const double w0 = W(i0), w1 = W(i1), w2 = W(i2), w3 = W(i3);
+                    acc += w0; acc += w1; acc += w2; acc += w3;
+                    q += 12;
+                }
+                if (rem & 2) {
+                    const uint32_t i0 = q[0], i1 = q[3];
+                    const double w0 = W(i0), w1 = W(i1);
+                    acc += w0; acc += w1;
+                    q += 6;
+                }
+                if (rem & 1) acc += W(q[0]);
                 if (active) cscore[i] = acc;
                 last = ni;
                 far = i;
@@ -477,15 +499,21 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
             double max_sc = -100.0;
             const double *__restrict__ mw = M.mot_wt;
             const uint32_t *__restrict__ live = M.mot_live;  // all but a few dozen cells hold the floor weight -4.0
+            // A cell that is not live holds exactly -4.0 and cannot replace a maximum that is already >= -4.0 (the
+            // comparison is a strict ">"), so once the first window has been taken only live cells matter; the
+            // per-length prefix filter M.mot_pf answers "possibly live" from registers for almost every window.
 #pragma unroll
             for (int l = 3; l >= 0; l--) {
                 const uint32_t lmask = (1u << (2 * (l + 3))) - 1u;
+                const uint64_t pf = M.mot_pf[l];
+                if (pf == 0 && max_sc >= -4.0) continue;
 #pragma unroll
                 for (int p = 0; p < 13; p++) {
                     const int j = start - 18 - l + p;
                     if (j < 0) continue;
                     const int spacendx = p <= 2 ? 3 : (p <= 4 ? 2 : (p >= 11 ? 1 : 0));
                     const int index = (int)((U >> (2 * (3 - l + p))) & lmask);
+                    if (!((pf >> (index & 63)) & 1ull) && max_sc >= -4.0) continue;
                     const int cell = (l * 4 + spacendx) * 4096 + index;
                     double sc = -4.0;
                     if (!live || ((__ldg(&live[cell >> 5]) >> (cell & 31)) & 1u)) sc = __ldg(&mw[cell]);
@@ -535,7 +563,13 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
             const int ncomp = min(2, start) + max(0, min(30, start - 14));
             uint64_t pc = pre_pc;
             int k = 0;
-            for (; k + 4 <= ncomp; k += 4, pc >>= 8) {  // 4 independent loads, adds in the reference's order
+            for (; k + 8 <= ncomp; k += 8, pc >>= 16) {  // 8 independent loads, adds in the reference's order
+                const double w0 = M.uc[k][pc & 3], w1 = M.uc[k + 1][(pc >> 2) & 3], w2 = M.uc[k + 2][(pc >> 4) & 3],
+                             w3 = M.uc[k + 3][(pc >> 6) & 3], w4 = M.uc[k + 4][(pc >> 8) & 3], w5 = M.uc[k + 5][(pc >> 10) & 3],
+                             w6 = M.uc[k + 6][(pc >> 12) & 3], w7 = M.uc[k + 7][(pc >> 14) & 3];
+                uscore += w0; uscore += w1; uscore += w2; uscore += w3; uscore += w4; uscore += w5; uscore += w6; uscore += w7;
+            }
+            for (; k + 4 <= ncomp; k += 4, pc >>= 8) {
                 const double w0 = M.uc[k][pc & 3], w1 = M.uc[k + 1][(pc >> 2) & 3], w2 = M.uc[k + 2][(pc >> 4) & 3],
                              w3 = M.uc[k + 3][(pc >> 6) & 3];
                 uscore += w0; uscore += w1; uscore += w2; uscore += w3;
