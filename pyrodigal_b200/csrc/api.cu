@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "codon_masks.hpp"
 #include "train_host.hpp"  // RawTraining + host half of the training path
 
 using namespace pgpu;
@@ -79,6 +80,8 @@ struct pgpu_ctx {
     cudaEvent_t ev[16];
     int64_t launches = 0;
     int dp_ml_minb = 6;        // k_dp_ml register budget: min CTAs/SM 5, 6 or 8 (PGPU_DP_ML_MINB)
+    int extract_algo = 2;      // 2: bit-parallel extraction (k_codon_bits + k_extract_b), 1: warp-cooperative k_extract_w
+                               // (PGPU_EXTRACT_ALGO; batches with N-run masks always use 1)
     bool dp_verify = false;    // PGPU_DP_VERIFY=1: run k_dp_dq after k_dp_ml and fail on any difference (self-check)
     int dp_algo = 5;           // 5: k_dp_ml for multi-model batches, k_dp_dq otherwise (default); 6: k_dp_ml always;
                                // 3/4: k_dp_dq, 1/2: k_dp_fast, 0: all-pairs k_dp (PGPU_DP_ALGO=n)
@@ -142,38 +145,6 @@ struct DevPool {
 // ------------------------------------------------------------------------------------------------
 // model preparation (host): everything that needs libm or is model-only
 // ------------------------------------------------------------------------------------------------
-
-// stop / start codon sets per translation table as bit masks over the 6-bit codon code
-// (code = b0 | b1<<2 | b2<<4, A0 G1 C2 T3).  Rules: src/pyrodigal/_sequence.h:45-73, 117-157.
-static void codon_masks(int tt, uint64_t *stopmask, uint64_t *startmask) {
-    auto in = [&](std::initializer_list<int> l) { for (int v : l) if (v == tt) return true; return false; };
-    const bool taa = in({1, 2, 3, 4, 5, 9, 10, 11, 12, 13, 15, 16, 21, 22, 23, 24, 25, 26, 32});
-    const bool tag = in({1, 2, 3, 4, 5, 9, 10, 11, 12, 13, 14, 21, 23, 24, 25, 26, 33});
-    const bool tga = in({1, 6, 11, 12, 15, 16, 22, 23, 26, 29, 30, 32});
-    uint64_t sm = 0, am = 0;
-    enum { A = 0, G = 1, C = 2, T = 3 };
-    for (int c = 0; c < 64; c++) {
-        const int x0 = c & 3, x1 = (c >> 2) & 3, x2 = (c >> 4) & 3;
-        bool stop = false;
-        if (x0 == T && x1 == A && x2 == G) stop = tag;
-        else if (x0 == T && x1 == G && x2 == A) stop = tga;
-        else if (x0 == T && x1 == A && x2 == A) stop = taa;
-        else if (tt == 2) stop = x0 == A && x1 == G && (x2 == A || x2 == G);
-        else if (tt == 22) stop = x0 == T && x1 == C && x2 == A;
-        else if (tt == 23) stop = x0 == T && x1 == T && x2 == A;
-        bool start = false;
-        if (x1 == T && x2 == G) {
-            if (x0 == A) start = true;
-            else if (in({6, 10, 14, 15, 16, 2})) start = false;
-            else if (x0 == G) start = !in({1, 3, 12, 2});
-            else if (x0 == T) start = !(tt < 4 || tt == 9 || (tt >= 21 && tt < 25));
-        }
-        if (stop) sm |= 1ull << c;
-        if (start) am |= 1ull << c;
-    }
-    *stopmask = sm;
-    *startmask = am;
-}
 
 // Model-independent part of the Shine-Dalgarno search: the set of motif bins the reference's two
 // enumerations (lib.pyx:827-888 exact, 928-977 one mismatch) can report for a window at offset `off`
@@ -496,6 +467,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     std::vector<int32_t> contig_ext_begin(n + 1, 0);
     int64_t nwords = 0;
     int total_chunks = 0;
+    int64_t cb_words = 0;   // codon bitmap words (bit-parallel extraction)
     exts.reserve((size_t)n * 2);
     chains.reserve((size_t)n * (meta ? 16 : 1));
     for (int c = 0; c < n; c++) {
@@ -513,6 +485,8 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
             X.chunk_off = total_chunks;
             X.n_chunks = std::max(1, (ci.slen / 3 + kExtractChunkCodons - 1) / kExtractChunkCodons);
             total_chunks += X.n_chunks;
+            X.cb_off = cb_words;
+            cb_words += (int64_t)6 * X.n_chunks * (kExtractChunkCodons / 32);
             X.mask_off = ci.mask_off; X.n_masks = ci.n_masks;
             {   // codon masks per translation table, computed once
                 static thread_local uint64_t cache[34][2];
@@ -569,8 +543,23 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     int *d_block_sums = pool.alloc<int>(scan_num_blocks(nwords) + 1);
     int *d_total = pool.alloc<int>(1, true);
     if (pool.failed) return PGPU_ENOMEM;
+    // bit-parallel extraction unless the batch has N-run masks (GeneFinder(mask=True)) or PGPU_EXTRACT_ALGO=1
+    bool extract_bits = ctx->extract_algo != 1;
+    for (const auto &X : exts) if (X.n_masks) { extract_bits = false; break; }
+    if (extract_bits) {
+        B.cb_stop = pool.alloc<uint32_t>(cb_words + 8);
+        B.cb_start = pool.alloc<uint32_t>(cb_words + 8);
+        if (pool.failed) return PGPU_ENOMEM;
+    }
     tev("plan+alloc");
-    launch_extract_mark(B, n_ext, total_chunks, ro, st);
+    if (extract_bits) {
+        launch_codon_bits(B, n_ext, total_chunks, st);
+        tev("k_codon_bits");
+        launch_extract_bits(B, n_ext, total_chunks, ro, false, st);
+        ctx->launches++;
+    } else {
+        launch_extract_mark(B, n_ext, total_chunks, ro, st);
+    }
     tev("k_extract mark");
     launch_word_scan(B, nwords, d_block_sums, d_total, st);
     tev("word scan");
@@ -634,7 +623,8 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         ctx->launches++;
     }
     tev("sync2+alloc");
-    launch_extract_fill(B, n_ext, total_chunks, ro, st);
+    if (extract_bits) launch_extract_bits(B, n_ext, total_chunks, ro, true, st);
+    else launch_extract_fill(B, n_ext, total_chunks, ro, st);
     tev("k_extract fill");
     launch_node_prep(B, n_ext, total_nodes, 1, st);
     tev("k_node_prep+class_index");
@@ -1211,6 +1201,7 @@ int pgpu_create(int device, pgpu_ctx **out) {
     if (const char *a = getenv("PGPU_DP_ALGO")) ctx->dp_algo = atoi(a);
     if (const char *a = getenv("PGPU_DP_VERIFY")) ctx->dp_verify = atoi(a) != 0;
     if (const char *a = getenv("PGPU_DP_ML_MINB")) ctx->dp_ml_minb = atoi(a);
+    if (const char *a = getenv("PGPU_EXTRACT_ALGO")) ctx->extract_algo = atoi(a);
     // keep freed blocks cached in the stream-ordered pool: sub-batches reuse them without going to the driver
     cudaMemPool_t mp;
     if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {

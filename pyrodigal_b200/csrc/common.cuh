@@ -87,6 +87,7 @@ struct ExtractInfo {
     int32_t chunk_off;   // first extraction chunk of this extraction (k_extract_w: one warp per chunk x strand x frame)
     int32_t n_chunks;    // ceil(codons of the longest frame / kExtractChunkCodons), >= 1
     int32_t pad;
+    int64_t cb_off;      // first word of this extraction's codon bitmaps: [strand*3+frame][n_chunks * kExtractChunkCodons/32]
     uint64_t stopmask, startmask;
 };
 
@@ -124,6 +125,7 @@ struct DevBatch {
     // extraction
     ExtractInfo *exts;
     uint32_t *bits_fwd, *bits_rev;  // node bitmaps (per extraction, word offset woff)
+    uint32_t *cb_stop, *cb_start;   // codon bitmaps in scan order (extract_device.cuh), per extraction at cb_off
     int32_t *wordbase;              // exclusive prefix of node counts per bitmap word
     // extraction nodes
     int32_t *ndx, *stop_val;

@@ -11,6 +11,8 @@ void launch_dicodon_index(const DevBatch &B, const int2 *tiles, int n_tiles, cud
 void launch_find_masks(const DevBatch &B, const int2 *tiles, int n_tiles, int min_mask, int4 *out, int cap,
                        int *count, cudaStream_t st);
 void launch_extract_mark(const DevBatch &B, int n_ext, int total_chunks, RunOpts o, cudaStream_t st);
+void launch_codon_bits(const DevBatch &B, int n_ext, int total_chunks, cudaStream_t st);
+void launch_extract_bits(const DevBatch &B, int n_ext, int total_chunks, RunOpts o, bool fill, cudaStream_t st);
 void launch_extract_fill(const DevBatch &B, int n_ext, int total_chunks, RunOpts o, cudaStream_t st);
 int scan_num_blocks(int64_t nwords);
 void launch_gc_scan(const DevBatch &B, int64_t nwords, int *block_sums, int *total_out, cudaStream_t st);

@@ -8,6 +8,7 @@
 // marks node positions in two bitmaps, a prefix sum over bitmap words then gives every node its final
 // rank in (ndx, strand) order, and a second scan writes the nodes straight into their sorted slots --
 // no sort pass and no per-node atomics.
+#include "extract_device.cuh"
 #include "kernels.cuh"
 
 namespace pgpu {
@@ -357,6 +358,110 @@ __global__ void __launch_bounds__(128) k_extract_w(DevBatch B, int n_ext, int to
 }
 
 // --------------------------------------------------------------------------------------------------
+// bit-parallel extraction (extract_device.cuh): k_codon_bits writes the stop / start-codon bitmaps of every
+// (extraction, strand, frame) in scan order, k_extract_b<FILL> then handles one word of 32 codons per THREAD.
+// Both use the chunk geometry of k_extract_w: one warp per (chunk of kExtractChunkCodons codons, strand, frame).
+// --------------------------------------------------------------------------------------------------
+constexpr int kChunkWords = kExtractChunkCodons / 32;
+
+__device__ __forceinline__ int chunk_owner(const ExtractInfo *__restrict__ exts, int n_ext, int cidx) {
+    int e = 0, hi = n_ext - 1;
+    while (e < hi) {
+        const int mid = (e + hi + 1) >> 1;
+        if (exts[mid].chunk_off <= cidx) e = mid; else hi = mid - 1;
+    }
+    return e;
+}
+
+__global__ void __launch_bounds__(128) k_codon_bits(DevBatch B, int n_ext, int total_chunks) {
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= total_chunks * 6) return;
+    const int cidx = wid / 6, sf = wid % 6, rev = sf / 3, f = sf % 3;
+    const ExtractInfo X = B.exts[chunk_owner(B.exts, n_ext, cidx)];
+    const int chunk = cidx - X.chunk_off, slen = X.slen;
+    if (slen < 3) return;
+    int i_top0, n_codons;
+    extract_frame_geometry(slen, f, &i_top0, &n_codons);
+    const uint8_t *__restrict__ cod = B.cod + X.doff;
+    const int64_t base = X.cb_off + (int64_t)sf * X.n_chunks * kChunkWords + (int64_t)chunk * kChunkWords;
+#pragma unroll 1
+    for (int r = 0; r < kChunkWords / 32; r++) {
+        const int w0 = chunk * kChunkWords + r * 32;
+        if (w0 * 32 >= n_codons) break;
+        uint32_t myS = 0, myC = 0;
+#pragma unroll 4
+        for (int k = 0; k < 32; k++) {
+            const int u = (w0 + k) * 32 + lane;
+            const int fl = u < n_codons ? codon_flags(cod, slen, rev != 0, i_top0 - 3 * u, X.stopmask, X.startmask) : 0;
+            const uint32_t S = __ballot_sync(0xffffffffu, fl & 1), C = __ballot_sync(0xffffffffu, fl & 2);
+            if (lane == k) { myS = S; myC = C; }
+        }
+        B.cb_stop[base + r * 32 + lane] = myS;
+        B.cb_start[base + r * 32 + lane] = myC;
+    }
+}
+
+template <bool FILL>
+struct BitEmit {
+    const DevBatch &B;
+    const ExtractInfo &X;
+    const uint8_t *cod;
+    RunOpts o;
+    bool rev;
+    __device__ __forceinline__ void put(int pos, int type, int sv, int edge) const {
+        const int slen = X.slen;
+        const int p = rev ? slen - 1 - pos : pos;
+        if (!FILL) {
+            atomicOr((rev ? B.bits_rev : B.bits_fwd) + X.woff + (p >> 5), 1u << (p & 31));
+        } else {
+            const uint32_t *__restrict__ bf = B.bits_fwd + X.woff;
+            const uint32_t *__restrict__ br = B.bits_rev + X.woff;
+            const int ww = p >> 5, b = p & 31;
+            const uint32_t lt = (1u << b) - 1u;
+            const int slot = (B.wordbase + X.woff)[ww] + __popc(bf[ww] & lt) + __popc(br[ww] & lt) + (rev ? (int)((bf[ww] >> b) & 1u) : 0);
+            const int conv = (!o.closed && type != 3 && !edge && (rev ? p >= slen - 3 : p <= 2)) ? CLS_CONV : 0;
+            B.ndx[slot] = p;
+            B.stop_val[slot] = rev ? slen - 1 - sv : sv;
+            B.cls[slot] = (uint8_t)(type | (rev ? CLS_REV : 0) | (edge ? CLS_EDGE : 0) | conv | ((p % 3) << CLS_FRAME_SHIFT));
+        }
+    }
+    __device__ __forceinline__ void start(int i, int last, int edge) const {
+        int type = 0;
+        if (FILL && !edge) {
+            const int c = rev ? rev_code(cod[X.slen - 3 - i] & 63) : (cod[i] & 63);
+            const int b0 = c & 3;
+            type = b0 == 0 ? 0 : (b0 == 1 ? 1 : 2);
+        }
+        put(i, type, last, edge);
+    }
+    __device__ __forceinline__ void stop(int last, int sv, int edge) const { put(last, 3, sv, edge); }
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_extract_b(DevBatch B, int n_ext, int total_chunks, RunOpts o) {
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= total_chunks * 6) return;
+    const int cidx = wid / 6, sf = wid % 6, rev = sf / 3, f = sf % 3;
+    const ExtractInfo X = B.exts[chunk_owner(B.exts, n_ext, cidx)];
+    const int chunk = cidx - X.chunk_off, slen = X.slen;
+    if (slen < 3) return;
+    ExtractFrame F;
+    extract_frame_geometry(slen, f, &F.i_top0, &F.n_codons);
+    F.n_words = (F.n_codons + 31) >> 5;
+    F.f = f; F.closed = o.closed;
+    F.d_real = extract_min_codons(o.min_gene); F.d_virt = extract_min_codons(o.min_edge_gene);
+    F.min_edge_gene = o.min_edge_gene;
+    const int64_t base = X.cb_off + (int64_t)sf * X.n_chunks * kChunkWords;
+    F.S = B.cb_stop + base; F.C = B.cb_start + base;
+    BitEmit<FILL> em{B, X, B.cod + X.doff, o, rev != 0};
+#pragma unroll 1
+    for (int r = 0; r < kChunkWords / 32; r++) {
+        const int w = chunk * kChunkWords + r * 32 + lane;
+        if (w < F.n_words) extract_word(F, w, em);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
 // exclusive prefix sum of per-word node counts (three-phase: block sums, top scan, apply)
 // --------------------------------------------------------------------------------------------------
 constexpr int kScanThreads = 256;
@@ -492,6 +597,16 @@ void launch_find_masks(const DevBatch &B, const int2 *tiles, int n_tiles, int mi
 void launch_extract_mark(const DevBatch &B, int n_ext, int total_chunks, RunOpts o, cudaStream_t st) {
     if (n_ext > 0 && total_chunks > 0)
         k_extract_w<false><<<(unsigned)(((int64_t)total_chunks * 6 * 32 + 127) / 128), 128, 0, st>>>(B, n_ext, total_chunks, o);
+}
+void launch_codon_bits(const DevBatch &B, int n_ext, int total_chunks, cudaStream_t st) {
+    if (n_ext > 0 && total_chunks > 0)
+        k_codon_bits<<<(unsigned)(((int64_t)total_chunks * 6 * 32 + 127) / 128), 128, 0, st>>>(B, n_ext, total_chunks);
+}
+void launch_extract_bits(const DevBatch &B, int n_ext, int total_chunks, RunOpts o, bool fill, cudaStream_t st) {
+    if (n_ext == 0 || total_chunks == 0) return;
+    const unsigned nb = (unsigned)(((int64_t)total_chunks * 6 * 32 + 127) / 128);
+    if (fill) k_extract_b<true><<<nb, 128, 0, st>>>(B, n_ext, total_chunks, o);
+    else k_extract_b<false><<<nb, 128, 0, st>>>(B, n_ext, total_chunks, o);
 }
 void launch_extract_fill(const DevBatch &B, int n_ext, int total_chunks, RunOpts o, cudaStream_t st) {
     if (n_ext > 0 && total_chunks > 0)
