@@ -94,40 +94,81 @@ class Dist:
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+    """SM clock and throttle reasons sampled every 200 ms DURING the timed region (B200_PROFILING.md's clocks line).
+    Read through NVML in this process (the library nvidia-smi itself queries): starting an `nvidia-smi` process per
+    sample initialises the driver API every time and was seen to delay the launches of the step being timed by tens
+    of ms.  Falls back to ONE `nvidia-smi -lms 200` process started before the region when pynvml is missing."""
+
+    REASONS = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.nvml, self.handle, self.proc, self.sm_max = None, None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: map the CUDA device through its UUID when CUDA_VISIBLE_DEVICES is set
+            try:
+                import torch
+                uuid = torch.cuda.get_device_properties(index).uuid
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def start(self):
+        if self.nvml is None:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                              "--format=csv,noheader,nounits", "-lms", "200"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                time.sleep(1.0)  # its start-up stays outside the timed region
+            except Exception:
+                self.proc = None
+            return
+        super().start()
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+        n = self.nvml
+        masks = (n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
+                 n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap)
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 7:
-                    self.rows.append(f)
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.rows.append((sm, self.sm_max, [name for name, m in zip(self.REASONS, masks) if r & m]))
             except Exception:
                 pass
             self._stop_evt.wait(0.2)
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=3)
+        if self.nvml is None:
+            if self.proc is not None:
+                self.proc.terminate()
+                try:
+                    out = self.proc.communicate(timeout=3)[0]
+                except Exception:
+                    out = ""
+                for line in out.strip().splitlines():
+                    f = [x.strip() for x in line.split(",")]
+                    if len(f) >= 6 and f[0].replace(".", "").isdigit():
+                        self.rows.append((float(f[0]), float(f[1]),
+                                          [nm for nm, v in zip(self.REASONS, f[2:6]) if v.lower().startswith("active")]))
+        else:
+            self._stop_evt.set()
+            self.join(timeout=3)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted({x for r in self.rows for x in r[2]})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons, "samples": len(self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi -lms 200"}
 
 
 def measured_peak():
@@ -249,7 +290,7 @@ def time_cpu(flat, offsets, steps, warmup, max_contigs):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--contigs", type=int, default=CONTIGS_PER_GPU, help="contigs per GPU (default = cfg4 shard)")
@@ -324,7 +365,7 @@ def main():
         r = None  # at most two results alive at a time: their pinned buffers are recycled by the library
         r = batch.run(opts)
     r = None
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     if rank == 0:
         sampler.start()
     ms, wall_ms, res = timed(lambda: batch.run(opts), args.steps)

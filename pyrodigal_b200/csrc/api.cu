@@ -129,15 +129,45 @@ struct DevPool {
         if (zero) cudaMemsetAsync(p, 0, sz, ctx->stream);
         return (T *)p;
     }
+    // Host-to-device uploads are staged through recycled pinned memory: a copy from pageable memory makes the host
+    // wait until the stream has drained up to it and then runs at bounce-buffer speed, which left the GPU idle between
+    // the planning steps; from pinned memory the copy is queued and the host keeps issuing work.
+    std::vector<PinnedBuf> stage;
+    size_t stage_used = 0;
+    void *stage_alloc(size_t bytes) {
+        bytes = (bytes + 63) & ~size_t(63);
+        if (stage.empty() || stage_used + bytes > stage.back().cap) {
+            PinnedBuf b = ctx->pinned->acquire(std::max<size_t>(bytes, size_t(16) << 20));
+            if (!b.p) return nullptr;
+            stage.push_back(b);
+            stage_used = 0;
+        }
+        void *p = (char *)stage.back().p + stage_used;
+        stage_used += bytes;
+        return p;
+    }
+    void copy_in(void *dst, const void *src, size_t bytes) {
+        if (!bytes) return;
+        void *h = stage_alloc(bytes);
+        if (h) { memcpy(h, src, bytes); src = h; }
+        cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    }
     template <typename T>
     T *upload(const std::vector<T> &v) {
         T *p = alloc<T>(v.size());
-        if (p && !v.empty()) cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+        if (p) copy_in(p, v.data(), v.size() * sizeof(T));
         return p;
     }
+    // frees are stream ordered; the staging buffers go back to the pinned pool, so the caller must have synchronised
+    // the stream after its last upload (every exit of run_range does, or has failed)
     void release() {
         for (void *p : ptrs) cudaFreeAsync(p, ctx->stream);
         ptrs.clear();
+        if (!stage.empty()) {
+            cudaStreamSynchronize(ctx->stream);
+            for (auto &b : stage) ctx->pinned->release(b);
+            stage.clear();
+        }
     }
     ~DevPool() { release(); }
 };
@@ -416,10 +446,6 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     if (pool.failed) return PGPU_ENOMEM;
     tev("setup/alloc/memset");
     launch_encode(B, d_tiles, (int)tiles.size(), st);
-    launch_gc_scan(B, dtot / 32, d_gc_bs, d_gc_tot, st);
-    if (plan.stage >= 2 || plan.train) { launch_dicodon_index(B, d_tiles, (int)tiles.size(), st); ctx->launches++; }
-    ctx->launches += 3;
-    tev("k_encode+gc scan");
     ctx->launches++;
     std::vector<int4> h_masks;
     if (opts.mask) {
@@ -439,9 +465,16 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     std::vector<int32_t> h_gc(n), h_unk(n);
     CK(cudaMemcpyAsync(h_gc.data(), B.gc_count, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h_unk.data(), B.unknown, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    // the host only needs the G/C counts to plan the chains: the GC prefix scan and the dicodon index run behind
+    // that copy, underneath the planning loop
+    CK(cudaEventRecord(ctx->ev[13], st));
+    launch_gc_scan(B, dtot / 32, d_gc_bs, d_gc_tot, st);
+    ctx->launches += 3;
+    if (plan.stage >= 2 || plan.train) { launch_dicodon_index(B, d_tiles, (int)tiles.size(), st); ctx->launches++; }
+    tev("k_encode+gc scan");
     int e_enc = mark();
     S.reserved[0] += since(t_host);  // host: stage A issue
-    CK(cudaStreamSynchronize(st));
+    CK(cudaEventSynchronize(ctx->ev[13]));
     t_host = now();
     S.d2h_bytes += 8 * (int64_t)n;
 
@@ -593,7 +626,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     for (int e = 0; e < n_ext; e++) { exts[e].node_off = h_base[e]; exts[e].nn = h_base[e + 1] - h_base[e]; }
     int64_t total_cn = 0;
     for (auto &K : chains) { K.node_off = exts[K.ext].node_off; K.nn = exts[K.ext].nn; K.coff = total_cn; total_cn += K.nn; }
-    CK(cudaMemcpyAsync(B.exts, exts.data(), n_ext * sizeof(ExtractInfo), cudaMemcpyHostToDevice, st));
+    pool.copy_in(B.exts, exts.data(), n_ext * sizeof(ExtractInfo));
 
     // ---- extraction pass 2: fill, then per-extraction preparation ----------------------------------
     B.ndx = pool.alloc<int32_t>(total_nodes);

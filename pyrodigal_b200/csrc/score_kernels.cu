@@ -39,9 +39,11 @@ __device__ __forceinline__ int find_ext(const ExtractInfo *__restrict__ ex, int 
 
 // First candidate owner of flat index g: from the block table when the batch has one (one broadcast load), else by
 // binary search shared through the CTA.  Callers advance linearly from it (`while (next.off <= g) k++`).
-__device__ __forceinline__ int chain_hint(const DevBatch &B, int n_chains, int64_t g, int64_t total, int *s_first) {
+__device__ __forceinline__ int chain_hint(const DevBatch &B, int n_chains, int64_t g, int64_t total, int *s_first,
+                                          int64_t block_first = -1) {
     if (B.blk_chain) return B.blk_chain[g >> 7];
-    if (threadIdx.x == 0) *s_first = find_chain(B.chains, n_chains, min((int64_t)blockIdx.x * blockDim.x, total - 1));
+    if (block_first < 0) block_first = (int64_t)blockIdx.x * blockDim.x;
+    if (threadIdx.x == 0) *s_first = find_chain(B.chains, n_chains, min(block_first, total - 1));
     __syncthreads();
     return *s_first;
 }
@@ -314,15 +316,18 @@ __global__ void __launch_bounds__(32 * kOrfWarps, 5) k_coding_orf(DevBatch B, co
                                                                 int total_nodes) {
     __shared__ int s_first;
     const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * kOrfWarps + (threadIdx.x >> 5);  // flat extraction-node index
-    int e = ext_hint(B, n_ext, min(t, total_nodes - 1), blockIdx.x * kOrfWarps, total_nodes, &s_first);
-    if (t >= total_nodes) return;
-    while (e + 1 < n_ext && B.exts[e + 1].node_off <= t) e++;
+    // Work items are the STOP nodes.  A STOP node exists only if its ORF has a start, so an extraction with nn nodes
+    // has at most nn / 2 of them: the warps index a half-size slot space in which extraction e owns the slots from
+    // (node_off + 1) / 2 on, and only its first (#STOP nodes) slots have work.
+    const int h = blockIdx.x * kOrfWarps + (threadIdx.x >> 5);
+    int e = ext_hint(B, n_ext, min(2 * h, total_nodes - 1), 2 * blockIdx.x * kOrfWarps, total_nodes, &s_first);
+    if (h > (total_nodes + 1) / 2) return;
+    while (e + 1 < n_ext && ((B.exts[e + 1].node_off + 1) >> 1) <= h) e++;
     const ExtractInfo X = B.exts[e];
     const int32_t *__restrict__ cbase = B.cbase + 4 * e;
-    const int tl = t - X.node_off, nn = X.nn;
+    const int tl = h - ((X.node_off + 1) >> 1), nn = X.nn;
     const int n_fe = cbase[2] - cbase[1], n_re = nn - cbase[3];
-    if (tl >= n_fe + n_re) return;  // only the first (#STOP nodes) warps of an extraction have work
+    if (tl >= n_fe + n_re) return;
     const int z = (B.clist + X.node_off)[tl < n_fe ? cbase[1] + tl : cbase[3] + (tl - n_fe)];
     const uint8_t *__restrict__ cls = B.cls + X.node_off;
     const int32_t *__restrict__ ndx = B.ndx + X.node_off;
@@ -683,14 +688,15 @@ __device__ __forceinline__ double operon_value(int cz, int z, int s, const uint8
 __global__ void __launch_bounds__(128, 12) k_overlap(DevBatch B, const DevModel *__restrict__ models, int n_chains,
                                                   int64_t total, RunOpts o, int flag) {
     __shared__ int s_first;
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int k = chain_hint(B, n_chains, min(g, total - 1), total, &s_first);
-    if (g >= total) return;
-    while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
+    // half-size slot space, as in k_coding_orf: chain k owns the slots from (coff + 1) / 2 on and its STOP nodes (at
+    // most nn / 2) take the first of them; star_ptr was preset to -1 for every node
+    const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int k = chain_hint(B, n_chains, min(2 * h, total - 1), total, &s_first, 2 * (int64_t)blockIdx.x * blockDim.x);
+    if (h > (total + 1) / 2) return;
+    while (k + 1 < n_chains && ((B.chains[k + 1].coff + 1) >> 1) <= h) k++;
     const ChainInfo C = B.chains[k];
-    const int t = (int)(g - C.coff), nn = C.nn;
+    const int t = (int)(h - ((C.coff + 1) >> 1)), nn = C.nn;
     if (t >= nn) return;
-    // star_ptr was preset to -1 for every node; only STOP nodes (first #STOP threads of the chain) have work
     const int32_t *__restrict__ cbase = B.cbase + 4 * C.ext;
     const int n_fe = cbase[2] - cbase[1], n_re = nn - cbase[3];
     if (t >= n_fe + n_re) return;
@@ -828,7 +834,7 @@ void launch_coding(const DevBatch &B, const DevModel *models, int n_chains, int6
                    cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
     if (B.ext_chains && B.dcT && n_ext > 0 && total_nodes > 0)
-        k_coding_orf<<<(total_nodes + kOrfWarps - 1) / kOrfWarps, 32 * kOrfWarps, 0, st>>>(B, models, n_ext, total_nodes);
+        k_coding_orf<<<((total_nodes + 1) / 2 + 1 + kOrfWarps - 1) / kOrfWarps, 32 * kOrfWarps, 0, st>>>(B, models, n_ext, total_nodes);
     else
         k_coding<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total);
 }
@@ -854,7 +860,7 @@ void launch_overlap(const DevBatch &B, const DevModel *models, int n_chains, int
                     cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
     cudaMemsetAsync(B.star_ptr, 0xff, 3 * (size_t)total * sizeof(int32_t), st);  // -1 everywhere
-    k_overlap<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total, o, flag);
+    k_overlap<<<(unsigned)(((total + 1) / 2 + 1 + 127) / 128), 128, 0, st>>>(B, models, n_chains, total, o, flag);
 }
 
 }  // namespace pgpu

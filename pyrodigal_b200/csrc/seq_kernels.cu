@@ -384,17 +384,35 @@ __global__ void __launch_bounds__(128) k_codon_bits(DevBatch B, int n_ext, int t
     extract_frame_geometry(slen, f, &i_top0, &n_codons);
     const uint8_t *__restrict__ cod = B.cod + X.doff;
     const int64_t base = X.cb_off + (int64_t)sf * X.n_chunks * kChunkWords + (int64_t)chunk * kChunkWords;
+    // strand coordinate i = i_top0 - 3u sits at cod[i] (forward) or cod[slen - 3 - i] (reverse): base + u * step
+    const uint8_t *__restrict__ cp = rev ? cod + (slen - 3 - i_top0) : cod + i_top0;
+    const int step = rev ? 3 : -3;
+    const uint64_t stopmask = X.stopmask, startmask = X.startmask;
 #pragma unroll 1
     for (int r = 0; r < kChunkWords / 32; r++) {
         const int w0 = chunk * kChunkWords + r * 32;
         if (w0 * 32 >= n_codons) break;
         uint32_t myS = 0, myC = 0;
-#pragma unroll 4
-        for (int k = 0; k < 32; k++) {
-            const int u = (w0 + k) * 32 + lane;
-            const int fl = u < n_codons ? codon_flags(cod, slen, rev != 0, i_top0 - 3 * u, X.stopmask, X.startmask) : 0;
-            const uint32_t S = __ballot_sync(0xffffffffu, fl & 1), C = __ballot_sync(0xffffffffu, fl & 2);
-            if (lane == k) { myS = S; myC = C; }
+#pragma unroll 1
+        for (int k0 = 0; k0 < 32; k0 += 8) {
+            // eight independent byte loads first (clamped: slots past the end repeat the last codon and are
+            // masked out), then branch-free flags and the ballots
+            int cs[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int u = (w0 + k0 + j) * 32 + lane;
+                cs[j] = cp[min(u, n_codons - 1) * step];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int u = (w0 + k0 + j) * 32 + lane;
+                int c = cs[j] & 63;
+                if (rev) c = rev_code(c);
+                const bool ok = u < n_codons && !(cs[j] & 64);
+                const uint32_t S = __ballot_sync(0xffffffffu, ok && ((stopmask >> c) & 1ull));
+                const uint32_t C = __ballot_sync(0xffffffffu, ok && ((startmask >> c) & 1ull));
+                if (lane == k0 + j) { myS = S; myC = C; }
+            }
         }
         B.cb_stop[base + r * 32 + lane] = myS;
         B.cb_start[base + r * 32 + lane] = myC;
