@@ -82,6 +82,8 @@ struct pgpu_ctx {
     int dp_ml_minb = 6;        // k_dp_ml register budget: min CTAs/SM 5, 6 or 8 (PGPU_DP_ML_MINB)
     int extract_algo = 2;      // 2: bit-parallel extraction (k_codon_bits + k_extract_b), 1: warp-cooperative k_extract_w
                                // (PGPU_EXTRACT_ALGO; batches with N-run masks always use 1)
+    int final_algo = 2;        // meta mode without node arrays: 2 = final scoring pass over the genes' ORFs only,
+                               // 1 = over every node as with want_nodes (PGPU_FINAL_ALGO)
     bool dp_verify = false;    // PGPU_DP_VERIFY=1: run k_dp_dq after k_dp_ml and fail on any difference (self-check)
     int dp_algo = 5;           // 5: k_dp_ml for multi-model batches, k_dp_dq otherwise (default); 6: k_dp_ml always;
                                // 3/4: k_dp_dq, 1/2: k_dp_fast, 0: all-pairs k_dp (PGPU_DP_ALGO=n)
@@ -874,9 +876,19 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         // unused tail of every contig's slot is never touched because kernels index by chain, but the flat
         // index space must be dense: use per-contig capacity as the chain length for the search only.
         F.ext_chains = nullptr;  // final pass: one chain per contig, use the per-chain kernel
-        launch_score_chains(F, ctx->d_models, n, ftot, ro, d_mot, n_ext, total_nodes, st);
-        launch_pack_nodes(F, n, ftot, d_mot, nullptr, nullptr, 0, d_nodes, st);
-        ctx->launches += 4;
+        if (opts.want_nodes || ctx->final_algo == 1) {
+            launch_score_chains(F, ctx->d_models, n, ftot, ro, d_mot, n_ext, total_nodes, st);
+            launch_pack_nodes(F, n, ftot, d_mot, nullptr, nullptr, 0, d_nodes, st);
+            ctx->launches += 4;
+        } else {
+            // only the start / stop node records of the genes leave the device: re-score just their ORFs
+            int2 *d_list = pool.alloc<int2>(gene_off[n]);
+            int *d_count = pool.alloc<int>(1);
+            if (pool.failed) return PGPU_ENOMEM;
+            launch_score_genes(F, ctx->d_models, n, d_summ, d_genes, d_gene_off, gene_off[n], d_list, d_count, ro, d_mot, st);
+            launch_pack_nodes_genes(F, d_list, d_count, gene_off[n], d_genes, d_gene_off, d_mot, d_nodes, st);
+            ctx->launches += 5;
+        }
         node_out_off = fin_coff;
         d_node_out_off = d_fin_coff;
     } else {
@@ -1235,6 +1247,7 @@ int pgpu_create(int device, pgpu_ctx **out) {
     if (const char *a = getenv("PGPU_DP_VERIFY")) ctx->dp_verify = atoi(a) != 0;
     if (const char *a = getenv("PGPU_DP_ML_MINB")) ctx->dp_ml_minb = atoi(a);
     if (const char *a = getenv("PGPU_EXTRACT_ALGO")) ctx->extract_algo = atoi(a);
+    if (const char *a = getenv("PGPU_FINAL_ALGO")) ctx->final_algo = atoi(a);
     // keep freed blocks cached in the stream-ordered pool: sub-batches reuse them without going to the driver
     cudaMemPool_t mp;
     if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {

@@ -1593,20 +1593,9 @@ __global__ void __launch_bounds__(128) k_tweak(DevBatch B, const DevModel *__res
 // nodes of a chain list -> pgpu_node records.  `dp_state`: 1 = single mode (keep the DP state of the
 // winning chain), 0 = meta mode (nodes were re-extracted and re-scored: score 0, traceb/tracef -1,
 // star_ptr 0)
-__global__ void __launch_bounds__(128) k_pack_nodes(DevBatch B, int n_chains, int64_t total,
-                                                     const MotifOut *__restrict__ mot, const int32_t *__restrict__ tracef,
-                                                     const uint8_t *__restrict__ elim, int dp_state,
-                                                     pgpu_node *__restrict__ out) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total) return;
-    int lo = 0, hi = n_chains - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (B.chains[mid].coff <= g) lo = mid; else hi = mid - 1;
-    }
-    const ChainInfo C = B.chains[lo];
-    const int i = (int)(g - C.coff);
-    if (i >= C.nn) return;
+__device__ __forceinline__ void pack_node(const DevBatch &B, const ChainInfo &C, int64_t g, int i,
+                                          const MotifOut *__restrict__ mot, const int32_t *__restrict__ tracef,
+                                          const uint8_t *__restrict__ elim, int dp_state, pgpu_node *__restrict__ out) {
     const int c = B.cls[C.node_off + i];
     pgpu_node n;
     memset(&n, 0, sizeof(n));  // deterministic padding bytes: records are compared / hashed as raw bytes
@@ -1635,6 +1624,38 @@ __global__ void __launch_bounds__(128) k_pack_nodes(DevBatch B, int n_chains, in
     uint64_t *dst = reinterpret_cast<uint64_t *>(out + g);
 #pragma unroll
     for (int q = 0; q < (int)(sizeof(pgpu_node) / 8); q++) dst[q] = src[q];
+}
+
+__global__ void __launch_bounds__(128) k_pack_nodes(DevBatch B, int n_chains, int64_t total,
+                                                     const MotifOut *__restrict__ mot, const int32_t *__restrict__ tracef,
+                                                     const uint8_t *__restrict__ elim, int dp_state,
+                                                     pgpu_node *__restrict__ out) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    int lo = 0, hi = n_chains - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (B.chains[mid].coff <= g) lo = mid; else hi = mid - 1;
+    }
+    const ChainInfo C = B.chains[lo];
+    const int i = (int)(g - C.coff);
+    if (i >= C.nn) return;
+    pack_node(B, C, g, i, mot, tracef, elim, dp_state, out);
+}
+
+// records of the start and stop node of every listed gene only (meta mode without node arrays; B = final-pass
+// batch, chain index == contig), written at their usual place out[coff + node]
+__global__ void __launch_bounds__(128) k_pack_nodes_genes(DevBatch B, const int2 *__restrict__ list, const int *__restrict__ count,
+                                                           const pgpu_gene *__restrict__ genes,
+                                                           const int64_t *__restrict__ gene_off,
+                                                           const MotifOut *__restrict__ mot, pgpu_node *__restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((t >> 1) >= *count) return;
+    const int2 e = list[t >> 1];
+    const ChainInfo C = B.chains[e.x];
+    const pgpu_gene G = genes[gene_off[e.x] + e.y];
+    const int i = (t & 1) ? G.stop_ndx : G.start_ndx;
+    pack_node(B, C, C.coff + i, i, mot, nullptr, nullptr, 0, out);
 }
 
 // meta mode: the winner's nodes are re-extracted and re-scored from scratch (lib.pyx:5380-5394); this
@@ -1750,6 +1771,12 @@ void launch_pack_nodes(const DevBatch &B, int n_chains, int64_t total, const voi
     if (n_chains == 0 || total == 0) return;
     k_pack_nodes<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, n_chains, total, (const MotifOut *)mot, tracef, elim,
                                                                    dp_state, out);
+}
+void launch_pack_nodes_genes(const DevBatch &B, const int2 *list, const int *count, int64_t gene_cap, const pgpu_gene *genes,
+                             const int64_t *gene_off, const void *mot, pgpu_node *out, cudaStream_t st) {
+    if (gene_cap == 0) return;
+    k_pack_nodes_genes<<<(unsigned)((2 * gene_cap + 127) / 128), 128, 0, st>>>(B, list, count, genes, gene_off,
+                                                                              (const MotifOut *)mot, out);
 }
 void launch_pack_gene_nodes(int n_contigs, const pgpu_contig_summary *summary, const pgpu_gene *genes,
                             const int64_t *gene_off, const int64_t *gene_out_off, const int64_t *node_out_off,

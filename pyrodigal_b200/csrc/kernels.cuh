@@ -47,6 +47,11 @@ void launch_trace(const DevBatch &B, const DevModel *models, int n_contigs, cons
                   cudaStream_t st);
 void launch_pack_nodes(const DevBatch &B, int n_chains, int64_t total, const void *mot, const int32_t *tracef,
                        const uint8_t *elim, int dp_state, pgpu_node *out, cudaStream_t st);
+void launch_score_genes(const DevBatch &B, const DevModel *models, int n_contigs, const void *summary, const void *genes,
+                        const int64_t *gene_off, int64_t gene_cap, int2 *list, int *count, RunOpts o, void *mot_out,
+                        cudaStream_t st);
+void launch_pack_nodes_genes(const DevBatch &B, const int2 *list, const int *count, int64_t gene_cap, const pgpu_gene *genes,
+                             const int64_t *gene_off, const void *mot, pgpu_node *out, cudaStream_t st);
 void launch_pack_gene_nodes(int n_contigs, const pgpu_contig_summary *summary, const pgpu_gene *genes,
                             const int64_t *gene_off, const int64_t *gene_out_off, const int64_t *node_out_off,
                             const pgpu_node *nodes, pgpu_node *out, pgpu_gene *genes_out, cudaStream_t st);

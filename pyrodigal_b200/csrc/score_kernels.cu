@@ -216,22 +216,9 @@ __global__ void __launch_bounds__(128) k_class_index(DevBatch B, int n_ext) {
 // --------------------------------------------------------------------------------------------------
 // raw coding score: one thread per STOP node (= per ORF)
 // --------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_coding(DevBatch B, const DevModel *__restrict__ models, int n_chains,
-                                                 int64_t total) {
-    __shared__ int s_first;
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int k = chain_hint(B, n_chains, min(g, total - 1), total, &s_first);
-    if (g >= total) return;
-    while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
-    const ChainInfo C = B.chains[k];
-    // the first (#STOP nodes) threads of a chain's index range take one STOP node each, through the
-    // class-sorted index list, so that warps are either fully busy or exit at once
-    const int t = (int)(g - C.coff);
-    if (t >= C.nn) return;
-    const int32_t *__restrict__ cbase = B.cbase + 4 * C.ext;
-    const int n_fe = cbase[2] - cbase[1], n_re = C.nn - cbase[3];
-    if (t >= n_fe + n_re) return;
-    const int z = (B.clist + C.node_off)[t < n_fe ? cbase[1] + t : cbase[3] + (t - n_fe)];
+// the ORF that ends at STOP node z of chain C (all three sweeps), by one thread
+__device__ __forceinline__ void coding_orf_thread(const DevBatch &B, const DevModel *__restrict__ models, const ChainInfo &C,
+                                                  int z) {
     const uint8_t *__restrict__ cls = B.cls + C.node_off;
     const int c = cls[z];
     const DevModel &M = models[C.model];
@@ -302,6 +289,24 @@ __global__ void __launch_bounds__(128) k_coding(DevBatch B, const DevModel *__re
         cs += lfac;
         cscore[i] = cs;
     }
+}
+
+__global__ void __launch_bounds__(128) k_coding(DevBatch B, const DevModel *__restrict__ models, int n_chains,
+                                                 int64_t total) {
+    __shared__ int s_first;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int k = chain_hint(B, n_chains, min(g, total - 1), total, &s_first);
+    if (g >= total) return;
+    while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
+    const ChainInfo C = B.chains[k];
+    // the first (#STOP nodes) threads of a chain's index range take one STOP node each, through the
+    // class-sorted index list, so that warps are either fully busy or exit at once
+    const int t = (int)(g - C.coff);
+    if (t >= C.nn) return;
+    const int32_t *__restrict__ cbase = B.cbase + 4 * C.ext;
+    const int n_fe = cbase[2] - cbase[1], n_re = C.nn - cbase[3];
+    if (t >= n_fe + n_re) return;
+    coding_orf_thread(B, models, C, (B.clist + C.node_off)[t < n_fe ? cbase[1] + t : cbase[3] + (t - n_fe)]);
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -444,16 +449,9 @@ __global__ void __launch_bounds__(32 * kOrfWarps, 5) k_coding_orf(DevBatch B, co
 // start scoring: RBS / upstream motif / type / upstream composition / penalties (lib.pyx:2331-2487)
 // --------------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel *__restrict__ models, int n_chains,
-                                                      int64_t total, RunOpts o, MotifOut *__restrict__ mot_out) {
-    __shared__ int s_first;
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int k = chain_hint(B, n_chains, min(g, total - 1), total, &s_first);
-    if (g >= total) return;
-    while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
-    const ChainInfo C = B.chains[k];
-    const int i = (int)(g - C.coff);
-    if (i >= C.nn) return;
+// node i of chain C (chain-node g = C.coff + i)
+__device__ __forceinline__ void start_score_node(const DevBatch &B, const DevModel *__restrict__ models, const ChainInfo &C,
+                                                 int64_t g, int i, RunOpts o, MotifOut *__restrict__ mot_out) {
     const uint8_t *__restrict__ cls = B.cls + C.node_off;
     const int c = cls[i];
     if (cls_is_stop(c)) {
@@ -646,6 +644,59 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
     B.cscore[g] = cscore; B.sscore[g] = sscore; B.rscore[g] = rscore; B.uscore[g] = uscore; B.tscore[g] = tscore;
     B.rbs[2 * g] = (uint8_t)rbs0; B.rbs[2 * g + 1] = (uint8_t)rbs1;
     if (mot_out) mot_out[g] = mot;
+}
+
+__global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel *__restrict__ models, int n_chains,
+                                                      int64_t total, RunOpts o, MotifOut *__restrict__ mot_out) {
+    __shared__ int s_first;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int k = chain_hint(B, n_chains, min(g, total - 1), total, &s_first);
+    if (g >= total) return;
+    while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
+    const ChainInfo C = B.chains[k];
+    const int i = (int)(g - C.coff);
+    if (i >= C.nn) return;
+    start_score_node(B, models, C, g, i, o, mot_out);
+}
+
+// --------------------------------------------------------------------------------------------------
+// Final scoring pass of meta mode restricted to what the result exposes when node arrays are not requested: the
+// start and stop node of every gene.  B is the final-pass batch (one chain per contig: chain index == contig).
+//   k_gene_list        compacts (contig, gene) pairs into a work list (order is irrelevant)
+//   k_coding_genes     one thread per listed gene: the three coding sweeps over the gene's ORF (they need every
+//                      start of that ORF, nothing outside it)
+//   k_start_score_genes one thread per listed node (2 per gene)
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_gene_list(int n_contigs, const pgpu_contig_summary *__restrict__ summary,
+                                                    int2 *__restrict__ list, int *__restrict__ count) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_contigs) return;
+    const int ng = summary[c].n_genes;
+    if (ng <= 0) return;
+    const int base = atomicAdd(count, ng);
+    for (int j = 0; j < ng; j++) list[base + j] = make_int2(c, j);
+}
+__global__ void __launch_bounds__(128) k_coding_genes(DevBatch B, const DevModel *__restrict__ models,
+                                                       const int2 *__restrict__ list, const int *__restrict__ count,
+                                                       const pgpu_gene *__restrict__ genes, const int64_t *__restrict__ gene_off) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *count) return;
+    const int2 e = list[t];
+    const ChainInfo C = B.chains[e.x];
+    coding_orf_thread(B, models, C, genes[gene_off[e.x] + e.y].stop_ndx);
+}
+__global__ void __launch_bounds__(128) k_start_score_genes(DevBatch B, const DevModel *__restrict__ models,
+                                                            const int2 *__restrict__ list, const int *__restrict__ count,
+                                                            const pgpu_gene *__restrict__ genes,
+                                                            const int64_t *__restrict__ gene_off, RunOpts o,
+                                                            MotifOut *__restrict__ mot_out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((t >> 1) >= *count) return;
+    const int2 e = list[t >> 1];
+    const ChainInfo C = B.chains[e.x];
+    const pgpu_gene G = genes[gene_off[e.x] + e.y];
+    const int i = (t & 1) ? G.stop_ndx : G.start_ndx;
+    start_score_node(B, models, C, C.coff + i, i, o, mot_out);
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -847,6 +898,16 @@ void launch_score_chains(const DevBatch &B, const DevModel *models, int n_chains
                          void *mot_out, int n_ext, int total_nodes, cudaStream_t st) {
     launch_coding(B, models, n_chains, total, n_ext, total_nodes, st);
     launch_start_score(B, models, n_chains, total, o, mot_out, st);
+}
+void launch_score_genes(const DevBatch &B, const DevModel *models, int n_contigs, const void *summary, const void *genes,
+                        const int64_t *gene_off, int64_t gene_cap, int2 *list, int *count, RunOpts o, void *mot_out,
+                        cudaStream_t st) {
+    if (n_contigs == 0 || gene_cap == 0) return;
+    cudaMemsetAsync(count, 0, sizeof(int), st);
+    k_gene_list<<<(n_contigs + 127) / 128, 128, 0, st>>>(n_contigs, (const pgpu_contig_summary *)summary, list, count);
+    k_coding_genes<<<(unsigned)((gene_cap + 127) / 128), 128, 0, st>>>(B, models, list, count, (const pgpu_gene *)genes, gene_off);
+    k_start_score_genes<<<(unsigned)((2 * gene_cap + 127) / 128), 128, 0, st>>>(B, models, list, count, (const pgpu_gene *)genes,
+                                                                                   gene_off, o, (MotifOut *)mot_out);
 }
 void launch_opv(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;

@@ -386,3 +386,31 @@ def test_single_chain_16mbp_vs_oracle(capi):
     cmp_nodes(r.nodes(0), n2, "chr", dp=True)
     assert int(r.summary["ipath"][0]) == ipath and len(n2) > 500_000
     r.free(); c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("closed", [False, True])
+def test_gene_only_final_pass_equals_full_final_pass(ctx, capi, closed):
+    """meta mode without node arrays re-scores only the genes' ORFs: the start / stop node records of every gene must
+    be byte-identical to the ones taken from the full final pass (want_nodes=True), which is checked against the
+    oracle node by node elsewhere"""
+    rng = np.random.default_rng(5)
+    seqs = [b"", R.synth(95, .5, 3), R.synth(150000, .45, 4)]
+    for k in range(80):
+        seqs.append(R.synth(int(rng.integers(200, 40000)), float(rng.uniform(.28, .72)), 7000 + k,
+                            n_frac=0.002 if k % 5 == 0 else 0.0))
+    full = run_meta(ctx, capi, seqs, closed=closed, want_nodes=True)
+    lean = run_meta(ctx, capi, seqs, closed=closed, want_nodes=False)
+    assert np.array_equal(full.gene_off, lean.gene_off)
+    assert len(lean.genes) > 500
+    assert lean.genes.tobytes() == full.genes.tobytes()
+    assert lean.gene_nodes.tobytes() == full.gene_nodes.tobytes()
+    # and against the full node arrays directly
+    gn = lean.gene_nodes.reshape(-1, 2)
+    for k in range(len(seqs)):
+        a, b = full.gene_off[k], full.gene_off[k + 1]
+        if b > a:
+            nodes = full.nodes(k)
+            # field-wise: fancy indexing leaves the padding bytes of a structured copy uninitialised
+            assert np.array_equal(nodes[full.genes["start_ndx"][a:b]], gn[a:b, 0])
+            assert np.array_equal(nodes[full.genes["stop_ndx"][a:b]], gn[a:b, 1])
