@@ -708,6 +708,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     B.cscore = pool.alloc<double>(total_cn); B.sscore = pool.alloc<double>(total_cn);
     B.rscore = pool.alloc<double>(total_cn); B.uscore = pool.alloc<double>(total_cn);
     B.tscore = pool.alloc<double>(total_cn);
+    B.cs = pool.alloc<double>(total_cn);
     B.opv = pool.alloc<double>(3 * (size_t)total_cn);
     B.star_ptr = pool.alloc<int32_t>(3 * (size_t)total_cn);
     B.rbs = pool.alloc<uint8_t>(2 * (size_t)total_cn + 16);
@@ -865,6 +866,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         const int64_t ftot = fin_coff[n];
         F.chains = d_fin;
         F.blk_chain = nullptr;   // the final pass has its own chain-node index space
+        F.cs = nullptr;
         F.cscore = pool.alloc<double>(ftot); F.sscore = pool.alloc<double>(ftot); F.rscore = pool.alloc<double>(ftot);
         F.uscore = pool.alloc<double>(ftot); F.tscore = pool.alloc<double>(ftot);
         F.rbs = pool.alloc<uint8_t>(2 * (size_t)ftot + 16);

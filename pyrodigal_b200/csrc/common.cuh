@@ -151,6 +151,7 @@ struct DevBatch {
     // chains
     ChainInfo *chains;
     double *cscore, *sscore, *rscore, *uscore, *tscore;  // per chain-node
+    double *cs;           // per chain-node: cscore + sscore as one array (main pass of find_genes; nullptr otherwise)
     double *opv;          // [3 * chain-node] operon values (cs[n3] + igm) for STOP nodes
     double *gcb;          // training DP: bias . gc_score per chain-node (only final == 0)
     int32_t *star_ptr;    // [3 * chain-node]

@@ -1015,6 +1015,7 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
     const int32_t *__restrict__ fe_q = B.feq + C.node_off + fe0;       // merged-stream position
     const double *__restrict__ cscore = B.cscore + C.coff;
     const double *__restrict__ sscore = B.sscore + C.coff;
+    const double *__restrict__ csum = B.cs ? B.cs + C.coff : nullptr;  // cscore + sscore, written by the scoring pass
     const double *__restrict__ opv = B.opv + 3 * C.coff;
     const int32_t *__restrict__ star_ptr = B.star_ptr + 3 * C.coff;
     double *score = B.score + C.coff;
@@ -1065,11 +1066,11 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
           sk[lane] = k;
       }
       if (act && i0 + 32 < nn) {  // the chain-major score lines of the next block
-          const double *pc = cscore + i0 + 32, *ps = sscore + i0 + 32;
+          const double *pc = (csum ? csum : cscore) + i0 + 32, *ps = sscore + i0 + 32;
 #pragma unroll
           for (int t = 0; t < 3; t++) {
               asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + min(16 * t, 31)));
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + min(16 * t, 31)));
+              if (!csum) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + min(16 * t, 31)));
           }
       }
       __syncwarp();
@@ -1081,7 +1082,7 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
         lo_fe += K.leave == K_FE;
         // cscore + sscore of a start target (chain-major, sequential per lane: L1 lines are reused 16 times)
         double cs_i = 0.0;
-        if (kind == K_FS || kind == K_RS) cs_i = cscore[i] + sscore[i];
+        if (kind == K_FS || kind == K_RS) cs_i = csum ? csum[i] : cscore[i] + sscore[i];
         double wv = kNeg;
         int wkey = -1;  // (node << 2) | (overlap frame + 1)
         // larger value, then larger node; the same node seen twice (far maximum + overlap re-evaluation) keeps the

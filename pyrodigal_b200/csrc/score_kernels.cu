@@ -457,6 +457,7 @@ __device__ __forceinline__ void start_score_node(const DevBatch &B, const DevMod
     if (cls_is_stop(c)) {
         // STOP nodes keep the reset state (node.c:176-197)
         B.cscore[g] = 0.0; B.sscore[g] = 0.0; B.rscore[g] = 0.0; B.uscore[g] = 0.0; B.tscore[g] = 0.0;
+        if (B.cs) B.cs[g] = 0.0;
         B.rbs[2 * g] = 0; B.rbs[2 * g + 1] = 0;
         if (mot_out) { MotifOut m = {}; mot_out[g] = m; }
         return;
@@ -642,6 +643,7 @@ __device__ __forceinline__ void start_score_node(const DevBatch &B, const DevMod
         sscore -= st_wt;
     }
     B.cscore[g] = cscore; B.sscore[g] = sscore; B.rscore[g] = rscore; B.uscore[g] = uscore; B.tscore[g] = tscore;
+    if (B.cs) B.cs[g] = cscore + sscore;  // what record_overlapping_starts and the DP read of a start
     B.rbs[2 * g] = (uint8_t)rbs0; B.rbs[2 * g + 1] = (uint8_t)rbs1;
     if (mot_out) mot_out[g] = mot;
 }
@@ -702,38 +704,43 @@ __global__ void __launch_bounds__(128) k_start_score_genes(DevBatch B, const Dev
 // --------------------------------------------------------------------------------------------------
 // overlapping starts (lib.pyx:2279-2329) + operon values for the DP
 // --------------------------------------------------------------------------------------------------
-struct NodeView {
-    int ndx, strand;
-    double rscore, uscore;
-};
-
-// _connection.h:52-78
-__device__ __forceinline__ double igm_same(const NodeView &n1, const NodeView &n2, const DevModel &M) {
-    const int dist = abs(n1.ndx - n2.ndx);
-    const bool overlap = n1.ndx + 2 * n1.strand >= n2.ndx;
+// _intergenic_mod_same (_connection.h:52-78) for n1 = (ndx1, strand1), n2 = ndx2 on the same strand.  The rbs /
+// upstream scores of the start involved (node `start` of this chain -- in every use here the node whose scores the
+// reference reads is the start, never the STOP) are needed only when the two nodes touch, so they are loaded on
+// demand: that case is rare and the two loads were half of this kernel's score traffic.
+__device__ __forceinline__ double igm_same(int ndx1, int strand1, int ndx2, int start, const double *__restrict__ rscore,
+                                           const double *__restrict__ uscore, const DevModel &M) {
+    const int dist = abs(ndx1 - ndx2);
+    const bool overlap = ndx1 + 2 * strand1 >= ndx2;
     double r = 0.0;
-    if (n1.ndx + 2 == n2.ndx || n1.ndx == n2.ndx + 1) {
-        const NodeView &s = n1.strand == 1 ? n2 : n1;
-        if (s.rscore < 0) r -= s.rscore;
-        if (s.uscore < 0) r -= s.uscore;
+    if (ndx1 + 2 == ndx2 || ndx1 == ndx2 + 1) {
+        const double rs = rscore[start], us = uscore[start];
+        if (rs < 0) r -= rs;
+        if (us < 0) r -= us;
     }
     if (dist > 3 * kOperDist) r -= 0.15 * M.st_wt;
     else if ((dist <= kOperDist && !overlap) || dist * 4 < kOperDist) r += (2.0 - ((double)dist / kOperDist)) * 0.15 * M.st_wt;
     return r;
 }
 
+// cscore + sscore of a start: from the combined array when the scoring pass wrote one
+__device__ __forceinline__ double cs_of(int j, const double *__restrict__ cs, const double *__restrict__ cscore,
+                                        const double *__restrict__ sscore) {
+    return cs ? cs[j] : cscore[j] + sscore[j];
+}
+
 // cs[n3] + intergenic_mod for the start n3 recorded in star_ptr of STOP node z:
 // forward STOP: _connection.h:189 (n1 = z, n3);  reverse STOP: _connection.h:320,329,354 (n3, n2 = z)
 __device__ __forceinline__ double operon_value(int cz, int z, int s, const uint8_t *__restrict__ cls,
-                                               const int32_t *__restrict__ ndx, const double *__restrict__ cscore,
-                                               const double *__restrict__ sscore, const double *__restrict__ rscore,
-                                               const double *__restrict__ uscore, const DevModel &M) {
+                                               const int32_t *__restrict__ ndx, const double *__restrict__ cs,
+                                               const double *__restrict__ cscore, const double *__restrict__ sscore,
+                                               const double *__restrict__ rscore, const double *__restrict__ uscore,
+                                               const DevModel &M) {
     const int cs_ = cls[s];
-    const double base = cscore[s] + sscore[s];
+    const double base = cs_of(s, cs, cscore, sscore);
     if (((cz ^ cs_) & CLS_REV) != 0) return base + M.ig_neg;
-    NodeView a = {ndx[z], (cz & CLS_REV) ? -1 : 1, rscore[z], uscore[z]};
-    NodeView b = {ndx[s], (cs_ & CLS_REV) ? -1 : 1, rscore[s], uscore[s]};
-    return (cz & CLS_REV) ? base + igm_same(b, a, M) : base + igm_same(a, b, M);
+    return (cz & CLS_REV) ? base + igm_same(ndx[s], -1, ndx[z], s, rscore, uscore, M)
+                          : base + igm_same(ndx[z], 1, ndx[s], s, rscore, uscore, M);
 }
 
 __global__ void __launch_bounds__(128, 12) k_overlap(DevBatch B, const DevModel *__restrict__ models, int n_chains,
@@ -759,6 +766,7 @@ __global__ void __launch_bounds__(128, 12) k_overlap(DevBatch B, const DevModel 
     const double *__restrict__ sscore = B.sscore + C.coff;
     const double *__restrict__ rscore = B.rscore + C.coff;
     const double *__restrict__ uscore = B.uscore + C.coff;
+    const double *__restrict__ cs = B.cs ? B.cs + C.coff : nullptr;
     const DevModel &M = models[C.model];
     int sp[3] = {-1, -1, -1};
     const int c = cls[i];
@@ -766,7 +774,6 @@ __global__ void __launch_bounds__(128, 12) k_overlap(DevBatch B, const DevModel 
         const int my = ndx[i];
         double max_sc = -100.0;
         if (!(c & CLS_REV)) {
-            NodeView me = {my, 1, 0.0, 0.0};
             for (int j = i + 3; j >= 0; j--) {
                 if (j >= nn || ndx[j] > my + 2) continue;
                 if (ndx[j] + o.max_overlap < my) break;
@@ -777,13 +784,11 @@ __global__ void __launch_bounds__(128, 12) k_overlap(DevBatch B, const DevModel 
                 if (flag == 0) {
                     if (sp[f] == -1) sp[f] = j;
                 } else {
-                    NodeView st = {ndx[j], 1, rscore[j], uscore[j]};
-                    const double sc = cscore[j] + sscore[j] + igm_same(me, st, M);
+                    const double sc = cs_of(j, cs, cscore, sscore) + igm_same(my, 1, ndx[j], j, rscore, uscore, M);
                     if (sc > max_sc) { sp[f] = j; max_sc = sc; }
                 }
             }
         } else {
-            NodeView me = {my, -1, 0.0, 0.0};
             for (int j = i - 3; j < nn; j++) {
                 if (j < 0 || ndx[j] < my - 2) continue;
                 if (ndx[j] - o.max_overlap > my) break;
@@ -794,8 +799,7 @@ __global__ void __launch_bounds__(128, 12) k_overlap(DevBatch B, const DevModel 
                 if (flag == 0) {
                     if (sp[f] == -1) sp[f] = j;
                 } else {
-                    NodeView st = {ndx[j], -1, rscore[j], uscore[j]};
-                    const double sc = cscore[j] + sscore[j] + igm_same(st, me, M);
+                    const double sc = cs_of(j, cs, cscore, sscore) + igm_same(ndx[j], -1, my, j, rscore, uscore, M);
                     if (sc > max_sc) { sp[f] = j; max_sc = sc; }
                 }
             }
@@ -805,7 +809,7 @@ __global__ void __launch_bounds__(128, 12) k_overlap(DevBatch B, const DevModel 
 #pragma unroll
     for (int f = 0; f < 3; f++) {
         B.star_ptr[3 * gi + f] = sp[f];
-        B.opv[3 * gi + f] = sp[f] == -1 ? 0.0 : operon_value(c, i, sp[f], cls, ndx, cscore, sscore, rscore, uscore, M);
+        B.opv[3 * gi + f] = sp[f] == -1 ? 0.0 : operon_value(c, i, sp[f], cls, ndx, cs, cscore, sscore, rscore, uscore, M);
     }
 }
 
@@ -825,7 +829,7 @@ __global__ void __launch_bounds__(128) k_opv(DevBatch B, const DevModel *__restr
     for (int f = 0; f < 3; f++) {
         const int s = B.star_ptr[3 * g + f];
         B.opv[3 * g + f] = (s < 0 || s >= C.nn || !cls_is_stop(c)) ? 0.0
-            : operon_value(c, i, s, cls, B.ndx + C.node_off, B.cscore + C.coff, B.sscore + C.coff, B.rscore + C.coff,
+            : operon_value(c, i, s, cls, B.ndx + C.node_off, nullptr, B.cscore + C.coff, B.sscore + C.coff, B.rscore + C.coff,
                            B.uscore + C.coff, models[C.model]);
     }
 }
