@@ -7,6 +7,7 @@
 //   coding score -> start score -> overlapping starts -> DP -> winner/traceback/genes -> final re-score
 //   (meta) -> pack -> [sync: gene counts] -> D2H.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -15,6 +16,8 @@
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "kernels.cuh"
@@ -68,7 +71,6 @@ struct pgpu_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int n_models = 0;
-    std::vector<RawTraining> h_raw;
     std::vector<DevModel> h_models;
     std::vector<double> model_gc;     // compact copies for the per-contig planning loop
     std::vector<int> model_tt;
@@ -88,6 +90,14 @@ struct pgpu_ctx {
     int dp_algo = 5;           // 5: k_dp_ml for multi-model batches, k_dp_dq otherwise (default); 6: k_dp_ml always;
                                // 3/4: k_dp_dq, 1/2: k_dp_fast, 0: all-pairs k_dp (PGPU_DP_ALGO=n)
     std::shared_ptr<struct PinnedPool> pinned;  // shared with the results it backs (they may outlive the context)
+    // Host-input calls (pgpu_find_genes_batch) on large batches run as two halves on two worker threads / streams
+    // ("lanes"): the H2D copy, the host planning gaps and the D2H of one half hide under the kernels of the other.
+    // Device-resident batches (pgpu_batch_run) stay on the single stream, so per-kernel timings remain well defined.
+    int lanes = 2;                         // PGPU_LANES=1 disables
+    int64_t lane_min_bp = int64_t(64) << 20;   // smaller batches are not split (PGPU_LANE_MIN_BP)
+    cudaStream_t lane_stream[2] = {nullptr, nullptr};
+    cudaEvent_t lane_ev[2][16];
+    cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
 };
 
 static thread_local std::string g_create_err;
@@ -1162,6 +1172,94 @@ static int check_opts(pgpu_ctx *ctx, const pgpu_opts *o) {
     return PGPU_OK;
 }
 
+// Two worker threads take the sub-batches in order, each on its own stream with its own copy of the context's host
+// state; the partial results are stitched together in sub-batch order afterwards.  The lane streams are forked
+// from / joined to the context's stream with events, so work queued on that stream (e.g. the stopwatch events of
+// pgpu_timer_*) still brackets the whole call.
+static int run_lanes(pgpu_ctx *ctx, const uint8_t *h_seq, const int64_t *offsets, int n, const pgpu_opts &opts,
+                     RunPlan &plan, const std::vector<std::pair<int, int>> &ranges, pgpu_result *res) {
+    if (!ctx->lane_stream[0]) {
+        for (int k = 0; k < 2; k++) {
+            if (cudaStreamCreateWithFlags(&ctx->lane_stream[k], cudaStreamNonBlocking) != cudaSuccess)
+                return fail(ctx, PGPU_ECUDA, "cudaStreamCreate (lane) failed");
+            for (auto &ev : ctx->lane_ev[k]) cudaEventCreate(&ev);
+            cudaEventCreateWithFlags(&ctx->join_ev[k], cudaEventDisableTiming);
+        }
+        cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
+    }
+    CK(cudaEventRecord(ctx->fork_ev, ctx->stream));
+    const int P = (int)ranges.size();
+    std::vector<std::unique_ptr<pgpu_result>> parts(P);
+    std::vector<int> prc(P, PGPU_OK);
+    std::vector<std::string> perr(P);
+    std::atomic<int> next{0};
+    std::atomic<int64_t> launches{0};
+    auto worker = [&](int k) {
+        cudaSetDevice(ctx->device);
+        pgpu_ctx L = *ctx;          // host-side state is small (prepared model tables); device pointers are shared
+        L.stream = ctx->lane_stream[k];
+        memcpy(L.ev, ctx->lane_ev[k], sizeof(L.ev));
+        L.launches = 0;
+        cudaStreamWaitEvent(L.stream, ctx->fork_ev, 0);
+        for (;;) {
+            const int p = next.fetch_add(1);
+            if (p >= P) break;
+            parts[p].reset(new pgpu_result());
+            pgpu_result *r = parts[p].get();
+            r->pinned = ctx->pinned;
+            r->n_contigs = n;
+            r->summary.resize(n);
+            r->gene_off.assign(n + 1, 0);
+            r->node_off.assign(n + 1, 0);
+            memset(&r->stats, 0, sizeof(r->stats));
+            L.err.clear();
+            RunPlan pl = plan;
+            prc[p] = run_range(&L, h_seq, nullptr, offsets, ranges[p].first, ranges[p].second, opts, pl, r, nullptr);
+            if (prc[p]) { perr[p] = L.err; break; }
+        }
+        cudaEventRecord(ctx->join_ev[k], L.stream);
+        launches += L.launches;
+    };
+    std::thread t1(worker, 1);
+    worker(0);
+    t1.join();
+    for (int k = 0; k < 2; k++) cudaStreamWaitEvent(ctx->stream, ctx->join_ev[k], 0);
+    ctx->launches += launches.load();
+    for (int p = 0; p < P; p++)
+        if (prc[p]) return fail(ctx, prc[p], perr[p]);
+    // stitch: genes of part p follow those of parts 0..p-1
+    for (int p = 0; p < P; p++) {
+        pgpu_result *r = parts[p].get();
+        if (!r) return fail(ctx, PGPU_ECUDA, "lane left a sub-batch unprocessed");
+        const int64_t shift = res->total_genes;
+        for (auto &sg : r->segs) { sg.g0 += shift; res->segs.push_back(sg); }
+        r->segs.clear();  // the pinned buffers now belong to `res`
+        const size_t n0 = res->nodes.size();
+        if (r->have_nodes) {
+            res->nodes.insert(res->nodes.end(), r->nodes.begin(), r->nodes.end());
+            res->have_nodes = true;
+        }
+        for (int c = ranges[p].first; c < ranges[p].second; c++) {
+            res->summary[c] = r->summary[c];
+            res->gene_off[c + 1] = r->gene_off[c + 1] + shift;
+            if (r->have_nodes) res->node_off[c] = r->node_off[c] + (int64_t)n0;
+        }
+        if (r->have_nodes) res->node_off[ranges[p].second] = r->node_off[ranges[p].second] + (int64_t)n0;
+        res->total_genes += r->total_genes;
+        pgpu_stats &S = res->stats;
+        const pgpu_stats &T = r->stats;
+        S.n_contigs += T.n_contigs; S.total_bp += T.total_bp; S.total_nodes += T.total_nodes;
+        S.total_chain_nodes += T.total_chain_nodes; S.n_chains += T.n_chains; S.total_genes += T.total_genes;
+        S.pairs += T.pairs; S.dp_steps += T.dp_steps; S.h2d_bytes += T.h2d_bytes; S.d2h_bytes += T.d2h_bytes;
+        // phase times are per-lane stream times and overlap between lanes: sums, not wall time
+        S.ms_total_device += T.ms_total_device; S.ms_encode += T.ms_encode; S.ms_extract += T.ms_extract;
+        S.ms_score += T.ms_score; S.ms_overlap += T.ms_overlap; S.ms_dp += T.ms_dp; S.ms_trace += T.ms_trace;
+        S.ms_final += T.ms_final; S.ms_h2d += T.ms_h2d; S.ms_d2h += T.ms_d2h;
+        for (int q = 0; q < 4; q++) S.reserved[q] += T.reserved[q];
+    }
+    return PGPU_OK;
+}
+
 static int run_all(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, const int64_t *offsets, int n,
                    const pgpu_opts *opts, pgpu_result **out) {
     if (!ctx) return PGPU_EINVAL;
@@ -1199,21 +1297,37 @@ static int run_all(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, co
             freeb += reserved - used;
     }
     size_t limit = ctx->ws_limit ? ctx->ws_limit : (size_t)(0.6 * (double)freeb);
-    const int64_t bp_budget = std::max<int64_t>((int64_t)(limit / 160), 1 << 20);
+    const int64_t total_bp = n > 0 ? offsets[n] - offsets[0] : 0;
+    const int lanes = (h_seq && !d_seq && ctx->lanes > 1 && n >= 2 && total_bp >= ctx->lane_min_bp) ? 2 : 1;
+    const int64_t bp_budget = std::max<int64_t>((int64_t)(limit / 160) / lanes, 1 << 20);
     RunPlan plan;
-    int lo = 0;
-    while (lo < n) {
+    std::vector<std::pair<int, int>> ranges;
+    for (int lo = 0; lo < n;) {
         int hi = lo;
         int64_t bp = 0;
         while (hi < n && (hi == lo || bp + (offsets[hi + 1] - offsets[hi]) <= bp_budget) && hi - lo < (1 << 22)) {
             bp += offsets[hi + 1] - offsets[hi];
             hi++;
         }
-        tr("sub-batch begin");
-        rc = run_range(ctx, h_seq, d_seq, offsets, lo, hi, *opts, plan, res, nullptr);
-        tr("sub-batch end (buffers released)");
-        if (rc) { delete res; return rc; }
+        ranges.push_back({lo, hi});
         lo = hi;
+    }
+    if (lanes == 2 && ranges.size() == 1) {  // one sub-batch: cut it where the bases split evenly
+        int mid = 1;
+        while (mid < n - 1 && offsets[mid] - offsets[0] < total_bp / 2) mid++;
+        ranges = {{0, mid}, {mid, n}};
+    }
+    if (lanes == 1 || ranges.size() < 2) {
+        for (auto &r : ranges) {
+            tr("sub-batch begin");
+            rc = run_range(ctx, h_seq, d_seq, offsets, r.first, r.second, *opts, plan, res, nullptr);
+            tr("sub-batch end (buffers released)");
+            if (rc) { delete res; return rc; }
+        }
+    } else {
+        rc = run_lanes(ctx, h_seq, offsets, n, *opts, plan, ranges, res);
+        tr("lanes joined");
+        if (rc) { delete res; return rc; }
     }
     res->stats.kernel_launches = ctx->launches - launches0;
     *out = res;
@@ -1250,6 +1364,8 @@ int pgpu_create(int device, pgpu_ctx **out) {
     if (const char *a = getenv("PGPU_DP_ML_MINB")) ctx->dp_ml_minb = atoi(a);
     if (const char *a = getenv("PGPU_EXTRACT_ALGO")) ctx->extract_algo = atoi(a);
     if (const char *a = getenv("PGPU_FINAL_ALGO")) ctx->final_algo = atoi(a);
+    if (const char *a = getenv("PGPU_LANES")) ctx->lanes = atoi(a);
+    if (const char *a = getenv("PGPU_LANE_MIN_BP")) ctx->lane_min_bp = atoll(a);
     // keep freed blocks cached in the stream-ordered pool: sub-batches reuse them without going to the driver
     cudaMemPool_t mp;
     if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
@@ -1269,6 +1385,15 @@ void pgpu_destroy(pgpu_ctx *ctx) {
     if (ctx->d_dcT) cudaFree(ctx->d_dcT);
     if (ctx->d_live) cudaFree(ctx->d_live);
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
+    if (ctx->lane_stream[0]) {
+        for (int k = 0; k < 2; k++) {
+            cudaStreamSynchronize(ctx->lane_stream[k]);
+            for (auto &ev : ctx->lane_ev[k]) cudaEventDestroy(ev);
+            cudaEventDestroy(ctx->join_ev[k]);
+            cudaStreamDestroy(ctx->lane_stream[k]);
+        }
+        cudaEventDestroy(ctx->fork_ev);
+    }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1282,26 +1407,26 @@ int pgpu_set_models(pgpu_ctx *ctx, const void *blobs, int n, size_t stride) {
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->d_raw) { cudaFree(ctx->d_raw); ctx->d_raw = nullptr; }
     if (ctx->d_models) { cudaFree(ctx->d_models); ctx->d_models = nullptr; }
-    ctx->h_raw.resize(n);
-    for (int k = 0; k < n; k++) memcpy(&ctx->h_raw[k], (const char *)blobs + k * stride, sizeof(RawTraining));
+    std::vector<RawTraining> h_raw_v(n);   // host copy of the raw structs, only needed to prepare the device tables
+    for (int k = 0; k < n; k++) memcpy(&h_raw_v[k], (const char *)blobs + k * stride, sizeof(RawTraining));
     CK(cudaMalloc(&ctx->d_raw, n * sizeof(RawTraining)));
     CK(cudaMalloc(&ctx->d_models, n * sizeof(DevModel)));
     if (ctx->d_live) { cudaFree(ctx->d_live); ctx->d_live = nullptr; }
     CK(cudaMalloc(&ctx->d_live, (size_t)n * 2048 * sizeof(uint32_t)));
     {
         std::vector<uint32_t> live((size_t)n * 2048);
-        for (int k = 0; k < n; k++) motif_live_bits(ctx->h_raw[k], live.data() + (size_t)k * 2048);
+        for (int k = 0; k < n; k++) motif_live_bits(h_raw_v[k], live.data() + (size_t)k * 2048);
         CK(cudaMemcpy(ctx->d_live, live.data(), live.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     ctx->h_models.resize(n);
-    for (int k = 0; k < n; k++) prepare_model(ctx->h_raw[k], ctx->h_models[k], ctx->d_raw + k, ctx->d_live + (size_t)k * 2048);
+    for (int k = 0; k < n; k++) prepare_model(h_raw_v[k], ctx->h_models[k], ctx->d_raw + k, ctx->d_live + (size_t)k * 2048);
     {
         // transposed dicodon table: models that are evaluated together (same table, neighbouring GC) get
         // neighbouring columns, so the lanes of k_coding_orf read one or two cache lines per codon
         std::vector<int> ord(n);
         std::iota(ord.begin(), ord.end(), 0);
         std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) {
-            const RawTraining &x = ctx->h_raw[a], &y = ctx->h_raw[b];
+            const RawTraining &x = h_raw_v[a], &y = h_raw_v[b];
             return x.trans_table != y.trans_table ? x.trans_table < y.trans_table : x.gc < y.gc;
         });
         // rows are kDcCols wide (a compile-time stride: one multiply-add per weight address in the kernel); a model
@@ -1311,17 +1436,17 @@ int pgpu_set_models(pgpu_ctx *ctx, const void *blobs, int n, size_t stride) {
         if (n <= kDcCols) {
             std::vector<double> t((size_t)4096 * kDcCols, 0.0);
             for (int c = 0; c < n; c++)
-                for (int i = 0; i < 4096; i++) t[(size_t)i * kDcCols + c] = ctx->h_raw[ord[c]].gene_dc[i];
+                for (int i = 0; i < 4096; i++) t[(size_t)i * kDcCols + c] = h_raw_v[ord[c]].gene_dc[i];
             CK(cudaMalloc(&ctx->d_dcT, t.size() * sizeof(double)));
             CK(cudaMemcpy(ctx->d_dcT, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
         }
     }
-    CK(cudaMemcpy(ctx->d_raw, ctx->h_raw.data(), n * sizeof(RawTraining), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_raw, h_raw_v.data(), n * sizeof(RawTraining), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_models, ctx->h_models.data(), n * sizeof(DevModel), cudaMemcpyHostToDevice));
     ctx->n_models = n;
     ctx->model_gc.resize(n);
     ctx->model_tt.resize(n);
-    for (int k = 0; k < n; k++) { ctx->model_gc[k] = ctx->h_raw[k].gc; ctx->model_tt[k] = ctx->h_raw[k].trans_table; }
+    for (int k = 0; k < n; k++) { ctx->model_gc[k] = h_raw_v[k].gc; ctx->model_tt[k] = h_raw_v[k].trans_table; }
     return PGPU_OK;
 }
 

@@ -414,3 +414,47 @@ def test_gene_only_final_pass_equals_full_final_pass(ctx, capi, closed):
             # field-wise: fancy indexing leaves the padding bytes of a structured copy uninitialised
             assert np.array_equal(nodes[full.genes["start_ndx"][a:b]], gn[a:b, 0])
             assert np.array_equal(nodes[full.genes["stop_ndx"][a:b]], gn[a:b, 1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("many_parts", [False, True])
+def test_two_lane_host_batches_match_single_stream(capi, monkeypatch, many_parts):
+    """host-input batches above PGPU_LANE_MIN_BP run as sub-batches on two worker threads / streams; the stitched
+    result (summaries, genes, gene node records, node arrays, counters) must be identical to the single-stream run"""
+    seqs = [R.synth(20_000 + 3000 * (k % 11), 0.32 + 0.004 * k, 12000 + k) for k in range(90)] + [b"", R.synth(50, .5, 1)]
+    arrs = [np.frombuffer(s, np.uint8) for s in seqs]
+    off = np.zeros(len(arrs) + 1, np.int64)
+    np.cumsum([len(a) for a in arrs], out=off[1:])
+    flat = np.ascontiguousarray(np.concatenate(arrs))
+    o = capi.make_opts(meta=True, want_nodes=True)
+    monkeypatch.setenv("PGPU_LANES", "1")
+    c1 = capi.Context(0)
+    c1.set_models(R.bins_blob(), 50)
+    r1 = c1.find_genes_batch(flat, off, o)
+    monkeypatch.setenv("PGPU_LANES", "2")
+    monkeypatch.setenv("PGPU_LANE_MIN_BP", "0")
+    c2 = capi.Context(0)
+    c2.set_models(R.bins_blob(), 50)
+    if many_parts:
+        capi.check(capi.lib.pgpu_set_workspace_limit(c2.handle, 1), c2.handle)  # -> 1 Mbp per sub-batch, several per lane
+    for rep in range(2):  # the second call reuses the lane streams and the recycled buffers
+        r2 = c2.find_genes_batch(flat, off, o)
+        assert r1.summary.tobytes() == r2.summary.tobytes()
+        assert np.array_equal(r1.gene_off, r2.gene_off)
+        cmp_int(r2.genes, r1.genes, "lanes.genes")
+        assert r2.gene_nodes.tobytes() == r1.gene_nodes.tobytes()
+        for k in (0, 1, 44, 45, 46, 89):
+            assert r1.nodes(k).tobytes() == r2.nodes(k).tobytes()
+        for key in ("n_contigs", "total_bp", "total_nodes", "total_chain_nodes", "n_chains", "total_genes", "pairs", "dp_steps"):
+            assert r1.stats[key] == r2.stats[key], key
+        for k in range(len(seqs)):
+            a, b = r2.gene_off[k], r2.gene_off[k + 1]
+            g = np.zeros(b - a, dtype=capi.GENE_DTYPE)
+            capi.check(capi.lib.pgpu_result_genes(r2.handle, k, capi.ptr(g)))
+            cmp_int(g, r1.genes[a:b], f"lanes.contig{k}")
+        r2.free()
+    # the genes-only path (no node arrays) through the lanes as well
+    o2 = capi.make_opts(meta=True, want_nodes=False)
+    ra, rb = c1.find_genes_batch(flat, off, o2), c2.find_genes_batch(flat, off, o2)
+    assert ra.gene_nodes.tobytes() == rb.gene_nodes.tobytes() and ra.genes.tobytes() == rb.genes.tobytes()
+    ra.free(); rb.free(); r1.free(); c1.close(); c2.close()
