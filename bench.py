@@ -94,7 +94,7 @@ class Dist:
 
 
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons sampled every 200 ms DURING the timed region (B200_PROFILING.md's clocks line).
+    """SM clock and throttle reasons sampled every 250 ms DURING the timed region (B200_PROFILING.md's clocks line).
     Read through NVML in this process (the library nvidia-smi itself queries): starting an `nvidia-smi` process per
     sample initialises the driver API every time and was seen to delay the launches of the step being timed by tens
     of ms.  Falls back to ONE `nvidia-smi -lms 200` process started before the region when pynvml is missing."""
@@ -145,7 +145,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append((sm, self.sm_max, [name for name, m in zip(self.REASONS, masks) if r & m]))
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.25)
 
     def stop(self):
         if self.nvml is None:

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <numeric>
@@ -90,10 +91,11 @@ struct pgpu_ctx {
     int dp_algo = 5;           // 5: k_dp_ml for multi-model batches, k_dp_dq otherwise (default); 6: k_dp_ml always;
                                // 3/4: k_dp_dq, 1/2: k_dp_fast, 0: all-pairs k_dp (PGPU_DP_ALGO=n)
     std::shared_ptr<struct PinnedPool> pinned;  // shared with the results it backs (they may outlive the context)
-    // Host-input calls (pgpu_find_genes_batch) on large batches run as two halves on two worker threads / streams
-    // ("lanes"): the H2D copy, the host planning gaps and the D2H of one half hide under the kernels of the other.
+    // Optional: host-input calls (pgpu_find_genes_batch) on large batches run as sub-batches on two worker threads /
+    // streams ("lanes"), so that the H2D copy, the host planning gaps and the D2H of one hide under the kernels of the other.
     // Device-resident batches (pgpu_batch_run) stay on the single stream, so per-kernel timings remain well defined.
-    int lanes = 2;                         // PGPU_LANES=1 disables
+    int lanes = 1;                         // PGPU_LANES=2 enables.  Off by default: on the 630 Mbp bench shard the two
+                                           // half-size pipelines interleave no faster than one (117 vs 122 ms per step)
     int64_t lane_min_bp = int64_t(64) << 20;   // smaller batches are not split (PGPU_LANE_MIN_BP)
     cudaStream_t lane_stream[2] = {nullptr, nullptr};
     cudaEvent_t lane_ev[2][16];
@@ -367,6 +369,9 @@ struct RunPlan {
     int forced_first_pass = 1;
     int forced_is_meta = 0;
     TrainRequest *train = nullptr;  // pgpu_train: run the training pass on the (single) extraction
+    // lanes: called right before / after the input copy is queued on the sub-batch's stream (run_lanes chains the
+    // copies of consecutive sub-batches, so that one half computes while the other half is still being copied)
+    std::function<void(cudaStream_t)> before_h2d, after_h2d;
 };
 
 static int train_stage(pgpu_ctx *ctx, DevPool &pool, DevBatch &B, const ExtractInfo &X, RunOpts ro, int gc_count,
@@ -436,7 +441,9 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     } else {
         d_ascii_local = pool.alloc<uint8_t>(atot + 16);
         if (pool.failed) return PGPU_ENOMEM;
+        if (plan.before_h2d) plan.before_h2d(st);
         if (atot) CK(cudaMemcpyAsync(d_ascii_local, h_seq + abase, atot, cudaMemcpyHostToDevice, st));
+        if (plan.after_h2d) plan.after_h2d(st);
         B.ascii = d_ascii_local;
         S.h2d_bytes += atot;
     }
@@ -1194,6 +1201,11 @@ static int run_lanes(pgpu_ctx *ctx, const uint8_t *h_seq, const int64_t *offsets
     std::vector<std::string> perr(P);
     std::atomic<int> next{0};
     std::atomic<int64_t> launches{0};
+    // the input copies are chained in sub-batch order: two copies issued together would share the link and finish
+    // together, and neither lane could start computing before both were done
+    std::vector<cudaEvent_t> h2d_ev(P, nullptr);
+    std::unique_ptr<std::atomic<int>[]> h2d_issued(new std::atomic<int>[P]);
+    for (int p = 0; p < P; p++) { cudaEventCreateWithFlags(&h2d_ev[p], cudaEventDisableTiming); h2d_issued[p].store(0); }
     auto worker = [&](int k) {
         cudaSetDevice(ctx->device);
         pgpu_ctx L = *ctx;          // host-side state is small (prepared model tables); device pointers are shared
@@ -1214,7 +1226,17 @@ static int run_lanes(pgpu_ctx *ctx, const uint8_t *h_seq, const int64_t *offsets
             memset(&r->stats, 0, sizeof(r->stats));
             L.err.clear();
             RunPlan pl = plan;
+            pl.before_h2d = [&, p](cudaStream_t st) {
+                if (p == 0) return;
+                while (!h2d_issued[p - 1].load()) std::this_thread::yield();   // its record must be queued first
+                cudaStreamWaitEvent(st, h2d_ev[p - 1], 0);
+            };
+            pl.after_h2d = [&, p](cudaStream_t st) {
+                cudaEventRecord(h2d_ev[p], st);
+                h2d_issued[p].store(1);
+            };
             prc[p] = run_range(&L, h_seq, nullptr, offsets, ranges[p].first, ranges[p].second, opts, pl, r, nullptr);
+            h2d_issued[p].store(1);  // also when the sub-batch failed before its copy: nobody may wait forever
             if (prc[p]) { perr[p] = L.err; break; }
         }
         cudaEventRecord(ctx->join_ev[k], L.stream);
@@ -1224,6 +1246,7 @@ static int run_lanes(pgpu_ctx *ctx, const uint8_t *h_seq, const int64_t *offsets
     worker(0);
     t1.join();
     for (int k = 0; k < 2; k++) cudaStreamWaitEvent(ctx->stream, ctx->join_ev[k], 0);
+    for (auto &ev : h2d_ev) cudaEventDestroy(ev);
     ctx->launches += launches.load();
     for (int p = 0; p < P; p++)
         if (prc[p]) return fail(ctx, prc[p], perr[p]);
