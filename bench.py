@@ -342,7 +342,7 @@ def main():
     ctx.set_models(R.bins_blob(), 50)
     opts = _capi.make_opts(meta=True)
 
-    def timed(fn, steps):
+    def timed(fn, steps, per_step=None):
         """K steps bracketed by barrier + synchronize; CUDA events on the library's stream; max over ranks"""
         D.barrier()
         ctx.timer_start()
@@ -351,6 +351,8 @@ def main():
         for _ in range(steps):
             last = None  # release the previous result first: its pinned buffer is reused by the next step
             last = fn()
+            if per_step is not None:
+                per_step.append(last.stats)
         ms = ctx.timer_stop()
         wall = (time.perf_counter() - t0) * 1e3
         torch.cuda.synchronize()
@@ -368,7 +370,8 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if rank == 0:
         sampler.start()
-    ms, wall_ms, res = timed(lambda: batch.run(opts), args.steps)
+    step_stats = []
+    ms, wall_ms, res = timed(lambda: batch.run(opts), args.steps, step_stats)
     clocks = sampler.stop() if rank == 0 else None
     stats = res.stats
     genes_rank = int(res.summary["n_genes"].sum())
@@ -390,7 +393,7 @@ def main():
     if rank == 0:
         per_step = ms / args.steps
         peak, peak_src = measured_peak()
-        dp_ms = stats["ms_dp"]
+        dp_ms = float(np.mean([t["ms_dp"] for t in step_stats]))  # CUDA events on the launching stream, every timed step
         achieved = DP_BYTES_PER_STEP * stats["dp_steps"] / (dp_ms * 1e-3) / 1e9 if dp_ms > 0 else 0.0
         traffic = None  # dram__bytes_read+write of the DP kernel per launch, from the committed ncu capture
         try:
@@ -411,9 +414,10 @@ def main():
             "gpu_launches": int(tot_launch * args.steps),
             "roofline": {"bound": "hbm", "kernel": "k_dp_ml (connection-scoring DP, one lane per model)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "note": "the DP is latency / issue bound (ncu: 34 % issue-active, ~400 warp-instructions per warp "
-                                 "step covering ~11 chains), not HBM bound; DRAM traffic 1.5x the algorithmic bytes "
-                                 "(suffix-maximum arrays of the window maximum)",
+                         "note": "kernel_ms = mean over the timed steps of the DP phase (k_dp_ml + k_chain_best) between CUDA events "
+                                 "on the launching stream; the DP is latency bound (ncu in profiles/: issue-active 38 %, "
+                                 "~365 warp-instructions per warp step covering ~11 chains), not HBM bound; DRAM traffic "
+                                 "1.5x the algorithmic bytes (suffix-maximum arrays of the window maximum)",
                          "algorithmic_bytes_per_dp_step": DP_BYTES_PER_STEP, "dp_steps_per_launch": int(stats["dp_steps"]),
                          "kernel_ms": dp_ms, "node_pairs_per_s": stats["pairs"] / (dp_ms * 1e-3) if dp_ms > 0 else None},
             "node_pairs_per_s_job": tot_pairs / (per_step * 1e-3),
