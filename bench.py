@@ -350,9 +350,10 @@ def main():
         last = None
         for _ in range(steps):
             last = None  # release the previous result first: its pinned buffer is reused by the next step
+            t1 = time.perf_counter()
             last = fn()
             if per_step is not None:
-                per_step.append(last.stats)
+                per_step.append(dict(last.stats, wall_ms=(time.perf_counter() - t1) * 1e3))
         ms = ctx.timer_stop()
         wall = (time.perf_counter() - t0) * 1e3
         torch.cuda.synchronize()
@@ -379,11 +380,12 @@ def main():
 
     # ---- end-to-end leg: C ABI call with host buffers, H2D + D2H inside ----
     res = None
-    for _ in range(2):
+    for _ in range(max(2, args.warmup)):
         r = None
         r = ctx.find_genes_batch(host, offsets, opts)
     r = None
-    ms_e2e, wall_e2e, res2 = timed(lambda: ctx.find_genes_batch(host, offsets, opts), args.steps)
+    e2e_steps = []
+    ms_e2e, wall_e2e, res2 = timed(lambda: ctx.find_genes_batch(host, offsets, opts), args.steps, e2e_steps)
     st2 = res2.stats
     batch.free()
 
@@ -410,14 +412,17 @@ def main():
             "e2e": {"value": tot_bp / (ms_e2e / args.steps * 1e-3) / 1e6, "unit": "Mbp/s",
                     "h2d_bytes_per_step": int(st2["h2d_bytes"]), "d2h_bytes_per_step": int(st2["d2h_bytes"]),
                     "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e / args.steps,
+                    "h2d_ms_per_step": [round(t["ms_h2d"], 2) for t in e2e_steps],   # the input copy alone, per timed step
+                    "wall_ms_steps": [round(t["wall_ms"], 1) for t in e2e_steps],
+                    "device_ms_steps": [round(t["ms_total_device"], 1) for t in e2e_steps],
                     "api": "pgpu_find_genes_batch (C ABI, pinned host input)"},
             "gpu_launches": int(tot_launch * args.steps),
             "roofline": {"bound": "hbm", "kernel": "k_dp_ml (connection-scoring DP, one lane per model)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "note": "kernel_ms = mean over the timed steps of the DP phase (k_dp_ml + k_chain_best) between CUDA events "
-                                 "on the launching stream; the DP is latency bound (ncu in profiles/: issue-active 38 %, "
-                                 "~365 warp-instructions per warp step covering ~11 chains), not HBM bound; DRAM traffic "
-                                 "1.5x the algorithmic bytes (suffix-maximum arrays of the window maximum)",
+                                 "on the launching stream; the DP is latency bound (ncu in profiles/: issue-active 39 %, "
+                                 "~370 warp-instructions per warp step covering ~11 chains), not HBM bound; DRAM traffic "
+                                 "1.2x the algorithmic bytes (suffix-maximum arrays of the window maximum)",
                          "algorithmic_bytes_per_dp_step": DP_BYTES_PER_STEP, "dp_steps_per_launch": int(stats["dp_steps"]),
                          "kernel_ms": dp_ms, "node_pairs_per_s": stats["pairs"] / (dp_ms * 1e-3) if dp_ms > 0 else None},
             "node_pairs_per_s_job": tot_pairs / (per_step * 1e-3),
@@ -425,6 +430,7 @@ def main():
                                                            "ms_trace", "ms_final", "ms_d2h", "ms_total_device")},
                                     host_issue_ms=stats["host_ms"]),
             "wall_ms_per_step": wall_ms / args.steps,
+            "wall_ms_steps": [round(t["wall_ms"], 1) for t in step_stats],
             "totals": {"bp": int(tot_bp), "genes": int(tot_genes), "dp_steps": int(tot_steps), "pairs": int(tot_pairs),
                        "chains_rank0": int(stats["n_chains"]), "nodes_rank0": int(stats["total_nodes"])},
             "clocks": clocks,
