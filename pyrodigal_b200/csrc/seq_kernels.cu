@@ -4,10 +4,10 @@
 // (lib.pyx:1905-2117) + Nodes._sort (lib.pyx:2489, node.c:1578-1587).
 //
 // B200 design: the sequence is streamed once (encode: 1 B in, 2 B out per base, 16-byte stores); node
-// extraction is a backward scan per (contig, strand, frame) over the 1-byte codon-code array that first
-// marks node positions in two bitmaps, a prefix sum over bitmap words then gives every node its final
-// rank in (ndx, strand) order, and a second scan writes the nodes straight into their sorted slots --
-// no sort pass and no per-node atomics.
+// extraction works on per-(strand, frame) codon bitmaps in scan order, one thread per 32 codons
+// (extract_device.cuh): a first pass marks node positions in two bitmaps, a prefix sum over bitmap words
+// gives every node its final rank in (ndx, strand) order, and a second pass writes the nodes straight into
+// their sorted slots -- no sort pass and no per-node atomics.
 #include "extract_device.cuh"
 #include "kernels.cuh"
 
@@ -146,76 +146,8 @@ __device__ __forceinline__ bool masked_any(const int32_t *__restrict__ m, int n,
     return lo < n && m[2 * lo] < end;
 }
 
-template <bool FILL>
-__global__ void __launch_bounds__(128) k_extract(DevBatch B, int n_ext, RunOpts o) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_ext * 6) return;
-    const int e = t / 6, sf = t % 6, rev = sf / 3, f = sf % 3;
-    const ExtractInfo X = B.exts[e];
-    const int slen = X.slen;
-    if (slen < 3) return;
-    const uint8_t *__restrict__ cod = B.cod + X.doff;
-    uint32_t *bits = (rev ? B.bits_rev : B.bits_fwd) + X.woff;
-    const uint32_t *__restrict__ bf = B.bits_fwd + X.woff;
-    const uint32_t *__restrict__ br = B.bits_rev + X.woff;
-    const int32_t *__restrict__ wb = B.wordbase + X.woff;
-    const int32_t *__restrict__ masks = B.masks + 2 * (int64_t)X.mask_off;
-
-    auto emit = [&](int pos, int type, int sv, int edge) {
-        const int p = rev ? slen - 1 - pos : pos;
-        if (!FILL) {
-            atomicOr(&bits[p >> 5], 1u << (p & 31));
-        } else {
-            const int w = p >> 5, b = p & 31;
-            const uint32_t lt = (1u << b) - 1u;
-            int slot = wb[w] + __popc(bf[w] & lt) + __popc(br[w] & lt) + (rev ? (int)((bf[w] >> b) & 1u) : 0);
-            int conv = (!o.closed && type != 3 && !edge && (rev ? p >= slen - 3 : p <= 2)) ? CLS_CONV : 0;
-            B.ndx[slot] = p;
-            B.stop_val[slot] = rev ? slen - 1 - sv : sv;
-            B.cls[slot] = (uint8_t)(type | (rev ? CLS_REV : 0) | (edge ? CLS_EDGE : 0) | conv | ((p % 3) << CLS_FRAME_SHIFT));
-        }
-    };
-
-    // initial "last" of this frame: lib.pyx:1933-1939
-    int last = slen + ((f - slen % 3 + 3) % 3);
-    if (!o.closed)
-        while (last + 3 > slen) last -= 3;
-    bool last_real = false, saw = false;
-    int min_dist = o.min_edge_gene;
-    int i = slen - 3;
-    i -= ((i % 3) - f + 3) % 3;  // largest i <= slen-3 in this frame
-    for (; i >= 0; i -= 3) {
-        int c = rev ? cod[slen - 3 - i] : cod[i];
-        const bool has_n = c & 64;
-        c &= 63;
-        if (rev) c = rev_code(c);
-        if (!has_n && ((X.stopmask >> c) & 1)) {
-            if (saw) emit(last, 3, i, !last_real);
-            min_dist = o.min_gene;
-            last = i;
-            last_real = true;
-            saw = false;
-            continue;
-        }
-        if (last >= slen) continue;
-        if (X.n_masks) {
-            bool hit = rev ? masked_any(masks, X.n_masks, slen - last - 1, slen - i - 1)
-                           : masked_any(masks, X.n_masks, i, last);
-            if (hit) continue;
-        }
-        if (last - i + 3 >= min_dist && !has_n && ((X.startmask >> c) & 1)) {
-            const int b0 = c & 3;
-            emit(i, b0 == 0 ? 0 : (b0 == 1 ? 1 : 2), last, 0);
-            saw = true;
-        } else if (i <= 2 && !o.closed && last - i > o.min_edge_gene) {
-            emit(i, 0, last, 1);
-            saw = true;
-        }
-    }
-    if (saw) emit(last, 3, f - 6, !last_real);
-}
-
-// Warp-cooperative, chunked version of the same scan: one warp per (extraction, chunk, strand, frame) looks at
+// Warp-cooperative, chunked scan (used for batches with N-run masks; the default path is the bit-parallel
+// k_extract_b below): one warp per (extraction, chunk, strand, frame) looks at
 // 32 codons of its frame per iteration.  The sequential state of the reference's loop (lib.pyx:1940-2010)
 // depends only on the nearest stop codon seen earlier in scan order and on "has a start been emitted since that
 // stop", both of which are bit operations on the ballot masks of the block (stops S, qualifying starts Q):
