@@ -114,7 +114,7 @@ __host__ __device__ inline void extract_word(const ExtractFrame &F, int w, Emit 
             const uint32_t Q = Cw & seg & qm;
             uint32_t E = 0;
             const int ul = F.n_codons - 1 - u0;  // the last codon of the frame (i <= 2): edge start, lib.pyx:1996-2003
-            if (!F.closed && ul >= lo && ul < b && !((Q >> ul) & 1u) && 3 * (F.n_codons - 1 - ug) > F.min_edge_gene)
+            if (!F.closed && ul >= lo && ul < b && !((Q >> ul) & 1u) && (int64_t)3 * (F.n_codons - 1 - ug) > F.min_edge_gene)
                 E = 1u << ul;
             uint32_t all = Q | E;
             if (all) saw = true;
