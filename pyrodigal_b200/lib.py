@@ -384,10 +384,16 @@ class Node:
 
 
 class Nodes(typing.Sequence):
-    """Sorted node array of one contig as a numpy structured array (`_capi.NODE_DTYPE`)."""
+    """Sorted node array of one contig as a numpy structured array (`_capi.NODE_DTYPE`).
+
+    The operator-level methods of the reference (`extract`, `sort`, `reset_scores`, `score`, lib.pyx:2512-2595) are
+    mirrored on top of the C ABI's operator twins (`pgpu_extract_nodes`, `pgpu_score_nodes`): the GPU extracts
+    straight into sorted order, so `extract` already returns what the reference has after `extract` + `sort`."""
 
     def __init__(self, array=None):
         self.array = np.zeros(0, dtype=_capi.NODE_DTYPE) if array is None else array
+        self._params = None     # how the nodes were extracted (pgpu_score_nodes re-extracts with the same options)
+        self._scored = False    # nodes that were scored once carry converted edge flags (SURVEY T6)
 
     def __len__(self):
         return len(self.array)
@@ -398,13 +404,91 @@ class Nodes(typing.Sequence):
         return Node(self, self.array[index])
 
     def copy(self):
-        return Nodes(self.array.copy())
+        new = Nodes(self.array.copy())
+        new._params, new._scored = self._params, self._scored
+        return new
+
+    __copy__ = copy
+
+    def clear(self):
+        """Remove all nodes from the node list (lib.pyx:2512-2516)."""
+        self.array = np.zeros(0, dtype=_capi.NODE_DTYPE)
+        self._params, self._scored = None, False
+
+    def extract(self, sequence, *, closed=False, min_gene=90, min_edge_gene=60, translation_table=11):
+        """Nodes.extract (lib.pyx:2518-2560, = add_nodes) on the GPU; returns the number of nodes added.
+
+        The nodes arrive in (index, strand) order, i.e. as the reference has them after `sort()`."""
+        if translation_table not in TRANSLATION_TABLES:
+            raise ValueError(f"{translation_table} is not a valid translation table index")
+        if min_gene <= 0 or min_edge_gene <= 0:
+            raise ValueError("`min_gene` and `min_edge_gene` must be strictly positive")
+        seq = sequence if isinstance(sequence, Sequence) else Sequence(sequence)
+        opts = _capi.make_opts(meta=False, closed=closed, mask=seq._mask, min_mask=seq._mask_size, min_gene=min_gene,
+                               min_edge_gene=min_edge_gene, max_overlap=min(60, min_gene))
+        ctx = _context_for(_LazyBins.get()._blob_bytes(), 50)  # extraction needs no model; any context will do
+        with ctx.lock:
+            out = ctx.extract_nodes(seq._ascii, translation_table, opts)
+        n = len(out["ndx"])
+        new = np.zeros(n, dtype=_capi.NODE_DTYPE)
+        for name in ("ndx", "stop_val", "strand", "type", "edge"):
+            new[name] = out[name]
+        first = len(self.array) == 0
+        self.array = new if first else np.concatenate([self.array, new])
+        self._params = dict(closed=bool(closed), min_gene=min_gene, min_edge_gene=min_edge_gene,
+                            translation_table=translation_table) if first else None
+        self._scored = False
+        return n
+
+    def _is_sorted(self):
+        a = self.array
+        if len(a) < 2:
+            return True
+        d = np.diff(a["ndx"].astype(np.int64))
+        # compare_nodes (node.c:1578-1587): by index, forward strand first
+        return bool(np.all((d > 0) | ((d == 0) & (a["strand"][:-1] >= a["strand"][1:]))))
+
+    def sort(self):
+        """Nodes.sort (lib.pyx:2591-2595).  Extraction on the GPU already emits the sorted order, so this only checks."""
+        if not self._is_sorted():
+            raise NotImplementedError("nodes of several extractions were concatenated: clear() before extract()")
+
+    def reset_scores(self):
+        """Nodes.reset_scores (node.c:176-197): scores to zero, trace pointers to -1; the edge flags are kept."""
+        a = self.array
+        for name in ("score", "cscore", "sscore", "rscore", "tscore", "uscore", "mot_score"):
+            a[name] = 0.0
+        for name in ("rbs", "mot_len", "mot_ndx", "mot_spacer", "mot_spacendx", "star_ptr", "elim"):
+            a[name] = 0
+        a["traceb"] = a["tracef"] = -1
+        a["ov_mark"] = -1
+
+    def score(self, sequence, training_info, *, closed=False, is_meta=False):
+        """Nodes.score (lib.pyx:2569-2589, = score_nodes) on the GPU for the nodes of `sequence` held by this object."""
+        seq = sequence if isinstance(sequence, Sequence) else Sequence(sequence)
+        p = self._params or {}
+        opts = _capi.make_opts(meta=False, single_model=0, closed=closed, mask=seq._mask, min_mask=seq._mask_size,
+                               min_gene=p.get("min_gene", 90), min_edge_gene=p.get("min_edge_gene", 60),
+                               max_overlap=min(60, p.get("min_gene", 90)))
+        ctx = _context_for(bytes(training_info), 1)
+        with ctx.lock:
+            scored = ctx.score_nodes(seq._ascii, 0, opts, is_meta=is_meta, first_pass=not self._scored)
+        a = self.array
+        if (len(scored) != len(a) or not np.array_equal(scored["ndx"], a["ndx"])
+                or not np.array_equal(scored["strand"], a["strand"]) or not np.array_equal(scored["type"], a["type"])):
+            raise ValueError("the nodes were not extracted from this sequence with these options "
+                             "(translation table, `closed`, minimum gene lengths)")
+        for name in ("cscore", "sscore", "rscore", "tscore", "uscore", "rbs", "mot_len", "mot_ndx", "mot_spacer",
+                     "mot_spacendx", "mot_score", "gc_cont", "edge"):
+            a[name] = scored[name]
+        self._scored = True
 
     def __getstate__(self):
-        return {"array": self.array}
+        return {"array": self.array, "params": self._params, "scored": self._scored}
 
     def __setstate__(self, state):
         self.array = state["array"]
+        self._params, self._scored = state.get("params"), state.get("scored", False)
 
 
 def _codon_masks(tt):
