@@ -138,11 +138,34 @@ class TrainingInfo:
     def __repr__(self):
         return f"<pyrodigal_b200.TrainingInfo gc={self.gc!r} translation_table={self.translation_table!r}>"
 
+    def to_dict(self):
+        """The constructor's keyword arguments as plain Python objects (lib.pyx:4829-4862), e.g. for JSON."""
+        return {
+            "gc": self.gc,
+            "translation_table": self.translation_table,
+            "start_weight": self.start_weight,
+            "bias": self.bias.tolist(),
+            "type_weights": self.type_weights.tolist(),
+            "uses_sd": self.uses_sd,
+            "rbs_weights": self.rbs_weights.tolist(),
+            "upstream_compositions": self.upstream_compositions.tolist(),
+            "motif_weights": self.motif_weights.tolist(),
+            "missing_motif_weight": self.missing_motif_weight,
+            "coding_statistics": self.coding_statistics.tolist(),
+        }
+
+    def __sizeof__(self):
+        return TRAINING_SIZE + object.__sizeof__(self)
+
     def __getstate__(self):
         return {"raw": self._raw.tobytes()}
 
     def __setstate__(self, state):
-        self._raw = np.frombuffer(state["raw"], dtype=_T_DTYPE).copy()
+        if "raw" in state:
+            self._raw = np.frombuffer(state["raw"], dtype=_T_DTYPE).copy()
+        else:  # the reference pickles the `to_dict` form (lib.pyx:4024-4045)
+            state = dict(state)
+            self.__init__(state.pop("gc"), **state)
 
     def __eq__(self, other):
         return isinstance(other, TrainingInfo) and self._raw.tobytes() == other._raw.tobytes()
@@ -150,17 +173,40 @@ class TrainingInfo:
     def __hash__(self):
         return hash(self._raw.tobytes()[:2048])
 
-    translation_table = property(lambda s: int(s._raw[0]["trans_table"]))
-    gc = property(lambda s: float(s._raw[0]["gc"]))
-    start_weight = property(lambda s: float(s._raw[0]["st_wt"]))
-    uses_sd = property(lambda s: bool(s._raw[0]["uses_sd"]))
-    missing_motif_weight = property(lambda s: float(s._raw[0]["no_mot"]))
-    bias = property(lambda s: s._raw[0]["bias"])
-    type_weights = property(lambda s: s._raw[0]["type_wt"])
-    rbs_weights = property(lambda s: s._raw[0]["rbs_wt"])
-    upstream_compositions = property(lambda s: s._raw[0]["ups_comp"])
-    motif_weights = property(lambda s: s._raw[0]["mot_wt"])
-    coding_statistics = property(lambda s: s._raw[0]["gene_dc"])
+    def _scalar(field, cast):
+        def fget(self):
+            return cast(self._raw[0][field])
+
+        def fset(self, value):
+            if field == "trans_table" and value not in TRANSLATION_TABLES:
+                raise ValueError(f"{value} is not a valid translation table index")
+            self._raw[0][field] = value
+        return property(fget, fset)
+
+    def _array(field):
+        def fget(self):
+            return self._raw[0][field]
+
+        def fset(self, value):
+            dst = self._raw[0][field]
+            src = np.asarray(value, dtype=np.float64)
+            if src.size != dst.size:
+                raise ValueError(f"expected {dst.size} values, got {src.size}")
+            dst[...] = src.reshape(dst.shape)
+        return property(fget, fset)
+
+    translation_table = _scalar("trans_table", int)
+    gc = _scalar("gc", float)
+    start_weight = _scalar("st_wt", float)
+    uses_sd = _scalar("uses_sd", bool)
+    missing_motif_weight = _scalar("no_mot", float)
+    bias = _array("bias")
+    type_weights = _array("type_wt")
+    rbs_weights = _array("rbs_wt")
+    upstream_compositions = _array("ups_comp")
+    motif_weights = _array("mot_wt")
+    coding_statistics = _array("gene_dc")
+    del _scalar, _array
 
 
 class MetagenomicBin:
@@ -283,7 +329,24 @@ class Mask:
 
 
 class Masks(list):
-    pass
+    """List of `Mask` regions (lib.pyx:345-470); pickles as the reference does, as a list of (begin, end) pairs."""
+
+    def copy(self):
+        return Masks(Mask(m.begin, m.end) for m in self)
+
+    __copy__ = copy
+
+    def __getstate__(self):
+        return [(m.begin, m.end) for m in self]
+
+    def __setstate__(self, state):
+        self[:] = [Mask(b, e) for b, e in state]
+
+    def __reduce__(self):
+        return (Masks, (), self.__getstate__())
+
+    def __sizeof__(self):
+        return 8 * len(self) + object.__sizeof__(self)
 
 
 _ENC = np.full(256, 6, dtype=np.uint8)
@@ -341,6 +404,40 @@ class Sequence(typing.Sized):
     def gc_known(self):
         gc, unk = self._counts()
         return gc / (len(self) - unk) if len(self) > unk else 0.0
+
+    def start_probability(self):
+        """Start codon probability estimated from the GC content (lib.pyx:983-990)."""
+        gc = self.gc_known
+        p_atg = (1 - gc) * (1 - gc) * gc / 8
+        p_gtg = gc * (1 - gc) * gc / 8
+        p_ttg = (1 - gc) * (1 - gc) * gc / 8
+        return p_atg + p_gtg + p_ttg
+
+    def stop_probability(self):
+        """Stop codon probability estimated from the GC content (lib.pyx:992-999)."""
+        gc = self.gc_known
+        p_tga = (1 - gc) * (1 - gc) * gc / 8.0
+        p_tag = (1 - gc) * gc * (1 - gc) / 8.0
+        p_taa = (1 - gc) * (1 - gc) * (1 - gc) / 8.0
+        return p_tga + p_tag + p_taa
+
+    def __sizeof__(self):
+        return len(self) + object.__sizeof__(self)
+
+    def __getstate__(self):
+        # the reference's keys (lib.pyx:616-630) plus what this mirror needs to rebuild itself
+        return {"slen": len(self), "gc": self.gc, "masks": self.masks, "digits": bytearray(self.digits.tobytes()),
+                "ascii": self._ascii.tobytes(), "mask": self._mask, "mask_size": self._mask_size}
+
+    def __setstate__(self, state):
+        if "ascii" in state:
+            self._ascii = np.frombuffer(state["ascii"], dtype=np.uint8)
+        else:  # a state pickled by the reference: digits only
+            self._ascii = np.frombuffer(b"AGCTNNN", dtype=np.uint8)[np.frombuffer(bytes(state["digits"]), dtype=np.uint8)]
+        self._digits = None
+        self._mask, self._mask_size = state.get("mask", bool(len(state.get("masks", ())))), state.get("mask_size", 50)
+        self._masks = state.get("masks")
+        self._gc_count = self._unknown = None
 
     @property
     def masks(self):
