@@ -12,6 +12,10 @@
  * are written into caller-owned buffers; pgpu_result objects are owned by the library until
  * pgpu_result_free().  Plain pointers and sizes only -- no torch / CUDA types in signatures.
  * All compute runs on the GPU: there is NO CPU fallback; without a CUDA device pgpu_create fails.
+ * Threading: a context owns one stream; calls on the SAME context must not overlap (the Python mirror
+ * holds a lock per context), different contexts may be used from different threads concurrently.
+ * (The reference's find_genes is re-entrant because every call allocates its own scorer / nodes / genes,
+ * lib.pyx:5424-5426; here the per-call state lives in the context's stream-ordered workspace.)
  */
 #ifndef PYRODIGAL_B200_H
 #define PYRODIGAL_B200_H
