@@ -85,3 +85,16 @@ def test_high_gc_long_orfs():
     # GC-rich sequence: long ORFs spanning many words, so the look-back crosses several words
     check(R.synth(200000, 0.75, 9))
     check(R.synth(200000, 0.75, 9), tt=4, closed=True)
+
+
+def test_randomised_parameters():
+    """seeded sweep over length, GC content, unknown-base fraction, end mode, translation table and the two length
+    thresholds (the word function's masks depend on all of them)"""
+    rng = np.random.default_rng(20261017)
+    tables = [1, 2, 4, 11, 22, 23, 25, 33]
+    for it in range(160):
+        length = int(rng.integers(0, 4000)) if it % 4 else int(rng.integers(0, 140))
+        seq = R.synth(length, float(rng.uniform(0.2, 0.8)), 50000 + it, n_frac=float(rng.choice([0.0, 0.0, 0.01, 0.1])))
+        mg = int(rng.choice([1, 2, 3, 4, 5, 6, 29, 30, 31, 60, 89, 90, 91, 92, 93, 96, 99, 180, 300, 2000]))
+        meg = int(rng.choice([1, 2, 3, 4, 30, 59, 60, 61, 62, 63, 90, 120, 600]))
+        check(seq, tt=int(rng.choice(tables)), closed=bool(rng.integers(0, 2)), min_gene=mg, min_edge_gene=meg)
