@@ -23,6 +23,7 @@
 
 #include "kernels.cuh"
 #include "codon_masks.hpp"
+#include "extract_device.cuh"
 #include "train_host.hpp"  // RawTraining + host half of the training path
 
 using namespace pgpu;
@@ -87,6 +88,8 @@ struct pgpu_ctx {
                                // (PGPU_EXTRACT_ALGO; batches with N-run masks always use 1)
     int final_algo = 2;        // meta mode without node arrays: 2 = final scoring pass over the genes' ORFs only,
                                // 1 = over every node as with want_nodes (PGPU_FINAL_ALGO)
+    bool codon_lut = false;    // PGPU_CODON_LUT=1: k_codon_bits reads codon flags from a per-table byte table (written
+                               // after the last GPU run of round 1: logic checked by the host emulation only, so off)
     bool dp_verify = false;    // PGPU_DP_VERIFY=1: run k_dp_dq after k_dp_ml and fail on any difference (self-check)
     int dp_algo = 5;           // 5: k_dp_ml for multi-model batches, k_dp_dq otherwise (default); 6: k_dp_ml always;
                                // 3/4: k_dp_dq, 1/2: k_dp_fast, 0: all-pairs k_dp (PGPU_DP_ALGO=n)
@@ -520,6 +523,8 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     int64_t nwords = 0;
     int total_chunks = 0;
     int64_t cb_words = 0;   // codon bitmap words (bit-parallel extraction)
+    std::vector<int> lut_tt;            // translation tables met in this sub-batch: one codon table row each
+    std::vector<uint8_t> lut_rows;
     exts.reserve((size_t)n * 2);
     chains.reserve((size_t)n * (meta ? 16 : 1));
     for (int c = 0; c < n; c++) {
@@ -549,6 +554,15 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
                 } else {
                     codon_masks(tt, &X.stopmask, &X.startmask);
                 }
+            }
+            {
+                size_t row = std::find(lut_tt.begin(), lut_tt.end(), tt) - lut_tt.begin();
+                if (row == lut_tt.size()) {
+                    lut_tt.push_back(tt);
+                    lut_rows.resize(lut_rows.size() + 128);
+                    codon_lut_build(X.stopmask, X.startmask, lut_rows.data() + 128 * row);
+                }
+                X.lut = (int32_t)row;
             }
             nwords += X.nwords;
             exts.push_back(X);
@@ -601,6 +615,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     if (extract_bits) {
         B.cb_stop = pool.alloc<uint32_t>(cb_words + 8);
         B.cb_start = pool.alloc<uint32_t>(cb_words + 8);
+        if (ctx->codon_lut) B.codon_lut = pool.upload(lut_rows);
         if (pool.failed) return PGPU_ENOMEM;
     }
     tev("plan+alloc");
@@ -1387,6 +1402,7 @@ int pgpu_create(int device, pgpu_ctx **out) {
     if (const char *a = getenv("PGPU_DP_ML_MINB")) ctx->dp_ml_minb = atoi(a);
     if (const char *a = getenv("PGPU_EXTRACT_ALGO")) ctx->extract_algo = atoi(a);
     if (const char *a = getenv("PGPU_FINAL_ALGO")) ctx->final_algo = atoi(a);
+    if (const char *a = getenv("PGPU_CODON_LUT")) ctx->codon_lut = atoi(a) != 0;
     if (const char *a = getenv("PGPU_LANES")) ctx->lanes = atoi(a);
     if (const char *a = getenv("PGPU_LANE_MIN_BP")) ctx->lane_min_bp = atoll(a);
     // keep freed blocks cached in the stream-ordered pool: sub-batches reuse them without going to the driver

@@ -86,7 +86,7 @@ struct ExtractInfo {
     int32_t n_hi;        // number of nodes with ndx >= slen - 5    edge flag; written by k_class_index)
     int32_t chunk_off;   // first extraction chunk of this extraction (k_extract_w: one warp per chunk x strand x frame)
     int32_t n_chunks;    // ceil(codons of the longest frame / kExtractChunkCodons), >= 1
-    int32_t pad;
+    int32_t lut;         // row of this extraction's translation table in DevBatch::codon_lut (or 0)
     int64_t cb_off;      // first word of this extraction's codon bitmaps: [strand*3+frame][n_chunks * kExtractChunkCodons/32]
     uint64_t stopmask, startmask;
 };
@@ -126,6 +126,7 @@ struct DevBatch {
     ExtractInfo *exts;
     uint32_t *bits_fwd, *bits_rev;  // node bitmaps (per extraction, word offset woff)
     uint32_t *cb_stop, *cb_start;   // codon bitmaps in scan order (extract_device.cuh), per extraction at cb_off
+    const uint8_t *codon_lut;       // optional [rows][128] codon-byte -> flags tables (codon_lut_build); nullptr = mask arithmetic
     int32_t *wordbase;              // exclusive prefix of node counts per bitmap word
     // extraction nodes
     int32_t *ndx, *stop_val;

@@ -60,6 +60,21 @@ __host__ __device__ inline int codon_flags(const uint8_t *cod, int slen, bool re
     return (int)((stopmask >> c) & 1) | ((int)((startmask >> c) & 1) << 1);
 }
 
+// The same flags for every value of a codon byte, both strands at once: bit 0 / 1 = stop / start on the forward
+// strand, bit 2 / 3 = stop / start of the reverse-strand codon that the byte encodes (k_codon_bits with
+// PGPU_CODON_LUT=1 replaces the mask arithmetic by one table load per codon).
+__host__ __device__ inline void codon_lut_build(uint64_t stopmask, uint64_t startmask, uint8_t *lut /*[128]*/) {
+    for (int b = 0; b < 128; b++) {
+        int v = 0;
+        if (!(b & 64)) {
+            const int c = b & 63, r = rev_code(c);
+            v = (int)((stopmask >> c) & 1) | ((int)((startmask >> c) & 1) << 1) | ((int)((stopmask >> r) & 1) << 2) |
+                ((int)((startmask >> r) & 1) << 3);
+        }
+        lut[b] = (uint8_t)v;
+    }
+}
+
 __host__ __device__ inline int ex_clz(uint32_t x) {
 #ifdef __CUDA_ARCH__
     return __clz((int)x);

@@ -320,11 +320,36 @@ __global__ void __launch_bounds__(128) k_codon_bits(DevBatch B, int n_ext, int t
     const uint8_t *__restrict__ cp = rev ? cod + (slen - 3 - i_top0) : cod + i_top0;
     const int step = rev ? 3 : -3;
     const uint64_t stopmask = X.stopmask, startmask = X.startmask;
+    const uint8_t *__restrict__ lut = B.codon_lut ? B.codon_lut + 128 * X.lut : nullptr;
+    const int lsh = rev ? 2 : 0;
 #pragma unroll 1
     for (int r = 0; r < kChunkWords / 32; r++) {
         const int w0 = chunk * kChunkWords + r * 32;
         if (w0 * 32 >= n_codons) break;
         uint32_t myS = 0, myC = 0;
+        if (lut) {  // table variant: one dependent byte load instead of the mask arithmetic (uniform branch)
+#pragma unroll 1
+            for (int k0 = 0; k0 < 32; k0 += 8) {
+                int fl[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int u = (w0 + k0 + j) * 32 + lane;
+                    fl[j] = cp[min(u, n_codons - 1) * step];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) fl[j] = lut[fl[j] & 127] >> lsh;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const bool ok = (w0 + k0 + j) * 32 + lane < n_codons;
+                    const uint32_t S = __ballot_sync(0xffffffffu, ok && (fl[j] & 1));
+                    const uint32_t C = __ballot_sync(0xffffffffu, ok && (fl[j] & 2));
+                    if (lane == k0 + j) { myS = S; myC = C; }
+                }
+            }
+            B.cb_stop[base + r * 32 + lane] = myS;
+            B.cb_start[base + r * 32 + lane] = myC;
+            continue;
+        }
 #pragma unroll 1
         for (int k0 = 0; k0 < 32; k0 += 8) {
             // eight independent byte loads first (clamped: slots past the end repeat the last codon and are

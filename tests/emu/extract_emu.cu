@@ -75,3 +75,20 @@ extern "C" int emu_extract(const uint8_t *digits, int slen, int tt, int closed, 
     }
     return n;
 }
+
+// codon_lut_build against codon_flags for every byte value, both strands: number of mismatches
+extern "C" int emu_lut_mismatches(int tt) {
+    uint64_t stopmask, startmask;
+    codon_masks(tt, &stopmask, &startmask);
+    uint8_t lut[128];
+    codon_lut_build(stopmask, startmask, lut);
+    int bad = 0;
+    for (int b = 0; b < 128; b++)
+        for (int rev = 0; rev < 2; rev++) {
+            const uint8_t cod[4] = {(uint8_t)b, 0, 0, 0};
+            const int want = codon_flags(cod, 3, rev != 0, 0, stopmask, startmask);
+            const int got = (lut[b] >> (rev ? 2 : 0)) & 3;
+            bad += want != got;
+        }
+    return bad;
+}

@@ -98,3 +98,9 @@ def test_randomised_parameters():
         mg = int(rng.choice([1, 2, 3, 4, 5, 6, 29, 30, 31, 60, 89, 90, 91, 92, 93, 96, 99, 180, 300, 2000]))
         meg = int(rng.choice([1, 2, 3, 4, 30, 59, 60, 61, 62, 63, 90, 120, 600]))
         check(seq, tt=int(rng.choice(tables)), closed=bool(rng.integers(0, 2)), min_gene=mg, min_edge_gene=meg)
+
+
+@pytest.mark.parametrize("tt", [1, 2, 3, 4, 5, 6, 9, 10, 11, 12, 13, 14, 15, 16, 21, 22, 23, 24, 25, 26, 29, 30, 32, 33])
+def test_codon_flag_table_equals_mask_arithmetic(tt):
+    """the optional byte table of k_codon_bits (PGPU_CODON_LUT=1) holds exactly what codon_flags computes"""
+    assert _emu().emu_lut_mismatches(tt) == 0

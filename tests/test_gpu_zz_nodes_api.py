@@ -10,3 +10,24 @@ pytestmark = pytest.mark.gpu
 def test_nodes_api_gpu():
     import pyrodigal_b200.lib as L
     cases.run_cases(L)
+
+
+@pytest.mark.parametrize("tt", [11, 4, 25])
+def test_codon_table_variant_of_k_codon_bits(monkeypatch, tt):
+    """PGPU_CODON_LUT=1 (off by default): the byte-table variant of k_codon_bits must extract the same nodes"""
+    import numpy as np
+    import refutil as R
+    from oracle import oracle as orc
+    from pyrodigal_b200 import _capi
+    monkeypatch.setenv("PGPU_CODON_LUT", "1")
+    ctx = _capi.Context(0)
+    try:
+        for length, gc, seed, nfrac, closed in ((40000, .5, 1, 0.0, False), (3001, .62, 3, 0.0, True), (20000, .45, 4, .002, False)):
+            seq = R.synth(length, gc, seed, n_frac=nfrac)
+            d, _, _ = orc.encode(seq)
+            want = orc.extract(d, tt, orc.make_opts(closed=closed))
+            got = ctx.extract_nodes(np.frombuffer(seq, np.uint8), tt, _capi.make_opts(closed=closed))
+            for f in ("ndx", "stop_val", "strand", "type", "edge"):
+                assert np.array_equal(got[f], want[f]), (tt, length, f)
+    finally:
+        ctx.close()
