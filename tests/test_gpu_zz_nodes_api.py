@@ -21,6 +21,7 @@ def test_codon_table_variant_of_k_codon_bits(monkeypatch, tt):
     from pyrodigal_b200 import _capi
     monkeypatch.setenv("PGPU_CODON_LUT", "1")
     ctx = _capi.Context(0)
+    ctx.set_models(R.bins_blob(), 50)
     try:
         for length, gc, seed, nfrac, closed in ((40000, .5, 1, 0.0, False), (3001, .62, 3, 0.0, True), (20000, .45, 4, .002, False)):
             seq = R.synth(length, gc, seed, n_frac=nfrac)
