@@ -1,0 +1,170 @@
+// emu_engine.cpp -- TEST INFRASTRUCTURE ONLY: fiber scheduler behind tests/emu/cuda_emu/cuda_runtime.h.
+#include <stdio.h>
+#include <ucontext.h>
+
+#include <vector>
+
+#include "cuda_runtime.h"
+
+namespace emu {
+
+enum { READY = 0, WAIT_WARP = 1, WAIT_BLOCK = 2, DONE = 3 };
+
+struct Warp {
+    uint64_t slot[2][32];
+    uint32_t live_snap[2];
+    uint32_t live_mask = 0;
+    int live = 0, arrived = 0;
+    unsigned gen = 0;
+};
+
+struct Thread {
+    ucontext_t ctx;
+    int tid = 0, state = READY;
+    unsigned wait_gen = 0;
+    Warp *warp = nullptr;
+};
+
+struct Engine {
+    ucontext_t sched;
+    std::vector<Thread> threads;
+    std::vector<Warp> warps;
+    std::vector<char *> stacks;
+    const std::function<void()> *body = nullptr;
+    unsigned grid = 0, block = 0, bidx = 0;
+    int block_live = 0, block_arrived = 0;
+    unsigned block_gen = 0;
+};
+
+static constexpr size_t kStack = 256 * 1024;
+thread_local Thread *cur = nullptr;
+static thread_local Engine *E = nullptr;
+
+uint3 thread_idx() { return {(unsigned)cur->tid, 0, 0}; }
+uint3 block_idx() { return {E->bidx, 0, 0}; }
+dim3 block_dim() { return dim3(E->block); }
+dim3 grid_dim() { return dim3(E->grid); }
+int lane_id() { return cur->tid & 31; }
+
+static void yield_to_scheduler() { swapcontext(&cur->ctx, &E->sched); }
+
+static void release_warp(Warp *w) {
+    w->live_snap[w->gen & 1] = w->live_mask;
+    w->arrived = 0;
+    w->gen++;
+}
+
+uint64_t warp_exchange(uint64_t mine, uint64_t out[32], uint32_t *live_mask) {
+    Thread *t = cur;
+    Warp *w = t->warp;
+    const unsigned g = w->gen, buf = g & 1;
+    w->slot[buf][t->tid & 31] = mine;
+    w->arrived++;
+    if (w->arrived == w->live) {
+        release_warp(w);
+    } else {
+        t->state = WAIT_WARP;
+        t->wait_gen = g;
+        while (w->gen == g) yield_to_scheduler();
+        t->state = READY;
+    }
+    memcpy(out, w->slot[buf], sizeof(w->slot[buf]));
+    *live_mask = w->live_snap[buf];
+    return mine;
+}
+
+void sync_block() {
+    Thread *t = cur;
+    const unsigned g = E->block_gen;
+    E->block_arrived++;
+    if (E->block_arrived == E->block_live) {
+        E->block_arrived = 0;
+        E->block_gen++;
+        return;
+    }
+    t->state = WAIT_BLOCK;
+    t->wait_gen = g;
+    while (E->block_gen == g) yield_to_scheduler();
+    t->state = READY;
+}
+
+static void trampoline() {
+    Thread *t = cur;
+    (*E->body)();
+    // thread exit: it no longer takes part in barriers
+    t->state = DONE;
+    Warp *w = t->warp;
+    w->live--;
+    w->live_mask &= ~(1u << (t->tid & 31));
+    if (w->live > 0 && w->arrived == w->live) release_warp(w);
+    E->block_live--;
+    if (E->block_live > 0 && E->block_arrived == E->block_live) { E->block_arrived = 0; E->block_gen++; }
+    swapcontext(&t->ctx, &E->sched);
+}
+
+static bool resumable(const Thread &t) {
+    if (t.state == READY) return true;
+    if (t.state == WAIT_WARP) return t.warp->gen != t.wait_gen;
+    if (t.state == WAIT_BLOCK) return E->block_gen != t.wait_gen;
+    return false;
+}
+
+static void run_block(unsigned b) {
+    Engine &e = *E;
+    e.bidx = b;
+    const unsigned T = e.block, nw = (T + 31) / 32;
+    e.threads.resize(T);
+    e.warps.assign(nw, Warp());
+    while (e.stacks.size() < T) e.stacks.push_back((char *)malloc(kStack));
+    e.block_live = (int)T;
+    e.block_arrived = 0;
+    for (unsigned i = 0; i < T; i++) {
+        Thread &t = e.threads[i];
+        t.tid = (int)i;
+        t.state = READY;
+        t.warp = &e.warps[i / 32];
+        t.warp->live++;
+        t.warp->live_mask |= 1u << (i & 31);
+        getcontext(&t.ctx);
+        t.ctx.uc_stack.ss_sp = e.stacks[i];
+        t.ctx.uc_stack.ss_size = kStack;
+        t.ctx.uc_link = nullptr;
+        makecontext(&t.ctx, trampoline, 0);
+    }
+    while (e.block_live > 0) {
+        bool progress = false;
+        for (unsigned wi = 0; wi < nw; wi++) {
+            bool again = true;
+            while (again) {  // run the lanes of this warp until all of them are finished or blocked
+                again = false;
+                for (unsigned i = wi * 32; i < std::min(T, wi * 32 + 32); i++) {
+                    Thread &t = e.threads[i];
+                    if (!resumable(t)) continue;
+                    cur = &t;
+                    swapcontext(&e.sched, &t.ctx);
+                    cur = nullptr;
+                    again = progress = true;
+                }
+            }
+        }
+        if (!progress) {
+            fprintf(stderr, "cuda_emu: deadlock in block %u (threads wait for a barrier that cannot complete)\n", b);
+            abort();
+        }
+    }
+}
+
+void Launch::operator<<(const std::function<void()> &body) const {
+    if (grid == 0 || block == 0) return;
+    Engine engine;
+    Engine *outer = E;
+    E = &engine;
+    engine.body = &body;
+    engine.grid = grid;
+    engine.block = block;
+    for (unsigned b = 0; b < grid; b++) run_block(b);
+    for (char *s : engine.stacks) free(s);
+    E = outer;
+}
+
+}  // namespace emu

@@ -388,7 +388,6 @@ def test_single_chain_16mbp_vs_oracle(capi):
     r.free(); c.close()
 
 
-@pytest.mark.gpu
 @pytest.mark.parametrize("closed", [False, True])
 def test_gene_only_final_pass_equals_full_final_pass(ctx, capi, closed):
     """meta mode without node arrays re-scores only the genes' ORFs: the start / stop node records of every gene must
@@ -416,7 +415,6 @@ def test_gene_only_final_pass_equals_full_final_pass(ctx, capi, closed):
             assert np.array_equal(nodes[full.genes["stop_ndx"][a:b]], gn[a:b, 1])
 
 
-@pytest.mark.gpu
 @pytest.mark.parametrize("many_parts", [False, True])
 def test_two_lane_host_batches_match_single_stream(capi, monkeypatch, many_parts):
     """host-input batches above PGPU_LANE_MIN_BP run as sub-batches on two worker threads / streams; the stitched
