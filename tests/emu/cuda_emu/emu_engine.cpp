@@ -2,6 +2,7 @@
 #include <stdio.h>
 #include <ucontext.h>
 
+#include <mutex>
 #include <vector>
 
 #include "cuda_runtime.h"
@@ -154,8 +155,13 @@ static void run_block(unsigned b) {
     }
 }
 
+// `__shared__` variables are function-level statics here, so only one kernel may run at a time in the process: host
+// threads that launch concurrently (the library's two-lane mode) take turns
+static std::mutex g_launch_mutex;
+
 void Launch::operator<<(const std::function<void()> &body) const {
     if (grid == 0 || block == 0) return;
+    std::lock_guard<std::mutex> guard(g_launch_mutex);
     Engine engine;
     Engine *outer = E;
     E = &engine;

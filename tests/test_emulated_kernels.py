@@ -38,8 +38,7 @@ def ctx(capi):
 FULL = os.environ.get("PGPU_EMU_FULL") == "1"   # also the four heavy cases (about 8 minutes more)
 heavy = pytest.mark.skipif(not FULL, reason="heavy under emulation: set PGPU_EMU_FULL=1")
 
-# the operator-level and end-to-end parity tests of the GPU suite, unchanged (the Mbp-sized inputs and the two-thread
-# lanes stay GPU-only)
+# the operator-level and end-to-end parity tests of the GPU suite, unchanged (the Mbp-sized inputs stay GPU-only)
 test_extract_nodes = G.test_extract_nodes
 test_extract_nodes_masked = G.test_extract_nodes_masked
 test_score_nodes = G.test_score_nodes
@@ -51,6 +50,7 @@ test_find_genes_batch_vs_oracle = G.test_find_genes_batch_vs_oracle
 test_find_genes_options_vs_oracle = G.test_find_genes_options_vs_oracle
 test_dp_kernel_variants_single_golden = G.test_dp_kernel_variants_single_golden
 test_resident_batch_matches_host_batch = G.test_resident_batch_matches_host_batch
+test_two_lane_host_batches_match_single_stream = heavy(G.test_two_lane_host_batches_match_single_stream)
 test_dp_model_lane_kernel_equals_per_chain_kernel = heavy(G.test_dp_model_lane_kernel_equals_per_chain_kernel)
 test_sub_batching_matches_single_batch = heavy(G.test_sub_batching_matches_single_batch)
 test_gene_only_final_pass_equals_full_final_pass = heavy(G.test_gene_only_final_pass_equals_full_final_pass)
@@ -84,6 +84,31 @@ def test_dp_model_lane_kernel_small(capi, monkeypatch):
     res = c.find_genes_batch(flat, off, capi.make_opts(meta=True))   # PGPU_DP_VERIFY fails the call on any difference
     assert int(res.summary["n_genes"].sum()) > 20
     c.close()
+
+
+def test_two_lanes_small(capi, monkeypatch):
+    """PGPU_LANES=2: two worker threads / sub-batches, results stitched in order (the emulation runs one kernel at a time)"""
+    seqs = [R.synth(3000 + 1700 * k, .32 + .03 * k, 12000 + k) for k in range(11)] + [b"", R.synth(50, .5, 1)]
+    flat, off = _batch(seqs)
+    o = capi.make_opts(meta=True, want_nodes=True)
+    monkeypatch.setenv("PGPU_LANES", "1")
+    c1 = capi.Context(0)
+    c1.set_models(R.bins_blob(), 50)
+    r1 = c1.find_genes_batch(flat, off, o)
+    monkeypatch.setenv("PGPU_LANES", "2")
+    monkeypatch.setenv("PGPU_LANE_MIN_BP", "0")
+    c2 = capi.Context(0)
+    c2.set_models(R.bins_blob(), 50)
+    for rep in range(2):
+        r2 = c2.find_genes_batch(flat, off, o)
+        assert r2.stats["kernel_launches"] > 1.5 * r1.stats["kernel_launches"]   # really ran as two sub-batches
+        assert r1.summary.tobytes() == r2.summary.tobytes() and np.array_equal(r1.gene_off, r2.gene_off)
+        assert r1.genes.tobytes() == r2.genes.tobytes() and r1.gene_nodes.tobytes() == r2.gene_nodes.tobytes()
+        for k in (0, 5, 6, 10):
+            assert r1.nodes(k).tobytes() == r2.nodes(k).tobytes()
+        for key in ("n_contigs", "total_bp", "total_nodes", "total_chain_nodes", "n_chains", "total_genes", "pairs", "dp_steps"):
+            assert r1.stats[key] == r2.stats[key], key
+    c1.close(); c2.close()
 
 
 @pytest.mark.parametrize("tt", [11, 4])
