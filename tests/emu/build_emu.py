@@ -11,7 +11,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "pyrodigal_b200", "csrc")
 OUT = os.path.join(HERE, "_emu_build")
-LIB = os.path.join(HERE, "libpgpu_emu.so")
+SANITIZE = os.environ.get("PGPU_EMU_SANITIZE") == "1"   # AddressSanitizer build (run python under LD_PRELOAD=libasan)
+LIB = os.path.join(HERE, "libpgpu_emu_asan.so" if SANITIZE else "libpgpu_emu.so")
+if SANITIZE:
+    OUT += "_asan"
 SOURCES = ["api.cu", "seq_kernels.cu", "score_kernels.cu", "dp_kernels.cu", "train_kernels.cu"]
 
 
@@ -85,6 +88,8 @@ def build(force=False):
     objs = []
     flags = ["g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-fPIC", "-pthread", "-w",
              "-I", os.path.join(HERE, "cuda_emu"), "-I", CSRC]
+    if SANITIZE:
+        flags += ["-fsanitize=address", "-fno-omit-frame-pointer"]
     procs = []
     for f in SOURCES:
         cpp = os.path.join(OUT, f.replace(".cu", ".emu.cpp"))
@@ -100,7 +105,7 @@ def build(force=False):
     for p in procs:
         if p.wait() != 0:
             raise RuntimeError("emulation build failed")
-    subprocess.check_call(["g++", "-shared", "-pthread", "-o", LIB] + objs + [eng])
+    subprocess.check_call(["g++", "-shared", "-pthread", "-o", LIB] + (["-fsanitize=address"] if SANITIZE else []) + objs + [eng])
     return LIB
 
 
