@@ -16,6 +16,8 @@
 //    window's A/G match pattern and its distance to the start, so a per-model 15x64 byte table (built on
 //    the host) replaces the nested loops; the per-node 32-bit A/G pattern is model independent.
 //  * log/pow of the length factor come from a host table (host libm == the reference's libm).
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace pgpu {
@@ -317,7 +319,8 @@ __global__ void __launch_bounds__(128) k_coding(DevBatch B, const DevModel *__re
 // --------------------------------------------------------------------------------------------------
 constexpr int kOrfWarps = 8;
 
-__global__ void __launch_bounds__(32 * kOrfWarps, 5) k_coding_orf(DevBatch B, const DevModel *__restrict__ models, int n_ext,
+template <int MINB>   // min CTAs per SM: 5 = 46 registers / 40 warps, 6 = 40 registers (a few spilled bytes) / 48 warps
+__global__ void __launch_bounds__(32 * kOrfWarps, MINB) k_coding_orf(DevBatch B, const DevModel *__restrict__ models, int n_ext,
                                                                 int total_nodes) {
     __shared__ int s_first;
     const int lane = threadIdx.x & 31;
@@ -888,10 +891,14 @@ void launch_node_prep(const DevBatch &B, int n_ext, int total_nodes, int seq_par
 void launch_coding(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, int n_ext, int total_nodes,
                    cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
-    if (B.ext_chains && B.dcT && n_ext > 0 && total_nodes > 0)
-        k_coding_orf<<<((total_nodes + 1) / 2 + 1 + kOrfWarps - 1) / kOrfWarps, 32 * kOrfWarps, 0, st>>>(B, models, n_ext, total_nodes);
-    else
+    if (B.ext_chains && B.dcT && n_ext > 0 && total_nodes > 0) {
+        static const int minb = getenv("PGPU_CODING_MINB") ? atoi(getenv("PGPU_CODING_MINB")) : 5;  // A/B switch
+        const unsigned nb = ((total_nodes + 1) / 2 + 1 + kOrfWarps - 1) / kOrfWarps;
+        if (minb == 6) k_coding_orf<6><<<nb, 32 * kOrfWarps, 0, st>>>(B, models, n_ext, total_nodes);
+        else k_coding_orf<5><<<nb, 32 * kOrfWarps, 0, st>>>(B, models, n_ext, total_nodes);
+    } else {
         k_coding<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total);
+    }
 }
 void launch_start_score(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o, void *mot_out,
                         cudaStream_t st) {
