@@ -160,3 +160,14 @@ def test_train_multi_contig_linker(emulated_lib):
 
 def test_python_api_drop_in(emulated_lib):
     G.test_python_api_drop_in()
+
+
+def test_command_line_end_to_end(emulated_lib, tmp_path):
+    """FASTA ingest -> emulated kernels -> writers, against what the reference's command line wrote (meta and single
+    mode, GFF / GenBank / FASTA / score tables, training file)"""
+    import test_gpu_cli
+    for k, name in enumerate(test_gpu_cli.W["names"]):
+        d = tmp_path / str(k)
+        d.mkdir()
+        test_gpu_cli.test_cli_matches_reference_cli(name, d)
+    test_gpu_cli.test_cli_rejects_training_file_in_meta_mode(tmp_path)
