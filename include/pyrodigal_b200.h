@@ -196,6 +196,18 @@ int pgpu_extract_nodes(pgpu_ctx *ctx, const uint8_t *seq, int slen, int translat
                        const pgpu_opts *opts, int cap, int32_t *ndx, int32_t *stop_val,
                        int8_t *strand, uint8_t *type, uint8_t *edge);
 
+/* Sequence.max_gc_frame_plot (lib.pyx:724-768, 1001-1026): for every base the codon position (0..2) with the highest
+ * GC content in the 120-base window around its triplet, -1 for the one or two bases after the last full triplet.
+ * out[slen].  (The reference ignores its window_size argument and always uses 120 bases; so does this.) */
+int pgpu_max_gc_frame_plot(pgpu_ctx *ctx, const uint8_t *seq, int slen, int8_t *out);
+
+/* Sequence.shine_dalgarno (lib.pyx:1028-1072): bin of the best Shine-Dalgarno motif in the window that starts at
+ * strand coordinate `pos` upstream of the start codon at `start`, for the rbs weights of loaded model `model`;
+ * exact != 0: AGGAGG sub-motifs without mismatch, else with exactly one.  PGPU_EINVAL (ValueError) on a bad strand or
+ * negative coordinates. */
+int pgpu_shine_dalgarno(pgpu_ctx *ctx, const uint8_t *seq, int slen, int pos, int start, int model, int strand,
+                        int exact, int32_t *out);
+
 /* Nodes.reset_scores + Nodes.score (lib.pyx:2563-2595) for one loaded model, followed by
  * _record_overlapping_starts(flag=1).  `first_pass`: 1 = nodes freshly extracted.
  * dst[cap] receives the scored node array. returns number of nodes. */

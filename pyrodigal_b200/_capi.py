@@ -102,6 +102,8 @@ lib.pgpu_result_free.restype = None
 lib.pgpu_train.argtypes = [_vp, _vp, C.c_int64, C.POINTER(Opts), C.POINTER(TrainOpts), _vp, C.POINTER(Stats)]
 lib.pgpu_extract_nodes.argtypes = [_vp, _vp, C.c_int, C.c_int, C.POINTER(Opts), C.c_int, _vp, _vp, _vp, _vp, _vp]
 lib.pgpu_score_nodes.argtypes = [_vp, _vp, C.c_int, C.c_int, C.POINTER(Opts), C.c_int, C.c_int, C.c_int, _vp]
+lib.pgpu_max_gc_frame_plot.argtypes = [_vp, _vp, C.c_int, _vp]
+lib.pgpu_shine_dalgarno.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
 lib.pgpu_score_connections.argtypes = [_vp, C.c_int] + [_vp] * 10 + [C.c_int, C.c_int] + [_vp] * 5
 lib.pgpu_compute_skippable.argtypes = [_vp, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp]
 
@@ -209,6 +211,17 @@ class Context:
         n = check(lib.pgpu_score_nodes(self.handle, ptr(seq), len(seq), model, C.byref(opts), int(is_meta),
                                        int(first_pass), cap, ptr(out)), self.handle)
         return out[:n].copy()
+
+    def max_gc_frame_plot(self, seq):
+        out = np.empty(len(seq), dtype=np.int8)
+        check(lib.pgpu_max_gc_frame_plot(self.handle, ptr(seq), len(seq), ptr(out)), self.handle)
+        return out
+
+    def shine_dalgarno(self, seq, pos, start, model=0, strand=1, exact=True):
+        out = C.c_int32(0)
+        check(lib.pgpu_shine_dalgarno(self.handle, ptr(seq), len(seq), pos, start, model, strand, int(exact),
+                                      C.byref(out)), self.handle)
+        return out.value
 
     def score_connections(self, ndx, stop_val, strand, type_, cscore, sscore, rscore, uscore, gc_score, star_ptr,
                           model, final):

@@ -375,6 +375,9 @@ struct RunPlan {
     // lanes: called right before / after the input copy is queued on the sub-batch's stream (run_lanes chains the
     // copies of consecutive sub-batches, so that one half computes while the other half is still being copied)
     std::function<void(cudaStream_t)> before_h2d, after_h2d;
+    // operator-level queries on the encoded sequence of a single contig (stage 0: nothing else runs)
+    int8_t *gc_frame_out = nullptr;      // pgpu_max_gc_frame_plot: host buffer [slen]
+    struct { int pos, start, model, strand, exact; int32_t *out; } sd = {0, 0, 0, 1, 1, nullptr};  // pgpu_shine_dalgarno
 };
 
 static int train_stage(pgpu_ctx *ctx, DevPool &pool, DevBatch &B, const ExtractInfo &X, RunOpts ro, int gc_count,
@@ -469,6 +472,27 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     tev("setup/alloc/memset");
     launch_encode(B, d_tiles, (int)tiles.size(), st);
     ctx->launches++;
+    if (plan.gc_frame_out || plan.sd.out) {
+        // stage 0: the query only needs what k_encode wrote (digits, GC bitmap of contig 0 at offset 0)
+        const int slen = contigs[0].slen;
+        if (plan.gc_frame_out && slen > 0) {
+            int8_t *d_gp = pool.alloc<int8_t>((size_t)slen + 16);
+            if (pool.failed) return PGPU_ENOMEM;
+            launch_gc_frame(B.gcbits, slen, d_gp, st);
+            ctx->launches++;
+            CK(cudaMemcpyAsync(plan.gc_frame_out, d_gp, slen, cudaMemcpyDeviceToHost, st));
+        }
+        if (plan.sd.out) {
+            int32_t *d_out = pool.alloc<int32_t>(1);
+            if (pool.failed) return PGPU_ENOMEM;
+            launch_shine_dalgarno(B, ctx->d_models, plan.sd.model, plan.sd.pos, plan.sd.start, plan.sd.strand, plan.sd.exact,
+                                  d_out, st);
+            ctx->launches++;
+            CK(cudaMemcpyAsync(plan.sd.out, d_out, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
+        return PGPU_OK;
+    }
     std::vector<int4> h_masks;
     if (opts.mask) {
         const int cap = (int)std::min<int64_t>(std::max<int64_t>(1024, atot / std::max(1, opts.min_mask) + n + 16), 1 << 28);
@@ -1653,6 +1677,44 @@ int pgpu_extract_nodes(pgpu_ctx *ctx, const uint8_t *seq, int slen, int translat
         }
     }
     return nn;
+}
+
+static int run_query(pgpu_ctx *ctx, const uint8_t *seq, int slen, RunPlan &plan) {
+    cudaSetDevice(ctx->device);
+    pgpu_result tmp;
+    tmp.pinned = ctx->pinned;
+    memset(&tmp.stats, 0, sizeof(tmp.stats));
+    tmp.summary.resize(1); tmp.gene_off.assign(2, 0); tmp.node_off.assign(2, 0);
+    pgpu_opts opts;
+    memset(&opts, 0, sizeof(opts));
+    opts.min_gene = 90; opts.min_edge_gene = 60; opts.max_overlap = 60; opts.min_mask = 50;
+    plan.stage = 1;
+    const int64_t offs[2] = {0, slen};
+    return run_range(ctx, seq, nullptr, offs, 0, 1, opts, plan, &tmp, nullptr);
+}
+
+int pgpu_max_gc_frame_plot(pgpu_ctx *ctx, const uint8_t *seq, int slen, int8_t *out) {
+    if (!ctx) return PGPU_EINVAL;
+    if (slen < 0 || (slen > 0 && (!seq || !out))) return fail(ctx, PGPU_EINVAL, "bad arguments");
+    if (slen == 0) return PGPU_OK;
+    RunPlan plan;
+    plan.gc_frame_out = out;
+    return run_query(ctx, seq, slen, plan);
+}
+
+int pgpu_shine_dalgarno(pgpu_ctx *ctx, const uint8_t *seq, int slen, int pos, int start, int model, int strand, int exact,
+                        int32_t *out) {
+    if (!ctx) return PGPU_EINVAL;
+    if (!out || slen < 0 || (slen > 0 && !seq)) return fail(ctx, PGPU_EINVAL, "bad arguments");
+    if (strand != 1 && strand != -1) return fail(ctx, PGPU_EINVAL, "Invalid strand (must be +1 or -1)");
+    if (pos < 0) return fail(ctx, PGPU_EINVAL, "`pos` must be positive");
+    if (start < 0) return fail(ctx, PGPU_EINVAL, "`start` must be positive");
+    if (model < 0 || model >= ctx->n_models) return fail(ctx, PGPU_ESTATE, "model index out of range");
+    *out = 0;
+    if (slen == 0) return PGPU_OK;
+    RunPlan plan;
+    plan.sd = {pos, start, model, strand, exact, out};
+    return run_query(ctx, seq, slen, plan);
 }
 
 int pgpu_score_nodes(pgpu_ctx *ctx, const uint8_t *seq, int slen, int model, const pgpu_opts *opts, int is_meta,

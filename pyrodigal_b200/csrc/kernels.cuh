@@ -47,6 +47,8 @@ void launch_trace(const DevBatch &B, const DevModel *models, int n_contigs, cons
                   cudaStream_t st);
 void launch_pack_nodes(const DevBatch &B, int n_chains, int64_t total, const void *mot, const int32_t *tracef,
                        const uint8_t *elim, int dp_state, pgpu_node *out, cudaStream_t st);
+void launch_shine_dalgarno(const DevBatch &B, const DevModel *models, int model, int pos, int start, int strand, int exact,
+                           int32_t *out, cudaStream_t st);
 void launch_score_genes(const DevBatch &B, const DevModel *models, int n_contigs, const void *summary, const void *genes,
                         const int64_t *gene_off, int64_t gene_cap, int2 *list, int *count, RunOpts o, void *mot_out,
                         cudaStream_t st);

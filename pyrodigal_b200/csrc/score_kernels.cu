@@ -19,6 +19,7 @@
 #include <cstdlib>
 
 #include "kernels.cuh"
+#include "sd_device.cuh"
 
 namespace pgpu {
 
@@ -919,6 +920,16 @@ void launch_score_genes(const DevBatch &B, const DevModel *models, int n_contigs
     k_coding_genes<<<(unsigned)((gene_cap + 127) / 128), 128, 0, st>>>(B, models, list, count, (const pgpu_gene *)genes, gene_off);
     k_start_score_genes<<<(unsigned)((2 * gene_cap + 127) / 128), 128, 0, st>>>(B, models, list, count, (const pgpu_gene *)genes,
                                                                                    gene_off, o, (MotifOut *)mot_out);
+}
+// operator Sequence.shine_dalgarno: one window of contig 0, rules evaluated directly (sd_device.cuh)
+__global__ void k_shine_dalgarno(DevBatch B, const DevModel *__restrict__ models, int model, int pos, int start, int strand,
+                                 int exact, int32_t *__restrict__ out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        *out = sd_window(B.digits, B.contigs[0].slen, pos, start, models[model].rbs_wt, strand, exact != 0);
+}
+void launch_shine_dalgarno(const DevBatch &B, const DevModel *models, int model, int pos, int start, int strand, int exact,
+                           int32_t *out, cudaStream_t st) {
+    k_shine_dalgarno<<<1, 32, 0, st>>>(B, models, model, pos, start, strand, exact, out);
 }
 void launch_opv(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;

@@ -421,6 +421,33 @@ class Sequence(typing.Sized):
         p_taa = (1 - gc) * (1 - gc) * (1 - gc) / 8.0
         return p_tga + p_tag + p_taa
 
+    def max_gc_frame_plot(self, window_size=120):
+        """Frame with the highest GC content around every position (lib.pyx:1001-1026), computed on the GPU.
+
+        Like the reference, the plot always uses a 120-base window: `window_size` is only validated."""
+        if window_size < 0:
+            raise ValueError(f"Invalid window size {window_size!r}")
+        import array
+        ctx = _context_for(_LazyBins.get()._blob_bytes(), 50)
+        with ctx.lock:
+            gp = ctx.max_gc_frame_plot(self._ascii)
+        plot = array.array("i")
+        plot.frombytes(gp.astype(np.intc).tobytes())
+        return plot
+
+    def shine_dalgarno(self, pos, start, training_info, strand=1, exact=True):
+        """Bin of the highest scoring Shine-Dalgarno motif in the window at `pos` upstream of `start`
+        (lib.pyx:1028-1072), evaluated on the GPU with the rbs weights of `training_info`."""
+        if strand != 1 and strand != -1:
+            raise ValueError(f"Invalid strand: {strand!r} (must be +1 or -1)")
+        if pos < 0:
+            raise ValueError("`pos` must be positive")
+        if start < 0:
+            raise ValueError("`start` must be positive")
+        ctx = _context_for(bytes(training_info), 1)
+        with ctx.lock:
+            return ctx.shine_dalgarno(self._ascii, pos, start, 0, strand, exact)
+
     def __sizeof__(self):
         return len(self) + object.__sizeof__(self)
 

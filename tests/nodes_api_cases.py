@@ -80,3 +80,42 @@ def run_cases(L):
     other = L.Sequence(R.synth(30000, 0.5, 78))
     with pytest.raises(ValueError):
         nodes.score(other, tinf)
+
+
+def run_sequence_operator_cases(L):
+    """Sequence.shine_dalgarno / max_gc_frame_plot (reference: tests/test_sequence.py:52-75 and the oracle)"""
+    tinf = L.TrainingInfo._from_bytes(R.bin_blob(0))
+    seq = L.Sequence("AGGAGGTTAGCAAATATG")
+    for i in range(10):
+        assert seq.shine_dalgarno(i, 15, tinf) == (24 if i == 0 else 13 if i == 3 else 0), i
+        assert seq.shine_dalgarno(i, 15, tinf, exact=False) == 0, i
+    seq = L.Sequence("AGGTGGTTAGCAAATATG")
+    for i in range(10):
+        assert seq.shine_dalgarno(i, 15, tinf) == (6 if i == 0 else 0), i
+        assert seq.shine_dalgarno(i, 15, tinf, exact=False) == (19 if i == 0 else 0), i
+    for bad in (dict(pos=-1, start=5), dict(pos=1, start=-5), dict(pos=1, start=9, strand=0)):
+        with pytest.raises(ValueError):
+            seq.shine_dalgarno(training_info=tinf, **bad)
+    # seeded sweep against the oracle: both strands, both modes, windows anywhere around the start
+    rng = np.random.default_rng(11)
+    s = R.synth(600, 0.45, 90) + b"AGGAGGTAGGAGGAAGGAGNNGGAGG" * 4 + R.synth(300, 0.6, 91)
+    d, _, _ = orc.encode(s)
+    seq = L.Sequence(s)
+    for model in (0, 24):
+        blob = R.bin_blob(model)
+        tinf = L.TrainingInfo._from_bytes(blob)
+        rbs_wt = np.ascontiguousarray(tinf.rbs_weights, dtype=np.float64)
+        for _ in range(120):
+            start = int(rng.integers(0, len(s)))
+            pos = max(0, start - int(rng.integers(0, 30)))
+            strand = int(rng.choice([1, -1]))
+            for exact in (True, False):
+                want = orc.shine_dalgarno(d, pos, start, rbs_wt, strand=strand, exact=exact)
+                assert seq.shine_dalgarno(pos, start, tinf, strand=strand, exact=exact) == want, (model, pos, start, strand, exact)
+    # GC frame plot
+    for text in (R.synth(5000, 0.5, 3), R.synth(361, 0.3, 4), R.synth(1000, 0.7, 5, n_frac=0.02), b"ACGTAC", b"GC"):
+        d, _, _ = orc.encode(text)
+        plot = L.Sequence(text).max_gc_frame_plot()
+        assert plot.typecode == "i" and list(plot) == orc.gc_frame_plot(d).astype(int).tolist(), len(text)
+    with pytest.raises(ValueError):
+        L.Sequence(b"ACGT").max_gc_frame_plot(window_size=-1)

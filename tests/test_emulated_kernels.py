@@ -146,6 +146,11 @@ def test_nodes_operator_api(emulated_lib):
     nodes_api_cases.run_cases(emulated_lib)
 
 
+def test_sequence_operators(emulated_lib):
+    import nodes_api_cases
+    nodes_api_cases.run_sequence_operator_cases(emulated_lib)
+
+
 @pytest.mark.parametrize("name", ["s20000_min", "s30k_tt4_forced", "s40k_N_mask"] +
                          (["s25k_closed_hi", "s60k_nonsd", "srr_contig", "ref100k_open", "ref100k_closed"] if FULL else []))
 def test_train_golden(emulated_lib, name, tmp_path):

@@ -12,6 +12,11 @@ def test_nodes_api_gpu():
     cases.run_cases(L)
 
 
+def test_sequence_operators_gpu():
+    import pyrodigal_b200.lib as L
+    cases.run_sequence_operator_cases(L)
+
+
 @pytest.mark.parametrize("tt", [11, 4, 25])
 def test_codon_table_variant_of_k_codon_bits(monkeypatch, tt):
     """PGPU_CODON_LUT=1 (off by default): the byte-table variant of k_codon_bits must extract the same nodes"""
