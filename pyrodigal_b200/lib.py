@@ -831,6 +831,11 @@ class Genes(typing.Sequence):
             raise IndexError("genes index out of range")
         return Gene(self, index)
 
+    def clear(self):
+        """Remove all genes from the list (lib.pyx:3185-3191)."""
+        self._genes = self._genes[:0]
+        self._gene_nodes = self._gene_nodes[:0]
+
     @property
     def nodes(self):
         if self._nodes is None:
