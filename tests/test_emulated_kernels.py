@@ -176,3 +176,14 @@ def test_command_line_end_to_end(emulated_lib, tmp_path):
         d.mkdir()
         test_gpu_cli.test_cli_matches_reference_cli(name, d)
     test_gpu_cli.test_cli_rejects_training_file_in_meta_mode(tmp_path)
+
+
+def test_randomised_batches_against_the_oracle(monkeypatch):
+    """a short seeded run of tests/emu/fuzz.py and fuzz_train.py (odd contigs: Ns, repeats, tiny / extreme-GC contigs,
+    IUPAC letters; random end mode, masks, translation tables, start weights)"""
+    import fuzz
+    import fuzz_train
+    monkeypatch.setattr(sys, "argv", ["fuzz", "12", "2026"])
+    assert fuzz.main() == 0
+    monkeypatch.setattr(sys, "argv", ["fuzz_train", "10", "2026"])
+    assert fuzz_train.main() == 0
