@@ -88,6 +88,8 @@ struct pgpu_ctx {
                                // (PGPU_EXTRACT_ALGO; batches with N-run masks always use 1)
     int final_algo = 2;        // meta mode without node arrays: 2 = final scoring pass over the genes' ORFs only,
                                // 1 = over every node as with want_nodes (PGPU_FINAL_ALGO)
+    bool coding_groups = true; // k_coding_orf with 4 / 8 / 16 lanes per ORF for extractions with few models (PGPU_CODING_GROUPS=0:
+                               // one warp per ORF, the mapping measured in round 1)
     bool codon_lut = false;    // PGPU_CODON_LUT=1: k_codon_bits reads codon flags from a per-table byte table (written
                                // after the last GPU run of round 1: logic checked by the host emulation only, so off)
     bool dp_verify = false;    // PGPU_DP_VERIFY=1: run k_dp_dq after k_dp_ml and fail on any difference (self-check)
@@ -760,6 +762,25 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         B.ext_chains = pool.upload(elist);
         B.dcT = ctx->d_dcT;
         B.n_models = ctx->n_models;
+        if (ctx->coding_groups && ctx->d_dcT && n_chains > n_ext) {
+            // k_coding_orf, grouped: W lanes per ORF for an extraction with L chains, (nn / 2 + 1) ORF slots
+            std::vector<int64_t> toff(n_ext + 1, 0);
+            std::vector<uint8_t> w(n_ext + 1, 32);
+            for (int e = 0; e < n_ext; e++) {
+                const int L = eoff[e + 1] - eoff[e];
+                w[e] = (uint8_t)(L <= 4 ? 4 : L <= 8 ? 8 : L <= 16 ? 16 : 32);
+                const int64_t threads = L > 0 ? ((int64_t)exts[e].nn / 2 + 1) * w[e] : 0;
+                toff[e + 1] = toff[e] + ((threads + 31) & ~int64_t(31));
+            }
+            B.orf_threads = toff[n_ext];
+            B.orf_toff = pool.upload(toff);
+            B.orf_w = pool.upload(w);
+            int32_t *tab = pool.alloc<int32_t>((size_t)(B.orf_threads >> 8) + 2);
+            if (pool.failed) return PGPU_ENOMEM;
+            launch_block_owner_off(B.orf_toff, n_ext, 8, tab, st);
+            B.orf_blk = tab;
+            ctx->launches++;
+        }
     }
     B.cscore = pool.alloc<double>(total_cn); B.sscore = pool.alloc<double>(total_cn);
     B.rscore = pool.alloc<double>(total_cn); B.uscore = pool.alloc<double>(total_cn);
@@ -1427,6 +1448,7 @@ int pgpu_create(int device, pgpu_ctx **out) {
     if (const char *a = getenv("PGPU_EXTRACT_ALGO")) ctx->extract_algo = atoi(a);
     if (const char *a = getenv("PGPU_FINAL_ALGO")) ctx->final_algo = atoi(a);
     if (const char *a = getenv("PGPU_CODON_LUT")) ctx->codon_lut = atoi(a) != 0;
+    if (const char *a = getenv("PGPU_CODING_GROUPS")) ctx->coding_groups = atoi(a) != 0;
     if (const char *a = getenv("PGPU_LANES")) ctx->lanes = atoi(a);
     if (const char *a = getenv("PGPU_LANE_MIN_BP")) ctx->lane_min_bp = atoll(a);
     // keep freed blocks cached in the stream-ordered pool: sub-batches reuse them without going to the driver

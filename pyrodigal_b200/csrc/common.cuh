@@ -173,6 +173,12 @@ struct DevBatch {
     // the extraction that contains node index 128*b, so that a thread block does not start with a serial search
     const int32_t *blk_chain;
     const int32_t *blk_ext;
+    // grouped mapping of k_coding_orf (optional; nullptr = one warp per ORF): thread range of every extraction
+    // (orf_toff[0..n_ext], multiples of 32), lanes per ORF (4 / 8 / 16 / 32), owner of every 256-thread block
+    const int64_t *orf_toff;
+    const uint8_t *orf_w;
+    const int32_t *orf_blk;
+    int64_t orf_threads;
     // per chain results
     int32_t *chain_ipath;
     double *chain_score;

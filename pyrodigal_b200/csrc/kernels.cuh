@@ -19,6 +19,7 @@ void launch_gc_scan(const DevBatch &B, int64_t nwords, int *block_sums, int *tot
 void launch_word_scan(const DevBatch &B, int64_t nwords, int *block_sums, int *total_out, cudaStream_t st);
 
 // score_kernels.cu
+void launch_block_owner_off(const int64_t *off, int n, int shift, int32_t *tab, cudaStream_t st);
 void launch_block_owner_chains(const ChainInfo *chains, int n, int32_t *tab, cudaStream_t st);
 void launch_block_owner_exts(const ExtractInfo *exts, int n, int32_t *tab, cudaStream_t st);
 void launch_node_prep(const DevBatch &B, int n_ext, int total_nodes, int seq_parts, cudaStream_t st);

@@ -320,21 +320,42 @@ __global__ void __launch_bounds__(128) k_coding(DevBatch B, const DevModel *__re
 // --------------------------------------------------------------------------------------------------
 constexpr int kOrfWarps = 8;
 
-template <int MINB>   // min CTAs per SM: 5 = 46 registers / 40 warps, 6 = 40 registers (a few spilled bytes) / 48 warps
+// GROUPED: an extraction with L <= 16 models does not need a whole warp per ORF.  Its ORFs are handled by groups of
+// W = 4 / 8 / 16 lanes (the next power of two >= L), 32 / W ORFs per warp: the lanes of a group still take one model
+// each and share every node / codon load, different groups of a warp simply diverge (there is no warp-level
+// primitive in this kernel), and a warp costs the longest of its ORFs instead of their sum.  About two thirds of the
+// (extraction, ORF) items of a metagenome batch are in extractions with L <= 16 (a third with L <= 4: the
+// translation-table-4 extractions of low-GC contigs).  Thread ranges per extraction (`orf_toff`, multiples of 32) and
+// group widths (`orf_w`) are planned on the host.  MINB: min CTAs per SM, 5 = 46 registers / 40 warps, 6 = 40 registers.
+template <int MINB, bool GROUPED>
 __global__ void __launch_bounds__(32 * kOrfWarps, MINB) k_coding_orf(DevBatch B, const DevModel *__restrict__ models, int n_ext,
                                                                 int total_nodes) {
     __shared__ int s_first;
-    const int lane = threadIdx.x & 31;
-    // Work items are the STOP nodes.  A STOP node exists only if its ORF has a start, so an extraction with nn nodes
-    // has at most nn / 2 of them: the warps index a half-size slot space in which extraction e owns the slots from
-    // (node_off + 1) / 2 on, and only its first (#STOP nodes) slots have work.
-    const int h = blockIdx.x * kOrfWarps + (threadIdx.x >> 5);
-    int e = ext_hint(B, n_ext, min(2 * h, total_nodes - 1), 2 * blockIdx.x * kOrfWarps, total_nodes, &s_first);
-    if (h > (total_nodes + 1) / 2) return;
-    while (e + 1 < n_ext && ((B.exts[e + 1].node_off + 1) >> 1) <= h) e++;
+    int e, tl, lane, W;
+    if (GROUPED) {
+        const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (gt >= B.orf_toff[n_ext]) return;
+        e = B.orf_blk[gt >> 8];
+        while (e + 1 < n_ext && B.orf_toff[e + 1] <= gt) e++;
+        W = B.orf_w[e];
+        const int local = (int)(gt - B.orf_toff[e]);
+        tl = local / W;
+        lane = local % W;
+    } else {
+        // Work items are the STOP nodes.  A STOP node exists only if its ORF has a start, so an extraction with nn
+        // nodes has at most nn / 2 of them: the warps index a half-size slot space in which extraction e owns the
+        // slots from (node_off + 1) / 2 on, and only its first (#STOP nodes) slots have work.
+        const int h = blockIdx.x * kOrfWarps + (threadIdx.x >> 5);
+        e = ext_hint(B, n_ext, min(2 * h, total_nodes - 1), 2 * blockIdx.x * kOrfWarps, total_nodes, &s_first);
+        if (h > (total_nodes + 1) / 2) return;
+        while (e + 1 < n_ext && ((B.exts[e + 1].node_off + 1) >> 1) <= h) e++;
+        tl = h - ((B.exts[e].node_off + 1) >> 1);
+        lane = threadIdx.x & 31;
+        W = 32;
+    }
     const ExtractInfo X = B.exts[e];
     const int32_t *__restrict__ cbase = B.cbase + 4 * e;
-    const int tl = h - ((X.node_off + 1) >> 1), nn = X.nn;
+    const int nn = X.nn;
     const int n_fe = cbase[2] - cbase[1], n_re = nn - cbase[3];
     if (tl >= n_fe + n_re) return;
     const int z = (B.clist + X.node_off)[tl < n_fe ? cbase[1] + tl : cbase[3] + (tl - n_fe)];
@@ -347,7 +368,7 @@ __global__ void __launch_bounds__(32 * kOrfWarps, MINB) k_coding_orf(DevBatch B,
     const bool rev = c & CLS_REV;
     const int ch0 = B.ext_chain_off[e], nch = B.ext_chain_off[e + 1] - ch0;
 
-    for (int c0 = 0; c0 < nch; c0 += 32) {
+    for (int c0 = 0; c0 < nch; c0 += W) {
         const bool active = c0 + lane < nch;
         const int chain = active ? B.ext_chains[ch0 + c0 + lane] : 0;
         const ChainInfo C = B.chains[active ? chain : B.ext_chains[ch0]];
@@ -877,6 +898,16 @@ __global__ void __launch_bounds__(128) k_block_owner_exts(const ExtractInfo *__r
     const int64_t a = exts[k].node_off, e = a + exts[k].nn;
     for (int64_t b = (a + 127) >> 7; (b << 7) < e; b++) tab[b] = k;
 }
+// the same for ranges given by an offset array off[0..n] (entry b = owner of index b << shift)
+__global__ void __launch_bounds__(128) k_block_owner_off(const int64_t *__restrict__ off, int n, int shift, int32_t *__restrict__ tab) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t a = off[k], e = off[k + 1], step = (int64_t)1 << shift;
+    for (int64_t b = (a + step - 1) >> shift; (b << shift) < e; b++) tab[b] = k;
+}
+void launch_block_owner_off(const int64_t *off, int n, int shift, int32_t *tab, cudaStream_t st) {
+    if (n > 0) k_block_owner_off<<<(n + 127) / 128, 128, 0, st>>>(off, n, shift, tab);
+}
 void launch_block_owner_chains(const ChainInfo *chains, int n, int32_t *tab, cudaStream_t st) {
     if (n > 0) k_block_owner_chains<<<(n + 127) / 128, 128, 0, st>>>(chains, n, tab);
 }
@@ -894,9 +925,15 @@ void launch_coding(const DevBatch &B, const DevModel *models, int n_chains, int6
     if (n_chains == 0 || total == 0) return;
     if (B.ext_chains && B.dcT && n_ext > 0 && total_nodes > 0) {
         static const int minb = getenv("PGPU_CODING_MINB") ? atoi(getenv("PGPU_CODING_MINB")) : 5;  // A/B switch
-        const unsigned nb = ((total_nodes + 1) / 2 + 1 + kOrfWarps - 1) / kOrfWarps;
-        if (minb == 6) k_coding_orf<6><<<nb, 32 * kOrfWarps, 0, st>>>(B, models, n_ext, total_nodes);
-        else k_coding_orf<5><<<nb, 32 * kOrfWarps, 0, st>>>(B, models, n_ext, total_nodes);
+        if (B.orf_toff) {  // grouped mapping planned by the host (api.cu)
+            const unsigned nb = (unsigned)((B.orf_threads + 32 * kOrfWarps - 1) / (32 * kOrfWarps));
+            if (minb == 6) k_coding_orf<6, true><<<nb, 32 * kOrfWarps, 0, st>>>(B, models, n_ext, total_nodes);
+            else k_coding_orf<5, true><<<nb, 32 * kOrfWarps, 0, st>>>(B, models, n_ext, total_nodes);
+        } else {
+            const unsigned nb = ((total_nodes + 1) / 2 + 1 + kOrfWarps - 1) / kOrfWarps;
+            if (minb == 6) k_coding_orf<6, false><<<nb, 32 * kOrfWarps, 0, st>>>(B, models, n_ext, total_nodes);
+            else k_coding_orf<5, false><<<nb, 32 * kOrfWarps, 0, st>>>(B, models, n_ext, total_nodes);
+        }
     } else {
         k_coding<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total);
     }
