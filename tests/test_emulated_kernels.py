@@ -189,24 +189,4 @@ def test_randomised_batches_against_the_oracle(monkeypatch):
     assert fuzz_train.main() == 0
 
 
-@pytest.mark.parametrize("groups", ["1", "0"])
-def test_coding_score_lane_groups(capi, monkeypatch, groups):
-    """k_coding_orf with 4 / 8 / 16 / 32 lanes per ORF (PGPU_CODING_GROUPS=1) and with a warp per ORF (=0), on contigs
-    whose GC content sweeps the whole range, so that extractions with 1 ... 27 models (both translation tables) occur"""
-    monkeypatch.setenv("PGPU_CODING_GROUPS", groups)
-    c = capi.Context(0)
-    c.set_models(R.bins_blob(), 50)
-    seqs = [R.synth(2500 + 137 * k, 0.24 + 0.02 * k, 4100 + k) for k in range(27)]
-    flat, off = _batch(seqs)
-    res = c.find_genes_batch(flat, off, capi.make_opts(meta=True, want_nodes=True))
-    for k, s in enumerate(seqs):
-        d, gc, unk = orc.encode(s)
-        genes, nodes, winner, pairs = orc.find_genes_meta(d, gc / len(d), R.bins_blob())
-        a, b = res.gene_off[k], res.gene_off[k + 1]
-        assert int(res.summary["winner"][k]) == winner and b - a == len(genes), k
-        if winner >= 0:
-            n = res.nodes(k)
-            for f in ("ndx", "cscore", "sscore", "score", "traceb"):
-                assert np.array_equal(n[f], nodes[f]), (k, f)
-    assert res.stats["n_chains"] > 27 * 5
-    c.close()
+test_coding_score_lane_groups = G.test_coding_score_lane_groups
