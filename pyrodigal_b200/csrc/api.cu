@@ -88,6 +88,9 @@ struct pgpu_ctx {
                                // (PGPU_EXTRACT_ALGO; batches with N-run masks always use 1)
     int final_algo = 2;        // meta mode without node arrays: 2 = final scoring pass over the genes' ORFs only,
                                // 1 = over every node as with want_nodes (PGPU_FINAL_ALGO)
+    bool dp_ml_pack = false;   // PGPU_DP_ML_PACK=1: k_dp_ml walks 32 / W extraction groups of <= W chains per warp (W = 4 / 8 / 16).
+                               // Bit-exact under emulation but not timed yet: the groups of a warp diverge at every step, and
+                               // whether the hardware overlaps their memory stalls decides if this is a gain; off until measured
     bool coding_groups = true; // k_coding_orf with 4 / 8 / 16 lanes per ORF for extractions with few models (PGPU_CODING_GROUPS=0:
                                // one warp per ORF, the mapping measured in round 1)
     bool codon_lut = false;    // PGPU_CODON_LUT=1: k_codon_bits reads codon flags from a per-table byte table (written
@@ -870,17 +873,33 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     tr("uploaded dp tables");
     tev("dp uploads");
     if (dp_ml) {
-        // one warp per extraction (contig x translation table) and <= 32 of its chains, longest first
+        // a group = an extraction (contig x translation table) and <= 32 of its chains, one lane per chain; a job = what
+        // one warp walks: 32 / W groups of <= W chains (W = 4, 8, 16, 32), neighbours in the "longest first" order so
+        // that the groups of a warp have similar lengths (only with PGPU_DP_ML_PACK=1; default: one group per warp)
         std::vector<int4> groups;
         for (int e = 0; e < n_ext; e++)
             for (int c = h_eoff[e]; c < h_eoff[e + 1]; c += 32) groups.push_back(make_int4(c, std::min(32, h_eoff[e + 1] - c), e, exts[e].nn));
-        std::stable_sort(groups.begin(), groups.end(), [](const int4 &a, const int4 &b) { return a.w > b.w; });
+        auto width = [&](int L) { return !ctx->dp_ml_pack ? 32 : (L <= 4 ? 4 : L <= 8 ? 8 : L <= 16 ? 16 : 32); };
+        std::stable_sort(groups.begin(), groups.end(), [&](const int4 &a, const int4 &b) {
+            const int wa = width(a.y), wb = width(b.y);
+            return wa != wb ? wa > wb : a.w > b.w;   // by lane width, then longest first
+        });
         std::vector<int64_t> goff(groups.size() + 1, 0);
         for (size_t g = 0; g < groups.size(); g++) goff[g + 1] = goff[g] + (int64_t)groups[g].w * groups[g].y;
+        std::vector<int4> jobs;
+        for (size_t g = 0; g < groups.size();) {
+            const int W = width(groups[g].y), per = 32 / W;
+            int cnt = 0;
+            while (g + cnt < groups.size() && cnt < per && width(groups[g + cnt].y) == W) cnt++;
+            jobs.push_back(make_int4((int)g, W, cnt, groups[g].w));
+            g += cnt;
+        }
+        std::stable_sort(jobs.begin(), jobs.end(), [](const int4 &a, const int4 &b) { return a.w > b.w; });  // longest first
         int4 *d_groups = pool.upload(groups);
         int64_t *d_goff = pool.upload(goff);
+        int4 *d_jobs = pool.upload(jobs);
         if (pool.failed) return PGPU_ENOMEM;
-        launch_dp_ml(B, ctx->d_models, d_groups, d_goff, (int)groups.size(), n_chains, ctx->dp_ml_minb, st);
+        launch_dp_ml(B, ctx->d_models, d_groups, d_goff, d_jobs, (int)jobs.size(), n_chains, ctx->dp_ml_minb, st);
         ctx->launches++;
         if (ctx->dp_verify && total_cn > 0) {
             // self-check: the per-chain kernel must reproduce every score / traceback / overlap frame
@@ -1449,6 +1468,7 @@ int pgpu_create(int device, pgpu_ctx **out) {
     if (const char *a = getenv("PGPU_FINAL_ALGO")) ctx->final_algo = atoi(a);
     if (const char *a = getenv("PGPU_CODON_LUT")) ctx->codon_lut = atoi(a) != 0;
     if (const char *a = getenv("PGPU_CODING_GROUPS")) ctx->coding_groups = atoi(a) != 0;
+    if (const char *a = getenv("PGPU_DP_ML_PACK")) ctx->dp_ml_pack = atoi(a) != 0;
     if (const char *a = getenv("PGPU_LANES")) ctx->lanes = atoi(a);
     if (const char *a = getenv("PGPU_LANE_MIN_BP")) ctx->lane_min_bp = atoll(a);
     // keep freed blocks cached in the stream-ordered pool: sub-batches reuse them without going to the driver

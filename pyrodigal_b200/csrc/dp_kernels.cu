@@ -987,14 +987,23 @@ __device__ double g_ml_no_source = -DBL_MAX;  // what idle lanes read instead of
 template <int MINB>
 __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const DevModel *__restrict__ models,
                                                                const int4 *__restrict__ groups,
-                                                               const int64_t *__restrict__ group_off, int n_groups) {
+                                                               const int64_t *__restrict__ group_off,
+                                                               const int4 *__restrict__ jobs, int n_jobs) {
     __shared__ MlK s_k[kMlWarps][32];
     __shared__ double s_rcv[3][32 * kMlWarps];  // per frame: best +start of the open forward ORF (value, node)
     __shared__ int32_t s_rcj[3][32 * kMlWarps];
-    const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
-    const int slot = blockIdx.x * kMlWarps + wslot;
-    if (slot >= n_groups) return;
-    const int4 G = groups[slot];  // x: first entry in ext_chains, y: number of chains (<= 32), z: extraction
+    const int wlane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
+    const int jslot = blockIdx.x * kMlWarps + wslot;
+    if (jslot >= n_jobs) return;
+    // A job packs 32 / W extraction groups of at most W chains each into one warp (W = 4, 8, 16 or 32 lanes per group):
+    // everything below is written per group -- `lane` is the lane within the group, the "uniform" cursors are uniform
+    // within a group, and the groups of a warp simply diverge; the few collective operations take the group's mask.
+    const int4 J = jobs[jslot];   // x: first group, y: W, z: groups in this job
+    const int W = J.y, gsub = wlane / W, lane = wlane % W;
+    if (gsub >= J.z) return;
+    const unsigned gmask = W == 32 ? 0xffffffffu : (((1u << W) - 1u) << (gsub * W));
+    const int slot = J.x + gsub;
+    const int4 G = groups[slot];  // x: first entry in ext_chains, y: number of chains (<= W), z: extraction
     const int L = G.y;
     const bool act = lane < L;
     const int ll = act ? lane : 0;  // idle lanes shadow lane 0 (loads stay in bounds, stores are suppressed)
@@ -1027,7 +1036,7 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
     int32_t *tbig = B.dp_tbig + goff;
     double *fmv = B.dp_fmv + goff;
     int32_t *fmj = B.dp_fmj + goff;
-    MlK *sk = s_k[wslot];
+    MlK *sk = s_k[wslot] + gsub * W;   // W staged targets per group
     const double ig_neg = M.ig_neg;
     const double *__restrict__ igt = M.igt;
     // source value of a merged-stream entry for this lane; idle lanes read "no source" (stride 0)
@@ -1044,8 +1053,8 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
 #pragma unroll
     for (int f = 0; f < 3; f++) { s_rcv[f][threadIdx.x] = kNeg; s_rcj[f][threadIdx.x] = -1; }
 
-    for (int i0 = 0; i0 < nn; i0 += 32) {
-      __syncwarp();
+    for (int i0 = 0; i0 < nn; i0 += W) {
+      __syncwarp(gmask);
       if (i0 + lane < nn) {
           const int i = i0 + lane;
           MlK k;
@@ -1065,7 +1074,7 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
           }
           sk[lane] = k;
       }
-      if (act && i0 + 32 < nn) {  // the chain-major score lines of the next block
+      if (act && i0 + 32 < nn && (i0 & 31) == 0) {  // the chain-major score lines of the next 32 targets
           const double *pc = (csum ? csum : cscore) + i0 + 32, *ps = sscore + i0 + 32;
 #pragma unroll
           for (int t = 0; t < 3; t++) {
@@ -1073,8 +1082,8 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
               if (!csum) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + min(16 * t, 31)));
           }
       }
-      __syncwarp();
-      const int iend = min(i0 + 32, nn);
+      __syncwarp(gmask);
+      const int iend = min(i0 + W, nn);
       for (int i = i0; i < iend; i++) {
         const MlK &K = sk[i - i0];
         const int ci = K.cls, kind = cls_kind(ci), f2 = cls_frame(ci), ndx_i = K.ndx, sv_i = K.sv;
@@ -1248,9 +1257,9 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
                             a_ = max(sa, lo_fe); b_ = min(sb, ffe);
                         }
                         const bool any = a_ < b_;
-                        if (!__any_sync(0xffffffffu, any)) continue;
-                        const int ua = __reduce_min_sync(0xffffffffu, any ? a_ : 0x7fffffff);
-                        const int ub = __reduce_max_sync(0xffffffffu, any ? b_ : -1);
+                        if (!__any_sync(gmask, any)) continue;
+                        const int ua = __reduce_min_sync(gmask, any ? a_ : 0x7fffffff);
+                        const int ub = __reduce_max_sync(gmask, any ? b_ : -1);
 #pragma unroll 1
                         for (int r = ua; r < ub; r++) {
                             if (r < a_ || r >= b_) continue;
@@ -1286,7 +1295,7 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
             const double g = sc_i + cs_i;
             if (g >= s_rcv[f2][threadIdx.x]) { s_rcv[f2][threadIdx.x] = g; s_rcj[f2][threadIdx.x] = i; }
         }
-        __syncwarp();  // every lane reads only its own column; the barrier just keeps the warp converged
+        __syncwarp(gmask);  // every lane reads only its own column; the barrier just keeps the group converged
       }
     }
 }
@@ -1733,13 +1742,13 @@ void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, 
     else if (final) k_dp<1><<<n_chains, kDpThreads, 0, st>>>(B, models, order, n_chains);
     else k_dp<0><<<n_chains, kDpThreads, 0, st>>>(B, models, order, n_chains);
 }
-void launch_dp_ml(const DevBatch &B, const DevModel *models, const int4 *groups, const int64_t *group_off, int n_groups,
-                  int n_chains, int minb, cudaStream_t st) {
-    if (n_groups == 0 || n_chains == 0) return;
-    const int nb = (n_groups + kMlWarps - 1) / kMlWarps;
-    if (minb == 8) k_dp_ml<8><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, n_groups);
-    else if (minb == 6) k_dp_ml<6><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, n_groups);
-    else k_dp_ml<5><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, n_groups);
+void launch_dp_ml(const DevBatch &B, const DevModel *models, const int4 *groups, const int64_t *group_off, const int4 *jobs,
+                  int n_jobs, int n_chains, int minb, cudaStream_t st) {
+    if (n_jobs == 0 || n_chains == 0) return;
+    const int nb = (n_jobs + kMlWarps - 1) / kMlWarps;
+    if (minb == 8) k_dp_ml<8><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, jobs, n_jobs);
+    else if (minb == 6) k_dp_ml<6><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, jobs, n_jobs);
+    else k_dp_ml<5><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, jobs, n_jobs);
     k_chain_best<<<(n_chains * 32 + 127) / 128, 128, 0, st>>>(B, n_chains);
 }
 // PGPU_DP_VERIFY: element-wise comparison of two DP results (score, traceback, overlap frame)

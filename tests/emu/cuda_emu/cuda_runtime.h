@@ -57,7 +57,9 @@ uint3 block_idx();
 dim3 block_dim();
 dim3 grid_dim();
 void sync_block();                           // __syncthreads
-uint64_t warp_exchange(uint64_t mine, uint64_t out[32], uint32_t *live_mask);  // all live lanes publish a value
+// the live lanes named by `mask` publish a value each and wait for one another (lanes that use different masks --
+// diverged groups of a warp -- rendezvous independently)
+uint64_t warp_exchange(unsigned mask, uint64_t mine, uint64_t out[32], uint32_t *live_mask);
 int lane_id();
 struct Launch {
     unsigned grid, block;
@@ -73,10 +75,10 @@ struct Launch {
 static constexpr int warpSize = 32;
 
 static inline void __syncthreads() { emu::sync_block(); }
-static inline void __syncwarp(unsigned = 0xffffffffu) { uint64_t v[32]; uint32_t m; emu::warp_exchange(0, v, &m); }
-static inline unsigned __ballot_sync(unsigned, int pred) {
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { uint64_t v[32]; uint32_t m; emu::warp_exchange(mask, 0, v, &m); }
+static inline unsigned __ballot_sync(unsigned mask, int pred) {
     uint64_t v[32]; uint32_t live;
-    emu::warp_exchange(pred ? 1 : 0, v, &live);
+    emu::warp_exchange(mask, pred ? 1 : 0, v, &live);
     unsigned r = 0;
     for (int l = 0; l < 32; l++) if (((live >> l) & 1u) && v[l]) r |= 1u << l;
     return r;
@@ -84,61 +86,61 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 static inline int __all_sync(unsigned m, int pred) {
     uint64_t v[32]; uint32_t live;
-    emu::warp_exchange(pred ? 1 : 0, v, &live);
+    emu::warp_exchange(m, pred ? 1 : 0, v, &live);
     for (int l = 0; l < 32; l++) if (((live >> l) & 1u) && !v[l]) return 0;
     return 1;
 }
 template <class T> static inline uint64_t emu_bits(T x) { uint64_t b = 0; static_assert(sizeof(T) <= 8, ""); memcpy(&b, &x, sizeof(T)); return b; }
 template <class T> static inline T emu_unbits(uint64_t b) { T x; memcpy(&x, &b, sizeof(T)); return x; }
-template <class T> static inline T __shfl_sync(unsigned, T var, int src, int width = 32) {
+template <class T> static inline T __shfl_sync(unsigned mask, T var, int src, int width = 32) {
     uint64_t v[32]; uint32_t live;
-    emu::warp_exchange(emu_bits(var), v, &live);
+    emu::warp_exchange(mask, emu_bits(var), v, &live);
     const int lane = emu::lane_id(), base = lane / width * width;
     const int s = base + (src % width + width) % width;
     return ((live >> s) & 1u) ? emu_unbits<T>(v[s]) : var;
 }
-template <class T> static inline T __shfl_xor_sync(unsigned, T var, int lm, int width = 32) {
+template <class T> static inline T __shfl_xor_sync(unsigned mask, T var, int lm, int width = 32) {
     uint64_t v[32]; uint32_t live;
-    emu::warp_exchange(emu_bits(var), v, &live);
+    emu::warp_exchange(mask, emu_bits(var), v, &live);
     const int lane = emu::lane_id(), s = lane ^ lm;
     return (s / width == lane / width && ((live >> s) & 1u)) ? emu_unbits<T>(v[s]) : var;
 }
-template <class T> static inline T __shfl_down_sync(unsigned, T var, unsigned d, int width = 32) {
+template <class T> static inline T __shfl_down_sync(unsigned mask, T var, unsigned d, int width = 32) {
     uint64_t v[32]; uint32_t live;
-    emu::warp_exchange(emu_bits(var), v, &live);
+    emu::warp_exchange(mask, emu_bits(var), v, &live);
     const int lane = emu::lane_id(), s = lane + (int)d;
     return (s / width == lane / width && s < 32 && ((live >> s) & 1u)) ? emu_unbits<T>(v[s]) : var;
 }
-template <class T> static inline T __shfl_up_sync(unsigned, T var, unsigned d, int width = 32) {
+template <class T> static inline T __shfl_up_sync(unsigned mask, T var, unsigned d, int width = 32) {
     uint64_t v[32]; uint32_t live;
-    emu::warp_exchange(emu_bits(var), v, &live);
+    emu::warp_exchange(mask, emu_bits(var), v, &live);
     const int lane = emu::lane_id(), s = lane - (int)d;
     return (s >= 0 && s / width == lane / width && ((live >> s) & 1u)) ? emu_unbits<T>(v[s]) : var;
 }
-static inline int __reduce_max_sync(unsigned, int x) {
+static inline int __reduce_max_sync(unsigned mask, int x) {
     uint64_t v[32]; uint32_t live;
-    emu::warp_exchange(emu_bits(x), v, &live);
+    emu::warp_exchange(mask, emu_bits(x), v, &live);
     int r = x;
     for (int l = 0; l < 32; l++) if ((live >> l) & 1u) r = std::max(r, emu_unbits<int>(v[l]));
     return r;
 }
-static inline int __reduce_min_sync(unsigned, int x) {
+static inline int __reduce_min_sync(unsigned mask, int x) {
     uint64_t v[32]; uint32_t live;
-    emu::warp_exchange(emu_bits(x), v, &live);
+    emu::warp_exchange(mask, emu_bits(x), v, &live);
     int r = x;
     for (int l = 0; l < 32; l++) if ((live >> l) & 1u) r = std::min(r, emu_unbits<int>(v[l]));
     return r;
 }
-static inline unsigned __reduce_max_sync(unsigned, unsigned x) {
+static inline unsigned __reduce_max_sync(unsigned mask, unsigned x) {
     uint64_t v[32]; uint32_t live;
-    emu::warp_exchange(emu_bits(x), v, &live);
+    emu::warp_exchange(mask, emu_bits(x), v, &live);
     unsigned r = x;
     for (int l = 0; l < 32; l++) if ((live >> l) & 1u) r = std::max(r, emu_unbits<unsigned>(v[l]));
     return r;
 }
-static inline unsigned __reduce_min_sync(unsigned, unsigned x) {
+static inline unsigned __reduce_min_sync(unsigned mask, unsigned x) {
     uint64_t v[32]; uint32_t live;
-    emu::warp_exchange(emu_bits(x), v, &live);
+    emu::warp_exchange(mask, emu_bits(x), v, &live);
     unsigned r = x;
     for (int l = 0; l < 32; l++) if ((live >> l) & 1u) r = std::min(r, emu_unbits<unsigned>(v[l]));
     return r;

@@ -11,12 +11,19 @@ namespace emu {
 
 enum { READY = 0, WAIT_WARP = 1, WAIT_BLOCK = 2, DONE = 3 };
 
-struct Warp {
+struct Barrier {          // rendezvous of the lanes named by one mask
+    uint32_t mask = 0;
     uint64_t slot[2][32];
     uint32_t live_snap[2];
-    uint32_t live_mask = 0;
-    int live = 0, arrived = 0;
+    int arrived = 0;
     unsigned gen = 0;
+};
+
+struct Warp {
+    Barrier bars[40];     // one per distinct mask seen in this block (full warp, 2 x 16, 4 x 8, 8 x 4 lanes, ...)
+    int n_bars = 0;
+    uint32_t live_mask = 0;
+    int live = 0;
 };
 
 struct Thread {
@@ -24,6 +31,7 @@ struct Thread {
     int tid = 0, state = READY;
     unsigned wait_gen = 0;
     Warp *warp = nullptr;
+    Barrier *bar = nullptr;
 };
 
 struct Engine {
@@ -49,28 +57,42 @@ int lane_id() { return cur->tid & 31; }
 
 static void yield_to_scheduler() { swapcontext(&cur->ctx, &E->sched); }
 
-static void release_warp(Warp *w) {
-    w->live_snap[w->gen & 1] = w->live_mask;
-    w->arrived = 0;
-    w->gen++;
+static void release(Warp *w, Barrier *b) {
+    b->live_snap[b->gen & 1] = w->live_mask & b->mask;
+    b->arrived = 0;
+    b->gen++;
 }
 
-uint64_t warp_exchange(uint64_t mine, uint64_t out[32], uint32_t *live_mask) {
+static Barrier *barrier_for(Warp *w, uint32_t mask) {
+    for (int k = 0; k < w->n_bars; k++)
+        if (w->bars[k].mask == mask) return &w->bars[k];
+    if (w->n_bars == 40) { fprintf(stderr, "cuda_emu: too many distinct warp masks\n"); abort(); }
+    Barrier *b = &w->bars[w->n_bars++];
+    *b = Barrier();
+    b->mask = mask;
+    return b;
+}
+
+uint64_t warp_exchange(unsigned mask, uint64_t mine, uint64_t out[32], uint32_t *live_mask) {
     Thread *t = cur;
     Warp *w = t->warp;
-    const unsigned g = w->gen, buf = g & 1;
-    w->slot[buf][t->tid & 31] = mine;
-    w->arrived++;
-    if (w->arrived == w->live) {
-        release_warp(w);
+    const int lane = t->tid & 31;
+    if (!((mask >> lane) & 1u)) { fprintf(stderr, "cuda_emu: lane %d is not in its own mask %08x\n", lane, mask); abort(); }
+    Barrier *b = barrier_for(w, mask);
+    const unsigned g = b->gen, buf = g & 1;
+    b->slot[buf][lane] = mine;
+    b->arrived++;
+    if (b->arrived >= __builtin_popcount(mask & w->live_mask)) {
+        release(w, b);
     } else {
         t->state = WAIT_WARP;
+        t->bar = b;
         t->wait_gen = g;
-        while (w->gen == g) yield_to_scheduler();
+        while (b->gen == g) yield_to_scheduler();
         t->state = READY;
     }
-    memcpy(out, w->slot[buf], sizeof(w->slot[buf]));
-    *live_mask = w->live_snap[buf];
+    memcpy(out, b->slot[buf], sizeof(b->slot[buf]));
+    *live_mask = b->live_snap[buf];
     return mine;
 }
 
@@ -97,7 +119,10 @@ static void trampoline() {
     Warp *w = t->warp;
     w->live--;
     w->live_mask &= ~(1u << (t->tid & 31));
-    if (w->live > 0 && w->arrived == w->live) release_warp(w);
+    for (int k = 0; k < w->n_bars; k++) {   // lanes that wait for this one at some barrier no longer have to
+        Barrier *b = &w->bars[k];
+        if (b->arrived > 0 && b->arrived >= __builtin_popcount(b->mask & w->live_mask)) release(w, b);
+    }
     E->block_live--;
     if (E->block_live > 0 && E->block_arrived == E->block_live) { E->block_arrived = 0; E->block_gen++; }
     swapcontext(&t->ctx, &E->sched);
@@ -105,7 +130,7 @@ static void trampoline() {
 
 static bool resumable(const Thread &t) {
     if (t.state == READY) return true;
-    if (t.state == WAIT_WARP) return t.warp->gen != t.wait_gen;
+    if (t.state == WAIT_WARP) return t.bar->gen != t.wait_gen;
     if (t.state == WAIT_BLOCK) return E->block_gen != t.wait_gen;
     return false;
 }
@@ -115,7 +140,8 @@ static void run_block(unsigned b) {
     e.bidx = b;
     const unsigned T = e.block, nw = (T + 31) / 32;
     e.threads.resize(T);
-    e.warps.assign(nw, Warp());
+    e.warps.clear();
+    e.warps.resize(nw);
     while (e.stacks.size() < T) e.stacks.push_back((char *)malloc(kStack));
     e.block_live = (int)T;
     e.block_arrived = 0;

@@ -190,3 +190,4 @@ def test_randomised_batches_against_the_oracle(monkeypatch):
 
 
 test_coding_score_lane_groups = G.test_coding_score_lane_groups
+test_dp_model_lane_kernel_packed_groups = G.test_dp_model_lane_kernel_packed_groups

@@ -482,3 +482,28 @@ def test_coding_score_lane_groups(capi, monkeypatch, groups):
                 assert np.array_equal(n[f], nodes[f]), (k, f)
     assert res.stats["n_chains"] > 27 * 5
     c.close()
+
+
+def test_dp_model_lane_kernel_packed_groups(capi, monkeypatch):
+    """PGPU_DP_ML_PACK=1: several extraction groups of few chains per warp; checked by the library's own
+    PGPU_DP_VERIFY comparison with k_dp_dq on a GC sweep (1 ... 27 models per extraction) and against the oracle"""
+    monkeypatch.setenv("PGPU_DP_ML_PACK", "1")
+    monkeypatch.setenv("PGPU_DP_VERIFY", "1")
+    c = capi.Context(0)
+    c.set_models(R.bins_blob(), 50)
+    seqs = [R.synth(3000 + 911 * (k % 7), 0.24 + 0.02 * (k % 27), 5200 + k) for k in range(54)]
+    arrs = [np.frombuffer(s, np.uint8) for s in seqs]
+    off = np.zeros(len(arrs) + 1, np.int64)
+    np.cumsum([len(a) for a in arrs], out=off[1:])
+    flat = np.ascontiguousarray(np.concatenate(arrs))
+    res = c.find_genes_batch(flat, off, capi.make_opts(meta=True, want_nodes=True))
+    for k in (0, 3, 13, 26, 27, 40, 53):
+        d, gc, unk = orc.encode(seqs[k])
+        genes, nodes, winner, pairs = orc.find_genes_meta(d, gc / len(d), R.bins_blob())
+        a, b = res.gene_off[k], res.gene_off[k + 1]
+        assert int(res.summary["winner"][k]) == winner and b - a == len(genes), k
+        if winner >= 0:
+            n = res.nodes(k)
+            for f in ("score", "traceb", "ov_mark", "cscore"):
+                assert np.array_equal(n[f], nodes[f]), (k, f)
+    c.close()
