@@ -899,7 +899,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         int64_t *d_goff = pool.upload(goff);
         int4 *d_jobs = pool.upload(jobs);
         if (pool.failed) return PGPU_ENOMEM;
-        launch_dp_ml(B, ctx->d_models, d_groups, d_goff, d_jobs, (int)jobs.size(), n_chains, ctx->dp_ml_minb, st);
+        launch_dp_ml(B, ctx->d_models, d_groups, d_goff, d_jobs, (int)jobs.size(), n_chains, ctx->dp_ml_minb, ctx->dp_ml_pack, st);
         ctx->launches++;
         if (ctx->dp_verify && total_cn > 0) {
             // self-check: the per-chain kernel must reproduce every score / traceback / overlap frame

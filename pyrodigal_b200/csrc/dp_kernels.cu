@@ -984,7 +984,7 @@ struct MlK {  // geometric constants of a target, staged 32 targets at a time (m
 
 __device__ double g_ml_no_source = -DBL_MAX;  // what idle lanes read instead of a source value
 
-template <int MINB>
+template <int MINB, bool PACK>   // PACK = false: one group of up to 32 chains per warp (W is the constant 32)
 __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const DevModel *__restrict__ models,
                                                                const int4 *__restrict__ groups,
                                                                const int64_t *__restrict__ group_off,
@@ -999,9 +999,9 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
     // everything below is written per group -- `lane` is the lane within the group, the "uniform" cursors are uniform
     // within a group, and the groups of a warp simply diverge; the few collective operations take the group's mask.
     const int4 J = jobs[jslot];   // x: first group, y: W, z: groups in this job
-    const int W = J.y, gsub = wlane / W, lane = wlane % W;
+    const int W = PACK ? J.y : 32, gsub = PACK ? wlane / W : 0, lane = PACK ? wlane % W : wlane;
     if (gsub >= J.z) return;
-    const unsigned gmask = W == 32 ? 0xffffffffu : (((1u << W) - 1u) << (gsub * W));
+    const unsigned gmask = (!PACK || W == 32) ? 0xffffffffu : (((1u << W) - 1u) << (gsub * W));
     const int slot = J.x + gsub;
     const int4 G = groups[slot];  // x: first entry in ext_chains, y: number of chains (<= W), z: extraction
     const int L = G.y;
@@ -1743,12 +1743,18 @@ void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, 
     else k_dp<0><<<n_chains, kDpThreads, 0, st>>>(B, models, order, n_chains);
 }
 void launch_dp_ml(const DevBatch &B, const DevModel *models, const int4 *groups, const int64_t *group_off, const int4 *jobs,
-                  int n_jobs, int n_chains, int minb, cudaStream_t st) {
+                  int n_jobs, int n_chains, int minb, bool pack, cudaStream_t st) {
     if (n_jobs == 0 || n_chains == 0) return;
     const int nb = (n_jobs + kMlWarps - 1) / kMlWarps;
-    if (minb == 8) k_dp_ml<8><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, jobs, n_jobs);
-    else if (minb == 6) k_dp_ml<6><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, jobs, n_jobs);
-    else k_dp_ml<5><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, jobs, n_jobs);
+    if (pack) {
+        if (minb == 8) k_dp_ml<8, true><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, jobs, n_jobs);
+        else if (minb == 6) k_dp_ml<6, true><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, jobs, n_jobs);
+        else k_dp_ml<5, true><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, jobs, n_jobs);
+    } else {
+        if (minb == 8) k_dp_ml<8, false><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, jobs, n_jobs);
+        else if (minb == 6) k_dp_ml<6, false><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, jobs, n_jobs);
+        else k_dp_ml<5, false><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, jobs, n_jobs);
+    }
     k_chain_best<<<(n_chains * 32 + 127) / 128, 128, 0, st>>>(B, n_chains);
 }
 // PGPU_DP_VERIFY: element-wise comparison of two DP results (score, traceback, overlap frame)

@@ -37,7 +37,7 @@ void launch_pairs(const DevBatch &B, int n_ext, int total_nodes, unsigned long l
 
 // dp_kernels.cu
 void launch_dp_ml(const DevBatch &B, const DevModel *models, const int4 *groups, const int64_t *group_off, const int4 *jobs,
-                  int n_jobs, int n_chains, int minb, cudaStream_t st);
+                  int n_jobs, int n_chains, int minb, bool pack, cudaStream_t st);
 void launch_dp_compare(const double *sa, const double *sb, const int32_t *ta, const int32_t *tb, const int8_t *oa,
                        const int8_t *ob, int64_t n, unsigned long long *bad, cudaStream_t st);
 void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, int n_chains, int final, int algo,
