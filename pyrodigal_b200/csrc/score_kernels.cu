@@ -673,6 +673,10 @@ __device__ __forceinline__ void start_score_node(const DevBatch &B, const DevMod
     if (mot_out) mot_out[g] = mot;
 }
 
+// BY_CLASS: the t-th thread of a chain takes the t-th node in class order (+starts, -starts, then the STOP nodes, through
+// the class-sorted index list) instead of node t, so that a warp holds either starts only -- no lanes idling on the
+// quarter of the nodes that are STOP nodes -- or STOP nodes only (which just write the reset state).
+template <bool BY_CLASS>
 __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel *__restrict__ models, int n_chains,
                                                       int64_t total, RunOpts o, MotifOut *__restrict__ mot_out) {
     __shared__ int s_first;
@@ -681,9 +685,21 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
     if (g >= total) return;
     while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
     const ChainInfo C = B.chains[k];
-    const int i = (int)(g - C.coff);
+    int i = (int)(g - C.coff);
     if (i >= C.nn) return;
-    start_score_node(B, models, C, g, i, o, mot_out);
+    if (BY_CLASS) {
+        // class order of clist: [0, c1) +starts, [c1, c2) +STOPs, [c2, c3) -starts, [c3, nn) -STOPs
+        const int32_t *__restrict__ cbase = B.cbase + 4 * C.ext;
+        const int c1 = cbase[1], c2 = cbase[2], c3 = cbase[3];
+        const int n_fs = c1, n_rs = c3 - c2, n_fe = c2 - c1;
+        int p;
+        if (i < n_fs) p = i;
+        else if (i < n_fs + n_rs) p = c2 + (i - n_fs);
+        else if (i < n_fs + n_rs + n_fe) p = c1 + (i - n_fs - n_rs);
+        else p = c3 + (i - n_fs - n_rs - n_fe);
+        i = (B.clist + C.node_off)[p];
+    }
+    start_score_node(B, models, C, C.coff + i, i, o, mot_out);
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -941,7 +957,11 @@ void launch_coding(const DevBatch &B, const DevModel *models, int n_chains, int6
 void launch_start_score(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o, void *mot_out,
                         cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
-    k_start_score<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total, o, (MotifOut *)mot_out);
+    static const bool by_class = getenv("PGPU_SCORE_BY_CLASS") && atoi(getenv("PGPU_SCORE_BY_CLASS")) != 0;  // A/B switch
+    if (by_class && B.clist && B.cbase)
+        k_start_score<true><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total, o, (MotifOut *)mot_out);
+    else
+        k_start_score<false><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total, o, (MotifOut *)mot_out);
 }
 void launch_score_chains(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o,
                          void *mot_out, int n_ext, int total_nodes, cudaStream_t st) {
