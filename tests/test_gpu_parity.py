@@ -507,23 +507,3 @@ def test_dp_model_lane_kernel_packed_groups(capi, monkeypatch):
             for f in ("score", "traceb", "ov_mark", "cscore"):
                 assert np.array_equal(n[f], nodes[f]), (k, f)
     c.close()
-
-
-def test_start_scoring_in_class_order(capi, monkeypatch):
-    """PGPU_SCORE_BY_CLASS=1: k_start_score with threads mapped to nodes in class order (starts first); read at library
-    load time, hence a fresh process-wide setting is not possible here: the variant is exercised when the variable is set
-    for the whole test run, and this test only asserts that scoring matches the oracle in the current setting"""
-    c = capi.Context(0)
-    c.set_models(R.bins_blob(), 50)
-    seq = R.synth(30000, .45, 515)
-    d, _, _ = orc.encode(seq)
-    for model, is_meta in ((0, True), (24, False)):
-        blob = R.bin_blob(model)
-        tt = int(np.frombuffer(blob, np.int32, count=1, offset=8)[0])
-        ref = orc.extract(d, tt)
-        orc.reset_scores(ref)
-        orc.score(d, ref, blob, closed=False, is_meta=is_meta)
-        orc.record_overlapping_starts(ref, blob, flag=1, max_overlap=60)
-        got = c.score_nodes(np.frombuffer(seq, np.uint8), model, capi.make_opts(), is_meta=is_meta, first_pass=True)
-        cmp_nodes(got, ref, f"score_nodes[m{model}]", star=True)
-    c.close()
