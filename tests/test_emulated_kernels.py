@@ -9,6 +9,7 @@ libpyrodigal_b200.so and still fails without a CUDA device.  What the emulation 
 real concurrency between blocks or on the hardware's memory model (the GPU run remains the parity gate)."""
 import os
 import sys
+import types
 
 import numpy as np
 import pytest
@@ -36,7 +37,21 @@ def ctx(capi):
 
 
 FULL = os.environ.get("PGPU_EMU_FULL") == "1"   # also the four heavy cases (about 8 minutes more)
-heavy = pytest.mark.skipif(not FULL, reason="heavy under emulation: set PGPU_EMU_FULL=1")
+_heavy_mark = pytest.mark.skipif(not FULL, reason="heavy under emulation: set PGPU_EMU_FULL=1")
+
+
+def _clone(fn):
+    """an independent copy of a test function: pytest marks are stored ON the function object, so marking the
+    function imported from test_gpu_parity would also skip it in the GPU run (that happened in round 1)"""
+    g = types.FunctionType(fn.__code__, fn.__globals__, fn.__name__, fn.__defaults__, fn.__closure__)
+    g.__dict__.update(fn.__dict__)
+    g.__kwdefaults__ = fn.__kwdefaults__
+    g.pytestmark = list(getattr(fn, "pytestmark", []))
+    return g
+
+
+def heavy(fn):
+    return _heavy_mark(_clone(fn))
 
 # the operator-level and end-to-end parity tests of the GPU suite, unchanged (the Mbp-sized inputs stay GPU-only)
 test_extract_nodes = G.test_extract_nodes

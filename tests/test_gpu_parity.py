@@ -415,6 +415,32 @@ def test_gene_only_final_pass_equals_full_final_pass(ctx, capi, closed):
             assert np.array_equal(nodes[full.genes["stop_ndx"][a:b]], gn[a:b, 1])
 
 
+@pytest.mark.parametrize("closed", [False, True])
+def test_gene_only_final_pass_vs_oracle(ctx, capi, closed):
+    """the path bench.py times (meta mode, want_nodes=False): genes, winner and the start / stop node record of every
+    gene -- all five scores, rbs, motif, gc_cont -- directly against the oracle's node arrays"""
+    rng = np.random.default_rng(15)
+    seqs = [b"", R.synth(95, .5, 3), R.synth(90000, .47, 14)]
+    for k in range(40):
+        seqs.append(R.synth(int(rng.integers(200, 30000)), float(rng.uniform(.28, .72)), 17000 + k,
+                            n_frac=0.002 if k % 5 == 0 else 0.0))
+    lean = run_meta(ctx, capi, seqs, closed=closed, want_nodes=False)
+    gn = lean.gene_nodes.reshape(-1, 2)
+    checked = 0
+    for k, s in enumerate(seqs):
+        d, gc, unk = orc.encode(s)
+        genes, nodes, winner, _ = orc.find_genes_meta(d, gc / len(d) if len(d) else 0.0, R.bins_blob(),
+                                                      orc.make_opts(closed=closed))
+        assert int(lean.summary["winner"][k]) == winner, k
+        a, b = lean.gene_off[k], lean.gene_off[k + 1]
+        cmp_int(lean.genes[a:b], genes, f"contig{k}.genes")
+        if b > a:
+            cmp_nodes(gn[a:b, 0], nodes[genes["start_ndx"]], f"contig{k}.start_nodes")
+            cmp_nodes(gn[a:b, 1], nodes[genes["stop_ndx"]], f"contig{k}.stop_nodes")
+            checked += b - a
+    assert checked > 300
+
+
 @pytest.mark.parametrize("many_parts", [False, True])
 def test_two_lane_host_batches_match_single_stream(capi, monkeypatch, many_parts):
     """host-input batches above PGPU_LANE_MIN_BP run as sub-batches on two worker threads / streams; the stitched
