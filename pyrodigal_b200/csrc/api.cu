@@ -91,8 +91,8 @@ struct pgpu_ctx {
     bool dp_ml_pack = false;   // PGPU_DP_ML_PACK=1: k_dp_ml walks 32 / W extraction groups of <= W chains per warp (W = 4 / 8 / 16).
                                // Bit-exact under emulation but not timed yet: the groups of a warp diverge at every step, and
                                // whether the hardware overlaps their memory stalls decides if this is a gain; off until measured
-    bool coding_groups = false; // PGPU_CODING_GROUPS=1: k_coding_orf with 4 / 8 / 16 lanes per ORF for extractions with few models
-                                // (bit-exact under emulation, not timed yet; default: one warp per ORF, as measured in round 1)
+    bool coding_groups = true;  // k_coding_orf with 4 / 8 / 16 lanes per ORF for extractions with few models (measured on the
+                                // cfg4 shard: scoring phase 44.0 -> 39.6 ms); PGPU_CODING_GROUPS=0 = one warp per ORF
     bool codon_lut = false;    // PGPU_CODON_LUT=1: k_codon_bits reads codon flags from a per-table byte table (written
                                // after the last GPU run of round 1: logic checked by the host emulation only, so off)
     bool dp_verify = false;    // PGPU_DP_VERIFY=1: run k_dp_dq after k_dp_ml and fail on any difference (self-check)
