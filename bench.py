@@ -52,14 +52,21 @@ def synth_into(out, gc, seed):
         out[s:s + len(u)] = lut[code]
 
 
-def make_contigs(first, count, seed=4, universe=100_000, contig_seed0=1_000_000):
-    """contigs [first, first+count) of a (lengths uniform 1-100 kbp, GC uniform .30-.70) configuration:
-    (flat uint8 ASCII array, int64 offsets).  Defaults = cfg4; cfg3 = (seed 3, universe 1000, contig seeds 10 000 + k)"""
+def config_table(seed=4, universe=100_000):
+    """(lengths, gcs) of every contig of a configuration, drawn once so that shards are disjoint subsets of it"""
     rng = np.random.default_rng(seed)
-    # lengths / gc of the whole configuration are drawn once so that shards are disjoint slices of it
     lengths = rng.integers(1_000, 100_001, size=universe)
     gcs = rng.uniform(0.30, 0.70, size=universe)
-    idx = np.arange(first, first + count) % universe
+    return lengths, gcs
+
+
+def make_contigs(first, count, seed=4, universe=100_000, contig_seed0=1_000_000, ids=None):
+    """contigs [first, first+count) (or the contigs `ids`) of a (lengths uniform 1-100 kbp, GC uniform .30-.70)
+    configuration: (flat uint8 ASCII array, int64 offsets).  Defaults = cfg4; cfg3 = (seed 3, universe 1000, contig
+    seeds 10 000 + k)"""
+    lengths, gcs = config_table(seed, universe)
+    idx = (np.arange(first, first + count) if ids is None else np.asarray(ids)) % universe
+    count = len(idx)
     lens = lengths[idx]
     offsets = np.zeros(count + 1, dtype=np.int64)
     np.cumsum(lens, out=offsets[1:])
@@ -70,8 +77,23 @@ def make_contigs(first, count, seed=4, universe=100_000, contig_seed0=1_000_000)
 
 
 def shard_range(rank, contigs_per_gpu):
-    """contigs owned by `rank`: a disjoint slice of the 100k-contig configuration (weak scaling)"""
+    """contigs owned by `rank` under the by-index partition: a disjoint slice of the 100k-contig configuration"""
     return rank * contigs_per_gpu, contigs_per_gpu
+
+
+def shard_ids(rank, world, contigs_per_gpu):
+    """contigs owned by `rank` when `world` GPUs share the first world x contigs_per_gpu contigs of cfg4 (weak scaling:
+    the job grows with N, N = 8 is the whole 100k-contig batch): greedy longest-processing-time partition over the
+    estimated cost per contig (pyrodigal_b200.distributed).  One rank = the by-index slice."""
+    if world == 1:
+        return np.arange(contigs_per_gpu)
+    from pyrodigal_b200 import distributed as PD
+    import pyrodigal_b200
+    n = min(world * contigs_per_gpu, 100_000)
+    lengths, gcs = config_table()
+    model_gc = [b.training_info.gc for b in pyrodigal_b200.METAGENOMIC_BINS]
+    owner = PD.lpt_partition(PD.contig_cost(lengths[:n], gcs[:n], model_gc), world)
+    return np.flatnonzero(owner == rank)
 
 
 class Dist:
@@ -224,13 +246,13 @@ META_CONFIGS = ("cfg4", "cfg4-full", "cfg3")
 SINGLE_CONFIGS = ("cfg2", "cfg5", "cfg5-tt4")
 
 
-def workload(config, rank, contigs):
+def workload(config, rank, contigs, world=1):
     """-> dict(flat, offsets, meta, label, ...) of the rank's input for `config`"""
     import refutil as R
     if config == "cfg4":
-        first, count = shard_range(rank, contigs)
-        flat, off = make_contigs(first, count)
-        return {"flat": flat, "offsets": off, "meta": True,
+        ids = shard_ids(rank, world, contigs)
+        flat, off = make_contigs(0, 0, ids=ids)
+        return {"flat": flat, "offsets": off, "meta": True, "ids": ids, "n_total": min(world * contigs, 100_000),
                 "label": "cfg4: 100k-contig synthetic metagenome (1-100 kbp, GC 0.30-0.70), meta mode, "
                          f"{contigs} contigs per GPU, contig-sharded"}
     if config == "cfg4-full":
@@ -438,7 +460,8 @@ def main():
 
     def base_line(w):
         cfg = {"workload": w["label"], "name": args.config,
-               "parallelism": (f"contig-shard x{n_gpus}" if sharded else f"replicas x{n_gpus}"),
+               "parallelism": (f"contig-shard x{n_gpus} (LPT by estimated cost; gene records gathered on rank 0 inside e2e)"
+                               if sharded else f"replicas x{n_gpus}"),
                "l2_policy": "L2 flushed between timed steps (256 MB device memset)" if small
                else "inputs larger than L2 (per-step working set >> 126 MB)"}
         if sharded:
@@ -483,7 +506,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     D = Dist("nccl", f"cuda:{local_rank}")
-    w = workload(args.config, rank, args.contigs)
+    w = workload(args.config, rank, args.contigs, world)
     flat, offsets = w["flat"], w["offsets"]
     bp = int(offsets[-1])
     # pinned host staging of the step's input (the e2e leg copies from here every step)
@@ -509,7 +532,35 @@ def main():
         else:
             ctx.set_models(R.bin_blob(w["bin"]), 1)
 
-    def timed(fn, steps, per_step=None):
+    class Gatherer:
+        """N > 1: the gene records of every step are gathered on rank 0 (pyrodigal_b200.distributed.gather_result: counts by
+        all_gather, records over NCCL) by a helper thread, so that the gather of step k overlaps the kernels of step k+1;
+        the last gather is waited for INSIDE the timed region."""
+        def __init__(self):
+            from pyrodigal_b200 import distributed as PD
+            self.PD, self.t, self.out, self.err = PD, None, None, None
+
+        def _run(self, res):
+            try:
+                torch.cuda.set_device(local_rank)
+                self.out = self.PD.gather_result(res, w["ids"], w["n_total"], device=local_rank)
+            except Exception as e:   # re-raised by wait()
+                self.err = e
+
+        def submit(self, res):
+            self.wait()
+            self.t = threading.Thread(target=self._run, args=(res,))
+            self.t.start()
+
+        def wait(self):
+            if self.t is not None:
+                self.t.join()
+                self.t = None
+            if self.err is not None:
+                raise self.err
+            return self.out
+
+    def timed(fn, steps, per_step=None, gather=None):
         """K steps bracketed by barrier + synchronize; CUDA events on the library's stream; max over ranks.  Small
         inputs: L2 is flushed before every step, and the step times (CUDA events per step) are summed instead."""
         D.barrier()
@@ -520,18 +571,23 @@ def main():
         wall = 0.0
         last = None
         for _ in range(steps):
-            last = None  # release the previous result first: its pinned buffer is reused by the next step
+            if gather is None:
+                last = None  # release the previous result first: its pinned buffer is reused by the next step
             if small:
                 flush_l2()
                 ctx.timer_start()
             t1 = time.perf_counter()
             last = fn()
+            if gather is not None:
+                gather.submit(last)
             dt = (time.perf_counter() - t1) * 1e3
             if small:
                 tot_ms += ctx.timer_stop()
                 wall += dt
             if per_step is not None:
                 per_step.append(dict(last.stats, wall_ms=dt))
+        if gather is not None:
+            gather.wait()
         if not small:
             tot_ms = ctx.timer_stop()
             wall = (time.perf_counter() - t0) * 1e3
@@ -590,10 +646,15 @@ def main():
         r = step_host()
     r = None
     e2e_steps = []
-    ms_e2e, wall_e2e, res2 = timed(step_host, args.steps, e2e_steps)
+    gatherer = Gatherer() if (sharded and world > 1) else None
+    if gatherer is not None:   # one untimed gather: NCCL connections, pinned receive buffers
+        gatherer.submit(step_host())
+        gatherer.wait()
+    ms_e2e, wall_e2e, res2 = timed(step_host, args.steps, e2e_steps, gatherer)
     st2 = res2.stats
-    if w.get("train"):
-        ms_e2e = wall_e2e   # two calls with host work in between: the wall clock is the end-to-end time
+    gathered = gatherer.wait() if gatherer is not None else None
+    if w.get("train") or gatherer is not None:
+        ms_e2e = wall_e2e   # host work between / after the library calls: the wall clock is the end-to-end time
     # the same call from pageable (ordinary numpy) memory, as a Python caller holding `bytes` would make it
     res2 = None
     pe_steps = max(2, min(3, args.steps))
@@ -676,7 +737,8 @@ def main():
                     "wall_ms_steps": [round(t["wall_ms"], 1) for t in e2e_steps],
                     "device_ms_steps": [round(t["ms_total_device"], 1) for t in e2e_steps],
                     "api": "pgpu_train + pgpu_set_models + pgpu_find_genes_batch (C ABI, pinned host input)" if w.get("train")
-                           else "pgpu_find_genes_batch (C ABI, pinned host input)"},
+                           else "pgpu_find_genes_batch (C ABI, pinned host input)"
+                           + (" + distributed.gather_result (gene records of all ranks on rank 0, NCCL)" if gathered is not None else "")},
             "gpu_launches": int(tot_launch * args.steps),
             "roofline": {"bound": "hbm", "kernel": dp_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "note": dp_note,
@@ -695,6 +757,9 @@ def main():
         if w.get("train"):
             line["phases_ms_rank0"].update({k: float(np.mean([t[k] for t in step_stats])) for k in
                                             ("train_ms_total_device", "train_ms_dp", "train_ms_score")})
+        if gathered is not None:
+            line["e2e"]["gathered_on_rank0"] = {"contigs": int(gathered.n), "genes": int(gathered.gene_off[-1]),
+                                                "ranks": len(gathered.stats)}
         if e2e_page is not None:
             e2e_page["value"] = mbps(e2e_page["ms_per_step"])
             line["e2e"]["pageable_input"] = e2e_page

@@ -141,6 +141,11 @@ int pgpu_find_genes_batch(pgpu_ctx *ctx, const uint8_t *seq, const int64_t *offs
 typedef struct pgpu_batch pgpu_batch;
 int pgpu_batch_upload(pgpu_ctx *ctx, const uint8_t *seq, const int64_t *offsets, int n_contigs,
                       pgpu_batch **out);
+/* The same for input that ALREADY sits in device memory of ctx's device (e.g. a sequence shard received from
+ * another GPU over NCCL, pyrodigal_b200/distributed.py): `d_seq` is a device pointer, borrowed -- the caller keeps
+ * it alive until pgpu_batch_free and frees it itself.  `offsets` is a host array as above. */
+int pgpu_batch_wrap_device(pgpu_ctx *ctx, const uint8_t *d_seq, const int64_t *offsets, int n_contigs,
+                           pgpu_batch **out);
 int pgpu_batch_run(pgpu_ctx *ctx, pgpu_batch *batch, const pgpu_opts *opts, pgpu_result **out);
 void pgpu_batch_free(pgpu_batch *batch);
 

@@ -84,6 +84,7 @@ lib.pgpu_timer_start.argtypes = [_vp]
 lib.pgpu_timer_stop.argtypes = [_vp, C.POINTER(C.c_double)]
 lib.pgpu_find_genes_batch.argtypes = [_vp, _vp, _vp, C.c_int, C.POINTER(Opts), C.POINTER(_vp)]
 lib.pgpu_batch_upload.argtypes = [_vp, _vp, _vp, C.c_int, C.POINTER(_vp)]
+lib.pgpu_batch_wrap_device.argtypes = [_vp, _vp, _vp, C.c_int, C.POINTER(_vp)]
 lib.pgpu_batch_run.argtypes = [_vp, _vp, C.POINTER(Opts), C.POINTER(_vp)]
 lib.pgpu_batch_free.argtypes = [_vp]
 lib.pgpu_batch_free.restype = None
@@ -183,6 +184,17 @@ class Context:
         b = _vp()
         check(lib.pgpu_batch_upload(self.handle, ptr(seq), ptr(offsets), len(offsets) - 1, C.byref(b)), self.handle)
         return Batch(self, b)
+
+    def wrap_device(self, device_ptr, offsets, keepalive=None):
+        """a Batch over ASCII bytes that already sit in this device's memory (device_ptr: int); `keepalive` (e.g. the
+        torch tensor that owns the memory) is held until the Batch is freed"""
+        b = _vp()
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        check(lib.pgpu_batch_wrap_device(self.handle, _vp(int(device_ptr)), ptr(offsets), len(offsets) - 1, C.byref(b)),
+              self.handle)
+        bt = Batch(self, b)
+        bt.keepalive = keepalive
+        return bt
 
     def train(self, seq, opts, translation_table=11, start_weight=4.35, force_nonsd=False):
         """GeneFinder.train on one (already joined) ASCII sequence -> (raw training struct bytes, stats dict)"""

@@ -353,7 +353,8 @@ struct pgpu_result {
 };
 
 struct pgpu_batch {
-    pgpu_ctx *ctx = nullptr;
+    int device = 0;                // the context may be destroyed before its batches: keep the device, not the context
+    bool owned = true;             // false: d_ascii is caller-owned device memory (pgpu_batch_wrap_device)
     int n_contigs = 0;
     std::vector<int64_t> offsets;  // [n+1]
     uint8_t *d_ascii = nullptr;    // device copy of the whole concatenated input
@@ -1591,7 +1592,7 @@ int pgpu_batch_upload(pgpu_ctx *ctx, const uint8_t *seq, const int64_t *offsets,
     if (!out || !offsets || n_contigs < 0) return fail(ctx, PGPU_EINVAL, "bad arguments");
     cudaSetDevice(ctx->device);
     pgpu_batch *b = new pgpu_batch();
-    b->ctx = ctx;
+    b->device = ctx->device;
     b->n_contigs = n_contigs;
     b->offsets.assign(offsets, offsets + n_contigs + 1);
     const int64_t base = offsets[0];
@@ -1613,9 +1614,26 @@ int pgpu_batch_run(pgpu_ctx *ctx, pgpu_batch *batch, const pgpu_opts *opts, pgpu
     return run_all(ctx, nullptr, batch->d_ascii, batch->offsets.data(), batch->n_contigs, opts, out);
 }
 
+int pgpu_batch_wrap_device(pgpu_ctx *ctx, const uint8_t *d_seq, const int64_t *offsets, int n_contigs, pgpu_batch **out) {
+    if (!ctx) return PGPU_EINVAL;
+    if (!out || !offsets || n_contigs < 0 || (!d_seq && n_contigs > 0 && offsets[n_contigs] > offsets[0]))
+        return fail(ctx, PGPU_EINVAL, "bad arguments");
+    pgpu_batch *b = new pgpu_batch();
+    b->device = ctx->device;
+    b->owned = false;
+    b->n_contigs = n_contigs;
+    b->offsets.assign(offsets, offsets + n_contigs + 1);
+    const int64_t base = offsets[0];
+    for (auto &o : b->offsets) o -= base;
+    b->total = b->offsets[n_contigs];
+    b->d_ascii = const_cast<uint8_t *>(d_seq) + base;
+    *out = b;
+    return PGPU_OK;
+}
+
 void pgpu_batch_free(pgpu_batch *b) {
     if (!b) return;
-    if (b->d_ascii) { cudaSetDevice(b->ctx->device); cudaFree(b->d_ascii); }
+    if (b->d_ascii && b->owned) { cudaSetDevice(b->device); cudaFree(b->d_ascii); }
     delete b;
 }
 

@@ -279,29 +279,57 @@ _ctx_lock = threading.Lock()
 _ctx_cache = {}
 
 
+class _CtxLock:
+    """The per-context lock callers hold around a library call.  Leaving it also drops the use count that
+    `_context_for` / `_training_context` took for the caller, and a context is only evicted from the cache (and
+    destroyed) while its use count is zero -- so no thread can be inside, or on its way into, a call on a context
+    that is being destroyed."""
+
+    def __init__(self, ctx):
+        self._lock, self._ctx = threading.Lock(), ctx
+
+    def __enter__(self):
+        self._lock.acquire()
+        return self
+
+    def __exit__(self, *exc):
+        self._lock.release()
+        with _ctx_lock:
+            self._ctx.users = max(0, self._ctx.users - 1)
+        return False
+
+
 def _context_for(model_blob, n_models, device=0):
+    """the cached context of (device, model set), with its use count taken: the caller enters `ctx.lock` exactly once"""
     key = (device, n_models, hash(model_blob))
     with _ctx_lock:
         ctx = _ctx_cache.get(key)
         if ctx is None:
-            if len(_ctx_cache) >= 4:  # keep the device footprint bounded
-                _ctx_cache.pop(next(iter(_ctx_cache))).close()
+            # keep the device footprint bounded: drop an IDLE model context (never the training context, never one
+            # that a thread holds or is about to lock); if every context is busy the cache grows instead
+            idle = [k for k, c in _ctx_cache.items() if k[1] != "train" and getattr(c, "users", 0) == 0]
+            if len(_ctx_cache) >= 4 and idle:
+                _ctx_cache.pop(idle[0]).close()
             ctx = _capi.Context(device)
             ctx.set_models(model_blob, n_models, key)
-            ctx.lock = threading.Lock()
+            ctx.users = 0
+            ctx.lock = _CtxLock(ctx)
             _ctx_cache[key] = ctx
+        ctx.users += 1
         return ctx
 
 
 def _training_context(device=0):
-    """training needs a device and a stream but no model set: one model-less context per device"""
+    """training needs a device and a stream but no model set: one model-less context per device (never evicted)"""
     key = (device, "train")
     with _ctx_lock:
         ctx = _ctx_cache.get(key)
         if ctx is None:
             ctx = _capi.Context(device)
-            ctx.lock = threading.Lock()
+            ctx.users = 0
+            ctx.lock = _CtxLock(ctx)
             _ctx_cache[key] = ctx
+        ctx.users += 1
         return ctx
 
 
