@@ -113,12 +113,12 @@ static int mer_ndx(const uint8_t *d, int slen, int i, int len, int strand) {
 /* node extraction (add_nodes)                                                           */
 /* ------------------------------------------------------------------------------------ */
 
-static int masked(const orc_opts *o, int begin, int end) {
-    /* lib.pyx:337-340 applied to every mask (the per-frame cursor of lib.pyx:1959-1963 /
-     * 2053-2057 is an optimisation of "intersects any mask") */
-    for (int m = 0; m < o->n_masks; m++)
-        if (o->masks[2 * m] < end && begin < o->masks[2 * m + 1]) return 1;
-    return 0;
+/* lib.pyx:337-340 for ONE mask (index m; -1 = the NULL cursor; n_masks = the zero-initialised slot behind the last
+ * mask that the reverse-strand cursor can rest on, lib.pyx:2055 compares with &masks[length]) */
+static int mask_hits(const orc_opts *o, int m, int begin, int end) {
+    if (m < 0) return 0;
+    const int mb = m < o->n_masks ? o->masks[2 * m] : 0, me = m < o->n_masks ? o->masks[2 * m + 1] : 0;
+    return mb < end && begin < me;
 }
 
 typedef struct { orc_node *out; int n, cap; } node_sink;
@@ -141,6 +141,14 @@ static void emit(node_sink *s, int slen, int strand, int pos, int type, int stop
  * coordinates, frame = i % 3 */
 static void scan_strand(const uint8_t *d, int slen, int tt, const orc_opts *o, int strand, node_sink *s) {
     int last[3], saw[3] = {0, 0, 0}, min_dist[3];
+    /* The reference does NOT test a candidate ORF against every mask: each frame keeps one cursor into the sorted mask
+     * list (lib.pyx:1929-1932 / 2023-2026) and only the mask under the cursor is tested (1959-1966 / 2053-2061).
+     * Forward strand: the cursor starts at the last mask and steps down while the ORF end lies before the mask
+     * (-> the last mask with begin <= last); reverse strand: it starts at the first mask and steps up while the
+     * ORF's left end lies beyond the mask's end (-> the first mask with end >= left end; it may rest on the zeroed
+     * slot behind the list before it becomes NULL).  A second N run further inside the ORF is therefore not seen. */
+    int cur[3];
+    for (int k = 0; k < 3; k++) cur[k] = o->n_masks > 0 ? (strand == 1 ? o->n_masks - 1 : 0) : -1;
     for (int k = 0; k < 3; k++) {
         int f = (slen + k) % 3;
         last[f] = slen + k;
@@ -159,7 +167,16 @@ static void scan_strand(const uint8_t *d, int slen, int tt, const orc_opts *o, i
         }
         if (last[f] >= slen) continue;
         if (o->n_masks) {
-            int hit = strand == 1 ? masked(o, i, last[f]) : masked(o, slen - last[f] - 1, slen - i - 1);
+            int hit;
+            if (strand == 1) {
+                while (cur[f] >= 0 && last[f] < o->masks[2 * cur[f]]) cur[f] = cur[f] == 0 ? -1 : cur[f] - 1;
+                hit = mask_hits(o, cur[f], i, last[f]);
+            } else {
+                const int left = slen - last[f] - 1;
+                while (cur[f] >= 0 && left > (cur[f] < o->n_masks ? o->masks[2 * cur[f] + 1] : 0))
+                    cur[f] = cur[f] == o->n_masks ? -1 : cur[f] + 1;
+                hit = mask_hits(o, cur[f], left, slen - i - 1);
+            }
             if (hit) continue;
         }
         if (last[f] - i + 3 >= min_dist[f] && is_start(d, slen, i, tt, strand)) {

@@ -218,8 +218,12 @@ class Context:
         return out
 
     def score_nodes(self, seq, model, opts, is_meta=False, first_pass=True):
-        cap = max(1024, len(seq) // 4 + 64)
-        out = np.zeros(cap, dtype=NODE_DTYPE)
+        # every position can carry at most one node per strand (plus the closing STOP nodes of the six frames)
+        cap = 2 * len(seq) + 16
+        if cap > (1 << 16):   # long sequences: ask for the count first (dst = NULL) instead of reserving 208 B per base
+            cap = check(lib.pgpu_score_nodes(self.handle, ptr(seq), len(seq), model, C.byref(opts), int(is_meta),
+                                             int(first_pass), 0, None), self.handle)
+        out = np.zeros(max(cap, 1), dtype=NODE_DTYPE)
         n = check(lib.pgpu_score_nodes(self.handle, ptr(seq), len(seq), model, C.byref(opts), int(is_meta),
                                        int(first_pass), cap, ptr(out)), self.handle)
         return out[:n].copy()

@@ -1509,24 +1509,33 @@ const char *pgpu_last_error(const pgpu_ctx *ctx) { return ctx ? ctx->err.c_str()
 int pgpu_set_models(pgpu_ctx *ctx, const void *blobs, int n, size_t stride) {
     if (!ctx) return PGPU_EINVAL;
     if (!blobs || n <= 0 || stride < sizeof(RawTraining)) return fail(ctx, PGPU_EINVAL, "bad model blobs");
-    cudaSetDevice(ctx->device);
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (ctx->d_raw) { cudaFree(ctx->d_raw); ctx->d_raw = nullptr; }
-    if (ctx->d_models) { cudaFree(ctx->d_models); ctx->d_models = nullptr; }
     std::vector<RawTraining> h_raw_v(n);   // host copy of the raw structs, only needed to prepare the device tables
     for (int k = 0; k < n; k++) memcpy(&h_raw_v[k], (const char *)blobs + k * stride, sizeof(RawTraining));
-    CK(cudaMalloc(&ctx->d_raw, n * sizeof(RawTraining)));
-    CK(cudaMalloc(&ctx->d_models, n * sizeof(DevModel)));
-    if (ctx->d_live) { cudaFree(ctx->d_live); ctx->d_live = nullptr; }
-    CK(cudaMalloc(&ctx->d_live, (size_t)n * 2048 * sizeof(uint32_t)));
-    {
+    for (int k = 0; k < n; k++) {
+        // the translation tables the reference accepts (lib.pyx TRANSLATION_TABLES: 1-6, 9-16, 21-33); the value
+        // selects codon sets in every kernel, so a corrupt blob is refused here
+        const int tt = h_raw_v[k].trans_table;
+        const bool ok = (tt >= 1 && tt <= 6) || (tt >= 9 && tt <= 16) || (tt >= 21 && tt <= 33);
+        if (!ok) return fail(ctx, PGPU_EINVAL, "model " + std::to_string(k) + ": translation table " + std::to_string(tt) + " is not valid");
+    }
+    cudaSetDevice(ctx->device);
+    CK(cudaStreamSynchronize(ctx->stream));
+    // Build the new device tables next to the old ones and swap them in only when every step has succeeded: a failed
+    // call leaves the context with the model set it had.
+    RawTraining *d_raw = nullptr;
+    DevModel *d_models = nullptr;
+    uint32_t *d_live = nullptr;
+    double *d_dcT = nullptr;
+    std::vector<DevModel> h_models(n);
+    auto build = [&]() -> cudaError_t {
+        cudaError_t e;
+        if ((e = cudaMalloc(&d_raw, n * sizeof(RawTraining))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&d_models, n * sizeof(DevModel))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&d_live, (size_t)n * 2048 * sizeof(uint32_t))) != cudaSuccess) return e;
         std::vector<uint32_t> live((size_t)n * 2048);
         for (int k = 0; k < n; k++) motif_live_bits(h_raw_v[k], live.data() + (size_t)k * 2048);
-        CK(cudaMemcpy(ctx->d_live, live.data(), live.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    }
-    ctx->h_models.resize(n);
-    for (int k = 0; k < n; k++) prepare_model(h_raw_v[k], ctx->h_models[k], ctx->d_raw + k, ctx->d_live + (size_t)k * 2048);
-    {
+        if ((e = cudaMemcpy(d_live, live.data(), live.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+        for (int k = 0; k < n; k++) prepare_model(h_raw_v[k], h_models[k], d_raw + k, d_live + (size_t)k * 2048);
         // transposed dicodon table: models that are evaluated together (same table, neighbouring GC) get
         // neighbouring columns, so the lanes of k_coding_orf read one or two cache lines per codon
         std::vector<int> ord(n);
@@ -1537,18 +1546,25 @@ int pgpu_set_models(pgpu_ctx *ctx, const void *blobs, int n, size_t stride) {
         });
         // rows are kDcCols wide (a compile-time stride: one multiply-add per weight address in the kernel); a model
         // set with more columns than that runs the per-chain kernel k_coding instead (d_dcT stays null)
-        if (ctx->d_dcT) { cudaFree(ctx->d_dcT); ctx->d_dcT = nullptr; }
-        for (int c = 0; c < n; c++) ctx->h_models[ord[c]].col = c;
+        for (int c = 0; c < n; c++) h_models[ord[c]].col = c;
         if (n <= kDcCols) {
             std::vector<double> t((size_t)4096 * kDcCols, 0.0);
             for (int c = 0; c < n; c++)
                 for (int i = 0; i < 4096; i++) t[(size_t)i * kDcCols + c] = h_raw_v[ord[c]].gene_dc[i];
-            CK(cudaMalloc(&ctx->d_dcT, t.size() * sizeof(double)));
-            CK(cudaMemcpy(ctx->d_dcT, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+            if ((e = cudaMalloc(&d_dcT, t.size() * sizeof(double))) != cudaSuccess) return e;
+            if ((e = cudaMemcpy(d_dcT, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
         }
+        if ((e = cudaMemcpy(d_raw, h_raw_v.data(), n * sizeof(RawTraining), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+        return cudaMemcpy(d_models, h_models.data(), n * sizeof(DevModel), cudaMemcpyHostToDevice);
+    };
+    const cudaError_t e = build();
+    if (e != cudaSuccess) {
+        cudaFree(d_raw); cudaFree(d_models); cudaFree(d_live); cudaFree(d_dcT);
+        return fail(ctx, e == cudaErrorMemoryAllocation ? PGPU_ENOMEM : PGPU_ECUDA, std::string("pgpu_set_models: ") + cudaGetErrorString(e));
     }
-    CK(cudaMemcpy(ctx->d_raw, h_raw_v.data(), n * sizeof(RawTraining), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_models, ctx->h_models.data(), n * sizeof(DevModel), cudaMemcpyHostToDevice));
+    cudaFree(ctx->d_raw); cudaFree(ctx->d_models); cudaFree(ctx->d_live); cudaFree(ctx->d_dcT);
+    ctx->d_raw = d_raw; ctx->d_models = d_models; ctx->d_live = d_live; ctx->d_dcT = d_dcT;
+    ctx->h_models.swap(h_models);
     ctx->n_models = n;
     ctx->model_gc.resize(n);
     ctx->model_tt.resize(n);

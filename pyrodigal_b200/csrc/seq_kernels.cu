@@ -136,14 +136,27 @@ __global__ void k_find_masks(DevBatch B, const int2 *__restrict__ tiles, int min
 // node extraction
 // --------------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ bool masked_any(const int32_t *__restrict__ m, int n, int begin, int end) {
-    // masks are disjoint and sorted: first mask whose end is > begin, then test its begin (lib.pyx:337-340)
-    int lo = 0, hi = n;
+// The reference tests a candidate ORF against ONE mask only, the one under a per-frame cursor into the sorted mask
+// list (lib.pyx:1959-1966 forward, 2053-2061 reverse).  The ORF end only moves one way during the scan, so the cursor
+// is a function of the ORF end and needs no state here:
+//   forward: the LAST mask with begin <= last      (then lib.pyx:337-340: begin < last && i < end)
+//   reverse: the FIRST mask with end >= left end   (left = slen-last-1; then begin < right && left < end)
+// A second N run further inside the ORF is not seen by the reference and must not be seen here.
+__device__ __forceinline__ bool masked_fwd(const int32_t *__restrict__ m, int n, int i, int last) {
+    int lo = 0, hi = n;   // first mask with begin > last
     while (lo < hi) {
         int mid = (lo + hi) >> 1;
-        if (m[2 * mid + 1] > begin) hi = mid; else lo = mid + 1;
+        if (m[2 * mid] > last) hi = mid; else lo = mid + 1;
     }
-    return lo < n && m[2 * lo] < end;
+    return lo > 0 && m[2 * (lo - 1)] < last && i < m[2 * (lo - 1) + 1];
+}
+__device__ __forceinline__ bool masked_rev(const int32_t *__restrict__ m, int n, int left, int right) {
+    int lo = 0, hi = n;   // first mask with end >= left
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (m[2 * mid + 1] >= left) hi = mid; else lo = mid + 1;
+    }
+    return lo < n && m[2 * lo] < right && left < m[2 * lo + 1];
 }
 
 // Warp-cooperative, chunked scan (used for batches with N-run masks; the default path is the bit-parallel
@@ -260,7 +273,7 @@ __global__ void __launch_bounds__(128) k_extract_w(DevBatch B, int n_ext, int to
         if (valid && !is_stop && my_last < slen) {
             bool hit = false;
             if (X.n_masks)
-                hit = rev ? masked_any(masks, X.n_masks, slen - my_last - 1, slen - i - 1) : masked_any(masks, X.n_masks, i, my_last);
+                hit = rev ? masked_rev(masks, X.n_masks, slen - my_last - 1, slen - i - 1) : masked_fwd(masks, X.n_masks, i, my_last);
             if (!hit) {
                 q_start = is_startc && (my_last - i + 3 >= my_min);
                 qual = q_start || (i <= 2 && !o.closed && my_last - i > o.min_edge_gene);

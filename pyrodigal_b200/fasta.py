@@ -89,7 +89,20 @@ def read_batch(source):
     # end of every header line (exclusive): the next newline, or the end of the file
     k = np.searchsorted(eol, hdr_pos)
     hdr_end = np.where(k < len(eol), eol[np.minimum(k, len(eol) - 1)] if len(eol) else n, n)
-    keep = ~(nl | (a == 13) | (a == 32) | (a == 9))       # sequence bytes: everything but line ends / blanks
+    # sequence bytes: the reference strips every line (tests/fasta.py:61-86: `line.strip()`), i.e. white space at the
+    # ENDS of a line goes, white space inside a line stays (and later encodes as an unknown base)
+    ws = (a == 13) | (a == 32) | (a == 9) | (a == 11) | (a == 12)
+    keep = ~(nl | ws)
+    if ws.any():
+        c = np.cumsum(keep)                                  # non-blank bytes so far
+        line_id = np.cumsum(nl) - nl                         # a newline belongs to the line it ends
+        n_lines = int(line_id[-1]) + 1
+        starts = np.concatenate(([0], np.flatnonzero(nl) + 1))[:n_lines]
+        ends = np.concatenate((np.flatnonzero(nl), [n - 1]))[:n_lines]
+        c_before = np.where(starts > 0, c[np.maximum(starts - 1, 0)], 0)
+        c_end = c[ends]
+        inner = ws & (c > c_before[line_id]) & (c < c_end[line_id])
+        keep |= inner
     for b, e in zip(hdr_pos, hdr_end):
         keep[b:e] = False
     if len(hdr_pos) == 0:

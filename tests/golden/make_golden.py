@@ -86,6 +86,10 @@ def meta_cases():
     for name, sk, gk in specs:
         seq = R.synth(**sk)
         cases[name] = (seq, gk, None)
+    # mask=True with a trailing N run and an N run inside the last open reading frame: the reference's per-frame
+    # mask cursor (lib.pyx:1959-1966) keeps starts that an "intersects any mask" test would drop
+    for seed in (0, 2, 7):
+        cases[f"trailing_N_mask_{seed}"] = (R.trailing_n_case(seed), dict(mask=True), None)
     for fn in ("KK037166", "SRR492066"):
         _, s = R.read_fasta_gz(os.path.join(R.REF_DATA, fn + ".fna.gz"))[0]
         cases[fn] = (s.encode(), {}, fn)
@@ -337,6 +341,9 @@ def writer_cases():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "writers":
         writer_cases()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "meta":
+        meta_cases()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "train":
         train_cases()

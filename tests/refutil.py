@@ -62,6 +62,20 @@ def synth(length, gc=0.5, seed=0, n_frac=0.0):
     return a.tobytes()
 
 
+def trailing_n_case(seed):
+    """the advisor's scenario (round 1): a contig that ends in 3-5 Ns -- always a mask, lib.pyx:711-712 -- with an N run of
+    >= 50 inside the last open reading frame: the forward cursor rests on the trailing mask (begin == last), so the inner
+    run is never tested and the reference keeps the starts that span it"""
+    rng = np.random.default_rng(seed)
+    L = int(rng.integers(2000, 5000))
+    a = np.frombuffer(synth(L, .7, 3000 + seed), np.uint8).copy()
+    tail, inner = int(rng.integers(3, 6)), int(rng.integers(50, 90))
+    pos = L - int(rng.integers(150, 500))
+    a[pos:pos + inner] = ord("N")
+    a[L - tail:] = ord("N")
+    return a.tobytes()
+
+
 def read_fasta_gz(path):
     seqs, name, buf = [], None, []
     with gzip.open(path, "rt") as f:

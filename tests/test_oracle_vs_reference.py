@@ -61,3 +61,10 @@ def test_random_short_contigs_all_modes(seed):
         L = int(rng.integers(90, 6000))
         gc = float(rng.uniform(.25, .75))
         check_meta(R.synth(L, gc, seed=int(rng.integers(1 << 30))), closed=bool(rng.integers(2)), what=f"rand{L}")
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_masks_follow_the_reference_cursor(seed):
+    """GeneFinder(mask=True): the reference tests a candidate ORF only against the mask under a per-frame cursor
+    (lib.pyx:1959-1966 / 2053-2061), not against every mask (an "intersects any mask" rule fails 5 of these 30)"""
+    check_meta(R.trailing_n_case(seed), mask=True, closed=False, what=f"masks{seed}")
