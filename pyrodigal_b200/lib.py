@@ -7,6 +7,7 @@ lib.ConnectionScorer.  All computation happens in libpyrodigal_b200.so on the GP
 (include/pyrodigal_b200.h); this module only marshals buffers and formats results.
 """
 import datetime
+import collections.abc
 import itertools
 import json
 import lzma
@@ -1144,10 +1145,34 @@ class GeneFinder:
             seq = Sequence(seq, mask=self.mask, mask_size=self.min_mask)
         seq._gc_count, seq._unknown = int(s["gc_count"]), int(s["unknown"])
         nodes = Nodes(res.nodes(k)) if want_nodes else None
-        return Genes(res.genes[a:b].copy(), res.gene_nodes[a:b].copy(), sequence=seq, training_info=tinf, metagenomic_bin=mbin,
+        return Genes(res.genes[a:b], res.gene_nodes[a:b], sequence=seq, training_info=tinf, metagenomic_bin=mbin,
                      meta=self.meta, nodes=nodes, ipath=int(s["ipath"]), num_seq=num_seq)
 
     # ---- public ----
+    class _Batch(collections.abc.Sequence):
+        """What `find_genes_many` / `find_genes_batch` return: a read-only sequence of `Genes`, one per contig, built on
+        first access from the result buffers of the batched call (zero-copy views of the library's page-locked result
+        memory).  Creating twelve thousand `Genes` / `Sequence` objects eagerly cost more host time than the GPU pass."""
+
+        def __init__(self, finder, res, sequences, want_nodes, first):
+            self._finder, self._res, self._sequences, self._want_nodes, self._first = finder, res, sequences, want_nodes, first
+            self._cache = {}
+
+        def __len__(self):
+            return self._res.n
+
+        def __getitem__(self, k):
+            if isinstance(k, slice):
+                return [self[i] for i in range(*k.indices(len(self)))]
+            if k < 0:
+                k += len(self)
+            if not 0 <= k < len(self):
+                raise IndexError("batch index out of range")
+            g = self._cache.get(k)
+            if g is None:
+                g = self._cache[k] = self._finder._wrap(self._res, k, self._sequences(k), self._want_nodes, self._first + k)
+            return g
+
     def find_genes(self, sequence):
         """Find all the genes in one input sequence (lib.pyx:5400-5469)."""
         return self.find_genes_many([sequence], want_nodes=True)[0]
@@ -1179,8 +1204,10 @@ class GeneFinder:
             res = ctx.find_genes_batch(flat, offsets, self._opts(want_nodes))
         self.last_stats = res.stats
         if sequences is None:
-            sequences = [flat[offsets[k]:offsets[k + 1]] for k in range(n)]
-        return [self._wrap(res, k, sequences[k], want_nodes, first + k) for k in range(n)]
+            get = lambda k: flat[offsets[k]:offsets[k + 1]]
+        else:
+            get = sequences.__getitem__
+        return GeneFinder._Batch(self, res, get, want_nodes, first)
 
     def train(self, sequence, *sequences, force_nonsd=False, start_weight=4.35, translation_table=11):
         """Search parameters for the ORF finder using a training sequence (lib.pyx:5471-5575).
