@@ -88,16 +88,11 @@ struct pgpu_ctx {
                                // (PGPU_EXTRACT_ALGO; batches with N-run masks always use 1)
     int final_algo = 2;        // meta mode without node arrays: 2 = final scoring pass over the genes' ORFs only,
                                // 1 = over every node as with want_nodes (PGPU_FINAL_ALGO)
-    bool dp_ml_pack = false;   // PGPU_DP_ML_PACK=1: k_dp_ml walks 32 / W extraction groups of <= W chains per warp (W = 4 / 8 / 16).
-                               // Bit-exact under emulation but not timed yet: the groups of a warp diverge at every step, and
-                               // whether the hardware overlaps their memory stalls decides if this is a gain; off until measured
-    bool coding_groups = true;  // k_coding_orf with 4 / 8 / 16 lanes per ORF for extractions with few models (measured on the
-                                // cfg4 shard: scoring phase 44.0 -> 39.6 ms); PGPU_CODING_GROUPS=0 = one warp per ORF
     bool codon_lut = false;    // PGPU_CODON_LUT=1: k_codon_bits reads codon flags from a per-table byte table (written
                                // after the last GPU run of round 1: logic checked by the host emulation only, so off)
     bool dp_verify = false;    // PGPU_DP_VERIFY=1: run k_dp_dq after k_dp_ml and fail on any difference (self-check)
     int dp_algo = 5;           // 5: k_dp_ml for multi-model batches, k_dp_dq otherwise (default); 6: k_dp_ml always;
-                               // 3/4: k_dp_dq, 1/2: k_dp_fast, 0: all-pairs k_dp (PGPU_DP_ALGO=n)
+                               // 1-4: k_dp_dq, 0: all-pairs k_dp (PGPU_DP_ALGO=n)
     std::shared_ptr<struct PinnedPool> pinned;  // shared with the results it backs (they may outlive the context)
     // Optional: host-input calls (pgpu_find_genes_batch) on large batches run as sub-batches on two worker threads /
     // streams ("lanes"), so that the H2D copy, the host planning gaps and the D2H of one hide under the kernels of the other.
@@ -690,6 +685,19 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     for (int e = 0; e < n_ext; e++) { exts[e].node_off = h_base[e]; exts[e].nn = h_base[e + 1] - h_base[e]; }
     int64_t total_cn = 0;
     for (auto &K : chains) { K.node_off = exts[K.ext].node_off; K.nn = exts[K.ext].nn; K.coff = total_cn; total_cn += K.nn; }
+    // interleaved layout of the arrays the DP touches (ChainInfo::ioff): the chains of an extraction share one block of
+    // nn x L elements, element (node, chain) at block + node * L + position of the chain among them
+    std::vector<int32_t> h_eoff(n_ext + 1, 0);   // chains of an extraction: [h_eoff[e], h_eoff[e+1]) in B.ext_chains
+    std::vector<int32_t> h_elist(n_chains);
+    {
+        for (const auto &K : chains) h_eoff[K.ext + 1]++;
+        for (int e = 0; e < n_ext; e++) h_eoff[e + 1] += h_eoff[e];
+        std::vector<int32_t> fillp(h_eoff.begin(), h_eoff.end() - 1);
+        for (int k = 0; k < n_chains; k++) { chains[k].lane = fillp[chains[k].ext] - h_eoff[chains[k].ext]; h_elist[fillp[chains[k].ext]++] = k; }
+        std::vector<int64_t> iblock(n_ext + 1, 0);
+        for (int e = 0; e < n_ext; e++) iblock[e + 1] = iblock[e] + (int64_t)exts[e].nn * (h_eoff[e + 1] - h_eoff[e]);
+        for (auto &K : chains) { K.istride = h_eoff[K.ext + 1] - h_eoff[K.ext]; K.ioff = iblock[K.ext] + K.lane; }
+    }
     pool.copy_in(B.exts, exts.data(), n_ext * sizeof(ExtractInfo));
 
     // ---- extraction pass 2: fill, then per-extraction preparation ----------------------------------
@@ -753,21 +761,15 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     tr("issued fill/prep");
     // ---- per-chain scoring ---------------------------------------------------------------------------
     B.chains = pool.upload(chains);
-    std::vector<int32_t> h_eoff;  // chains of an extraction: [h_eoff[e], h_eoff[e+1]) in B.ext_chains
     {
-        std::vector<int32_t> &eoff = h_eoff;
-        eoff.assign(n_ext + 1, 0);
-        std::vector<int32_t> elist(n_chains);
-        for (const auto &K : chains) eoff[K.ext + 1]++;
-        for (int e = 0; e < n_ext; e++) eoff[e + 1] += eoff[e];
-        std::vector<int32_t> fillp(eoff.begin(), eoff.end() - 1);
-        for (int k = 0; k < n_chains; k++) elist[fillp[chains[k].ext]++] = k;
-        B.ext_chain_off = pool.upload(eoff);
-        B.ext_chains = pool.upload(elist);
+        const std::vector<int32_t> &eoff = h_eoff;
+        B.ext_chain_off = pool.upload(h_eoff);
+        B.ext_chains = pool.upload(h_elist);
         B.dcT = ctx->d_dcT;
         B.n_models = ctx->n_models;
-        if (ctx->coding_groups && ctx->d_dcT && n_chains > n_ext) {
-            // k_coding_orf, grouped: W lanes per ORF for an extraction with L chains, (nn / 2 + 1) ORF slots
+        if (n_chains > n_ext) {
+            // thread layout of the kernels that put the lanes of a group over the chains (models) of an extraction
+            // (k_coding_orf, k_overlap_lanes): W lanes per STOP node for an extraction with L chains, nn / 2 + 1 slots
             std::vector<int64_t> toff(n_ext + 1, 0);
             std::vector<uint8_t> w(n_ext + 1, 32);
             for (int e = 0; e < n_ext; e++) {
@@ -799,18 +801,13 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     B.chain_ipath = pool.alloc<int32_t>(n_chains);
     B.chain_score = pool.alloc<double>(n_chains);
     const bool dp_ml = ctx->dp_algo >= 6 || (ctx->dp_algo == 5 && n_chains > n_ext);
-    if (ctx->dp_algo >= 3) {
+    if (ctx->dp_algo >= 1) {
         B.dp_svig = pool.alloc<double>(total_cn);
         B.dp_tbig = pool.alloc<int32_t>(total_cn);
         if (dp_ml) {
             B.dp_fmv = pool.alloc<double>(total_cn);
             B.dp_fmj = pool.alloc<int32_t>(total_cn);
         }
-    } else if (ctx->dp_algo >= 1) {
-        B.dp_sv = pool.alloc<double>(total_cn);
-        B.dp_tbn = pool.alloc<int32_t>(total_cn);
-        B.dp_bx = pool.alloc<double>(total_cn / 16 + 2 * (size_t)n_chains + 8);
-        B.dp_bj = pool.alloc<int32_t>(total_cn / 16 + 2 * (size_t)n_chains + 8);
     }
     int32_t *d_tracef = pool.alloc<int32_t>(total_cn);
     uint8_t *d_elim = pool.alloc<uint8_t>(total_cn + 16, true);
@@ -831,7 +828,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     tev("k_start_score");
     ctx->launches += 2;
     int e_score = mark();
-    launch_overlap(B, ctx->d_models, n_chains, total_cn, ro, 1, st);
+    launch_overlap(B, ctx->d_models, n_chains, total_cn, n_ext, ro, 1, st);
     tev("k_overlap");
     ctx->launches++;
     int e_ovl = mark();
@@ -874,33 +871,15 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     tr("uploaded dp tables");
     tev("dp uploads");
     if (dp_ml) {
-        // a group = an extraction (contig x translation table) and <= 32 of its chains, one lane per chain; a job = what
-        // one warp walks: 32 / W groups of <= W chains (W = 4, 8, 16, 32), neighbours in the "longest first" order so
-        // that the groups of a warp have similar lengths (only with PGPU_DP_ML_PACK=1; default: one group per warp)
+        // a group = an extraction (contig x translation table) and <= 32 of its chains, one lane per chain = what one warp
+        // walks; longest first, so that the tail of the launch consists of short walks
         std::vector<int4> groups;
         for (int e = 0; e < n_ext; e++)
             for (int c = h_eoff[e]; c < h_eoff[e + 1]; c += 32) groups.push_back(make_int4(c, std::min(32, h_eoff[e + 1] - c), e, exts[e].nn));
-        auto width = [&](int L) { return !ctx->dp_ml_pack ? 32 : (L <= 4 ? 4 : L <= 8 ? 8 : L <= 16 ? 16 : 32); };
-        std::stable_sort(groups.begin(), groups.end(), [&](const int4 &a, const int4 &b) {
-            const int wa = width(a.y), wb = width(b.y);
-            return wa != wb ? wa > wb : a.w > b.w;   // by lane width, then longest first
-        });
-        std::vector<int64_t> goff(groups.size() + 1, 0);
-        for (size_t g = 0; g < groups.size(); g++) goff[g + 1] = goff[g] + (int64_t)groups[g].w * groups[g].y;
-        std::vector<int4> jobs;
-        for (size_t g = 0; g < groups.size();) {
-            const int W = width(groups[g].y), per = 32 / W;
-            int cnt = 0;
-            while (g + cnt < groups.size() && cnt < per && width(groups[g + cnt].y) == W) cnt++;
-            jobs.push_back(make_int4((int)g, W, cnt, groups[g].w));
-            g += cnt;
-        }
-        std::stable_sort(jobs.begin(), jobs.end(), [](const int4 &a, const int4 &b) { return a.w > b.w; });  // longest first
+        std::stable_sort(groups.begin(), groups.end(), [](const int4 &a, const int4 &b) { return a.w > b.w; });
         int4 *d_groups = pool.upload(groups);
-        int64_t *d_goff = pool.upload(goff);
-        int4 *d_jobs = pool.upload(jobs);
         if (pool.failed) return PGPU_ENOMEM;
-        launch_dp_ml(B, ctx->d_models, d_groups, d_goff, d_jobs, (int)jobs.size(), n_chains, ctx->dp_ml_minb, ctx->dp_ml_pack, st);
+        launch_dp_ml(B, ctx->d_models, d_groups, (int)groups.size(), n_chains, ctx->dp_ml_minb, st);
         ctx->launches++;
         if (ctx->dp_verify && total_cn > 0) {
             // self-check: the per-chain kernel must reproduce every score / traceback / overlap frame
@@ -918,11 +897,14 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
             CK(cudaMemcpyAsync(bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             if (bad[0]) {
-                // describe the first differing chain-node
+                // describe the first differing element (interleaved index, ChainInfo::ioff)
                 const int64_t g = (int64_t)bad[1];
                 int k = 0;
-                while (k + 1 < n_chains && chains[k + 1].coff <= g) k++;
-                const int node = (int)(g - chains[k].coff);
+                for (int q = 0; q < n_chains; q++) {
+                    const int64_t d = g - chains[q].ioff;
+                    if (d >= 0 && d % chains[q].istride == 0 && d / chains[q].istride < chains[q].nn) { k = q; break; }
+                }
+                const int node = (int)((g - chains[k].ioff) / chains[k].istride);
                 double sc[2]; int32_t tb[2]; int8_t ov[2]; int32_t nx = 0, svv = 0; uint8_t cl = 0;
                 cudaMemcpy(&sc[0], B.score + g, 8, cudaMemcpyDeviceToHost); cudaMemcpy(&sc[1], V.score + g, 8, cudaMemcpyDeviceToHost);
                 cudaMemcpy(&tb[0], B.traceb + g, 4, cudaMemcpyDeviceToHost); cudaMemcpy(&tb[1], V.traceb + g, 4, cudaMemcpyDeviceToHost);
@@ -1107,6 +1089,7 @@ static int train_stage(pgpu_ctx *ctx, DevPool &pool, DevBatch &B, const ExtractI
     std::vector<ChainInfo> chain(1);
     memset(&chain[0], 0, sizeof(ChainInfo));
     chain[0].first_pass = 1; chain[0].node_off = X.node_off; chain[0].nn = nn; chain[0].doff = X.doff; chain[0].slen = slen;
+    chain[0].istride = 1;   // one chain: the interleaved arrays are plain arrays (ioff = coff = 0)
     B.chains = pool.upload(chain);
     B.ext_chains = nullptr; B.dcT = nullptr; B.n_models = 1;
     const size_t n1 = std::max(nn, 1);
@@ -1167,7 +1150,7 @@ static int train_stage(pgpu_ctx *ctx, DevPool &pool, DevBatch &B, const ExtractI
             launch_gc_frame(B.gcbits + (X.doff >> 5), slen, V.gp, st);
             launch_gc_bias(B, V, d_bias, B.gcb, st);
             upload_model(T);
-            launch_overlap(B, d_model, 1, nn, ro, 0, st);        // first start of each frame, no scores yet
+            launch_overlap(B, d_model, 1, nn, 1, ro, 0, st);     // first start of each frame, no scores yet
             launch_dp(B, d_model, nullptr, 1, 0, 0, st);          // final == 0: GC frame bias is the only score
             launch_training_path(B, V, d_iv, icap, d_niv, st);
             launch_dicodon(B.digits + X.doff, slen, d_iv, d_niv, icap, d_dc, d_dc + 4096, d_gene_total, st);
@@ -1468,8 +1451,6 @@ int pgpu_create(int device, pgpu_ctx **out) {
     if (const char *a = getenv("PGPU_EXTRACT_ALGO")) ctx->extract_algo = atoi(a);
     if (const char *a = getenv("PGPU_FINAL_ALGO")) ctx->final_algo = atoi(a);
     if (const char *a = getenv("PGPU_CODON_LUT")) ctx->codon_lut = atoi(a) != 0;
-    if (const char *a = getenv("PGPU_CODING_GROUPS")) ctx->coding_groups = atoi(a) != 0;
-    if (const char *a = getenv("PGPU_DP_ML_PACK")) ctx->dp_ml_pack = atoi(a) != 0;
     if (const char *a = getenv("PGPU_LANES")) ctx->lanes = atoi(a);
     if (const char *a = getenv("PGPU_LANE_MIN_BP")) ctx->lane_min_bp = atoll(a);
     // keep freed blocks cached in the stream-ordered pool: sub-batches reuse them without going to the driver
@@ -1847,7 +1828,7 @@ int pgpu_score_connections(pgpu_ctx *ctx, int n, const int32_t *ndx, const int32
     exts[0].nn = n;
     std::vector<ChainInfo> chains(1);
     memset(&chains[0], 0, sizeof(ChainInfo));
-    chains[0].model = model; chains[0].nn = n; chains[0].first_pass = 1;
+    chains[0].model = model; chains[0].nn = n; chains[0].first_pass = 1; chains[0].istride = 1;
     const DevModel &M = ctx->h_models[model];
     std::vector<double> gcb(n, 0.0);
     if (!final)
@@ -1866,11 +1847,8 @@ int pgpu_score_connections(pgpu_ctx *ctx, int n, const int32_t *ndx, const int32
     B.cndx = pool.alloc<int32_t>(n);
     B.dpx = pool.alloc<int4>(n);
     B.ig_node = pool.alloc<int32_t>(n + 1); B.ig_ndx = pool.alloc<int32_t>(n + 1); B.dqx = pool.alloc<int4>(n);
-    if (final && ctx->dp_algo >= 3) {
+    if (final && ctx->dp_algo >= 1) {
         B.dp_svig = pool.alloc<double>(n); B.dp_tbig = pool.alloc<int32_t>(n);
-    } else if (final && ctx->dp_algo >= 1) {
-        B.dp_sv = pool.alloc<double>(n); B.dp_tbn = pool.alloc<int32_t>(n);
-        B.dp_bx = pool.alloc<double>(n / 16 + 16); B.dp_bj = pool.alloc<int32_t>(n / 16 + 16);
     }
     unsigned long long *d_pairs = pool.alloc<unsigned long long>(1, true);
     if (pool.failed) return PGPU_ENOMEM;

@@ -98,10 +98,26 @@ struct ChainInfo {
     int32_t first_pass;  // 1: first model scored after this extraction
     int32_t node_off;    // extraction-node offset
     int32_t nn;
-    int64_t coff;        // chain-node offset
+    int64_t coff;        // chain-node offset, chain-major arrays: node i of this chain at coff + i
     int64_t doff;
     int32_t slen;
     int32_t is_meta;
+    // The arrays the DP touches (cs, opv, star_ptr, score, traceb, ov_mark) are INTERLEAVED over the chains that share
+    // an extraction: node i of this chain sits at ioff + i * istride, istride = number of chains of the extraction,
+    // ioff = first element of the extraction's block + this chain's position among them.  k_dp_ml walks those chains
+    // together, one lane per chain, so a warp access touches istride consecutive elements (one or two cache lines
+    // instead of one line per lane).  A chain that is alone on its extraction has istride 1 and ioff == coff.
+    int64_t ioff;
+    int32_t istride;
+    int32_t lane;        // position among the chains of the extraction
+};
+
+// element i of an interleaved per-chain-node array (see ChainInfo::ioff)
+template <typename T>
+struct Strided {
+    T *p;
+    int64_t s;
+    __host__ __device__ __forceinline__ T &operator[](int64_t i) const { return p[i * s]; }
 };
 
 struct RunOpts {

@@ -81,12 +81,14 @@ __global__ void __launch_bounds__(kDpThreads) k_dp(DevBatch B, const DevModel *_
     const int32_t *__restrict__ cbase = B.cbase + 4 * C.ext;
     const double *__restrict__ cscore = B.cscore + C.coff;
     const double *__restrict__ sscore = B.sscore + C.coff;
-    const double *__restrict__ opv = B.opv + 3 * C.coff;
+    // interleaved arrays (ChainInfo::ioff): node j at j * S (3-vectors: S3 * j + f)
+    const int64_t S = C.istride, S3 = 3 * S;
+    const double *__restrict__ opv = B.opv + 3 * C.ioff;
     const double *__restrict__ gcb = FINAL ? nullptr : B.gcb + C.coff;
-    const int32_t *__restrict__ star_ptr = B.star_ptr + 3 * C.coff;
-    double *score = B.score + C.coff;
-    int32_t *traceb = B.traceb + C.coff;
-    int8_t *ov_mark = B.ov_mark + C.coff;
+    const int32_t *__restrict__ star_ptr = B.star_ptr + 3 * C.ioff;
+    const Strided<double> score{B.score + C.ioff, S};
+    const Strided<int32_t> traceb{B.traceb + C.ioff, S};
+    const Strided<int8_t> ov_mark{B.ov_mark + C.ioff, S};
     const int cb0 = cbase[0], cb1 = cbase[1], cb2 = cbase[2], cb3 = cbase[3];
     const double ig_neg = M.ig_neg;
 
@@ -113,11 +115,11 @@ __global__ void __launch_bounds__(kDpThreads) k_dp(DevBatch B, const DevModel *_
             if (kind == K_RE) {
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
-                    const int s = star_ptr[3 * (int64_t)i + k];
+                    const int s = star_ptr[S3 * (int64_t)i + k];
                     sc.sp[k] = s;
                     if (s != -1) {
                         sc.n3ndx[k] = ndx[s]; sc.n3sv[k] = sv[s];
-                        sc.opv[k] = opv[3 * (int64_t)i + k];
+                        sc.opv[k] = opv[S3 * (int64_t)i + k];
                         if (!FINAL) sc.gcb3[k] = gcb[s];
                     }
                 }
@@ -181,10 +183,10 @@ __global__ void __launch_bounds__(kDpThreads) k_dp(DevBatch B, const DevModel *_
                     if (sv_i >= nj) continue;
                     double sj; int tj; state(j, sj, tj);
                     if (tj == kTbNone) continue;
-                    const int s = star_ptr[3 * (int64_t)j + f2];
+                    const int s = star_ptr[S3 * (int64_t)j + f2];
                     if (s == -1) continue;
                     double term;
-                    if (FINAL) term = opv[3 * (int64_t)j + f2];
+                    if (FINAL) term = opv[S3 * (int64_t)j + f2];
                     else term = ((double)(ndx_i + 2 - ndx[s] + 1)) * gcb[s];
                     cand_take(b2, sj + term, j, nj, -1);
                 }
@@ -340,292 +342,6 @@ __device__ __forceinline__ void wc_merge(WCand &a, double v, int j, int fr) {
     if (v > a.v || (v == a.v && j > a.j)) { a.v = v; a.j = j; a.fr = fr; }
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_fast(DevBatch B, const DevModel *__restrict__ models,
-                                                              const int32_t *__restrict__ order, int n_chains) {
-    __shared__ FastK s_fast[kFastWarps][32];
-    const int lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * kFastWarps + (threadIdx.x >> 5);
-    if (slot >= n_chains) return;
-    const int chain = order ? order[slot] : slot;
-    const ChainInfo C = B.chains[chain];
-    const int nn = C.nn;
-    if (nn == 0) {
-        if (lane == 0) { B.chain_ipath[chain] = -1; B.chain_score[chain] = 0.0; }
-        return;
-    }
-    const DevModel &M = models[C.model];
-    const int32_t *__restrict__ ndx = B.ndx + C.node_off;
-    const int32_t *__restrict__ sv = B.stop_val + C.node_off;
-    const uint8_t *__restrict__ cls = B.cls + C.node_off;
-    const int32_t *__restrict__ win_min = B.win_min + C.node_off;
-    const int32_t *__restrict__ crank = B.crank + 4 * (int64_t)C.node_off;
-    const int32_t *__restrict__ clist = B.clist + C.node_off;
-    const int32_t *__restrict__ cndx = B.cndx + C.node_off;
-    const int4 *__restrict__ dpx = B.dpx + C.node_off;
-    const int32_t *__restrict__ cbase = B.cbase + 4 * C.ext;
-    const double *__restrict__ cscore = B.cscore + C.coff;
-    const double *__restrict__ sscore = B.sscore + C.coff;
-    const double *__restrict__ opv = B.opv + 3 * C.coff;
-    const int32_t *__restrict__ star_ptr = B.star_ptr + 3 * C.coff;
-    // written and re-read by this warp: no __restrict__ / read-only path
-    double *score = B.score + C.coff;
-    int32_t *traceb = B.traceb + C.coff;
-    int8_t *ov_mark = B.ov_mark + C.coff;
-    const int cbFE = cbase[1], cbRS = cbase[2], cbRE = cbase[3];
-    const int nFE = cbRS - cbFE;
-    double *svFE = B.dp_sv + C.coff + cbFE, *svRS = B.dp_sv + C.coff + cbRS;
-    int32_t *tbnFE = B.dp_tbn + C.coff + cbFE;
-    const int64_t boff = (C.coff >> 4) + 2 * (int64_t)chain;
-    double *bxFE = B.dp_bx + boff, *bxRS = bxFE + ((nFE + 15) >> 4);
-    int32_t *bjFE = B.dp_bj + boff, *bjRS = bjFE + ((nFE + 15) >> 4);
-    const int32_t *__restrict__ clFE = clist + cbFE, *__restrict__ clRS = clist + cbRS;
-    const int32_t *__restrict__ cnFE = cndx + cbFE, *__restrict__ cnRS = cndx + cbRS;
-    const double ig_neg = M.ig_neg;
-
-    // class cursors (class-relative positions): cur = finalized entries, lo = first entry inside the
-    // regular 1000-node window, far = first entry NOT more than 180 bp behind the target
-    int curFE = 0, curRS = 0, loFE = 0, loRS = 0, farFE = 0, farRS = 0;
-    // best +start of the open forward ORF of each frame (scalars + selects: no local-memory arrays)
-    double rc_v0 = kNeg, rc_v1 = kNeg, rc_v2 = kNeg;
-    int rc_j0 = -1, rc_j1 = -1, rc_j2 = -1;
-    double best_sc = -1.0;
-    int best_i = -1, best_tb = -1;
-
-    // range maximum of fl(sv + ig_neg) over class positions [a, b): lanes stride over head entries, whole
-    // blocks and tail entries
-    auto range_far = [&](WCand &w, const double *svc, const double *bx, const int32_t *bj, const int32_t *cl, int a, int b) {
-        if (a >= b) return;
-        const int fb = (a + 15) >> 4, lb = b >> 4;
-        int nh, nb, nt, t0;
-        if (fb < lb) { nh = fb * 16 - a; nb = lb - fb; nt = b - lb * 16; t0 = lb * 16; }
-        else { nh = b - a; nb = 0; nt = 0; t0 = b; }
-        for (int t = lane; t < nh + nb + nt; t += 32) {
-            if (t < nh || t >= nh + nb) {
-                const int p = t < nh ? a + t : t0 + (t - nh - nb);
-                const double s = svc[p];
-                if (s != kNeg) wc_merge(w, s + ig_neg, cl[p], -1);
-            } else {
-                const int q = fb + (t - nh);
-                wc_merge(w, bx[q], bj[q], -1);
-            }
-        }
-    };
-
-    FastK *sk = s_fast[threadIdx.x >> 5];
-    for (int i0 = 0; i0 < nn; i0 += 32) {
-      // ---- stage the model/geometry constants of the next 32 targets: one lane per target, so the dependent
-      //      lookups (star_ptr -> ndx/sv, win_min -> crank) of 32 steps overlap instead of serialising ----
-      __syncwarp();
-      if (i0 + lane < nn) {
-          const int i = i0 + lane;
-          FastK k;
-          k.ndx = ndx[i]; k.sv = sv[i]; k.cls = cls[i];
-          k.leave = i > 2 * kMaxNodeDist ? cls_kind(cls[i - 2 * kMaxNodeDist - 1]) : -1;
-          const int kind = cls_kind(k.cls);
-          const int4 dx = dpx[i];
-          k.dx = dx.x; k.dy = dx.y; k.dz = dx.z;
-          k.wmin = win_min[i];
-          k.wlo = (kind == K_FE || kind == K_RS) ? crank[4 * (int64_t)k.wmin + 1] : 0;
-          k.cs = (kind == K_FS || kind == K_RS) ? cscore[i] + sscore[i] : 0.0;
-          k.sp0 = k.sp1 = k.sp2 = -1;
-          k.n3n0 = k.n3n1 = k.n3n2 = k.n3s0 = k.n3s1 = k.n3s2 = 0;
-          k.op0 = k.op1 = k.op2 = 0.0;
-          if (kind == K_RE) {
-              k.sp0 = star_ptr[3 * (int64_t)i]; k.sp1 = star_ptr[3 * (int64_t)i + 1]; k.sp2 = star_ptr[3 * (int64_t)i + 2];
-              if (k.sp0 != -1) { k.n3n0 = ndx[k.sp0]; k.n3s0 = sv[k.sp0]; k.op0 = opv[3 * (int64_t)i]; }
-              if (k.sp1 != -1) { k.n3n1 = ndx[k.sp1]; k.n3s1 = sv[k.sp1]; k.op1 = opv[3 * (int64_t)i + 1]; }
-              if (k.sp2 != -1) { k.n3n2 = ndx[k.sp2]; k.n3s2 = sv[k.sp2]; k.op2 = opv[3 * (int64_t)i + 2]; }
-          }
-          sk[lane] = k;
-      }
-      __syncwarp();
-      const int iend = min(i0 + 32, nn);
-      for (int i = i0; i < iend; i++) {
-        const FastK &K = sk[i - i0];
-        const int ci = K.cls, kind = cls_kind(ci), f2 = cls_frame(ci), ndx_i = K.ndx, sv_i = K.sv;
-        // node i-1001 drops out of the regular window [i-1000, i)
-        loFE += K.leave == K_FE;
-        loRS += K.leave == K_RS;
-        WCand w = {kNeg, -1, -1};
-        const double cs_i = K.cs;
-
-        if (kind == K_FS || kind == K_RE) {
-            // advance the 180-bp boundaries (32 entries per probe)
-            const int thr = ndx_i - 3 * kOperDist;
-            for (;;) {
-                const int p = farFE + lane;
-                const int c = __popc(__ballot_sync(0xffffffffu, p < curFE && cnFE[p] < thr));
-                farFE += c;
-                if (c < 32) break;
-            }
-            for (;;) {
-                const int p = farRS + lane;
-                const int c = __popc(__ballot_sync(0xffffffffu, p < curRS && cnRS[p] < thr));
-                farRS += c;
-                if (c < 32) break;
-            }
-            const int fFE = max(farFE, loFE), fRS = max(farRS, loRS);
-            // far parts: constant term
-            range_far(w, svFE, bxFE, bjFE, clFE, loFE, fFE);
-            range_far(w, svRS, bxRS, bjRS, clRS, loRS, fRS);
-            if (kind == K_FS) {
-                // near +STOPs: distance-dependent intergenic term (_connection.h:116-123, 52-78)
-                for (int p = fFE + lane; p < curFE; p += 32) {
-                    const double s = svFE[p];
-                    const int nj = cnFE[p];
-                    if (s == kNeg || nj + 2 >= ndx_i) continue;
-                    const int dist = ndx_i - nj;
-                    const double term = dist > 3 * kOperDist ? ig_neg : (dist <= kOperDist ? M.igt[dist] : 0.0);
-                    wc_merge(w, s + term, clFE[p], -1);
-                }
-                // near -starts: strand switch (_connection.h:124-129)
-                for (int p = fRS + lane; p < curRS; p += 32) {
-                    const double s = svRS[p];
-                    if (s == kNeg || cnRS[p] >= ndx_i) continue;
-                    wc_merge(w, s + ig_neg, clRS[p], -1);
-                }
-            } else {
-                const int sp0 = K.sp0, sp1 = K.sp1, sp2 = K.sp2;
-                const int n3n0 = K.n3n0, n3n1 = K.n3n1, n3n2 = K.n3n2, n3s0 = K.n3s0, n3s1 = K.n3s1, n3s2 = K.n3s2;
-                const double op0 = K.op0, op1 = K.op1, op2 = K.op2;
-                // +STOP with the triple-overlap search (_connection.h:297-334), for one class position
-                auto eval_fe = [&](int p) {
-                    const double s = svFE[p];
-                    const int nj = cnFE[p];
-                    const int left = nj + 2, right = ndx_i - 2;
-                    if (s == kNeg || left >= right) return;
-                    int maxfr = -1, tj = kTbNone;
-                    double maxval = 0.0;
-                    auto probe = [&](int k, int spk, int n3n, int n3s, double op) {
-                        if (spk == -1) return;
-                        const int ovlp = left - n3s + 3;
-                        if (ovlp <= 0 || ovlp >= kMaxOppOvlp) return;
-                        if (ovlp >= n3n - left) return;
-                        if (tj == kTbNone) tj = ndx[tbnFE[p]];  // ndx of the traceback node (resolved on demand)
-                        if (ovlp >= n3s - tj - 2) return;
-                        if (op > maxval) { maxfr = k; maxval = op; }
-                    };
-                    probe(0, sp0, n3n0, n3s0, op0);
-                    probe(1, sp1, n3n1, n3s1, op1);
-                    probe(2, sp2, n3n2, n3s2, op2);
-                    // maxval == opv of the selected frame (it is only ever assigned from it)
-                    wc_merge(w, s + (maxfr != -1 ? maxval : ig_neg), clFE[p], maxfr);
-                };
-                for (int p = fFE + lane; p < curFE; p += 32) eval_fe(p);
-                // +STOPs far away whose position can trigger the triple overlap: the 200 bp after the stop of
-                // each recorded start (their plain value is already in the range maximum; the overlap value
-                // can only be larger, so evaluating them again is exact)
-                auto special = [&](int spk, int n3s) {
-                    if (spk == -1) return;
-                    // left = ndx+2 in (n3s-3, n3s+197)  <=>  ndx in [n3s-4, n3s+194]
-                    int lo_ = loFE, hi_ = fFE;
-                    while (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if (cnFE[mid] < n3s - 4) lo_ = mid + 1; else hi_ = mid; }
-                    const int a = lo_;
-                    hi_ = fFE;
-                    while (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if (cnFE[mid] < n3s + 195) lo_ = mid + 1; else hi_ = mid; }
-                    for (int p = a + lane; p < lo_; p += 32) eval_fe(p);
-                };
-                special(sp0, n3s0);
-                special(sp1, n3s1);
-                special(sp2, n3s2);
-                // near -starts (_connection.h:335-341)
-                for (int p = fRS + lane; p < curRS; p += 32) {
-                    const double s = svRS[p];
-                    const int nj = cnRS[p];
-                    if (s == kNeg || nj >= ndx_i - 2) continue;
-                    const int dist = ndx_i - nj;
-                    const double term = dist > 3 * kOperDist ? ig_neg : (dist <= kOperDist ? M.igt[dist] : 0.0);
-                    wc_merge(w, s + term, clRS[p], -1);
-                }
-                // -STOPs whose ORF spans this stop: operon (_connection.h:343-356); at most one per frame
-                if (lane < 3) {
-                    const int j = lane == 0 ? K.dx : (lane == 1 ? K.dy : K.dz);
-                    const int spl = lane == 0 ? sp0 : (lane == 1 ? sp1 : sp2);
-                    const double opl = lane == 0 ? op0 : (lane == 1 ? op1 : op2);
-                    if (j >= 0 && j >= i - 2 * kMaxNodeDist && spl != -1) wc_merge(w, score[j] + opl, j, -1);
-                }
-            }
-        } else if (kind == K_FE) {
-            // best +start of this ORF (gene): running maximum of fl(score + cscore + sscore)
-            {
-                const double rv = f2 == 0 ? rc_v0 : (f2 == 1 ? rc_v1 : rc_v2);
-                const int rj = f2 == 0 ? rc_j0 : (f2 == 1 ? rc_j1 : rc_j2);
-                if (lane == 0 && rj >= 0) wc_merge(w, rv, rj, -1);
-            }
-            // +STOPs inside the ORF (operon, _connection.h:178-191)
-            for (int p = max(K.dx, K.wlo) + lane; p < curFE; p += 32) {
-                const double s = svFE[p];
-                if (s == kNeg) continue;
-                const int j = clFE[p];
-                if (star_ptr[3 * (int64_t)j + f2] == -1) continue;
-                wc_merge(w, s + opv[3 * (int64_t)j + f2], j, -1);
-            }
-        } else {  // K_RS
-            // own -STOP (gene, _connection.h:228-237)
-            if (lane == 0 && K.dx >= K.wmin && K.dx >= 0 && K.dx < i) wc_merge(w, score[K.dx] + cs_i, K.dx, -1);
-            // +STOPs overlapping the 3' end (_connection.h:239-256)
-            const double cs_diff = cs_i + ig_neg;
-            for (int p = max(K.dy, K.wlo) + lane; p < min(K.dz, curFE); p += 32) {
-                const double s = svFE[p];
-                if (s == kNeg) continue;
-                const int nj = cnFE[p];
-                if (sv_i - 2 >= nj + 2) continue;
-                const int ovlp = (nj + 2) - (sv_i - 2) + 1;
-                if (ovlp >= kMaxOppOvlp) continue;
-                if ((nj - sv_i) >= (ndx_i - nj + 3)) continue;
-                if ((nj - sv_i) >= (sv_i - 3 - ndx[tbnFE[p]])) continue;
-                wc_merge(w, s + cs_diff, clFE[p], -1);
-            }
-        }
-
-        // ---- warp arg-max: equal values -> larger j ----
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double v = __shfl_xor_sync(0xffffffffu, w.v, off);
-            const int j = __shfl_xor_sync(0xffffffffu, w.j, off);
-            const int fr = __shfl_xor_sync(0xffffffffu, w.fr, off);
-            wc_merge(w, v, j, fr);
-        }
-        double sc_i = 0.0;
-        int tb_i = -1, fr_i = -1;
-        if (w.j >= 0 && w.v >= 0.0) { sc_i = w.v; tb_i = w.j; fr_i = w.fr; }
-        if (lane == 0) {
-            score[i] = sc_i; traceb[i] = tb_i; ov_mark[i] = (int8_t)fr_i;
-            if (kind == K_FE || kind == K_RS) {
-                const bool fe = kind == K_FE;
-                const int p = fe ? curFE : curRS;
-                const double s = tb_i == -1 ? kNeg : sc_i;  // edge artifact rule: nothing leads into it
-                (fe ? svFE : svRS)[p] = s;
-                if (fe) tbnFE[p] = tb_i;  // traceback node; its ndx is looked up only where a rule needs it
-                double *bx = fe ? bxFE : bxRS;
-                int32_t *bj = fe ? bjFE : bjRS;
-                const double x = s + ig_neg;
-                if ((p & 15) == 0 || x >= bx[p >> 4]) { bx[p >> 4] = x; bj[p >> 4] = i; }
-            }
-        }
-        if (kind == K_FE) {
-            curFE++;
-            if (f2 == 0) { rc_v0 = kNeg; rc_j0 = -1; } else if (f2 == 1) { rc_v1 = kNeg; rc_j1 = -1; } else { rc_v2 = kNeg; rc_j2 = -1; }
-        } else if (kind == K_RS) {
-            curRS++;
-        } else if (kind == K_FS) {
-            const double g = sc_i + cs_i;
-            if (f2 == 0) { if (g >= rc_v0) { rc_v0 = g; rc_j0 = i; } }
-            else if (f2 == 1) { if (g >= rc_v1) { rc_v1 = g; rc_j1 = i; } }
-            else { if (g >= rc_v2) { rc_v2 = g; rc_j2 = i; } }
-        }
-        if ((kind == K_FE || kind == K_RS) && sc_i >= best_sc) { best_sc = sc_i; best_i = i; best_tb = tb_i; }
-        __syncwarp();
-      }
-    }
-    if (lane == 0) {
-        const bool ok = best_i >= 0 && best_tb != -1;
-        B.chain_ipath[chain] = ok ? best_i : -1;
-        B.chain_score[chain] = ok ? best_sc : 0.0;
-    }
-}
-
 // --------------------------------------------------------------------------------------------------
 // k_dp_dq: like k_dp_fast, but the constant-term (far intergenic) maximum is a sliding-window maximum kept
 // in a monotone deque (shared memory, per warp), so a DP step costs O(1) instead of a range query:
@@ -694,11 +410,13 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
     const int4 *__restrict__ dqx = B.dqx + C.node_off;
     const double *__restrict__ cscore = B.cscore + C.coff;
     const double *__restrict__ sscore = B.sscore + C.coff;
-    const double *__restrict__ opv = B.opv + 3 * C.coff;
-    const int32_t *__restrict__ star_ptr = B.star_ptr + 3 * C.coff;
-    double *score = B.score + C.coff;       // written and re-read by this warp: no read-only path
-    int32_t *traceb = B.traceb + C.coff;
-    int8_t *ov_mark = B.ov_mark + C.coff;
+    // interleaved arrays (ChainInfo::ioff): node j at j * S (3-vectors: S3 * j + f)
+    const int64_t S = C.istride, S3 = 3 * S;
+    const double *__restrict__ opv = B.opv + 3 * C.ioff;
+    const int32_t *__restrict__ star_ptr = B.star_ptr + 3 * C.ioff;
+    const Strided<double> score{B.score + C.ioff, S};       // written and re-read by this warp: no read-only path
+    const Strided<int32_t> traceb{B.traceb + C.ioff, S};
+    const Strided<int8_t> ov_mark{B.ov_mark + C.ioff, S};
     double *svig = B.dp_svig + C.coff;
     int32_t *tbig = B.dp_tbig + C.coff;
     DqK *sk = s_k[wslot];
@@ -765,10 +483,10 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
           k.op0 = k.op1 = k.op2 = 0.0;
           k.pad = kind == K_RS ? B.win_min[C.node_off + i] : 0;  // node index of the window start
           if (kind == K_RE) {
-              k.sp0 = star_ptr[3 * (int64_t)i]; k.sp1 = star_ptr[3 * (int64_t)i + 1]; k.sp2 = star_ptr[3 * (int64_t)i + 2];
-              if (k.sp0 != -1) { k.n3n0 = ndx[k.sp0]; k.n3s0 = sv[k.sp0]; k.op0 = opv[3 * (int64_t)i]; }
-              if (k.sp1 != -1) { k.n3n1 = ndx[k.sp1]; k.n3s1 = sv[k.sp1]; k.op1 = opv[3 * (int64_t)i + 1]; }
-              if (k.sp2 != -1) { k.n3n2 = ndx[k.sp2]; k.n3s2 = sv[k.sp2]; k.op2 = opv[3 * (int64_t)i + 2]; }
+              k.sp0 = star_ptr[S3 * (int64_t)i]; k.sp1 = star_ptr[S3 * (int64_t)i + 1]; k.sp2 = star_ptr[S3 * (int64_t)i + 2];
+              if (k.sp0 != -1) { k.n3n0 = ndx[k.sp0]; k.n3s0 = sv[k.sp0]; k.op0 = opv[S3 * (int64_t)i]; }
+              if (k.sp1 != -1) { k.n3n1 = ndx[k.sp1]; k.n3s1 = sv[k.sp1]; k.op1 = opv[S3 * (int64_t)i + 1]; }
+              if (k.sp2 != -1) { k.n3n2 = ndx[k.sp2]; k.n3s2 = sv[k.sp2]; k.op2 = opv[S3 * (int64_t)i + 2]; }
           }
           sk[lane] = k;
       }
@@ -913,8 +631,8 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
                 const double s = svig[q];
                 if (s == kNeg) continue;
                 const int j = nd & 0x7fffffff;
-                if (star_ptr[3 * (int64_t)j + f2] == -1) continue;
-                cand(s + opv[3 * (int64_t)j + f2], j, -1);
+                if (star_ptr[S3 * (int64_t)j + f2] == -1) continue;
+                cand(s + opv[S3 * (int64_t)j + f2], j, -1);
             }
         }
 
@@ -984,26 +702,18 @@ struct MlK {  // geometric constants of a target, staged 32 targets at a time (m
 
 __device__ double g_ml_no_source = -DBL_MAX;  // what idle lanes read instead of a source value
 
-template <int MINB, bool PACK>   // PACK = false: one group of up to 32 chains per warp (W is the constant 32)
+template <int MINB>
 __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const DevModel *__restrict__ models,
-                                                               const int4 *__restrict__ groups,
-                                                               const int64_t *__restrict__ group_off,
-                                                               const int4 *__restrict__ jobs, int n_jobs) {
+                                                               const int4 *__restrict__ groups, int n_groups) {
     __shared__ MlK s_k[kMlWarps][32];
     __shared__ double s_rcv[3][32 * kMlWarps];  // per frame: best +start of the open forward ORF (value, node)
     __shared__ int32_t s_rcj[3][32 * kMlWarps];
-    const int wlane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
-    const int jslot = blockIdx.x * kMlWarps + wslot;
-    if (jslot >= n_jobs) return;
-    // A job packs 32 / W extraction groups of at most W chains each into one warp (W = 4, 8, 16 or 32 lanes per group):
-    // everything below is written per group -- `lane` is the lane within the group, the "uniform" cursors are uniform
-    // within a group, and the groups of a warp simply diverge; the few collective operations take the group's mask.
-    const int4 J = jobs[jslot];   // x: first group, y: W, z: groups in this job
-    const int W = PACK ? J.y : 32, gsub = PACK ? wlane / W : 0, lane = PACK ? wlane % W : wlane;
-    if (gsub >= J.z) return;
-    const unsigned gmask = (!PACK || W == 32) ? 0xffffffffu : (((1u << W) - 1u) << (gsub * W));
-    const int slot = J.x + gsub;
-    const int4 G = groups[slot];  // x: first entry in ext_chains, y: number of chains (<= W), z: extraction
+    const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
+    const int slot = blockIdx.x * kMlWarps + wslot;
+    if (slot >= n_groups) return;
+    constexpr int W = 32;
+    constexpr unsigned gmask = 0xffffffffu;
+    const int4 G = groups[slot];  // x: first entry in ext_chains, y: number of chains (<= 32), z: extraction; longest first
     const int L = G.y;
     const bool act = lane < L;
     const int ll = act ? lane : 0;  // idle lanes shadow lane 0 (loads stay in bounds, stores are suppressed)
@@ -1022,26 +732,27 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
     const int32_t *__restrict__ fe_node = B.clist + C.node_off + fe0;  // +STOPs in class order: node,
     const int32_t *__restrict__ fe_ndx = B.cndx + C.node_off + fe0;    // ndx,
     const int32_t *__restrict__ fe_q = B.feq + C.node_off + fe0;       // merged-stream position
-    const double *__restrict__ cscore = B.cscore + C.coff;
-    const double *__restrict__ sscore = B.sscore + C.coff;
-    const double *__restrict__ csum = B.cs ? B.cs + C.coff : nullptr;  // cscore + sscore, written by the scoring pass
-    const double *__restrict__ opv = B.opv + 3 * C.coff;
-    const int32_t *__restrict__ star_ptr = B.star_ptr + 3 * C.coff;
-    double *score = B.score + C.coff;
-    int32_t *traceb = B.traceb + C.coff;
-    int8_t *ov_mark = B.ov_mark + C.coff;
-    // interleaved DP-private arrays: element (q, lane) at goff + q * L + lane
-    const int64_t goff = group_off[slot] + ll;
-    double *svig = B.dp_svig + goff;
-    int32_t *tbig = B.dp_tbig + goff;
-    double *fmv = B.dp_fmv + goff;
-    int32_t *fmj = B.dp_fmj + goff;
-    MlK *sk = s_k[wslot] + gsub * W;   // W staged targets per group
+    // Every per-chain array of this kernel is interleaved over the chains of the extraction (ChainInfo::ioff): element
+    // (x, lane) at ioff + x * S, where x is a node index (cs, opv, star_ptr, score, traceb, ov_mark) or a merged-stream
+    // position (the DP-private source values / traceback nodes / suffix maxima).  A warp access touches S consecutive
+    // elements.
+    const int64_t S = C.istride, S3 = 3 * S;
+    const double *__restrict__ csum = B.cs + C.ioff;  // cscore + sscore, written by the scoring pass
+    const double *__restrict__ opv = B.opv + 3 * C.ioff;
+    const int32_t *__restrict__ star_ptr = B.star_ptr + 3 * C.ioff;
+    const Strided<double> score{B.score + C.ioff, S};
+    const Strided<int32_t> traceb{B.traceb + C.ioff, S};
+    const Strided<int8_t> ov_mark{B.ov_mark + C.ioff, S};
+    double *svig = B.dp_svig + C.ioff;
+    int32_t *tbig = B.dp_tbig + C.ioff;
+    double *fmv = B.dp_fmv + C.ioff;
+    int32_t *fmj = B.dp_fmj + C.ioff;
+    MlK *sk = s_k[wslot];
     const double ig_neg = M.ig_neg;
     const double *__restrict__ igt = M.igt;
     // source value of a merged-stream entry for this lane; idle lanes read "no source" (stride 0)
     const double *svr = act ? svig : &g_ml_no_source;
-    const int svs = act ? L : 0;
+    const int64_t svs = act ? S : 0;
     auto SV = [&](int q) -> double { return svr[q * svs]; };
 
     // merged-stream cursors (uniform): cur = finalized entries, lo = first entry inside [i-1000, i), far = first
@@ -1074,14 +785,6 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
           }
           sk[lane] = k;
       }
-      if (act && i0 + 32 < nn && (i0 & 31) == 0) {  // the chain-major score lines of the next 32 targets
-          const double *pc = (csum ? csum : cscore) + i0 + 32, *ps = sscore + i0 + 32;
-#pragma unroll
-          for (int t = 0; t < 3; t++) {
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + min(16 * t, 31)));
-              if (!csum) asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + min(16 * t, 31)));
-          }
-      }
       __syncwarp(gmask);
       const int iend = min(i0 + W, nn);
       for (int i = i0; i < iend; i++) {
@@ -1089,9 +792,9 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
         const int ci = K.cls, kind = cls_kind(ci), f2 = cls_frame(ci), ndx_i = K.ndx, sv_i = K.sv;
         lo += (K.leave == K_FE) | (K.leave == K_RS);
         lo_fe += K.leave == K_FE;
-        // cscore + sscore of a start target (chain-major, sequential per lane: L1 lines are reused 16 times)
+        // cscore + sscore of a start target
         double cs_i = 0.0;
-        if (kind == K_FS || kind == K_RS) cs_i = csum ? csum[i] : cscore[i] + sscore[i];
+        if (kind == K_FS || kind == K_RS) cs_i = csum[i * S];
         double wv = kNeg;
         int wkey = -1;  // (node << 2) | (overlap frame + 1)
         // larger value, then larger node; the same node seen twice (far maximum + overlap re-evaluation) keeps the
@@ -1116,7 +819,7 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
                 if (ovlp >= kMaxOppOvlp) continue;
                 if ((nj - sv_i) >= (ndx_i - nj + 3)) continue;
                 if (s == kNeg) continue;
-                if ((nj - sv_i) >= (sv_i - 3 - ndx[tbig[q * L]])) continue;
+                if ((nj - sv_i) >= (sv_i - 3 - ndx[tbig[q * S]])) continue;
                 cand(s + cs_diff, j, -1);
             }
         } else if (kind == K_FE) {
@@ -1129,8 +832,8 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
             for (int r = K.a; r < cur_fe; r++) {
                 const int q = fe_q[r], j = fe_node[r];
                 const double s = SV(q);
-                const int spj = star_ptr[3 * (int64_t)j + f2];
-                const double opj = opv[3 * (int64_t)j + f2];
+                const int spj = star_ptr[S3 * (int64_t)j + f2];
+                const double opj = opv[S3 * (int64_t)j + f2];
                 if (s != kNeg && spj != -1) cand(s + opj, j, -1);
             }
         } else {  // K_FS, K_RE: intergenic sources
@@ -1140,10 +843,10 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
             int sa0 = 0, sa1 = 0, sa2 = 0, sb0 = 0, sb1 = 0, sb2 = 0;
             double op0 = 0.0, op1 = 0.0, op2 = 0.0;
             if (kind == K_RE) {
-                sp0 = star_ptr[3 * (int64_t)i]; sp1 = star_ptr[3 * (int64_t)i + 1]; sp2 = star_ptr[3 * (int64_t)i + 2];
-                if (sp0 != -1) { n3n0 = ndx[sp0]; n3s0 = sv[sp0]; op0 = opv[3 * (int64_t)i]; const int4 d = dpx[sp0]; sa0 = d.y; sb0 = d.z; }
-                if (sp1 != -1) { n3n1 = ndx[sp1]; n3s1 = sv[sp1]; op1 = opv[3 * (int64_t)i + 1]; const int4 d = dpx[sp1]; sa1 = d.y; sb1 = d.z; }
-                if (sp2 != -1) { n3n2 = ndx[sp2]; n3s2 = sv[sp2]; op2 = opv[3 * (int64_t)i + 2]; const int4 d = dpx[sp2]; sa2 = d.y; sb2 = d.z; }
+                sp0 = star_ptr[S3 * (int64_t)i]; sp1 = star_ptr[S3 * (int64_t)i + 1]; sp2 = star_ptr[S3 * (int64_t)i + 2];
+                if (sp0 != -1) { n3n0 = ndx[sp0]; n3s0 = sv[sp0]; op0 = opv[S3 * (int64_t)i]; const int4 d = dpx[sp0]; sa0 = d.y; sb0 = d.z; }
+                if (sp1 != -1) { n3n1 = ndx[sp1]; n3s1 = sv[sp1]; op1 = opv[S3 * (int64_t)i + 1]; const int4 d = dpx[sp1]; sa1 = d.y; sb1 = d.z; }
+                if (sp2 != -1) { n3n2 = ndx[sp2]; n3s2 = sv[sp2]; op2 = opv[S3 * (int64_t)i + 2]; const int4 d = dpx[sp2]; sa2 = d.y; sb2 = d.z; }
             }
             // ---- entries that fall more than 180 bp behind move onto the back stack ----
             const int thr = ndx_i - 3 * kOperDist;
@@ -1171,14 +874,14 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
                         const double x = s + ig_neg;
                         if (x > fv) { fv = x; fj = ig_node[q] & 0x7fffffff; }  // earlier entry loses a tie
                     }
-                    if (act) { fmv[q * L] = fv; fmj[q * L] = fj; }
+                    if (act) { fmv[q * S] = fv; fmj[q * S] = fj; }
                 }
                 split = far;
                 bk_v = kNeg; bk_j = -1;
             }
             if (lo < split && act) {
-                const int fj = fmj[lo * L];
-                const double fv = fmv[lo * L];
+                const int fj = fmj[lo * S];
+                const double fv = fmv[lo * S];
                 if (fj >= 0) cand(fv, fj, -1);
             }
             if (bk_j >= 0) cand(bk_v, bk_j, -1);
@@ -1217,7 +920,7 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
                         const int ovlp = left - n3s + 3;
                         if (ovlp <= 0 || ovlp >= kMaxOppOvlp) return;
                         if (ovlp >= n3n - left) return;
-                        if (tj == kTbNone) tj = ndx[tbig[q * L]];
+                        if (tj == kTbNone) tj = ndx[tbig[q * S]];
                         if (ovlp >= n3s - tj - 2) return;
                         if (op > maxval) { maxfr = k; maxval = op; }
                     };
@@ -1282,8 +985,8 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
         if (act) {
             score[i] = sc_i; traceb[i] = tb_i; ov_mark[i] = (int8_t)fr_i;
             if (kind == K_FE || kind == K_RS) {
-                svig[cur * L] = tb_i == -1 ? kNeg : sc_i;  // edge-artifact rule: nothing leads into it
-                tbig[cur * L] = tb_i;
+                svig[cur * S] = tb_i == -1 ? kNeg : sc_i;  // edge-artifact rule: nothing leads into it
+                tbig[cur * S] = tb_i;
             }
         }
         if (kind == K_FE) {
@@ -1307,7 +1010,7 @@ __global__ void __launch_bounds__(128) k_chain_best(DevBatch B, int n_chains) {
     if (chain >= n_chains) return;
     const ChainInfo C = B.chains[chain];
     const uint8_t *__restrict__ cls = B.cls + C.node_off;
-    const double *__restrict__ score = B.score + C.coff;
+    const Strided<double> score{B.score + C.ioff, C.istride};
     double bv = -1.0;
     int bi = -1;
     for (int i = lane; i < C.nn; i += 32) {
@@ -1320,7 +1023,7 @@ __global__ void __launch_bounds__(128) k_chain_best(DevBatch B, int n_chains) {
     if (bi < 0) bv = -DBL_MAX;
     warp_argmax(bv, bi, fr);
     if (lane == 0) {
-        const bool ok = bi >= 0 && (B.traceb + C.coff)[bi] != -1;
+        const bool ok = bi >= 0 && B.traceb[C.ioff + (int64_t)bi * C.istride] != -1;
         B.chain_ipath[chain] = ok ? bi : -1;
         B.chain_score[chain] = ok ? bv : 0.0;
     }
@@ -1332,10 +1035,14 @@ __global__ void __launch_bounds__(128) k_chain_best(DevBatch B, int n_chains) {
 struct NodeRef {
     const int32_t *ndx, *sv;
     const uint8_t *cls;
-    double *cscore, *sscore, *rscore, *uscore, *tscore;
-    int32_t *traceb, *tracef, *star_ptr;
-    int8_t *ov_mark;
+    double *cscore, *sscore, *rscore, *uscore, *tscore;   // chain-major (ChainInfo::coff)
+    Strided<int32_t> traceb;                              // interleaved (ChainInfo::ioff)
+    int32_t *tracef;
+    int32_t *star_ptr;                                    // interleaved 3-vectors: node j, frame f at s3 * j + f
+    int64_t s3;
+    Strided<int8_t> ov_mark;
     uint8_t *elim;
+    __device__ __forceinline__ int32_t sp(int node, int f) const { return star_ptr[s3 * node + f]; }
 };
 
 __device__ __forceinline__ double igm_nodes(const NodeRef &N, int a, int b, const DevModel &M) {
@@ -1398,8 +1105,9 @@ __global__ void __launch_bounds__(64) k_trace(DevBatch B, const DevModel *__rest
     N.ndx = B.ndx + C.node_off; N.sv = B.stop_val + C.node_off; N.cls = B.cls + C.node_off;
     N.cscore = B.cscore + C.coff; N.sscore = B.sscore + C.coff; N.rscore = B.rscore + C.coff;
     N.uscore = B.uscore + C.coff; N.tscore = B.tscore + C.coff;
-    N.traceb = B.traceb + C.coff; N.tracef = A.tracef + C.coff; N.star_ptr = B.star_ptr + 3 * C.coff;
-    N.ov_mark = B.ov_mark + C.coff; N.elim = A.elim + C.coff;
+    N.traceb = Strided<int32_t>{B.traceb + C.ioff, C.istride}; N.tracef = A.tracef + C.coff;
+    N.star_ptr = B.star_ptr + 3 * C.ioff; N.s3 = 3 * (int64_t)C.istride;
+    N.ov_mark = Strided<int8_t>{B.ov_mark + C.ioff, C.istride}; N.elim = A.elim + C.coff;
     if (nn == 0) { A.summary[c] = S; return; }
 
     // the reference untangles overlaps from the arg-max node even when that node has no traceback
@@ -1410,7 +1118,7 @@ __global__ void __launch_bounds__(64) k_trace(DevBatch B, const DevModel *__rest
             const int nxt = N.traceb[path];
             if (cls_kind(N.cls[path]) == K_RE && cls_kind(N.cls[nxt]) == K_FE && N.ov_mark[path] != -1 &&
                 N.ndx[path] > N.ndx[nxt]) {
-                const int tmp = N.star_ptr[3 * path + N.ov_mark[path]];
+                const int tmp = N.sp(path, N.ov_mark[path]);
                 int i = tmp;
                 while (N.ndx[i] != N.sv[tmp]) i--;
                 N.traceb[path] = tmp;
@@ -1430,11 +1138,11 @@ __global__ void __launch_bounds__(64) k_trace(DevBatch B, const DevModel *__rest
                 N.traceb[i] = nxt;
             }
             if (kp == K_FE && kn == K_FE) {
-                N.traceb[path] = N.star_ptr[3 * nxt + N.ndx[path] % 3];
+                N.traceb[path] = N.sp(nxt, N.ndx[path] % 3);
                 N.traceb[N.traceb[path]] = nxt;
             }
             if (kp == K_RE && kn == K_RE) {
-                N.traceb[path] = N.star_ptr[3 * path + N.ndx[nxt] % 3];
+                N.traceb[path] = N.sp(path, N.ndx[nxt] % 3);
                 N.traceb[N.traceb[path]] = nxt;
             }
         }
@@ -1508,7 +1216,8 @@ __global__ void __launch_bounds__(128) k_tweak(DevBatch B, const DevModel *__res
     N.ndx = B.ndx + C.node_off; N.sv = B.stop_val + C.node_off; N.cls = B.cls + C.node_off;
     N.cscore = B.cscore + C.coff; N.sscore = B.sscore + C.coff; N.rscore = B.rscore + C.coff;
     N.uscore = B.uscore + C.coff; N.tscore = B.tscore + C.coff;
-    N.traceb = nullptr; N.tracef = nullptr; N.star_ptr = nullptr; N.ov_mark = nullptr; N.elim = nullptr;
+    N.traceb = Strided<int32_t>{nullptr, 1}; N.tracef = nullptr; N.star_ptr = nullptr; N.s3 = 3;
+    N.ov_mark = Strided<int8_t>{nullptr, 1}; N.elim = nullptr;
     const pgpu_gene *og = orig + A.gene_off[c];   // untouched genes (Genes._extract)
     pgpu_gene *genes = A.genes + A.gene_off[c];    // output (pass 0: reverse genes, pass 1: forward genes)
     auto is_edge = [&](int x) { return (N.cls[x] & (CLS_EDGE | CLS_CONV)) != 0; };
@@ -1619,15 +1328,16 @@ __device__ __forceinline__ void pack_node(const DevBatch &B, const ChainInfo &C,
     const MotifOut m = mot ? mot[g] : MotifOut{};
     n.mot_score = m.score; n.mot_ndx = m.ndx; n.mot_len = m.len; n.mot_spacer = m.spacer; n.mot_spacendx = m.spacendx;
     n.cscore = B.cscore[g]; n.uscore = B.uscore[g]; n.tscore = B.tscore[g]; n.rscore = B.rscore[g]; n.sscore = B.sscore[g];
+    const int64_t gi = C.ioff + (int64_t)i * C.istride;   // interleaved arrays (ChainInfo::ioff)
     if (dp_state == 1) {
-        n.score = B.score[g]; n.traceb = B.traceb[g]; n.tracef = tracef[g]; n.ov_mark = B.ov_mark[g];
+        n.score = B.score[gi]; n.traceb = B.traceb[gi]; n.tracef = tracef[g]; n.ov_mark = B.ov_mark[gi];
         n.elim = elim[g];
-        n.star_ptr[0] = B.star_ptr[3 * g]; n.star_ptr[1] = B.star_ptr[3 * g + 1]; n.star_ptr[2] = B.star_ptr[3 * g + 2];
+        n.star_ptr[0] = B.star_ptr[3 * gi]; n.star_ptr[1] = B.star_ptr[3 * gi + 1]; n.star_ptr[2] = B.star_ptr[3 * gi + 2];
     } else {
         n.score = 0.0; n.traceb = -1; n.tracef = -1; n.ov_mark = -1; n.elim = 0;
         n.star_ptr[0] = n.star_ptr[1] = n.star_ptr[2] = 0;
         if (dp_state == 2) {  // scored + record_overlapping_starts, no DP (pgpu_score_nodes)
-            n.star_ptr[0] = B.star_ptr[3 * g]; n.star_ptr[1] = B.star_ptr[3 * g + 1]; n.star_ptr[2] = B.star_ptr[3 * g + 2];
+            n.star_ptr[0] = B.star_ptr[3 * gi]; n.star_ptr[1] = B.star_ptr[3 * gi + 1]; n.star_ptr[2] = B.star_ptr[3 * gi + 2];
         }
     }
     const uint64_t *src = reinterpret_cast<const uint64_t *>(&n);
@@ -1679,6 +1389,7 @@ __global__ void k_build_final_chains(DevBatch B, int n_contigs, const int32_t *_
     if (w >= 0) { F = B.chains[w]; F.first_pass = 1; }
     else { F = ChainInfo{}; F.contig = c; F.nn = 0; }
     F.coff = fin_coff[c];
+    F.ioff = F.coff; F.istride = 1; F.lane = 0;   // the final pass scores one chain per contig: nothing to interleave
     fin[c] = F;
 }
 
@@ -1728,33 +1439,23 @@ __global__ void k_skippable(int n, const int8_t *__restrict__ strand, const uint
 void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, int n_chains, int final, int algo,
                cudaStream_t st) {
     if (n_chains == 0) return;
-    // algo 1 (default): k_dp_fast, final scoring only; algo 0: the all-pairs kernel (also the training DP)
-    if (final && algo >= 3 && B.dp_svig) {
+    // final scoring: k_dp_dq (one warp per chain) unless algo 0 asks for the all-pairs kernel, which is also the training DP
+    if (final && algo >= 1 && B.dp_svig) {
         const int nb = (n_chains + kFastWarps - 1) / kFastWarps;
         if (algo == 4) k_dp_dq<4><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);
         else k_dp_dq<8><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);
         k_chain_best<<<(n_chains * 32 + 127) / 128, 128, 0, st>>>(B, n_chains);
-    } else if (final && algo >= 1 && B.dp_sv) {
-        const int nb = (n_chains + kFastWarps - 1) / kFastWarps;
-        if (algo == 2) k_dp_fast<4><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);   // up to 128 regs
-        else k_dp_fast<8><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);             // 64 regs, 32 warps/SM
     }
     else if (final) k_dp<1><<<n_chains, kDpThreads, 0, st>>>(B, models, order, n_chains);
     else k_dp<0><<<n_chains, kDpThreads, 0, st>>>(B, models, order, n_chains);
 }
-void launch_dp_ml(const DevBatch &B, const DevModel *models, const int4 *groups, const int64_t *group_off, const int4 *jobs,
-                  int n_jobs, int n_chains, int minb, bool pack, cudaStream_t st) {
-    if (n_jobs == 0 || n_chains == 0) return;
-    const int nb = (n_jobs + kMlWarps - 1) / kMlWarps;
-    if (pack) {
-        if (minb == 8) k_dp_ml<8, true><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, jobs, n_jobs);
-        else if (minb == 6) k_dp_ml<6, true><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, jobs, n_jobs);
-        else k_dp_ml<5, true><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, jobs, n_jobs);
-    } else {
-        if (minb == 8) k_dp_ml<8, false><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, jobs, n_jobs);
-        else if (minb == 6) k_dp_ml<6, false><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, jobs, n_jobs);
-        else k_dp_ml<5, false><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, group_off, jobs, n_jobs);
-    }
+void launch_dp_ml(const DevBatch &B, const DevModel *models, const int4 *groups, int n_groups, int n_chains, int minb,
+                  cudaStream_t st) {
+    if (n_groups == 0 || n_chains == 0) return;
+    const int nb = (n_groups + kMlWarps - 1) / kMlWarps;
+    if (minb == 8) k_dp_ml<8><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, n_groups);
+    else if (minb == 5) k_dp_ml<5><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, n_groups);
+    else k_dp_ml<6><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, n_groups);
     k_chain_best<<<(n_chains * 32 + 127) / 128, 128, 0, st>>>(B, n_chains);
 }
 // PGPU_DP_VERIFY: element-wise comparison of two DP results (score, traceback, overlap frame)

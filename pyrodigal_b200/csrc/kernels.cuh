@@ -29,15 +29,15 @@ void launch_coding(const DevBatch &B, const DevModel *models, int n_chains, int6
                    cudaStream_t st);
 void launch_start_score(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o, void *mot_out,
                         cudaStream_t st);
-void launch_overlap(const DevBatch &B, const DevModel *models, int n_chains, int64_t total_chain_nodes, RunOpts o,
+void launch_overlap(const DevBatch &B, const DevModel *models, int n_chains, int64_t total_chain_nodes, int n_ext, RunOpts o,
                     int flag, cudaStream_t st);
 void launch_opv(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, cudaStream_t st);
 void launch_dp_index(const DevBatch &B, int n_ext, int total_nodes, cudaStream_t st);
 void launch_pairs(const DevBatch &B, int n_ext, int total_nodes, unsigned long long *ext_pairs, cudaStream_t st);
 
 // dp_kernels.cu
-void launch_dp_ml(const DevBatch &B, const DevModel *models, const int4 *groups, const int64_t *group_off, const int4 *jobs,
-                  int n_jobs, int n_chains, int minb, bool pack, cudaStream_t st);
+void launch_dp_ml(const DevBatch &B, const DevModel *models, const int4 *groups, int n_groups, int n_chains, int minb,
+                  cudaStream_t st);
 void launch_dp_compare(const double *sa, const double *sb, const int32_t *ta, const int32_t *tb, const int8_t *oa,
                        const int8_t *ob, int64_t n, unsigned long long *bad, cudaStream_t st);
 void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, int n_chains, int final, int algo,

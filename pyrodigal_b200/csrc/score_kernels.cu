@@ -482,7 +482,7 @@ __device__ __forceinline__ void start_score_node(const DevBatch &B, const DevMod
     if (cls_is_stop(c)) {
         // STOP nodes keep the reset state (node.c:176-197)
         B.cscore[g] = 0.0; B.sscore[g] = 0.0; B.rscore[g] = 0.0; B.uscore[g] = 0.0; B.tscore[g] = 0.0;
-        if (B.cs) B.cs[g] = 0.0;
+        if (B.cs) B.cs[C.ioff + (int64_t)i * C.istride] = 0.0;
         B.rbs[2 * g] = 0; B.rbs[2 * g + 1] = 0;
         if (mot_out) { MotifOut m = {}; mot_out[g] = m; }
         return;
@@ -668,7 +668,8 @@ __device__ __forceinline__ void start_score_node(const DevBatch &B, const DevMod
         sscore -= st_wt;
     }
     B.cscore[g] = cscore; B.sscore[g] = sscore; B.rscore[g] = rscore; B.uscore[g] = uscore; B.tscore[g] = tscore;
-    if (B.cs) B.cs[g] = cscore + sscore;  // what record_overlapping_starts and the DP read of a start
+    // what record_overlapping_starts and the DP read of a start: one value, interleaved over the chains of the extraction
+    if (B.cs) B.cs[C.ioff + (int64_t)i * C.istride] = cscore + sscore;
     B.rbs[2 * g] = (uint8_t)rbs0; B.rbs[2 * g + 1] = (uint8_t)rbs1;
     if (mot_out) mot_out[g] = mot;
 }
@@ -765,41 +766,29 @@ __device__ __forceinline__ double igm_same(int ndx1, int strand1, int ndx2, int 
 }
 
 // cscore + sscore of a start: from the combined array when the scoring pass wrote one
-__device__ __forceinline__ double cs_of(int j, const double *__restrict__ cs, const double *__restrict__ cscore,
+__device__ __forceinline__ double cs_of(int j, const double *__restrict__ cs, int64_t S, const double *__restrict__ cscore,
                                         const double *__restrict__ sscore) {
-    return cs ? cs[j] : cscore[j] + sscore[j];
+    return cs ? cs[j * S] : cscore[j] + sscore[j];
 }
 
 // cs[n3] + intergenic_mod for the start n3 recorded in star_ptr of STOP node z:
 // forward STOP: _connection.h:189 (n1 = z, n3);  reverse STOP: _connection.h:320,329,354 (n3, n2 = z)
 __device__ __forceinline__ double operon_value(int cz, int z, int s, const uint8_t *__restrict__ cls,
-                                               const int32_t *__restrict__ ndx, const double *__restrict__ cs,
+                                               const int32_t *__restrict__ ndx, const double *__restrict__ cs, int64_t S,
                                                const double *__restrict__ cscore, const double *__restrict__ sscore,
                                                const double *__restrict__ rscore, const double *__restrict__ uscore,
                                                const DevModel &M) {
     const int cs_ = cls[s];
-    const double base = cs_of(s, cs, cscore, sscore);
+    const double base = cs_of(s, cs, S, cscore, sscore);
     if (((cz ^ cs_) & CLS_REV) != 0) return base + M.ig_neg;
     return (cz & CLS_REV) ? base + igm_same(ndx[s], -1, ndx[z], s, rscore, uscore, M)
                           : base + igm_same(ndx[z], 1, ndx[s], s, rscore, uscore, M);
 }
 
-__global__ void __launch_bounds__(128, 12) k_overlap(DevBatch B, const DevModel *__restrict__ models, int n_chains,
-                                                  int64_t total, RunOpts o, int flag) {
-    __shared__ int s_first;
-    // half-size slot space, as in k_coding_orf: chain k owns the slots from (coff + 1) / 2 on and its STOP nodes (at
-    // most nn / 2) take the first of them; star_ptr was preset to -1 for every node
-    const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int k = chain_hint(B, n_chains, min(2 * h, total - 1), total, &s_first, 2 * (int64_t)blockIdx.x * blockDim.x);
-    if (h > (total + 1) / 2) return;
-    while (k + 1 < n_chains && ((B.chains[k + 1].coff + 1) >> 1) <= h) k++;
-    const ChainInfo C = B.chains[k];
-    const int t = (int)(h - ((C.coff + 1) >> 1)), nn = C.nn;
-    if (t >= nn) return;
-    const int32_t *__restrict__ cbase = B.cbase + 4 * C.ext;
-    const int n_fe = cbase[2] - cbase[1], n_re = nn - cbase[3];
-    if (t >= n_fe + n_re) return;
-    const int i = (B.clist + C.node_off)[t < n_fe ? cbase[1] + t : cbase[3] + (t - n_fe)];
+// STOP node i of chain C: star_ptr[3] and the operon values (interleaved arrays, ChainInfo::ioff)
+__device__ __forceinline__ void overlap_stop_node(const DevBatch &B, const DevModel &M, const ChainInfo &C, int i, RunOpts o,
+                                                  int flag) {
+    const int nn = C.nn;
     const uint8_t *__restrict__ cls = B.cls + C.node_off;
     const int32_t *__restrict__ ndx = B.ndx + C.node_off;
     const int32_t *__restrict__ sv = B.stop_val + C.node_off;
@@ -807,8 +796,8 @@ __global__ void __launch_bounds__(128, 12) k_overlap(DevBatch B, const DevModel 
     const double *__restrict__ sscore = B.sscore + C.coff;
     const double *__restrict__ rscore = B.rscore + C.coff;
     const double *__restrict__ uscore = B.uscore + C.coff;
-    const double *__restrict__ cs = B.cs ? B.cs + C.coff : nullptr;
-    const DevModel &M = models[C.model];
+    const int64_t S = C.istride;
+    const double *__restrict__ cs = B.cs ? B.cs + C.ioff : nullptr;
     int sp[3] = {-1, -1, -1};
     const int c = cls[i];
     if (cls_is_stop(c) && !(c & CLS_EDGE)) {
@@ -825,7 +814,7 @@ __global__ void __launch_bounds__(128, 12) k_overlap(DevBatch B, const DevModel 
                 if (flag == 0) {
                     if (sp[f] == -1) sp[f] = j;
                 } else {
-                    const double sc = cs_of(j, cs, cscore, sscore) + igm_same(my, 1, ndx[j], j, rscore, uscore, M);
+                    const double sc = cs_of(j, cs, S, cscore, sscore) + igm_same(my, 1, ndx[j], j, rscore, uscore, M);
                     if (sc > max_sc) { sp[f] = j; max_sc = sc; }
                 }
             }
@@ -840,17 +829,63 @@ __global__ void __launch_bounds__(128, 12) k_overlap(DevBatch B, const DevModel 
                 if (flag == 0) {
                     if (sp[f] == -1) sp[f] = j;
                 } else {
-                    const double sc = cs_of(j, cs, cscore, sscore) + igm_same(ndx[j], -1, my, j, rscore, uscore, M);
+                    const double sc = cs_of(j, cs, S, cscore, sscore) + igm_same(ndx[j], -1, my, j, rscore, uscore, M);
                     if (sc > max_sc) { sp[f] = j; max_sc = sc; }
                 }
             }
         }
     }
-    const int64_t gi = C.coff + i;
+    const int64_t gi = C.ioff + (int64_t)i * S;
 #pragma unroll
     for (int f = 0; f < 3; f++) {
         B.star_ptr[3 * gi + f] = sp[f];
-        B.opv[3 * gi + f] = sp[f] == -1 ? 0.0 : operon_value(c, i, sp[f], cls, ndx, cs, cscore, sscore, rscore, uscore, M);
+        B.opv[3 * gi + f] = sp[f] == -1 ? 0.0 : operon_value(c, i, sp[f], cls, ndx, cs, S, cscore, sscore, rscore, uscore, M);
+    }
+}
+
+// one thread per (chain, STOP node); used when the chains do not share extractions (single mode, training, operators)
+__global__ void __launch_bounds__(128, 12) k_overlap(DevBatch B, const DevModel *__restrict__ models, int n_chains,
+                                                  int64_t total, RunOpts o, int flag) {
+    __shared__ int s_first;
+    // half-size slot space, as in k_coding_orf: chain k owns the slots from (coff + 1) / 2 on and its STOP nodes (at
+    // most nn / 2) take the first of them; star_ptr was preset to -1 for every node
+    const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int k = chain_hint(B, n_chains, min(2 * h, total - 1), total, &s_first, 2 * (int64_t)blockIdx.x * blockDim.x);
+    if (h > (total + 1) / 2) return;
+    while (k + 1 < n_chains && ((B.chains[k + 1].coff + 1) >> 1) <= h) k++;
+    const ChainInfo C = B.chains[k];
+    const int t = (int)(h - ((C.coff + 1) >> 1)), nn = C.nn;
+    if (t >= nn) return;
+    const int32_t *__restrict__ cbase = B.cbase + 4 * C.ext;
+    const int n_fe = cbase[2] - cbase[1], n_re = nn - cbase[3];
+    if (t >= n_fe + n_re) return;
+    const int i = (B.clist + C.node_off)[t < n_fe ? cbase[1] + t : cbase[3] + (t - n_fe)];
+    overlap_stop_node(B, models[C.model], C, i, o, flag);
+}
+
+// the same with the lanes of a group over the chains (models) that share the extraction, W = 4 / 8 / 16 / 32 lanes per
+// STOP node (the thread layout of the grouped k_coding_orf: orf_toff / orf_w / orf_blk): the geometric loop is
+// identical for the lanes of a node, so node loads are broadcasts and the interleaved cs / star_ptr / opv accesses of a
+// group are contiguous
+__global__ void __launch_bounds__(256, 6) k_overlap_lanes(DevBatch B, const DevModel *__restrict__ models, int n_ext, RunOpts o,
+                                                        int flag) {
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gt >= B.orf_toff[n_ext]) return;
+    int e = B.orf_blk[gt >> 8];
+    while (e + 1 < n_ext && B.orf_toff[e + 1] <= gt) e++;
+    const int W = B.orf_w[e];
+    const int local = (int)(gt - B.orf_toff[e]);
+    const int tl = local / W, lane = local % W;
+    const int32_t *__restrict__ cbase = B.cbase + 4 * e;
+    const ExtractInfo &X = B.exts[e];
+    const int nn = X.nn;
+    const int n_fe = cbase[2] - cbase[1], n_re = nn - cbase[3];
+    if (tl >= n_fe + n_re) return;
+    const int i = (B.clist + X.node_off)[tl < n_fe ? cbase[1] + tl : cbase[3] + (tl - n_fe)];
+    const int ch0 = B.ext_chain_off[e], nch = B.ext_chain_off[e + 1] - ch0;
+    for (int c0 = lane; c0 < nch; c0 += W) {
+        const ChainInfo C = B.chains[B.ext_chains[ch0 + c0]];
+        overlap_stop_node(B, models[C.model], C, i, o, flag);
     }
 }
 
@@ -868,9 +903,10 @@ __global__ void __launch_bounds__(128) k_opv(DevBatch B, const DevModel *__restr
     const int c = cls[i];
 #pragma unroll
     for (int f = 0; f < 3; f++) {
-        const int s = B.star_ptr[3 * g + f];
-        B.opv[3 * g + f] = (s < 0 || s >= C.nn || !cls_is_stop(c)) ? 0.0
-            : operon_value(c, i, s, cls, B.ndx + C.node_off, nullptr, B.cscore + C.coff, B.sscore + C.coff, B.rscore + C.coff,
+        const int64_t gi = C.ioff + (int64_t)i * C.istride;
+        const int s = B.star_ptr[3 * gi + f];
+        B.opv[3 * gi + f] = (s < 0 || s >= C.nn || !cls_is_stop(c)) ? 0.0
+            : operon_value(c, i, s, cls, B.ndx + C.node_off, nullptr, 1, B.cscore + C.coff, B.sscore + C.coff, B.rscore + C.coff,
                            B.uscore + C.coff, models[C.model]);
     }
 }
@@ -996,11 +1032,14 @@ void launch_pairs(const DevBatch &B, int n_ext, int total_nodes, unsigned long l
     if (n_ext == 0 || total_nodes == 0) return;
     k_pairs<<<(total_nodes + 255) / 256, 256, 0, st>>>(B, n_ext, total_nodes, ext_pairs);
 }
-void launch_overlap(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o, int flag,
+void launch_overlap(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, int n_ext, RunOpts o, int flag,
                     cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
     cudaMemsetAsync(B.star_ptr, 0xff, 3 * (size_t)total * sizeof(int32_t), st);  // -1 everywhere
-    k_overlap<<<(unsigned)(((total + 1) / 2 + 1 + 127) / 128), 128, 0, st>>>(B, models, n_chains, total, o, flag);
+    if (B.orf_toff && B.ext_chains && n_ext > 0)
+        k_overlap_lanes<<<(unsigned)((B.orf_threads + 255) / 256), 256, 0, st>>>(B, models, n_ext, o, flag);
+    else
+        k_overlap<<<(unsigned)(((total + 1) / 2 + 1 + 127) / 128), 128, 0, st>>>(B, models, n_chains, total, o, flag);
 }
 
 }  // namespace pgpu
