@@ -83,7 +83,7 @@ struct pgpu_ctx {
     size_t ws_limit = 0;
     cudaEvent_t ev[16];
     int64_t launches = 0;
-    int dp_ml_minb = 6;        // k_dp_ml register budget: min CTAs/SM 5, 6 or 8 (PGPU_DP_ML_MINB)
+    int dp_ml_minb = 8;        // k_dp_ml register budget: min CTAs/SM 5, 6 or 8 (PGPU_DP_ML_MINB); 8 = 64 registers, 32 warps / SM
     int extract_algo = 2;      // 2: bit-parallel extraction (k_codon_bits + k_extract_b), 1: warp-cooperative k_extract_w
                                // (PGPU_EXTRACT_ALGO; batches with N-run masks always use 1)
     int final_algo = 2;        // meta mode without node arrays: 2 = final scoring pass over the genes' ORFs only,
@@ -624,6 +624,16 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     contig_chain_begin[n] = (int)chains.size();
     contig_ext_begin[n] = (int)exts.size();
     const int n_ext = (int)exts.size(), n_chains = (int)chains.size();
+    // chains grouped by extraction (the lanes of k_dp_ml / k_coding_orf / k_overlap_lanes); node counts are not needed yet
+    std::vector<int32_t> h_eoff(n_ext + 1, 0);   // chains of an extraction: [h_eoff[e], h_eoff[e+1]) in B.ext_chains
+    std::vector<int32_t> h_elist(n_chains);
+    {
+        for (const auto &K : chains) h_eoff[K.ext + 1]++;
+        for (int e = 0; e < n_ext; e++) h_eoff[e + 1] += h_eoff[e];
+        std::vector<int32_t> fillp(h_eoff.begin(), h_eoff.end() - 1);
+        for (int k = 0; k < n_chains; k++) { chains[k].lane = fillp[chains[k].ext] - h_eoff[chains[k].ext]; h_elist[fillp[chains[k].ext]++] = k; }
+    }
+    int64_t total_il = 0;   // elements of an interleaved per-chain-node array (>= total chain-nodes: blocks are padded)
 
     tr("planned chains");
     // ---- extraction pass 1: mark + scan ------------------------------------------------------------
@@ -685,18 +695,12 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     for (int e = 0; e < n_ext; e++) { exts[e].node_off = h_base[e]; exts[e].nn = h_base[e + 1] - h_base[e]; }
     int64_t total_cn = 0;
     for (auto &K : chains) { K.node_off = exts[K.ext].node_off; K.nn = exts[K.ext].nn; K.coff = total_cn; total_cn += K.nn; }
-    // interleaved layout of the arrays the DP touches (ChainInfo::ioff): the chains of an extraction share one block of
-    // nn x L elements, element (node, chain) at block + node * L + position of the chain among them
-    std::vector<int32_t> h_eoff(n_ext + 1, 0);   // chains of an extraction: [h_eoff[e], h_eoff[e+1]) in B.ext_chains
-    std::vector<int32_t> h_elist(n_chains);
-    {
-        for (const auto &K : chains) h_eoff[K.ext + 1]++;
-        for (int e = 0; e < n_ext; e++) h_eoff[e + 1] += h_eoff[e];
-        std::vector<int32_t> fillp(h_eoff.begin(), h_eoff.end() - 1);
-        for (int k = 0; k < n_chains; k++) { chains[k].lane = fillp[chains[k].ext] - h_eoff[chains[k].ext]; h_elist[fillp[chains[k].ext]++] = k; }
+    {   // interleaved layout of the arrays the DP touches (ChainInfo::ioff): the chains of an extraction share one block
+        // of nn x L elements, element (node, chain) at block + node * L + position of the chain among them
         std::vector<int64_t> iblock(n_ext + 1, 0);
-        for (int e = 0; e < n_ext; e++) iblock[e + 1] = iblock[e] + (int64_t)exts[e].nn * (h_eoff[e + 1] - h_eoff[e]);
+        for (int e = 0; e < n_ext; e++) iblock[e + 1] = iblock[e] + (((int64_t)exts[e].nn * (h_eoff[e + 1] - h_eoff[e]) + 1) & ~int64_t(1));
         for (auto &K : chains) { K.istride = h_eoff[K.ext + 1] - h_eoff[K.ext]; K.ioff = iblock[K.ext] + K.lane; }
+        total_il = iblock[n_ext];   // blocks start at even elements (16-byte aligned doubles: bulk copies)
     }
     pool.copy_in(B.exts, exts.data(), n_ext * sizeof(ExtractInfo));
 
@@ -791,22 +795,23 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     B.cscore = pool.alloc<double>(total_cn); B.sscore = pool.alloc<double>(total_cn);
     B.rscore = pool.alloc<double>(total_cn); B.uscore = pool.alloc<double>(total_cn);
     B.tscore = pool.alloc<double>(total_cn);
-    B.cs = pool.alloc<double>(total_cn);
-    B.opv = pool.alloc<double>(3 * (size_t)total_cn);
-    B.star_ptr = pool.alloc<int32_t>(3 * (size_t)total_cn);
+    // interleaved arrays: total_il elements (blocks padded to even sizes) + slack for the bulk copies of the last rows
+    B.cs = pool.alloc<double>(total_il + 64);
+    B.opv = pool.alloc<double>(3 * (size_t)total_il + 64);
+    B.star_ptr = pool.alloc<int32_t>(3 * (size_t)total_il + 64);
     B.rbs = pool.alloc<uint8_t>(2 * (size_t)total_cn + 16);
-    B.score = pool.alloc<double>(total_cn);
-    B.traceb = pool.alloc<int32_t>(total_cn);
-    B.ov_mark = pool.alloc<int8_t>(total_cn + 16);
+    B.score = pool.alloc<double>(total_il + 64);
+    B.traceb = pool.alloc<int32_t>(total_il + 64);
+    B.ov_mark = pool.alloc<int8_t>(total_il + 64);
     B.chain_ipath = pool.alloc<int32_t>(n_chains);
     B.chain_score = pool.alloc<double>(n_chains);
     const bool dp_ml = ctx->dp_algo >= 6 || (ctx->dp_algo == 5 && n_chains > n_ext);
     if (ctx->dp_algo >= 1) {
-        B.dp_svig = pool.alloc<double>(total_cn);
-        B.dp_tbig = pool.alloc<int32_t>(total_cn);
+        B.dp_svig = pool.alloc<double>(total_il + 64);
+        B.dp_tbig = pool.alloc<int32_t>(total_il + 64);
         if (dp_ml) {
-            B.dp_fmv = pool.alloc<double>(total_cn);
-            B.dp_fmj = pool.alloc<int32_t>(total_cn);
+            B.dp_fmv = pool.alloc<double>(total_il + 64);
+            B.dp_fmj = pool.alloc<int32_t>(total_il + 64);
         }
     }
     int32_t *d_tracef = pool.alloc<int32_t>(total_cn);
@@ -828,7 +833,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     tev("k_start_score");
     ctx->launches += 2;
     int e_score = mark();
-    launch_overlap(B, ctx->d_models, n_chains, total_cn, n_ext, ro, 1, st);
+    launch_overlap(B, ctx->d_models, n_chains, total_cn, total_il, n_ext, ro, 1, st);
     tev("k_overlap");
     ctx->launches++;
     int e_ovl = mark();
@@ -879,20 +884,30 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         std::stable_sort(groups.begin(), groups.end(), [](const int4 &a, const int4 &b) { return a.w > b.w; });
         int4 *d_groups = pool.upload(groups);
         if (pool.failed) return PGPU_ENOMEM;
+        if (ctx->dp_verify) {   // the self-check compares whole arrays: define the padding between the blocks
+            cudaMemsetAsync(B.score, 0, (total_il + 64) * sizeof(double), st);
+            cudaMemsetAsync(B.traceb, 0, (total_il + 64) * sizeof(int32_t), st);
+            cudaMemsetAsync(B.ov_mark, 0, (total_il + 64) * sizeof(int8_t), st);
+        }
         launch_dp_ml(B, ctx->d_models, d_groups, (int)groups.size(), n_chains, ctx->dp_ml_minb, st);
         ctx->launches++;
         if (ctx->dp_verify && total_cn > 0) {
             // self-check: the per-chain kernel must reproduce every score / traceback / overlap frame
             DevBatch V = B;
-            V.score = pool.alloc<double>(total_cn);
-            V.traceb = pool.alloc<int32_t>(total_cn);
-            V.ov_mark = pool.alloc<int8_t>(total_cn + 16);
+            V.score = pool.alloc<double>(total_il + 64);
+            V.traceb = pool.alloc<int32_t>(total_il + 64);
+            V.ov_mark = pool.alloc<int8_t>(total_il + 64);
             unsigned long long *d_bad = pool.alloc<unsigned long long>(2);
             if (pool.failed) return PGPU_ENOMEM;
+            cudaMemsetAsync(V.score, 0, (total_il + 64) * sizeof(double), st);
+            cudaMemsetAsync(V.traceb, 0, (total_il + 64) * sizeof(int32_t), st);
+            cudaMemsetAsync(V.ov_mark, 0, (total_il + 64) * sizeof(int8_t), st);
             const unsigned long long init[2] = {0ULL, ~0ULL};
             CK(cudaMemcpyAsync(d_bad, init, sizeof(init), cudaMemcpyHostToDevice, st));
             launch_dp(V, ctx->d_models, d_order, n_chains, 1, 3, st);
-            launch_dp_compare(B.score, V.score, B.traceb, V.traceb, B.ov_mark, V.ov_mark, total_cn, d_bad, st);
+            // the padding elements between blocks are never written: compare zeros there
+            if (pool.failed) return PGPU_ENOMEM;
+            launch_dp_compare(B.score, V.score, B.traceb, V.traceb, B.ov_mark, V.ov_mark, total_il, d_bad, st);
             unsigned long long bad[2] = {0, 0};
             CK(cudaMemcpyAsync(bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -1150,7 +1165,7 @@ static int train_stage(pgpu_ctx *ctx, DevPool &pool, DevBatch &B, const ExtractI
             launch_gc_frame(B.gcbits + (X.doff >> 5), slen, V.gp, st);
             launch_gc_bias(B, V, d_bias, B.gcb, st);
             upload_model(T);
-            launch_overlap(B, d_model, 1, nn, 1, ro, 0, st);     // first start of each frame, no scores yet
+            launch_overlap(B, d_model, 1, nn, nn, 1, ro, 0, st); // first start of each frame, no scores yet
             launch_dp(B, d_model, nullptr, 1, 0, 0, st);          // final == 0: GC frame bias is the only score
             launch_training_path(B, V, d_iv, icap, d_niv, st);
             launch_dicodon(B.digits + X.doff, slen, d_iv, d_niv, icap, d_dc, d_dc + 4096, d_gene_total, st);

@@ -1032,10 +1032,10 @@ void launch_pairs(const DevBatch &B, int n_ext, int total_nodes, unsigned long l
     if (n_ext == 0 || total_nodes == 0) return;
     k_pairs<<<(total_nodes + 255) / 256, 256, 0, st>>>(B, n_ext, total_nodes, ext_pairs);
 }
-void launch_overlap(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, int n_ext, RunOpts o, int flag,
-                    cudaStream_t st) {
+void launch_overlap(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, int64_t total_il, int n_ext,
+                    RunOpts o, int flag, cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
-    cudaMemsetAsync(B.star_ptr, 0xff, 3 * (size_t)total * sizeof(int32_t), st);  // -1 everywhere
+    cudaMemsetAsync(B.star_ptr, 0xff, 3 * (size_t)total_il * sizeof(int32_t), st);  // -1 everywhere
     if (B.orf_toff && B.ext_chains && n_ext > 0)
         k_overlap_lanes<<<(unsigned)((B.orf_threads + 255) / 256), 256, 0, st>>>(B, models, n_ext, o, flag);
     else
