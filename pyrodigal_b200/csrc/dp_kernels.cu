@@ -683,14 +683,20 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
 //     the back stack is a running (value, node) maximum in registers, the front stack a suffix maximum written
 //     once per entry to an interleaved array when the window start passes the split point.  Window and split
 //     positions are geometric, hence uniform: the rebuild loop does not diverge.
-//   * DP-private arrays (source values, traceback nodes, suffix maxima) are interleaved [entry][lane], so a
-//     warp access touches L consecutive elements; the public score / traceb / ov_mark arrays stay chain-major.
+//   * every per-chain array is interleaved [node or entry][lane] (ChainInfo::ioff), so a warp access touches S
+//     consecutive elements.
+//   * the DP window in shared memory.  A step is a chain of dependent loads, so what bounds the kernel is the
+//     latency of each load, not bandwidth; the state a target reads most is therefore kept on chip, per warp:
+//       - cs = cscore + sscore of the next targets: the rows [i, i + rows) x S lanes of the interleaved array are
+//         contiguous, so they are fetched with 1-D bulk copies (TMA, cp.async.bulk + mbarrier complete_tx) into a
+//         double-buffered tile one chunk ahead of the walk;
+//       - per frame the score of the last -STOP (own stop of a reverse gene, operon predecessors) and the best
+//         +start of the open forward ORF.
 //   * rules that only admit +STOPs (operon, 3' overlap, triple overlap) walk the +STOP class list (node, ndx,
 //     merged position) instead of the merged stream; their ranges are geometric and come from k_dp_index.
 // Candidate order does not matter: the arg-max is "larger value, then larger node index", as everywhere else.
 // --------------------------------------------------------------------------------------------------
 constexpr int kMlWarps = 4;
-constexpr int kMlBatch = 2;  // near-source loads issued together (hides the L2 round trip of the source values)
 
 struct MlK {  // geometric constants of a target, staged 32 targets at a time (model independent)
     int32_t ndx, sv, cls, leave;
@@ -700,19 +706,129 @@ struct MlK {  // geometric constants of a target, staged 32 targets at a time (m
     int32_t a, b, c, pad;
 };
 
-__device__ double g_ml_no_source = -DBL_MAX;  // what idle lanes read instead of a source value
+// ---- 1-D bulk copy global -> shared (TMA) completing on an mbarrier; raw PTX, sm_90+ ---------------
+#ifndef PGPU_HOST_EMULATION
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// arm the barrier with the byte count of the copy, then start the copy (one elected lane)
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+#else   // host emulation (tests/emu): the copy happens at once, the barrier is always complete
+__device__ __forceinline__ void mbar_init(uint64_t *, int) {}
+__device__ __forceinline__ void mbar_init_fence() {}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void mbar_wait(uint64_t *, uint32_t) {}
+#endif
 
-template <int MINB>
+// (2.0 - dist / 60) * 0.15 of _connection.h:74 for dist = 0..60: the model-independent part of the distance term; the
+// term itself is this times the start weight of the lane's model (same operations, same order as the reference)
+__constant__ double c_igA[61] = {
+    (2.0 - ((double)0 / 60)) * 0.15,
+    (2.0 - ((double)1 / 60)) * 0.15,
+    (2.0 - ((double)2 / 60)) * 0.15,
+    (2.0 - ((double)3 / 60)) * 0.15,
+    (2.0 - ((double)4 / 60)) * 0.15,
+    (2.0 - ((double)5 / 60)) * 0.15,
+    (2.0 - ((double)6 / 60)) * 0.15,
+    (2.0 - ((double)7 / 60)) * 0.15,
+    (2.0 - ((double)8 / 60)) * 0.15,
+    (2.0 - ((double)9 / 60)) * 0.15,
+    (2.0 - ((double)10 / 60)) * 0.15,
+    (2.0 - ((double)11 / 60)) * 0.15,
+    (2.0 - ((double)12 / 60)) * 0.15,
+    (2.0 - ((double)13 / 60)) * 0.15,
+    (2.0 - ((double)14 / 60)) * 0.15,
+    (2.0 - ((double)15 / 60)) * 0.15,
+    (2.0 - ((double)16 / 60)) * 0.15,
+    (2.0 - ((double)17 / 60)) * 0.15,
+    (2.0 - ((double)18 / 60)) * 0.15,
+    (2.0 - ((double)19 / 60)) * 0.15,
+    (2.0 - ((double)20 / 60)) * 0.15,
+    (2.0 - ((double)21 / 60)) * 0.15,
+    (2.0 - ((double)22 / 60)) * 0.15,
+    (2.0 - ((double)23 / 60)) * 0.15,
+    (2.0 - ((double)24 / 60)) * 0.15,
+    (2.0 - ((double)25 / 60)) * 0.15,
+    (2.0 - ((double)26 / 60)) * 0.15,
+    (2.0 - ((double)27 / 60)) * 0.15,
+    (2.0 - ((double)28 / 60)) * 0.15,
+    (2.0 - ((double)29 / 60)) * 0.15,
+    (2.0 - ((double)30 / 60)) * 0.15,
+    (2.0 - ((double)31 / 60)) * 0.15,
+    (2.0 - ((double)32 / 60)) * 0.15,
+    (2.0 - ((double)33 / 60)) * 0.15,
+    (2.0 - ((double)34 / 60)) * 0.15,
+    (2.0 - ((double)35 / 60)) * 0.15,
+    (2.0 - ((double)36 / 60)) * 0.15,
+    (2.0 - ((double)37 / 60)) * 0.15,
+    (2.0 - ((double)38 / 60)) * 0.15,
+    (2.0 - ((double)39 / 60)) * 0.15,
+    (2.0 - ((double)40 / 60)) * 0.15,
+    (2.0 - ((double)41 / 60)) * 0.15,
+    (2.0 - ((double)42 / 60)) * 0.15,
+    (2.0 - ((double)43 / 60)) * 0.15,
+    (2.0 - ((double)44 / 60)) * 0.15,
+    (2.0 - ((double)45 / 60)) * 0.15,
+    (2.0 - ((double)46 / 60)) * 0.15,
+    (2.0 - ((double)47 / 60)) * 0.15,
+    (2.0 - ((double)48 / 60)) * 0.15,
+    (2.0 - ((double)49 / 60)) * 0.15,
+    (2.0 - ((double)50 / 60)) * 0.15,
+    (2.0 - ((double)51 / 60)) * 0.15,
+    (2.0 - ((double)52 / 60)) * 0.15,
+    (2.0 - ((double)53 / 60)) * 0.15,
+    (2.0 - ((double)54 / 60)) * 0.15,
+    (2.0 - ((double)55 / 60)) * 0.15,
+    (2.0 - ((double)56 / 60)) * 0.15,
+    (2.0 - ((double)57 / 60)) * 0.15,
+    (2.0 - ((double)58 / 60)) * 0.15,
+    (2.0 - ((double)59 / 60)) * 0.15,
+    (2.0 - ((double)60 / 60)) * 0.15
+};
+
+// CSH: doubles of one half of the cs tile (rows per half = largest even number <= CSH / S)
+template <int MINB, int CSH>
 __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const DevModel *__restrict__ models,
                                                                const int4 *__restrict__ groups, int n_groups) {
-    __shared__ MlK s_k[kMlWarps][32];
-    __shared__ double s_rcv[3][32 * kMlWarps];  // per frame: best +start of the open forward ORF (value, node)
-    __shared__ int32_t s_rcj[3][32 * kMlWarps];
+    struct __align__(16) WarpMem {
+        double cs[2][CSH];       // bulk-copy destinations: 16-byte aligned
+        MlK k[32];
+        double rcv[3][32];       // per frame: best +start of the open forward ORF (value ...
+        double rev[3][32];       // per frame: score of the last -STOP
+        int32_t rcj[3][32];      // ... and node)
+        int32_t rej[4];          // node of the last -STOP of every frame
+        // -STOP target, per frame k and lane: the recorded overlapping -start (node sp, position n3n, its -STOP n3s), the
+        // class range [sa, sb) of the +STOPs that can trigger the triple overlap with it, and the operon value -- kept
+        // here instead of in 21 registers (only every eighth target is a -STOP; registers decide the occupancy)
+        int32_t t_sp[3][32], t_n3n[3][32], t_n3s[3][32], t_sa[3][32], t_sb[3][32];
+        double t_op[3][32];
+        uint64_t bar[2];
+    };
+    __shared__ WarpMem s_w[kMlWarps];
     const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
     const int slot = blockIdx.x * kMlWarps + wslot;
     if (slot >= n_groups) return;
     constexpr int W = 32;
-    constexpr unsigned gmask = 0xffffffffu;
     const int4 G = groups[slot];  // x: first entry in ext_chains, y: number of chains (<= 32), z: extraction; longest first
     const int L = G.y;
     const bool act = lane < L;
@@ -722,38 +838,48 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
     const int nn = C.nn;  // the same for every lane: one extraction
     if (nn == 0) return;  // k_chain_best reports "no path"
     const DevModel &M = models[C.model];
-    const int32_t *__restrict__ ndx = B.ndx + C.node_off;
-    const int32_t *__restrict__ sv = B.stop_val + C.node_off;
-    const uint8_t *__restrict__ cls = B.cls + C.node_off;
-    const int32_t *__restrict__ ig_node = B.ig_node + C.node_off;
-    const int32_t *__restrict__ ig_ndx = B.ig_ndx + C.node_off;
-    const int4 *__restrict__ dpx = B.dpx + C.node_off;
-    const int fe0 = B.cbase[4 * G.z + 1];
-    const int32_t *__restrict__ fe_node = B.clist + C.node_off + fe0;  // +STOPs in class order: node,
-    const int32_t *__restrict__ fe_ndx = B.cndx + C.node_off + fe0;    // ndx,
-    const int32_t *__restrict__ fe_q = B.feq + C.node_off + fe0;       // merged-stream position
-    // Every per-chain array of this kernel is interleaved over the chains of the extraction (ChainInfo::ioff): element
-    // (x, lane) at ioff + x * S, where x is a node index (cs, opv, star_ptr, score, traceb, ov_mark) or a merged-stream
-    // position (the DP-private source values / traceback nodes / suffix maxima).  A warp access touches S consecutive
-    // elements.
-    const int64_t S = C.istride, S3 = 3 * S;
-    const double *__restrict__ csum = B.cs + C.ioff;  // cscore + sscore, written by the scoring pass
-    const double *__restrict__ opv = B.opv + 3 * C.ioff;
-    const int32_t *__restrict__ star_ptr = B.star_ptr + 3 * C.ioff;
-    const Strided<double> score{B.score + C.ioff, S};
-    const Strided<int32_t> traceb{B.traceb + C.ioff, S};
-    const Strided<int8_t> ov_mark{B.ov_mark + C.ioff, S};
-    double *svig = B.dp_svig + C.ioff;
-    int32_t *tbig = B.dp_tbig + C.ioff;
-    double *fmv = B.dp_fmv + C.ioff;
-    int32_t *fmj = B.dp_fmj + C.ioff;
-    MlK *sk = s_k[wslot];
-    const double ig_neg = M.ig_neg;
-    const double *__restrict__ igt = M.igt;
-    // source value of a merged-stream entry for this lane; idle lanes read "no source" (stride 0)
-    const double *svr = act ? svig : &g_ml_no_source;
-    const int64_t svs = act ? S : 0;
-    auto SV = [&](int q) -> double { return svr[q * svs]; };
+    // Arrays are addressed from the kernel parameters (constant bank) + two offsets instead of through eighteen
+    // precomputed pointers: the pointers alone would take 36 registers, and occupancy is what hides the load latency
+    // of the walk.  no: first node of the extraction; io: this lane's element of the extraction's interleaved block
+    // (ChainInfo::ioff) -- element (x, lane) at io + x * S, where x is a node index (cs, opv, star_ptr, score, traceb,
+    // ov_mark) or a merged-stream position (the DP-private source values / traceback positions / suffix maxima).
+    const int no = C.node_off;
+    const int64_t io = C.ioff;
+    const int S = C.istride;
+    const int fe0 = no + B.cbase[4 * G.z + 1];   // +STOPs in class order: node (clist), ndx (cndx), merged-stream position (feq)
+#define ndx(j) B.ndx[no + (j)]
+#define sv(j) B.stop_val[no + (j)]
+#define cls(j) B.cls[no + (j)]
+#define dpx(j) B.dpx[no + (j)]
+#define ig_node(q) B.ig_node[no + (q)]
+#define ig_ndx(q) B.ig_ndx[no + (q)]
+#define fe_node(r) B.clist[fe0 + (r)]
+#define fe_ndx(r) B.cndx[fe0 + (r)]
+#define fe_q(r) B.feq[fe0 + (r)]
+#define IL(x) (io + (int64_t)(x) * S)
+#define opv(j, f) B.opv[3 * IL(j) + (f)]
+#define star_ptr(j, f) B.star_ptr[3 * IL(j) + (f)]
+#define score(j) B.score[IL(j)]
+#define svig(q) B.dp_svig[IL(q)]   /* source value of a merged-stream entry (-DBL_MAX: nothing leads into it) */
+#define tbx(q) B.dp_tbig[IL(q)]    /* +STOP entries: POSITION (ndx) of the node their traceback points to */
+#define fmv(q) B.dp_fmv[IL(q)]
+#define fmj(q) B.dp_fmj[IL(q)]
+    WarpMem &wm = s_w[wslot];
+    MlK *sk = wm.k;
+    const double ig_neg = M.ig_neg, st_wt = M.st_wt;
+
+    // ---- cs tile: chunks of `rows` target rows, chunk c in half c & 1, fetched one chunk ahead ----
+    const int rows = max(2, (CSH / S) & ~1);
+    const double *cs_block = B.cs + (io - C.lane);   // row r of the extraction at cs_block + r * S (16-byte aligned for even r)
+    const uint32_t chunk_bytes = (uint32_t)rows * S * 8u;
+    int chunk = 0, chunk_begin = 0;
+    if (lane == 0) { mbar_init(&wm.bar[0], 1); mbar_init(&wm.bar[1], 1); mbar_init_fence(); }
+    __syncwarp();
+    if (lane == 0) {
+        bulk_load(wm.cs[0], cs_block, chunk_bytes, &wm.bar[0]);
+        if (rows < nn) bulk_load(wm.cs[1], cs_block + (int64_t)rows * S, chunk_bytes, &wm.bar[1]);
+    }
+    mbar_wait(&wm.bar[0], 0);
 
     // merged-stream cursors (uniform): cur = finalized entries, lo = first entry inside [i-1000, i), far = first
     // entry that is NOT more than 180 bp behind the target, split = boundary between front and back stack;
@@ -762,21 +888,26 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
     double bk_v = kNeg;  // back stack: running maximum over the entries [split, far)
     int bk_j = -1;
 #pragma unroll
-    for (int f = 0; f < 3; f++) { s_rcv[f][threadIdx.x] = kNeg; s_rcj[f][threadIdx.x] = -1; }
+    for (int f = 0; f < 3; f++) { wm.rcv[f][lane] = kNeg; wm.rcj[f][lane] = -1; wm.rev[f][lane] = 0.0; }
+    if (lane < 4) wm.rej[lane] = -1;
+
+    auto ENT_ND = [&](int q) -> int { return ig_node(q); };
+    auto ENT_NX = [&](int q) -> int { return ig_ndx(q); };
+    auto ENT_SV = [&](int q) -> double { return svig(q); };
 
     for (int i0 = 0; i0 < nn; i0 += W) {
-      __syncwarp(gmask);
+      __syncwarp();
       if (i0 + lane < nn) {
           const int i = i0 + lane;
           MlK k;
-          k.ndx = ndx[i]; k.sv = sv[i]; k.cls = cls[i];
-          k.leave = i > 2 * kMaxNodeDist ? cls_kind(cls[i - 2 * kMaxNodeDist - 1]) : -1;
+          k.ndx = ndx(i); k.sv = sv(i); k.cls = cls(i);
+          k.leave = i > 2 * kMaxNodeDist ? cls_kind(cls(i - 2 * kMaxNodeDist - 1)) : -1;
           const int kind = cls_kind(k.cls);
-          const int4 dx = dpx[i];
+          const int4 dx = dpx(i);
           k.a = k.b = k.c = -1; k.pad = 0;
           if (kind == K_FE || kind == K_RS) {
-              const int wmin = B.win_min[C.node_off + i];                       // first node of the window
-              const int wlo = B.crank[4 * (int64_t)(C.node_off + wmin) + 1];    // +STOPs before it
+              const int wmin = B.win_min[no + i];                       // first node of the window
+              const int wlo = B.crank[4 * (int64_t)(no + wmin) + 1];    // +STOPs before it
               if (kind == K_FE) { k.a = max(dx.x, wlo); }
               else { k.a = (dx.x >= wmin && dx.x >= 0 && dx.x < i) ? dx.x : -1; k.b = max(dx.y, wlo); k.c = dx.z; }
           } else if (kind == K_RE) {
@@ -785,16 +916,24 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
           }
           sk[lane] = k;
       }
-      __syncwarp(gmask);
+      __syncwarp();
       const int iend = min(i0 + W, nn);
       for (int i = i0; i < iend; i++) {
         const MlK &K = sk[i - i0];
         const int ci = K.cls, kind = cls_kind(ci), f2 = cls_frame(ci), ndx_i = K.ndx, sv_i = K.sv;
         lo += (K.leave == K_FE) | (K.leave == K_RS);
         lo_fe += K.leave == K_FE;
+        // ---- cs tile: entering the next chunk (uniform) ----
+        if (i >= chunk_begin + rows) {
+            chunk++; chunk_begin += rows;
+            mbar_wait(&wm.bar[chunk & 1], (chunk >> 1) & 1);   // every phase is observed exactly once
+            // the half of the chunk just left is free (every lane is past its last read: __syncwarp at the end of a step)
+            const int nxt = chunk_begin + rows;
+            if (lane == 0 && nxt < nn) bulk_load(wm.cs[(chunk + 1) & 1], cs_block + (int64_t)nxt * S, chunk_bytes, &wm.bar[(chunk + 1) & 1]);
+        }
         // cscore + sscore of a start target
         double cs_i = 0.0;
-        if (kind == K_FS || kind == K_RS) cs_i = csum[i * S];
+        if (kind == K_FS || kind == K_RS) cs_i = wm.cs[chunk & 1][(i - chunk_begin) * S + ll];
         double wv = kNeg;
         int wkey = -1;  // (node << 2) | (overlap frame + 1)
         // larger value, then larger node; the same node seen twice (far maximum + overlap re-evaluation) keeps the
@@ -805,56 +944,65 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
         };
 
         if (kind == K_RS) {
-            // own -STOP (gene, _connection.h:228-237)
-            if (K.a >= 0) cand(score[K.a] + cs_i, K.a, -1);
+            // own -STOP (gene, _connection.h:228-237): the last -STOP of this frame
+            if (K.a >= 0) cand((wm.rej[f2] == K.a ? wm.rev[f2][lane] : score(K.a)) + cs_i, K.a, -1);
             // +STOPs overlapping the 3' end (_connection.h:239-256)
             const double cs_diff = cs_i + ig_neg;
             const int re = min(K.c, cur_fe);
 #pragma unroll 1
             for (int r = K.b; r < re; r++) {
-                const int nj = fe_ndx[r], q = fe_q[r], j = fe_node[r];
-                const double s = SV(q);
+                const int nj = fe_ndx(r), q = fe_q(r), j = fe_node(r);
                 if (sv_i - 2 >= nj + 2) continue;
                 const int ovlp = (nj + 2) - (sv_i - 2) + 1;
                 if (ovlp >= kMaxOppOvlp) continue;
                 if ((nj - sv_i) >= (ndx_i - nj + 3)) continue;
+                const double s = ENT_SV(q);
+                const int tx = tbx(q);
                 if (s == kNeg) continue;
-                if ((nj - sv_i) >= (sv_i - 3 - ndx[tbig[q * S]])) continue;
+                if ((nj - sv_i) >= (sv_i - 3 - tx)) continue;
                 cand(s + cs_diff, j, -1);
             }
         } else if (kind == K_FE) {
             {   // best +start of this ORF (gene): running maximum of fl(score + cscore + sscore)
-                const int rj = s_rcj[f2][threadIdx.x];
-                if (rj >= 0) cand(s_rcv[f2][threadIdx.x], rj, -1);
+                const int rj = wm.rcj[f2][lane];
+                if (rj >= 0) cand(wm.rcv[f2][lane], rj, -1);
             }
             // +STOPs inside the ORF (operon, _connection.h:178-191)
 #pragma unroll 1
             for (int r = K.a; r < cur_fe; r++) {
-                const int q = fe_q[r], j = fe_node[r];
-                const double s = SV(q);
-                const int spj = star_ptr[S3 * (int64_t)j + f2];
-                const double opj = opv[S3 * (int64_t)j + f2];
+                const int q = fe_q(r), j = fe_node(r);
+                const double s = ENT_SV(q);
+                const int spj = star_ptr(j, f2);
+                const double opj = opv(j, f2);
                 if (s != kNeg && spj != -1) cand(s + opj, j, -1);
             }
         } else {  // K_FS, K_RE: intergenic sources
+            // the front stack's answer for this window start: issued first, consumed after the near sources
+            double fm_v = kNeg;
+            int fm_j = -1;
+            const bool flip = lo > split;
+            if (!flip && lo < split) { fm_j = fmj(lo); fm_v = fmv(lo); }
             // -STOP only: the recorded overlapping -starts of this model (lane): node, its -STOP, and the class
             // range of the +STOPs that can trigger the triple overlap with it
-            int sp0 = -1, sp1 = -1, sp2 = -1, n3n0 = 0, n3n1 = 0, n3n2 = 0, n3s0 = 0, n3s1 = 0, n3s2 = 0;
-            int sa0 = 0, sa1 = 0, sa2 = 0, sb0 = 0, sb1 = 0, sb2 = 0;
-            double op0 = 0.0, op1 = 0.0, op2 = 0.0;
             if (kind == K_RE) {
-                sp0 = star_ptr[S3 * (int64_t)i]; sp1 = star_ptr[S3 * (int64_t)i + 1]; sp2 = star_ptr[S3 * (int64_t)i + 2];
-                if (sp0 != -1) { n3n0 = ndx[sp0]; n3s0 = sv[sp0]; op0 = opv[S3 * (int64_t)i]; const int4 d = dpx[sp0]; sa0 = d.y; sb0 = d.z; }
-                if (sp1 != -1) { n3n1 = ndx[sp1]; n3s1 = sv[sp1]; op1 = opv[S3 * (int64_t)i + 1]; const int4 d = dpx[sp1]; sa1 = d.y; sb1 = d.z; }
-                if (sp2 != -1) { n3n2 = ndx[sp2]; n3s2 = sv[sp2]; op2 = opv[S3 * (int64_t)i + 2]; const int4 d = dpx[sp2]; sa2 = d.y; sb2 = d.z; }
+#pragma unroll
+                for (int f = 0; f < 3; f++) {
+                    const int sp = star_ptr(i, f);
+                    wm.t_sp[f][lane] = sp;
+                    if (sp != -1) {
+                        const int4 d = dpx(sp);
+                        wm.t_n3n[f][lane] = ndx(sp); wm.t_n3s[f][lane] = sv(sp); wm.t_op[f][lane] = opv(i, f);
+                        wm.t_sa[f][lane] = d.y; wm.t_sb[f][lane] = d.z;
+                    }
+                }
             }
             // ---- entries that fall more than 180 bp behind move onto the back stack ----
             const int thr = ndx_i - 3 * kOperDist;
 #pragma unroll 1
-            while (far < cur && ig_ndx[far] < thr) {
-                const int nd = ig_node[far];
+            while (far < cur && ENT_NX(far) < thr) {
+                const int nd = ENT_ND(far);
                 if (far >= lo) {
-                    const double s = SV(far);
+                    const double s = ENT_SV(far);
                     if (s != kNeg) {
                         const double x = s + ig_neg;
                         if (x >= bk_v) { bk_v = x; bk_j = nd & 0x7fffffff; }  // later entry wins a tie
@@ -864,48 +1012,58 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
                 far++;
             }
             // ---- the window start passed the split: flip the back stack into suffix maxima ----
-            if (lo > split) {
+            if (flip) {
                 double fv = kNeg;
                 int fj = -1;
-#pragma unroll 2
-                for (int q = far - 1; q >= lo; q--) {
-                    const double s = SV(q);
+                // the entries are read once, here: four independent loads per round (values, then nodes)
+                int q = far - 1;
+#pragma unroll 1
+                for (; q - 3 >= lo; q -= 4) {
+                    double s8[4];
+                    int n8[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { s8[u] = ENT_SV(q - u); n8[u] = ENT_ND(q - u); }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (s8[u] != kNeg) {
+                            const double x = s8[u] + ig_neg;
+                            if (x > fv) { fv = x; fj = n8[u] & 0x7fffffff; }  // earlier entry loses a tie
+                        }
+                        if (act) { fmv(q - u) = fv; fmj(q - u) = fj; }
+                    }
+                }
+#pragma unroll 1
+                for (; q >= lo; q--) {
+                    const double s = ENT_SV(q);
                     if (s != kNeg) {
                         const double x = s + ig_neg;
-                        if (x > fv) { fv = x; fj = ig_node[q] & 0x7fffffff; }  // earlier entry loses a tie
+                        if (x > fv) { fv = x; fj = ENT_ND(q) & 0x7fffffff; }
                     }
-                    if (act) { fmv[q * S] = fv; fmj[q * S] = fj; }
+                    if (act) { fmv(q) = fv; fmj(q) = fj; }
                 }
                 split = far;
                 bk_v = kNeg; bk_j = -1;
+                if (lo < split) { fm_v = fv; fm_j = fj; }   // what the loop stored last is the entry of `lo`
             }
-            if (lo < split && act) {
-                const int fj = fmj[lo * S];
-                const double fv = fmv[lo * S];
-                if (fj >= 0) cand(fv, fj, -1);
-            }
+            if (fm_j >= 0) cand(fm_v, fm_j, -1);
             if (bk_j >= 0) cand(bk_v, bk_j, -1);
             const int flo = max(far, lo);
             if (kind == K_FS) {
                 // near sources (_connection.h:116-129): +STOP distance-dependent term, -start strand switch
 #pragma unroll 1
-                for (int q0 = flo; q0 < cur; q0 += kMlBatch) {
-                    double s[kMlBatch];
-                    int nd[kMlBatch], nj[kMlBatch];
-#pragma unroll
-                    for (int u = 0; u < kMlBatch; u++) {
-                        const int q = min(q0 + u, cur - 1);  // a clamped slot repeats the last entry: harmless
-                        nd[u] = ig_node[q];
-                        nj[u] = ig_ndx[q];
-                        s[u] = SV(q);
+                for (int q0 = flo; q0 < cur; q0 += 2) {   // two entries per round: their loads are in flight together
+                    const int q1 = min(q0 + 1, cur - 1);   // a clamped slot repeats the last entry: harmless
+                    const int nd0 = ENT_ND(q0), nj0 = ENT_NX(q0), nd1 = ENT_ND(q1), nj1 = ENT_NX(q1);
+                    const double s0 = ENT_SV(q0), s1 = ENT_SV(q1);
+                    if (s0 != kNeg && !(nd0 < 0 ? (nj0 + 2 >= ndx_i) : (nj0 >= ndx_i))) {
+                        const int dist = ndx_i - nj0;
+                        const double term = (nd0 >= 0 || dist > 3 * kOperDist) ? ig_neg : (dist <= kOperDist ? c_igA[dist] * st_wt : 0.0);
+                        cand(s0 + term, nd0 & 0x7fffffff, -1);
                     }
-#pragma unroll
-                    for (int u = 0; u < kMlBatch; u++) {
-                        if (s[u] == kNeg) continue;
-                        if (nd[u] < 0 ? (nj[u] + 2 >= ndx_i) : (nj[u] >= ndx_i)) continue;
-                        const int dist = ndx_i - nj[u];
-                        const double term = (nd[u] >= 0 || dist > 3 * kOperDist) ? ig_neg : (dist <= kOperDist ? igt[dist] : 0.0);
-                        cand(s[u] + term, nd[u] & 0x7fffffff, -1);
+                    if (s1 != kNeg && !(nd1 < 0 ? (nj1 + 2 >= ndx_i) : (nj1 >= ndx_i))) {
+                        const int dist = ndx_i - nj1;
+                        const double term = (nd1 >= 0 || dist > 3 * kOperDist) ? ig_neg : (dist <= kOperDist ? c_igA[dist] * st_wt : 0.0);
+                        cand(s1 + term, nd1 & 0x7fffffff, -1);
                     }
                 }
             } else {
@@ -915,31 +1073,31 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
                     if (left >= right) return;
                     int maxfr = -1, tj = kTbNone;
                     double maxval = 0.0;
-                    auto probe = [&](int k, int spk, int n3n, int n3s, double op) {
-                        if (spk == -1) return;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        if (wm.t_sp[k][lane] == -1) continue;
+                        const int n3s = wm.t_n3s[k][lane];
                         const int ovlp = left - n3s + 3;
-                        if (ovlp <= 0 || ovlp >= kMaxOppOvlp) return;
-                        if (ovlp >= n3n - left) return;
-                        if (tj == kTbNone) tj = ndx[tbig[q * S]];
-                        if (ovlp >= n3s - tj - 2) return;
+                        if (ovlp <= 0 || ovlp >= kMaxOppOvlp) continue;
+                        if (ovlp >= wm.t_n3n[k][lane] - left) continue;
+                        if (tj == kTbNone) tj = tbx(q);
+                        if (ovlp >= n3s - tj - 2) continue;
+                        const double op = wm.t_op[k][lane];
                         if (op > maxval) { maxfr = k; maxval = op; }
-                    };
-                    probe(0, sp0, n3n0, n3s0, op0);
-                    probe(1, sp1, n3n1, n3s1, op1);
-                    probe(2, sp2, n3n2, n3s2, op2);
+                    }
                     cand(s + (maxfr != -1 ? maxval : ig_neg), j, maxfr);
                 };
 #pragma unroll 1
                 for (int q = flo; q < cur; q++) {
-                    const int nd = ig_node[q], nj = ig_ndx[q];
-                    const double s = SV(q);
+                    const int nd = ENT_ND(q), nj = ENT_NX(q);
+                    const double s = ENT_SV(q);
                     if (s == kNeg) continue;
                     if (nd < 0) {
                         eval_fe(q, s, nj, nd & 0x7fffffff);
                     } else {  // -start (_connection.h:335-341)
                         if (nj >= ndx_i - 2) continue;
                         const int dist = ndx_i - nj;
-                        cand(s + (dist > 3 * kOperDist ? ig_neg : (dist <= kOperDist ? igt[dist] : 0.0)), nd, -1);
+                        cand(s + (dist > 3 * kOperDist ? ig_neg : (dist <= kOperDist ? c_igA[dist] * st_wt : 0.0)), nd, -1);
                     }
                 }
                 // far +STOPs whose position can trigger the triple overlap (ndx in [n3s-4, n3s+194], n3s = the -STOP
@@ -951,31 +1109,32 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
                 if (lo_fe < ffe) {
 #pragma unroll 1
                     for (int k = 0; k < 3; k++) {
-                        const int spk = k == 0 ? sp0 : (k == 1 ? sp1 : sp2), n3s = k == 0 ? n3s0 : (k == 1 ? n3s1 : n3s2);
-                        int sa = k == 0 ? sa0 : (k == 1 ? sa1 : sa2);
-                        const int sb = k == 0 ? sb0 : (k == 1 ? sb1 : sb2);
+                        const int spk = wm.t_sp[k][lane], n3s = wm.t_n3s[k][lane];
+                        int sa = wm.t_sa[k][lane];
+                        const int sb = wm.t_sb[k][lane];
                         int a_ = 0, b_ = 0;
                         if (spk != -1) {
-                            while (sa > lo_fe && fe_ndx[sa - 1] >= n3s - 4) sa--;
+                            while (sa > lo_fe && fe_ndx(sa - 1) >= n3s - 4) sa--;
                             a_ = max(sa, lo_fe); b_ = min(sb, ffe);
                         }
                         const bool any = a_ < b_;
-                        if (!__any_sync(gmask, any)) continue;
-                        const int ua = __reduce_min_sync(gmask, any ? a_ : 0x7fffffff);
-                        const int ub = __reduce_max_sync(gmask, any ? b_ : -1);
+                        if (!__any_sync(0xffffffffu, any)) continue;
+                        const int ua = __reduce_min_sync(0xffffffffu, any ? a_ : 0x7fffffff);
+                        const int ub = __reduce_max_sync(0xffffffffu, any ? b_ : -1);
 #pragma unroll 1
                         for (int r = ua; r < ub; r++) {
                             if (r < a_ || r >= b_) continue;
-                            const int q = fe_q[r];
-                            const double s = SV(q);
-                            if (s != kNeg) eval_fe(q, s, fe_ndx[r], fe_node[r]);
+                            const int q = fe_q(r);
+                            const double s = ENT_SV(q);
+                            if (s != kNeg) eval_fe(q, s, fe_ndx(r), fe_node(r));
                         }
                     }
                 }
-                // -STOPs whose ORF spans this stop: operon (_connection.h:343-356); at most one per frame
-                if (K.a >= 0 && sp0 != -1) cand(score[K.a] + op0, K.a, -1);
-                if (K.b >= 0 && sp1 != -1) cand(score[K.b] + op1, K.b, -1);
-                if (K.c >= 0 && sp2 != -1) cand(score[K.c] + op2, K.c, -1);
+                // -STOPs whose ORF spans this stop: operon (_connection.h:343-356); at most one per frame = the last
+                // -STOP of that frame
+                if (K.a >= 0 && wm.t_sp[0][lane] != -1) cand((wm.rej[0] == K.a ? wm.rev[0][lane] : score(K.a)) + wm.t_op[0][lane], K.a, -1);
+                if (K.b >= 0 && wm.t_sp[1][lane] != -1) cand((wm.rej[1] == K.b ? wm.rev[1][lane] : score(K.b)) + wm.t_op[1][lane], K.b, -1);
+                if (K.c >= 0 && wm.t_sp[2][lane] != -1) cand((wm.rej[2] == K.c ? wm.rev[2][lane] : score(K.c)) + wm.t_op[2][lane], K.c, -1);
             }
         }
 
@@ -983,25 +1142,45 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
         int tb_i = -1, fr_i = -1;
         if (wkey >= 0 && wv >= 0.0) { sc_i = wv; tb_i = wkey >> 2; fr_i = (wkey & 3) - 1; }
         if (act) {
-            score[i] = sc_i; traceb[i] = tb_i; ov_mark[i] = (int8_t)fr_i;
+            score(i) = sc_i; B.traceb[IL(i)] = tb_i; B.ov_mark[IL(i)] = (int8_t)fr_i;
             if (kind == K_FE || kind == K_RS) {
-                svig[cur * S] = tb_i == -1 ? kNeg : sc_i;  // edge-artifact rule: nothing leads into it
-                tbig[cur * S] = tb_i;
+                svig(cur) = tb_i == -1 ? kNeg : sc_i;  // edge-artifact rule: nothing leads into it
+                if (kind == K_FE) tbx(cur) = tb_i >= 0 ? ndx(tb_i) : 0;
             }
         }
         if (kind == K_FE) {
             cur++; cur_fe++;
-            s_rcv[f2][threadIdx.x] = kNeg; s_rcj[f2][threadIdx.x] = -1;
+            wm.rcv[f2][lane] = kNeg; wm.rcj[f2][lane] = -1;
         } else if (kind == K_RS) {
             cur++;
         } else if (kind == K_FS) {
             const double g = sc_i + cs_i;
-            if (g >= s_rcv[f2][threadIdx.x]) { s_rcv[f2][threadIdx.x] = g; s_rcj[f2][threadIdx.x] = i; }
+            if (g >= wm.rcv[f2][lane]) { wm.rcv[f2][lane] = g; wm.rcj[f2][lane] = i; }
+        } else {
+            wm.rev[f2][lane] = sc_i;
+            if (lane == 0) wm.rej[f2] = i;
         }
-        __syncwarp(gmask);  // every lane reads only its own column; the barrier just keeps the group converged
+        __syncwarp();  // the per-frame slots written above are visible to every lane of the next step
       }
     }
 }
+#undef ndx
+#undef sv
+#undef cls
+#undef dpx
+#undef ig_node
+#undef ig_ndx
+#undef fe_node
+#undef fe_ndx
+#undef fe_q
+#undef IL
+#undef opv
+#undef star_ptr
+#undef score
+#undef svig
+#undef tbx
+#undef fmv
+#undef fmj
 
 // arg-max of the DP score over the terminal node kinds (+STOP, -start), largest index among equal maxima
 // (lib.pyx:1239-1251 scans from the end with a strict ">"); -1 when nothing leads into it (lib.pyx:1311)
@@ -1453,9 +1632,9 @@ void launch_dp_ml(const DevBatch &B, const DevModel *models, const int4 *groups,
                   cudaStream_t st) {
     if (n_groups == 0 || n_chains == 0) return;
     const int nb = (n_groups + kMlWarps - 1) / kMlWarps;
-    if (minb == 8) k_dp_ml<8><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, n_groups);
-    else if (minb == 5) k_dp_ml<5><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, n_groups);
-    else k_dp_ml<6><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, n_groups);
+    if (minb == 6) k_dp_ml<6, 64><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, n_groups);         // 80 registers, 24 warps / SM
+    else if (minb == 10) k_dp_ml<10, 64><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, n_groups);  // 48 registers, 40 warps / SM
+    else k_dp_ml<8, 64><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, n_groups);                   // 64 registers, 32 warps / SM
     k_chain_best<<<(n_chains * 32 + 127) / 128, 128, 0, st>>>(B, n_chains);
 }
 // PGPU_DP_VERIFY: element-wise comparison of two DP results (score, traceback, overlap frame)
