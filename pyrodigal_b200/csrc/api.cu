@@ -83,7 +83,7 @@ struct pgpu_ctx {
     size_t ws_limit = 0;
     cudaEvent_t ev[16];
     int64_t launches = 0;
-    int dp_ml_minb = 8;        // k_dp_ml register budget: min CTAs/SM 5, 6 or 8 (PGPU_DP_ML_MINB); 8 = 64 registers, 32 warps / SM
+    int dp_ml_minb = 6;        // k_dp_ml register budget: min CTAs/SM 6, 8 or 10 (PGPU_DP_ML_MINB); 6 = 78 registers, no spills, 24 warps / SM
     int extract_algo = 2;      // 2: bit-parallel extraction (k_codon_bits + k_extract_b), 1: warp-cooperative k_extract_w
                                // (PGPU_EXTRACT_ALGO; batches with N-run masks always use 1)
     int final_algo = 2;        // meta mode without node arrays: 2 = final scoring pass over the genes' ORFs only,
@@ -792,14 +792,32 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
             ctx->launches++;
         }
     }
-    B.cscore = pool.alloc<double>(total_cn); B.sscore = pool.alloc<double>(total_cn);
-    B.rscore = pool.alloc<double>(total_cn); B.uscore = pool.alloc<double>(total_cn);
-    B.tscore = pool.alloc<double>(total_cn);
+    // Meta mode scores every (contig, model) chain "lean": per chain-node only the raw coding score, cs = cscore + sscore
+    // and (sparse) the penalty of touching starts are kept; the winner of every contig is scored in full, into one
+    // slot per contig, right before the traceback (launch_trace).  Single mode / operators keep every score.
+    const bool lean = meta && plan.stage >= 3;
+    // slot per contig of the passes that score one chain per contig (winner pass, final pass): the largest extraction
+    std::vector<int64_t> gene_off(n + 1, 0), fin_coff(n + 1, 0);
+    for (int c = 0; c < n; c++) {
+        int mx = 0;
+        for (int e = contig_ext_begin[c]; e < contig_ext_begin[c + 1]; e++) mx = std::max(mx, exts[e].nn);
+        gene_off[c + 1] = gene_off[c] + mx / 2 + 1;   // a gene ends at a distinct STOP node: nn / 2 + 1 bounds the genes
+        fin_coff[c + 1] = fin_coff[c] + mx;
+    }
+    const int64_t ftot = fin_coff[n];
+    B.cscore = pool.alloc<double>(total_cn);
+    if (!lean) {
+        B.sscore = pool.alloc<double>(total_cn);
+        B.rscore = pool.alloc<double>(total_cn); B.uscore = pool.alloc<double>(total_cn);
+        B.tscore = pool.alloc<double>(total_cn);
+        B.rbs = pool.alloc<uint8_t>(2 * (size_t)total_cn + 16);
+    } else {
+        B.rupen = pool.alloc<double>(total_il + 64);
+    }
     // interleaved arrays: total_il elements (blocks padded to even sizes) + slack for the bulk copies of the last rows
     B.cs = pool.alloc<double>(total_il + 64);
     B.opv = pool.alloc<double>(3 * (size_t)total_il + 64);
     B.star_ptr = pool.alloc<int32_t>(3 * (size_t)total_il + 64);
-    B.rbs = pool.alloc<uint8_t>(2 * (size_t)total_cn + 16);
     B.score = pool.alloc<double>(total_il + 64);
     B.traceb = pool.alloc<int32_t>(total_il + 64);
     B.ov_mark = pool.alloc<int8_t>(total_il + 64);
@@ -814,11 +832,12 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
             B.dp_fmj = pool.alloc<int32_t>(total_il + 64);
         }
     }
-    int32_t *d_tracef = pool.alloc<int32_t>(total_cn);
-    uint8_t *d_elim = pool.alloc<uint8_t>(total_cn + 16, true);
+    const int64_t trace_cn = lean ? ftot : total_cn;   // forward pointers / elimination flags: winner slots or every chain
+    int32_t *d_tracef = pool.alloc<int32_t>(trace_cn);
+    uint8_t *d_elim = pool.alloc<uint8_t>(trace_cn + 16, true);
     MotifOut *d_mot_main = (!meta) ? pool.alloc<MotifOut>(total_cn) : nullptr;
     if (pool.failed) return PGPU_ENOMEM;
-    if (total_cn) CK(cudaMemsetAsync(d_tracef, 0xff, total_cn * sizeof(int32_t), st));
+    if (trace_cn) CK(cudaMemsetAsync(d_tracef, 0xff, trace_cn * sizeof(int32_t), st));
     {
         int32_t *tab = pool.alloc<int32_t>((size_t)total_cn / 128 + 2);
         if (pool.failed) return PGPU_ENOMEM;
@@ -829,7 +848,8 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     tev("chain alloc/upload");
     launch_coding(B, ctx->d_models, n_chains, total_cn, n_ext, total_nodes, st);
     tev("k_coding_orf");
-    launch_start_score(B, ctx->d_models, n_chains, total_cn, ro, d_mot_main, st);
+    if (lean) launch_start_score_lean(B, ctx->d_models, n_ext, total_nodes, ro, st);
+    else launch_start_score(B, ctx->d_models, n_chains, total_cn, ro, d_mot_main, st);
     tev("k_start_score");
     ctx->launches += 2;
     int e_score = mark();
@@ -857,14 +877,6 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return chains[a].nn > chains[b].nn; });
     int32_t *d_order = pool.upload(order);
     int32_t *d_ccb = pool.upload(contig_chain_begin);
-    // gene buffers: a gene ends at a distinct STOP node, so nn/2+1 bounds the genes of any chain
-    std::vector<int64_t> gene_off(n + 1, 0), fin_coff(n + 1, 0);
-    for (int c = 0; c < n; c++) {
-        int mx = 0;
-        for (int e = contig_ext_begin[c]; e < contig_ext_begin[c + 1]; e++) mx = std::max(mx, exts[e].nn);
-        gene_off[c + 1] = gene_off[c] + mx / 2 + 1;
-        fin_coff[c + 1] = fin_coff[c] + mx;
-    }
     pgpu_gene *d_genes = pool.alloc<pgpu_gene>(gene_off[n]);
     pgpu_gene *d_genes_raw = pool.alloc<pgpu_gene>(gene_off[n]);
     int64_t *d_gene_off = pool.upload(gene_off);
@@ -941,8 +953,40 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     tev("k_dp");
     ctx->launches++;
     int e_dp = mark();
-    launch_trace(B, ctx->d_models, n, d_ccb, d_tracef, d_elim, d_genes, d_genes_raw, d_gene_off, gene_off[n], d_summ,
-                 d_winner_chain, meta ? 1 : 0, opts.max_overlap, st);
+    // one-chain-per-contig passes of meta mode (winner pass before the traceback, final pass after it): their own
+    // chain-node index space (one slot per contig) and score arrays, shared by the two passes
+    DevBatch F = B;
+    ChainInfo *d_fin = nullptr, *d_win = nullptr;
+    int64_t *d_fin_coff = nullptr;
+    MotifOut *d_mot = nullptr;
+    if (meta) {
+        d_fin = pool.alloc<ChainInfo>(n);
+        d_win = pool.alloc<ChainInfo>(n);
+        d_fin_coff = pool.upload(fin_coff);
+        F.chains = d_fin;
+        F.blk_chain = nullptr;   // its own chain-node index space
+        F.cs = nullptr; F.rupen = nullptr;
+        F.cscore = pool.alloc<double>(ftot); F.sscore = pool.alloc<double>(ftot); F.rscore = pool.alloc<double>(ftot);
+        F.uscore = pool.alloc<double>(ftot); F.tscore = pool.alloc<double>(ftot);
+        F.rbs = pool.alloc<uint8_t>(2 * (size_t)ftot + 16);
+        F.ext_chains = nullptr;  // one chain per contig: the per-chain kernels
+        F.orf_toff = nullptr;
+        d_mot = pool.alloc<MotifOut>(ftot);
+        if (pool.failed) return PGPU_ENOMEM;
+    }
+    if (lean) {
+        // winner pass: the winner's chain with its own first_pass flag, raw coding scores taken from the main pass
+        DevBatch Wb = F;
+        Wb.chains = d_win;
+        Wb.cscore_in = B.cscore;
+        launch_trace(B, ctx->d_models, n, d_ccb, d_tracef, d_elim, d_genes, d_genes_raw, d_gene_off, gene_off[n], d_summ,
+                     d_winner_chain, 1, opts.max_overlap, &Wb,
+                     [&]() { launch_start_score(Wb, ctx->d_models, n, ftot, ro, nullptr, st); }, d_fin_coff, st);
+        ctx->launches += 2;
+    } else {
+        launch_trace(B, ctx->d_models, n, d_ccb, d_tracef, d_elim, d_genes, d_genes_raw, d_gene_off, gene_off[n], d_summ,
+                     d_winner_chain, meta ? 1 : 0, opts.max_overlap, nullptr, nullptr, nullptr, st);
+    }
     ctx->launches += 3;
     tev("k_trace");
     int e_trace = mark();
@@ -954,24 +998,11 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     std::vector<int64_t> node_out_off(n + 1, 0);
     if (meta) {
         // re-score the winner's nodes as a fresh first pass (lib.pyx:5380-5394)
-        DevBatch F = B;
-        ChainInfo *d_fin = pool.alloc<ChainInfo>(n);
-        int64_t *d_fin_coff = pool.upload(fin_coff);
-        const int64_t ftot = fin_coff[n];
-        F.chains = d_fin;
-        F.blk_chain = nullptr;   // the final pass has its own chain-node index space
-        F.cs = nullptr;
-        F.cscore = pool.alloc<double>(ftot); F.sscore = pool.alloc<double>(ftot); F.rscore = pool.alloc<double>(ftot);
-        F.uscore = pool.alloc<double>(ftot); F.tscore = pool.alloc<double>(ftot);
-        F.rbs = pool.alloc<uint8_t>(2 * (size_t)ftot + 16);
-        MotifOut *d_mot = pool.alloc<MotifOut>(ftot);
         d_nodes = pool.alloc<pgpu_node>(ftot);
         if (pool.failed) return PGPU_ENOMEM;
         launch_build_final_chains(B, n, d_winner_chain, d_fin_coff, d_fin, st);
         // chains with nn == 0 keep coff monotone, so the chain search inside the kernels stays valid; the
-        // unused tail of every contig's slot is never touched because kernels index by chain, but the flat
-        // index space must be dense: use per-contig capacity as the chain length for the search only.
-        F.ext_chains = nullptr;  // final pass: one chain per contig, use the per-chain kernel
+        // unused tail of every contig's slot is never touched because kernels index by chain
         if (opts.want_nodes || ctx->final_algo == 1) {
             launch_score_chains(F, ctx->d_models, n, ftot, ro, d_mot, n_ext, total_nodes, st);
             launch_pack_nodes(F, n, ftot, d_mot, nullptr, nullptr, 0, d_nodes, st);

@@ -110,6 +110,7 @@ struct ChainInfo {
     int64_t ioff;
     int32_t istride;
     int32_t lane;        // position among the chains of the extraction
+    int64_t coff_in;     // winner pass of meta mode: chain-node offset of this chain in the MAIN pass (raw coding scores)
 };
 
 // element i of an interleaved per-chain-node array (see ChainInfo::ioff)
@@ -168,7 +169,10 @@ struct DevBatch {
     // chains
     ChainInfo *chains;
     double *cscore, *sscore, *rscore, *uscore, *tscore;  // per chain-node
-    double *cs;           // per chain-node: cscore + sscore as one array (main pass of find_genes; nullptr otherwise)
+    double *cs;           // per chain-node, interleaved: cscore + sscore as one array (main pass of find_genes; nullptr otherwise)
+    double *rupen;        // lean main pass of meta mode (interleaved, sparse): what _intergenic_mod_same subtracts for a start
+                          // that touches another node; nullptr = read rscore / uscore
+    const double *cscore_in;  // winner pass of meta mode: the raw coding scores of the main pass (at ChainInfo::coff_in)
     double *opv;          // [3 * chain-node] operon values (cs[n3] + igm) for STOP nodes
     double *gcb;          // training DP: bias . gc_score per chain-node (only final == 0)
     int32_t *star_ptr;    // [3 * chain-node]

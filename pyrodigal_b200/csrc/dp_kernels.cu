@@ -17,6 +17,7 @@
 //  * per step: lanes stride over admissible predecessors, warp-shuffle arg-max, one __syncthreads.
 //  * doubles everywhere, no FMA contraction (-fmad=false): results are bit-identical to the reference.
 #include <cfloat>
+#include <functional>
 #include <cstring>
 
 #include "kernels.cuh"
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(kDpThreads) k_dp(DevBatch B, const DevModel *_
     const double *__restrict__ sscore = B.sscore + C.coff;
     // interleaved arrays (ChainInfo::ioff): node j at j * S (3-vectors: S3 * j + f)
     const int64_t S = C.istride, S3 = 3 * S;
+    const double *__restrict__ csum = B.cs ? B.cs + C.ioff : nullptr;   // cscore + sscore as one (interleaved) array
     const double *__restrict__ opv = B.opv + 3 * C.ioff;
     const double *__restrict__ gcb = FINAL ? nullptr : B.gcb + C.coff;
     const int32_t *__restrict__ star_ptr = B.star_ptr + 3 * C.ioff;
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(kDpThreads) k_dp(DevBatch B, const DevModel *_
                     }
                 }
             } else if (kind == K_RS) {
-                sc.cs = cscore[i] + sscore[i];
+                sc.cs = csum ? csum[i * S] : cscore[i] + sscore[i];
                 if (!FINAL) sc.gcb = gcb[i];
             }
             s_c[tid] = sc;
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(kDpThreads) k_dp(DevBatch B, const DevModel *_
                     if (sv_i >= nj) continue;
                     double sj; int tj; state(j, sj, tj);
                     double term;
-                    if (FINAL) term = cscore[j] + sscore[j];
+                    if (FINAL) term = csum ? csum[j * S] : cscore[j] + sscore[j];
                     else term = ((double)(ndx_i + 2 - nj + 1)) * gcb[j];
                     cand_take(best, sj + term, j, nj, -1);
                 }
@@ -412,6 +414,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
     const double *__restrict__ sscore = B.sscore + C.coff;
     // interleaved arrays (ChainInfo::ioff): node j at j * S (3-vectors: S3 * j + f)
     const int64_t S = C.istride, S3 = 3 * S;
+    const double *__restrict__ csum = B.cs ? B.cs + C.ioff : nullptr;   // cscore + sscore as one (interleaved) array
     const double *__restrict__ opv = B.opv + 3 * C.ioff;
     const int32_t *__restrict__ star_ptr = B.star_ptr + 3 * C.ioff;
     const Strided<double> score{B.score + C.ioff, S};       // written and re-read by this warp: no read-only path
@@ -477,7 +480,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
           const int kind = cls_kind(k.cls);
           const int4 dx = dqx[i];
           k.x = dx.x; k.y = dx.y; k.z = dx.z; k.w = dx.w;
-          k.cs = (kind == K_FS || kind == K_RS) ? cscore[i] + sscore[i] : 0.0;
+          k.cs = (kind == K_FS || kind == K_RS) ? (csum ? csum[i * S] : cscore[i] + sscore[i]) : 0.0;
           k.sp0 = k.sp1 = k.sp2 = -1;
           k.n3n0 = k.n3n1 = k.n3n2 = k.n3s0 = k.n3s1 = k.n3s2 = 0;
           k.op0 = k.op1 = k.op2 = 0.0;
@@ -1254,13 +1257,15 @@ struct TraceArgs {
     int32_t *winner_chain;              // [n_contigs] chain index of the winner or -1
     int meta;
     int max_overlap;
+    // Lean main pass of meta mode: only the winner's chain has been scored in full, into arrays of its own (one slot per
+    // contig).  wchains[c] is the winner's chain with coff = its slot (ChainInfo::coff_in = its offset in the main
+    // pass); the score arrays below, tracef and elim are indexed through it.  nullptr: everything lives in B at C.coff.
+    const ChainInfo *wchains;
+    double *cscore, *sscore, *rscore, *uscore, *tscore;
 };
 
-__global__ void __launch_bounds__(64) k_trace(DevBatch B, const DevModel *__restrict__ models, int n_contigs,
-                                               TraceArgs A) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_contigs) return;
-    // ---- winner: strict ">" from -100 in bin order, so the lowest bin wins ties (lib.pyx:5331,5364) ----
+// meta mode: the winner = strict ">" from -100 in bin order, so the lowest bin wins ties (lib.pyx:5331,5364)
+__device__ __forceinline__ int pick_winner(const DevBatch &B, const TraceArgs &A, int c) {
     int win = -1;
     double max_score = -100.0;
     for (int k = A.contig_chain_begin[c]; k < A.contig_chain_begin[c + 1]; k++) {
@@ -1271,6 +1276,28 @@ __global__ void __launch_bounds__(64) k_trace(DevBatch B, const DevModel *__rest
             win = k;  // single mode: exactly one chain, kept even when no path exists
         }
     }
+    return win;
+}
+
+// lean main pass: pick the winners first and list their chains for the full scoring pass that precedes the traceback
+__global__ void __launch_bounds__(128) k_winner(DevBatch B, int n_contigs, TraceArgs A, const int64_t *__restrict__ slot_off,
+                                                 ChainInfo *__restrict__ wchains) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_contigs) return;
+    const int win = pick_winner(B, A, c);
+    A.winner_chain[c] = win;
+    ChainInfo W;
+    if (win >= 0) { W = B.chains[win]; W.coff_in = W.coff; }
+    else { W = ChainInfo{}; W.contig = c; W.nn = 0; W.istride = 1; }
+    W.coff = slot_off[c];
+    wchains[c] = W;
+}
+
+__global__ void __launch_bounds__(64) k_trace(DevBatch B, const DevModel *__restrict__ models, int n_contigs,
+                                               TraceArgs A) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_contigs) return;
+    const int win = A.wchains ? A.winner_chain[c] : pick_winner(B, A, c);
     pgpu_contig_summary S = A.summary[c];
     S.n_genes = 0; S.n_nodes = 0; S.winner = -1; S.ipath = -1; S.score = 0.0;
     A.winner_chain[c] = win;
@@ -1282,11 +1309,13 @@ __global__ void __launch_bounds__(64) k_trace(DevBatch B, const DevModel *__rest
     S.winner = C.model; S.n_nodes = nn; S.ipath = ipath; S.score = ipath >= 0 ? B.chain_score[win] : 0.0;
     NodeRef N;
     N.ndx = B.ndx + C.node_off; N.sv = B.stop_val + C.node_off; N.cls = B.cls + C.node_off;
-    N.cscore = B.cscore + C.coff; N.sscore = B.sscore + C.coff; N.rscore = B.rscore + C.coff;
-    N.uscore = B.uscore + C.coff; N.tscore = B.tscore + C.coff;
-    N.traceb = Strided<int32_t>{B.traceb + C.ioff, C.istride}; N.tracef = A.tracef + C.coff;
+    const int64_t so = A.wchains ? A.wchains[c].coff : C.coff;   // where this chain's full scores / tracef / elim live
+    N.cscore = (A.wchains ? A.cscore : B.cscore) + so; N.sscore = (A.wchains ? A.sscore : B.sscore) + so;
+    N.rscore = (A.wchains ? A.rscore : B.rscore) + so; N.uscore = (A.wchains ? A.uscore : B.uscore) + so;
+    N.tscore = (A.wchains ? A.tscore : B.tscore) + so;
+    N.traceb = Strided<int32_t>{B.traceb + C.ioff, C.istride}; N.tracef = A.tracef + so;
     N.star_ptr = B.star_ptr + 3 * C.ioff; N.s3 = 3 * (int64_t)C.istride;
-    N.ov_mark = Strided<int8_t>{B.ov_mark + C.ioff, C.istride}; N.elim = A.elim + C.coff;
+    N.ov_mark = Strided<int8_t>{B.ov_mark + C.ioff, C.istride}; N.elim = A.elim + so;
     if (nn == 0) { A.summary[c] = S; return; }
 
     // the reference untangles overlaps from the arg-max node even when that node has no traceback
@@ -1393,8 +1422,10 @@ __global__ void __launch_bounds__(128) k_tweak(DevBatch B, const DevModel *__res
     const int nn = C.nn;
     NodeRef N;
     N.ndx = B.ndx + C.node_off; N.sv = B.stop_val + C.node_off; N.cls = B.cls + C.node_off;
-    N.cscore = B.cscore + C.coff; N.sscore = B.sscore + C.coff; N.rscore = B.rscore + C.coff;
-    N.uscore = B.uscore + C.coff; N.tscore = B.tscore + C.coff;
+    const int64_t so = A.wchains ? A.wchains[c].coff : C.coff;
+    N.cscore = (A.wchains ? A.cscore : B.cscore) + so; N.sscore = (A.wchains ? A.sscore : B.sscore) + so;
+    N.rscore = (A.wchains ? A.rscore : B.rscore) + so; N.uscore = (A.wchains ? A.uscore : B.uscore) + so;
+    N.tscore = (A.wchains ? A.tscore : B.tscore) + so;
     N.traceb = Strided<int32_t>{nullptr, 1}; N.tracef = nullptr; N.star_ptr = nullptr; N.s3 = 3;
     N.ov_mark = Strided<int8_t>{nullptr, 1}; N.elim = nullptr;
     const pgpu_gene *og = orig + A.gene_off[c];   // untouched genes (Genes._extract)
@@ -1652,9 +1683,18 @@ void launch_dp_compare(const double *sa, const double *sb, const int32_t *ta, co
 void launch_trace(const DevBatch &B, const DevModel *models, int n_contigs, const int32_t *contig_chain_begin,
                   int32_t *tracef, uint8_t *elim, pgpu_gene *genes, pgpu_gene *genes_raw, const int64_t *gene_off,
                   int64_t total_gene_slots, pgpu_contig_summary *summary, int32_t *winner_chain, int meta, int max_overlap,
-                  cudaStream_t st) {
+                  const DevBatch *W, const std::function<void()> &score_winners, const int64_t *slot_off, cudaStream_t st) {
     if (n_contigs == 0) return;
-    TraceArgs A = {contig_chain_begin, tracef, elim, genes, genes_raw, gene_off, summary, winner_chain, meta, max_overlap};
+    TraceArgs A = {contig_chain_begin, tracef, elim, genes, genes_raw, gene_off, summary, winner_chain, meta, max_overlap,
+                   nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (W) {
+        // lean main pass: winners first, then their chains are scored in full (W: the batch view of that pass, its chain
+        // list is filled here), then the traceback reads those scores
+        k_winner<<<(n_contigs + 127) / 128, 128, 0, st>>>(B, n_contigs, A, slot_off, W->chains);
+        score_winners();
+        A.wchains = W->chains;
+        A.cscore = W->cscore; A.sscore = W->sscore; A.rscore = W->rscore; A.uscore = W->uscore; A.tscore = W->tscore;
+    }
     k_trace<<<(n_contigs + 63) / 64, 64, 0, st>>>(B, models, n_contigs, A);
     if (total_gene_slots > 0) {
         const unsigned nb = (unsigned)((total_gene_slots + 127) / 128);

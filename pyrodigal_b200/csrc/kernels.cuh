@@ -1,5 +1,6 @@
 // kernels.cuh -- launch wrappers shared between the translation units of libpyrodigal_b200.so
 #pragma once
+#include <functional>
 #include "common.cuh"
 #include "train_device.cuh"
 
@@ -29,6 +30,7 @@ void launch_coding(const DevBatch &B, const DevModel *models, int n_chains, int6
                    cudaStream_t st);
 void launch_start_score(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o, void *mot_out,
                         cudaStream_t st);
+void launch_start_score_lean(const DevBatch &B, const DevModel *models, int n_ext, int total_nodes, RunOpts o, cudaStream_t st);
 void launch_overlap(const DevBatch &B, const DevModel *models, int n_chains, int64_t total_chain_nodes, int64_t total_il,
                     int n_ext, RunOpts o, int flag, cudaStream_t st);
 void launch_opv(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, cudaStream_t st);
@@ -45,7 +47,7 @@ void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, 
 void launch_trace(const DevBatch &B, const DevModel *models, int n_contigs, const int32_t *contig_chain_begin,
                   int32_t *tracef, uint8_t *elim, pgpu_gene *genes, pgpu_gene *genes_raw, const int64_t *gene_off,
                   int64_t total_gene_slots, pgpu_contig_summary *summary, int32_t *winner_chain, int meta, int max_overlap,
-                  cudaStream_t st);
+                  const DevBatch *W, const std::function<void()> &score_winners, const int64_t *slot_off, cudaStream_t st);
 void launch_pack_nodes(const DevBatch &B, int n_chains, int64_t total, const void *mot, const int32_t *tracef,
                        const uint8_t *elim, int dp_state, pgpu_node *out, cudaStream_t st);
 void launch_shine_dalgarno(const DevBatch &B, const DevModel *models, int model, int pos, int start, int strand, int exact,

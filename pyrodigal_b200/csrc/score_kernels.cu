@@ -474,12 +474,41 @@ __global__ void __launch_bounds__(32 * kOrfWarps, MINB) k_coding_orf(DevBatch B,
 // start scoring: RBS / upstream motif / type / upstream composition / penalties (lib.pyx:2331-2487)
 // --------------------------------------------------------------------------------------------------
 
-// node i of chain C (chain-node g = C.coff + i)
-__device__ __forceinline__ void start_score_node(const DevBatch &B, const DevModel *__restrict__ models, const ChainInfo &C,
-                                                 int64_t g, int i, RunOpts o, MotifOut *__restrict__ mot_out) {
+// What scoring a start needs from the node itself (model independent): loaded once per node and reused for every chain
+// (model) of the extraction by the main pass of meta mode.
+struct StartNode {
+    int c, ndx, stop_val, cc;   // cls byte, position, stop position, codon byte at the stop
+    uint32_t bits;              // upstream A/G pattern (SD search)
+    uint64_t U, pc;             // packed upstream bases (motif search, composition)
+    bool touch;                 // another node lies within 2 bp: _intergenic_mod may read this start's rbs / upstream
+                                // scores (_connection.h:60-67: ndx1 + 2 == ndx2 || ndx1 == ndx2 + 1)
+};
+__device__ __forceinline__ void load_start_node(const DevBatch &B, int node_off, int64_t doff, int nn, int i, StartNode &N) {
+    N.c = B.cls[node_off + i];
+    N.ndx = B.ndx[node_off + i];
+    N.stop_val = B.stop_val[node_off + i];
+    N.bits = B.sdbits[node_off + i];
+    N.U = B.umot[node_off + i];
+    N.pc = B.upc[node_off + i];
+    const uint8_t *__restrict__ cod = B.cod + doff;
+    N.cc = cls_is_stop(N.c) ? 0 : ((N.c & CLS_REV) ? cod[N.stop_val - 2] : cod[N.stop_val]);
+    N.touch = (i > 0 && B.ndx[node_off + i - 1] >= N.ndx - 2) || (i + 1 < nn && B.ndx[node_off + i + 1] <= N.ndx + 2);
+}
+
+// node i of chain C.  FULL pass (LEAN = false): every score of the node is written at chain-node g = C.coff + i (plus cs,
+// interleaved, when the batch has it); the raw coding score is read from cs_in[g_in].  LEAN pass (the main pass of meta
+// mode, every (contig, model) chain): only what the chains that do NOT win are ever asked for is written -- cs =
+// cscore + sscore of the starts (record_overlapping_starts, the DP) and, for starts that touch another node, the
+// rbs / upstream penalty _intergenic_mod subtracts (`rupen`).  The winner's chain is scored again in full before the
+// traceback (api.cu); that is 8 B instead of 54 B written per chain-node.
+template <bool LEAN>
+__device__ __forceinline__ void start_score_eval(const DevBatch &B, const DevModel *__restrict__ models, const ChainInfo &C,
+                                                 const StartNode &N, int64_t g, int i, const double *__restrict__ cs_in,
+                                                 int64_t g_in, RunOpts o, MotifOut *__restrict__ mot_out) {
     const uint8_t *__restrict__ cls = B.cls + C.node_off;
-    const int c = cls[i];
+    const int c = N.c;
     if (cls_is_stop(c)) {
+        if (LEAN) return;   // nothing reads the scores of a STOP node of a chain that is not the winner
         // STOP nodes keep the reset state (node.c:176-197)
         B.cscore[g] = 0.0; B.sscore[g] = 0.0; B.rscore[g] = 0.0; B.uscore[g] = 0.0; B.tscore[g] = 0.0;
         if (B.cs) B.cs[C.ioff + (int64_t)i * C.istride] = 0.0;
@@ -488,11 +517,8 @@ __device__ __forceinline__ void start_score_node(const DevBatch &B, const DevMod
         return;
     }
     const DevModel &M = models[C.model];
-    const int32_t *__restrict__ ndxa = B.ndx + C.node_off;
     const int32_t *__restrict__ sva = B.stop_val + C.node_off;
-    const uint8_t *__restrict__ d = B.digits + C.doff;
-    const uint8_t *__restrict__ cod = B.cod + C.doff;
-    const int slen = C.slen, nn = C.nn, ndx = ndxa[i], stop_val = sva[i];
+    const int slen = C.slen, nn = C.nn, ndx = N.ndx, stop_val = N.stop_val;
     const bool rev = c & CLS_REV;
     const int type = c & CLS_TYPE;
     const int edge_mask_now = C.first_pass ? CLS_EDGE : (CLS_EDGE | CLS_CONV);
@@ -500,11 +526,11 @@ __device__ __forceinline__ void start_score_node(const DevBatch &B, const DevMod
     const int start = rev ? slen - 1 - ndx : ndx;
     const double st_wt = M.st_wt;
     // issue every independent load up front: the kernel is latency bound
-    const uint32_t pre_bits = B.sdbits[C.node_off + i];
-    const uint64_t pre_U = B.umot[C.node_off + i];
-    const uint64_t pre_pc = B.upc[C.node_off + i];
-    const double pre_cscore = B.cscore[g];
-    const int pre_cc = rev ? cod[stop_val - 2] : cod[stop_val];
+    const uint32_t pre_bits = N.bits;
+    const uint64_t pre_U = N.U;
+    const uint64_t pre_pc = N.pc;
+    const double pre_cscore = cs_in[g_in];
+    const int pre_cc = N.cc;
 
     int rbs0 = 0, rbs1 = 0;
     MotifOut mot = {};
@@ -667,17 +693,55 @@ __device__ __forceinline__ void start_score_node(const DevBatch &B, const DevMod
     } else if (C.is_meta && cscore < 5.0 && orf_length < 120 && sscore < 0.0) {
         sscore -= st_wt;
     }
-    B.cscore[g] = cscore; B.sscore[g] = sscore; B.rscore[g] = rscore; B.uscore[g] = uscore; B.tscore[g] = tscore;
     // what record_overlapping_starts and the DP read of a start: one value, interleaved over the chains of the extraction
+    if (LEAN) {
+        const int64_t gi = C.ioff + (int64_t)i * C.istride;
+        B.cs[gi] = cscore + sscore;
+        if (N.touch) {   // _intergenic_mod_same (_connection.h:60-67), the part that depends on this start's scores
+            double r = 0.0;
+            if (rscore < 0) r -= rscore;
+            if (uscore < 0) r -= uscore;
+            B.rupen[gi] = r;
+        }
+        return;
+    }
+    B.cscore[g] = cscore; B.sscore[g] = sscore; B.rscore[g] = rscore; B.uscore[g] = uscore; B.tscore[g] = tscore;
     if (B.cs) B.cs[C.ioff + (int64_t)i * C.istride] = cscore + sscore;
     B.rbs[2 * g] = (uint8_t)rbs0; B.rbs[2 * g + 1] = (uint8_t)rbs1;
     if (mot_out) mot_out[g] = mot;
 }
 
-// BY_CLASS: the t-th thread of a chain takes the t-th node in class order (+starts, -starts, then the STOP nodes, through
-// the class-sorted index list) instead of node t, so that a warp holds either starts only -- no lanes idling on the
-// quarter of the nodes that are STOP nodes -- or STOP nodes only (which just write the reset state).
-template <bool BY_CLASS>
+// FULL pass of one node by one thread: node data loaded here
+__device__ __forceinline__ void start_score_node(const DevBatch &B, const DevModel *__restrict__ models, const ChainInfo &C,
+                                                 int64_t g, int i, RunOpts o, MotifOut *__restrict__ mot_out) {
+    StartNode N;
+    load_start_node(B, C.node_off, C.doff, C.nn, i, N);
+    // the raw coding score: in place, or (winner pass of meta mode) in the main pass' array at the chain's own offset
+    const double *cs_in = B.cscore_in ? B.cscore_in : B.cscore;
+    start_score_eval<false>(B, models, C, N, g, i, cs_in, B.cscore_in ? C.coff_in + i : g, o, mot_out);
+}
+
+// LEAN main pass of meta mode: one thread per extraction NODE, looping over the chains (models) of the extraction, so
+// that the node's own data is loaded once for all of them and a warp still holds one model at a time
+__global__ void __launch_bounds__(128) k_start_score_lean(DevBatch B, const DevModel *__restrict__ models, int n_ext,
+                                                           int total_nodes, RunOpts o) {
+    __shared__ int s_first;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    int e = ext_hint(B, n_ext, min(g, total_nodes - 1), blockIdx.x * blockDim.x, total_nodes, &s_first);
+    if (g >= total_nodes) return;
+    while (e + 1 < n_ext && B.exts[e + 1].node_off <= g) e++;
+    const int node_off = B.exts[e].node_off, nn = B.exts[e].nn, i = g - node_off;
+    StartNode N;
+    N.c = B.cls[g];
+    if (cls_is_stop(N.c)) return;
+    load_start_node(B, node_off, B.exts[e].doff, nn, i, N);
+    const int c1 = B.ext_chain_off[e + 1];
+    for (int c = B.ext_chain_off[e]; c < c1; c++) {
+        const ChainInfo C = B.chains[B.ext_chains[c]];
+        start_score_eval<true>(B, models, C, N, 0, i, B.cscore, C.coff + i, o, nullptr);
+    }
+}
+
 __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel *__restrict__ models, int n_chains,
                                                       int64_t total, RunOpts o, MotifOut *__restrict__ mot_out) {
     __shared__ int s_first;
@@ -686,20 +750,8 @@ __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel 
     if (g >= total) return;
     while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
     const ChainInfo C = B.chains[k];
-    int i = (int)(g - C.coff);
+    const int i = (int)(g - C.coff);
     if (i >= C.nn) return;
-    if (BY_CLASS) {
-        // class order of clist: [0, c1) +starts, [c1, c2) +STOPs, [c2, c3) -starts, [c3, nn) -STOPs
-        const int32_t *__restrict__ cbase = B.cbase + 4 * C.ext;
-        const int c1 = cbase[1], c2 = cbase[2], c3 = cbase[3];
-        const int n_fs = c1, n_rs = c3 - c2, n_fe = c2 - c1;
-        int p;
-        if (i < n_fs) p = i;
-        else if (i < n_fs + n_rs) p = c2 + (i - n_fs);
-        else if (i < n_fs + n_rs + n_fe) p = c1 + (i - n_fs - n_rs);
-        else p = c3 + (i - n_fs - n_rs - n_fe);
-        i = (B.clist + C.node_off)[p];
-    }
     start_score_node(B, models, C, C.coff + i, i, o, mot_out);
 }
 
@@ -751,14 +803,19 @@ __global__ void __launch_bounds__(128) k_start_score_genes(DevBatch B, const Dev
 // reference reads is the start, never the STOP) are needed only when the two nodes touch, so they are loaded on
 // demand: that case is rare and the two loads were half of this kernel's score traffic.
 __device__ __forceinline__ double igm_same(int ndx1, int strand1, int ndx2, int start, const double *__restrict__ rscore,
-                                           const double *__restrict__ uscore, const DevModel &M) {
+                                           const double *__restrict__ uscore, const double *__restrict__ rupen, int64_t S,
+                                           const DevModel &M) {
     const int dist = abs(ndx1 - ndx2);
     const bool overlap = ndx1 + 2 * strand1 >= ndx2;
     double r = 0.0;
     if (ndx1 + 2 == ndx2 || ndx1 == ndx2 + 1) {
-        const double rs = rscore[start], us = uscore[start];
-        if (rs < 0) r -= rs;
-        if (us < 0) r -= us;
+        if (rupen) {   // lean main pass: the two subtractions were done by the scoring pass (interleaved array)
+            r = rupen[start * S];
+        } else {
+            const double rs = rscore[start], us = uscore[start];
+            if (rs < 0) r -= rs;
+            if (us < 0) r -= us;
+        }
     }
     if (dist > 3 * kOperDist) r -= 0.15 * M.st_wt;
     else if ((dist <= kOperDist && !overlap) || dist * 4 < kOperDist) r += (2.0 - ((double)dist / kOperDist)) * 0.15 * M.st_wt;
@@ -777,12 +834,12 @@ __device__ __forceinline__ double operon_value(int cz, int z, int s, const uint8
                                                const int32_t *__restrict__ ndx, const double *__restrict__ cs, int64_t S,
                                                const double *__restrict__ cscore, const double *__restrict__ sscore,
                                                const double *__restrict__ rscore, const double *__restrict__ uscore,
-                                               const DevModel &M) {
+                                               const double *__restrict__ rupen, const DevModel &M) {
     const int cs_ = cls[s];
     const double base = cs_of(s, cs, S, cscore, sscore);
     if (((cz ^ cs_) & CLS_REV) != 0) return base + M.ig_neg;
-    return (cz & CLS_REV) ? base + igm_same(ndx[s], -1, ndx[z], s, rscore, uscore, M)
-                          : base + igm_same(ndx[z], 1, ndx[s], s, rscore, uscore, M);
+    return (cz & CLS_REV) ? base + igm_same(ndx[s], -1, ndx[z], s, rscore, uscore, rupen, S, M)
+                          : base + igm_same(ndx[z], 1, ndx[s], s, rscore, uscore, rupen, S, M);
 }
 
 // STOP node i of chain C: star_ptr[3] and the operon values (interleaved arrays, ChainInfo::ioff)
@@ -798,6 +855,7 @@ __device__ __forceinline__ void overlap_stop_node(const DevBatch &B, const DevMo
     const double *__restrict__ uscore = B.uscore + C.coff;
     const int64_t S = C.istride;
     const double *__restrict__ cs = B.cs ? B.cs + C.ioff : nullptr;
+    const double *__restrict__ rupen = B.rupen ? B.rupen + C.ioff : nullptr;
     int sp[3] = {-1, -1, -1};
     const int c = cls[i];
     if (cls_is_stop(c) && !(c & CLS_EDGE)) {
@@ -814,7 +872,7 @@ __device__ __forceinline__ void overlap_stop_node(const DevBatch &B, const DevMo
                 if (flag == 0) {
                     if (sp[f] == -1) sp[f] = j;
                 } else {
-                    const double sc = cs_of(j, cs, S, cscore, sscore) + igm_same(my, 1, ndx[j], j, rscore, uscore, M);
+                    const double sc = cs_of(j, cs, S, cscore, sscore) + igm_same(my, 1, ndx[j], j, rscore, uscore, rupen, S, M);
                     if (sc > max_sc) { sp[f] = j; max_sc = sc; }
                 }
             }
@@ -829,7 +887,7 @@ __device__ __forceinline__ void overlap_stop_node(const DevBatch &B, const DevMo
                 if (flag == 0) {
                     if (sp[f] == -1) sp[f] = j;
                 } else {
-                    const double sc = cs_of(j, cs, S, cscore, sscore) + igm_same(ndx[j], -1, my, j, rscore, uscore, M);
+                    const double sc = cs_of(j, cs, S, cscore, sscore) + igm_same(ndx[j], -1, my, j, rscore, uscore, rupen, S, M);
                     if (sc > max_sc) { sp[f] = j; max_sc = sc; }
                 }
             }
@@ -839,7 +897,7 @@ __device__ __forceinline__ void overlap_stop_node(const DevBatch &B, const DevMo
 #pragma unroll
     for (int f = 0; f < 3; f++) {
         B.star_ptr[3 * gi + f] = sp[f];
-        B.opv[3 * gi + f] = sp[f] == -1 ? 0.0 : operon_value(c, i, sp[f], cls, ndx, cs, S, cscore, sscore, rscore, uscore, M);
+        B.opv[3 * gi + f] = sp[f] == -1 ? 0.0 : operon_value(c, i, sp[f], cls, ndx, cs, S, cscore, sscore, rscore, uscore, rupen, M);
     }
 }
 
@@ -907,7 +965,7 @@ __global__ void __launch_bounds__(128) k_opv(DevBatch B, const DevModel *__restr
         const int s = B.star_ptr[3 * gi + f];
         B.opv[3 * gi + f] = (s < 0 || s >= C.nn || !cls_is_stop(c)) ? 0.0
             : operon_value(c, i, s, cls, B.ndx + C.node_off, nullptr, 1, B.cscore + C.coff, B.sscore + C.coff, B.rscore + C.coff,
-                           B.uscore + C.coff, models[C.model]);
+                           B.uscore + C.coff, nullptr, models[C.model]);
     }
 }
 
@@ -993,11 +1051,11 @@ void launch_coding(const DevBatch &B, const DevModel *models, int n_chains, int6
 void launch_start_score(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o, void *mot_out,
                         cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
-    static const bool by_class = getenv("PGPU_SCORE_BY_CLASS") && atoi(getenv("PGPU_SCORE_BY_CLASS")) != 0;  // A/B switch
-    if (by_class && B.clist && B.cbase)
-        k_start_score<true><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total, o, (MotifOut *)mot_out);
-    else
-        k_start_score<false><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total, o, (MotifOut *)mot_out);
+    k_start_score<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total, o, (MotifOut *)mot_out);
+}
+void launch_start_score_lean(const DevBatch &B, const DevModel *models, int n_ext, int total_nodes, RunOpts o, cudaStream_t st) {
+    if (n_ext == 0 || total_nodes == 0) return;
+    k_start_score_lean<<<(total_nodes + 127) / 128, 128, 0, st>>>(B, models, n_ext, total_nodes, o);
 }
 void launch_score_chains(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o,
                          void *mot_out, int n_ext, int total_nodes, cudaStream_t st) {
