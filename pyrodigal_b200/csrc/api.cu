@@ -848,7 +848,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     tev("chain alloc/upload");
     launch_coding(B, ctx->d_models, n_chains, total_cn, n_ext, total_nodes, st);
     tev("k_coding_orf");
-    if (lean) launch_start_score_lean(B, ctx->d_models, n_ext, total_nodes, ro, st);
+    if (lean) launch_start_score_lean(B, ctx->d_models, n_chains, total_cn, ro, st);
     else launch_start_score(B, ctx->d_models, n_chains, total_cn, ro, d_mot_main, st);
     tev("k_start_score");
     ctx->launches += 2;

@@ -30,7 +30,7 @@ void launch_coding(const DevBatch &B, const DevModel *models, int n_chains, int6
                    cudaStream_t st);
 void launch_start_score(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o, void *mot_out,
                         cudaStream_t st);
-void launch_start_score_lean(const DevBatch &B, const DevModel *models, int n_ext, int total_nodes, RunOpts o, cudaStream_t st);
+void launch_start_score_lean(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o, cudaStream_t st);
 void launch_overlap(const DevBatch &B, const DevModel *models, int n_chains, int64_t total_chain_nodes, int64_t total_il,
                     int n_ext, RunOpts o, int flag, cudaStream_t st);
 void launch_opv(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, cudaStream_t st);

@@ -474,8 +474,7 @@ __global__ void __launch_bounds__(32 * kOrfWarps, MINB) k_coding_orf(DevBatch B,
 // start scoring: RBS / upstream motif / type / upstream composition / penalties (lib.pyx:2331-2487)
 // --------------------------------------------------------------------------------------------------
 
-// What scoring a start needs from the node itself (model independent): loaded once per node and reused for every chain
-// (model) of the extraction by the main pass of meta mode.
+// What scoring a start needs from the node itself (model independent)
 struct StartNode {
     int c, ndx, stop_val, cc;   // cls byte, position, stop position, codon byte at the stop
     uint32_t bits;              // upstream A/G pattern (SD search)
@@ -721,25 +720,23 @@ __device__ __forceinline__ void start_score_node(const DevBatch &B, const DevMod
     start_score_eval<false>(B, models, C, N, g, i, cs_in, B.cscore_in ? C.coff_in + i : g, o, mot_out);
 }
 
-// LEAN main pass of meta mode: one thread per extraction NODE, looping over the chains (models) of the extraction, so
-// that the node's own data is loaded once for all of them and a warp still holds one model at a time
-__global__ void __launch_bounds__(128) k_start_score_lean(DevBatch B, const DevModel *__restrict__ models, int n_ext,
-                                                           int total_nodes, RunOpts o) {
+// LEAN main pass of meta mode: one thread per chain-node like the full pass (a warp = 32 consecutive nodes of one chain,
+// i.e. one model: the table lookups of a warp stay inside one model's tables)
+__global__ void __launch_bounds__(128) k_start_score_lean(DevBatch B, const DevModel *__restrict__ models, int n_chains,
+                                                           int64_t total, RunOpts o) {
     __shared__ int s_first;
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    int e = ext_hint(B, n_ext, min(g, total_nodes - 1), blockIdx.x * blockDim.x, total_nodes, &s_first);
-    if (g >= total_nodes) return;
-    while (e + 1 < n_ext && B.exts[e + 1].node_off <= g) e++;
-    const int node_off = B.exts[e].node_off, nn = B.exts[e].nn, i = g - node_off;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int k = chain_hint(B, n_chains, min(g, total - 1), total, &s_first);
+    if (g >= total) return;
+    while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
+    const ChainInfo C = B.chains[k];
+    const int i = (int)(g - C.coff);
+    if (i >= C.nn) return;
     StartNode N;
-    N.c = B.cls[g];
+    N.c = B.cls[C.node_off + i];
     if (cls_is_stop(N.c)) return;
-    load_start_node(B, node_off, B.exts[e].doff, nn, i, N);
-    const int c1 = B.ext_chain_off[e + 1];
-    for (int c = B.ext_chain_off[e]; c < c1; c++) {
-        const ChainInfo C = B.chains[B.ext_chains[c]];
-        start_score_eval<true>(B, models, C, N, 0, i, B.cscore, C.coff + i, o, nullptr);
-    }
+    load_start_node(B, C.node_off, C.doff, C.nn, i, N);
+    start_score_eval<true>(B, models, C, N, g, i, B.cscore, g, o, nullptr);
 }
 
 __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel *__restrict__ models, int n_chains,
@@ -1053,9 +1050,9 @@ void launch_start_score(const DevBatch &B, const DevModel *models, int n_chains,
     if (n_chains == 0 || total == 0) return;
     k_start_score<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total, o, (MotifOut *)mot_out);
 }
-void launch_start_score_lean(const DevBatch &B, const DevModel *models, int n_ext, int total_nodes, RunOpts o, cudaStream_t st) {
-    if (n_ext == 0 || total_nodes == 0) return;
-    k_start_score_lean<<<(total_nodes + 127) / 128, 128, 0, st>>>(B, models, n_ext, total_nodes, o);
+void launch_start_score_lean(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o, cudaStream_t st) {
+    if (n_chains == 0 || total == 0) return;
+    k_start_score_lean<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total, o);
 }
 void launch_score_chains(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o,
                          void *mot_out, int n_ext, int total_nodes, cudaStream_t st) {
