@@ -776,12 +776,21 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
             // (k_coding_orf, k_overlap_lanes): W lanes per STOP node for an extraction with L chains, nn / 2 + 1 slots
             std::vector<int64_t> toff(n_ext + 1, 0);
             std::vector<uint8_t> w(n_ext + 1, 32);
-            for (int e = 0; e < n_ext; e++) {
+            // order: by the first model of the extraction's chains (= by translation table and GC window: the models are
+            // sorted that way), so that concurrently resident warps share dicodon-table columns
+            std::vector<int32_t> perm(n_ext);
+            std::iota(perm.begin(), perm.end(), 0);
+            std::vector<int32_t> key(n_ext, 0);
+            for (int e = 0; e < n_ext; e++) if (eoff[e + 1] > eoff[e]) key[e] = ctx->h_models[chains[h_elist[eoff[e]]].model].col;
+            std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return key[a] < key[b]; });
+            for (int r = 0; r < n_ext; r++) {
+                const int e = perm[r];
                 const int L = eoff[e + 1] - eoff[e];
-                w[e] = (uint8_t)(L <= 4 ? 4 : L <= 8 ? 8 : L <= 16 ? 16 : 32);
-                const int64_t threads = L > 0 ? ((int64_t)exts[e].nn / 2 + 1) * w[e] : 0;
-                toff[e + 1] = toff[e] + ((threads + 31) & ~int64_t(31));
+                w[r] = (uint8_t)(L <= 4 ? 4 : L <= 8 ? 8 : L <= 16 ? 16 : 32);
+                const int64_t threads = L > 0 ? ((int64_t)exts[e].nn / 2 + 1) * w[r] : 0;
+                toff[r + 1] = toff[r] + ((threads + 31) & ~int64_t(31));
             }
+            B.orf_ext = pool.upload(perm);
             B.orf_threads = toff[n_ext];
             B.orf_toff = pool.upload(toff);
             B.orf_w = pool.upload(w);

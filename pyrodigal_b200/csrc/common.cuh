@@ -195,7 +195,9 @@ struct DevBatch {
     const int32_t *blk_ext;
     // grouped mapping of k_coding_orf (optional; nullptr = one warp per ORF): thread range of every extraction
     // (orf_toff[0..n_ext], multiples of 32), lanes per ORF (4 / 8 / 16 / 32), owner of every 256-thread block
-    const int64_t *orf_toff;
+    const int64_t *orf_toff;   // indexed by the position r of an extraction in the planned order
+    const int32_t *orf_ext;    // extraction at position r: extractions with the same model set are neighbours, so that the
+                               // warps resident on an SM read the same columns of the dicodon table (L1 locality)
     const uint8_t *orf_w;
     const int32_t *orf_blk;
     int64_t orf_threads;

@@ -335,10 +335,11 @@ __global__ void __launch_bounds__(32 * kOrfWarps, MINB) k_coding_orf(DevBatch B,
     if (GROUPED) {
         const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (gt >= B.orf_toff[n_ext]) return;
-        e = B.orf_blk[gt >> 8];
-        while (e + 1 < n_ext && B.orf_toff[e + 1] <= gt) e++;
-        W = B.orf_w[e];
-        const int local = (int)(gt - B.orf_toff[e]);
+        int r = B.orf_blk[gt >> 8];   // position in the planned order of the extractions (orf_ext: grouped by model set)
+        while (r + 1 < n_ext && B.orf_toff[r + 1] <= gt) r++;
+        W = B.orf_w[r];
+        const int local = (int)(gt - B.orf_toff[r]);
+        e = B.orf_ext[r];
         tl = local / W;
         lane = local % W;
     } else {
@@ -722,8 +723,9 @@ __device__ __forceinline__ void start_score_node(const DevBatch &B, const DevMod
 
 // LEAN main pass of meta mode: one thread per chain-node like the full pass (a warp = 32 consecutive nodes of one chain,
 // i.e. one model: the table lookups of a warp stay inside one model's tables)
-__global__ void __launch_bounds__(128) k_start_score_lean(DevBatch B, const DevModel *__restrict__ models, int n_chains,
-                                                           int64_t total, RunOpts o) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_start_score_lean(DevBatch B, const DevModel *__restrict__ models, int n_chains,
+                                                                 int64_t total, RunOpts o) {
     __shared__ int s_first;
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int k = chain_hint(B, n_chains, min(g, total - 1), total, &s_first);
@@ -926,10 +928,11 @@ __global__ void __launch_bounds__(256, 6) k_overlap_lanes(DevBatch B, const DevM
                                                         int flag) {
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gt >= B.orf_toff[n_ext]) return;
-    int e = B.orf_blk[gt >> 8];
-    while (e + 1 < n_ext && B.orf_toff[e + 1] <= gt) e++;
-    const int W = B.orf_w[e];
-    const int local = (int)(gt - B.orf_toff[e]);
+    int r = B.orf_blk[gt >> 8];
+    while (r + 1 < n_ext && B.orf_toff[r + 1] <= gt) r++;
+    const int W = B.orf_w[r];
+    const int local = (int)(gt - B.orf_toff[r]);
+    const int e = B.orf_ext[r];
     const int tl = local / W, lane = local % W;
     const int32_t *__restrict__ cbase = B.cbase + 4 * e;
     const ExtractInfo &X = B.exts[e];
@@ -1052,7 +1055,11 @@ void launch_start_score(const DevBatch &B, const DevModel *models, int n_chains,
 }
 void launch_start_score_lean(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o, cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
-    k_start_score_lean<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(B, models, n_chains, total, o);
+    static const int minb = getenv("PGPU_SCORE_MINB") ? atoi(getenv("PGPU_SCORE_MINB")) : 10;   // 10 = 48 registers, 40 warps / SM (measured: 17.6 ms vs 18.1 at 9, 18.6 at 12)
+    const unsigned nb = (unsigned)((total + 127) / 128);
+    if (minb == 12) k_start_score_lean<12><<<nb, 128, 0, st>>>(B, models, n_chains, total, o);
+    else if (minb == 10) k_start_score_lean<10><<<nb, 128, 0, st>>>(B, models, n_chains, total, o);
+    else k_start_score_lean<9><<<nb, 128, 0, st>>>(B, models, n_chains, total, o);
 }
 void launch_score_chains(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o,
                          void *mot_out, int n_ext, int total_nodes, cudaStream_t st) {
