@@ -647,8 +647,9 @@ def main():
     r = None
     e2e_steps = []
     gatherer = Gatherer() if (sharded and world > 1) else None
-    if gatherer is not None:   # one untimed gather: NCCL connections, pinned receive buffers
-        gatherer.submit(step_host())
+    if gatherer is not None:   # untimed pipelined steps: NCCL connections, the rotation of page-locked result / receive buffers
+        for _ in range(4):
+            gatherer.submit(step_host())
         gatherer.wait()
     ms_e2e, wall_e2e, res2 = timed(step_host, args.steps, e2e_steps, gatherer)
     st2 = res2.stats
@@ -683,6 +684,7 @@ def main():
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             out = run_py(); n_py = sum(len(g) for g in out); out = None
+            out = run_py(); out = None
             D.barrier()
             t0 = time.perf_counter()
             for _ in range(pe_steps):
@@ -740,6 +742,7 @@ def main():
                     "h2d_ms_per_step": [round(t["ms_h2d"], 2) for t in e2e_steps],   # the input copy alone, per timed step
                     "wall_ms_steps": [round(t["wall_ms"], 1) for t in e2e_steps],
                     "device_ms_steps": [round(t["ms_total_device"], 1) for t in e2e_steps],
+                    "host_ms_last_step": [round(x, 1) for x in st2["host_ms"]],
                     "api": "pgpu_train + pgpu_set_models + pgpu_find_genes_batch (C ABI, pinned host input)" if w.get("train")
                            else "pgpu_find_genes_batch (C ABI, pinned host input)"
                            + (" + distributed.gather_result (gene records of all ranks on rank 0, NCCL)" if gathered is not None else "")},

@@ -287,13 +287,30 @@ class Batch:
             pass
 
 
+class _ResultHandle:
+    """Owns the pgpu_result: freed when the last reference (the Result, or a numpy view of its buffers) goes away."""
+
+    def __init__(self, h):
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.pgpu_result_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 class Result:
-    """Owns a pgpu_result.  `summary`, `gene_off` and `stats` are read eagerly (small); `genes` and
-    `gene_nodes` are materialised on first use: zero-copy numpy views of the result's page-locked buffers when
-    the batch ran as one sub-batch (the views keep the Result alive), a concatenated copy otherwise."""
+    """A pgpu_result.  `summary`, `gene_off` and `stats` are read eagerly (small); `genes` and `gene_nodes` are
+    materialised on first use: zero-copy numpy views of the result's page-locked buffers when the batch ran as one
+    sub-batch, a concatenated copy otherwise.  The views keep the underlying pgpu_result alive through a handle object
+    -- not through this Result, which would form a reference cycle and leave the (large, page-locked) buffers to the
+    cyclic garbage collector."""
 
     def __init__(self, handle, ctx=None):
-        self.handle = handle
+        self._h = _ResultHandle(handle)
         self.ctx = ctx  # the result returns its pinned buffers to the context when freed: keep it alive
         self.n = lib.pgpu_result_num_contigs(handle)
         self.summary = np.zeros(self.n, dtype=SUMMARY_DTYPE)
@@ -306,6 +323,10 @@ class Result:
         lib.pgpu_result_stats(handle, C.byref(st))
         self.stats = st.as_dict()
 
+    @property
+    def handle(self):
+        return self._h.h if self._h is not None else None
+
     def _materialise(self):
         if self.handle is None:
             raise RuntimeError("result already freed")
@@ -317,7 +338,7 @@ class Result:
             assert cnt == ng and g0.value == 0
             gbuf = (C.c_char * (ng * GENE_DTYPE.itemsize)).from_address(pg.value)
             nbuf = (C.c_char * (2 * ng * NODE_DTYPE.itemsize)).from_address(pn.value)
-            gbuf._owner = nbuf._owner = self  # the buffers live as long as this Result
+            gbuf._owner = nbuf._owner = self._h  # the buffers live as long as any view of them
             self._genes = np.frombuffer(gbuf, dtype=GENE_DTYPE)
             self._gene_nodes = np.frombuffer(nbuf, dtype=NODE_DTYPE).reshape(ng, 2)
             self._genes.flags.writeable = self._gene_nodes.flags.writeable = False
@@ -349,12 +370,6 @@ class Result:
         return out
 
     def free(self):
-        if self.handle:
-            lib.pgpu_result_free(self.handle)
-            self.handle = None
-
-    def __del__(self):
-        try:
-            self.free()
-        except Exception:
-            pass
+        """drop this object's reference; the buffers are released once no view of them is left"""
+        self._genes = self._gene_nodes = None
+        self._h = None

@@ -56,7 +56,8 @@ struct PinnedPool {
     void release(PinnedBuf b) {
         if (!b.p) return;
         std::lock_guard<std::mutex> g(mu);
-        if (free_list.size() >= 6) {  // bound the pinned footprint: keep the larger buffers
+        if (free_list.size() >= 16) {  // bound the pinned footprint: keep the larger buffers (a caller that pipelines
+                                       // several results -- distributed.gather_result -- keeps three or four in rotation)
             int s = 0;
             for (int i = 1; i < (int)free_list.size(); i++) if (free_list[i].cap < free_list[s].cap) s = i;
             if (free_list[s].cap < b.cap) { cudaFreeHost(free_list[s].p); free_list[s] = b; }

@@ -17,6 +17,8 @@ the data path:
 torch is plumbing here (process group, device / pinned buffers); nothing in this module computes on genes.
 `runner` lets the tests drive the same code with another engine (the CUDA-on-CPU emulation of tests/emu) over gloo."""
 import heapq
+import os
+import time
 
 import numpy as np
 
@@ -201,40 +203,56 @@ def gather_result(local, ids, n_total, group=None, root=0, device=0):
     def as_bytes(a):
         return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1))
 
-    payload = [as_bytes(np.asarray(ids, dtype=np.int64)), as_bytes(local.summary)]
-    if ng:
-        payload += [as_bytes(local.genes), as_bytes(local.gene_nodes)]
+    S, G, N = _capi.SUMMARY_DTYPE.itemsize, _capi.GENE_DTYPE.itemsize, _capi.NODE_DTYPE.itemsize
+    trace = os.environ.get("PGPU_GATHER_TRACE") == "1"
+    t0 = time.perf_counter()
     if D.rank != root:
-        buf = torch.cat(payload) if len(payload) > 1 else payload[0]
+        # small header (contig ids + summaries) in one message, then the gene records and their node records straight
+        # from the result's page-locked buffers (asynchronous DMA to the device, then NCCL over NVLink)
+        pieces = [torch.cat([as_bytes(np.asarray(ids, dtype=np.int64)), as_bytes(local.summary)])]
+        if ng:
+            pieces += [as_bytes(local.genes), as_bytes(local.gene_nodes)]
+        for t in pieces:
+            if D.cuda:
+                t = t.to(dev, non_blocking=True)
+            if t.numel():
+                dist.send(t, dst=D.global_rank(root), group=group)
         if D.cuda:
-            buf = buf.to(dev, non_blocking=True)
-        if buf.numel():
-            dist.send(buf, dst=D.global_rank(root), group=group)
+            torch.cuda.current_stream(dev).synchronize()   # the result buffers may be recycled once this returns
+        if trace:
+            print(f"[gather rank {D.rank}] sent {sum(int(t.numel()) for t in pieces) / 1e6:.1f} MB in "
+                  f"{(time.perf_counter() - t0) * 1e3:.1f} ms", flush=True)
         return None
     parts, all_stats = [], [stats]
     _gather_seq[0] += 1
-    S, G, N = _capi.SUMMARY_DTYPE.itemsize, _capi.GENE_DTYPE.itemsize, _capi.NODE_DTYPE.itemsize
+
+    def receive(r, what, size):
+        buf = torch.empty(size, dtype=torch.uint8, device=dev)
+        if size:
+            dist.recv(buf, src=D.global_rank(r), group=group)
+        if D.cuda:   # one device -> host copy of what arrived over NVLink, into recycled page-locked memory
+            host = _pinned(("gather", r, what, _gather_seq[0] & 1), size, torch)
+            host[:size].copy_(buf)
+            return host[:size].numpy()
+        return buf.numpy()
+
     for r in range(D.world):
         nc, g = heads[r]
         if r == root:
             parts.append((np.asarray(ids, dtype=np.int64), local.summary, np.asarray(local.genes), np.asarray(local.gene_nodes)))
             continue
-        size = nc * (8 + S) + g * (G + 2 * N)
-        buf = torch.empty(size, dtype=torch.uint8, device=dev)
-        if size:
-            dist.recv(buf, src=D.global_rank(r), group=group)
-        if D.cuda:   # one device -> host copy of what arrived over NVLink, into recycled page-locked memory
-            host = _pinned(("gather", r, _gather_seq[0] & 1), size, torch)
-            host[:size].copy_(buf)
-            b = host[:size].numpy()
+        b = receive(r, "head", nc * (8 + S))
+        rid = b[:8 * nc].view(np.int64)
+        rsum = b[8 * nc:].view(_capi.SUMMARY_DTYPE)
+        if g:
+            rgen = receive(r, "genes", g * G).view(_capi.GENE_DTYPE)
+            rnod = receive(r, "nodes", 2 * g * N).view(_capi.NODE_DTYPE).reshape(g, 2)
         else:
-            b = buf.numpy()
-        o = 0
-        rid = b[o:o + 8 * nc].view(np.int64); o += 8 * nc
-        rsum = b[o:o + S * nc].view(_capi.SUMMARY_DTYPE); o += S * nc
-        rgen = b[o:o + G * g].view(_capi.GENE_DTYPE); o += G * g
-        rnod = b[o:o + 2 * N * g].view(_capi.NODE_DTYPE).reshape(g, 2)
+            rgen = np.zeros(0, dtype=_capi.GENE_DTYPE)
+            rnod = np.zeros((0, 2), dtype=_capi.NODE_DTYPE)
         parts.append((rid, rsum, rgen, rnod))
+    if trace:
+        print(f"[gather rank {D.rank}] received from {D.world - 1} ranks in {(time.perf_counter() - t0) * 1e3:.1f} ms", flush=True)
     return ShardedResult(parts, n_total, all_stats)
 
 
