@@ -98,8 +98,9 @@ struct pgpu_ctx {
     // Optional: host-input calls (pgpu_find_genes_batch) on large batches run as sub-batches on two worker threads /
     // streams ("lanes"), so that the H2D copy, the host planning gaps and the D2H of one hide under the kernels of the other.
     // Device-resident batches (pgpu_batch_run) stay on the single stream, so per-kernel timings remain well defined.
-    int lanes = 1;                         // PGPU_LANES=2 enables.  Off by default: on the 630 Mbp bench shard the two
-                                           // half-size pipelines interleave no faster than one (117 vs 122 ms per step)
+    int lanes = 2;                         // PGPU_LANES=1 disables.  Measured on the 630 Mbp bench shard (round 2): 98.8 ms per
+                                           // end-to-end step with two lanes against 105 ms with one (the 11 ms input copy of
+                                           // the second half hides under the kernels of the first)
     int64_t lane_min_bp = int64_t(64) << 20;   // smaller batches are not split (PGPU_LANE_MIN_BP)
     cudaStream_t lane_stream[2] = {nullptr, nullptr};
     cudaEvent_t lane_ev[2][16];
