@@ -126,22 +126,6 @@ def test_two_lanes_small(capi, monkeypatch):
     c1.close(); c2.close()
 
 
-@pytest.mark.parametrize("tt", [11, 4])
-def test_codon_table_variant_of_k_codon_bits(capi, monkeypatch, tt):
-    """PGPU_CODON_LUT=1: the byte-table variant of k_codon_bits extracts the same nodes"""
-    monkeypatch.setenv("PGPU_CODON_LUT", "1")
-    c = capi.Context(0)
-    c.set_models(R.bins_blob(), 50)
-    for length, gc, seed, nfrac, closed in ((40000, .5, 1, 0.0, False), (3001, .62, 3, 0.0, True), (20000, .45, 4, .002, False)):
-        seq = R.synth(length, gc, seed, n_frac=nfrac)
-        d, _, _ = orc.encode(seq)
-        want = orc.extract(d, tt, orc.make_opts(closed=closed))
-        got = c.extract_nodes(np.frombuffer(seq, np.uint8), tt, capi.make_opts(closed=closed))
-        for f in ("ndx", "stop_val", "strand", "type", "edge"):
-            assert np.array_equal(got[f], want[f]), (tt, length, f)
-    c.close()
-
-
 # ---- the Python mirror on top of the emulated library (pyrodigal_b200.lib with its ctypes binding swapped) ----
 @pytest.fixture()
 def emulated_lib(capi, monkeypatch):
@@ -205,4 +189,4 @@ def test_randomised_batches_against_the_oracle(monkeypatch):
 
 
 test_coding_score_lane_groups = G.test_coding_score_lane_groups
-test_dp_model_lane_kernel_packed_groups = G.test_dp_model_lane_kernel_packed_groups
+test_dp_model_lane_kernel_gc_sweep = G.test_dp_model_lane_kernel_gc_sweep

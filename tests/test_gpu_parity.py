@@ -484,11 +484,9 @@ def test_two_lane_host_batches_match_single_stream(capi, monkeypatch, many_parts
     ra.free(); rb.free(); r1.free(); c1.close(); c2.close()
 
 
-@pytest.mark.parametrize("groups", ["1", "0"])
-def test_coding_score_lane_groups(capi, monkeypatch, groups):
-    """k_coding_orf with 4 / 8 / 16 / 32 lanes per ORF (PGPU_CODING_GROUPS=1) and with a warp per ORF (=0), on contigs
+def test_coding_score_lane_groups(capi):
+    """k_coding_orf / k_overlap_lanes with 4 / 8 / 16 / 32 lanes per ORF (one lane per model of the extraction), on contigs
     whose GC content sweeps the whole range, so that extractions with 1 ... 27 models (both translation tables) occur"""
-    monkeypatch.setenv("PGPU_CODING_GROUPS", groups)
     c = capi.Context(0)
     c.set_models(R.bins_blob(), 50)
     seqs = [R.synth(2500 + 137 * k, 0.24 + 0.02 * k, 4100 + k) for k in range(27)]
@@ -510,10 +508,10 @@ def test_coding_score_lane_groups(capi, monkeypatch, groups):
     c.close()
 
 
-def test_dp_model_lane_kernel_packed_groups(capi, monkeypatch):
-    """PGPU_DP_ML_PACK=1: several extraction groups of few chains per warp; checked by the library's own
+def test_dp_model_lane_kernel_gc_sweep(capi, monkeypatch):
+    """k_dp_ml on extractions with 1 ... 27 chains (lanes), both register budgets: checked by the library's own
     PGPU_DP_VERIFY comparison with k_dp_dq on a GC sweep (1 ... 27 models per extraction) and against the oracle"""
-    monkeypatch.setenv("PGPU_DP_ML_PACK", "1")
+    monkeypatch.setenv("PGPU_DP_ML_MINB", "8")   # the 64-register instantiation; the default one runs everywhere else
     monkeypatch.setenv("PGPU_DP_VERIFY", "1")
     c = capi.Context(0)
     c.set_models(R.bins_blob(), 50)
