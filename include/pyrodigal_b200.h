@@ -124,6 +124,14 @@ int pgpu_num_models(const pgpu_ctx *ctx);
 int pgpu_timer_start(pgpu_ctx *ctx);
 int pgpu_timer_stop(pgpu_ctx *ctx, double *ms);
 
+/* Page-locked host memory for input buffers (cudaHostAlloc): a sequence buffer that lives in it is copied to the device
+ * by asynchronous DMA at link speed, and -- with two lanes -- the copy of one half of a batch overlaps the kernels of the
+ * other; a buffer in ordinary (pageable) memory is staged by the driver at roughly a third of that.  Used by the FASTA
+ * reader of the Python mirror (pyrodigal_b200/fasta.py; the reference's reader is tests/fasta.py:61-86 / cli.py:283-284).
+ * Returns NULL when the allocation fails (the caller falls back to ordinary memory). */
+void *pgpu_host_alloc(size_t bytes);
+void pgpu_host_free(void *p);
+
 /* Upper bound for the workspace the library may allocate on the device (bytes; 0 = default). */
 int pgpu_set_workspace_limit(pgpu_ctx *ctx, size_t bytes);
 

@@ -80,6 +80,10 @@ lib.pgpu_last_error.restype = C.c_char_p
 lib.pgpu_set_models.argtypes = [_vp, _vp, C.c_int, C.c_size_t]
 lib.pgpu_num_models.argtypes = [_vp]
 lib.pgpu_set_workspace_limit.argtypes = [_vp, C.c_size_t]
+lib.pgpu_host_alloc.argtypes = [C.c_size_t]
+lib.pgpu_host_alloc.restype = _vp
+lib.pgpu_host_free.argtypes = [_vp]
+lib.pgpu_host_free.restype = None
 lib.pgpu_timer_start.argtypes = [_vp]
 lib.pgpu_timer_stop.argtypes = [_vp, C.POINTER(C.c_double)]
 lib.pgpu_find_genes_batch.argtypes = [_vp, _vp, _vp, C.c_int, C.POINTER(Opts), C.POINTER(_vp)]
@@ -123,6 +127,30 @@ def check(rc, ctx=None):
 
 def ptr(a):
     return None if a is None else a.ctypes.data_as(_vp)
+
+
+class _PinnedBlock:
+    def __init__(self, p):
+        self.p = p
+
+    def __del__(self):
+        try:
+            if self.p:
+                lib.pgpu_host_free(self.p)
+                self.p = None
+        except Exception:
+            pass
+
+
+def pinned_empty(n):
+    """uint8 array of n bytes in page-locked host memory (pgpu_host_alloc), or an ordinary array when that is not
+    available (no CUDA device / allocation failed); freed with the last view of it"""
+    p = lib.pgpu_host_alloc(max(int(n), 1)) if n > 0 else None
+    if not p:
+        return np.empty(n, dtype=np.uint8)
+    buf = (C.c_ubyte * int(n)).from_address(p)
+    buf._owner = _PinnedBlock(p)
+    return np.frombuffer(buf, dtype=np.uint8)
 
 
 def make_opts(meta=False, single_model=0, closed=False, mask=False, min_mask=50, min_gene=90, min_edge_gene=60,

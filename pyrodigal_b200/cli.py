@@ -73,7 +73,8 @@ def main(argv=None, stdout=sys.stdout, stderr=sys.stderr, stdin=sys.stdin, *, ge
                     with open(args.t, "rb") as f:
                         training_info = TrainingInfo.load(f)
 
-            batch = fasta.read_batch(stdin.buffer if args.i is None and hasattr(stdin, "buffer") else (stdin if args.i is None else args.i))
+            batch = fasta.read_batch(stdin.buffer if args.i is None and hasattr(stdin, "buffer") else (stdin if args.i is None else args.i),
+                                     pinned=True)
             for seq_id in batch.ids:
                 if not seq_id:
                     warnings.warn("Input file contains a sequence without identifier", stacklevel=2)

@@ -1612,6 +1612,15 @@ int pgpu_set_models(pgpu_ctx *ctx, const void *blobs, int n, size_t stride) {
 
 int pgpu_num_models(const pgpu_ctx *ctx) { return ctx ? ctx->n_models : 0; }
 
+void *pgpu_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void pgpu_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
 int pgpu_set_workspace_limit(pgpu_ctx *ctx, size_t bytes) {
     if (!ctx) return PGPU_EINVAL;
     ctx->ws_limit = bytes;

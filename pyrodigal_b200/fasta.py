@@ -74,8 +74,21 @@ class Batch:
             yield Record(self.ids[k], self.sequence(k).tobytes().decode("ascii"), self.descriptions[k])
 
 
-def read_batch(source):
-    """Parse a FASTA file into one contiguous buffer + offsets (see module docstring)."""
+def _sequence_buffer(n, pinned):
+    """where the sequence bytes go: page-locked memory of the CUDA library when asked for (asynchronous input copies
+    that overlap the kernels of the previous sub-batch), ordinary memory otherwise"""
+    if pinned:
+        try:
+            from . import _capi
+            return _capi.pinned_empty(n)
+        except Exception:
+            pass
+    return np.empty(n, dtype=np.uint8)
+
+
+def read_batch(source, pinned=False):
+    """Parse a FASTA file into one contiguous buffer + offsets (see module docstring).  `pinned=True` writes the sequence
+    bytes straight into page-locked host memory (the only copy of them that is made)."""
     a = np.frombuffer(_read_bytes(source), dtype=np.uint8)
     n = len(a)
     if n == 0:
@@ -114,7 +127,8 @@ def read_batch(source):
     csum = np.concatenate(([0], np.cumsum(keep, dtype=np.int64)))
     bounds = np.concatenate((hdr_pos, [n]))
     offsets = csum[bounds] - csum[hdr_pos[0]]
-    flat = np.ascontiguousarray(a[keep])
+    flat = _sequence_buffer(int(csum[-1]), pinned)
+    np.compress(keep, a, out=flat)
     ids, descs = [], []
     raw = a.tobytes()
     for b, e in zip(hdr_pos, hdr_end):
