@@ -823,24 +823,26 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         B.tscore = pool.alloc<double>(total_cn);
         B.rbs = pool.alloc<uint8_t>(2 * (size_t)total_cn + 16);
     } else {
-        B.rupen = pool.alloc<double>(total_il + 64);
+        B.rupen = pool.alloc<double>(total_il + 512);
     }
     // interleaved arrays: total_il elements (blocks padded to even sizes) + slack for the bulk copies of the last rows
-    B.cs = pool.alloc<double>(total_il + 64);
-    B.opv = pool.alloc<double>(3 * (size_t)total_il + 64);
-    B.star_ptr = pool.alloc<int32_t>(3 * (size_t)total_il + 64);
-    B.score = pool.alloc<double>(total_il + 64);
-    B.traceb = pool.alloc<int32_t>(total_il + 64);
-    B.ov_mark = pool.alloc<int8_t>(total_il + 64);
+    B.cs = pool.alloc<double>(total_il + 512);
+    B.opv = pool.alloc<double>(3 * (size_t)total_il + 512);
+    B.star_ptr = pool.alloc<int32_t>(3 * (size_t)total_il + 512);
+    const bool dp_ml = ctx->dp_algo >= 6 || (ctx->dp_algo == 5 && n_chains > n_ext);
+    // the DP score of every chain-node is only kept when somebody reads it: node records of single mode, the per-chain
+    // kernels (their k_chain_best pass), the self-check.  k_dp_ml tracks the best terminal node of a chain itself.
+    if (!lean || !dp_ml || ctx->dp_verify) B.score = pool.alloc<double>(total_il + 512);
+    B.traceb = pool.alloc<int32_t>(total_il + 512);
+    B.ov_mark = pool.alloc<int8_t>(total_il + 512);
     B.chain_ipath = pool.alloc<int32_t>(n_chains);
     B.chain_score = pool.alloc<double>(n_chains);
-    const bool dp_ml = ctx->dp_algo >= 6 || (ctx->dp_algo == 5 && n_chains > n_ext);
     if (ctx->dp_algo >= 1) {
-        B.dp_svig = pool.alloc<double>(total_il + 64);
-        B.dp_tbig = pool.alloc<int32_t>(total_il + 64);
+        B.dp_svig = pool.alloc<double>(total_il + 512);
+        B.dp_tbig = pool.alloc<int32_t>(total_il + 512);
         if (dp_ml) {
-            B.dp_fmv = pool.alloc<double>(total_il + 64);
-            B.dp_fmj = pool.alloc<int32_t>(total_il + 64);
+            B.dp_fmv = pool.alloc<double>(total_il + 512);
+            B.dp_fmj = pool.alloc<int32_t>(total_il + 512);
         }
     }
     const int64_t trace_cn = lean ? ftot : total_cn;   // forward pointers / elimination flags: winner slots or every chain
@@ -908,23 +910,23 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         int4 *d_groups = pool.upload(groups);
         if (pool.failed) return PGPU_ENOMEM;
         if (ctx->dp_verify) {   // the self-check compares whole arrays: define the padding between the blocks
-            cudaMemsetAsync(B.score, 0, (total_il + 64) * sizeof(double), st);
-            cudaMemsetAsync(B.traceb, 0, (total_il + 64) * sizeof(int32_t), st);
-            cudaMemsetAsync(B.ov_mark, 0, (total_il + 64) * sizeof(int8_t), st);
+            cudaMemsetAsync(B.score, 0, (total_il + 512) * sizeof(double), st);
+            cudaMemsetAsync(B.traceb, 0, (total_il + 512) * sizeof(int32_t), st);
+            cudaMemsetAsync(B.ov_mark, 0, (total_il + 512) * sizeof(int8_t), st);
         }
         launch_dp_ml(B, ctx->d_models, d_groups, (int)groups.size(), n_chains, ctx->dp_ml_minb, st);
         ctx->launches++;
         if (ctx->dp_verify && total_cn > 0) {
             // self-check: the per-chain kernel must reproduce every score / traceback / overlap frame
             DevBatch V = B;
-            V.score = pool.alloc<double>(total_il + 64);
-            V.traceb = pool.alloc<int32_t>(total_il + 64);
-            V.ov_mark = pool.alloc<int8_t>(total_il + 64);
+            V.score = pool.alloc<double>(total_il + 512);
+            V.traceb = pool.alloc<int32_t>(total_il + 512);
+            V.ov_mark = pool.alloc<int8_t>(total_il + 512);
             unsigned long long *d_bad = pool.alloc<unsigned long long>(2);
             if (pool.failed) return PGPU_ENOMEM;
-            cudaMemsetAsync(V.score, 0, (total_il + 64) * sizeof(double), st);
-            cudaMemsetAsync(V.traceb, 0, (total_il + 64) * sizeof(int32_t), st);
-            cudaMemsetAsync(V.ov_mark, 0, (total_il + 64) * sizeof(int8_t), st);
+            cudaMemsetAsync(V.score, 0, (total_il + 512) * sizeof(double), st);
+            cudaMemsetAsync(V.traceb, 0, (total_il + 512) * sizeof(int32_t), st);
+            cudaMemsetAsync(V.ov_mark, 0, (total_il + 512) * sizeof(int8_t), st);
             const unsigned long long init[2] = {0ULL, ~0ULL};
             CK(cudaMemcpyAsync(d_bad, init, sizeof(init), cudaMemcpyHostToDevice, st));
             launch_dp(V, ctx->d_models, d_order, n_chains, 1, 3, st);

@@ -17,6 +17,8 @@
 //  * per step: lanes stride over admissible predecessors, warp-shuffle arg-max, one __syncthreads.
 //  * doubles everywhere, no FMA contraction (-fmad=false): results are bit-identical to the reference.
 #include <cfloat>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <cstring>
 
@@ -809,10 +811,16 @@ __constant__ double c_igA[61] = {
     (2.0 - ((double)60 / 60)) * 0.15
 };
 
+#ifdef PGPU_HOST_EMULATION
+#define ML_ASSERT(x) do { if (!(x)) { fprintf(stderr, "k_dp_ml invariant violated: %s\n", #x); abort(); } } while (0)
+#else
+#define ML_ASSERT(x) do { } while (0)
+#endif
+
 // CSH: doubles of one half of the cs tile (rows per half = largest even number <= CSH / S)
 template <int MINB, int CSH>
 __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const DevModel *__restrict__ models,
-                                                               const int4 *__restrict__ groups, int n_groups) {
+                                                               const int4 *__restrict__ groups, int n_groups, int prefetch) {
     struct __align__(16) WarpMem {
         double cs[2][CSH];       // bulk-copy destinations: 16-byte aligned
         MlK k[32];
@@ -839,7 +847,10 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
     const int chain = B.ext_chains[G.x + ll];
     const ChainInfo C = B.chains[chain];
     const int nn = C.nn;  // the same for every lane: one extraction
-    if (nn == 0) return;  // k_chain_best reports "no path"
+    if (nn == 0) {
+        if (act) { B.chain_ipath[chain] = -1; B.chain_score[chain] = 0.0; }
+        return;
+    }
     const DevModel &M = models[C.model];
     // Arrays are addressed from the kernel parameters (constant bank) + two offsets instead of through eighteen
     // precomputed pointers: the pointers alone would take 36 registers, and occupancy is what hides the load latency
@@ -850,6 +861,11 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
     const int64_t io = C.ioff;
     const int S = C.istride;
     const int fe0 = no + B.cbase[4 * G.z + 1];   // +STOPs in class order: node (clist), ndx (cndx), merged-stream position (feq)
+    const int n_fe = B.cbase[4 * G.z + 2] - B.cbase[4 * G.z + 1];
+    const int64_t rowb = io - C.lane;             // first element of row 0 of the extraction's interleaved block
+    auto pf_row = [](const void *p, int bytes) {
+        for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)p + o));
+    };
 #define ndx(j) B.ndx[no + (j)]
 #define sv(j) B.stop_val[no + (j)]
 #define cls(j) B.cls[no + (j)]
@@ -890,6 +906,10 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
     int cur = 0, lo = 0, far = 0, split = 0, cur_fe = 0, lo_fe = 0, far_fe = 0;
     double bk_v = kNeg;  // back stack: running maximum over the entries [split, far)
     int bk_j = -1;
+    double front_top = kNeg;   // maximum of the front stack at the last flip
+    // best terminal node of this lane's chain (lib.pyx:1239-1251: +STOP / -start nodes, largest index among equal maxima)
+    double best_v = -1.0;
+    int best_i = -1, best_tb = -1;
 #pragma unroll
     for (int f = 0; f < 3; f++) { wm.rcv[f][lane] = kNeg; wm.rcj[f][lane] = -1; wm.rev[f][lane] = 0.0; }
     if (lane < 4) wm.rej[lane] = -1;
@@ -918,6 +938,32 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
               k.a = dx.x >= max(w0, 0) ? dx.x : -1; k.b = dx.y >= max(w0, 0) ? dx.y : -1; k.c = dx.z >= max(w0, 0) ? dx.z : -1;
           }
           sk[lane] = k;
+          // Software prefetch into L2 of what the walk will read for this target and cannot have in cache: rows written
+          // (or last touched) hundreds of steps ago are in DRAM by now, and a dependent DRAM round trip on the walk costs
+          // about as much as a whole step.  Everything here is addressed geometrically, 1 .. 32 steps ahead of its use.
+          // Only when the launch does not oversubscribe the SMs (`prefetch`): under full load the lines are evicted again
+          // before they are used and the extra requests cost more than they save (measured: 18.3 -> 19.3 ms on the 630 Mbp
+          // shard, but 10.5 -> 8.6 ms on the 1 000-contig batch, where the longest walk is the critical path).
+          if (!prefetch) {
+          } else if (kind == K_RE) {   // the recorded overlapping starts / operon values of this -STOP (per lane: one row)
+              pf_row(&B.star_ptr[3 * (rowb + (int64_t)i * S)], S * 12);
+              pf_row(&B.opv[3 * (rowb + (int64_t)i * S)], S * 24);
+          } else if (kind == K_RS) {   // +STOPs of the 3' overlap range: source value, traceback position
+              const int r1 = min(min(k.c, k.b + 4), n_fe);
+              for (int r = k.b; r < r1; r++) {
+                  const int64_t q = rowb + (int64_t)fe_q(r) * S;
+                  pf_row(&B.dp_svig[q], S * 8);
+                  pf_row(&B.dp_tbig[q], S * 4);
+              }
+          } else if (kind == K_FE) {   // +STOPs inside the ORF (operon): source value, recorded start, operon value
+              const int r1 = min(k.a + 4, n_fe);
+              for (int r = k.a; r < r1; r++) {
+                  const int64_t q = rowb + (int64_t)fe_q(r) * S, j = rowb + (int64_t)fe_node(r) * S;
+                  pf_row(&B.dp_svig[q], S * 8);
+                  pf_row(&B.star_ptr[3 * j], S * 12);
+                  pf_row(&B.opv[3 * j], S * 24);
+              }
+          }
       }
       __syncwarp();
       const int iend = min(i0 + W, nn);
@@ -948,7 +994,8 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
 
         if (kind == K_RS) {
             // own -STOP (gene, _connection.h:228-237): the last -STOP of this frame
-            if (K.a >= 0) cand((wm.rej[f2] == K.a ? wm.rev[f2][lane] : score(K.a)) + cs_i, K.a, -1);
+            // (no stop codon of this frame lies inside the ORF, so the last -STOP node of the frame IS the own stop)
+            if (K.a >= 0) { ML_ASSERT(wm.rej[f2] == K.a); cand(wm.rev[f2][lane] + cs_i, K.a, -1); }
             // +STOPs overlapping the 3' end (_connection.h:239-256)
             const double cs_diff = cs_i + ig_neg;
             const int re = min(K.c, cur_fe);
@@ -980,11 +1027,9 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
                 if (s != kNeg && spj != -1) cand(s + opj, j, -1);
             }
         } else {  // K_FS, K_RE: intergenic sources
-            // the front stack's answer for this window start: issued first, consumed after the near sources
             double fm_v = kNeg;
             int fm_j = -1;
             const bool flip = lo > split;
-            if (!flip && lo < split) { fm_j = fmj(lo); fm_v = fmv(lo); }
             // -STOP only: the recorded overlapping -starts of this model (lane): node, its -STOP, and the class
             // range of the +STOPs that can trigger the triple overlap with it
             if (kind == K_RE) {
@@ -1046,7 +1091,14 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
                 }
                 split = far;
                 bk_v = kNeg; bk_j = -1;
+                front_top = fv;                             // the maximum of the whole front stack
                 if (lo < split) { fm_v = fv; fm_j = fj; }   // what the loop stored last is the entry of `lo`
+            } else if (lo < split && !(bk_j >= 0 && bk_v >= front_top)) {
+                // The front stack's answer for this window start.  DP scores grow along a chain, so soon after a flip the
+                // running maximum of the back stack exceeds everything the front stack holds (front_top bounds every
+                // later suffix maximum; on a tie the back stack's later node wins anyway): the load -- a DRAM round trip,
+                // the suffix maxima were written hundreds of steps ago -- is then skipped.
+                fm_j = fmj(lo); fm_v = fmv(lo);
             }
             if (fm_j >= 0) cand(fm_v, fm_j, -1);
             if (bk_j >= 0) cand(bk_v, bk_j, -1);
@@ -1135,9 +1187,10 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
                 }
                 // -STOPs whose ORF spans this stop: operon (_connection.h:343-356); at most one per frame = the last
                 // -STOP of that frame
-                if (K.a >= 0 && wm.t_sp[0][lane] != -1) cand((wm.rej[0] == K.a ? wm.rev[0][lane] : score(K.a)) + wm.t_op[0][lane], K.a, -1);
-                if (K.b >= 0 && wm.t_sp[1][lane] != -1) cand((wm.rej[1] == K.b ? wm.rev[1][lane] : score(K.b)) + wm.t_op[1][lane], K.b, -1);
-                if (K.c >= 0 && wm.t_sp[2][lane] != -1) cand((wm.rej[2] == K.c ? wm.rev[2][lane] : score(K.c)) + wm.t_op[2][lane], K.c, -1);
+                ML_ASSERT((K.a < 0 || wm.rej[0] == K.a) && (K.b < 0 || wm.rej[1] == K.b) && (K.c < 0 || wm.rej[2] == K.c));
+                if (K.a >= 0 && wm.t_sp[0][lane] != -1) cand(wm.rev[0][lane] + wm.t_op[0][lane], K.a, -1);
+                if (K.b >= 0 && wm.t_sp[1][lane] != -1) cand(wm.rev[1][lane] + wm.t_op[1][lane], K.b, -1);
+                if (K.c >= 0 && wm.t_sp[2][lane] != -1) cand(wm.rev[2][lane] + wm.t_op[2][lane], K.c, -1);
             }
         }
 
@@ -1145,12 +1198,15 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
         int tb_i = -1, fr_i = -1;
         if (wkey >= 0 && wv >= 0.0) { sc_i = wv; tb_i = wkey >> 2; fr_i = (wkey & 3) - 1; }
         if (act) {
-            score(i) = sc_i; B.traceb[IL(i)] = tb_i; B.ov_mark[IL(i)] = (int8_t)fr_i;
+            // the scores themselves are only stored when somebody reads them (single mode: node records; self-check)
+            if (B.score) score(i) = sc_i;
+            B.traceb[IL(i)] = tb_i; B.ov_mark[IL(i)] = (int8_t)fr_i;
             if (kind == K_FE || kind == K_RS) {
                 svig(cur) = tb_i == -1 ? kNeg : sc_i;  // edge-artifact rule: nothing leads into it
                 if (kind == K_FE) tbx(cur) = tb_i >= 0 ? ndx(tb_i) : 0;
             }
         }
+        if ((kind == K_FE || kind == K_RS) && sc_i >= best_v) { best_v = sc_i; best_i = i; best_tb = tb_i; }
         if (kind == K_FE) {
             cur++; cur_fe++;
             wm.rcv[f2][lane] = kNeg; wm.rcj[f2][lane] = -1;
@@ -1165,6 +1221,11 @@ __global__ void __launch_bounds__(32 * kMlWarps, MINB) k_dp_ml(DevBatch B, const
         }
         __syncwarp();  // the per-frame slots written above are visible to every lane of the next step
       }
+    }
+    if (act) {   // lib.pyx:1311: no path when nothing leads into the best terminal node
+        const bool ok = best_i >= 0 && best_tb != -1;
+        B.chain_ipath[chain] = ok ? best_i : -1;
+        B.chain_score[chain] = ok ? best_v : 0.0;
     }
 }
 #undef ndx
@@ -1663,10 +1724,11 @@ void launch_dp_ml(const DevBatch &B, const DevModel *models, const int4 *groups,
                   cudaStream_t st) {
     if (n_groups == 0 || n_chains == 0) return;
     const int nb = (n_groups + kMlWarps - 1) / kMlWarps;
-    if (minb == 6) k_dp_ml<6, 64><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, n_groups);         // 80 registers, 24 warps / SM
-    else if (minb == 10) k_dp_ml<10, 64><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, n_groups);  // 48 registers, 40 warps / SM
-    else k_dp_ml<8, 64><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, n_groups);                   // 64 registers, 32 warps / SM
-    k_chain_best<<<(n_chains * 32 + 127) / 128, 128, 0, st>>>(B, n_chains);
+    // software prefetch only while every walk has an SM slot from the start (148 SMs x 24 resident warps)
+    const int prefetch = n_groups <= 148 * 24 ? 1 : 0;
+    if (minb == 8) k_dp_ml<8, 64><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, n_groups, prefetch);   // 64 registers, 32 warps / SM
+    else k_dp_ml<6, 64><<<nb, 32 * kMlWarps, 0, st>>>(B, models, groups, n_groups, prefetch);             // 80 registers, 24 warps / SM
+    // (the best terminal node of every chain is tracked by the walk itself: no k_chain_best pass)
 }
 // PGPU_DP_VERIFY: element-wise comparison of two DP results (score, traceback, overlap frame)
 __global__ void k_dp_compare(const double *__restrict__ sa, const double *__restrict__ sb, const int32_t *__restrict__ ta,
