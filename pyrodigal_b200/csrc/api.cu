@@ -1512,6 +1512,7 @@ int pgpu_create(int device, pgpu_ctx **out) {
     if (const char *a = getenv("PGPU_CODON_LUT")) ctx->codon_lut = atoi(a) != 0;
     if (const char *a = getenv("PGPU_LANES")) ctx->lanes = atoi(a);
     if (const char *a = getenv("PGPU_LANE_MIN_BP")) ctx->lane_min_bp = atoll(a);
+    if (const char *a = getenv("PGPU_WS_LIMIT_MB")) ctx->ws_limit = (size_t)atoll(a) << 20;   // = pgpu_set_workspace_limit
     // keep freed blocks cached in the stream-ordered pool: sub-batches reuse them without going to the driver
     cudaMemPool_t mp;
     if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {

@@ -1097,7 +1097,9 @@ void launch_pairs(const DevBatch &B, int n_ext, int total_nodes, unsigned long l
 void launch_overlap(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, int64_t total_il, int n_ext,
                     RunOpts o, int flag, cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
-    cudaMemsetAsync(B.star_ptr, 0xff, 3 * (size_t)total_il * sizeof(int32_t), st);  // -1 everywhere
+    // star_ptr = -1 for every node (node records of single mode show it for starts too); the lean main pass of meta mode
+    // only ever reads the STOP nodes' entries, which the kernel writes itself (all three frames of every STOP node)
+    if (!B.rupen) cudaMemsetAsync(B.star_ptr, 0xff, 3 * (size_t)total_il * sizeof(int32_t), st);
     if (B.orf_toff && B.ext_chains && n_ext > 0)
         k_overlap_lanes<<<(unsigned)((B.orf_threads + 255) / 256), 256, 0, st>>>(B, models, n_ext, o, flag);
     else
