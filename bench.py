@@ -646,7 +646,7 @@ def main():
         r = step_host()
     r = None
     e2e_steps = []
-    gatherer = Gatherer() if (sharded and world > 1) else None
+    gatherer = Gatherer() if (sharded and world > 1 and os.environ.get("BENCH_NO_GATHER") != "1") else None
     if gatherer is not None:   # untimed pipelined steps: NCCL connections, the rotation of page-locked result / receive buffers
         for _ in range(4):
             gatherer.submit(step_host())

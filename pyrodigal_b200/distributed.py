@@ -170,6 +170,18 @@ def _pinned(key, size, torch):
     return t
 
 
+_buffer_cache = {}
+
+
+def _buffer(key, size, dev, torch):
+    """a uint8 tensor of at least `size` bytes on `dev`, recycled between calls"""
+    t = _buffer_cache.get((key, str(dev)))
+    if t is None or t.numel() < size:
+        t = torch.empty(max(size + size // 4, 1 << 16), dtype=torch.uint8, device=dev)
+        _buffer_cache[(key, str(dev))] = t
+    return t
+
+
 def _shard_view(flat, offsets, ids):
     """contigs `ids` back to back: (flat_shard, offsets_shard); a zero-copy slice when the ids are one contiguous run"""
     lens = (offsets[1:] - offsets[:-1])[ids]
@@ -206,53 +218,61 @@ def gather_result(local, ids, n_total, group=None, root=0, device=0):
     S, G, N = _capi.SUMMARY_DTYPE.itemsize, _capi.GENE_DTYPE.itemsize, _capi.NODE_DTYPE.itemsize
     trace = os.environ.get("PGPU_GATHER_TRACE") == "1"
     t0 = time.perf_counter()
+    # one message per rank: [contig ids | summaries | genes | gene nodes], padded to the largest one, so that the whole
+    # exchange is ONE gather collective (over nccl: device buffers, NVLink) instead of three point-to-point messages per
+    # rank that the root would have to take one after the other
+    size_of = [nc * (8 + S) + g * (G + 2 * N) for nc, g in heads]
+    maxb = max(max(size_of), 16)
+    pieces = [as_bytes(np.asarray(ids, dtype=np.int64)), as_bytes(local.summary)]
+    if ng:
+        pieces += [as_bytes(local.genes), as_bytes(local.gene_nodes)]
+    send = _buffer(("send", _gather_seq[0] & 1), maxb, dev, torch)
+    o = 0
+    for t in pieces:   # from the result's page-locked buffers: asynchronous DMA when the destination is a device tensor
+        send[o:o + t.numel()].copy_(t, non_blocking=True)
+        o += t.numel()
     if D.rank != root:
-        # small header (contig ids + summaries) in one message, then the gene records and their node records straight
-        # from the result's page-locked buffers (asynchronous DMA to the device, then NCCL over NVLink)
-        pieces = [torch.cat([as_bytes(np.asarray(ids, dtype=np.int64)), as_bytes(local.summary)])]
-        if ng:
-            pieces += [as_bytes(local.genes), as_bytes(local.gene_nodes)]
-        for t in pieces:
-            if D.cuda:
-                t = t.to(dev, non_blocking=True)
-            if t.numel():
-                dist.send(t, dst=D.global_rank(root), group=group)
+        dist.gather(send[:maxb], None, dst=D.global_rank(root), group=group)
         if D.cuda:
             torch.cuda.current_stream(dev).synchronize()   # the result buffers may be recycled once this returns
         if trace:
-            print(f"[gather rank {D.rank}] sent {sum(int(t.numel()) for t in pieces) / 1e6:.1f} MB in "
-                  f"{(time.perf_counter() - t0) * 1e3:.1f} ms", flush=True)
+            print(f"[gather rank {D.rank}] sent {o / 1e6:.1f} MB in {(time.perf_counter() - t0) * 1e3:.1f} ms", flush=True)
+        _gather_seq[0] += 1
         return None
+    recv = [_buffer(("recv", r, _gather_seq[0] & 1), maxb, dev, torch)[:maxb] for r in range(D.world)]
+    dist.gather(send[:maxb], recv, dst=D.global_rank(root), group=group)
     parts, all_stats = [], [stats]
+    hosts = {}
+    for r in range(D.world):
+        if r == root or size_of[r] == 0:
+            continue
+        if D.cuda:   # device -> host copies of what arrived over NVLink, into recycled page-locked memory, all in flight
+            hosts[r] = _pinned(("gather", r, _gather_seq[0] & 1), size_of[r], torch)
+            hosts[r][:size_of[r]].copy_(recv[r][:size_of[r]], non_blocking=True)
+        else:
+            hosts[r] = recv[r].clone()   # gloo: the receive buffers are recycled
+    if D.cuda:
+        torch.cuda.current_stream(dev).synchronize()
     _gather_seq[0] += 1
-
-    def receive(r, what, size):
-        buf = torch.empty(size, dtype=torch.uint8, device=dev)
-        if size:
-            dist.recv(buf, src=D.global_rank(r), group=group)
-        if D.cuda:   # one device -> host copy of what arrived over NVLink, into recycled page-locked memory
-            host = _pinned(("gather", r, what, _gather_seq[0] & 1), size, torch)
-            host[:size].copy_(buf)
-            return host[:size].numpy()
-        return buf.numpy()
-
     for r in range(D.world):
         nc, g = heads[r]
         if r == root:
             parts.append((np.asarray(ids, dtype=np.int64), local.summary, np.asarray(local.genes), np.asarray(local.gene_nodes)))
             continue
-        b = receive(r, "head", nc * (8 + S))
-        rid = b[:8 * nc].view(np.int64)
-        rsum = b[8 * nc:].view(_capi.SUMMARY_DTYPE)
-        if g:
-            rgen = receive(r, "genes", g * G).view(_capi.GENE_DTYPE)
-            rnod = receive(r, "nodes", 2 * g * N).view(_capi.NODE_DTYPE).reshape(g, 2)
-        else:
-            rgen = np.zeros(0, dtype=_capi.GENE_DTYPE)
-            rnod = np.zeros((0, 2), dtype=_capi.NODE_DTYPE)
+        if size_of[r] == 0:
+            parts.append((np.zeros(0, np.int64), np.zeros(0, _capi.SUMMARY_DTYPE), np.zeros(0, _capi.GENE_DTYPE),
+                          np.zeros((0, 2), _capi.NODE_DTYPE)))
+            continue
+        bb = hosts[r][:size_of[r]].numpy()
+        o = 0
+        rid = bb[o:o + 8 * nc].view(np.int64); o += 8 * nc
+        rsum = bb[o:o + S * nc].view(_capi.SUMMARY_DTYPE); o += S * nc
+        rgen = bb[o:o + G * g].view(_capi.GENE_DTYPE); o += G * g
+        rnod = bb[o:o + 2 * N * g].view(_capi.NODE_DTYPE).reshape(g, 2)
         parts.append((rid, rsum, rgen, rnod))
     if trace:
-        print(f"[gather rank {D.rank}] received from {D.world - 1} ranks in {(time.perf_counter() - t0) * 1e3:.1f} ms", flush=True)
+        print(f"[gather rank {D.rank}] gathered {sum(size_of) / 1e6:.1f} MB from {D.world} ranks in "
+              f"{(time.perf_counter() - t0) * 1e3:.1f} ms", flush=True)
     return ShardedResult(parts, n_total, all_stats)
 
 
