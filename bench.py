@@ -109,6 +109,9 @@ class Dist:
         if self.world > 1 and not dist.is_initialized():
             kw = {}
             if backend == "nccl":
+                # NCCL kernels on high-priority streams: the gather of one step's gene records runs while the next
+                # step's kernels fill the GPU, and must not queue behind their pending CTAs
+                os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
                 kw["device_id"] = torch.device(self.device)
             dist.init_process_group(backend, **kw)
 
