@@ -81,6 +81,8 @@ struct pgpu_ctx {
     DevModel *d_models = nullptr;
     uint32_t *d_live = nullptr; // [n_models][2048] motif cells with a weight other than the floor (DevModel::mot_live)
     double *d_dcT = nullptr;   // dicodon weights transposed: [4096][kDcCols], columns sorted by (tt, gc); null if n_models > kDcCols
+    double *d_dcS = nullptr;   // the same weights as table sets of four neighbouring columns: [n_models][4096][4] (k_coding_smem)
+    int coding_smem = 1;       // PGPU_CODING_SMEM: 1 = k_coding_smem for multi-model batches, 0 = k_coding_orf
     size_t ws_limit = 0;
     cudaEvent_t ev[16];
     int64_t launches = 0;
@@ -91,6 +93,7 @@ struct pgpu_ctx {
                                // 1 = over every node as with want_nodes (PGPU_FINAL_ALGO)
     bool codon_lut = false;    // PGPU_CODON_LUT=1: k_codon_bits reads codon flags from a per-table byte table (written
                                // after the last GPU run of round 1: logic checked by the host emulation only, so off)
+    bool coding_verify = false;   // PGPU_CODING_VERIFY=1: run k_coding_orf after k_coding_smem and fail on any differing raw coding score
     bool dp_verify = false;    // PGPU_DP_VERIFY=1: run k_dp_dq after k_dp_ml and fail on any difference (self-check)
     int dp_algo = 5;           // 5: k_dp_ml for multi-model batches, k_dp_dq otherwise (default); 6: k_dp_ml always;
                                // 1-4: k_dp_dq, 0: all-pairs k_dp (PGPU_DP_ALGO=n)
@@ -394,6 +397,86 @@ struct OperatorOut {  // operator-level outputs (single contig)
 
 static double window_low(double gc) { return fmin(0.65, 0.88495 * gc - 0.0102337); }
 static double window_high(double gc) { return fmax(0.35, 0.86596 * gc + 0.1131991); }
+
+// Plan of k_coding_smem (score_kernels.cu): the chains of every extraction in table-column order, cut into groups of up
+// to four neighbouring columns = plan entries; entries sorted by (first column = table set, lanes per ORF), every class
+// padded to whole CTA spans by an entry without extraction.  Leaves B.dcS null (=> k_coding_orf) when the chains of an
+// extraction are not on neighbouring columns (cannot happen with a GC window, but nothing here depends on it).
+static void plan_coding_smem(pgpu_ctx *ctx, DevPool &pool, DevBatch &B, const std::vector<ExtractInfo> &exts,
+                             const std::vector<ChainInfo> &chains, const std::vector<int32_t> &eoff,
+                             const std::vector<int32_t> &elist) {
+    const int n_ext = (int)exts.size();
+    struct Ent { int32_t ext, key; int32_t chain[4]; };
+    std::vector<Ent> ents;
+    ents.reserve((size_t)n_ext * 4);
+    int64_t slots = 0;
+    int32_t tmp[kDcCols];
+    for (int e = 0; e < n_ext; e++) {
+        const int L = eoff[e + 1] - eoff[e];
+        if (L == 0 || exts[e].nn == 0) continue;
+        if (L > kDcCols) return;
+        for (int k = 0; k < L; k++) tmp[k] = elist[eoff[e] + k];
+        std::sort(tmp, tmp + L, [&](int a, int b) { return ctx->h_models[chains[a].model].col < ctx->h_models[chains[b].model].col; });
+        const int c0 = ctx->h_models[chains[tmp[0]].model].col;
+        for (int k = 1; k < L; k++) if (ctx->h_models[chains[tmp[k]].model].col != c0 + k) return;
+        for (int k = 0; k < L; k += 4) {
+            const int w = std::min(4, L - k);
+            Ent t;
+            t.ext = e;
+            t.key = (c0 + k) * 4 + (w >= 3 ? 2 : w - 1);   // (table set, log2 of the lanes per ORF)
+            for (int q = 0; q < 4; q++) t.chain[q] = q < w ? tmp[k + q] : -1;
+            ents.push_back(t);
+            slots += exts[e].nn / 2 + 1;
+        }
+    }
+    if (ents.empty()) return;
+    // CTA span: about eight spans per SM when the batch is large enough, between 1024 and 16384 ORF slots
+    int span = 16384;
+    while (span > 1024 && slots / span < 148 * 8) span >>= 1;
+    // counting sort by key, then offsets with the class padding
+    const int n_keys = kDcCols * 4;
+    std::vector<int32_t> first(n_keys + 1, 0);
+    for (const Ent &t : ents) first[t.key + 1]++;
+    for (int k = 0; k < n_keys; k++) first[k + 1] += first[k];
+    std::vector<int32_t> order(ents.size());
+    {
+        std::vector<int32_t> fill(first.begin(), first.end() - 1);
+        for (size_t i = 0; i < ents.size(); i++) order[fill[ents[i].key]++] = (int32_t)i;
+    }
+    std::vector<int64_t> soff;
+    std::vector<int32_t> pext, pchain;
+    soff.reserve(ents.size() + n_keys + 1); pext.reserve(ents.size() + n_keys); pchain.reserve(4 * (ents.size() + n_keys));
+    int64_t at = 0;
+    for (int k = 0; k < n_keys; k++) {
+        if (first[k + 1] == first[k]) continue;
+        for (int i = first[k]; i < first[k + 1]; i++) {
+            const Ent &t = ents[order[i]];
+            soff.push_back(at); pext.push_back(t.ext);
+            for (int q = 0; q < 4; q++) pchain.push_back(t.chain[q]);
+            at += exts[t.ext].nn / 2 + 1;
+        }
+        if (at % span) {   // padding entry up to the next span boundary
+            soff.push_back(at); pext.push_back(-1);
+            for (int q = 0; q < 4; q++) pchain.push_back(-1);
+            at += span - at % span;
+        }
+    }
+    soff.push_back(at);
+    const int n_ent = (int)pext.size(), n_cta = (int)(at / span);
+    std::vector<int32_t> cta(n_cta + 1);
+    for (int c = 0, r = 0; c < n_cta; c++) {
+        while (soff[r + 1] <= (int64_t)c * span) r++;
+        cta[c] = r;
+    }
+    cta[n_cta] = n_ent - 1;
+    B.cq_soff = pool.upload(soff);
+    B.cq_ext = pool.upload(pext);
+    B.cq_chain = pool.upload(pchain);
+    B.cq_cta = pool.upload(cta);
+    B.cq_span = span;
+    B.cq_n_cta = n_cta;
+    if (!pool.failed) B.dcS = ctx->d_dcS;
+}
 
 static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, const int64_t *offsets, int lo, int hi,
                      const pgpu_opts &opts, const RunPlan &plan, pgpu_result *res, OperatorOut *op) {
@@ -801,6 +884,8 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
             launch_block_owner_off(B.orf_toff, n_ext, 8, tab, st);
             B.orf_blk = tab;
             ctx->launches++;
+            if (ctx->coding_smem && ctx->d_dcS) plan_coding_smem(ctx, pool, B, exts, chains, h_eoff, h_elist);
+            if (trace) fprintf(stderr, "[pgpu] coding: %s, %d CTA spans of %d ORF slots\n", B.dcS ? "k_coding_smem" : "k_coding_orf", B.cq_n_cta, B.cq_span);
         }
     }
     // Meta mode scores every (contig, model) chain "lean": per chain-node only the raw coding score, cs = cscore + sscore
@@ -859,8 +944,34 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         ctx->launches++;
     }
     tev("chain alloc/upload");
+    const bool coding_verify = ctx->coding_verify && B.dcS && total_cn > 0;
+    if (coding_verify) cudaMemsetAsync(B.cscore, 0, total_cn * sizeof(double), st);   // STOP nodes are never written
     launch_coding(B, ctx->d_models, n_chains, total_cn, n_ext, total_nodes, st);
     tev("k_coding_orf");
+    if (coding_verify) {
+        // self-check: the lanes-over-models kernel (weights through L1 / L2) must reproduce every raw coding score
+        DevBatch V = B;
+        V.dcS = nullptr;
+        V.cscore = pool.alloc<double>(total_cn);
+        unsigned long long *d_bad = pool.alloc<unsigned long long>(2);
+        if (pool.failed) return PGPU_ENOMEM;
+        cudaMemsetAsync(V.cscore, 0, total_cn * sizeof(double), st);
+        const unsigned long long init[2] = {0ULL, ~0ULL};
+        CK(cudaMemcpyAsync(d_bad, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        launch_coding(V, ctx->d_models, n_chains, total_cn, n_ext, total_nodes, st);
+        launch_dp_compare(B.cscore, V.cscore, (const int32_t *)B.cscore, (const int32_t *)B.cscore, (const int8_t *)B.cscore,
+                          (const int8_t *)B.cscore, total_cn, d_bad, st);
+        unsigned long long bad[2] = {0, 0};
+        CK(cudaMemcpyAsync(bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (bad[0]) {
+            char msg[160];
+            snprintf(msg, sizeof msg, "PGPU_CODING_VERIFY: %llu of %lld raw coding scores differ between k_coding_smem and k_coding_orf, first at chain-node %llu",
+                     bad[0], (long long)total_cn, bad[1]);
+            return fail(ctx, PGPU_ESTATE, msg);
+        }
+        ctx->launches += 2;   // (tests read this: the comparison did run)
+    }
     if (lean) launch_start_score_lean(B, ctx->d_models, n_chains, total_cn, ro, st);
     else launch_start_score(B, ctx->d_models, n_chains, total_cn, ro, d_mot_main, st);
     tev("k_start_score");
@@ -984,6 +1095,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         F.rbs = pool.alloc<uint8_t>(2 * (size_t)ftot + 16);
         F.ext_chains = nullptr;  // one chain per contig: the per-chain kernels
         F.orf_toff = nullptr;
+        F.dcS = nullptr;
         d_mot = pool.alloc<MotifOut>(ftot);
         if (pool.failed) return PGPU_ENOMEM;
     }
@@ -1506,10 +1618,12 @@ int pgpu_create(int device, pgpu_ctx **out) {
     for (auto &ev : ctx->ev) cudaEventCreate(&ev);
     if (const char *a = getenv("PGPU_DP_ALGO")) ctx->dp_algo = atoi(a);
     if (const char *a = getenv("PGPU_DP_VERIFY")) ctx->dp_verify = atoi(a) != 0;
+    if (const char *a = getenv("PGPU_CODING_VERIFY")) ctx->coding_verify = atoi(a) != 0;
     if (const char *a = getenv("PGPU_DP_ML_MINB")) ctx->dp_ml_minb = atoi(a);
     if (const char *a = getenv("PGPU_EXTRACT_ALGO")) ctx->extract_algo = atoi(a);
     if (const char *a = getenv("PGPU_FINAL_ALGO")) ctx->final_algo = atoi(a);
     if (const char *a = getenv("PGPU_CODON_LUT")) ctx->codon_lut = atoi(a) != 0;
+    if (const char *a = getenv("PGPU_CODING_SMEM")) ctx->coding_smem = atoi(a);
     if (const char *a = getenv("PGPU_LANES")) ctx->lanes = atoi(a);
     if (const char *a = getenv("PGPU_LANE_MIN_BP")) ctx->lane_min_bp = atoll(a);
     if (const char *a = getenv("PGPU_WS_LIMIT_MB")) ctx->ws_limit = (size_t)atoll(a) << 20;   // = pgpu_set_workspace_limit
@@ -1530,6 +1644,7 @@ void pgpu_destroy(pgpu_ctx *ctx) {
     if (ctx->d_raw) cudaFree(ctx->d_raw);
     if (ctx->d_models) cudaFree(ctx->d_models);
     if (ctx->d_dcT) cudaFree(ctx->d_dcT);
+    if (ctx->d_dcS) cudaFree(ctx->d_dcS);
     if (ctx->d_live) cudaFree(ctx->d_live);
     for (auto &ev : ctx->ev) cudaEventDestroy(ev);
     if (ctx->lane_stream[0]) {
@@ -1566,7 +1681,7 @@ int pgpu_set_models(pgpu_ctx *ctx, const void *blobs, int n, size_t stride) {
     RawTraining *d_raw = nullptr;
     DevModel *d_models = nullptr;
     uint32_t *d_live = nullptr;
-    double *d_dcT = nullptr;
+    double *d_dcT = nullptr, *d_dcS = nullptr;
     std::vector<DevModel> h_models(n);
     auto build = [&]() -> cudaError_t {
         cudaError_t e;
@@ -1594,17 +1709,28 @@ int pgpu_set_models(pgpu_ctx *ctx, const void *blobs, int n, size_t stride) {
                 for (int i = 0; i < 4096; i++) t[(size_t)i * kDcCols + c] = h_raw_v[ord[c]].gene_dc[i];
             if ((e = cudaMalloc(&d_dcT, t.size() * sizeof(double))) != cudaSuccess) return e;
             if ((e = cudaMemcpy(d_dcT, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+            // table sets of k_coding_smem: set s = columns s .. s + 3 (zero past the last one), 128 KB each, contiguous
+            // so that a CTA fetches its set with a few bulk copies
+            std::vector<double> ts((size_t)n * 4096 * 4, 0.0);
+            for (int c = 0; c < n; c++)
+                for (int k = 0; k < 4 && c + k < n; k++) {
+                    const double *src = h_raw_v[ord[c + k]].gene_dc;
+                    double *dst = ts.data() + (size_t)c * 4096 * 4 + k;
+                    for (int i = 0; i < 4096; i++) dst[(size_t)i * 4] = src[i];
+                }
+            if ((e = cudaMalloc(&d_dcS, ts.size() * sizeof(double))) != cudaSuccess) return e;
+            if ((e = cudaMemcpy(d_dcS, ts.data(), ts.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
         }
         if ((e = cudaMemcpy(d_raw, h_raw_v.data(), n * sizeof(RawTraining), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
         return cudaMemcpy(d_models, h_models.data(), n * sizeof(DevModel), cudaMemcpyHostToDevice);
     };
     const cudaError_t e = build();
     if (e != cudaSuccess) {
-        cudaFree(d_raw); cudaFree(d_models); cudaFree(d_live); cudaFree(d_dcT);
+        cudaFree(d_raw); cudaFree(d_models); cudaFree(d_live); cudaFree(d_dcT); cudaFree(d_dcS);
         return fail(ctx, e == cudaErrorMemoryAllocation ? PGPU_ENOMEM : PGPU_ECUDA, std::string("pgpu_set_models: ") + cudaGetErrorString(e));
     }
-    cudaFree(ctx->d_raw); cudaFree(ctx->d_models); cudaFree(ctx->d_live); cudaFree(ctx->d_dcT);
-    ctx->d_raw = d_raw; ctx->d_models = d_models; ctx->d_live = d_live; ctx->d_dcT = d_dcT;
+    cudaFree(ctx->d_raw); cudaFree(ctx->d_models); cudaFree(ctx->d_live); cudaFree(ctx->d_dcT); cudaFree(ctx->d_dcS);
+    ctx->d_raw = d_raw; ctx->d_models = d_models; ctx->d_live = d_live; ctx->d_dcT = d_dcT; ctx->d_dcS = d_dcS;
     ctx->h_models.swap(h_models);
     ctx->n_models = n;
     ctx->model_gc.resize(n);

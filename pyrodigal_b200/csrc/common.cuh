@@ -11,6 +11,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/pyrodigal_b200.h"
 
@@ -201,6 +202,15 @@ struct DevBatch {
     const uint8_t *orf_w;
     const int32_t *orf_blk;
     int64_t orf_threads;
+    // shared-memory mapping of the raw coding score (k_coding_smem; optional, nullptr = k_coding_orf): plan entries
+    // r = (extraction, up to four chains on neighbouring table columns), sorted by (table set, lanes per ORF); entry r owns
+    // the ORF slots [cq_soff[r], cq_soff[r + 1]); classes are padded to whole CTA spans by entries with cq_ext = -1
+    const double *dcS;         // table sets: dcS[(s * 4096 + index) * 4 + k] = dicodon weight `index` of table column s + k
+    const int64_t *cq_soff;
+    const int32_t *cq_ext;
+    const int32_t *cq_chain;   // [4 * r + k]: chain of lane k, or -1
+    const int32_t *cq_cta;     // [n_cta + 1]: plan entry that holds the first slot of every CTA span
+    int32_t cq_span, cq_n_cta;
     // per chain results
     int32_t *chain_ipath;
     double *chain_score;
@@ -212,6 +222,50 @@ struct MotifOut {
     uint16_t ndx;
     uint8_t len, spacer, spacendx, pad[3];
 };
+
+// ---- 1-D bulk copy global -> shared (TMA) completing on an mbarrier; raw PTX, sm_90+ ---------------
+#ifndef PGPU_HOST_EMULATION
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// arm the barrier with the byte count of the copy, then start the copy (one elected lane)
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+// the same in two steps, for several copies that complete on one barrier phase
+__device__ __forceinline__ void mbar_expect(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+#else   // host emulation (tests/emu): the copy happens at once, the barrier is always complete
+__device__ __forceinline__ void mbar_init(uint64_t *, int) {}
+__device__ __forceinline__ void mbar_init_fence() {}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void mbar_expect(uint64_t *, uint32_t) {}
+__device__ __forceinline__ void bulk_copy(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void mbar_wait(uint64_t *, uint32_t) {}
+#endif
 
 // ---- device helpers ------------------------------------------------------------------------------
 

@@ -711,39 +711,7 @@ struct MlK {  // geometric constants of a target, staged 32 targets at a time (m
     int32_t a, b, c, pad;
 };
 
-// ---- 1-D bulk copy global -> shared (TMA) completing on an mbarrier; raw PTX, sm_90+ ---------------
-#ifndef PGPU_HOST_EMULATION
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_init_fence() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-// arm the barrier with the byte count of the copy, then start the copy (one elected lane)
-__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "MBAR_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra MBAR_DONE;\n"
-        "bra MBAR_WAIT;\n"
-        "MBAR_DONE:\n"
-        "}\n" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
-}
-#else   // host emulation (tests/emu): the copy happens at once, the barrier is always complete
-__device__ __forceinline__ void mbar_init(uint64_t *, int) {}
-__device__ __forceinline__ void mbar_init_fence() {}
-__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
-__device__ __forceinline__ void mbar_wait(uint64_t *, uint32_t) {}
-#endif
+// (mbarrier / 1-D bulk copy helpers: common.cuh)
 
 // (2.0 - dist / 60) * 0.15 of _connection.h:74 for dist = 0..60: the model-independent part of the distance term; the
 // term itself is this times the start weight of the lane's model (same operations, same order as the reference)

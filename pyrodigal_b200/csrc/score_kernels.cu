@@ -320,6 +320,102 @@ __global__ void __launch_bounds__(128) k_coding(DevBatch B, const DevModel *__re
 // --------------------------------------------------------------------------------------------------
 constexpr int kOrfWarps = 8;
 
+// The ORF that ends at STOP node z (position my, frame f, strand rev) for the chain of this lane: all three sweeps.
+// Wt(index) = the dicodon weight of this lane's model; a lane without a chain (active == false) walks along.
+template <class WF>
+__device__ __forceinline__ void coding_orf_lane(const uint8_t *__restrict__ cls, const int32_t *__restrict__ ndx,
+                                                const int32_t *__restrict__ sv, const uint16_t *__restrict__ dicf,
+                                                const uint16_t *__restrict__ dicr, int nn, int z, int f, int my, bool rev,
+                                                bool active, double *__restrict__ cscore, const DevModel &M, WF Wt) {
+    // sweep A: dicodon log-odds accumulated from the stop towards each start (lib.pyx:2149-2173).  The chain
+    // (index load -> weight load -> add) is latency bound: eight codons per round while at least eight remain
+    // (their loads are independent and in flight together), then 4 / 2 / 1; adds keep the reference's order.
+    int far = -1, last = my;
+    double acc = 0.0;
+    if (!rev) {
+        for (int i = z - 1; i >= 0; i--) {
+            const int ci = cls[i];
+            if ((ci & CLS_REV) || cls_frame(ci) != f) continue;
+            if (cls_is_stop(ci)) break;
+            const int ni = ndx[i];
+            const uint16_t *__restrict__ q = dicf + (last - 3);  // codons q[0], q[-3], ... down to position ni
+            int rem = (last - ni) / 3;
+#pragma unroll 1
+            for (; rem >= 8; rem -= 8, q -= 24) {
+                const uint32_t i0 = q[0], i1 = q[-3], i2 = q[-6], i3 = q[-9], i4 = q[-12], i5 = q[-15], i6 = q[-18], i7 = q[-21];
+                const double w0 = Wt(i0), w1 = Wt(i1), w2 = Wt(i2), w3 = Wt(i3), w4 = Wt(i4), w5 = Wt(i5), w6 = Wt(i6), w7 = Wt(i7);
+                acc += w0; acc += w1; acc += w2; acc += w3; acc += w4; acc += w5; acc += w6; acc += w7;
+            }
+            if (rem & 4) {
+                const uint32_t i0 = q[0], i1 = q[-3], i2 = q[-6], i3 = q[-9];
+                const double w0 = Wt(i0), w1 = Wt(i1), w2 = Wt(i2), w3 = Wt(i3);
+                acc += w0; acc += w1; acc += w2; acc += w3;
+                q -= 12;
+            }
+            if (rem & 2) {
+                const uint32_t i0 = q[0], i1 = q[-3];
+                const double w0 = Wt(i0), w1 = Wt(i1);
+                acc += w0; acc += w1;
+                q -= 6;
+            }
+            if (rem & 1) acc += Wt(q[0]);
+            if (active) cscore[i] = acc;
+            last = ni;
+            far = i;
+        }
+    } else {
+        for (int i = z + 1; i < nn; i++) {
+            const int ci = cls[i];
+            if (!(ci & CLS_REV) || cls_frame(ci) != f) continue;
+            if (cls_is_stop(ci)) break;
+            const int ni = ndx[i];
+            const uint16_t *__restrict__ q = dicr + (last + 3);  // codons q[0], q[3], ... up to position ni
+            int rem = (ni - last) / 3;
+#pragma unroll 1
+            for (; rem >= 8; rem -= 8, q += 24) {
+                const uint32_t i0 = q[0], i1 = q[3], i2 = q[6], i3 = q[9], i4 = q[12], i5 = q[15], i6 = q[18], i7 = q[21];
+                const double w0 = Wt(i0), w1 = Wt(i1), w2 = Wt(i2), w3 = Wt(i3), w4 = Wt(i4), w5 = Wt(i5), w6 = Wt(i6), w7 = Wt(i7);
+                acc += w0; acc += w1; acc += w2; acc += w3; acc += w4; acc += w5; acc += w6; acc += w7;
+            }
+            if (rem & 4) {
+                const uint32_t i0 = q[0], i1 = q[3], i2 = q[6], i3 = q[9];
+                const double w0 = Wt(i0), w1 = Wt(i1), w2 = Wt(i2), w3 = Wt(i3);
+                acc += w0; acc += w1; acc += w2; acc += w3;
+                q += 12;
+            }
+            if (rem & 2) {
+                const uint32_t i0 = q[0], i1 = q[3];
+                const double w0 = Wt(i0), w1 = Wt(i1);
+                acc += w0; acc += w1;
+                q += 6;
+            }
+            if (rem & 1) acc += Wt(q[0]);
+            if (active) cscore[i] = acc;
+            last = ni;
+            far = i;
+        }
+    }
+    if (far < 0) return;
+
+    // sweep B: the two penalty passes fused, walking back towards the stop (lib.pyx:2175-2236)
+    double s2 = -10000.0, s3 = -10000.0;
+    const int step = rev ? -1 : 1;
+    for (int i = far; i != z; i += step) {
+        const int ci = cls[i];
+        if (((ci & CLS_REV) != 0) != rev || cls_frame(ci) != f) continue;
+        double cs = active ? cscore[i] : 0.0;
+        if (cs > s2) s2 = cs; else cs -= (s2 - cs);
+        const double gsize = rev ? (((double)ndx[i] - sv[i]) + 3.0) / 3.0 : (((double)sv[i] - ndx[i]) + 3.0) / 3.0;
+        double lfac;
+        if (gsize > 1000.0) lfac = M.lfac_span * (gsize - 80) / 920.0;
+        else lfac = M.lfac[(int)gsize];
+        if (lfac > s3) s3 = lfac; else lfac -= fmax(fmin(s3 - lfac, lfac), 0.0);
+        if (lfac > 3.0 && cs < 0.5 * lfac) cs = 0.5 * lfac;
+        cs += lfac;
+        if (active) cscore[i] = cs;
+    }
+}
+
 // GROUPED: an extraction with L <= 16 models does not need a whole warp per ORF.  Its ORFs are handled by groups of
 // W = 4 / 8 / 16 lanes (the next power of two >= L), 32 / W ORFs per warp: the lanes of a group still take one model
 // each and share every node / codon load, different groups of a warp simply diverge (there is no warp-level
@@ -376,98 +472,86 @@ __global__ void __launch_bounds__(32 * kOrfWarps, MINB) k_coding_orf(DevBatch B,
         const DevModel &M = models[C.model];
         // this lane's column of the transposed table; a weight address is one 32x32->64 multiply-add from it
         const char *__restrict__ wcol = (const char *)(B.dcT + M.col);
-        auto W = [&](uint32_t index) -> double {
+        coding_orf_lane(cls, ndx, sv, dicf, dicr, nn, z, f, my, rev, active, B.cscore + C.coff, M, [&](uint32_t index) -> double {
             return *(const double *)(wcol + (uint64_t)index * (uint64_t)(kDcCols * sizeof(double)));
-        };
-        double *__restrict__ cscore = B.cscore + C.coff;
+        });
+    }
+}
 
-        // sweep A: dicodon log-odds accumulated from the stop towards each start (lib.pyx:2149-2173).  The chain
-        // (index load -> weight load -> add) is latency bound: eight codons per round while at least eight remain
-        // (their loads are independent and in flight together), then 4 / 2 / 1; adds keep the reference's order.
-        int far = -1, last = my;
-        double acc = 0.0;
-        if (!rev) {
-            for (int i = z - 1; i >= 0; i--) {
-                const int ci = cls[i];
-                if ((ci & CLS_REV) || cls_frame(ci) != f) continue;
-                if (cls_is_stop(ci)) break;
-                const int ni = ndx[i];
-                const uint16_t *__restrict__ q = dicf + (last - 3);  // codons q[0], q[-3], ... down to position ni
-                int rem = (last - ni) / 3;
-#pragma unroll 1
-                for (; rem >= 8; rem -= 8, q -= 24) {
-                    const uint32_t i0 = q[0], i1 = q[-3], i2 = q[-6], i3 = q[-9], i4 = q[-12], i5 = q[-15], i6 = q[-18], i7 = q[-21];
-                    const double w0 = W(i0), w1 = W(i1), w2 = W(i2), w3 = W(i3), w4 = W(i4), w5 = W(i5), w6 = W(i6), w7 = W(i7);
-                    acc += w0; acc += w1; acc += w2; acc += w3; acc += w4; acc += w5; acc += w6; acc += w7;
-                }
-                if (rem & 4) {
-                    const uint32_t i0 = q[0], i1 = q[-3], i2 = q[-6], i3 = q[-9];
-                    const double w0 = W(i0), w1 = W(i1), w2 = W(i2), w3 = W(i3);
-                    acc += w0; acc += w1; acc += w2; acc += w3;
-                    q -= 12;
-                }
-                if (rem & 2) {
-                    const uint32_t i0 = q[0], i1 = q[-3];
-                    const double w0 = W(i0), w1 = W(i1);
-                    acc += w0; acc += w1;
-                    q -= 6;
-                }
-                if (rem & 1) acc += W(q[0]);
-                if (active) cscore[i] = acc;
-                last = ni;
-                far = i;
-            }
-        } else {
-            for (int i = z + 1; i < nn; i++) {
-                const int ci = cls[i];
-                if (!(ci & CLS_REV) || cls_frame(ci) != f) continue;
-                if (cls_is_stop(ci)) break;
-                const int ni = ndx[i];
-                const uint16_t *__restrict__ q = dicr + (last + 3);  // codons q[0], q[3], ... up to position ni
-                int rem = (ni - last) / 3;
-#pragma unroll 1
-                for (; rem >= 8; rem -= 8, q += 24) {
-                    const uint32_t i0 = q[0], i1 = q[3], i2 = q[6], i3 = q[9], i4 = q[12], i5 = q[15], i6 = q[18], i7 = q[21];
-                    const double w0 = W(i0), w1 = W(i1), w2 = W(i2), w3 = W(i3), w4 = W(i4), w5 = W(i5), w6 = W(i6), w7 = W(i7);
-                    acc += w0; acc += w1; acc += w2; acc += w3; acc += w4; acc += w5; acc += w6; acc += w7;
-                }
-                if (rem & 4) {
-                    const uint32_t i0 = q[0], i1 = q[3], i2 = q[6], i3 = q[9];
-                    const double w0 = W(i0), w1 = W(i1), w2 = W(i2), w3 = W(i3);
-                    acc += w0; acc += w1; acc += w2; acc += w3;
-                    q += 12;
-                }
-                if (rem & 2) {
-                    const uint32_t i0 = q[0], i1 = q[3];
-                    const double w0 = W(i0), w1 = W(i1);
-                    acc += w0; acc += w1;
-                    q += 6;
-                }
-                if (rem & 1) acc += W(q[0]);
-                if (active) cscore[i] = acc;
-                last = ni;
-                far = i;
-            }
-        }
-        if (far < 0) continue;
+// --------------------------------------------------------------------------------------------------
+// raw coding score with the dicodon tables in shared memory (k_coding_smem).  k_coding_orf gathers its weights from
+// the 2 MB transposed table through L1 / L2 (ncu: 70 % of the stall samples long-scoreboard, L1 hit rate 54 %).  Here a
+// CTA owns the weights of kCqCols neighbouring table columns -- the models are sorted by (translation table, GC), the
+// chains of an extraction are a contiguous column range, cut into groups of up to four -- as one 128 KB table
+// dcS[set][index][4], fetched once with 1-D bulk copies (TMA, cp.async.bulk + mbarrier) and then read with LDS.64.
+// Work items are (extraction, column group, STOP node) = "ORF slots", planned on the host (api.cu: plan entries sorted
+// by (table set, lanes per ORF), every class padded to whole CTA spans, so a CTA has ONE table set and ONE group width
+// W = 1 / 2 / 4).  The groups of W lanes take slots from a shared-memory counter: a group that drew a short ORF simply
+// draws the next one, so the lanes stay busy whatever the ORF lengths are.  Per (ORF, model) the operations and their
+// order are those of k_coding_orf (coding_orf_lane).
+// --------------------------------------------------------------------------------------------------
+constexpr int kCqThreads = 1024;
+constexpr int kCqCols = 4;
+constexpr int kCqTableBytes = 4096 * kCqCols * (int)sizeof(double);   // 128 KB
 
-        // sweep B: the two penalty passes fused, walking back towards the stop (lib.pyx:2175-2236)
-        double s2 = -10000.0, s3 = -10000.0;
-        const int step = rev ? -1 : 1;
-        for (int i = far; i != z; i += step) {
-            const int ci = cls[i];
-            if (((ci & CLS_REV) != 0) != rev || cls_frame(ci) != f) continue;
-            double cs = active ? cscore[i] : 0.0;
-            if (cs > s2) s2 = cs; else cs -= (s2 - cs);
-            const double gsize = rev ? (((double)ndx[i] - sv[i]) + 3.0) / 3.0 : (((double)sv[i] - ndx[i]) + 3.0) / 3.0;
-            double lfac;
-            if (gsize > 1000.0) lfac = M.lfac_span * (gsize - 80) / 920.0;
-            else lfac = M.lfac[(int)gsize];
-            if (lfac > s3) s3 = lfac; else lfac -= fmax(fmin(s3 - lfac, lfac), 0.0);
-            if (lfac > 3.0 && cs < 0.5 * lfac) cs = 0.5 * lfac;
-            cs += lfac;
-            if (active) cscore[i] = cs;
-        }
+__global__ void __launch_bounds__(kCqThreads, 1) k_coding_smem(DevBatch B, const DevModel *__restrict__ models) {
+#ifdef PGPU_HOST_EMULATION
+    static double tab_store[4096 * kCqCols];
+    double *tab = tab_store;
+#else
+    extern __shared__ __align__(128) unsigned char cq_dyn_smem[];
+    double *tab = reinterpret_cast<double *>(cq_dyn_smem);
+#endif
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_next;
+    const int span = B.cq_span;
+    const int r0 = B.cq_cta[blockIdx.x], r1 = B.cq_cta[blockIdx.x + 1];   // plan entries of this CTA's span: [r0, r1]
+    const int first_chain = B.cq_chain[4 * r0];
+    if (first_chain < 0) return;   // a span of padding only (uniform for the CTA)
+    int W = 1;
+    if (B.cq_chain[4 * r0 + 2] >= 0) W = 4; else if (B.cq_chain[4 * r0 + 1] >= 0) W = 2;
+    if (threadIdx.x == 0) {
+        s_next = 0;
+        mbar_init(&s_bar, 1);
+        mbar_init_fence();
+        const char *src = (const char *)(B.dcS + (size_t)models[B.chains[first_chain].model].col * (4096 * kCqCols));
+        mbar_expect(&s_bar, kCqTableBytes);
+        for (int k = 0; k < kCqTableBytes; k += 16384) bulk_copy((char *)tab + k, src + k, 16384, &s_bar);
+    }
+    __syncthreads();
+    mbar_wait(&s_bar, 0);
+
+    const int lane = threadIdx.x & (W - 1);
+    const unsigned gmask = W == 4 ? 0xFu << (threadIdx.x & 28) : W == 2 ? 0x3u << (threadIdx.x & 30) : 0u;
+    const int64_t slot0 = (int64_t)blockIdx.x * span;
+    int r = r0;
+    for (;;) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(&s_next, 1);
+        if (W > 1) slot = __shfl_sync(gmask, slot, 0, W);
+        if (slot >= span) break;
+        const int64_t gs = slot0 + slot;
+        while (r < r1 && B.cq_soff[r + 1] <= gs) r++;   // slots are drawn in increasing order
+        const int e = B.cq_ext[r];
+        if (e < 0) continue;   // padding entry
+        const int tl = (int)(gs - B.cq_soff[r]);
+        const int32_t *__restrict__ cbase = B.cbase + 4 * e;
+        const ExtractInfo *__restrict__ X = B.exts + e;
+        const int nn = X->nn, node_off = X->node_off;
+        const int n_fe = cbase[2] - cbase[1], n_re = nn - cbase[3];
+        if (tl >= n_fe + n_re) continue;
+        const int z = (B.clist + node_off)[tl < n_fe ? cbase[1] + tl : cbase[3] + (tl - n_fe)];
+        const uint8_t *__restrict__ cls = B.cls + node_off;
+        const int32_t *__restrict__ ndx = B.ndx + node_off;
+        const int64_t doff = X->doff;
+        const int c = cls[z];
+        const int chain = B.cq_chain[4 * r + lane];
+        const bool active = chain >= 0;
+        const ChainInfo *__restrict__ C = B.chains + (active ? chain : B.cq_chain[4 * r]);
+        const double *__restrict__ wcol = tab + lane;
+        coding_orf_lane(cls, ndx, B.stop_val + node_off, B.dic_f + doff, B.dic_r + doff, nn, z, cls_frame(c), ndx[z],
+                        (c & CLS_REV) != 0, active, B.cscore + C->coff, models[C->model],
+                        [&](uint32_t index) -> double { return wcol[index * kCqCols]; });
     }
 }
 
@@ -1033,7 +1117,15 @@ void launch_node_prep(const DevBatch &B, int n_ext, int total_nodes, int seq_par
 void launch_coding(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, int n_ext, int total_nodes,
                    cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
-    if (B.ext_chains && B.dcT && n_ext > 0 && total_nodes > 0) {
+    if (B.ext_chains && B.dcS && B.cq_n_cta > 0 && total_nodes > 0) {   // dicodon tables in shared memory
+#ifdef PGPU_HOST_EMULATION
+        k_coding_smem<<<(unsigned)B.cq_n_cta, kCqThreads, 0, st>>>(B, models);
+#else
+        static const cudaError_t attr = cudaFuncSetAttribute(k_coding_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kCqTableBytes);
+        (void)attr;
+        k_coding_smem<<<(unsigned)B.cq_n_cta, kCqThreads, kCqTableBytes, st>>>(B, models);
+#endif
+    } else if (B.ext_chains && B.dcT && n_ext > 0 && total_nodes > 0) {
         static const int minb = getenv("PGPU_CODING_MINB") ? atoi(getenv("PGPU_CODING_MINB")) : 5;  // A/B switch
         if (B.orf_toff) {  // grouped mapping planned by the host (api.cu)
             const unsigned nb = (unsigned)((B.orf_threads + 32 * kOrfWarps - 1) / (32 * kOrfWarps));

@@ -508,6 +508,39 @@ def test_coding_score_lane_groups(capi):
     c.close()
 
 
+def test_coding_score_shared_memory_tables(capi, monkeypatch):
+    """k_coding_smem (dicodon tables of four neighbouring models in shared memory, ORF slots drawn from a counter) against
+    k_coding_orf (PGPU_CODING_VERIFY: every raw coding score of every chain, bit for bit) on a GC sweep -- extractions with
+    1 ... 27 models, i.e. every table set and every group width -- then against the oracle; PGPU_CODING_SMEM=0 gives the
+    same genes"""
+    seqs = [R.synth(2000 + 613 * (k % 5), 0.24 + 0.02 * (k % 27), 6300 + k) for k in range(54)]
+    arrs = [np.frombuffer(s, np.uint8) for s in seqs]
+    off = np.zeros(len(arrs) + 1, np.int64)
+    np.cumsum([len(a) for a in arrs], out=off[1:])
+    flat = np.ascontiguousarray(np.concatenate(arrs))
+    out = {}
+    for mode, verify in (("1", "0"), ("1", "1"), ("0", "1")):
+        monkeypatch.setenv("PGPU_CODING_SMEM", mode)
+        monkeypatch.setenv("PGPU_CODING_VERIFY", verify)
+        c = capi.Context(0)
+        c.set_models(R.bins_blob(), 50)
+        res = c.find_genes_batch(flat, off, capi.make_opts(meta=True, want_nodes=False))
+        out[mode, verify] = (res.genes.tobytes(), res.gene_nodes.tobytes(), res.summary.tobytes(), res.stats["kernel_launches"])
+        if (mode, verify) == ("1", "1"):
+            for k in (0, 5, 11, 20, 26, 33, 47):
+                d, gc, unk = orc.encode(seqs[k])
+                genes, nodes, winner, pairs = orc.find_genes_meta(d, gc / len(d), R.bins_blob())
+                a, b = res.gene_off[k], res.gene_off[k + 1]
+                assert int(res.summary["winner"][k]) == winner and b - a == len(genes), k
+                cmp_int(res.genes[a:b]["begin"], genes["begin"], f"smem.contig{k}.begin")
+                cmp_int(res.genes[a:b]["end"], genes["end"], f"smem.contig{k}.end")
+        res.free(); c.close()
+    assert out["1", "1"][3] == out["1", "0"][3] + 2, "the self-check did not run: k_coding_smem was not selected"
+    assert out["0", "1"][3] == out["1", "0"][3], "PGPU_CODING_SMEM=0 still ran the self-check"
+    for key in (("1", "1"), ("0", "1")):
+        assert out[key][:3] == out["1", "0"][:3], key
+
+
 def test_dp_model_lane_kernel_gc_sweep(capi, monkeypatch):
     """k_dp_ml on extractions with 1 ... 27 chains (lanes), both register budgets: checked by the library's own
     PGPU_DP_VERIFY comparison with k_dp_dq on a GC sweep (1 ... 27 models per extraction) and against the oracle"""
