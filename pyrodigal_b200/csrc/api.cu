@@ -101,6 +101,7 @@ struct pgpu_ctx {
     // Optional: host-input calls (pgpu_find_genes_batch) on large batches run as sub-batches on two worker threads /
     // streams ("lanes"), so that the H2D copy, the host planning gaps and the D2H of one hide under the kernels of the other.
     // Device-resident batches (pgpu_batch_run) stay on the single stream, so per-kernel timings remain well defined.
+    int lanes_resident = 0;                // PGPU_LANES_RESIDENT=1: two lanes for device-resident batches too
     int lanes = 2;                         // PGPU_LANES=1 disables.  Measured on the 630 Mbp bench shard (round 2): 98.8 ms per
                                            // end-to-end step with two lanes against 105 ms with one (the 11 ms input copy of
                                            // the second half hides under the kernels of the first)
@@ -522,7 +523,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         contigs[c].aoff = offsets[lo + c] - abase;
         contigs[c].slen = (int)len;
         contigs[c].mask_off = 0; contigs[c].n_masks = 0; contigs[c].pad = 0;
-        dtot += ((len + 16 + 127) / 128) * 128;
+        dtot += ((len + 64 + 127) / 128) * 128;   // >= 3 * dic_plane(len) (common.cuh) + the 16 padding bytes of digits / cod
         for (int64_t s = 0; s < len; s += 4096) tiles.push_back(make_int2(c, (int)s));
     }
     const int64_t atot = offsets[hi] - abase;
@@ -1417,7 +1418,7 @@ static int check_opts(pgpu_ctx *ctx, const pgpu_opts *o) {
 // state; the partial results are stitched together in sub-batch order afterwards.  The lane streams are forked
 // from / joined to the context's stream with events, so work queued on that stream (e.g. the stopwatch events of
 // pgpu_timer_*) still brackets the whole call.
-static int run_lanes(pgpu_ctx *ctx, const uint8_t *h_seq, const int64_t *offsets, int n, const pgpu_opts &opts,
+static int run_lanes(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, const int64_t *offsets, int n, const pgpu_opts &opts,
                      RunPlan &plan, const std::vector<std::pair<int, int>> &ranges, pgpu_result *res) {
     if (!ctx->lane_stream[0]) {
         for (int k = 0; k < 2; k++) {
@@ -1469,7 +1470,7 @@ static int run_lanes(pgpu_ctx *ctx, const uint8_t *h_seq, const int64_t *offsets
                 cudaEventRecord(h2d_ev[p], st);
                 h2d_issued[p].store(1);
             };
-            prc[p] = run_range(&L, h_seq, nullptr, offsets, ranges[p].first, ranges[p].second, opts, pl, r, nullptr);
+            prc[p] = run_range(&L, h_seq, d_seq, offsets, ranges[p].first, ranges[p].second, opts, pl, r, nullptr);
             h2d_issued[p].store(1);  // also when the sub-batch failed before its copy: nobody may wait forever
             if (prc[p]) { perr[p] = L.err; break; }
         }
@@ -1555,7 +1556,9 @@ static int run_all(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, co
     }
     size_t limit = ctx->ws_limit ? ctx->ws_limit : (size_t)(0.6 * (double)freeb);
     const int64_t total_bp = n > 0 ? offsets[n] - offsets[0] : 0;
-    const int lanes = (h_seq && !d_seq && ctx->lanes > 1 && n >= 2 && total_bp >= ctx->lane_min_bp) ? 2 : 1;
+    // (a device-resident batch runs on two lanes as well when PGPU_LANES_RESIDENT=1: the host planning gaps and the
+    // low-parallelism tail of one half under the kernels of the other)
+    const int lanes = ((d_seq ? ctx->lanes_resident != 0 : h_seq != nullptr) && ctx->lanes > 1 && n >= 2 && total_bp >= ctx->lane_min_bp) ? 2 : 1;
     const int64_t bp_budget = std::max<int64_t>((int64_t)(limit / 160) / lanes, 1 << 20);
     RunPlan plan;
     std::vector<std::pair<int, int>> ranges;
@@ -1582,7 +1585,7 @@ static int run_all(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, co
             if (rc) { delete res; return rc; }
         }
     } else {
-        rc = run_lanes(ctx, h_seq, offsets, n, *opts, plan, ranges, res);
+        rc = run_lanes(ctx, h_seq, d_seq, offsets, n, *opts, plan, ranges, res);
         tr("lanes joined");
         if (rc) { delete res; return rc; }
     }
@@ -1625,6 +1628,7 @@ int pgpu_create(int device, pgpu_ctx **out) {
     if (const char *a = getenv("PGPU_CODON_LUT")) ctx->codon_lut = atoi(a) != 0;
     if (const char *a = getenv("PGPU_CODING_SMEM")) ctx->coding_smem = atoi(a);
     if (const char *a = getenv("PGPU_LANES")) ctx->lanes = atoi(a);
+    if (const char *a = getenv("PGPU_LANES_RESIDENT")) ctx->lanes_resident = atoi(a);
     if (const char *a = getenv("PGPU_LANE_MIN_BP")) ctx->lane_min_bp = atoll(a);
     if (const char *a = getenv("PGPU_WS_LIMIT_MB")) ctx->ws_limit = (size_t)atoll(a) << 20;   // = pgpu_set_workspace_limit
     // keep freed blocks cached in the stream-ordered pool: sub-batches reuse them without going to the driver

@@ -132,8 +132,12 @@ struct DevBatch {
     const uint8_t *ascii;
     uint8_t *digits;
     uint8_t *cod;
-    uint16_t *dic_f;      // per base: index of the forward 6-mer starting here = cod[p] | cod[p+3] << 6
-    uint16_t *dic_r;      // per base p: reverse-strand 6-mer whose first codon has its 5' base at p (N indexes as C)
+    // dicodon (6-mer) indices, per contig three FRAME PLANES of dic_plane(slen) elements each (at doff): a coding-score walk
+    // visits every third base, so in a plane its indices are consecutive 2-byte elements (16-byte loads of eight codons)
+    uint16_t *dic_f;      // plane p % 3, element p / 3: index of the forward 6-mer starting at p = cod[p] | cod[p+3] << 6
+    uint16_t *dic_r;      // plane p % 3, element dic_plane - 1 - p / 3 (REVERSED, so that walking away from a stop means
+                          // decreasing elements on both strands): reverse-strand 6-mer whose first codon has its 5' base at
+                          // p (N indexes as C)
     uint32_t *gcbits;     // 1 bit per base: not A / not T (unknown bases count as GC, _sequence.h:35-43)
     int32_t *gcpre;       // exclusive prefix of popcount(gcbits) per 32-base word
     ContigInfo *contigs;
@@ -266,6 +270,9 @@ __device__ __forceinline__ void mbar_expect(uint64_t *, uint32_t) {}
 __device__ __forceinline__ void bulk_copy(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
 __device__ __forceinline__ void mbar_wait(uint64_t *, uint32_t) {}
 #endif
+
+// elements of one frame plane of the dicodon index arrays: ceil(slen / 3) plus slack for whole 16-byte chunks, a multiple of 8
+__host__ __device__ inline int dic_plane(int slen) { return ((slen + 2) / 3 + 8 + 7) & ~7; }
 
 // ---- device helpers ------------------------------------------------------------------------------
 

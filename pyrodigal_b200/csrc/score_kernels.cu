@@ -235,43 +235,27 @@ __device__ __forceinline__ void coding_orf_thread(const DevBatch &B, const DevMo
     const bool rev = c & CLS_REV;
 
     // sweep A: dicodon log-odds accumulated from the stop towards each start (lib.pyx:2149-2173); the 6-mer index of
-    // every position is precomputed (k_dicodon_index), so a codon costs one 2-byte load and one weight load
+    // every position is precomputed (k_dicodon_index, frame planes: a walk reads consecutive elements downwards on both
+    // strands), so a codon costs one 2-byte load and one weight load
     int far = -1, last = my;
     double acc = 0.0;
-    if (!rev) {
-        for (int i = z - 1; i >= 0; i--) {
-            int ci = cls[i];
-            if ((ci & CLS_REV) || cls_frame(ci) != f) continue;
-            if (cls_is_stop(ci)) break;
-            const int ni = ndx[i];
-            int j = last - 3;
-            for (; j - 9 >= ni; j -= 12) {   // four independent loads in flight, adds in the reference's order
-                const double w0 = __ldg(&dc[dicf[j]]), w1 = __ldg(&dc[dicf[j - 3]]), w2 = __ldg(&dc[dicf[j - 6]]),
-                             w3 = __ldg(&dc[dicf[j - 9]]);
-                acc += w0; acc += w1; acc += w2; acc += w3;
-            }
-            for (; j >= ni; j -= 3) acc += __ldg(&dc[dicf[j]]);
-            cscore[i] = acc;
-            last = ni;
-            far = i;
+    const int P = dic_plane(C.slen);
+    const uint16_t *__restrict__ pl = (rev ? dicr : dicf) + (my % 3) * P;
+    for (int i = rev ? z + 1 : z - 1; rev ? i < nn : i >= 0; i += rev ? 1 : -1) {
+        int ci = cls[i];
+        if (((ci & CLS_REV) != 0) != rev || cls_frame(ci) != f) continue;
+        if (cls_is_stop(ci)) break;
+        const int ni = ndx[i];
+        const uint16_t *__restrict__ q = pl + (rev ? P - 2 - last / 3 : last / 3 - 1);
+        int rem = rev ? (ni - last) / 3 : (last - ni) / 3;
+        for (; rem >= 4; rem -= 4, q -= 4) {   // four independent loads in flight, adds in the reference's order
+            const double w0 = __ldg(&dc[q[0]]), w1 = __ldg(&dc[q[-1]]), w2 = __ldg(&dc[q[-2]]), w3 = __ldg(&dc[q[-3]]);
+            acc += w0; acc += w1; acc += w2; acc += w3;
         }
-    } else {
-        for (int i = z + 1; i < nn; i++) {
-            int ci = cls[i];
-            if (!(ci & CLS_REV) || cls_frame(ci) != f) continue;
-            if (cls_is_stop(ci)) break;
-            const int ni = ndx[i];
-            int j = last + 3;
-            for (; j + 9 <= ni; j += 12) {
-                const double w0 = __ldg(&dc[dicr[j]]), w1 = __ldg(&dc[dicr[j + 3]]), w2 = __ldg(&dc[dicr[j + 6]]),
-                             w3 = __ldg(&dc[dicr[j + 9]]);
-                acc += w0; acc += w1; acc += w2; acc += w3;
-            }
-            for (; j <= ni; j += 3) acc += __ldg(&dc[dicr[j]]);
-            cscore[i] = acc;
-            last = ni;
-            far = i;
-        }
+        for (; rem > 0; rem--, q--) acc += __ldg(&dc[q[0]]);
+        cscore[i] = acc;
+        last = ni;
+        far = i;
     }
     if (far < 0) return;
 
@@ -325,75 +309,44 @@ constexpr int kOrfWarps = 8;
 template <class WF>
 __device__ __forceinline__ void coding_orf_lane(const uint8_t *__restrict__ cls, const int32_t *__restrict__ ndx,
                                                 const int32_t *__restrict__ sv, const uint16_t *__restrict__ dicf,
-                                                const uint16_t *__restrict__ dicr, int nn, int z, int f, int my, bool rev,
+                                                const uint16_t *__restrict__ dicr, int P, int nn, int z, int f, int my, bool rev,
                                                 bool active, double *__restrict__ cscore, const DevModel &M, WF Wt) {
     // sweep A: dicodon log-odds accumulated from the stop towards each start (lib.pyx:2149-2173).  The chain
     // (index load -> weight load -> add) is latency bound: eight codons per round while at least eight remain
     // (their loads are independent and in flight together), then 4 / 2 / 1; adds keep the reference's order.
+    // The indices of a walk are consecutive elements of one frame plane, downwards on both strands (DevBatch::dic_f).
     int far = -1, last = my;
     double acc = 0.0;
-    if (!rev) {
-        for (int i = z - 1; i >= 0; i--) {
-            const int ci = cls[i];
-            if ((ci & CLS_REV) || cls_frame(ci) != f) continue;
-            if (cls_is_stop(ci)) break;
-            const int ni = ndx[i];
-            const uint16_t *__restrict__ q = dicf + (last - 3);  // codons q[0], q[-3], ... down to position ni
-            int rem = (last - ni) / 3;
+    const uint16_t *__restrict__ pl = (rev ? dicr : dicf) + (my % 3) * P;
+    for (int i = rev ? z + 1 : z - 1; rev ? i < nn : i >= 0; i += rev ? 1 : -1) {
+        const int ci = cls[i];
+        if (((ci & CLS_REV) != 0) != rev || cls_frame(ci) != f) continue;
+        if (cls_is_stop(ci)) break;
+        const int ni = ndx[i];
+        const uint16_t *__restrict__ q = pl + (rev ? P - 2 - last / 3 : last / 3 - 1);
+        int rem = rev ? (ni - last) / 3 : (last - ni) / 3;
 #pragma unroll 1
-            for (; rem >= 8; rem -= 8, q -= 24) {
-                const uint32_t i0 = q[0], i1 = q[-3], i2 = q[-6], i3 = q[-9], i4 = q[-12], i5 = q[-15], i6 = q[-18], i7 = q[-21];
-                const double w0 = Wt(i0), w1 = Wt(i1), w2 = Wt(i2), w3 = Wt(i3), w4 = Wt(i4), w5 = Wt(i5), w6 = Wt(i6), w7 = Wt(i7);
-                acc += w0; acc += w1; acc += w2; acc += w3; acc += w4; acc += w5; acc += w6; acc += w7;
-            }
-            if (rem & 4) {
-                const uint32_t i0 = q[0], i1 = q[-3], i2 = q[-6], i3 = q[-9];
-                const double w0 = Wt(i0), w1 = Wt(i1), w2 = Wt(i2), w3 = Wt(i3);
-                acc += w0; acc += w1; acc += w2; acc += w3;
-                q -= 12;
-            }
-            if (rem & 2) {
-                const uint32_t i0 = q[0], i1 = q[-3];
-                const double w0 = Wt(i0), w1 = Wt(i1);
-                acc += w0; acc += w1;
-                q -= 6;
-            }
-            if (rem & 1) acc += Wt(q[0]);
-            if (active) cscore[i] = acc;
-            last = ni;
-            far = i;
+        for (; rem >= 8; rem -= 8, q -= 8) {
+            const uint32_t i0 = q[0], i1 = q[-1], i2 = q[-2], i3 = q[-3], i4 = q[-4], i5 = q[-5], i6 = q[-6], i7 = q[-7];
+            const double w0 = Wt(i0), w1 = Wt(i1), w2 = Wt(i2), w3 = Wt(i3), w4 = Wt(i4), w5 = Wt(i5), w6 = Wt(i6), w7 = Wt(i7);
+            acc += w0; acc += w1; acc += w2; acc += w3; acc += w4; acc += w5; acc += w6; acc += w7;
         }
-    } else {
-        for (int i = z + 1; i < nn; i++) {
-            const int ci = cls[i];
-            if (!(ci & CLS_REV) || cls_frame(ci) != f) continue;
-            if (cls_is_stop(ci)) break;
-            const int ni = ndx[i];
-            const uint16_t *__restrict__ q = dicr + (last + 3);  // codons q[0], q[3], ... up to position ni
-            int rem = (ni - last) / 3;
-#pragma unroll 1
-            for (; rem >= 8; rem -= 8, q += 24) {
-                const uint32_t i0 = q[0], i1 = q[3], i2 = q[6], i3 = q[9], i4 = q[12], i5 = q[15], i6 = q[18], i7 = q[21];
-                const double w0 = Wt(i0), w1 = Wt(i1), w2 = Wt(i2), w3 = Wt(i3), w4 = Wt(i4), w5 = Wt(i5), w6 = Wt(i6), w7 = Wt(i7);
-                acc += w0; acc += w1; acc += w2; acc += w3; acc += w4; acc += w5; acc += w6; acc += w7;
-            }
-            if (rem & 4) {
-                const uint32_t i0 = q[0], i1 = q[3], i2 = q[6], i3 = q[9];
-                const double w0 = Wt(i0), w1 = Wt(i1), w2 = Wt(i2), w3 = Wt(i3);
-                acc += w0; acc += w1; acc += w2; acc += w3;
-                q += 12;
-            }
-            if (rem & 2) {
-                const uint32_t i0 = q[0], i1 = q[3];
-                const double w0 = Wt(i0), w1 = Wt(i1);
-                acc += w0; acc += w1;
-                q += 6;
-            }
-            if (rem & 1) acc += Wt(q[0]);
-            if (active) cscore[i] = acc;
-            last = ni;
-            far = i;
+        if (rem & 4) {
+            const uint32_t i0 = q[0], i1 = q[-1], i2 = q[-2], i3 = q[-3];
+            const double w0 = Wt(i0), w1 = Wt(i1), w2 = Wt(i2), w3 = Wt(i3);
+            acc += w0; acc += w1; acc += w2; acc += w3;
+            q -= 4;
         }
+        if (rem & 2) {
+            const uint32_t i0 = q[0], i1 = q[-1];
+            const double w0 = Wt(i0), w1 = Wt(i1);
+            acc += w0; acc += w1;
+            q -= 2;
+        }
+        if (rem & 1) acc += Wt(q[0]);
+        if (active) cscore[i] = acc;
+        last = ni;
+        far = i;
     }
     if (far < 0) return;
 
@@ -472,7 +425,7 @@ __global__ void __launch_bounds__(32 * kOrfWarps, MINB) k_coding_orf(DevBatch B,
         const DevModel &M = models[C.model];
         // this lane's column of the transposed table; a weight address is one 32x32->64 multiply-add from it
         const char *__restrict__ wcol = (const char *)(B.dcT + M.col);
-        coding_orf_lane(cls, ndx, sv, dicf, dicr, nn, z, f, my, rev, active, B.cscore + C.coff, M, [&](uint32_t index) -> double {
+        coding_orf_lane(cls, ndx, sv, dicf, dicr, dic_plane(X.slen), nn, z, f, my, rev, active, B.cscore + C.coff, M, [&](uint32_t index) -> double {
             return *(const double *)(wcol + (uint64_t)index * (uint64_t)(kDcCols * sizeof(double)));
         });
     }
@@ -549,7 +502,7 @@ __global__ void __launch_bounds__(kCqThreads, 1) k_coding_smem(DevBatch B, const
         const bool active = chain >= 0;
         const ChainInfo *__restrict__ C = B.chains + (active ? chain : B.cq_chain[4 * r]);
         const double *__restrict__ wcol = tab + lane;
-        coding_orf_lane(cls, ndx, B.stop_val + node_off, B.dic_f + doff, B.dic_r + doff, nn, z, cls_frame(c), ndx[z],
+        coding_orf_lane(cls, ndx, B.stop_val + node_off, B.dic_f + doff, B.dic_r + doff, dic_plane(X->slen), nn, z, cls_frame(c), ndx[z],
                         (c & CLS_REV) != 0, active, B.cscore + C->coff, models[C->model],
                         [&](uint32_t index) -> double { return wcol[index * kCqCols]; });
     }

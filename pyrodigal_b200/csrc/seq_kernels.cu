@@ -98,18 +98,24 @@ __device__ __forceinline__ int rev_codon_at(const uint8_t *__restrict__ d, const
     }
     return r;
 }
+// frame-planar layout (DevBatch::dic_f / dic_r): the tile covers the elements [1366 j, 1366 (j + 1)) of every plane, i.e. all
+// positions of its 4096 bases; consecutive threads write consecutive elements of one plane
 __global__ void __launch_bounds__(256) k_dicodon_index(DevBatch B, const int2 *__restrict__ tiles) {
     const int2 tile = tiles[blockIdx.x];
     const ContigInfo ci = B.contigs[tile.x];
     const uint8_t *__restrict__ d = B.digits + ci.doff;
     const uint8_t *__restrict__ cod = B.cod + ci.doff;
+    const int P = dic_plane(ci.slen);
     uint16_t *__restrict__ df = B.dic_f + ci.doff;
     uint16_t *__restrict__ dr = B.dic_r + ci.doff;
-    for (int k = threadIdx.x; k < kTile; k += 256) {
-        const int p = tile.y + k;
-        if (p >= ci.slen) break;
-        df[p] = (uint16_t)((cod[p] & 63) | ((cod[p + 3] & 63) << 6));     // cod is zero padded past the end
-        dr[p] = p >= 5 ? (uint16_t)(rev_codon_at(d, cod, p) | (rev_codon_at(d, cod, p - 3) << 6)) : (uint16_t)0;
+    constexpr int kPer = (kTile + 2) / 3 + 1;   // 1366 elements per plane and tile
+    const int k0 = (tile.y / kTile) * kPer;
+    for (int t = threadIdx.x; t < 3 * kPer; t += 256) {
+        const int f = t / kPer, k = k0 + t % kPer;
+        const int p = 3 * k + f;
+        if (p >= ci.slen) continue;
+        df[f * P + k] = (uint16_t)((cod[p] & 63) | ((cod[p + 3] & 63) << 6));     // cod is zero padded past the end
+        dr[f * P + (P - 1 - k)] = p >= 5 ? (uint16_t)(rev_codon_at(d, cod, p) | (rev_codon_at(d, cod, p - 3) << 6)) : (uint16_t)0;
     }
 }
 
