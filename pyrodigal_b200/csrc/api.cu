@@ -101,7 +101,6 @@ struct pgpu_ctx {
     // Optional: host-input calls (pgpu_find_genes_batch) on large batches run as sub-batches on two worker threads /
     // streams ("lanes"), so that the H2D copy, the host planning gaps and the D2H of one hide under the kernels of the other.
     // Device-resident batches (pgpu_batch_run) stay on the single stream, so per-kernel timings remain well defined.
-    int lanes_resident = 0;                // PGPU_LANES_RESIDENT=1: two lanes for device-resident batches too
     int lanes = 2;                         // PGPU_LANES=1 disables.  Measured on the 630 Mbp bench shard (round 2): 98.8 ms per
                                            // end-to-end step with two lanes against 105 ms with one (the 11 ms input copy of
                                            // the second half hides under the kernels of the first)
@@ -403,7 +402,7 @@ static double window_high(double gc) { return fmax(0.35, 0.86596 * gc + 0.113199
 // to four neighbouring columns = plan entries; entries sorted by (first column = table set, lanes per ORF), every class
 // padded to whole CTA spans by an entry without extraction.  Leaves B.dcS null (=> k_coding_orf) when the chains of an
 // extraction are not on neighbouring columns (cannot happen with a GC window, but nothing here depends on it).
-static void plan_coding_smem(pgpu_ctx *ctx, DevPool &pool, DevBatch &B, const std::vector<ExtractInfo> &exts,
+static void plan_coding_smem(pgpu_ctx *ctx, DevPool &pool, DevBatch &B, int total_nodes, const std::vector<ExtractInfo> &exts,
                              const std::vector<ChainInfo> &chains, const std::vector<int32_t> &eoff,
                              const std::vector<int32_t> &elist) {
     const int n_ext = (int)exts.size();
@@ -476,6 +475,8 @@ static void plan_coding_smem(pgpu_ctx *ctx, DevPool &pool, DevBatch &B, const st
     B.cq_cta = pool.upload(cta);
     B.cq_span = span;
     B.cq_n_cta = n_cta;
+    B.olink = pool.alloc<int2>(total_nodes);
+    B.ilink = pool.alloc<int32_t>(total_nodes);
     if (!pool.failed) B.dcS = ctx->d_dcS;
 }
 
@@ -885,8 +886,8 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
             launch_block_owner_off(B.orf_toff, n_ext, 8, tab, st);
             B.orf_blk = tab;
             ctx->launches++;
-            if (ctx->coding_smem && ctx->d_dcS) plan_coding_smem(ctx, pool, B, exts, chains, h_eoff, h_elist);
-            if (trace) fprintf(stderr, "[pgpu] coding: %s, %d CTA spans of %d ORF slots\n", B.dcS ? "k_coding_smem" : "k_coding_orf", B.cq_n_cta, B.cq_span);
+            if (ctx->coding_smem && ctx->d_dcS) plan_coding_smem(ctx, pool, B, total_nodes, exts, chains, h_eoff, h_elist);
+            if (trace) fprintf(stderr, "[pgpu] coding: %s, %d CTA spans of %d ORF slots\n", B.dcS ? "k_coding_flat" : "k_coding_orf", B.cq_n_cta, B.cq_span);
         }
     }
     // Meta mode scores every (contig, model) chain "lean": per chain-node only the raw coding score, cs = cscore + sscore
@@ -1556,9 +1557,8 @@ static int run_all(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, co
     }
     size_t limit = ctx->ws_limit ? ctx->ws_limit : (size_t)(0.6 * (double)freeb);
     const int64_t total_bp = n > 0 ? offsets[n] - offsets[0] : 0;
-    // (a device-resident batch runs on two lanes as well when PGPU_LANES_RESIDENT=1: the host planning gaps and the
-    // low-parallelism tail of one half under the kernels of the other)
-    const int lanes = ((d_seq ? ctx->lanes_resident != 0 : h_seq != nullptr) && ctx->lanes > 1 && n >= 2 && total_bp >= ctx->lane_min_bp) ? 2 : 1;
+    // (device-resident batches stay on one stream: two lanes measured 6.43 against 6.48 Gbp/s on the bench shard)
+    const int lanes = (h_seq && !d_seq && ctx->lanes > 1 && n >= 2 && total_bp >= ctx->lane_min_bp) ? 2 : 1;
     const int64_t bp_budget = std::max<int64_t>((int64_t)(limit / 160) / lanes, 1 << 20);
     RunPlan plan;
     std::vector<std::pair<int, int>> ranges;
@@ -1628,7 +1628,6 @@ int pgpu_create(int device, pgpu_ctx **out) {
     if (const char *a = getenv("PGPU_CODON_LUT")) ctx->codon_lut = atoi(a) != 0;
     if (const char *a = getenv("PGPU_CODING_SMEM")) ctx->coding_smem = atoi(a);
     if (const char *a = getenv("PGPU_LANES")) ctx->lanes = atoi(a);
-    if (const char *a = getenv("PGPU_LANES_RESIDENT")) ctx->lanes_resident = atoi(a);
     if (const char *a = getenv("PGPU_LANE_MIN_BP")) ctx->lane_min_bp = atoll(a);
     if (const char *a = getenv("PGPU_WS_LIMIT_MB")) ctx->ws_limit = (size_t)atoll(a) << 20;   // = pgpu_set_workspace_limit
     // keep freed blocks cached in the stream-ordered pool: sub-batches reuse them without going to the driver

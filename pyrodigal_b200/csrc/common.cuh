@@ -215,6 +215,11 @@ struct DevBatch {
     const int32_t *cq_chain;   // [4 * r + k]: chain of lane k, or -1
     const int32_t *cq_cta;     // [n_cta + 1]: plan entry that holds the first slot of every CTA span
     int32_t cq_span, cq_n_cta;
+    // ORF links (k_orf_links; only with the plan above): the in-frame starts of an ORF as a list that begins at its STOP node
+    int2 *olink;               // per node: x = next in-frame start further away from the stop (-1: none), y = the element of
+                               //   that start in its frame plane of dic_f / dic_r (where the walk towards it ends)
+    int32_t *ilink;            // start: previous in-frame start towards the stop, or the STOP node itself;
+                               //   STOP: the start of its ORF that is furthest away (-1: none)
     // per chain results
     int32_t *chain_ipath;
     double *chain_score;

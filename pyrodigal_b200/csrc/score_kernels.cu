@@ -432,22 +432,65 @@ __global__ void __launch_bounds__(32 * kOrfWarps, MINB) k_coding_orf(DevBatch B,
 }
 
 // --------------------------------------------------------------------------------------------------
-// raw coding score with the dicodon tables in shared memory (k_coding_smem).  k_coding_orf gathers its weights from
-// the 2 MB transposed table through L1 / L2 (ncu: 70 % of the stall samples long-scoreboard, L1 hit rate 54 %).  Here a
-// CTA owns the weights of kCqCols neighbouring table columns -- the models are sorted by (translation table, GC), the
-// chains of an extraction are a contiguous column range, cut into groups of up to four -- as one 128 KB table
-// dcS[set][index][4], fetched once with 1-D bulk copies (TMA, cp.async.bulk + mbarrier) and then read with LDS.64.
-// Work items are (extraction, column group, STOP node) = "ORF slots", planned on the host (api.cu: plan entries sorted
-// by (table set, lanes per ORF), every class padded to whole CTA spans, so a CTA has ONE table set and ONE group width
-// W = 1 / 2 / 4).  The groups of W lanes take slots from a shared-memory counter: a group that drew a short ORF simply
-// draws the next one, so the lanes stay busy whatever the ORF lengths are.  Per (ORF, model) the operations and their
-// order are those of k_coding_orf (coding_orf_lane).
+// raw coding score with the dicodon tables in shared memory: k_orf_links + k_coding_flat + k_coding_pen.
+// k_coding_orf gathers its weights from the 2 MB transposed table through L1 / L2 (ncu: 70 % of the stall samples
+// long-scoreboard, L1 hit rate 54 %).  Here a CTA owns the weights of kCqCols neighbouring table columns -- the models are
+// sorted by (translation table, GC), the chains of an extraction are a contiguous column range, cut into groups of up to
+// four -- as one 128 KB table dcS[set][index][4], fetched once with 1-D bulk copies (TMA, cp.async.bulk + mbarrier) and
+// then read with LDS.64.  Work items are (extraction, column group, STOP node) = "ORF slots", planned on the host
+// (api.cu: plan entries sorted by (table set, lanes per ORF), every class padded to whole CTA spans, so a CTA has ONE
+// table set and ONE group width W = 1 / 2 / 4).
+//
+// With four models per table a warp has to walk 8 ... 32 ORFs at once, and ORFs differ in length by orders of magnitude.
+// A first version let every group of W lanes run the nested loops of coding_orf_lane on its own ORF: ncu showed 5.7
+// active lanes per LDS instruction (the groups of a warp were serialised) and 21.4 ms against the 19.5 ms of
+// k_coding_orf.  k_coding_flat therefore runs ONE warp-uniform loop: per round every group adds up to eight codons of
+// its current walk (predicated), and the rare transitions -- a start reached: store the sum, continue with the next
+// start of the ORF; ORF finished: draw the next slot from a shared-memory counter -- are short divergent blocks.
+//   * the starts of an ORF are a linked list from its STOP node (k_orf_links, once per extraction instead of a node
+//     scan per model), so a transition is one 8-byte load that was requested when the previous start was reached;
+//   * the indices of a walk are consecutive elements of a frame plane (DevBatch::dic_f): eight codons = one aligned
+//     16-byte load, requested one chunk ahead;
+//   * the penalty sweeps (lib.pyx:2175-2236) walk the list backwards in a kernel of their own (k_coding_pen, lanes over
+//     the chains of an extraction like k_coding_orf).
+// Per (ORF, model) the additions and their order are those of the reference.
 // --------------------------------------------------------------------------------------------------
 constexpr int kCqThreads = 1024;
 constexpr int kCqCols = 4;
 constexpr int kCqTableBytes = 4096 * kCqCols * (int)sizeof(double);   // 128 KB
 
-__global__ void __launch_bounds__(kCqThreads, 1) k_coding_smem(DevBatch B, const DevModel *__restrict__ models) {
+// one thread per STOP node: the in-frame starts of its ORF, nearest first
+__global__ void __launch_bounds__(128) k_orf_links(DevBatch B, int n_ext, int total_nodes) {
+    __shared__ int s_first;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    int e = ext_hint(B, n_ext, min(g, total_nodes - 1), blockIdx.x * blockDim.x, total_nodes, &s_first);
+    if (g >= total_nodes) return;
+    while (e + 1 < n_ext && B.exts[e + 1].node_off <= g) e++;
+    const ExtractInfo *__restrict__ X = B.exts + e;
+    const int node_off = X->node_off, nn = X->nn, z = g - node_off;
+    const uint8_t *__restrict__ cls = B.cls + node_off;
+    const int c = cls[z];
+    if (!cls_is_stop(c)) return;
+    const int32_t *__restrict__ ndx = B.ndx + node_off;
+    int2 *__restrict__ olink = B.olink + node_off;
+    int32_t *__restrict__ ilink = B.ilink + node_off;
+    const bool rev = (c & CLS_REV) != 0;
+    const int f = cls_frame(c), P = dic_plane(X->slen);
+    int prev = z;
+    for (int i = rev ? z + 1 : z - 1; rev ? i < nn : i >= 0; i += rev ? 1 : -1) {
+        const int ci = cls[i];
+        if (((ci & CLS_REV) != 0) != rev || cls_frame(ci) != f) continue;
+        if (cls_is_stop(ci)) break;
+        olink[prev] = make_int2(i, rev ? P - 1 - ndx[i] / 3 : ndx[i] / 3);
+        ilink[i] = prev;
+        prev = i;
+    }
+    olink[prev] = make_int2(-1, 0);
+    ilink[z] = prev == z ? -1 : prev;
+}
+
+// sweep A (see above).  Group state lives in registers, replicated in the W lanes of a group.
+__global__ void __launch_bounds__(kCqThreads, 1) k_coding_flat(DevBatch B, const DevModel *__restrict__ models) {
 #ifdef PGPU_HOST_EMULATION
     static double tab_store[4096 * kCqCols];
     double *tab = tab_store;
@@ -477,34 +520,132 @@ __global__ void __launch_bounds__(kCqThreads, 1) k_coding_smem(DevBatch B, const
     const int lane = threadIdx.x & (W - 1);
     const unsigned gmask = W == 4 ? 0xFu << (threadIdx.x & 28) : W == 2 ? 0x3u << (threadIdx.x & 30) : 0u;
     const int64_t slot0 = (int64_t)blockIdx.x * span;
+    const double *__restrict__ wcol = tab + lane;
     int r = r0;
-    for (;;) {
-        int slot = 0;
-        if (lane == 0) slot = atomicAdd(&s_next, 1);
-        if (W > 1) slot = __shfl_sync(gmask, slot, 0, W);
-        if (slot >= span) break;
-        const int64_t gs = slot0 + slot;
-        while (r < r1 && B.cq_soff[r + 1] <= gs) r++;   // slots are drawn in increasing order
-        const int e = B.cq_ext[r];
-        if (e < 0) continue;   // padding entry
-        const int tl = (int)(gs - B.cq_soff[r]);
-        const int32_t *__restrict__ cbase = B.cbase + 4 * e;
-        const ExtractInfo *__restrict__ X = B.exts + e;
-        const int nn = X->nn, node_off = X->node_off;
-        const int n_fe = cbase[2] - cbase[1], n_re = nn - cbase[3];
-        if (tl >= n_fe + n_re) continue;
-        const int z = (B.clist + node_off)[tl < n_fe ? cbase[1] + tl : cbase[3] + (tl - n_fe)];
-        const uint8_t *__restrict__ cls = B.cls + node_off;
-        const int32_t *__restrict__ ndx = B.ndx + node_off;
-        const int64_t doff = X->doff;
-        const int c = cls[z];
-        const int chain = B.cq_chain[4 * r + lane];
-        const bool active = chain >= 0;
-        const ChainInfo *__restrict__ C = B.chains + (active ? chain : B.cq_chain[4 * r]);
-        const double *__restrict__ wcol = tab + lane;
-        coding_orf_lane(cls, ndx, B.stop_val + node_off, B.dic_f + doff, B.dic_r + doff, dic_plane(X->slen), nn, z, cls_frame(c), ndx[z],
-                        (c & CLS_REV) != 0, active, B.cscore + C->coff, models[C->model],
-                        [&](uint32_t index) -> double { return wcol[index * kCqCols]; });
+    // the walk of this group: elements k_cur, k_cur - 1, ... lo of plane pl lead to start node seg (sum so far: acc);
+    // nxt = the start after it.  k_cur < lo: a transition is due.
+    const uint16_t *__restrict__ pl = nullptr;
+    const int2 *__restrict__ olink = nullptr;
+    double *__restrict__ cscore = nullptr;
+    int k_cur = -1, lo = 0, seg = -1;
+    int2 nxt = make_int2(-1, 0);
+    double acc = 0.0;
+    uint4 v = make_uint4(0, 0, 0, 0), vn = make_uint4(0, 0, 0, 0);   // chunk [vbase, vbase + 8) and the one below it
+    int vbase = -16;
+    bool done = false;
+    while (!__all_sync(0xffffffffu, done)) {
+        if (!done && k_cur < lo) {
+            if (seg >= 0 && cscore) cscore[seg] = acc;
+            if (nxt.x >= 0) {   // next start of the same ORF
+                seg = nxt.x; lo = nxt.y;
+                nxt = olink[seg];
+            } else {            // next ORF
+                seg = -1;
+                for (;;) {
+                    int slot = 0;
+                    if (lane == 0) slot = atomicAdd(&s_next, 1);
+                    if (W > 1) slot = __shfl_sync(gmask, slot, 0, W);
+                    if (slot >= span) { done = true; break; }
+                    const int64_t gs = slot0 + slot;
+                    while (r < r1 && B.cq_soff[r + 1] <= gs) r++;   // slots are drawn in increasing order
+                    const int e = B.cq_ext[r];
+                    if (e < 0) { done = true; break; }   // class padding: nothing behind it in this span
+                    const int tl = (int)(gs - B.cq_soff[r]);
+                    const int32_t *__restrict__ cbase = B.cbase + 4 * e;
+                    const ExtractInfo *__restrict__ X = B.exts + e;
+                    const int nn = X->nn, node_off = X->node_off;
+                    const int n_fe = cbase[2] - cbase[1], n_re = nn - cbase[3];
+                    if (tl >= n_fe + n_re) {   // the rest of this entry's slots is empty: move the counter past them
+                        if (lane == 0) atomicMax(&s_next, (int)(B.cq_soff[r + 1] - slot0));
+                        continue;
+                    }
+                    const int z = (B.clist + node_off)[tl < n_fe ? cbase[1] + tl : cbase[3] + (tl - n_fe)];
+                    olink = B.olink + node_off;
+                    const int2 first = olink[z];
+                    if (first.x < 0) continue;
+                    const int cz = B.cls[node_off + z], my = B.ndx[node_off + z], P = dic_plane(X->slen);
+                    const bool rev = (cz & CLS_REV) != 0;
+                    pl = (rev ? B.dic_r : B.dic_f) + X->doff + (my % 3) * P;
+                    k_cur = rev ? P - 2 - my / 3 : my / 3 - 1;
+                    seg = first.x; lo = first.y;
+                    nxt = olink[seg];
+                    const int chain = B.cq_chain[4 * r + lane];
+                    cscore = chain >= 0 ? B.cscore + B.chains[chain].coff : nullptr;
+                    acc = 0.0;
+                    vbase = -16;
+                    break;
+                }
+            }
+        }
+        if (!done && k_cur >= lo) {
+            const int base = k_cur & ~7;
+            if (base != vbase) {
+                if (base == vbase - 8) v = vn; else v = *reinterpret_cast<const uint4 *>(pl + base);
+                vbase = base;
+                if (base >= 8) vn = *reinterpret_cast<const uint4 *>(pl + base - 8);   // needed unless the ORF ends in this chunk
+            }
+            const int hi_t = k_cur - base, lo_t = max(lo - base, 0);
+            // (indices are masked: elements outside [lo_t, hi_t] may be anything, their weights are loaded and dropped)
+            const double w7 = wcol[((v.w >> 16) & 0xfffu) * kCqCols], w6 = wcol[(v.w & 0xfffu) * kCqCols];
+            const double w5 = wcol[((v.z >> 16) & 0xfffu) * kCqCols], w4 = wcol[(v.z & 0xfffu) * kCqCols];
+            const double w3 = wcol[((v.y >> 16) & 0xfffu) * kCqCols], w2 = wcol[(v.y & 0xfffu) * kCqCols];
+            const double w1 = wcol[((v.x >> 16) & 0xfffu) * kCqCols], w0 = wcol[(v.x & 0xfffu) * kCqCols];
+            if (hi_t >= 7 && lo_t <= 7) acc += w7;
+            if (hi_t >= 6 && lo_t <= 6) acc += w6;
+            if (hi_t >= 5 && lo_t <= 5) acc += w5;
+            if (hi_t >= 4 && lo_t <= 4) acc += w4;
+            if (hi_t >= 3 && lo_t <= 3) acc += w3;
+            if (hi_t >= 2 && lo_t <= 2) acc += w2;
+            if (hi_t >= 1 && lo_t <= 1) acc += w1;
+            if (lo_t <= 0) acc += w0;
+            k_cur = base + lo_t - 1;
+        }
+    }
+}
+
+// sweeps B of the ORF that ends at STOP node z (the two penalty passes fused, from the start furthest away back to the
+// stop: lib.pyx:2175-2236), for the chain of this lane; the starts come from the ORF links
+__device__ __forceinline__ void coding_pen_lane(const int32_t *__restrict__ ilink, const int32_t *__restrict__ ndx,
+                                                const int32_t *__restrict__ sv, int z, bool rev, bool active,
+                                                double *__restrict__ cscore, const DevModel &M) {
+    double s2 = -10000.0, s3 = -10000.0;
+    for (int i = ilink[z]; i != z && i >= 0; i = ilink[i]) {
+        double cs = active ? cscore[i] : 0.0;
+        if (cs > s2) s2 = cs; else cs -= (s2 - cs);
+        const double gsize = rev ? (((double)ndx[i] - sv[i]) + 3.0) / 3.0 : (((double)sv[i] - ndx[i]) + 3.0) / 3.0;
+        double lfac;
+        if (gsize > 1000.0) lfac = M.lfac_span * (gsize - 80) / 920.0;
+        else lfac = M.lfac[(int)gsize];
+        if (lfac > s3) s3 = lfac; else lfac -= fmax(fmin(s3 - lfac, lfac), 0.0);
+        if (lfac > 3.0 && cs < 0.5 * lfac) cs = 0.5 * lfac;
+        cs += lfac;
+        if (active) cscore[i] = cs;
+    }
+}
+
+// thread layout of the grouped k_coding_orf (orf_toff / orf_w / orf_blk): W lanes per STOP node, one lane per chain
+__global__ void __launch_bounds__(256) k_coding_pen(DevBatch B, const DevModel *__restrict__ models, int n_ext) {
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gt >= B.orf_toff[n_ext]) return;
+    int r = B.orf_blk[gt >> 8];
+    while (r + 1 < n_ext && B.orf_toff[r + 1] <= gt) r++;
+    const int W = B.orf_w[r];
+    const int local = (int)(gt - B.orf_toff[r]);
+    const int e = B.orf_ext[r];
+    const int tl = local / W, lane = local % W;
+    const ExtractInfo *__restrict__ X = B.exts + e;
+    const int32_t *__restrict__ cbase = B.cbase + 4 * e;
+    const int nn = X->nn, node_off = X->node_off;
+    const int n_fe = cbase[2] - cbase[1], n_re = nn - cbase[3];
+    if (tl >= n_fe + n_re) return;
+    const int z = (B.clist + node_off)[tl < n_fe ? cbase[1] + tl : cbase[3] + (tl - n_fe)];
+    const bool rev = tl >= n_fe;
+    const int ch0 = B.ext_chain_off[e], nch = B.ext_chain_off[e + 1] - ch0;
+    for (int c0 = 0; c0 < nch; c0 += W) {
+        const bool active = c0 + lane < nch;
+        const ChainInfo *__restrict__ C = B.chains + B.ext_chains[ch0 + (active ? c0 + lane : 0)];
+        coding_pen_lane(B.ilink + node_off, B.ndx + node_off, B.stop_val + node_off, z, rev, active, B.cscore + C->coff,
+                        models[C->model]);
     }
 }
 
@@ -1071,13 +1212,15 @@ void launch_coding(const DevBatch &B, const DevModel *models, int n_chains, int6
                    cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
     if (B.ext_chains && B.dcS && B.cq_n_cta > 0 && total_nodes > 0) {   // dicodon tables in shared memory
+        k_orf_links<<<(total_nodes + 127) / 128, 128, 0, st>>>(B, n_ext, total_nodes);
 #ifdef PGPU_HOST_EMULATION
-        k_coding_smem<<<(unsigned)B.cq_n_cta, kCqThreads, 0, st>>>(B, models);
+        k_coding_flat<<<(unsigned)B.cq_n_cta, kCqThreads, 0, st>>>(B, models);
 #else
-        static const cudaError_t attr = cudaFuncSetAttribute(k_coding_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, kCqTableBytes);
+        static const cudaError_t attr = cudaFuncSetAttribute(k_coding_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, kCqTableBytes);
         (void)attr;
-        k_coding_smem<<<(unsigned)B.cq_n_cta, kCqThreads, kCqTableBytes, st>>>(B, models);
+        k_coding_flat<<<(unsigned)B.cq_n_cta, kCqThreads, kCqTableBytes, st>>>(B, models);
 #endif
+        k_coding_pen<<<(unsigned)((B.orf_threads + 255) / 256), 256, 0, st>>>(B, models, n_ext);
     } else if (B.ext_chains && B.dcT && n_ext > 0 && total_nodes > 0) {
         static const int minb = getenv("PGPU_CODING_MINB") ? atoi(getenv("PGPU_CODING_MINB")) : 5;  // A/B switch
         if (B.orf_toff) {  // grouped mapping planned by the host (api.cu)
