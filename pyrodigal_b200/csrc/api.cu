@@ -398,14 +398,17 @@ struct OperatorOut {  // operator-level outputs (single contig)
 static double window_low(double gc) { return fmin(0.65, 0.88495 * gc - 0.0102337); }
 static double window_high(double gc) { return fmax(0.35, 0.86596 * gc + 0.1131991); }
 
-// Plan of k_coding_smem (score_kernels.cu): the chains of every extraction in table-column order, cut into groups of up
-// to four neighbouring columns = plan entries; entries sorted by (first column = table set, lanes per ORF), every class
-// padded to whole CTA spans by an entry without extraction.  Leaves B.dcS null (=> k_coding_orf) when the chains of an
-// extraction are not on neighbouring columns (cannot happen with a GC window, but nothing here depends on it).
+// Plan of k_coding_flat (score_kernels.cu): the chains of every extraction in table-column order, cut into groups of up
+// to four neighbouring columns = plan entries; entries sorted by class = (first column = table set, lanes per ORF), every
+// class followed by a padding entry.  The ORF slots of the entries are laid out on the device (k_cq_plan: the number of
+// STOP nodes of an extraction is only known there); the host bounds the number of CTA spans.  Leaves B.dcS null
+// (=> k_coding_orf) when the chains of an extraction are not on neighbouring columns (cannot happen with a GC window, but
+// nothing here depends on it) or the index arrays are too large for 32-bit element offsets.
 static void plan_coding_smem(pgpu_ctx *ctx, DevPool &pool, DevBatch &B, int total_nodes, const std::vector<ExtractInfo> &exts,
                              const std::vector<ChainInfo> &chains, const std::vector<int32_t> &eoff,
                              const std::vector<int32_t> &elist) {
     const int n_ext = (int)exts.size();
+    if (B.dic_r - B.dic_f >= (int64_t)1 << 30 || total_nodes <= 0) return;
     struct Ent { int32_t ext, key; int32_t chain[4]; };
     std::vector<Ent> ents;
     ents.reserve((size_t)n_ext * 4);
@@ -426,14 +429,15 @@ static void plan_coding_smem(pgpu_ctx *ctx, DevPool &pool, DevBatch &B, int tota
             t.key = (c0 + k) * 4 + (w >= 3 ? 2 : w - 1);   // (table set, log2 of the lanes per ORF)
             for (int q = 0; q < 4; q++) t.chain[q] = q < w ? tmp[k + q] : -1;
             ents.push_back(t);
-            slots += exts[e].nn / 2 + 1;
+            slots += exts[e].nn / 2;
         }
     }
     if (ents.empty()) return;
-    // CTA span: about eight spans per SM when the batch is large enough, between 1024 and 16384 ORF slots
-    int span = 16384;
-    while (span > 1024 && slots / span < 148 * 8) span >>= 1;
-    // counting sort by key, then offsets with the class padding
+    // CTA span: about eight spans per SM when the batch is large enough, between 1024 and 16384 ORF slots (the bound
+    // nn / 2 counts about twice the STOP nodes there are)
+    int span = 8192, shift = 13;
+    while (span > 1024 && slots / 2 / span < 148 * 8) { span >>= 1; shift--; }
+    // counting sort by class, a padding entry behind every class
     const int n_keys = kDcCols * 4;
     std::vector<int32_t> first(n_keys + 1, 0);
     for (const Ent &t : ents) first[t.key + 1]++;
@@ -443,40 +447,45 @@ static void plan_coding_smem(pgpu_ctx *ctx, DevPool &pool, DevBatch &B, int tota
         std::vector<int32_t> fill(first.begin(), first.end() - 1);
         for (size_t i = 0; i < ents.size(); i++) order[fill[ents[i].key]++] = (int32_t)i;
     }
-    std::vector<int64_t> soff;
-    std::vector<int32_t> pext, pchain;
-    soff.reserve(ents.size() + n_keys + 1); pext.reserve(ents.size() + n_keys); pchain.reserve(4 * (ents.size() + n_keys));
-    int64_t at = 0;
+    std::vector<int32_t> pext, pchain, phs0;
+    std::vector<int64_t> pcbase;
+    std::vector<uint8_t> pcls;
+    const size_t cap = ents.size() + n_keys;
+    pext.reserve(cap); pcls.reserve(cap); phs0.reserve(cap); pchain.reserve(4 * cap); pcbase.reserve(4 * cap);
+    int64_t max_cta = 0;
     for (int k = 0; k < n_keys; k++) {
         if (first[k + 1] == first[k]) continue;
+        int64_t bound = 0;
         for (int i = first[k]; i < first[k + 1]; i++) {
             const Ent &t = ents[order[i]];
-            soff.push_back(at); pext.push_back(t.ext);
-            for (int q = 0; q < 4; q++) pchain.push_back(t.chain[q]);
-            at += exts[t.ext].nn / 2 + 1;
+            pext.push_back(t.ext); pcls.push_back((uint8_t)k); phs0.push_back((exts[t.ext].node_off + 1) >> 1);
+            for (int q = 0; q < 4; q++) {
+                pchain.push_back(t.chain[q]);
+                pcbase.push_back(t.chain[q] >= 0 ? chains[t.chain[q]].coff - exts[t.ext].node_off : INT64_MIN);
+            }
+            bound += exts[t.ext].nn / 2;
         }
-        if (at % span) {   // padding entry up to the next span boundary
-            soff.push_back(at); pext.push_back(-1);
-            for (int q = 0; q < 4; q++) pchain.push_back(-1);
-            at += span - at % span;
-        }
+        pext.push_back(-1); pcls.push_back((uint8_t)k); phs0.push_back(0);
+        for (int q = 0; q < 4; q++) { pchain.push_back(-1); pcbase.push_back(INT64_MIN); }
+        max_cta += (bound + span - 1) / span;
     }
-    soff.push_back(at);
-    const int n_ent = (int)pext.size(), n_cta = (int)(at / span);
-    std::vector<int32_t> cta(n_cta + 1);
-    for (int c = 0, r = 0; c < n_cta; c++) {
-        while (soff[r + 1] <= (int64_t)c * span) r++;
-        cta[c] = r;
-    }
-    cta[n_cta] = n_ent - 1;
-    B.cq_soff = pool.upload(soff);
-    B.cq_ext = pool.upload(pext);
-    B.cq_chain = pool.upload(pchain);
-    B.cq_cta = pool.upload(cta);
+    std::vector<int32_t> colmodel(kDcCols, 0);
+    for (int m = 0; m < ctx->n_models; m++) colmodel[ctx->h_models[m].col] = m;
+    B.cq_n_ent = (int)pext.size();
     B.cq_span = span;
-    B.cq_n_cta = n_cta;
-    B.olink = pool.alloc<int2>(total_nodes);
-    B.ilink = pool.alloc<int32_t>(total_nodes);
+    B.cq_span_shift = shift;
+    B.cq_max_cta = (int)max_cta;
+    B.cq_ext = pool.upload(pext);
+    B.cq_cls = pool.upload(pcls);
+    B.cq_chain = pool.upload(pchain);
+    B.cq_cbase = pool.upload(pcbase);
+    B.cq_hs0 = pool.upload(phs0);
+    B.cq_colmodel = pool.upload(colmodel);
+    B.cq_soff = pool.alloc<int32_t>(pext.size() + 1);
+    B.cq_cta = pool.alloc<int32_t>((size_t)max_cta + 2);
+    B.cq_ncta = pool.alloc<int32_t>(1);
+    B.link = pool.alloc<int4>(total_nodes);
+    B.orfd = pool.alloc<int4>((size_t)(total_nodes + 1) / 2 + 2);
     if (!pool.failed) B.dcS = ctx->d_dcS;
 }
 
@@ -545,8 +554,8 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     // no memset: k_encode writes every byte that is ever read (whole 16-byte groups, zero padded past the end)
     B.digits = pool.alloc<uint8_t>(dtot + 256);
     B.cod = pool.alloc<uint8_t>(dtot + 256);
-    B.dic_f = pool.alloc<uint16_t>(dtot + 256);
-    B.dic_r = pool.alloc<uint16_t>(dtot + 256);
+    B.dic_f = pool.alloc<uint16_t>(2 * (dtot + 256));   // one buffer: k_coding_flat addresses both by offsets from dic_f
+    B.dic_r = B.dic_f ? B.dic_f + dtot + 256 : nullptr;
     B.contigs = pool.upload(contigs);
     const int64_t gcwords = dtot / 32 + 8;
     B.gcbits = pool.alloc<uint32_t>(gcwords);
@@ -887,7 +896,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
             B.orf_blk = tab;
             ctx->launches++;
             if (ctx->coding_smem && ctx->d_dcS) plan_coding_smem(ctx, pool, B, total_nodes, exts, chains, h_eoff, h_elist);
-            if (trace) fprintf(stderr, "[pgpu] coding: %s, %d CTA spans of %d ORF slots\n", B.dcS ? "k_coding_flat" : "k_coding_orf", B.cq_n_cta, B.cq_span);
+            if (trace) fprintf(stderr, "[pgpu] coding: %s, at most %d CTA spans of %d ORF slots\n", B.dcS ? "k_coding_flat" : "k_coding_orf", B.cq_max_cta, B.cq_span);
         }
     }
     // Meta mode scores every (contig, model) chain "lean": per chain-node only the raw coding score, cs = cscore + sscore

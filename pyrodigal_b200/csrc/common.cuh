@@ -206,20 +206,29 @@ struct DevBatch {
     const uint8_t *orf_w;
     const int32_t *orf_blk;
     int64_t orf_threads;
-    // shared-memory mapping of the raw coding score (k_coding_smem; optional, nullptr = k_coding_orf): plan entries
-    // r = (extraction, up to four chains on neighbouring table columns), sorted by (table set, lanes per ORF); entry r owns
-    // the ORF slots [cq_soff[r], cq_soff[r + 1]); classes are padded to whole CTA spans by entries with cq_ext = -1
+    // shared-memory mapping of the raw coding score (k_coding_flat; optional, dcS == nullptr => k_coding_orf).  Plan entries
+    // r = (extraction, up to four chains on neighbouring table columns), sorted by class = (table set, lanes per ORF); every
+    // class ends with a padding entry (cq_ext = -1) that fills the last CTA span of the class.  The host plans the entries,
+    // the device counts the STOP nodes and lays out the ORF slots (k_cq_plan): entry r owns [cq_soff[r], cq_soff[r + 1]).
     const double *dcS;         // table sets: dcS[(s * 4096 + index) * 4 + k] = dicodon weight `index` of table column s + k
-    const int64_t *cq_soff;
-    const int32_t *cq_ext;
+    const int32_t *cq_ext;     // extraction of entry r (-1: padding)
+    const uint8_t *cq_cls;     // class of entry r
     const int32_t *cq_chain;   // [4 * r + k]: chain of lane k, or -1
-    const int32_t *cq_cta;     // [n_cta + 1]: plan entry that holds the first slot of every CTA span
-    int32_t cq_span, cq_n_cta;
-    // ORF links (k_orf_links; only with the plan above): the in-frame starts of an ORF as a list that begins at its STOP node
-    int2 *olink;               // per node: x = next in-frame start further away from the stop (-1: none), y = the element of
-                               //   that start in its frame plane of dic_f / dic_r (where the walk towards it ends)
-    int32_t *ilink;            // start: previous in-frame start towards the stop, or the STOP node itself;
-                               //   STOP: the start of its ORF that is furthest away (-1: none)
+    const int64_t *cq_cbase;   // [4 * r + k]: chain-node offset of lane k's chain minus the extraction's node offset
+                               //   (cscore[cq_cbase + batch node index]), INT64_MIN = no chain
+    const int32_t *cq_hs0;     // first ORF descriptor of entry r's extraction
+    const int32_t *cq_colmodel;// model on table column c
+    int32_t *cq_soff;          // [n_ent + 1], device
+    int32_t *cq_cta;           // [max CTAs + 1], device: plan entry that holds the first slot of every CTA span
+    int32_t *cq_ncta;          // device: number of CTA spans in use
+    int32_t cq_n_ent, cq_span, cq_span_shift, cq_max_cta;
+    // ORF links and descriptors (k_orf_links), in batch node indices / element offsets from dic_f (dic_r lies behind it)
+    int4 *link;                // start node: x = next in-frame start further away from the stop (-1: none), y = the element
+                               //   where the walk towards that start ends, z = previous start towards the stop (or the STOP
+                               //   node), w = distance to the stop position (ORF length - 3)
+    int4 *orfd;                // per STOP node, at ((node_off + 1) >> 1) + rank among the STOP nodes of its extraction:
+                               //   x = element of the first codon of the walk, y = first start (-1: none), z = element
+                               //   where the walk to it ends, w = the STOP node
     // per chain results
     int32_t *chain_ipath;
     double *chain_score;

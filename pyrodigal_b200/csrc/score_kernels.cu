@@ -432,35 +432,39 @@ __global__ void __launch_bounds__(32 * kOrfWarps, MINB) k_coding_orf(DevBatch B,
 }
 
 // --------------------------------------------------------------------------------------------------
-// raw coding score with the dicodon tables in shared memory: k_orf_links + k_coding_flat + k_coding_pen.
+// raw coding score with the dicodon tables in shared memory: k_orf_links + k_cq_plan + k_coding_flat.
 // k_coding_orf gathers its weights from the 2 MB transposed table through L1 / L2 (ncu: 70 % of the stall samples
 // long-scoreboard, L1 hit rate 54 %).  Here a CTA owns the weights of kCqCols neighbouring table columns -- the models are
 // sorted by (translation table, GC), the chains of an extraction are a contiguous column range, cut into groups of up to
 // four -- as one 128 KB table dcS[set][index][4], fetched once with 1-D bulk copies (TMA, cp.async.bulk + mbarrier) and
-// then read with LDS.64.  Work items are (extraction, column group, STOP node) = "ORF slots", planned on the host
-// (api.cu: plan entries sorted by (table set, lanes per ORF), every class padded to whole CTA spans, so a CTA has ONE
-// table set and ONE group width W = 1 / 2 / 4).
+// then read with LDS.64.  Work items are (extraction, column group, STOP node) = "ORF slots": the host plans the entries
+// (api.cu: sorted by class = (table set, lanes per ORF), so that a CTA has ONE table set and ONE group width W = 1 / 2 /
+// 4), the device counts the STOP nodes and lays the slots out without gaps (k_cq_plan), classes padded to whole CTA spans.
 //
 // With four models per table a warp has to walk 8 ... 32 ORFs at once, and ORFs differ in length by orders of magnitude.
-// A first version let every group of W lanes run the nested loops of coding_orf_lane on its own ORF: ncu showed 5.7
-// active lanes per LDS instruction (the groups of a warp were serialised) and 21.4 ms against the 19.5 ms of
-// k_coding_orf.  k_coding_flat therefore runs ONE warp-uniform loop: per round every group adds up to eight codons of
-// its current walk (predicated), and the rare transitions -- a start reached: store the sum, continue with the next
-// start of the ORF; ORF finished: draw the next slot from a shared-memory counter -- are short divergent blocks.
-//   * the starts of an ORF are a linked list from its STOP node (k_orf_links, once per extraction instead of a node
-//     scan per model), so a transition is one 8-byte load that was requested when the previous start was reached;
-//   * the indices of a walk are consecutive elements of a frame plane (DevBatch::dic_f): eight codons = one aligned
+// Measured on the way (630 Mbp bench shard, k_coding_orf = 19.5 ms): every group of W lanes running the nested loops of
+// coding_orf_lane on its own ORF: 5.7 active lanes per LDS instruction, 21.4 ms; one warp-uniform loop with the node scan
+// replaced by ORF links, but six dependent loads to set up an ORF and the penalty sweeps in a kernel of their own: 12.7 +
+// 9.0 + 1.6 ms.  k_coding_flat therefore
+//   * runs ONE warp-uniform loop: per round every group adds up to eight codons of its current walk (predicated); the
+//     transitions -- a start reached: keep the sum, continue with the next start of the ORF; ORF finished: penalty
+//     sweeps, next slot from a shared-memory counter -- are short divergent blocks;
+//   * reads the starts of an ORF as a linked list from its STOP node (k_orf_links, once per extraction instead of a node
+//     scan per model) and everything an ORF needs from ONE 16-byte descriptor, requested one ORF ahead;
+//   * reads the indices of a walk as consecutive elements of a frame plane (DevBatch::dic_f): eight codons = one aligned
 //     16-byte load, requested one chunk ahead;
-//   * the penalty sweeps (lib.pyx:2175-2236) walk the list backwards in a kernel of their own (k_coding_pen, lanes over
-//     the chains of an extraction like k_coding_orf).
+//   * keeps the sums of the first eight starts of the ORF in shared memory for the penalty sweeps (lib.pyx:2175-2236),
+//     which run back from the last start at the end of the ORF: the raw sums never go to global memory.
 // Per (ORF, model) the additions and their order are those of the reference.
 // --------------------------------------------------------------------------------------------------
 constexpr int kCqThreads = 1024;
 constexpr int kCqCols = 4;
-constexpr int kCqTableBytes = 4096 * kCqCols * (int)sizeof(double);   // 128 KB
+constexpr int kCqRing = 8;
+constexpr int kCqTableBytes = 4096 * kCqCols * (int)sizeof(double);                 // 128 KB
+constexpr int kCqSmemBytes = kCqTableBytes + kCqRing * kCqThreads * (int)sizeof(double);   // + 64 KB
 
-// one thread per STOP node: the in-frame starts of its ORF, nearest first
-__global__ void __launch_bounds__(128) k_orf_links(DevBatch B, int n_ext, int total_nodes) {
+// one thread per STOP node: the in-frame starts of its ORF, nearest first (DevBatch::link, ::orfd)
+__global__ void __launch_bounds__(128) k_orf_links(DevBatch B, int n_ext, int total_nodes, int roff) {
     __shared__ int s_first;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     int e = ext_hint(B, n_ext, min(g, total_nodes - 1), blockIdx.x * blockDim.x, total_nodes, &s_first);
@@ -472,27 +476,100 @@ __global__ void __launch_bounds__(128) k_orf_links(DevBatch B, int n_ext, int to
     const int c = cls[z];
     if (!cls_is_stop(c)) return;
     const int32_t *__restrict__ ndx = B.ndx + node_off;
-    int2 *__restrict__ olink = B.olink + node_off;
-    int32_t *__restrict__ ilink = B.ilink + node_off;
+    const int32_t *__restrict__ sv = B.stop_val + node_off;
     const bool rev = (c & CLS_REV) != 0;
-    const int f = cls_frame(c), P = dic_plane(X->slen);
-    int prev = z;
+    const int f = cls_frame(c), P = dic_plane(X->slen), my = ndx[z];
+    const int plane = (rev ? roff : 0) + (int)X->doff + (my % 3) * P;
+    int4 d = make_int4(plane + (rev ? P - 2 - my / 3 : my / 3 - 1), -1, 0, g);
+    int prev = -1, pprev = g, pdiff = 0;   // the last start seen, the node before it, its distance to the stop
     for (int i = rev ? z + 1 : z - 1; rev ? i < nn : i >= 0; i += rev ? 1 : -1) {
         const int ci = cls[i];
         if (((ci & CLS_REV) != 0) != rev || cls_frame(ci) != f) continue;
         if (cls_is_stop(ci)) break;
-        olink[prev] = make_int2(i, rev ? P - 1 - ndx[i] / 3 : ndx[i] / 3);
-        ilink[i] = prev;
-        prev = i;
+        const int lo = plane + (rev ? P - 1 - ndx[i] / 3 : ndx[i] / 3);
+        if (prev < 0) { d.y = node_off + i; d.z = lo; }
+        else { B.link[prev] = make_int4(node_off + i, lo, pprev, pdiff); pprev = prev; }
+        prev = node_off + i;
+        pdiff = rev ? ndx[i] - sv[i] : sv[i] - ndx[i];
     }
-    olink[prev] = make_int2(-1, 0);
-    ilink[z] = prev == z ? -1 : prev;
+    if (prev >= 0) B.link[prev] = make_int4(-1, 0, pprev, pdiff);
+    const int32_t *__restrict__ cbase = B.cbase + 4 * e;
+    const int kind = cls_kind(c);   // 1 = +STOP, 3 = -STOP
+    const int tl = B.crank[4 * (int64_t)g + kind] + (kind == 3 ? cbase[2] - cbase[1] : 0);
+    B.orfd[((node_off + 1) >> 1) + tl] = d;
 }
 
-// sweep A (see above).  Group state lives in registers, replicated in the W lanes of a group.
+// ORF slots of the plan entries (one CTA): entry r gets as many slots as its extraction has STOP nodes, the padding
+// entry at the end of a class fills the class up to a whole number of CTA spans
+__global__ void __launch_bounds__(1024) k_cq_plan(DevBatch B) {
+    __shared__ int s_sum[256], s_base[256], s_gfirst[256], s_warp[32], s_carry;
+    const int n = B.cq_n_ent, tid = threadIdx.x;
+    int32_t *__restrict__ soff = B.cq_soff;
+    if (tid < 256) s_sum[tid] = 0;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    // exclusive prefix of the slot counts over all entries (padding entries count 0), class totals on the side
+    for (int r0 = 0; r0 < n; r0 += 1024) {
+        const int r = r0 + tid;
+        int v = 0;
+        if (r < n) {
+            const int e = B.cq_ext[r];
+            if (e >= 0) {
+                const int32_t *__restrict__ cbase = B.cbase + 4 * e;
+                v = (cbase[2] - cbase[1]) + (B.exts[e].nn - cbase[3]);
+                atomicAdd(&s_sum[B.cq_cls[r]], v);
+            }
+        }
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((tid & 31) >= o) x += y; }
+        if ((tid & 31) == 31) s_warp[tid >> 5] = x;
+        __syncthreads();
+        if (tid < 32) {
+            int w = s_warp[tid];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (tid >= o) w += y; }
+            s_warp[tid] = w;
+        }
+        __syncthreads();
+        const int excl = s_carry + (tid >= 32 ? s_warp[(tid >> 5) - 1] : 0) + x - v;
+        if (r < n) {
+            soff[r] = excl;
+            if (r == 0 || B.cq_cls[r - 1] != B.cq_cls[r]) s_gfirst[B.cq_cls[r]] = excl;
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        int at = 0;
+        const int span = B.cq_span;
+        for (int c = 0; c < 256; c++) {
+            s_base[c] = at;
+            at += (s_sum[c] + span - 1) / span * span;
+        }
+        soff[n] = at;
+        *B.cq_ncta = at / span;
+    }
+    __syncthreads();
+    for (int r = tid; r < n; r += 1024) {
+        const int c = B.cq_cls[r];
+        soff[r] = s_base[c] + (soff[r] - s_gfirst[c]);
+    }
+}
+
+// first plan entry of every CTA span
+__global__ void __launch_bounds__(128) k_cq_owner(DevBatch B) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B.cq_n_ent) return;
+    const int a = B.cq_soff[r], e = B.cq_soff[r + 1], sh = B.cq_span_shift;
+    for (int c = (a + (1 << sh) - 1) >> sh; (c << sh) < e; c++) B.cq_cta[c] = r;
+    if (r == B.cq_n_ent - 1) B.cq_cta[e >> sh] = r;
+}
+
 __global__ void __launch_bounds__(kCqThreads, 1) k_coding_flat(DevBatch B, const DevModel *__restrict__ models) {
 #ifdef PGPU_HOST_EMULATION
-    static double tab_store[4096 * kCqCols];
+    static double tab_store[4096 * kCqCols + kCqRing * kCqThreads];
     double *tab = tab_store;
 #else
     extern __shared__ __align__(128) unsigned char cq_dyn_smem[];
@@ -500,17 +577,19 @@ __global__ void __launch_bounds__(kCqThreads, 1) k_coding_flat(DevBatch B, const
 #endif
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_next;
+    if ((int)blockIdx.x >= *B.cq_ncta) return;
+    double *ring = tab + 4096 * kCqCols + threadIdx.x;   // sum of the j-th start of the current ORF: ring[j * kCqThreads]
     const int span = B.cq_span;
     const int r0 = B.cq_cta[blockIdx.x], r1 = B.cq_cta[blockIdx.x + 1];   // plan entries of this CTA's span: [r0, r1]
     const int first_chain = B.cq_chain[4 * r0];
-    if (first_chain < 0) return;   // a span of padding only (uniform for the CTA)
     int W = 1;
     if (B.cq_chain[4 * r0 + 2] >= 0) W = 4; else if (B.cq_chain[4 * r0 + 1] >= 0) W = 2;
+    const int set = models[B.chains[first_chain].model].col;
     if (threadIdx.x == 0) {
         s_next = 0;
         mbar_init(&s_bar, 1);
         mbar_init_fence();
-        const char *src = (const char *)(B.dcS + (size_t)models[B.chains[first_chain].model].col * (4096 * kCqCols));
+        const char *src = (const char *)(B.dcS + (size_t)set * (4096 * kCqCols));
         mbar_expect(&s_bar, kCqTableBytes);
         for (int k = 0; k < kCqTableBytes; k += 16384) bulk_copy((char *)tab + k, src + k, 16384, &s_bar);
     }
@@ -519,70 +598,95 @@ __global__ void __launch_bounds__(kCqThreads, 1) k_coding_flat(DevBatch B, const
 
     const int lane = threadIdx.x & (W - 1);
     const unsigned gmask = W == 4 ? 0xFu << (threadIdx.x & 28) : W == 2 ? 0x3u << (threadIdx.x & 30) : 0u;
-    const int64_t slot0 = (int64_t)blockIdx.x * span;
+    const int slot0 = blockIdx.x * span;
     const double *__restrict__ wcol = tab + lane;
+    const int mdl = set + lane < B.n_models ? B.cq_colmodel[set + lane] : 0;
+    const DevModel &M = models[mdl];
+    const uint16_t *__restrict__ dic = B.dic_f;
+    const int4 *__restrict__ link = B.link;
+    double *__restrict__ cscore = B.cscore;
     int r = r0;
-    // the walk of this group: elements k_cur, k_cur - 1, ... lo of plane pl lead to start node seg (sum so far: acc);
-    // nxt = the start after it.  k_cur < lo: a transition is due.
-    const uint16_t *__restrict__ pl = nullptr;
-    const int2 *__restrict__ olink = nullptr;
-    double *__restrict__ cscore = nullptr;
-    int k_cur = -1, lo = 0, seg = -1;
+    // next ORF: its descriptor, requested when the current ORF was set up (y == -2: no more slots)
+    int4 D1 = make_int4(0, -2, 0, 0);
+    int D1r = r0;
+    auto draw = [&]() {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(&s_next, 1);
+        if (W > 1) slot = __shfl_sync(gmask, slot, 0, W);
+        D1.y = -2;
+        if (slot >= span) return;
+        const int gs = slot0 + slot;
+        while (r < r1 && B.cq_soff[r + 1] <= gs) r++;   // slots are drawn in increasing order
+        if (B.cq_ext[r] < 0) return;                     // class padding: nothing behind it in this span
+        D1 = B.orfd[B.cq_hs0[r] + (gs - B.cq_soff[r])];
+        D1r = r;
+    };
+    draw();
+    // the walk of this group: elements k_cur, k_cur - 1, ... lo (offsets from dic) lead to start node seg (sum so far:
+    // acc), the cnt-th start of the ORF that ends at STOP node zstop; nxt = the start after it.  k_cur < lo: transition.
+    int k_cur = -1, lo = 0, seg = -1, cnt = 0, zstop = -1;
     int2 nxt = make_int2(-1, 0);
+    int64_t cb = INT64_MIN;
     double acc = 0.0;
     uint4 v = make_uint4(0, 0, 0, 0), vn = make_uint4(0, 0, 0, 0);   // chunk [vbase, vbase + 8) and the one below it
     int vbase = -16;
     bool done = false;
     while (!__all_sync(0xffffffffu, done)) {
         if (!done && k_cur < lo) {
-            if (seg >= 0 && cscore) cscore[seg] = acc;
-            if (nxt.x >= 0) {   // next start of the same ORF
-                seg = nxt.x; lo = nxt.y;
-                nxt = olink[seg];
-            } else {            // next ORF
-                seg = -1;
-                for (;;) {
-                    int slot = 0;
-                    if (lane == 0) slot = atomicAdd(&s_next, 1);
-                    if (W > 1) slot = __shfl_sync(gmask, slot, 0, W);
-                    if (slot >= span) { done = true; break; }
-                    const int64_t gs = slot0 + slot;
-                    while (r < r1 && B.cq_soff[r + 1] <= gs) r++;   // slots are drawn in increasing order
-                    const int e = B.cq_ext[r];
-                    if (e < 0) { done = true; break; }   // class padding: nothing behind it in this span
-                    const int tl = (int)(gs - B.cq_soff[r]);
-                    const int32_t *__restrict__ cbase = B.cbase + 4 * e;
-                    const ExtractInfo *__restrict__ X = B.exts + e;
-                    const int nn = X->nn, node_off = X->node_off;
-                    const int n_fe = cbase[2] - cbase[1], n_re = nn - cbase[3];
-                    if (tl >= n_fe + n_re) {   // the rest of this entry's slots is empty: move the counter past them
-                        if (lane == 0) atomicMax(&s_next, (int)(B.cq_soff[r + 1] - slot0));
-                        continue;
+            if (seg >= 0) {   // a start is reached
+                if (cnt < kCqRing) ring[cnt * kCqThreads] = acc;
+                else if (cb != INT64_MIN) cscore[cb + seg] = acc;
+                cnt++;
+                if (nxt.x >= 0) {   // on to the next start of the ORF
+                    seg = nxt.x; lo = nxt.y;
+                    const int4 L = link[seg];
+                    nxt = make_int2(L.x, L.y);
+                } else {
+                    // the ORF is finished: the two penalty sweeps, fused, from the last start back to the stop
+                    double s2 = -10000.0, s3 = -10000.0;
+                    const bool active = cb != INT64_MIN;
+                    for (int i = seg, j = cnt - 1; i != zstop; j--) {
+                        const int4 L = link[i];
+                        double cs = j < kCqRing ? ring[j * kCqThreads] : (active ? cscore[cb + i] : 0.0);
+                        if (cs > s2) s2 = cs; else cs -= (s2 - cs);
+                        const double gsize = ((double)L.w + 3.0) / 3.0;
+                        double lfac;
+                        if (gsize > 1000.0) lfac = M.lfac_span * (gsize - 80) / 920.0;
+                        else lfac = M.lfac[(int)gsize];
+                        if (lfac > s3) s3 = lfac; else lfac -= fmax(fmin(s3 - lfac, lfac), 0.0);
+                        if (lfac > 3.0 && cs < 0.5 * lfac) cs = 0.5 * lfac;
+                        cs += lfac;
+                        if (active) cscore[cb + i] = cs;
+                        i = L.z;
                     }
-                    const int z = (B.clist + node_off)[tl < n_fe ? cbase[1] + tl : cbase[3] + (tl - n_fe)];
-                    olink = B.olink + node_off;
-                    const int2 first = olink[z];
-                    if (first.x < 0) continue;
-                    const int cz = B.cls[node_off + z], my = B.ndx[node_off + z], P = dic_plane(X->slen);
-                    const bool rev = (cz & CLS_REV) != 0;
-                    pl = (rev ? B.dic_r : B.dic_f) + X->doff + (my % 3) * P;
-                    k_cur = rev ? P - 2 - my / 3 : my / 3 - 1;
-                    seg = first.x; lo = first.y;
-                    nxt = olink[seg];
-                    const int chain = B.cq_chain[4 * r + lane];
-                    cscore = chain >= 0 ? B.cscore + B.chains[chain].coff : nullptr;
-                    acc = 0.0;
-                    vbase = -16;
-                    break;
+                    seg = -1;
+                }
+            }
+            if (seg < 0) {   // next ORF
+                const int4 D = D1;
+                const int rr = D1r;
+                if (D.y == -2) {
+                    done = true;
+                } else {
+                    draw();
+                    if (D.y >= 0) {
+                        k_cur = D.x; seg = D.y; lo = D.z; zstop = D.w;
+                        const int4 L = link[seg];
+                        nxt = make_int2(L.x, L.y);
+                        cb = B.cq_cbase[4 * rr + lane];
+                        acc = 0.0;
+                        cnt = 0;
+                        vbase = -16;
+                    }
                 }
             }
         }
         if (!done && k_cur >= lo) {
             const int base = k_cur & ~7;
             if (base != vbase) {
-                if (base == vbase - 8) v = vn; else v = *reinterpret_cast<const uint4 *>(pl + base);
+                if (base == vbase - 8) v = vn; else v = *reinterpret_cast<const uint4 *>(dic + base);
                 vbase = base;
-                if (base >= 8) vn = *reinterpret_cast<const uint4 *>(pl + base - 8);   // needed unless the ORF ends in this chunk
+                if (base >= 8) vn = *reinterpret_cast<const uint4 *>(dic + base - 8);   // needed unless the ORF ends in this chunk
             }
             const int hi_t = k_cur - base, lo_t = max(lo - base, 0);
             // (indices are masked: elements outside [lo_t, hi_t] may be anything, their weights are loaded and dropped)
@@ -600,52 +704,6 @@ __global__ void __launch_bounds__(kCqThreads, 1) k_coding_flat(DevBatch B, const
             if (lo_t <= 0) acc += w0;
             k_cur = base + lo_t - 1;
         }
-    }
-}
-
-// sweeps B of the ORF that ends at STOP node z (the two penalty passes fused, from the start furthest away back to the
-// stop: lib.pyx:2175-2236), for the chain of this lane; the starts come from the ORF links
-__device__ __forceinline__ void coding_pen_lane(const int32_t *__restrict__ ilink, const int32_t *__restrict__ ndx,
-                                                const int32_t *__restrict__ sv, int z, bool rev, bool active,
-                                                double *__restrict__ cscore, const DevModel &M) {
-    double s2 = -10000.0, s3 = -10000.0;
-    for (int i = ilink[z]; i != z && i >= 0; i = ilink[i]) {
-        double cs = active ? cscore[i] : 0.0;
-        if (cs > s2) s2 = cs; else cs -= (s2 - cs);
-        const double gsize = rev ? (((double)ndx[i] - sv[i]) + 3.0) / 3.0 : (((double)sv[i] - ndx[i]) + 3.0) / 3.0;
-        double lfac;
-        if (gsize > 1000.0) lfac = M.lfac_span * (gsize - 80) / 920.0;
-        else lfac = M.lfac[(int)gsize];
-        if (lfac > s3) s3 = lfac; else lfac -= fmax(fmin(s3 - lfac, lfac), 0.0);
-        if (lfac > 3.0 && cs < 0.5 * lfac) cs = 0.5 * lfac;
-        cs += lfac;
-        if (active) cscore[i] = cs;
-    }
-}
-
-// thread layout of the grouped k_coding_orf (orf_toff / orf_w / orf_blk): W lanes per STOP node, one lane per chain
-__global__ void __launch_bounds__(256) k_coding_pen(DevBatch B, const DevModel *__restrict__ models, int n_ext) {
-    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gt >= B.orf_toff[n_ext]) return;
-    int r = B.orf_blk[gt >> 8];
-    while (r + 1 < n_ext && B.orf_toff[r + 1] <= gt) r++;
-    const int W = B.orf_w[r];
-    const int local = (int)(gt - B.orf_toff[r]);
-    const int e = B.orf_ext[r];
-    const int tl = local / W, lane = local % W;
-    const ExtractInfo *__restrict__ X = B.exts + e;
-    const int32_t *__restrict__ cbase = B.cbase + 4 * e;
-    const int nn = X->nn, node_off = X->node_off;
-    const int n_fe = cbase[2] - cbase[1], n_re = nn - cbase[3];
-    if (tl >= n_fe + n_re) return;
-    const int z = (B.clist + node_off)[tl < n_fe ? cbase[1] + tl : cbase[3] + (tl - n_fe)];
-    const bool rev = tl >= n_fe;
-    const int ch0 = B.ext_chain_off[e], nch = B.ext_chain_off[e + 1] - ch0;
-    for (int c0 = 0; c0 < nch; c0 += W) {
-        const bool active = c0 + lane < nch;
-        const ChainInfo *__restrict__ C = B.chains + B.ext_chains[ch0 + (active ? c0 + lane : 0)];
-        coding_pen_lane(B.ilink + node_off, B.ndx + node_off, B.stop_val + node_off, z, rev, active, B.cscore + C->coff,
-                        models[C->model]);
     }
 }
 
@@ -1211,16 +1269,17 @@ void launch_node_prep(const DevBatch &B, int n_ext, int total_nodes, int seq_par
 void launch_coding(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, int n_ext, int total_nodes,
                    cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
-    if (B.ext_chains && B.dcS && B.cq_n_cta > 0 && total_nodes > 0) {   // dicodon tables in shared memory
-        k_orf_links<<<(total_nodes + 127) / 128, 128, 0, st>>>(B, n_ext, total_nodes);
+    if (B.ext_chains && B.dcS && B.cq_max_cta > 0 && total_nodes > 0) {   // dicodon tables in shared memory
+        k_orf_links<<<(total_nodes + 127) / 128, 128, 0, st>>>(B, n_ext, total_nodes, (int)(B.dic_r - B.dic_f));
+        k_cq_plan<<<1, 1024, 0, st>>>(B);
+        k_cq_owner<<<(B.cq_n_ent + 127) / 128, 128, 0, st>>>(B);
 #ifdef PGPU_HOST_EMULATION
-        k_coding_flat<<<(unsigned)B.cq_n_cta, kCqThreads, 0, st>>>(B, models);
+        k_coding_flat<<<(unsigned)B.cq_max_cta, kCqThreads, 0, st>>>(B, models);
 #else
-        static const cudaError_t attr = cudaFuncSetAttribute(k_coding_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, kCqTableBytes);
+        static const cudaError_t attr = cudaFuncSetAttribute(k_coding_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, kCqSmemBytes);
         (void)attr;
-        k_coding_flat<<<(unsigned)B.cq_n_cta, kCqThreads, kCqTableBytes, st>>>(B, models);
+        k_coding_flat<<<(unsigned)B.cq_max_cta, kCqThreads, kCqSmemBytes, st>>>(B, models);
 #endif
-        k_coding_pen<<<(unsigned)((B.orf_threads + 255) / 256), 256, 0, st>>>(B, models, n_ext);
     } else if (B.ext_chains && B.dcT && n_ext > 0 && total_nodes > 0) {
         static const int minb = getenv("PGPU_CODING_MINB") ? atoi(getenv("PGPU_CODING_MINB")) : 5;  // A/B switch
         if (B.orf_toff) {  // grouped mapping planned by the host (api.cu)
