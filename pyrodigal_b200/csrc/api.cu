@@ -79,7 +79,7 @@ struct pgpu_ctx {
     std::vector<int> model_tt;
     RawTraining *d_raw = nullptr;
     DevModel *d_models = nullptr;
-    uint32_t *d_live = nullptr; // [n_models][2048] motif cells with a weight other than the floor (DevModel::mot_live)
+    uint32_t *d_live = nullptr; // [n_models][kMotifWords]: motif cells with a weight other than the floor (DevModel::mot_live) + window table (mot_hit)
     double *d_dcT = nullptr;   // dicodon weights transposed: [4096][kDcCols], columns sorted by (tt, gc); null if n_models > kDcCols
     double *d_dcS = nullptr;   // the same weights as table sets of four neighbouring columns: [n_models][4096][4] (k_coding_smem)
     int coding_smem = 1;       // PGPU_CODING_SMEM: 1 = k_coding_smem for multi-model batches, 0 = k_coding_orf
@@ -265,12 +265,33 @@ static void build_sd_masks() {
     g_sd_ready = true;
 }
 
-// 1 bit per motif cell: weight != -4.0 (host side of DevModel::mot_live)
+// Host side of DevModel::mot_live / mot_hit, kMotifWords words per model.
+// bits[0 .. 2047]: 1 bit per motif cell: weight != -4.0.
+// bits[2048 ..]  : 4096 uint16, indexed by six upstream bases x (2 bits each, the first base in the low bits): bit
+//   4 l + o is set when a motif of length l + 3 that starts at base o of the window MAY be live -- some live cell
+//   [l][*][index] agrees with the window on the min(l + 3, 6 - o) bases of the motif that lie inside the window.
+constexpr int kMotifWords = 4096;
 static void motif_live_bits(const RawTraining &r, uint32_t *bits) {
     const double *w = &r.mot_wt[0][0][0];
-    for (int k = 0; k < 2048; k++) bits[k] = 0;
+    for (int k = 0; k < kMotifWords; k++) bits[k] = 0;
     for (int c = 0; c < 4 * 4 * 4096; c++)
         if (!(w[c] == -4.0)) bits[c >> 5] |= 1u << (c & 31);
+    uint16_t *hit = reinterpret_cast<uint16_t *>(bits + 2048);
+    for (int l = 0; l < 4; l++)
+        for (int sp = 0; sp < 4; sp++)
+            for (int idx = 0; idx < (1 << (2 * (l + 3))); idx++) {
+                if (r.mot_wt[l][sp][idx] == -4.0) continue;
+                for (int o = 0; o < 4; o++) {
+                    const int nb = std::min(l + 3, 6 - o);          // bases of the motif inside the window
+                    const int known = idx & ((1 << (2 * nb)) - 1);
+                    // every window whose bases o .. o + nb - 1 equal `known`: the other 6 - nb bases are free
+                    for (int rest = 0; rest < (1 << (2 * (6 - nb))); rest++) {
+                        const int lowb = rest & ((1 << (2 * o)) - 1), highb = rest >> (2 * o);
+                        const int x = lowb | (known << (2 * o)) | (highb << (2 * (o + nb)));
+                        hit[x] |= (uint16_t)(1u << (4 * l + o));
+                    }
+                }
+            }
 }
 
 static void prepare_model(const RawTraining &r, DevModel &m, const RawTraining *d_raw_k, const uint32_t *d_live_k = nullptr) {
@@ -316,6 +337,7 @@ static void prepare_model(const RawTraining &r, DevModel &m, const RawTraining *
     m.gene_dc = d_raw_k->gene_dc;
     m.mot_wt = &d_raw_k->mot_wt[0][0][0];
     m.mot_live = d_live_k;
+    m.mot_hit = d_live_k ? reinterpret_cast<const uint16_t *>(d_live_k + 2048) : nullptr;
     for (int l = 0; l < 4; l++) {
         uint64_t f = 0;
         for (int sp = 0; sp < 4; sp++)
@@ -1699,11 +1721,11 @@ int pgpu_set_models(pgpu_ctx *ctx, const void *blobs, int n, size_t stride) {
         cudaError_t e;
         if ((e = cudaMalloc(&d_raw, n * sizeof(RawTraining))) != cudaSuccess) return e;
         if ((e = cudaMalloc(&d_models, n * sizeof(DevModel))) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&d_live, (size_t)n * 2048 * sizeof(uint32_t))) != cudaSuccess) return e;
-        std::vector<uint32_t> live((size_t)n * 2048);
-        for (int k = 0; k < n; k++) motif_live_bits(h_raw_v[k], live.data() + (size_t)k * 2048);
+        if ((e = cudaMalloc(&d_live, (size_t)n * kMotifWords * sizeof(uint32_t))) != cudaSuccess) return e;
+        std::vector<uint32_t> live((size_t)n * kMotifWords);
+        for (int k = 0; k < n; k++) motif_live_bits(h_raw_v[k], live.data() + (size_t)k * kMotifWords);
         if ((e = cudaMemcpy(d_live, live.data(), live.size() * sizeof(uint32_t), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
-        for (int k = 0; k < n; k++) prepare_model(h_raw_v[k], h_models[k], d_raw + k, d_live + (size_t)k * 2048);
+        for (int k = 0; k < n; k++) prepare_model(h_raw_v[k], h_models[k], d_raw + k, d_live + (size_t)k * kMotifWords);
         // transposed dicodon table: models that are evaluated together (same table, neighbouring GC) get
         // neighbouring columns, so the lanes of k_coding_orf read one or two cache lines per codon
         std::vector<int> ord(n);

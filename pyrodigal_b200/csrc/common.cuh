@@ -60,6 +60,8 @@ struct DevModel {
                                    // what all but a few dozen cells of a trained model hold); nullptr = always load
     uint64_t mot_pf[4];            // per motif length: bit (index & 63) set when any cell [len][*][index] is live; a
                                    // register-only pre-filter in front of mot_live (exactness never depends on it)
+    const uint16_t *mot_hit;       // [4096] by six upstream bases: which motifs (length, offset in the window) may be live
+                                   // (api.cu: motif_live_bits); with it the search only visits candidate windows
     int32_t col;                   // column of this model in the transposed dicodon table (sorted by tt, gc)
     int32_t pad;
 };

@@ -649,10 +649,11 @@ __global__ void __launch_bounds__(kCqThreads, 1) k_coding_flat(DevBatch B, const
                         const int4 L = link[i];
                         double cs = j < kCqRing ? ring[j * kCqThreads] : (active ? cscore[cb + i] : 0.0);
                         if (cs > s2) s2 = cs; else cs -= (s2 - cs);
-                        const double gsize = ((double)L.w + 3.0) / 3.0;
+                        // gsize = (L.w + 3) / 3.0 of coding_orf_lane: its integer part and the comparison with 1000 in
+                        // integer arithmetic (exact: L.w + 3 < 2^31), the division only for genes above 3 kbp
                         double lfac;
-                        if (gsize > 1000.0) lfac = M.lfac_span * (gsize - 80) / 920.0;
-                        else lfac = M.lfac[(int)gsize];
+                        if (L.w + 3 > 3000) lfac = M.lfac_span * (((double)L.w + 3.0) / 3.0 - 80) / 920.0;
+                        else lfac = M.lfac[(unsigned)(L.w + 3) / 3u];
                         if (lfac > s3) s3 = lfac; else lfac -= fmax(fmin(s3 - lfac, lfac), 0.0);
                         if (lfac > 3.0 && cs < 0.5 * lfac) cs = 0.5 * lfac;
                         cs += lfac;
@@ -791,26 +792,66 @@ __device__ __forceinline__ void start_score_eval(const DevBatch &B, const DevMod
             const double *__restrict__ mw = M.mot_wt;
             const uint32_t *__restrict__ live = M.mot_live;  // all but a few dozen cells hold the floor weight -4.0
             // A cell that is not live holds exactly -4.0 and cannot replace a maximum that is already >= -4.0 (the
-            // comparison is a strict ">"), so once the first window has been taken only live cells matter; the
-            // per-length prefix filter M.mot_pf answers "possibly live" from registers for almost every window.
+            // comparison is a strict ">"), so once the first window has been taken only live cells matter.
+            auto probe = [&](int l, int p) {   // window p of motif length l + 3 (0 <= start - 18 - l + p)
+                const int spacendx = p <= 2 ? 3 : (p <= 4 ? 2 : (p >= 11 ? 1 : 0));
+                const int index = (int)((U >> (2 * (3 - l + p))) & ((1u << (2 * (l + 3))) - 1u));
+                const int cell = (l * 4 + spacendx) * 4096 + index;
+                double sc = -4.0;
+                if (!live || ((__ldg(&live[cell >> 5]) >> (cell & 31)) & 1u)) sc = __ldg(&mw[cell]);
+                if (sc > max_sc) {
+                    max_sc = sc; max_spacendx = spacendx; max_spacer = 15 - p;   // = start - j - l - 3, j = start - 18 - l + p
+                    max_ndx = index; max_len = l + 3;
+                }
+            };
+            // Candidate windows from the model's table M.mot_hit: four lookups by six upstream bases each tell, for all
+            // 52 windows at once, which can hold a live cell; the window the reference visits first is taken
+            // unconditionally.  (A live weight below the floor would break the argument: generic loop then.)
+            const uint16_t *__restrict__ hit = M.mot_hit;
+            bool generic = !hit || !live;
+            if (!generic) {
+                int l1 = -1, p1 = 0;
 #pragma unroll
-            for (int l = 3; l >= 0; l--) {
-                const uint32_t lmask = (1u << (2 * (l + 3))) - 1u;
-                const uint64_t pf = M.mot_pf[l];
-                if (pf == 0 && max_sc >= -4.0) continue;
+                for (int l = 3; l >= 0; l--) {
+                    const int pm = max(0, 18 + l - start);
+                    if (l1 < 0 && pm <= 12) { l1 = l; p1 = pm; }
+                }
+                if (l1 >= 0) {
+                    probe(l1, p1);
+                    if (max_sc < -4.0) {
+                        generic = true;
+                        max_sc = -100.0;
+                    } else {
+                        const uint32_t e0 = __ldg(&hit[(uint32_t)U & 0xfffu]), e4 = __ldg(&hit[(uint32_t)(U >> 8) & 0xfffu]),
+                                       e8 = __ldg(&hit[(uint32_t)(U >> 16) & 0xfffu]), e12 = __ldg(&hit[(uint32_t)(U >> 24) & 0xfffu]);
 #pragma unroll
-                for (int p = 0; p < 13; p++) {
-                    const int j = start - 18 - l + p;
-                    if (j < 0) continue;
-                    const int spacendx = p <= 2 ? 3 : (p <= 4 ? 2 : (p >= 11 ? 1 : 0));
-                    const int index = (int)((U >> (2 * (3 - l + p))) & lmask);
-                    if (!((pf >> (index & 63)) & 1ull) && max_sc >= -4.0) continue;
-                    const int cell = (l * 4 + spacendx) * 4096 + index;
-                    double sc = -4.0;
-                    if (!live || ((__ldg(&live[cell >> 5]) >> (cell & 31)) & 1u)) sc = __ldg(&mw[cell]);
-                    if (sc > max_sc) {
-                        max_sc = sc; max_spacendx = spacendx; max_spacer = start - j - l - 3;
-                        max_ndx = index; max_len = l + 3;
+                        for (int l = 3; l >= 0; l--) {
+                            const int pm = max(0, 18 + l - start);
+                            if (pm > 12) continue;
+                            // bit b: a motif of this length that starts at upstream base b = 3 - l + p
+                            uint32_t cand = ((e0 >> (4 * l)) & 15u) | (((e4 >> (4 * l)) & 15u) << 4) | (((e8 >> (4 * l)) & 15u) << 8) |
+                                            (((e12 >> (4 * l)) & 15u) << 12);
+                            cand &= ((1u << (16 - l)) - 1u) & ~((1u << (3 - l + pm)) - 1u);
+                            while (cand) {
+                                const int bpos = __ffs(cand) - 1;
+                                cand &= cand - 1;
+                                probe(l, bpos - 3 + l);
+                            }
+                        }
+                    }
+                }
+            }
+            if (generic) {
+#pragma unroll
+                for (int l = 3; l >= 0; l--) {
+                    const uint64_t pf = M.mot_pf[l];
+                    if (pf == 0 && max_sc >= -4.0) continue;
+#pragma unroll
+                    for (int p = 0; p < 13; p++) {
+                        if (start - 18 - l + p < 0) continue;
+                        const int index = (int)((U >> (2 * (3 - l + p))) & ((1u << (2 * (l + 3))) - 1u));
+                        if (!((pf >> (index & 63)) & 1ull) && max_sc >= -4.0) continue;
+                        probe(l, p);
                     }
                 }
             }

@@ -100,7 +100,7 @@ def test_extract_nodes_masked(ctx, capi, mask_size):
 
 
 @pytest.mark.parametrize("length,gc,seed", [(10000, .5, 21), (2500, .4, 22), (60000, .6, 23), (900, .55, 24)])
-@pytest.mark.parametrize("model", [0, 2, 11, 24, 33, 49])
+@pytest.mark.parametrize("model", [0, 2, 8, 11, 12, 24, 33, 49])
 @pytest.mark.parametrize("is_meta", [True, False])
 def test_score_nodes(ctx, capi, length, gc, seed, model, is_meta):
     seq = R.synth(length, gc, seed)
