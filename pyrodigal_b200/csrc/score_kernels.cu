@@ -712,19 +712,6 @@ __global__ void __launch_bounds__(kCqThreads, 1) k_coding_flat(DevBatch B, const
 // start scoring: RBS / upstream motif / type / upstream composition / penalties (lib.pyx:2331-2487)
 // --------------------------------------------------------------------------------------------------
 
-// Per-model tables of the start scoring in shared memory (k_start_score_lean): slot s = the s-th chain a CTA touches, its
-// upstream-composition weights DevModel::uc (32 x 4 doubles) followed by the SD table DevModel::sd_best (2 x 15 x 64
-// bytes).  Through the DevModel in global memory every one of the 32 + 30 lookups of a start costs a 64-bit address
-// computation on top of the load (22 instructions per composition term in the ncu source view); from shared memory it
-// is a shift, a mask and an LDS with an immediate offset.
-constexpr int kScoreSlots = 4;
-constexpr int kScoreSlotBytes = 32 * 4 * 8 + 2 * 15 * 64;   // 2944
-#ifdef PGPU_HOST_EMULATION
-alignas(16) static unsigned char score_tabs[kScoreSlots * kScoreSlotBytes];
-#else
-extern __shared__ __align__(16) unsigned char score_tabs[];
-#endif
-
 // What scoring a start needs from the node itself (model independent)
 struct StartNode {
     int c, ndx, stop_val, cc;   // cls byte, position, stop position, codon byte at the stop
@@ -754,10 +741,7 @@ __device__ __forceinline__ void load_start_node(const DevBatch &B, int node_off,
 template <bool LEAN>
 __device__ __forceinline__ void start_score_eval(const DevBatch &B, const DevModel *__restrict__ models, const ChainInfo &C,
                                                  const StartNode &N, int64_t g, int i, const double *__restrict__ cs_in,
-                                                 int64_t g_in, RunOpts o, MotifOut *__restrict__ mot_out, int slot = -1) {
-    // slot >= 0: the model's uc / sd_best tables are in shared memory (score_tabs)
-    const double *ucs = reinterpret_cast<const double *>(score_tabs + (slot < 0 ? 0 : slot) * kScoreSlotBytes);
-    const uint8_t *sds = score_tabs + (slot < 0 ? 0 : slot) * kScoreSlotBytes + 32 * 4 * 8;
+                                                 int64_t g_in, RunOpts o, MotifOut *__restrict__ mot_out) {
     const uint8_t *__restrict__ cls = B.cls + C.node_off;
     const int c = N.c;
     if (cls_is_stop(c)) {
@@ -793,20 +777,11 @@ __device__ __forceinline__ void start_score_eval(const DevBatch &B, const DevMod
             const uint32_t bits = pre_bits;
             const uint32_t A = bits & 0xffffu, G = bits >> 16;
             const int omin = rev ? 0 : max(0, 20 - start);  // forward skips negative offsets only
-            if (slot >= 0) {
-#pragma unroll
-                for (int off = 0; off < 15; off++) {
-                    const uint32_t gp = ((A >> off) & 0x09u) | ((G >> off) & 0x36u);
-                    const int e = sds[off * 64 + gp], m = sds[15 * 64 + off * 64 + gp];
-                    if (off >= omin) { rbs0 = max(rbs0, e); rbs1 = max(rbs1, m); }
-                }
-            } else {
-                for (int off = omin; off < 15; off++) {
-                    const uint32_t gp = ((A >> off) & 0x09u) | ((G >> off) & 0x36u);
-                    int e = M.sd_best[0][off][gp], m = M.sd_best[1][off][gp];
-                    rbs0 = max(rbs0, e);
-                    rbs1 = max(rbs1, m);
-                }
+            for (int off = omin; off < 15; off++) {
+                const uint32_t gp = ((A >> off) & 0x09u) | ((G >> off) & 0x36u);
+                int e = M.sd_best[0][off][gp], m = M.sd_best[1][off][gp];
+                rbs0 = max(rbs0, e);
+                rbs1 = max(rbs1, m);
             }
         } else {
             // best upstream motif, stage 2 (lib.pyx:1557-1616); spacer class of the p-th window of a length is
@@ -920,24 +895,6 @@ __device__ __forceinline__ void start_score_eval(const DevBatch &B, const DevMod
             const int ncomp = min(2, start) + max(0, min(30, start - 14));
             uint64_t pc = pre_pc;
             int k = 0;
-            if (slot >= 0) {
-                // 32-bit halves of the packed bases, constant offsets: LDS [idx * 8 + k * 32]
-                const uint32_t plo = (uint32_t)pc, phi = (uint32_t)(pc >> 32);
-                if (ncomp == 32) {
-#pragma unroll
-                    for (int q = 0; q < 32; q += 8) {
-                        const uint32_t w = (q < 16 ? plo : phi) >> (2 * (q & 15));
-                        const double w0 = ucs[(q + 0) * 4 + (w & 3)], w1 = ucs[(q + 1) * 4 + ((w >> 2) & 3)],
-                                     w2 = ucs[(q + 2) * 4 + ((w >> 4) & 3)], w3 = ucs[(q + 3) * 4 + ((w >> 6) & 3)],
-                                     w4 = ucs[(q + 4) * 4 + ((w >> 8) & 3)], w5 = ucs[(q + 5) * 4 + ((w >> 10) & 3)],
-                                     w6 = ucs[(q + 6) * 4 + ((w >> 12) & 3)], w7 = ucs[(q + 7) * 4 + ((w >> 14) & 3)];
-                        uscore += w0; uscore += w1; uscore += w2; uscore += w3; uscore += w4; uscore += w5; uscore += w6; uscore += w7;
-                    }
-                } else {
-                    for (; k < ncomp; k++, pc >>= 2) uscore += ucs[k * 4 + ((uint32_t)pc & 3)];
-                }
-                k = ncomp;
-            }
             for (; k + 8 <= ncomp; k += 8, pc >>= 16) {  // 8 independent loads, adds in the reference's order
                 const double w0 = M.uc[k][pc & 3], w1 = M.uc[k + 1][(pc >> 2) & 3], w2 = M.uc[k + 2][(pc >> 4) & 3],
                              w3 = M.uc[k + 3][(pc >> 6) & 3], w4 = M.uc[k + 4][(pc >> 8) & 3], w5 = M.uc[k + 5][(pc >> 10) & 3],
@@ -1046,24 +1003,11 @@ __device__ __forceinline__ void start_score_node(const DevBatch &B, const DevMod
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_start_score_lean(DevBatch B, const DevModel *__restrict__ models, int n_chains,
                                                                  int64_t total, RunOpts o) {
-    __shared__ int s_first, s_last;
+    __shared__ int s_first;
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int k_first = chain_hint(B, n_chains, min(g, total - 1), total, &s_first);   // the same for the whole CTA
-    int k = k_first;
-    while (k + 1 < n_chains && B.chains[k + 1].coff <= min(g, total - 1)) k++;
-    // the tables of the (up to kScoreSlots) chains this CTA touches, into shared memory
-    if (threadIdx.x == blockDim.x - 1) s_last = k;
-    __syncthreads();
-    const int n_slots = min(kScoreSlots, s_last - k_first + 1);
-    for (int t = threadIdx.x; t < n_slots * (kScoreSlotBytes / 4); t += blockDim.x) {
-        const int sl = t / (kScoreSlotBytes / 4), w = t % (kScoreSlotBytes / 4);
-        const DevModel *__restrict__ Ms = models + B.chains[k_first + sl].model;
-        const uint32_t *src = w < 256 ? reinterpret_cast<const uint32_t *>(&Ms->uc[0][0]) + w
-                                      : reinterpret_cast<const uint32_t *>(&Ms->sd_best[0][0][0]) + (w - 256);
-        reinterpret_cast<uint32_t *>(score_tabs)[sl * (kScoreSlotBytes / 4) + w] = *src;
-    }
-    __syncthreads();
+    int k = chain_hint(B, n_chains, min(g, total - 1), total, &s_first);
     if (g >= total) return;
+    while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
     const ChainInfo C = B.chains[k];
     const int i = (int)(g - C.coff);
     if (i >= C.nn) return;
@@ -1071,7 +1015,7 @@ __global__ void __launch_bounds__(128, MINB) k_start_score_lean(DevBatch B, cons
     N.c = B.cls[C.node_off + i];
     if (cls_is_stop(N.c)) return;
     load_start_node(B, C.node_off, C.doff, C.nn, i, N);
-    start_score_eval<true>(B, models, C, N, g, i, B.cscore, g, o, nullptr, k - k_first < kScoreSlots ? k - k_first : -1);
+    start_score_eval<true>(B, models, C, N, g, i, B.cscore, g, o, nullptr);
 }
 
 __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel *__restrict__ models, int n_chains,
@@ -1401,10 +1345,9 @@ void launch_start_score_lean(const DevBatch &B, const DevModel *models, int n_ch
     if (n_chains == 0 || total == 0) return;
     static const int minb = getenv("PGPU_SCORE_MINB") ? atoi(getenv("PGPU_SCORE_MINB")) : 10;   // 10 = 48 registers, 40 warps / SM (measured: 17.6 ms vs 18.1 at 9, 18.6 at 12)
     const unsigned nb = (unsigned)((total + 127) / 128);
-    constexpr int sm = kScoreSlots * kScoreSlotBytes;
-    if (minb == 12) k_start_score_lean<12><<<nb, 128, sm, st>>>(B, models, n_chains, total, o);
-    else if (minb == 10) k_start_score_lean<10><<<nb, 128, sm, st>>>(B, models, n_chains, total, o);
-    else k_start_score_lean<9><<<nb, 128, sm, st>>>(B, models, n_chains, total, o);
+    if (minb == 12) k_start_score_lean<12><<<nb, 128, 0, st>>>(B, models, n_chains, total, o);
+    else if (minb == 10) k_start_score_lean<10><<<nb, 128, 0, st>>>(B, models, n_chains, total, o);
+    else k_start_score_lean<9><<<nb, 128, 0, st>>>(B, models, n_chains, total, o);
 }
 void launch_score_chains(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o,
                          void *mot_out, int n_ext, int total_nodes, cudaStream_t st) {

@@ -9,4 +9,4 @@ PY
 }
 run default X=1
 for v in "$@"; do run "$(echo $v | tr '=' '_')" $v; done
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_coding_flat|k_start_score_lean|k_orf_links" -c 3 -f -o gpurun_out/r2h_score python bench.py --steps 1 --warmup 0 --no-cpu > gpurun_out/r2h_ncu.log 2>&1; ls -la gpurun_out/r2h_score.ncu-rep
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_coding_flat|k_cq_plan|k_cq_owner|k_orf_links" -c 4 -f -o gpurun_out/r2g_coding_flat python bench.py --steps 1 --warmup 0 --no-cpu > gpurun_out/r2g_ncu.log 2>&1; ls -la gpurun_out/r2g_coding_flat.ncu-rep
