@@ -1,7 +1,8 @@
-# A/B helper for gpurun: parity tests, then bench.py under alternative kernel selections (env switches of the library).
-# Switches that are read once per process (PGPU_SCORE_BY_CLASS, PGPU_CODING_MINB) can also be verified by running the
-# whole GPU suite under them: `PGPU_SCORE_BY_CLASS=1 python -m pytest tests -m gpu -x -q`.
-python -m pytest tests -m gpu -x -q > gpurun_out/ab_gpu_tests.log 2>&1; tail -3 gpurun_out/ab_gpu_tests.log
+# A/B helper for one gpurun call: parity tests (TESTS = pytest -k filter, default all GPU tests), then bench.py under
+# alternative kernel selections (env switches of the library: arguments NAME=VALUE), then optionally one ncu --set full
+# capture (NCU = kernel-name regex, TAG = output name).  Example:
+#   TESTS="shared_memory or two_lane" NCU="k_coding_flat|k_start_score_lean" TAG=r2h bash tools/gpu_ab.sh PGPU_CODING_SMEM=0
+python -m pytest tests -m gpu -x -q ${TESTS:+-k "$TESTS"} > gpurun_out/ab_gpu_tests.log 2>&1; tail -3 gpurun_out/ab_gpu_tests.log
 run() { name=$1; shift; env "$@" python bench.py --no-cpu --steps 3 --warmup 3 > gpurun_out/ab_bench_$name.log 2>&1; python - <<PY
 import json
 for l in open("gpurun_out/ab_bench_$name.log"):
@@ -11,3 +12,6 @@ PY
 }
 run default X=1
 for v in "$@"; do run "$(echo $v | tr '=' '_')" $v; done
+if [ -n "$NCU" ]; then
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:"$NCU" -c ${NCU_COUNT:-3} -f -o gpurun_out/${TAG:-ab}_ncu python bench.py --steps 1 --warmup 0 --no-cpu > gpurun_out/${TAG:-ab}_ncu.log 2>&1; ls -la gpurun_out/${TAG:-ab}_ncu.ncu-rep
+fi
