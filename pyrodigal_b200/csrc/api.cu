@@ -1303,6 +1303,7 @@ static int train_stage(pgpu_ctx *ctx, DevPool &pool, DevBatch &B, const ExtractI
     B.star_ptr = pool.alloc<int32_t>(3 * n1); B.rbs = pool.alloc<uint8_t>(2 * n1 + 16, true);
     B.score = pool.alloc<double>(n1, true); B.traceb = pool.alloc<int32_t>(n1); B.ov_mark = pool.alloc<int8_t>(n1 + 16, true);
     B.chain_ipath = pool.alloc<int32_t>(1); B.chain_score = pool.alloc<double>(1);
+    if (ctx->dp_algo >= 1) { B.dp_svig = pool.alloc<double>(n1); B.dp_tbig = pool.alloc<int32_t>(n1); }   // k_dp_dq<.., 0>
     TrainView V;
     memset(&V, 0, sizeof(V));
     V.N.ndx = B.ndx + X.node_off; V.N.sv = B.stop_val + X.node_off; V.N.cls = B.cls + X.node_off; V.N.nn = nn; V.N.slen = slen;
@@ -1355,7 +1356,7 @@ static int train_stage(pgpu_ctx *ctx, DevPool &pool, DevBatch &B, const ExtractI
             launch_gc_bias(B, V, d_bias, B.gcb, st);
             upload_model(T);
             launch_overlap(B, d_model, 1, nn, nn, 1, ro, 0, st); // first start of each frame, no scores yet
-            launch_dp(B, d_model, nullptr, 1, 0, 0, st);          // final == 0: GC frame bias is the only score
+            launch_dp(B, d_model, nullptr, 1, 0, ctx->dp_algo, st);   // final == 0: GC frame bias is the only score
             launch_training_path(B, V, d_iv, icap, d_niv, st);
             launch_dicodon(B.digits + X.doff, slen, d_iv, d_niv, icap, d_dc, d_dc + 4096, d_gene_total, st);
             ctx->launches += 10;
@@ -2076,7 +2077,7 @@ int pgpu_score_connections(pgpu_ctx *ctx, int n, const int32_t *ndx, const int32
     B.cndx = pool.alloc<int32_t>(n);
     B.dpx = pool.alloc<int4>(n);
     B.ig_node = pool.alloc<int32_t>(n + 1); B.ig_ndx = pool.alloc<int32_t>(n + 1); B.dqx = pool.alloc<int4>(n);
-    if (final && ctx->dp_algo >= 1) {
+    if (ctx->dp_algo >= 1) {
         B.dp_svig = pool.alloc<double>(n); B.dp_tbig = pool.alloc<int32_t>(n);
     }
     unsigned long long *d_pairs = pool.alloc<unsigned long long>(1, true);

@@ -367,7 +367,8 @@ struct DqK {  // per-target constants, staged 32 targets at a time
     int32_t n3n0, n3n1, n3n2, n3s0, n3s1, n3s2;
     int32_t pad;
     double op0, op1, op2;
-    double cs;
+    double cs;          // final DP: cscore + sscore of a start; training DP: gene term of a +start / bias sum of a -start
+    double g0, g1, g2;  // training DP: bias . gc_score of the recorded starts
 };
 
 // arg-max over the warp of (v, j): larger v wins, equal v -> larger j; returns the winner in every lane
@@ -389,7 +390,7 @@ __device__ __forceinline__ void warp_argmax(double &v, int &j, int &fr) {
     fr = mfr;
 }
 
-template <int MINB>
+template <int MINB, int FINAL>
 __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, const DevModel *__restrict__ models,
                                                                    const int32_t *__restrict__ order, int n_chains) {
     __shared__ DqK s_k[kFastWarps][32];
@@ -427,7 +428,8 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
     DqK *sk = s_k[wslot];
     double *dqv = s_dqv[wslot];
     int32_t *dqj = s_dqj[wslot];
-    const double ig_neg = M.ig_neg;
+    const double ig_neg = FINAL ? M.ig_neg : 0.0;   // training DP: every intergenic connection scores 0
+    const double *__restrict__ gcb = FINAL ? nullptr : B.gcb + C.coff;   // training DP: bias . gc_score of a start
 
     // merged-stream cursors: cur = finalized entries, lo = first entry inside [i-1000, i), far = first entry
     // that is NOT more than 180 bp behind the target
@@ -445,7 +447,10 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
             const DqK &P = sk[pend_i - i0];
             double bv = kNeg;
             int bj = -1;
-            if (P.x >= P.pad && P.x >= 0 && P.x < pend_i) { bv = score[P.x] + P.cs; bj = P.x; }  // own -STOP (gene)
+            if (P.x >= P.pad && P.x >= 0 && P.x < pend_i) {   // own -STOP (gene)
+                bv = score[P.x] + (FINAL ? P.cs : ((double)(P.ndx - (ndx[P.x] - 2) + 1)) * P.cs);
+                bj = P.x;
+            }
             const double cs_diff = P.cs + ig_neg;
             for (int q = max(P.y, P.w); q < min(P.z, pend_q); q++) {  // +STOPs overlapping the 3' end
                 const int nd = ig_node[q];
@@ -458,7 +463,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
                 if (ovlp >= kMaxOppOvlp) continue;
                 if ((nj - P.sv) >= (P.ndx - nj + 3)) continue;
                 if ((nj - P.sv) >= (P.sv - 3 - ndx[tbig[q]])) continue;
-                const double v = s + cs_diff;
+                const double v = s + (FINAL ? cs_diff : ((double)(P.ndx - (P.sv - 2) + 1 - ovlp * 2)) * P.cs);
                 const int j = nd & 0x7fffffff;
                 if (v > bv || (v == bv && j > bj)) { bv = v; bj = j; }
             }
@@ -482,16 +487,18 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
           const int kind = cls_kind(k.cls);
           const int4 dx = dqx[i];
           k.x = dx.x; k.y = dx.y; k.z = dx.z; k.w = dx.w;
-          k.cs = (kind == K_FS || kind == K_RS) ? (csum ? csum[i * S] : cscore[i] + sscore[i]) : 0.0;
+          if (FINAL) k.cs = (kind == K_FS || kind == K_RS) ? (csum ? csum[i * S] : cscore[i] + sscore[i]) : 0.0;
+          else k.cs = kind == K_FS ? ((double)(k.sv + 2 - k.ndx + 1)) * gcb[i] : (kind == K_RS ? gcb[i] : 0.0);   // gene term / bias sum
+          k.g0 = k.g1 = k.g2 = 0.0;
           k.sp0 = k.sp1 = k.sp2 = -1;
           k.n3n0 = k.n3n1 = k.n3n2 = k.n3s0 = k.n3s1 = k.n3s2 = 0;
           k.op0 = k.op1 = k.op2 = 0.0;
           k.pad = kind == K_RS ? B.win_min[C.node_off + i] : 0;  // node index of the window start
           if (kind == K_RE) {
               k.sp0 = star_ptr[S3 * (int64_t)i]; k.sp1 = star_ptr[S3 * (int64_t)i + 1]; k.sp2 = star_ptr[S3 * (int64_t)i + 2];
-              if (k.sp0 != -1) { k.n3n0 = ndx[k.sp0]; k.n3s0 = sv[k.sp0]; k.op0 = opv[S3 * (int64_t)i]; }
-              if (k.sp1 != -1) { k.n3n1 = ndx[k.sp1]; k.n3s1 = sv[k.sp1]; k.op1 = opv[S3 * (int64_t)i + 1]; }
-              if (k.sp2 != -1) { k.n3n2 = ndx[k.sp2]; k.n3s2 = sv[k.sp2]; k.op2 = opv[S3 * (int64_t)i + 2]; }
+              if (k.sp0 != -1) { k.n3n0 = ndx[k.sp0]; k.n3s0 = sv[k.sp0]; k.op0 = opv[S3 * (int64_t)i]; if (!FINAL) k.g0 = gcb[k.sp0]; }
+              if (k.sp1 != -1) { k.n3n1 = ndx[k.sp1]; k.n3s1 = sv[k.sp1]; k.op1 = opv[S3 * (int64_t)i + 1]; if (!FINAL) k.g1 = gcb[k.sp1]; }
+              if (k.sp2 != -1) { k.n3n2 = ndx[k.sp2]; k.n3s2 = sv[k.sp2]; k.op2 = opv[S3 * (int64_t)i + 2]; if (!FINAL) k.g2 = gcb[k.sp2]; }
           }
           sk[lane] = k;
       }
@@ -539,11 +546,24 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
                 if (c < 32) break;
             }
             const int flo = max(far, lo);
+            bool far_scan = !dq_ok;   // deque overflowed once (scores fell monotonically over > 64 entries): scan the far range
             if (dq_ok) {
                 while (dq_cnt > 0 && dqj[dq_head] < i - 2 * kMaxNodeDist) { dq_head = (dq_head + 1) & (kDqCap - 1); dq_cnt--; }
-                if (dq_cnt > 0 && lane == 0) cand(dqv[dq_head], dqj[dq_head], -1);
-            } else {
-                // deque overflowed once (scores fell monotonically over > 64 entries): scan the far range
+                if (!FINAL && kind == K_RE && dq_cnt > 0) {
+                    // Training DP: a far +STOP that triggers the triple overlap does not score "at least the plain value"
+                    // as in the final DP (its term replaces the 0), so the far maximum is only usable when its node
+                    // cannot trigger: not a +STOP within [stop - 4, stop + 194] of a recorded start.  Otherwise every far
+                    // source is evaluated (rare).
+                    const int fj = dqj[dq_head];
+                    if (cls_kind(cls[fj]) == K_FE) {
+                        const int nf = ndx[fj];
+                        far_scan = (K.sp0 != -1 && nf >= K.n3s0 - 4 && nf < K.n3s0 + 195) || (K.sp1 != -1 && nf >= K.n3s1 - 4 && nf < K.n3s1 + 195) ||
+                                   (K.sp2 != -1 && nf >= K.n3s2 - 4 && nf < K.n3s2 + 195);
+                    }
+                }
+                if (!far_scan && dq_cnt > 0 && lane == 0) cand(dqv[dq_head], dqj[dq_head], -1);
+            }
+            if (far_scan && (FINAL || kind == K_FS)) {
                 for (int q = lo + lane; q < flo; q += 32) {
                     const double s = svig[q];
                     if (s != kNeg) cand(s + ig_neg, ig_node[q] & 0x7fffffff, -1);
@@ -558,7 +578,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
                     if (nd < 0) {
                         if (nj + 2 >= ndx_i) continue;
                         const int dist = ndx_i - nj;
-                        cand(s + (dist > 3 * kOperDist ? ig_neg : (dist <= kOperDist ? M.igt[dist] : 0.0)), nd & 0x7fffffff, -1);
+                        cand(s + (!FINAL || dist > 3 * kOperDist ? ig_neg : (dist <= kOperDist ? M.igt[dist] : 0.0)), nd & 0x7fffffff, -1);
                     } else {
                         if (nj >= ndx_i) continue;
                         cand(s + ig_neg, nd, -1);
@@ -569,21 +589,24 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
                 auto eval_fe = [&](int q, double s, int nj, int nd) {
                     const int left = nj + 2, right = ndx_i - 2;
                     if (left >= right) return;
-                    int maxfr = -1, tj = kTbNone;
-                    double maxval = 0.0;
-                    auto probe = [&](int k, int spk, int n3n, int n3s, double op) {
+                    int maxfr = -1, tj = kTbNone, ovlp = 0;
+                    double maxval = 0.0, maxg = 0.0;
+                    // (training DP: the comparison is between the bias sum and the value of the final DP, the overlap
+                    // that enters the score is the one examined last: _connection.h:320-324)
+                    auto probe = [&](int k, int spk, int n3n, int n3s, double op, double g) {
                         if (spk == -1) return;
-                        const int ovlp = left - n3s + 3;
+                        ovlp = left - n3s + 3;
                         if (ovlp <= 0 || ovlp >= kMaxOppOvlp) return;
                         if (ovlp >= n3n - left) return;
                         if (tj == kTbNone) tj = ndx[tbig[q]];
                         if (ovlp >= n3s - tj - 2) return;
-                        if (op > maxval) { maxfr = k; maxval = op; }
+                        if (FINAL ? (op > maxval) : (g > maxval)) { maxfr = k; maxval = op; maxg = g; }
                     };
-                    probe(0, K.sp0, K.n3n0, K.n3s0, K.op0);
-                    probe(1, K.sp1, K.n3n1, K.n3s1, K.op1);
-                    probe(2, K.sp2, K.n3n2, K.n3s2, K.op2);
-                    cand(s + (maxfr != -1 ? maxval : ig_neg), nd & 0x7fffffff, maxfr);
+                    probe(0, K.sp0, K.n3n0, K.n3s0, K.op0, K.g0);
+                    probe(1, K.sp1, K.n3n1, K.n3s1, K.op1, K.g1);
+                    probe(2, K.sp2, K.n3n2, K.n3s2, K.op2, K.g2);
+                    if (FINAL) cand(s + (maxfr != -1 ? maxval : ig_neg), nd & 0x7fffffff, maxfr);
+                    else cand(s + ((double)(right - left + 1 - ovlp * 2)) * (maxfr != -1 ? maxg : 0.0), nd & 0x7fffffff, maxfr);
                 };
                 for (int q = flo + lane; q < cur; q += 32) {
                     const double s = svig[q];
@@ -594,7 +617,15 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
                     } else {  // -start (_connection.h:335-341)
                         if (nj >= ndx_i - 2) continue;
                         const int dist = ndx_i - nj;
-                        cand(s + (dist > 3 * kOperDist ? ig_neg : (dist <= kOperDist ? M.igt[dist] : 0.0)), nd, -1);
+                        cand(s + (!FINAL || dist > 3 * kOperDist ? ig_neg : (dist <= kOperDist ? M.igt[dist] : 0.0)), nd, -1);
+                    }
+                }
+                if (!FINAL && far_scan) {   // every far source, exactly
+                    for (int q = lo + lane; q < flo; q += 32) {
+                        const double s = svig[q];
+                        if (s == kNeg) continue;
+                        const int nd = ig_node[q];
+                        if (nd < 0) eval_fe(q, s, ig_ndx[q], nd); else cand(s + ig_neg, nd, -1);
                     }
                 }
                 // far +STOPs whose position can trigger the triple overlap (200 bp after the stop of a recorded
@@ -620,7 +651,10 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
                     const int j = lane == 0 ? K.x : (lane == 1 ? K.y : K.z);
                     const int spl = lane == 0 ? K.sp0 : (lane == 1 ? K.sp1 : K.sp2);
                     const double opl = lane == 0 ? K.op0 : (lane == 1 ? K.op1 : K.op2);
-                    if (j >= 0 && j >= i - 2 * kMaxNodeDist && spl != -1) cand(score[j] + opl, j, -1);
+                    const int n3l = lane == 0 ? K.n3n0 : (lane == 1 ? K.n3n1 : K.n3n2);
+                    const double gl = lane == 0 ? K.g0 : (lane == 1 ? K.g1 : K.g2);
+                    if (j >= 0 && j >= i - 2 * kMaxNodeDist && spl != -1)
+                        cand(score[j] + (FINAL ? opl : ((double)(n3l - (ndx[j] - 2) + 1)) * gl), j, -1);
                 }
             }
         } else if (kind == K_FE) {
@@ -636,8 +670,9 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
                 const double s = svig[q];
                 if (s == kNeg) continue;
                 const int j = nd & 0x7fffffff;
-                if (star_ptr[S3 * (int64_t)j + f2] == -1) continue;
-                cand(s + opv[S3 * (int64_t)j + f2], j, -1);
+                const int sp = star_ptr[S3 * (int64_t)j + f2];
+                if (sp == -1) continue;
+                cand(s + (FINAL ? opv[S3 * (int64_t)j + f2] : ((double)(ndx_i + 2 - ndx[sp] + 1)) * gcb[sp]), j, -1);
             }
         }
 
@@ -1681,8 +1716,13 @@ void launch_dp(const DevBatch &B, const DevModel *models, const int32_t *order, 
     // final scoring: k_dp_dq (one warp per chain) unless algo 0 asks for the all-pairs kernel, which is also the training DP
     if (final && algo >= 1 && B.dp_svig) {
         const int nb = (n_chains + kFastWarps - 1) / kFastWarps;
-        if (algo == 4) k_dp_dq<4><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);
-        else k_dp_dq<8><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);
+        // <4>: 93 registers, no spills -- also whenever the chains fit into one wave at that occupancy (single chains are
+        // pure latency: spills only cost); <8>: 64 registers for batches of many chains
+        if (algo == 4 || n_chains <= 148 * 4 * kFastWarps) k_dp_dq<4, 1><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);
+        else k_dp_dq<8, 1><<<nb, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);
+        k_chain_best<<<(n_chains * 32 + 127) / 128, 128, 0, st>>>(B, n_chains);
+    } else if (!final && algo >= 1 && B.dp_svig) {   // training DP on the deque formulation
+        k_dp_dq<4, 0><<<(n_chains + kFastWarps - 1) / kFastWarps, 32 * kFastWarps, 0, st>>>(B, models, order, n_chains);
         k_chain_best<<<(n_chains * 32 + 127) / 128, 128, 0, st>>>(B, n_chains);
     }
     else if (final) k_dp<1><<<n_chains, kDpThreads, 0, st>>>(B, models, order, n_chains);

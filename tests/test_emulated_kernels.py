@@ -58,6 +58,7 @@ test_extract_nodes = G.test_extract_nodes
 test_extract_nodes_masked = G.test_extract_nodes_masked
 test_score_nodes = G.test_score_nodes
 test_score_connections_golden = G.test_score_connections_golden
+test_training_dp_vs_oracle = G.test_training_dp_vs_oracle
 test_compute_skippable = G.test_compute_skippable
 test_find_genes_meta_golden = G.test_find_genes_meta_golden
 test_find_genes_single_golden = G.test_find_genes_single_golden

@@ -134,13 +134,54 @@ def test_score_connections_golden(ctx, name, final):
     assert pairs == orc.score_connections(ref, R.bin_blob(b), final=final)
 
 
-def test_compute_skippable(ctx):
-    a = DP["kk_bin38/in"]
-    i = len(a) - 1
-    mn = max(0, i - 1000)
-    skip = ctx.compute_skippable(a["strand"], a["type"], a["ndx"], mn, i)
-    want = np.array([orc.skippable(a, j, i) for j in range(mn, i)], dtype=np.uint8)
-    cmp_int(skip[mn:i], want, "skippable")
+@pytest.mark.parametrize("length,gc,tt,seed", [(30000, .35, 11, 71), (45000, .5, 11, 72), (60000, .65, 11, 73), (40000, .3, 4, 74),
+                                               (25000, .72, 11, 75)])
+@pytest.mark.parametrize("scored", [False, True])
+def test_training_dp_vs_oracle(ctx, length, gc, tt, seed, scored):
+    """ConnectionScorer.score_connections(final=False) -- the training DP, k_dp_dq<.., 0> -- on node arrays the oracle
+    extracted from synthetic sequences: with the state the training pass really has (scores reset, first start of every
+    frame recorded) and with scored nodes / best recorded starts (the comparison of the bias sum with the final DP's value
+    in the triple-overlap search, _connection.h:320-324, then sees non-zero values)"""
+    rng = np.random.default_rng(seed)
+    d, _, _ = orc.encode(R.synth(length, gc, seed))
+    model = 0 if tt == 4 else 11
+    blob = R.bin_blob(model)
+    nodes = orc.extract(d, tt)
+    if scored:
+        orc.score(d, nodes, blob)
+    else:
+        orc.reset_scores(nodes)
+    orc.record_overlapping_starts(nodes, blob, flag=1 if scored else 0)
+    nodes["gc_score"] = rng.integers(0, 60, size=(len(nodes), 3)).astype(np.float64) * rng.choice([1.0, 0.5, 0.0], size=(len(nodes), 1))
+    ref = nodes.copy()
+    ref["ov_mark"] = -1   # (the DP only writes the marker of nodes something leads into)
+    pairs = orc.score_connections(ref, blob, final=False)
+    score, traceb, ov, got_pairs, ms = ctx.score_connections(
+        nodes["ndx"], nodes["stop_val"], nodes["strand"], nodes["type"], nodes["cscore"], nodes["sscore"], nodes["rscore"],
+        nodes["uscore"], nodes["gc_score"], nodes["star_ptr"], model, False)
+    cmp_int(traceb, ref["traceb"], "train_dp.traceb")
+    cmp_int(ov, ref["ov_mark"], "train_dp.ov_mark")
+    cmp_float(score, ref["score"], "train_dp.score")
+    assert got_pairs == pairs
+
+
+@pytest.mark.parametrize("name", list(DP["names"]))
+def test_compute_skippable(ctx, name):
+    """the skip filter as an operator (ConnectionScorer.compute_skippable, lib.pyx:1321-1334): every fixture, windows at
+    both ends and in the middle of the node array, the reference's 500-node window and shorter / longer ones"""
+    a = DP[name + "/in"]
+    n = len(a)
+    checked = 0
+    for i in sorted({0, 1, 2, 17, min(n - 1, 499), min(n - 1, 500), min(n - 1, 501), n // 3, n // 2, n - 2, n - 1}):
+        if i < 0 or i >= n:
+            continue
+        for width in (1, 7, 500, 1000, 2500):
+            mn = max(0, i - width)
+            skip = ctx.compute_skippable(a["strand"], a["type"], a["ndx"], mn, i)
+            want = np.array([orc.skippable(a, j, i) for j in range(mn, i)], dtype=np.uint8)
+            cmp_int(skip[mn:i], want, f"skippable[{name} i={i} min={mn}]")
+            checked += i - mn
+    assert checked > 0
 
 
 # ---------------------------------------------------------------------------------------------------
