@@ -716,7 +716,7 @@ def main():
         peak, peak_src = measured_peak()
         # the DP kernel of this configuration, CUDA events on the launching stream, every timed step
         if w.get("train"):
-            dp_kernel = "k_dp_train (training DP, final = 0; one chain)"
+            dp_kernel = "k_dp_dq<FINAL = 0> (training DP, one warp per chain)"
             dp_ms = float(np.mean([t["train_ms_dp"] for t in step_stats]))
             dp_bytes, dp_note = DP_BYTES_TRAIN, ("kernel_ms = first training phase (GC frame plot + bias + training DP + path + "
                                                  "dicodon counts) between CUDA events; the DP dominates it")

@@ -463,15 +463,22 @@ constexpr int kCqRing = 8;
 constexpr int kCqTableBytes = 4096 * kCqCols * (int)sizeof(double);                 // 128 KB
 constexpr int kCqSmemBytes = kCqTableBytes + kCqRing * kCqThreads * (int)sizeof(double);   // + 64 KB
 
-// one thread per STOP node: the in-frame starts of its ORF, nearest first (DevBatch::link, ::orfd)
+// one thread per STOP node: the in-frame starts of its ORF, nearest first (DevBatch::link, ::orfd).  Threads index the
+// half-size slot space of the descriptors (extraction e owns the slots from (node_off + 1) / 2 on, its first
+// (#STOP nodes) slots have work: a STOP node exists only if its ORF has a start), so busy lanes are neighbours.
 __global__ void __launch_bounds__(128) k_orf_links(DevBatch B, int n_ext, int total_nodes, int roff) {
     __shared__ int s_first;
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    int e = ext_hint(B, n_ext, min(g, total_nodes - 1), blockIdx.x * blockDim.x, total_nodes, &s_first);
-    if (g >= total_nodes) return;
-    while (e + 1 < n_ext && B.exts[e + 1].node_off <= g) e++;
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    int e = ext_hint(B, n_ext, min(2 * h, total_nodes - 1), 2 * blockIdx.x * blockDim.x, total_nodes, &s_first);
+    if (h > (total_nodes + 1) / 2) return;
+    while (e + 1 < n_ext && ((B.exts[e + 1].node_off + 1) >> 1) <= h) e++;
     const ExtractInfo *__restrict__ X = B.exts + e;
-    const int node_off = X->node_off, nn = X->nn, z = g - node_off;
+    const int node_off = X->node_off, nn = X->nn;
+    const int32_t *__restrict__ cbase = B.cbase + 4 * e;
+    const int tl = h - ((node_off + 1) >> 1), n_fe = cbase[2] - cbase[1], n_re = nn - cbase[3];
+    if (tl >= n_fe + n_re) return;
+    const int z = (B.clist + node_off)[tl < n_fe ? cbase[1] + tl : cbase[3] + (tl - n_fe)];
+    const int g = node_off + z;
     const uint8_t *__restrict__ cls = B.cls + node_off;
     const int c = cls[z];
     if (!cls_is_stop(c)) return;
@@ -493,10 +500,7 @@ __global__ void __launch_bounds__(128) k_orf_links(DevBatch B, int n_ext, int to
         pdiff = rev ? ndx[i] - sv[i] : sv[i] - ndx[i];
     }
     if (prev >= 0) B.link[prev] = make_int4(-1, 0, pprev, pdiff);
-    const int32_t *__restrict__ cbase = B.cbase + 4 * e;
-    const int kind = cls_kind(c);   // 1 = +STOP, 3 = -STOP
-    const int tl = B.crank[4 * (int64_t)g + kind] + (kind == 3 ? cbase[2] - cbase[1] : 0);
-    B.orfd[((node_off + 1) >> 1) + tl] = d;
+    B.orfd[h] = d;
 }
 
 // ORF slots of the plan entries (one CTA): entry r gets as many slots as its extraction has STOP nodes, the padding
@@ -1311,7 +1315,7 @@ void launch_coding(const DevBatch &B, const DevModel *models, int n_chains, int6
                    cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
     if (B.ext_chains && B.dcS && B.cq_max_cta > 0 && total_nodes > 0) {   // dicodon tables in shared memory
-        k_orf_links<<<(total_nodes + 127) / 128, 128, 0, st>>>(B, n_ext, total_nodes, (int)(B.dic_r - B.dic_f));
+        k_orf_links<<<((total_nodes + 1) / 2 + 1 + 127) / 128, 128, 0, st>>>(B, n_ext, total_nodes, (int)(B.dic_r - B.dic_f));
         k_cq_plan<<<1, 1024, 0, st>>>(B);
         k_cq_owner<<<(B.cq_n_ent + 127) / 128, 128, 0, st>>>(B);
 #ifdef PGPU_HOST_EMULATION
