@@ -191,4 +191,5 @@ def test_randomised_batches_against_the_oracle(monkeypatch):
 
 test_coding_score_lane_groups = G.test_coding_score_lane_groups
 test_coding_score_shared_memory_tables = G.test_coding_score_shared_memory_tables
+test_coding_score_many_plan_entries = G.test_coding_score_many_plan_entries
 test_dp_model_lane_kernel_gc_sweep = G.test_dp_model_lane_kernel_gc_sweep

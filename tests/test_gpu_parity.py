@@ -550,7 +550,7 @@ def test_coding_score_lane_groups(capi):
 
 
 def test_coding_score_shared_memory_tables(capi, monkeypatch):
-    """k_coding_smem (dicodon tables of four neighbouring models in shared memory, ORF slots drawn from a counter) against
+    """k_coding_flat (dicodon tables of four neighbouring models in shared memory, ORF slots drawn from a counter) against
     k_coding_orf (PGPU_CODING_VERIFY: every raw coding score of every chain, bit for bit) on a GC sweep -- extractions with
     1 ... 27 models, i.e. every table set and every group width -- then against the oracle; PGPU_CODING_SMEM=0 gives the
     same genes"""
@@ -576,10 +576,34 @@ def test_coding_score_shared_memory_tables(capi, monkeypatch):
                 cmp_int(res.genes[a:b]["begin"], genes["begin"], f"smem.contig{k}.begin")
                 cmp_int(res.genes[a:b]["end"], genes["end"], f"smem.contig{k}.end")
         res.free(); c.close()
-    assert out["1", "1"][3] == out["1", "0"][3] + 2, "the self-check did not run: k_coding_smem was not selected"
+    assert out["1", "1"][3] == out["1", "0"][3] + 2, "the self-check did not run: k_coding_flat was not selected"
     assert out["0", "1"][3] == out["1", "0"][3], "PGPU_CODING_SMEM=0 still ran the self-check"
     for key in (("1", "1"), ("0", "1")):
         assert out[key][:3] == out["1", "0"][:3], key
+
+
+def test_coding_score_many_plan_entries(capi, monkeypatch):
+    """k_cq_plan lays out the ORF slots of more than 1024 plan entries (several rounds of its block-wide scan) and of
+    classes that need padding: 700 short contigs over the whole GC range, raw coding scores checked against k_coding_orf
+    (PGPU_CODING_VERIFY), genes of a few contigs against the oracle"""
+    monkeypatch.setenv("PGPU_CODING_SMEM", "1")
+    monkeypatch.setenv("PGPU_CODING_VERIFY", "1")
+    seqs = [R.synth(400 + 37 * (k % 23), 0.26 + 0.0006 * k, 9100 + k) for k in range(700)]
+    arrs = [np.frombuffer(s, np.uint8) for s in seqs]
+    off = np.zeros(len(arrs) + 1, np.int64)
+    np.cumsum([len(a) for a in arrs], out=off[1:])
+    flat = np.ascontiguousarray(np.concatenate(arrs))
+    c = capi.Context(0)
+    c.set_models(R.bins_blob(), 50)
+    res = c.find_genes_batch(flat, off, capi.make_opts(meta=True, want_nodes=False))
+    assert res.stats["n_chains"] > 4 * 1024
+    for k in (0, 99, 350, 699):
+        d, gc, unk = orc.encode(seqs[k])
+        genes, nodes, winner, pairs = orc.find_genes_meta(d, gc / len(d), R.bins_blob())
+        a, b = res.gene_off[k], res.gene_off[k + 1]
+        assert int(res.summary["winner"][k]) == winner and b - a == len(genes), k
+        cmp_int(res.genes[a:b]["begin"], genes["begin"], f"plan.contig{k}.begin")
+    res.free(); c.close()
 
 
 def test_dp_model_lane_kernel_gc_sweep(capi, monkeypatch):
