@@ -81,8 +81,8 @@ struct pgpu_ctx {
     DevModel *d_models = nullptr;
     uint32_t *d_live = nullptr; // [n_models][kMotifWords]: motif cells with a weight other than the floor (DevModel::mot_live) + window table (mot_hit)
     double *d_dcT = nullptr;   // dicodon weights transposed: [4096][kDcCols], columns sorted by (tt, gc); null if n_models > kDcCols
-    double *d_dcS = nullptr;   // the same weights as table sets of four neighbouring columns: [n_models][4096][4] (k_coding_smem)
-    int coding_smem = 1;       // PGPU_CODING_SMEM: 1 = k_coding_smem for multi-model batches, 0 = k_coding_orf
+    double *d_dcS = nullptr;   // the same weights as table sets of four neighbouring columns: [n_models][4096][4] (k_coding_flat)
+    int coding_smem = 1;       // PGPU_CODING_SMEM: 1 = k_coding_flat for multi-model batches, 0 = k_coding_orf
     size_t ws_limit = 0;
     cudaEvent_t ev[16];
     int64_t launches = 0;
@@ -93,7 +93,7 @@ struct pgpu_ctx {
                                // 1 = over every node as with want_nodes (PGPU_FINAL_ALGO)
     bool codon_lut = false;    // PGPU_CODON_LUT=1: k_codon_bits reads codon flags from a per-table byte table (written
                                // after the last GPU run of round 1: logic checked by the host emulation only, so off)
-    bool coding_verify = false;   // PGPU_CODING_VERIFY=1: run k_coding_orf after k_coding_smem and fail on any differing raw coding score
+    bool coding_verify = false;   // PGPU_CODING_VERIFY=1: run k_coding_orf after k_coding_flat and fail on any differing raw coding score
     bool dp_verify = false;    // PGPU_DP_VERIFY=1: run k_dp_dq after k_dp_ml and fail on any difference (self-check)
     int dp_algo = 5;           // 5: k_dp_ml for multi-model batches, k_dp_dq otherwise (default); 6: k_dp_ml always;
                                // 1-4: k_dp_dq, 0: all-pairs k_dp (PGPU_DP_ALGO=n)
@@ -999,7 +999,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
         CK(cudaStreamSynchronize(st));
         if (bad[0]) {
             char msg[160];
-            snprintf(msg, sizeof msg, "PGPU_CODING_VERIFY: %llu of %lld raw coding scores differ between k_coding_smem and k_coding_orf, first at chain-node %llu",
+            snprintf(msg, sizeof msg, "PGPU_CODING_VERIFY: %llu of %lld raw coding scores differ between k_coding_flat and k_coding_orf, first at chain-node %llu",
                      bad[0], (long long)total_cn, bad[1]);
             return fail(ctx, PGPU_ESTATE, msg);
         }
@@ -1744,7 +1744,7 @@ int pgpu_set_models(pgpu_ctx *ctx, const void *blobs, int n, size_t stride) {
                 for (int i = 0; i < 4096; i++) t[(size_t)i * kDcCols + c] = h_raw_v[ord[c]].gene_dc[i];
             if ((e = cudaMalloc(&d_dcT, t.size() * sizeof(double))) != cudaSuccess) return e;
             if ((e = cudaMemcpy(d_dcT, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
-            // table sets of k_coding_smem: set s = columns s .. s + 3 (zero past the last one), 128 KB each, contiguous
+            // table sets of k_coding_flat: set s = columns s .. s + 3 (zero past the last one), 128 KB each, contiguous
             // so that a CTA fetches its set with a few bulk copies
             std::vector<double> ts((size_t)n * 4096 * 4, 0.0);
             for (int c = 0; c < n; c++)
