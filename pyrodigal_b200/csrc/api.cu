@@ -1008,7 +1008,7 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
     if (lean) launch_start_score_lean(B, ctx->d_models, n_chains, total_cn, ro, st);
     else launch_start_score(B, ctx->d_models, n_chains, total_cn, ro, d_mot_main, st);
     tev("k_start_score");
-    ctx->launches += 2;
+    ctx->launches += B.dcS ? 5 : 2;   // k_orf_links + k_cq_plan + k_cq_owner + k_coding_flat, or k_coding_orf; the start scoring
     int e_score = mark();
     launch_overlap(B, ctx->d_models, n_chains, total_cn, total_il, n_ext, ro, 1, st);
     tev("k_overlap");
