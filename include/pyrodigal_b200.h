@@ -174,6 +174,10 @@ long long pgpu_result_segment(const pgpu_result *res, int k, long long *first_ge
                               const pgpu_node **gene_nodes);
 /* final node array of one contig (requires opts.want_nodes) -> dst[n_nodes] */
 int pgpu_result_nodes(const pgpu_result *res, int contig, pgpu_node *dst);
+/* the same nodes in the reference's own `struct _node` layout (src/Prodigal/node.h:41-76, 128 bytes as packed by
+ * Pyrodigal), so that the Cython side fills `Nodes.nodes` with one memcpy -> dst[n_nodes * PGPU_NODE_STRUCT_SIZE] */
+#define PGPU_NODE_STRUCT_SIZE 128
+int pgpu_result_nodes_struct(const pgpu_result *res, int contig, void *dst);
 int pgpu_result_stats(const pgpu_result *res, pgpu_stats *dst);
 void pgpu_result_free(pgpu_result *res);
 
@@ -241,6 +245,13 @@ int pgpu_score_connections(pgpu_ctx *ctx, int n, const int32_t *ndx, const int32
  * plug-in ABI skippable_t, lib.pxd:120): skip[j] for j in [min, i). */
 int pgpu_compute_skippable(pgpu_ctx *ctx, int n, const int8_t *strand, const uint8_t *type,
                            const int32_t *ndx, int min, int i, uint8_t *skip);
+/* The same filter with exactly the signature of the plug-in ABI (`skippable_t`, lib.pxd:120: node strands (1 / 255),
+ * types, frames = ndx % 3, window start, target, output), so that it can be stored in
+ * BaseConnectionScorer.skippable (lib.pyx:1149-1162) next to the SIMD back-ends.  It has no context argument: it
+ * runs on a process-wide context (device $PGPU_DEVICE, default 0).  On failure skip[min .. i) is cleared, which is
+ * always a valid answer. */
+void pgpu_skippable(const uint8_t *strands, const uint8_t *types, const uint8_t *frames, const int min, const int i,
+                    uint8_t *skip);
 
 #ifdef __cplusplus
 }

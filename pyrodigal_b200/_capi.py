@@ -65,6 +65,21 @@ NODE_DTYPE = np.dtype(
     }
 )
 
+# `struct _node` of the reference (src/Prodigal/node.h:41-76, 128 bytes as packed by Pyrodigal): what
+# pgpu_result_nodes_struct writes.  `mot_bits` = the motif bit fields: ndx (12 bits) | spacer (4) << 12 | len (3) << 16 |
+# spacendx (2) << 19.
+NODE_STRUCT_DTYPE = np.dtype(
+    {
+        "names": ["mot_score", "mot_bits", "gc_score", "cscore", "uscore", "tscore", "rscore", "sscore", "score", "gc_cont",
+                  "star_ptr", "traceb", "tracef", "ndx", "stop_val", "ov_mark", "strand", "rbs", "edge", "elim", "gc_bias",
+                  "type"],
+        "formats": ["<f8", "<u4", ("<f8", (3,)), "<f8", "<f8", "<f8", "<f8", "<f8", "<f8", "<f4", ("<i4", (3,)), "<i4", "<i4",
+                    "<i4", "<i4", "i1", "i1", ("u1", (2,)), "u1", "u1", "u1", "u1"],
+        "offsets": [0, 8, 16, 40, 48, 56, 64, 72, 80, 88, 92, 104, 108, 112, 116, 120, 121, 122, 124, 125, 126, 127],
+        "itemsize": 128,
+    }
+)
+
 SUMMARY_DTYPE = np.dtype(
     [("n_genes", "<i4"), ("n_nodes", "<i4"), ("winner", "<i4"), ("ipath", "<i4"), ("unknown", "<i4"),
      ("gc_count", "<i4"), ("score", "<f8")]
@@ -101,6 +116,9 @@ lib.pgpu_result_num_segments.argtypes = [_vp]
 lib.pgpu_result_segment.argtypes = [_vp, C.c_int, C.POINTER(C.c_longlong), C.POINTER(_vp), C.POINTER(_vp)]
 lib.pgpu_result_segment.restype = C.c_longlong
 lib.pgpu_result_nodes.argtypes = [_vp, C.c_int, _vp]
+lib.pgpu_result_nodes_struct.argtypes = [_vp, C.c_int, _vp]
+lib.pgpu_skippable.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, _vp]
+lib.pgpu_skippable.restype = None
 lib.pgpu_result_stats.argtypes = [_vp, C.POINTER(Stats)]
 lib.pgpu_result_free.argtypes = [_vp]
 lib.pgpu_result_free.restype = None
@@ -292,6 +310,14 @@ class Context:
         return skip
 
 
+def skippable_plugin(strands, types, frames, mn, i):
+    """pgpu_skippable: the skip filter through the reference's plug-in signature (skippable_t), on the process-wide context"""
+    skip = np.full(len(types), 0xAA, np.uint8)   # only [mn, i) is written
+    lib.pgpu_skippable(ptr(np.ascontiguousarray(strands, np.uint8)), ptr(np.ascontiguousarray(types, np.uint8)),
+                       ptr(np.ascontiguousarray(frames, np.uint8)), mn, i, ptr(skip))
+    return skip
+
+
 class Batch:
     """Device-resident input (pgpu_batch): upload once, run many times."""
 
@@ -388,6 +414,15 @@ class Result:
         if self._gene_nodes is None:
             self._materialise()
         return self._gene_nodes
+
+    def nodes_struct(self, contig):
+        """the final node array of one contig in the reference's own `struct _node` layout (NODE_STRUCT_DTYPE)"""
+        n = int(self.summary["n_nodes"][contig])
+        out = np.zeros(n, dtype=NODE_STRUCT_DTYPE)
+        rc = lib.pgpu_result_nodes_struct(self.handle, contig, ptr(out))
+        if rc < 0:
+            raise RuntimeError("node arrays were not requested (want_nodes=False)")
+        return out
 
     def nodes(self, contig):
         n = int(self.summary["n_nodes"][contig])

@@ -1919,6 +1919,36 @@ int pgpu_result_nodes(const pgpu_result *res, int contig, pgpu_node *dst) {
     return PGPU_OK;
 }
 
+// `struct _node` of the reference (src/Prodigal/node.h:41-76 as packed by Pyrodigal: 128 bytes): the motif record first
+// (its bit fields share one 32-bit unit: ndx 12 bits, spacer 4, len 3, spacendx 2), then the doubles, gc_cont, the ints
+// and the eight byte-sized fields.  gc_score / gc_bias are training state and are zero in a find_genes result.
+int pgpu_result_nodes_struct(const pgpu_result *res, int contig, void *dst) {
+    if (!res || contig < 0 || contig >= res->n_contigs) return PGPU_EINVAL;
+    if (!res->have_nodes) return PGPU_ESTATE;
+    const int64_t a = res->node_off[contig], b = res->node_off[contig + 1];
+    if (b > a && !dst) return PGPU_EINVAL;
+    unsigned char *out = static_cast<unsigned char *>(dst);
+    for (int64_t k = a; k < b; k++, out += PGPU_NODE_STRUCT_SIZE) {
+        const pgpu_node &n = res->nodes[(size_t)k];
+        memset(out, 0, PGPU_NODE_STRUCT_SIZE);
+        const uint32_t bits = (uint32_t)(n.mot_ndx & 0xfffu) | ((uint32_t)(n.mot_spacer & 0xfu) << 12) |
+                              ((uint32_t)(n.mot_len & 0x7u) << 16) | ((uint32_t)(n.mot_spacendx & 0x3u) << 19);
+        memcpy(out + 0, &n.mot_score, 8);
+        memcpy(out + 8, &bits, 4);
+        // out + 16: gc_score[3] = 0
+        memcpy(out + 40, &n.cscore, 8); memcpy(out + 48, &n.uscore, 8); memcpy(out + 56, &n.tscore, 8);
+        memcpy(out + 64, &n.rscore, 8); memcpy(out + 72, &n.sscore, 8); memcpy(out + 80, &n.score, 8);
+        memcpy(out + 88, &n.gc_cont, 4);
+        memcpy(out + 92, n.star_ptr, 12);
+        memcpy(out + 104, &n.traceb, 4); memcpy(out + 108, &n.tracef, 4);
+        memcpy(out + 112, &n.ndx, 4); memcpy(out + 116, &n.stop_val, 4);
+        out[120] = (unsigned char)n.ov_mark; out[121] = (unsigned char)n.strand;
+        out[122] = n.rbs[0]; out[123] = n.rbs[1];
+        out[124] = n.edge; out[125] = n.elim; out[126] = 0; out[127] = n.type;
+    }
+    return PGPU_OK;
+}
+
 int pgpu_result_stats(const pgpu_result *res, pgpu_stats *dst) {
     if (!res || !dst) return PGPU_EINVAL;
     *dst = res->stats;
@@ -2167,6 +2197,43 @@ int pgpu_compute_skippable(pgpu_ctx *ctx, int n, const int8_t *strand, const uin
     CK(cudaMemcpyAsync(skip + mn, d_k + mn, i - mn, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return PGPU_OK;
+}
+
+// The skip filter with the signature of the reference's plug-in ABI (skippable_t, lib.pxd:120; called per target node by
+// BaseConnectionScorer._compute_skippable, lib.pyx:1321-1334): no context argument, so it runs on a process-wide context
+// (device PGPU_DEVICE, default 0) created on first use.  A void function cannot report an error: on any failure it
+// clears skip[min .. i), which is always a valid answer (nothing is skipped, the connection rules decide).
+void pgpu_skippable(const uint8_t *strands, const uint8_t *types, const uint8_t *frames, const int mn, const int i,
+                    uint8_t *skip) {
+    static std::mutex mu;
+    static pgpu_ctx *dctx = nullptr;
+    if (!strands || !types || !frames || !skip || mn < 0 || i <= mn) return;
+    std::lock_guard<std::mutex> lock(mu);
+    const int cnt = i - mn;
+    bool ok = false;
+    if (!dctx) {
+        const char *d = getenv("PGPU_DEVICE");
+        if (pgpu_create(d ? atoi(d) : 0, &dctx) != PGPU_OK) dctx = nullptr;
+    }
+    if (dctx) {
+        cudaSetDevice(dctx->device);
+        cudaStream_t st = dctx->stream;
+        DevPool pool(dctx);
+        uint8_t *d_s = pool.alloc<uint8_t>(cnt + 1), *d_t = pool.alloc<uint8_t>(cnt + 1), *d_f = pool.alloc<uint8_t>(cnt + 1);
+        uint8_t *d_k = pool.alloc<uint8_t>(cnt);
+        if (!pool.failed) {
+            ok = cudaMemcpyAsync(d_s, strands + mn, cnt + 1, cudaMemcpyHostToDevice, st) == cudaSuccess &&
+                 cudaMemcpyAsync(d_t, types + mn, cnt + 1, cudaMemcpyHostToDevice, st) == cudaSuccess &&
+                 cudaMemcpyAsync(d_f, frames + mn, cnt + 1, cudaMemcpyHostToDevice, st) == cudaSuccess;
+            if (ok) {
+                launch_skippable_plugin(d_s, d_t, d_f, cnt, d_k, st);
+                dctx->launches++;
+                ok = cudaMemcpyAsync(skip + mn, d_k, cnt, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+                     cudaStreamSynchronize(st) == cudaSuccess;
+            }
+        }
+    }
+    if (!ok) memset(skip + mn, 0, cnt);
 }
 
 }  // extern "C"

@@ -1707,6 +1707,24 @@ __global__ void k_skippable(int n, const int8_t *__restrict__ strand, const uint
     skip[j] = ok ? 0 : 1;
 }
 
+// the same with the arrays of the reference's plug-in ABI (skippable_t, lib.pxd:120): strand (1 / 255), type, frame of the
+// window [mn, i]; element 0 = node mn
+__global__ void k_skippable_plugin(const uint8_t *__restrict__ strand, const uint8_t *__restrict__ type,
+                                   const uint8_t *__restrict__ frame, int cnt, uint8_t *__restrict__ skip) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;   // relative to mn; the target is element cnt
+    if (j >= cnt) return;
+    const int k1 = 2 * (strand[j] != 1) + (type[j] == 3), k2 = 2 * (strand[cnt] != 1) + (type[cnt] == 3);
+    const bool same_frame = frame[j] == frame[cnt];
+    bool ok;
+    switch (k2) {
+    case K_FS: ok = (k1 == K_FE || k1 == K_RS); break;
+    case K_FE: ok = ((k1 == K_FS && same_frame) || k1 == K_FE); break;
+    case K_RS: ok = ((k1 == K_RE && same_frame) || k1 == K_FE); break;
+    default: ok = (k1 == K_FE || k1 == K_RS || k1 == K_RE); break;
+    }
+    skip[j] = ok ? 0 : 1;
+}
+
 // --------------------------------------------------------------------------------------------------
 // launch wrappers
 // --------------------------------------------------------------------------------------------------
@@ -1798,6 +1816,10 @@ void launch_build_final_chains(const DevBatch &B, int n_contigs, const int32_t *
 void launch_skippable(int n, const int8_t *strand, const uint8_t *type, const int32_t *ndx, int mn, int i, uint8_t *skip,
                       cudaStream_t st) {
     if (i > mn) k_skippable<<<(i - mn + 127) / 128, 128, 0, st>>>(n, strand, type, ndx, mn, i, skip);
+}
+void launch_skippable_plugin(const uint8_t *strand, const uint8_t *type, const uint8_t *frame, int cnt, uint8_t *skip,
+                             cudaStream_t st) {
+    if (cnt > 0) k_skippable_plugin<<<(cnt + 127) / 128, 128, 0, st>>>(strand, type, frame, cnt, skip);
 }
 
 }  // namespace pgpu

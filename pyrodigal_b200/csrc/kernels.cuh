@@ -62,6 +62,8 @@ void launch_pack_gene_nodes(int n_contigs, const pgpu_contig_summary *summary, c
                             const pgpu_node *nodes, pgpu_node *out, pgpu_gene *genes_out, cudaStream_t st);
 void launch_skippable(int n, const int8_t *strand, const uint8_t *type, const int32_t *ndx, int mn, int i,
                       uint8_t *skip, cudaStream_t st);
+void launch_skippable_plugin(const uint8_t *strand, const uint8_t *type, const uint8_t *frame, int cnt, uint8_t *skip,
+                             cudaStream_t st);
 void launch_build_final_chains(const DevBatch &B, int n_contigs, const int32_t *winner_chain, const int64_t *fin_coff,
                                ChainInfo *fin_chains, cudaStream_t st);
 

@@ -60,6 +60,8 @@ test_score_nodes = G.test_score_nodes
 test_score_connections_golden = G.test_score_connections_golden
 test_training_dp_vs_oracle = G.test_training_dp_vs_oracle
 test_compute_skippable = G.test_compute_skippable
+test_skippable_plugin_signature = G.test_skippable_plugin_signature
+test_result_nodes_in_reference_struct_layout = G.test_result_nodes_in_reference_struct_layout
 test_find_genes_meta_golden = G.test_find_genes_meta_golden
 test_find_genes_single_golden = G.test_find_genes_single_golden
 test_find_genes_batch_vs_oracle = G.test_find_genes_batch_vs_oracle

@@ -184,6 +184,37 @@ def test_compute_skippable(ctx, name):
     assert checked > 0
 
 
+def test_skippable_plugin_signature(ctx, capi):
+    """pgpu_skippable(strands, types, frames, min, i, skip) -- the reference's skippable_t (lib.pxd:120) -- gives what the
+    operator gives, writes [min, i) only"""
+    a = DP[list(DP["names"])[0] + "/in"]
+    n = len(a)
+    strands = a["strand"].astype(np.int8).view(np.uint8)     # 1 / 255, as BaseConnectionScorer._index stores them
+    frames = (a["ndx"] % 3).astype(np.uint8)
+    for i, mn in ((n - 1, max(0, n - 1 - 500)), (n // 2, max(0, n // 2 - 1000)), (5, 0), (1, 0)):
+        got = capi.skippable_plugin(strands, a["type"], frames, mn, i)
+        want = ctx.compute_skippable(a["strand"], a["type"], a["ndx"], mn, i)
+        cmp_int(got[mn:i], want[mn:i], f"skippable_plugin[i={i}]")
+        assert (got[:mn] == 0xAA).all() and (got[i:] == 0xAA).all()
+
+
+def test_result_nodes_in_reference_struct_layout(ctx, capi):
+    """pgpu_result_nodes_struct: the final nodes as 128-byte `struct _node` records (node.h:41-76) == the pgpu_node records"""
+    seqs = [R.synth(9000, .45, 31), R.synth(4000, .62, 32)]
+    res = run_meta(ctx, capi, seqs)
+    for k in range(len(seqs)):
+        a, b = res.nodes(k), res.nodes_struct(k)
+        assert len(a) == len(b) > 0 and b.dtype.itemsize == 128
+        for f in ("ndx", "stop_val", "traceb", "tracef", "star_ptr", "strand", "type", "edge", "elim", "ov_mark", "rbs",
+                  "gc_cont", "mot_score", "cscore", "uscore", "tscore", "rscore", "sscore", "score"):
+            assert np.array_equal(a[f], b[f]), f
+        bits = b["mot_bits"]
+        assert np.array_equal(bits & 0xfff, a["mot_ndx"]) and np.array_equal((bits >> 12) & 0xf, a["mot_spacer"])
+        assert np.array_equal((bits >> 16) & 0x7, a["mot_len"]) and np.array_equal((bits >> 19) & 0x3, a["mot_spacendx"])
+        assert not b["gc_score"].any() and not b["gc_bias"].any()
+    res.free()
+
+
 # ---------------------------------------------------------------------------------------------------
 # find_genes
 # ---------------------------------------------------------------------------------------------------
