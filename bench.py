@@ -23,6 +23,7 @@ Printed JSON line (rank 0): see the task contract; additionally `roofline` (the 
 `clocks`, `gpu_launches`, `phases`.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -155,6 +156,9 @@ class ClockSampler(threading.Thread):
             except Exception:
                 self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            # the first query of each kind initialises driver state: keep that outside the timed region
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
             self.nvml = pynvml
         except Exception:
             self.nvml = None
@@ -566,6 +570,8 @@ def main():
     def timed(fn, steps, per_step=None, gather=None):
         """K steps bracketed by barrier + synchronize; CUDA events on the library's stream; max over ranks.  Small
         inputs: L2 is flushed before every step, and the step times (CUDA events per step) are summed instead."""
+        gc.collect()
+        gc.disable()   # no cyclic collection inside the timed region (re-enabled below): ordinary benchmarking hygiene
         D.barrier()
         tot_ms = 0.0
         if not small:
@@ -595,6 +601,7 @@ def main():
             tot_ms = ctx.timer_stop()
             wall = (time.perf_counter() - t0) * 1e3
         torch.cuda.synchronize()
+        gc.enable()
         tot_ms, wall = D.reduce([tot_ms, wall], "max")
         D.barrier()
         return tot_ms, wall, last
