@@ -487,7 +487,7 @@ static void plan_coding_smem(pgpu_ctx *ctx, DevPool &pool, DevBatch &B, int tota
             }
             bound += exts[t.ext].nn / 2;
         }
-        pext.push_back(-1); pcls.push_back((uint8_t)k); phs0.push_back(0);
+        pext.push_back(-1); pcls.push_back((uint8_t)k); phs0.push_back(-1);
         for (int q = 0; q < 4; q++) { pchain.push_back(-1); pcbase.push_back(INT64_MIN); }
         max_cta += (bound + span - 1) / span;
     }

@@ -218,7 +218,7 @@ struct DevBatch {
     const int32_t *cq_chain;   // [4 * r + k]: chain of lane k, or -1
     const int64_t *cq_cbase;   // [4 * r + k]: chain-node offset of lane k's chain minus the extraction's node offset
                                //   (cscore[cq_cbase + batch node index]), INT64_MIN = no chain
-    const int32_t *cq_hs0;     // first ORF descriptor of entry r's extraction
+    const int32_t *cq_hs0;     // first ORF descriptor of entry r's extraction (-1: padding entry)
     const int32_t *cq_colmodel;// model on table column c
     int32_t *cq_soff;          // [n_ent + 1], device
     int32_t *cq_cta;           // [max CTAs + 1], device: plan entry that holds the first slot of every CTA span

@@ -621,8 +621,9 @@ __global__ void __launch_bounds__(kCqThreads, 1) k_coding_flat(DevBatch B, const
         if (slot >= span) return;
         const int gs = slot0 + slot;
         while (r < r1 && B.cq_soff[r + 1] <= gs) r++;   // slots are drawn in increasing order
-        if (B.cq_ext[r] < 0) return;                     // class padding: nothing behind it in this span
-        D1 = B.orfd[B.cq_hs0[r] + (gs - B.cq_soff[r])];
+        const int hs0 = B.cq_hs0[r];
+        if (hs0 < 0) return;                             // class padding: nothing behind it in this span
+        D1 = B.orfd[hs0 + (gs - B.cq_soff[r])];
         D1r = r;
     };
     draw();
@@ -649,19 +650,36 @@ __global__ void __launch_bounds__(kCqThreads, 1) k_coding_flat(DevBatch B, const
                     // the ORF is finished: the two penalty sweeps, fused, from the last start back to the stop
                     double s2 = -10000.0, s3 = -10000.0;
                     const bool active = cb != INT64_MIN;
-                    for (int i = seg, j = cnt - 1; i != zstop; j--) {
-                        const int4 L = link[i];
-                        double cs = j < kCqRing ? ring[j * kCqThreads] : (active ? cscore[cb + i] : 0.0);
+                    // one start: cs = its sum, L = its link record (L.w = gene length - 3, L.z = the start before it).
+                    // gsize = (L.w + 3) / 3.0 of coding_orf_lane: its integer part and the comparison with 1000 in integer
+                    // arithmetic (exact: L.w + 3 < 2^31), the division only for genes above 3 kbp; fmax(fmin(d, lfac), 0)
+                    // as two comparisons (the weights are finite: same value, and subtracting +-0 changes nothing)
+                    auto sweep = [&](int i, double cs, const int4 &L) {
                         if (cs > s2) s2 = cs; else cs -= (s2 - cs);
-                        // gsize = (L.w + 3) / 3.0 of coding_orf_lane: its integer part and the comparison with 1000 in
-                        // integer arithmetic (exact: L.w + 3 < 2^31), the division only for genes above 3 kbp
                         double lfac;
                         if (L.w + 3 > 3000) lfac = M.lfac_span * (((double)L.w + 3.0) / 3.0 - 80) / 920.0;
                         else lfac = M.lfac[(unsigned)(L.w + 3) / 3u];
-                        if (lfac > s3) s3 = lfac; else lfac -= fmax(fmin(s3 - lfac, lfac), 0.0);
+                        if (lfac > s3) {
+                            s3 = lfac;
+                        } else {
+                            const double d = s3 - lfac, m = d < lfac ? d : lfac;
+                            if (m > 0.0) lfac -= m;
+                        }
                         if (lfac > 3.0 && cs < 0.5 * lfac) cs = 0.5 * lfac;
                         cs += lfac;
                         if (active) cscore[cb + i] = cs;
+                    };
+                    int i = seg, j = cnt - 1;
+#pragma unroll 1
+                    for (; j >= kCqRing; j--) {   // (an ORF with more than kCqRing starts: the sums beyond are in global memory)
+                        const int4 L = link[i];
+                        sweep(i, active ? cscore[cb + i] : 0.0, L);
+                        i = L.z;
+                    }
+#pragma unroll 1
+                    for (; j >= 0; j--) {
+                        const int4 L = link[i];
+                        sweep(i, ring[j * kCqThreads], L);
                         i = L.z;
                     }
                     seg = -1;
@@ -1321,8 +1339,8 @@ void launch_coding(const DevBatch &B, const DevModel *models, int n_chains, int6
 #ifdef PGPU_HOST_EMULATION
         k_coding_flat<<<(unsigned)B.cq_max_cta, kCqThreads, 0, st>>>(B, models);
 #else
-        static const cudaError_t attr = cudaFuncSetAttribute(k_coding_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, kCqSmemBytes);
-        (void)attr;
+        // (per device: set before every launch, a process may drive several devices)
+        cudaFuncSetAttribute(k_coding_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, kCqSmemBytes);
         k_coding_flat<<<(unsigned)B.cq_max_cta, kCqThreads, kCqSmemBytes, st>>>(B, models);
 #endif
     } else if (B.ext_chains && B.dcT && n_ext > 0 && total_nodes > 0) {
