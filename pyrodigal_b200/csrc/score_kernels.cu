@@ -712,19 +712,22 @@ __global__ void __launch_bounds__(kCqThreads, 1) k_coding_flat(DevBatch B, const
                 if (base >= 8) vn = *reinterpret_cast<const uint4 *>(dic + base - 8);   // needed unless the ORF ends in this chunk
             }
             const int hi_t = k_cur - base, lo_t = max(lo - base, 0);
-            // (indices are masked: elements outside [lo_t, hi_t] may be anything, their weights are loaded and dropped)
-            const double w7 = wcol[((v.w >> 16) & 0xfffu) * kCqCols], w6 = wcol[(v.w & 0xfffu) * kCqCols];
-            const double w5 = wcol[((v.z >> 16) & 0xfffu) * kCqCols], w4 = wcol[(v.z & 0xfffu) * kCqCols];
-            const double w3 = wcol[((v.y >> 16) & 0xfffu) * kCqCols], w2 = wcol[(v.y & 0xfffu) * kCqCols];
-            const double w1 = wcol[((v.x >> 16) & 0xfffu) * kCqCols], w0 = wcol[(v.x & 0xfffu) * kCqCols];
-            if (hi_t >= 7 && lo_t <= 7) acc += w7;
-            if (hi_t >= 6 && lo_t <= 6) acc += w6;
-            if (hi_t >= 5 && lo_t <= 5) acc += w5;
-            if (hi_t >= 4 && lo_t <= 4) acc += w4;
-            if (hi_t >= 3 && lo_t <= 3) acc += w3;
-            if (hi_t >= 2 && lo_t <= 2) acc += w2;
-            if (hi_t >= 1 && lo_t <= 1) acc += w1;
-            if (lo_t <= 0) acc += w0;
+            // elements lo_t .. hi_t of the chunk are added; every element of a plane is a valid index (k_dicodon_index
+            // fills the slack), so all eight weights are loaded and the others dropped.  Byte offset of a weight = index * 32.
+            const char *__restrict__ wb = reinterpret_cast<const char *>(wcol);
+            const double w7 = *reinterpret_cast<const double *>(wb + ((v.w >> 16) << 5)), w6 = *reinterpret_cast<const double *>(wb + ((v.w & 0xffffu) << 5));
+            const double w5 = *reinterpret_cast<const double *>(wb + ((v.z >> 16) << 5)), w4 = *reinterpret_cast<const double *>(wb + ((v.z & 0xffffu) << 5));
+            const double w3 = *reinterpret_cast<const double *>(wb + ((v.y >> 16) << 5)), w2 = *reinterpret_cast<const double *>(wb + ((v.y & 0xffffu) << 5));
+            const double w1 = *reinterpret_cast<const double *>(wb + ((v.x >> 16) << 5)), w0 = *reinterpret_cast<const double *>(wb + ((v.x & 0xffffu) << 5));
+            const unsigned take = ((2u << hi_t) - 1u) & ~((1u << lo_t) - 1u);   // bit t: element t is added
+            if (take & 0x80u) acc += w7;
+            if (take & 0x40u) acc += w6;
+            if (take & 0x20u) acc += w5;
+            if (take & 0x10u) acc += w4;
+            if (take & 0x08u) acc += w3;
+            if (take & 0x04u) acc += w2;
+            if (take & 0x02u) acc += w1;
+            if (take & 0x01u) acc += w0;
             k_cur = base + lo_t - 1;
         }
     }

@@ -113,10 +113,18 @@ __global__ void __launch_bounds__(256) k_dicodon_index(DevBatch B, const int2 *_
     for (int t = threadIdx.x; t < 3 * kPer; t += 256) {
         const int f = t / kPer, k = k0 + t % kPer;
         const int p = 3 * k + f;
-        if (p >= ci.slen) continue;
+        if (p >= ci.slen) {   // slack of the plane: a valid index (k_coding_flat reads whole 16-byte chunks and looks every
+            if (k < P) { df[f * P + k] = 0; dr[f * P + (P - 1 - k)] = 0; }   // element up, also the ones it does not add)
+            continue;
+        }
         df[f * P + k] = (uint16_t)((cod[p] & 63) | ((cod[p + 3] & 63) << 6));     // cod is zero padded past the end
         dr[f * P + (P - 1 - k)] = p >= 5 ? (uint16_t)(rev_codon_at(d, cod, p) | (rev_codon_at(d, cod, p - 3) << 6)) : (uint16_t)0;
     }
+    if (tile.y + kTile >= ci.slen)   // last tile of the contig: the slack behind its elements
+        for (int t = threadIdx.x; t < 3 * 32; t += 256) {
+            const int f = t / 32, k = k0 + kPer + t % 32;
+            if (k < P) { df[f * P + k] = 0; dr[f * P + (P - 1 - k)] = 0; }
+        }
 }
 
 // runs of N: one thread per run start walks to the end of its run (lib.pyx:699-713)
