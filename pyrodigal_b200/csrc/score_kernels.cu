@@ -1034,13 +1034,18 @@ __global__ void __launch_bounds__(128, MINB) k_start_score_lean(DevBatch B, cons
     if (g >= total) return;
     while (k + 1 < n_chains && B.chains[k + 1].coff <= g) k++;
     const ChainInfo C = B.chains[k];
-    const int i = (int)(g - C.coff);
-    if (i >= C.nn) return;
+    // Only starts are scored: the first (#starts) threads of the chain's index range take one start each through the
+    // class-sorted node list (+starts, then -starts), so that a warp is either full of starts or exits at once (a
+    // quarter of the nodes are STOP nodes; thread per node left 20 of 32 lanes busy).
+    const int t = (int)(g - C.coff);
+    const int32_t *__restrict__ cbase = B.cbase + 4 * C.ext;
+    const int n_fs = cbase[1] - cbase[0], n_rs = cbase[3] - cbase[2];
+    if (t >= n_fs + n_rs) return;
+    const int i = (B.clist + C.node_off)[t < n_fs ? cbase[0] + t : cbase[2] + (t - n_fs)];
     StartNode N;
     N.c = B.cls[C.node_off + i];
-    if (cls_is_stop(N.c)) return;
     load_start_node(B, C.node_off, C.doff, C.nn, i, N);
-    start_score_eval<true>(B, models, C, N, g, i, B.cscore, g, o, nullptr);
+    start_score_eval<true>(B, models, C, N, C.coff + i, i, B.cscore, C.coff + i, o, nullptr);
 }
 
 __global__ void __launch_bounds__(128) k_start_score(DevBatch B, const DevModel *__restrict__ models, int n_chains,
