@@ -659,8 +659,14 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
 
     tr("sync1 done (gc counts)");
     // ---- stage B: plan extractions and chains ------------------------------------------------------
-    std::vector<ExtractInfo> exts;
-    std::vector<ChainInfo> chains;
+    // (per-thread scratch: a 630 Mbp sub-batch plans 185 k chains = 15 MB, and fresh vectors would be page-faulted in on
+    // every call while the GPU waits for this loop)
+    static thread_local std::vector<ExtractInfo> tl_exts;
+    static thread_local std::vector<ChainInfo> tl_chains;
+    std::vector<ExtractInfo> &exts = tl_exts;
+    std::vector<ChainInfo> &chains = tl_chains;
+    exts.clear();
+    chains.clear();
     std::vector<int32_t> contig_chain_begin(n + 1, 0);
     std::vector<int32_t> contig_ext_begin(n + 1, 0);
     int64_t nwords = 0;
@@ -712,11 +718,12 @@ static int run_range(pgpu_ctx *ctx, const uint8_t *h_seq, const uint8_t *d_seq, 
             return (int)exts.size() - 1;
         };
         auto add_chain = [&](int model, int tt, int first_pass, int is_meta) {
-            ChainInfo K;
+            const int e = get_ext(tt);
+            chains.emplace_back();   // filled in place: this loop runs while the GPU waits for the plan
+            ChainInfo &K = chains.back();
             memset(&K, 0, sizeof(K));
-            K.ext = get_ext(tt); K.model = model; K.contig = c; K.first_pass = first_pass;
+            K.ext = e; K.model = model; K.contig = c; K.first_pass = first_pass;
             K.doff = ci.doff; K.slen = ci.slen; K.is_meta = is_meta;
-            chains.push_back(K);
         };
         if (plan.forced_tt >= 0) {
             get_ext(plan.forced_tt);
