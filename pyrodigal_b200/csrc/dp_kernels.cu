@@ -1306,7 +1306,7 @@ __device__ __forceinline__ double igm_nodes(const NodeRef &N, int a, int b, cons
         if (N.uscore[s] < 0) r -= N.uscore[s];
     }
     if (dist > 3 * kOperDist) r -= 0.15 * M.st_wt;
-    else if ((dist <= kOperDist && !overlap) || dist * 4 < kOperDist) r += (2.0 - ((double)dist / kOperDist)) * 0.15 * M.st_wt;
+    else if ((dist <= kOperDist && !overlap) || dist * 4 < kOperDist) r += M.igt[dist];   // (2.0 - dist / 60) * 0.15 * st_wt, tabulated (no FP64 division)
     return r;
 }
 

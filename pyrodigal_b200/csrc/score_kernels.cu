@@ -389,8 +389,8 @@ __global__ void __launch_bounds__(32 * kOrfWarps, MINB) k_coding_orf(DevBatch B,
         W = B.orf_w[r];
         const int local = (int)(gt - B.orf_toff[r]);
         e = B.orf_ext[r];
-        tl = local / W;
-        lane = local % W;
+        tl = local >> (31 - __clz(W));   // W is a power of two
+        lane = local & (W - 1);
     } else {
         // Work items are the STOP nodes.  A STOP node exists only if its ORF has a start, so an extraction with nn
         // nodes has at most nn / 2 of them: the warps index a half-size slot space in which extraction e owns the
@@ -1124,7 +1124,7 @@ __device__ __forceinline__ double igm_same(int ndx1, int strand1, int ndx2, int 
         }
     }
     if (dist > 3 * kOperDist) r -= 0.15 * M.st_wt;
-    else if ((dist <= kOperDist && !overlap) || dist * 4 < kOperDist) r += (2.0 - ((double)dist / kOperDist)) * 0.15 * M.st_wt;
+    else if ((dist <= kOperDist && !overlap) || dist * 4 < kOperDist) r += M.igt[dist];   // (2.0 - dist / 60) * 0.15 * st_wt, tabulated (no FP64 division)
     return r;
 }
 
@@ -1240,7 +1240,7 @@ __global__ void __launch_bounds__(256, 6) k_overlap_lanes(DevBatch B, const DevM
     const int W = B.orf_w[r];
     const int local = (int)(gt - B.orf_toff[r]);
     const int e = B.orf_ext[r];
-    const int tl = local / W, lane = local % W;
+    const int tl = local >> (31 - __clz(W)), lane = local & (W - 1);   // W is a power of two
     const int32_t *__restrict__ cbase = B.cbase + 4 * e;
     const ExtractInfo &X = B.exts[e];
     const int nn = X.nn;
