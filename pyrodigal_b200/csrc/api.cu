@@ -334,6 +334,7 @@ static void prepare_model(const RawTraining &r, DevModel &m, const RawTraining *
                 }
                 m.sd_best[x][off][gp] = (uint8_t)best;
             }
+    for (int L = 0; L < 250; L++) { m.len_neg[L] = 250.0 / (float)L; m.len_pos[L] = (float)L / 250.0; }
     m.gene_dc = d_raw_k->gene_dc;
     m.mot_wt = &d_raw_k->mot_wt[0][0][0];
     m.mot_live = d_live_k;

@@ -60,6 +60,8 @@ struct DevModel {
                                    // what all but a few dozen cells of a trained model hold); nullptr = always load
     uint64_t mot_pf[4];            // per motif length: bit (index & 63) set when any cell [len][*][index] is live; a
                                    // register-only pre-filter in front of mot_live (exactness never depends on it)
+    double len_neg[250], len_pos[250];   // 250.0 / L and L / 250.0 for ORF lengths L < 250 (lib.pyx:2436-2440): the two FP64
+                                   // divisions of every short-ORF start, tabulated (IEEE division: host == device)
     const uint16_t *mot_hit;       // [4096] by six upstream bases: which motifs (length, offset in the window) may be live
                                    // (api.cu: motif_live_bits); with it the search only visits candidate windows
     int32_t col;                   // column of this model in the transposed dicodon table (sorted by tt, gc)

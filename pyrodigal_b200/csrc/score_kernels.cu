@@ -970,7 +970,7 @@ __device__ __forceinline__ void start_score_eval(const DevBatch &B, const DevMod
     }
     if (!edge && edge_gene == 1) uscore -= 0.5 * PGPU_EDGE_BONUS * st_wt;
     if (edge_gene == 0 && orf_length < 250) {
-        const double negf = 250.0 / (float)orf_length, posf = (float)orf_length / 250.0;
+        const double negf = M.len_neg[orf_length], posf = M.len_pos[orf_length];   // 250.0 / L, L / 250.0
         rscore *= rscore < 0 ? negf : posf;
         uscore *= uscore < 0 ? negf : posf;
         tscore *= tscore < 0 ? negf : posf;
@@ -1373,7 +1373,7 @@ void launch_start_score(const DevBatch &B, const DevModel *models, int n_chains,
 }
 void launch_start_score_lean(const DevBatch &B, const DevModel *models, int n_chains, int64_t total, RunOpts o, cudaStream_t st) {
     if (n_chains == 0 || total == 0) return;
-    static const int minb = getenv("PGPU_SCORE_MINB") ? atoi(getenv("PGPU_SCORE_MINB")) : 10;   // 10 = 48 registers, 40 warps / SM (measured: 17.6 ms vs 18.1 at 9, 18.6 at 12)
+    static const int minb = getenv("PGPU_SCORE_MINB") ? atoi(getenv("PGPU_SCORE_MINB")) : 9;   // 9 = 56 registers, no spills, 36 warps / SM; 10 = 48 registers (a few spilled words), 40 warps / SM: measured equal (32.5 vs 32.2 ms scoring phase)
     const unsigned nb = (unsigned)((total + 127) / 128);
     if (minb == 12) k_start_score_lean<12><<<nb, 128, 0, st>>>(B, models, n_chains, total, o);
     else if (minb == 10) k_start_score_lean<10><<<nb, 128, 0, st>>>(B, models, n_chains, total, o);
