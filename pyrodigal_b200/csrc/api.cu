@@ -332,7 +332,7 @@ static void prepare_model(const RawTraining &r, DevModel &m, const RawTraining *
                     if (r.rbs_wt[v] == r.rbs_wt[best] && v < best) continue;
                     best = v;
                 }
-                m.sd_best[x][off][gp] = (uint8_t)best;
+                m.sd_best[off][gp][x] = (uint8_t)best;
             }
     for (int L = 0; L < 250; L++) { m.len_neg[L] = 250.0 / (float)L; m.len_pos[L] = (float)L / 250.0; }
     m.gene_dc = d_raw_k->gene_dc;

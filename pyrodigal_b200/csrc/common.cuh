@@ -53,7 +53,7 @@ struct DevModel {
     double ig_neg;         // -0.15 * st_wt                            (_connection.h:48,72)
     int32_t trans_table, uses_sd;
     uint64_t stopmask, startmask;  // bit c: codon code c is a stop / start in trans_table
-    uint8_t sd_best[2][15][64];    // best SD bin for (exact|mismatch, offset, 6-bit match pattern)
+    uint8_t sd_best[15][64][2];    // best SD bin for (offset, 6-bit match pattern, exact | mismatch): the pair is one 2-byte load
     const double *gene_dc;         // device pointers into the raw blob
     const double *mot_wt;
     const uint32_t *mot_live;      // bitmap over the 4*4*4096 motif cells: weight != -4.0 (the clamped floor, which is

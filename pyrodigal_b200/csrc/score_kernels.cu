@@ -804,7 +804,8 @@ __device__ __forceinline__ void start_score_eval(const DevBatch &B, const DevMod
             const int omin = rev ? 0 : max(0, 20 - start);  // forward skips negative offsets only
             for (int off = omin; off < 15; off++) {
                 const uint32_t gp = ((A >> off) & 0x09u) | ((G >> off) & 0x36u);
-                int e = M.sd_best[0][off][gp], m = M.sd_best[1][off][gp];
+                const uint32_t em = *reinterpret_cast<const uint16_t *>(&M.sd_best[off][gp][0]);   // exact | mismatch << 8
+                const int e = em & 0xff, m = em >> 8;
                 rbs0 = max(rbs0, e);
                 rbs1 = max(rbs1, m);
             }
