@@ -359,6 +359,7 @@ __device__ __forceinline__ void wc_merge(WCand &a, double v, int j, int fr) {
 // The warp arg-max uses redux.sync on an order-preserving integer image of the doubles.
 // --------------------------------------------------------------------------------------------------
 constexpr int kDqCap = 64;
+constexpr int kDqRing = 128;   // merged-stream entries kept in shared memory per chain (power of two)
 
 struct DqK {  // per-target constants, staged 32 targets at a time
     int32_t ndx, sv, cls, leave;
@@ -396,6 +397,10 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
     __shared__ DqK s_k[kFastWarps][32];
     __shared__ double s_dqv[kFastWarps][kDqCap];
     __shared__ int32_t s_dqj[kFastWarps][kDqCap];
+    // the most recent merged-stream entries (source value, traceback node) of the chain: what a step reads from within
+    // 200 bp was written a few steps ago -- from shared memory instead of an L2 round trip (a single chain is pure latency)
+    __shared__ double s_rsv[MINB == 4 ? kFastWarps : 1][MINB == 4 ? kDqRing : 1];
+    __shared__ int32_t s_rtb[MINB == 4 ? kFastWarps : 1][MINB == 4 ? kDqRing : 1];
     const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
     const int slot = blockIdx.x * kFastWarps + wslot;
     if (slot >= n_chains) return;
@@ -428,12 +433,21 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
     DqK *sk = s_k[wslot];
     double *dqv = s_dqv[wslot];
     int32_t *dqj = s_dqj[wslot];
+    double *rsv = s_rsv[MINB == 4 ? wslot : 0];
+    int32_t *rtb = s_rtb[MINB == 4 ? wslot : 0];
     const double ig_neg = FINAL ? M.ig_neg : 0.0;   // training DP: every intergenic connection scores 0
     const double *__restrict__ gcb = FINAL ? nullptr : B.gcb + C.coff;   // training DP: bias . gc_score of a start
 
     // merged-stream cursors: cur = finalized entries, lo = first entry inside [i-1000, i), far = first entry
     // that is NOT more than 180 bp behind the target
     int cur = 0, lo = 0, far = 0;
+    // entry q: from the ring while it is among the last kDqRing - 1 entries (slot q & mask is not reused before entry
+    // q + kDqRing is written, and entries are written in order: index <= cur)
+    // (only in the instantiation for few chains, MINB == 4: with thousands of chains the kernel is throughput bound and
+    // the 64-register instantiation has no room for it)
+    constexpr bool kRing = MINB == 4;
+    auto SV = [&](int q) -> double { return kRing && cur - q < kDqRing ? rsv[q & (kDqRing - 1)] : svig[q]; };
+    auto TB = [&](int q) -> int { return kRing && cur - q < kDqRing ? rtb[q & (kDqRing - 1)] : tbig[q]; };
     int dq_head = 0, dq_cnt = 0;
     bool dq_ok = true;
     double rc_v0 = kNeg, rc_v1 = kNeg, rc_v2 = kNeg;
@@ -455,14 +469,14 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
             for (int q = max(P.y, P.w); q < min(P.z, pend_q); q++) {  // +STOPs overlapping the 3' end
                 const int nd = ig_node[q];
                 if (nd >= 0) continue;
-                const double s = svig[q];
+                const double s = SV(q);
                 if (s == kNeg) continue;
                 const int nj = ig_ndx[q];
                 if (P.sv - 2 >= nj + 2) continue;
                 const int ovlp = (nj + 2) - (P.sv - 2) + 1;
                 if (ovlp >= kMaxOppOvlp) continue;
                 if ((nj - P.sv) >= (P.ndx - nj + 3)) continue;
-                if ((nj - P.sv) >= (P.sv - 3 - ndx[tbig[q]])) continue;
+                if ((nj - P.sv) >= (P.sv - 3 - ndx[TB(q)])) continue;
                 const double v = s + (FINAL ? cs_diff : ((double)(P.ndx - (P.sv - 2) + 1 - ovlp * 2)) * P.cs);
                 const int j = nd & 0x7fffffff;
                 if (v > bv || (v == bv && j > bj)) { bv = v; bj = j; }
@@ -472,6 +486,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
             if (bj >= 0 && bv >= 0.0) { sc = bv; tb = bj; }
             score[pend_i] = sc; traceb[pend_i] = tb; ov_mark[pend_i] = -1;
             svig[pend_q] = tb == -1 ? kNeg : sc;
+            if (kRing) rsv[pend_q & (kDqRing - 1)] = tb == -1 ? kNeg : sc;   // (a -start entry has no traceback record)
         }
         pend_cnt = 0;
         __syncwarp();
@@ -528,7 +543,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
                 const int q = far + lane;
                 const bool in = q < cur;
                 const int nq = in ? ig_ndx[q] : 0x7fffffff;
-                const double sq = in ? svig[q] : kNeg;
+                const double sq = in ? SV(q) : kNeg;
                 const int jq = in ? (ig_node[q] & 0x7fffffff) : 0;
                 const int c = __popc(__ballot_sync(0xffffffffu, nq < thr));  // ndx sorted: a prefix of the lanes
                 for (int t = 0; t < c; t++) {
@@ -565,14 +580,14 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
             }
             if (far_scan && (FINAL || kind == K_FS)) {
                 for (int q = lo + lane; q < flo; q += 32) {
-                    const double s = svig[q];
+                    const double s = SV(q);
                     if (s != kNeg) cand(s + ig_neg, ig_node[q] & 0x7fffffff, -1);
                 }
             }
             if (kind == K_FS) {
                 // near sources (_connection.h:116-129): +STOP distance-dependent term, -start strand switch
                 for (int q = flo + lane; q < cur; q += 32) {
-                    const double s = svig[q];
+                    const double s = SV(q);
                     if (s == kNeg) continue;
                     const int nd = ig_node[q], nj = ig_ndx[q];
                     if (nd < 0) {
@@ -598,7 +613,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
                         ovlp = left - n3s + 3;
                         if (ovlp <= 0 || ovlp >= kMaxOppOvlp) return;
                         if (ovlp >= n3n - left) return;
-                        if (tj == kTbNone) tj = ndx[tbig[q]];
+                        if (tj == kTbNone) tj = ndx[TB(q)];
                         if (ovlp >= n3s - tj - 2) return;
                         if (FINAL ? (op > maxval) : (g > maxval)) { maxfr = k; maxval = op; maxg = g; }
                     };
@@ -609,7 +624,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
                     else cand(s + ((double)(right - left + 1 - ovlp * 2)) * (maxfr != -1 ? maxg : 0.0), nd & 0x7fffffff, maxfr);
                 };
                 for (int q = flo + lane; q < cur; q += 32) {
-                    const double s = svig[q];
+                    const double s = SV(q);
                     if (s == kNeg) continue;
                     const int nd = ig_node[q], nj = ig_ndx[q];
                     if (nd < 0) {
@@ -622,7 +637,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
                 }
                 if (!FINAL && far_scan) {   // every far source, exactly
                     for (int q = lo + lane; q < flo; q += 32) {
-                        const double s = svig[q];
+                        const double s = SV(q);
                         if (s == kNeg) continue;
                         const int nd = ig_node[q];
                         if (nd < 0) eval_fe(q, s, ig_ndx[q], nd); else cand(s + ig_neg, nd, -1);
@@ -639,7 +654,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
                     while (a_ < b_) { const int mid = (a_ + b_) >> 1; if (ig_ndx[mid] < n3s + 195) a_ = mid + 1; else b_ = mid; }
                     for (int q = a + lane; q < a_; q += 32) {
                         const int nd = ig_node[q];
-                        const double s = svig[q];
+                        const double s = SV(q);
                         if (nd < 0 && s != kNeg) eval_fe(q, s, ig_ndx[q], nd);
                     }
                 };
@@ -667,7 +682,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
             for (int q = max(K.x, K.w) + lane; q < cur; q += 32) {
                 const int nd = ig_node[q];
                 if (nd >= 0) continue;
-                const double s = svig[q];
+                const double s = SV(q);
                 if (s == kNeg) continue;
                 const int j = nd & 0x7fffffff;
                 const int sp = star_ptr[S3 * (int64_t)j + f2];
@@ -695,6 +710,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
             if (kind == K_FE) {
                 svig[cur] = tb_i == -1 ? kNeg : sc_i;  // edge-artifact rule: nothing leads into it
                 tbig[cur] = tb_i;
+                if (kRing) { rsv[cur & (kDqRing - 1)] = tb_i == -1 ? kNeg : sc_i; rtb[cur & (kDqRing - 1)] = tb_i; }
             }
         }
         if (kind == K_FE) {
