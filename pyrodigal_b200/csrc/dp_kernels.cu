@@ -451,6 +451,16 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
     int dq_head = 0, dq_cnt = 0;
     bool dq_ok = true;
     double rc_v0 = kNeg, rc_v1 = kNeg, rc_v2 = kNeg;
+    // score of the last -STOP of every frame: a reverse gene's own stop and the operon predecessors of a -STOP are that
+    // node (no in-frame stop lies inside an ORF), so their score is at hand instead of a global read of what lane 0 stored;
+    // any other node falls back to the array
+    double re_v0 = 0.0, re_v1 = 0.0, re_v2 = 0.0;
+    int re_j0 = -1, re_j1 = -1, re_j2 = -1;
+    constexpr bool kFew = MINB == 4;   // (the instantiation for few chains; the 64-register one has no room for this)
+    auto SC = [&](int j) -> double {
+        if (!kFew) return score[j];
+        return j == re_j0 ? re_v0 : (j == re_j1 ? re_v1 : (j == re_j2 ? re_v2 : score[j]));
+    };
     int rc_j0 = -1, rc_j1 = -1, rc_j2 = -1;
     // -start nodes depend only on STOP nodes (their own -STOP, +STOPs around a 3' overlap): they are parked and
     // evaluated lane-parallel just before the next target that reads them (a +start or -STOP) or at the end of
@@ -462,7 +472,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
             double bv = kNeg;
             int bj = -1;
             if (P.x >= P.pad && P.x >= 0 && P.x < pend_i) {   // own -STOP (gene)
-                bv = score[P.x] + (FINAL ? P.cs : ((double)(P.ndx - (ndx[P.x] - 2) + 1)) * P.cs);
+                bv = SC(P.x) + (FINAL ? P.cs : ((double)(P.ndx - (ndx[P.x] - 2) + 1)) * P.cs);
                 bj = P.x;
             }
             const double cs_diff = P.cs + ig_neg;
@@ -669,7 +679,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
                     const int n3l = lane == 0 ? K.n3n0 : (lane == 1 ? K.n3n1 : K.n3n2);
                     const double gl = lane == 0 ? K.g0 : (lane == 1 ? K.g1 : K.g2);
                     if (j >= 0 && j >= i - 2 * kMaxNodeDist && spl != -1)
-                        cand(score[j] + (FINAL ? opl : ((double)(n3l - (ndx[j] - 2) + 1)) * gl), j, -1);
+                        cand(SC(j) + (FINAL ? opl : ((double)(n3l - (ndx[j] - 2) + 1)) * gl), j, -1);
                 }
             }
         } else if (kind == K_FE) {
@@ -712,6 +722,9 @@ __global__ void __launch_bounds__(32 * kFastWarps, MINB) k_dp_dq(DevBatch B, con
                 tbig[cur] = tb_i;
                 if (kRing) { rsv[cur & (kDqRing - 1)] = tb_i == -1 ? kNeg : sc_i; rtb[cur & (kDqRing - 1)] = tb_i; }
             }
+        }
+        if (kFew && kind == K_RE) {
+            if (f2 == 0) { re_v0 = sc_i; re_j0 = i; } else if (f2 == 1) { re_v1 = sc_i; re_j1 = i; } else { re_v2 = sc_i; re_j2 = i; }
         }
         if (kind == K_FE) {
             cur++;
