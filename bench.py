@@ -767,6 +767,7 @@ def main():
                                       "ms_d2h", "ms_total_device")}, host_issue_ms=stats["host_ms"]),
             "wall_ms_per_step": wall_ms / args.steps,
             "wall_ms_steps": [round(t["wall_ms"], 1) for t in step_stats],
+            "device_ms_steps": [round(t["ms_total_device"], 1) for t in step_stats],   # kernels only: wall - device = host between the syncs
             "totals": {"bp": int(tot_bp), "genes": int(tot_genes), "dp_steps": int(tot_steps), "pairs": int(tot_pairs),
                        "chains_rank0": int(stats["n_chains"]), "nodes_rank0": int(stats["total_nodes"])},
             "clocks": clocks,
